@@ -1,0 +1,1090 @@
+/*
+ * s4f_oracle.cpp -- CPU restatement of the solids4foam segregated solid-solver hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under solids4foam_b200/ (the product) may include, link,
+ * load or call this file; it is the checker used by tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py.
+ *
+ * PARITY STATUS: "parity unpinned" at the OpenFOAM operator boundary.  The reference
+ * (/root/reference) holds no golden fields or unit tests for this path, and the OpenFOAM library
+ * that implements fvc::grad / fvc::div / fvm::laplacian / lduMatrix / PCG / DIC is neither vendored
+ * nor installed.  The oracle is pinned instead against the closed-form known-answer
+ * tests the reference ships (Kirsch plate-hole, patch test, single-cell law identities, the
+ * neckingBar hardening table) in tests/test_oracle_*.py.
+ *
+ * Style: deliberately the reference's own data layout and loop shapes -- AoS fields, LDU
+ * owner/neighbour face-loop scatter, boundary patches as separate face ranges, one segregated PCG
+ * solve per component -- NOT the cell-centric SoA gather design of the CUDA path.
+ *
+ * Every function cites the reference lines it follows (paths relative to /root/reference;
+ * SM = src/solids4FoamModels/solidModels, ML = src/solids4FoamModels/materialModels/
+ * mechanicalModel/mechanicalLaws, NUM = src/solids4FoamModels/numerics).  "[OF-ext]" marks
+ * behaviour of the OpenFOAM library restated from its published algorithms.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../include/s4fgpu.h"
+
+namespace {
+
+const double SMALL = 1e-15;   // [OF-ext] Foam::SMALL (double)
+const double VSMALL = 1e-300;
+
+typedef std::vector<double> dvec;
+typedef std::vector<int> ivec;
+
+// ---- small tensor algebra (OpenFOAM component orders) ------------------------------------------
+inline void symm(const double* T, double* S) {             // symm(T) = (T+T^T)/2
+    S[0] = T[0]; S[1] = 0.5 * (T[1] + T[3]); S[2] = 0.5 * (T[2] + T[6]);
+    S[3] = T[4]; S[4] = 0.5 * (T[5] + T[7]); S[5] = T[8];
+}
+inline double trS(const double* S) { return S[0] + S[3] + S[5]; }
+inline void devS(const double* S, double* D) {
+    double t = trS(S) / 3.0;
+    D[0] = S[0] - t; D[1] = S[1]; D[2] = S[2]; D[3] = S[3] - t; D[4] = S[4]; D[5] = S[5] - t;
+}
+inline double magSqrS(const double* S) {
+    return S[0] * S[0] + 2 * S[1] * S[1] + 2 * S[2] * S[2] + S[3] * S[3] + 2 * S[4] * S[4] + S[5] * S[5];
+}
+inline double detS(const double* S) {
+    return S[0] * S[3] * S[5] + S[1] * S[4] * S[2] + S[2] * S[1] * S[4]
+         - S[0] * S[4] * S[4] - S[1] * S[1] * S[5] - S[2] * S[3] * S[2];
+}
+inline double detT(const double* T) {
+    return T[0] * (T[4] * T[8] - T[5] * T[7]) - T[1] * (T[3] * T[8] - T[5] * T[6])
+         + T[2] * (T[3] * T[7] - T[4] * T[6]);
+}
+inline void invT(const double* T, double* R) {
+    double d = detT(T);
+    R[0] = (T[4] * T[8] - T[5] * T[7]) / d; R[1] = (T[2] * T[7] - T[1] * T[8]) / d; R[2] = (T[1] * T[5] - T[2] * T[4]) / d;
+    R[3] = (T[5] * T[6] - T[3] * T[8]) / d; R[4] = (T[0] * T[8] - T[2] * T[6]) / d; R[5] = (T[2] * T[3] - T[0] * T[5]) / d;
+    R[6] = (T[3] * T[7] - T[4] * T[6]) / d; R[7] = (T[1] * T[6] - T[0] * T[7]) / d; R[8] = (T[0] * T[4] - T[1] * T[3]) / d;
+}
+inline void invS(const double* S, double* R) {
+    double d = detS(S);
+    R[0] = (S[3] * S[5] - S[4] * S[4]) / d; R[1] = (S[2] * S[4] - S[1] * S[5]) / d; R[2] = (S[1] * S[4] - S[2] * S[3]) / d;
+    R[3] = (S[0] * S[5] - S[2] * S[2]) / d; R[4] = (S[1] * S[2] - S[0] * S[4]) / d; R[5] = (S[0] * S[3] - S[1] * S[1]) / d;
+}
+inline void mulTT(const double* A, const double* B, double* R) {   // A & B
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+        double s = 0; for (int k = 0; k < 3; k++) s += A[3 * i + k] * B[3 * k + j];
+        R[3 * i + j] = s;
+    }
+}
+inline void S2T(const double* S, double* T) {
+    T[0] = S[0]; T[1] = S[1]; T[2] = S[2]; T[3] = S[1]; T[4] = S[3]; T[5] = S[4]; T[6] = S[2]; T[7] = S[4]; T[8] = S[5];
+}
+inline void transposeT(const double* A, double* R) {
+    R[0] = A[0]; R[1] = A[3]; R[2] = A[6]; R[3] = A[1]; R[4] = A[4]; R[5] = A[7]; R[6] = A[2]; R[7] = A[5]; R[8] = A[8];
+}
+inline void SvS(const double* S, const double* v, double* r) {      // S & v
+    r[0] = S[0] * v[0] + S[1] * v[1] + S[2] * v[2];
+    r[1] = S[1] * v[0] + S[3] * v[1] + S[4] * v[2];
+    r[2] = S[2] * v[0] + S[4] * v[1] + S[5] * v[2];
+}
+inline void vT(const double* v, const double* T, double* r) {       // v & T : r_j = v_i T_ij
+    for (int j = 0; j < 3; j++) r[j] = v[0] * T[j] + v[1] * T[3 + j] + v[2] * T[6 + j];
+}
+inline double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+inline double mag3(const double* a) { return std::sqrt(dot3(a, a)); }
+
+// s4f interpolationTable<scalar>::operator(), clamp; NUM/interpolationTable/interpolationTable.C:493-632
+double tableLookup(const s4fgpu_law& L, double x) {
+    int n = L.nTable;
+    if (n <= 1) return L.tableSigY[0];
+    if (x < L.tableEps[0]) return L.tableSigY[0];
+    if (x >= L.tableEps[n - 1]) return L.tableSigY[n - 1];
+    int lo = 0, hi = 0;
+    for (int i = 0; i < n; i++) {
+        if (x >= L.tableEps[i]) { lo = hi = i; } else { hi = i; break; }
+    }
+    if (lo == hi) return L.tableSigY[hi];
+    return L.tableSigY[lo] + (L.tableSigY[hi] - L.tableSigY[lo]) * (x - L.tableEps[lo]) / (L.tableEps[hi] - L.tableEps[lo]);
+}
+
+struct SolverPerf { double initRes, finalRes; int nIter; };
+
+}  // namespace
+
+struct s4f_oracle {
+    std::string err;
+    // mesh ([OF-ext] lduAddressing + fvBoundaryMesh)
+    int N = 0, F = 0, B = 0, nPatches = 0;
+    ivec own, nei, faceCells, pStart, pSize, pKind, bcKind;
+    int solD[3] = {1, 1, 1};
+    // geometry
+    dvec C, V, Sf, magSf, Cf, w, nod, corr, CnbrB;
+    dvec lsP, lsN;                 // least-squares vectors (F+B)*3, F*3
+    bool nonOrth = false;
+    // models
+    s4fgpu_law law{};
+    s4fgpu_controls ctl{};
+    double Hp = 0;
+    // BC data (B-arrays)
+    dvec bcValue, bcPressure, tracGrad;
+    // vol fields: internal [0,N) then boundary [N,N+B)
+    dvec D, Dprev, Dold, DoldOld, gradD, gradDold, sigma, sigmaOld;
+    dvec impK, impKf;              // impK (N+B), impKf (F+B)
+    dvec Ft, Finv, Jt;             // solver-level F, Finv, J of the TL models
+    // law history
+    dvec lawF, lawFold, relF, lawJ, lawJold, bEbar, bEbarOld, bEbarTrial, sigmaY, DSigmaY, epsPEq, DEpsPEq,
+         epsP, DEpsP, DEpsPprev, DLambda, plasticN, epsilon, sigmaHyd, epsPOld, epsPEqOld, sigmaYOld;
+    // fvMatrix
+    dvec upper, diag, diagC, source, intCoeffs, bouCoeffs;
+    bool matrixValid = false;
+    // Aitken
+    dvec aitkenRes, aitkenResPrev, aitkenAlpha;
+    // last solve
+    SolverPerf perf[3];
+    long long totalInner = 0;
+    int iCorrLast = 0;
+
+    int NB() const { return N + B; }
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// least-squares vectors: NUM/extendedLeastSquaresGrad/extendedLeastSquaresVectors.C:121-158 (dd),
+// :217 (inv), :229-272 (lsP, lsN).  1/|d|^2 weights, true boundary deltas Cf - Cn.  Empty
+// directions: [OF-ext] inv(symmTensorField) adds 1 on the diagonal of the singular direction,
+// inverts, and removes it again.
+// ------------------------------------------------------------------------------------------------
+void makeLeastSquaresVectors(s4f_oracle& o) {
+    const int N = o.N, F = o.F, B = o.B;
+    dvec dd(6 * N, 0.0);
+    auto addwdd = [&](int c, const double* d) {
+        double r = 1.0 / dot3(d, d);
+        double* t = &dd[6 * c];
+        t[0] += r * d[0] * d[0]; t[1] += r * d[0] * d[1]; t[2] += r * d[0] * d[2];
+        t[3] += r * d[1] * d[1]; t[4] += r * d[1] * d[2]; t[5] += r * d[2] * d[2];
+    };
+    for (int f = 0; f < F; f++) {
+        int P = o.own[f], Nn = o.nei[f];
+        double d[3] = {o.C[3 * Nn] - o.C[3 * P], o.C[3 * Nn + 1] - o.C[3 * P + 1], o.C[3 * Nn + 2] - o.C[3 * P + 2]};
+        addwdd(P, d); addwdd(Nn, d);
+    }
+    for (int b = 0; b < B; b++) {
+        int P = o.faceCells[b];
+        const double* x = &o.CnbrB[3 * b];   // Cf on ordinary patches (neighbour centre on processor faces)
+        double d[3] = {x[0] - o.C[3 * P], x[1] - o.C[3 * P + 1], x[2] - o.C[3 * P + 2]};
+        addwdd(P, d);
+    }
+    dvec invDd(6 * N);
+    for (int c = 0; c < N; c++) {
+        double t[6]; for (int k = 0; k < 6; k++) t[k] = dd[6 * c + k];
+        if (!o.solD[0]) t[0] += 1; if (!o.solD[1]) t[3] += 1; if (!o.solD[2]) t[5] += 1;
+        double r[6]; invS(t, r);
+        if (!o.solD[0]) r[0] -= 1; if (!o.solD[1]) r[3] -= 1; if (!o.solD[2]) r[5] -= 1;
+        for (int k = 0; k < 6; k++) invDd[6 * c + k] = r[k];
+    }
+    o.lsP.assign(3 * (F + B), 0.0); o.lsN.assign(3 * F, 0.0);
+    for (int f = 0; f < F; f++) {
+        int P = o.own[f], Nn = o.nei[f];
+        double d[3] = {o.C[3 * Nn] - o.C[3 * P], o.C[3 * Nn + 1] - o.C[3 * P + 1], o.C[3 * Nn + 2] - o.C[3 * P + 2]};
+        double r = 1.0 / dot3(d, d), a[3], b2[3];
+        SvS(&invDd[6 * P], d, a); SvS(&invDd[6 * Nn], d, b2);
+        for (int k = 0; k < 3; k++) { o.lsP[3 * f + k] = r * a[k]; o.lsN[3 * f + k] = -r * b2[k]; }
+    }
+    for (int b = 0; b < B; b++) {
+        int P = o.faceCells[b];
+        const double* x = &o.CnbrB[3 * b];
+        double d[3] = {x[0] - o.C[3 * P], x[1] - o.C[3 * P + 1], x[2] - o.C[3 * P + 2]};
+        double r = 1.0 / dot3(d, d), a[3];
+        SvS(&invDd[6 * P], d, a);
+        for (int k = 0; k < 3; k++) o.lsP[3 * (F + b) + k] = r * a[k];
+    }
+}
+
+// patchCorrectionVectors: k = (I - nn) & (Cf - Cn); NUM/patchCorrectionVectors/patchCorrectionVectors.C:24-36
+inline void patchGeom(const s4f_oracle& o, int b, double* n, double* k, double& delta) {
+    const int f = o.F + b, P = o.faceCells[b];
+    for (int i = 0; i < 3; i++) n[i] = o.Sf[3 * f + i] / o.magSf[f];
+    double d[3] = {o.Cf[3 * f] - o.C[3 * P], o.Cf[3 * f + 1] - o.C[3 * P + 1], o.Cf[3 * f + 2] - o.C[3 * P + 2]};
+    double nd = dot3(n, d);
+    for (int i = 0; i < 3; i++) k[i] = d[i] - n[i] * nd;
+    delta = o.nod[f];   // patch().deltaCoeffs(): 1/max(n.d, 0.05|d|)
+}
+
+// ------------------------------------------------------------------------------------------------
+// Boundary conditions of D
+// ------------------------------------------------------------------------------------------------
+
+// tractionBoundarySnGrad: SM/linGeomTotalDispSolid/linGeomTotalDispSolid.C:235-271 and the
+// total-Lagrangian form SM/nonLinGeomTotalLagTotalDispSolid/...C:284-328 (deformed normal).
+void tractionSnGrad(const s4f_oracle& o, int b, double* g) {
+    const int N = o.N;
+    double n[3], k[3], delta; patchGeom(o, b, n, k, delta);
+    const double* t = &o.bcValue[3 * b];
+    const double p = o.bcPressure[b];
+    const double impK = o.impK[N + b], rImpK = 1.0 / impK;
+    const double* gD = &o.gradD[9 * (N + b)];
+    const double* sg = &o.sigma[6 * (N + b)];
+    if (o.ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP) {
+        // ((traction - n*pressure) - (n & (pSigma - impK*pGradD)))*rImpK
+        double M[9]; S2T(sg, M);
+        for (int i = 0; i < 9; i++) M[i] -= impK * gD[i];
+        double nM[3]; vT(n, M, nM);
+        for (int i = 0; i < 3; i++) g[i] = ((t[i] - n[i] * p) - nM[i]) * rImpK;
+    } else {
+        // nCurrent = Finv.T() & n / mag;  ((t - nCur*p) - (nCur & pSigma) + impK*(n & pGradD))*rImpK
+        const double* Fi = &o.Finv[9 * (N + b)];
+        double FiT[9]; transposeT(Fi, FiT);
+        double nc[3] = {FiT[0] * n[0] + FiT[1] * n[1] + FiT[2] * n[2], FiT[3] * n[0] + FiT[4] * n[1] + FiT[5] * n[2],
+                        FiT[6] * n[0] + FiT[7] * n[1] + FiT[8] * n[2]};
+        double m = mag3(nc); for (int i = 0; i < 3; i++) nc[i] /= m;
+        double ns[3]; SvS(sg, nc, ns);          // nCur & sigma (symmetric)
+        double ng[3]; vT(n, gD, ng);
+        for (int i = 0; i < 3; i++) g[i] = ((t[i] - nc[i] * p) - ns[i] + impK * ng[i]) * rImpK;
+    }
+}
+
+// updateCoeffs() of every patch, as triggered by the fvMatrix constructor [OF-ext]:
+//  solidTraction: gradient() = tractionBoundarySnGrad (relaxFac 1)  solidTractionFvPatchVectorField.C:384-392
+//  fixedDisplacement: value = totalDisp                              fixedDisplacementFvPatchVectorField.C:258-294
+void bcUpdateCoeffs(s4f_oracle& o) {
+    for (int p = 0; p < o.nPatches; p++) for (int i = 0; i < o.pSize[p]; i++) {
+        int b = o.pStart[p] + i;
+        if (o.bcKind[p] == S4F_BC_SOLID_TRACTION) tractionSnGrad(o, b, &o.tracGrad[3 * b]);
+        else if (o.bcKind[p] == S4F_BC_FIXED_DISPLACEMENT) {
+            for (int c = 0; c < 3; c++) {
+                double v = o.bcValue[3 * b + c];
+                if (o.ctl.solidModel == S4F_MODEL_NONLIN_TL || o.ctl.solidModel == S4F_MODEL_NONLIN_UL)
+                    v -= o.Dold[3 * (o.N + b) + c];        // DD field: disp -= Dold  (:279-287)
+                o.D[3 * (o.N + b) + c] = v;
+            }
+        }
+    }
+}
+
+// snGrad() of patch face b.  gradRef = the registered "grad(D)" field at the time of the call.
+//  solidTraction (fixedGradient): gradient()
+//  fixedDisplacement: (D_b - (D_P + k & gradD_P))*deltaCoeffs         fixedDisplacement...C:297-326
+//  solidSymmetry: (transform(I-2nn, DP) - DP)*deltaCoeffs/2           solidSymmetry...C:148-196
+void bcSnGrad(const s4f_oracle& o, int p, int b, const dvec& gradRef, double* sn) {
+    const int N = o.N, P = o.faceCells[b];
+    double n[3], k[3], delta; patchGeom(o, b, n, k, delta);
+    if (o.bcKind[p] == S4F_BC_SOLID_TRACTION) { for (int i = 0; i < 3; i++) sn[i] = o.tracGrad[3 * b + i]; return; }
+    double kg[3]; vT(k, &gradRef[9 * P], kg);
+    double DP[3]; for (int i = 0; i < 3; i++) DP[i] = o.D[3 * P + i] + kg[i];
+    if (o.bcKind[p] == S4F_BC_FIXED_DISPLACEMENT) {
+        for (int i = 0; i < 3; i++) sn[i] = (o.D[3 * (N + b) + i] - DP[i]) * delta;
+    } else {   // symmetry
+        double nDP = dot3(n, DP);
+        for (int i = 0; i < 3; i++) sn[i] = ((DP[i] - 2.0 * n[i] * nDP) - DP[i]) * (delta / 2.0);
+    }
+}
+
+// evaluate() of every patch (D.correctBoundaryConditions()).  Uses the registered "grad(D)".
+//  solidTraction: D_b = D_P + (k & gradD_P) + gradient()/deltaCoeffs          solidTraction...C:398-463
+//  solidSymmetry: D_b = (DP + transform(I-2nn, DP))/2                         solidSymmetry...C:200-260
+//  fixedDisplacement: value stays
+void bcEvaluate(s4f_oracle& o) {
+    const int N = o.N;
+    for (int p = 0; p < o.nPatches; p++) for (int i = 0; i < o.pSize[p]; i++) {
+        int b = o.pStart[p] + i, P = o.faceCells[b];
+        double n[3], k[3], delta; patchGeom(o, b, n, k, delta);
+        double kg[3]; vT(k, &o.gradD[9 * P], kg);
+        if (o.bcKind[p] == S4F_BC_SOLID_TRACTION) {
+            for (int c = 0; c < 3; c++) o.D[3 * (N + b) + c] = o.D[3 * P + c] + kg[c] + o.tracGrad[3 * b + c] / delta;
+        } else if (o.bcKind[p] == S4F_BC_SOLID_SYMMETRY) {
+            double DP[3]; for (int c = 0; c < 3; c++) DP[c] = o.D[3 * P + c] + kg[c];
+            double nDP = dot3(n, DP);
+            for (int c = 0; c < 3; c++) o.D[3 * (N + b) + c] = (DP[c] + (DP[c] - 2.0 * n[c] * nDP)) / 2.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fvc::grad(D): least squares (NUM/extendedLeastSquaresGrad/extendedLeastSquaresGrad.C:103-167) or
+// [OF-ext] Gauss linear; then gaussGrad::correctBoundaryConditions: grad_b = grad_P + n (snGrad_b - n & grad_P).
+// mechanicalModel::grad, mechanicalModel.C:571-582.
+// ------------------------------------------------------------------------------------------------
+void calcGrad(s4f_oracle& o) {
+    const int N = o.N, F = o.F, B = o.B;
+    dvec g(9 * (N + B), 0.0);
+    if (o.ctl.gradScheme == S4F_GRAD_LEAST_SQUARES) {
+        for (int f = 0; f < F; f++) {
+            int P = o.own[f], Nn = o.nei[f];
+            double dv[3] = {o.D[3 * Nn] - o.D[3 * P], o.D[3 * Nn + 1] - o.D[3 * P + 1], o.D[3 * Nn + 2] - o.D[3 * P + 2]};
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+                g[9 * P + 3 * i + j] += o.lsP[3 * f + i] * dv[j];
+                g[9 * Nn + 3 * i + j] -= o.lsN[3 * f + i] * dv[j];
+            }
+        }
+        for (int b = 0; b < B; b++) {
+            int P = o.faceCells[b];
+            double dv[3] = {o.D[3 * (N + b)] - o.D[3 * P], o.D[3 * (N + b) + 1] - o.D[3 * P + 1], o.D[3 * (N + b) + 2] - o.D[3 * P + 2]};
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) g[9 * P + 3 * i + j] += o.lsP[3 * (F + b) + i] * dv[j];
+        }
+    } else {
+        for (int f = 0; f < F; f++) {
+            int P = o.own[f], Nn = o.nei[f];
+            double wf = o.w[f];
+            for (int j = 0; j < 3; j++) {
+                double vf = wf * o.D[3 * P + j] + (1 - wf) * o.D[3 * Nn + j];
+                for (int i = 0; i < 3; i++) {
+                    double t = o.Sf[3 * f + i] * vf;
+                    g[9 * P + 3 * i + j] += t; g[9 * Nn + 3 * i + j] -= t;
+                }
+            }
+        }
+        for (int b = 0; b < B; b++) {
+            int P = o.faceCells[b];
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) g[9 * P + 3 * i + j] += o.Sf[3 * (F + b) + i] * o.D[3 * (N + b) + j];
+        }
+        for (int c = 0; c < N; c++) for (int q = 0; q < 9; q++) g[9 * c + q] /= o.V[c];
+    }
+    // boundary: extrapolate then correct the normal component with the BC's snGrad (which reads the
+    // OLD registered grad(D) -- the assignment gradD = fvc::grad(D) happens after the evaluation)
+    for (int p = 0; p < o.nPatches; p++) for (int i2 = 0; i2 < o.pSize[p]; i2++) {
+        int b = o.pStart[p] + i2, P = o.faceCells[b];
+        double n[3], k[3], delta; patchGeom(o, b, n, k, delta);
+        double sn[3]; bcSnGrad(o, p, b, o.gradD, sn);
+        double* gb = &g[9 * (N + b)];
+        for (int q = 0; q < 9; q++) gb[q] = g[9 * P + q];
+        double ng[3]; vT(n, gb, ng);
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) gb[3 * i + j] += n[i] * (sn[j] - ng[j]);
+    }
+    o.gradD.swap(g);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mechanical laws (cells and boundary faces alike: OpenFOAM field algebra acts on both)
+// ------------------------------------------------------------------------------------------------
+
+// linearElastic::correct, ML/linearGeometryLaws/linearElastic/linearElastic.C:318-339;
+// updateEpsilon ML/mechanicalLaw/mechanicalLaw.C:983-1001; updateSigmaHyd explicit branch :1469-1475
+void lawLinearElastic(s4f_oracle& o) {
+    const int n = o.NB();
+    const double mu = o.law.mu, K = o.law.K;
+    for (int c = 0; c < n; c++) {
+        double e[6]; symm(&o.gradD[9 * c], e);
+        for (int q = 0; q < 6; q++) o.epsilon[6 * c + q] = e[q];
+        double sh = K * trS(e);
+        o.sigmaHyd[c] = sh;
+        double de[6]; devS(e, de);
+        double* s = &o.sigma[6 * c];
+        for (int q = 0; q < 6; q++) s[q] = 2.0 * mu * de[q] + o.law.sigma0[q];
+        s[0] += sh; s[3] += sh; s[5] += sh;
+    }
+}
+
+// mechanicalLaw::updateF, TL total displacement branch: F = I + gradD.T(); relF = F & inv(F.old)
+// ML/mechanicalLaw/mechanicalLaw.C:1130-1140
+void lawUpdateF(s4f_oracle& o) {
+    const int n = o.NB();
+    for (int c = 0; c < n; c++) {
+        double Ft[9]; transposeT(&o.gradD[9 * c], Ft);
+        Ft[0] += 1; Ft[4] += 1; Ft[8] += 1;
+        for (int q = 0; q < 9; q++) o.lawF[9 * c + q] = Ft[q];
+        double Fi[9]; invT(&o.lawFold[9 * c], Fi);
+        mulTT(Ft, Fi, &o.relF[9 * c]);
+    }
+}
+
+// neoHookeanElastic::correct, ML/nonLinearGeometryLaws/neoHookeanElastic/neoHookeanElastic.C:275-303
+void lawNeoHookean(s4f_oracle& o) {
+    lawUpdateF(o);
+    const int n = o.NB();
+    const double mu = o.law.mu, K = o.law.K;
+    for (int c = 0; c < n; c++) {
+        const double* Fm = &o.lawF[9 * c];
+        double J = detT(Fm);
+        double FT[9], FFT[9], b[6];
+        transposeT(Fm, FT); mulTT(Fm, FT, FFT); symm(FFT, b);
+        double sc = std::pow(J, -2.0 / 3.0);
+        for (int q = 0; q < 6; q++) b[q] *= sc;
+        double s[6]; devS(b, s);
+        for (int q = 0; q < 6; q++) s[q] *= mu;
+        double sh = 0.5 * K * (std::pow(J, 2.0) - 1.0);
+        o.sigmaHyd[c] = sh; o.lawJ[c] = J;
+        double* sg = &o.sigma[6 * c];
+        for (int q = 0; q < 6; q++) sg[q] = s[q];
+        sg[0] += sh; sg[3] += sh; sg[5] += sh;
+        for (int q = 0; q < 6; q++) sg[q] *= (1.0 / J);
+    }
+}
+
+// neoHookeanElasticMisesPlastic helpers: curYieldStress :139-150, yieldFunction :153-183,
+// newtonLoop :186-247 (LoopTol 1e-8, MaxNewtonIter 200, finiteDiff 0.25e-6: :41-47)
+const double sqrtTwoOverThree = std::sqrt(2.0 / 3.0);
+inline double curYieldStress(const s4fgpu_law& L, double epsPEq, double J) { return J * tableLookup(L, std::max(epsPEq, SMALL)); }
+inline double yieldFunction(const s4fgpu_law& L, double epsOld, double magSTrial, double DLambda, double muBar, double J) {
+    return magSTrial - 2 * muBar * DLambda - sqrtTwoOverThree * curYieldStress(L, epsOld + sqrtTwoOverThree * DLambda, J);
+}
+void newtonLoop(const s4fgpu_law& L, double& DLambda, double& curSigmaY, double epsOld, double magSTrial, double muBar,
+                double J, double maxMagDEpsilon) {
+    const double LoopTol = 1e-8, finiteDiff = 0.25e-6; const int MaxNewtonIter = 200;
+    int i = 0;
+    double fTrial = yieldFunction(L, epsOld, magSTrial, DLambda, muBar, J);
+    double residual = 1.0;
+    do {
+        double fStep = yieldFunction(L, epsOld, magSTrial, DLambda + finiteDiff, muBar, J);
+        double deriv = (fStep - fTrial) / finiteDiff;
+        residual = fTrial / deriv;
+        DLambda -= residual;
+        residual /= maxMagDEpsilon;
+        fTrial = yieldFunction(L, epsOld, magSTrial, DLambda, muBar, J);
+    } while ((std::fabs(residual) > LoopTol) && ++i < MaxNewtonIter);
+    curSigmaY = curYieldStress(L, epsOld + sqrtTwoOverThree * DLambda, J) / J;
+}
+// Ibar: Rubin-Attia cubic for det(bEbar)=1, :250-395
+inline double IbarOf(const double* devB) {
+    double detd = detS(devB), dotp = magSqrS(devB), fac1 = 2.0 * dotp / 3.0, alpha1;
+    if (std::fabs(fac1) < SMALL) alpha1 = 3.0;
+    else {
+        double fac2 = (4.0 * (1.0 - detd)) / std::pow(fac1, 1.5);
+        if (fac2 >= 1.0) alpha1 = 3.0 * std::sqrt(fac1) * std::cosh(std::acosh(fac2) / 3.0);
+        else alpha1 = 3.0 * std::sqrt(fac1) * std::cos(std::acos(fac2) / 3.0);
+    }
+    return alpha1 / 3.0;
+}
+
+// neoHookeanElasticMisesPlastic::correct, ...MisesPlastic.C:991-1223
+void lawNeoHookeanMises(s4f_oracle& o) {
+    lawUpdateF(o);
+    const int N = o.N, n = o.NB();
+    const double mu = o.law.mu, K = o.law.K;
+    dvec sTrial(6 * n), IbarT(n), muBar(n), fTrial(n);
+    o.DEpsPprev = o.DEpsP;                                   // DEpsilonP_.storePrevIter()
+    double maxMagBE = 0;
+    for (int c = 0; c < n; c++) {
+        double J = detT(&o.lawF[9 * c]);
+        o.lawJ[c] = J;
+        double relJ = J / o.lawJold[c];
+        double sc = std::pow(relJ, -1.0 / 3.0);
+        double rFb[9]; for (int q = 0; q < 9; q++) rFb[q] = sc * o.relF[9 * c + q];
+        double bo[9], t1[9], rT[9], t2[9];
+        S2T(&o.bEbarOld[6 * c], bo); mulTT(rFb, bo, t1); transposeT(rFb, rT); mulTT(t1, rT, t2);
+        double* bt = &o.bEbarTrial[6 * c];
+        symm(t2, bt);                                          // transform(relFbar, bEbar.oldTime())
+        double dv[6]; devS(bt, dv);
+        for (int q = 0; q < 6; q++) sTrial[6 * c + q] = mu * dv[q];
+        IbarT[c] = trS(bt) / 3.0; muBar[c] = IbarT[c] * mu;
+        if (c < N) maxMagBE = std::max(maxMagBE, std::sqrt(magSqrS(bt)));   // gMax over the internal field :1030
+        fTrial[c] = std::sqrt(magSqrS(&sTrial[6 * c])) - sqrtTwoOverThree * J * o.sigmaY[c];
+    }
+    maxMagBE = std::max(maxMagBE, SMALL);
+    const bool nonLinearPlasticity = o.law.nTable > 2;
+    const double magHp = std::fabs(o.Hp);
+    for (int c = 0; c < n; c++) {                              // cells :1066-1118, boundary faces :1120-1193
+        double magS = std::sqrt(magSqrS(&sTrial[6 * c]));
+        if (magS > SMALL) for (int q = 0; q < 6; q++) o.plasticN[6 * c + q] = sTrial[6 * c + q] / magS;
+        if (fTrial[c] < SMALL) { o.DSigmaY[c] = 0; o.DLambda[c] = 0; }
+        else if (nonLinearPlasticity) {
+            double curSigmaY = 0;
+            newtonLoop(o.law, o.DLambda[c], curSigmaY, o.epsPEq[c], magS, muBar[c], o.lawJ[c], maxMagBE);
+            o.DSigmaY[c] = curSigmaY - o.sigmaY[c];
+        } else {
+            o.DLambda[c] = fTrial[c] / (2 * muBar[c]);
+            if (magHp > SMALL) { o.DLambda[c] /= 1.0 + o.Hp / (3 * muBar[c]); o.DSigmaY[c] = sqrtTwoOverThree * o.DLambda[c] * o.Hp; }
+        }
+    }
+    const double relax = o.law.DEpsilonPRelax;
+    for (int c = 0; c < n; c++) {
+        o.DEpsPEq[c] = sqrtTwoOverThree * o.DLambda[c];
+        double s[6], devB[6];
+        for (int q = 0; q < 6; q++) {
+            double v = IbarT[c] * o.DLambda[c] * o.plasticN[6 * c + q];
+            // DEpsilonP_.relax(): prevIter + alpha*(new - prevIter)  [OF-ext] GeometricField::relax
+            if (relax != 1.0) v = o.DEpsPprev[6 * c + q] + relax * (v - o.DEpsPprev[6 * c + q]);
+            o.DEpsP[6 * c + q] = v;
+            s[q] = sTrial[6 * c + q] - 2 * mu * v;
+            devB[q] = s[q] / mu;
+        }
+        double Ib = o.law.updateBEbarConsistent ? IbarOf(devB) : IbarT[c];
+        double* be = &o.bEbar[6 * c];
+        for (int q = 0; q < 6; q++) be[q] = devB[q];
+        be[0] += Ib; be[3] += Ib; be[5] += Ib;
+        double J = o.lawJ[c];
+        double sh = 0.5 * K * (std::pow(J, 2.0) - 1.0);
+        o.sigmaHyd[c] = sh;
+        double* sg = &o.sigma[6 * c];
+        for (int q = 0; q < 6; q++) sg[q] = s[q];
+        sg[0] += sh; sg[3] += sh; sg[5] += sh;
+        for (int q = 0; q < 6; q++) sg[q] *= (1.0 / J);
+    }
+}
+
+// linearElasticMisesPlastic::correct (small strain J2), ML/linearGeometryLaws/linearElasticMisesPlastic/
+// linearElasticMisesPlastic.C:953-1078 with updatePlasticity :58-131, yieldFunction :144-171 and
+// newtonLoop :174-232 (no J scaling, muBar = mu).  Total fields are rebuilt from their old-time
+// values on every call (:1062-1066), so updateTotalFields has nothing to add for this law.
+void lawLinearElasticMises(s4f_oracle& o) {
+    const int N = o.N, n = o.NB();
+    const double mu = o.law.mu, K = o.law.K;
+    double maxMagBE = 0;
+    for (int c = 0; c < n; c++) {
+        symm(&o.gradD[9 * c], &o.epsilon[6 * c]);                         // updateEpsilon()
+        if (c < N) maxMagBE = std::max(maxMagBE, std::sqrt(magSqrS(&o.epsilon[6 * c])));
+    }
+    maxMagBE = std::max(maxMagBE, SMALL);
+    const bool nonLinearPlasticity = o.law.nTable > 2;
+    o.DEpsPprev = o.DEpsP;                                                 // DEpsilonP_.storePrevIter()
+    for (int c = 0; c < n; c++) {
+        const double* eps = &o.epsilon[6 * c];
+        double e[6], dpo[6], sT[6];
+        devS(eps, e); devS(&o.epsPOld[6 * c], dpo);
+        for (int q = 0; q < 6; q++) sT[q] = 2.0 * mu * (e[q] - dpo[q]);
+        double fT = std::sqrt(magSqrS(sT)) - sqrtTwoOverThree * o.sigmaYOld[c];
+        double* pn = &o.plasticN[6 * c];
+        if (fT < SMALL) {
+            pn[0] = 1; pn[1] = 0; pn[2] = 0; pn[3] = 1; pn[4] = 0; pn[5] = 1;
+            o.DLambda[c] = 0; o.DSigmaY[c] = 0; o.sigmaY[c] = o.sigmaYOld[c];
+        } else {
+            double magS = std::sqrt(magSqrS(sT));
+            if (magS > SMALL) for (int q = 0; q < 6; q++) pn[q] = sT[q] / magS;
+            else { pn[0] = 1; pn[1] = 0; pn[2] = 0; pn[3] = 1; pn[4] = 0; pn[5] = 1; }
+            if (nonLinearPlasticity) {
+                // same Newton iteration as the finite-strain law with J = 1 (Kirchhoff == Cauchy)
+                newtonLoop(o.law, o.DLambda[c], o.sigmaY[c], o.epsPEqOld[c], magS, mu, 1.0, maxMagBE);
+                o.DSigmaY[c] = o.sigmaY[c] - o.sigmaYOld[c];
+            } else {
+                o.DLambda[c] = fT / (2 * mu);
+                if (std::fabs(o.Hp) > SMALL) {
+                    o.DLambda[c] /= 1.0 + o.Hp / (3 * mu);
+                    o.DSigmaY[c] = sqrtTwoOverThree * o.DLambda[c] * o.Hp;
+                    o.sigmaY[c] = o.sigmaYOld[c] + o.DSigmaY[c];
+                }
+            }
+        }
+        o.DEpsPEq[c] = sqrtTwoOverThree * o.DLambda[c];
+        double s[6];
+        for (int q = 0; q < 6; q++) {
+            o.DEpsP[6 * c + q] = o.DLambda[c] * pn[q];
+            o.epsP[6 * c + q] = o.epsPOld[6 * c + q] + o.DEpsP[6 * c + q];
+            s[q] = sT[q] - 2 * mu * o.DEpsP[6 * c + q];
+        }
+        o.epsPEq[c] = o.epsPEqOld[c] + o.DEpsPEq[c];
+        double sh = K * trS(eps);
+        o.sigmaHyd[c] = sh;
+        double* sg = &o.sigma[6 * c];
+        for (int q = 0; q < 6; q++) sg[q] = s[q];
+        sg[0] += sh; sg[3] += sh; sg[5] += sh;
+    }
+}
+
+void lawCorrect(s4f_oracle& o) {
+    switch (o.law.kind) {
+        case S4F_LAW_LINEAR_ELASTIC: lawLinearElastic(o); break;
+        case S4F_LAW_NEO_HOOKEAN_ELASTIC: lawNeoHookean(o); break;
+        case S4F_LAW_NEO_HOOKEAN_MISES_PLASTIC: lawNeoHookeanMises(o); break;
+        case S4F_LAW_LINEAR_ELASTIC_MISES_PLASTIC: lawLinearElasticMises(o); break;
+    }
+}
+
+// residual(): neoHookeanElasticMisesPlastic.C:1468-1523 (internal field only); elastic laws: 0
+double lawResidual(const s4f_oracle& o) {
+    if (o.law.kind != S4F_LAW_NEO_HOOKEAN_MISES_PLASTIC && o.law.kind != S4F_LAW_LINEAR_ELASTIC_MISES_PLASTIC) return 0.0;
+    double num = 0, den = 0;
+    for (int c = 0; c < o.N; c++) {
+        double d[6]; for (int q = 0; q < 6; q++) d[q] = o.DEpsP[6 * c + q] - o.DEpsPprev[6 * c + q];
+        num = std::max(num, std::sqrt(magSqrS(d)));
+        den = std::max(den, SMALL + std::sqrt(magSqrS(&o.DEpsPprev[6 * c])));
+    }
+    return num / den;
+}
+
+// solver-level kinematics of the TL models: F = I + gradD.T(); Finv = inv(F); J = det(F)
+// SM/nonLinGeomTotalLagTotalDispSolid/nonLinGeomTotalLagTotalDispSolid.C:225-232
+void updateKinematics(s4f_oracle& o) {
+    const int n = o.NB();
+    for (int c = 0; c < n; c++) {
+        double* Fm = &o.Ft[9 * c];
+        transposeT(&o.gradD[9 * c], Fm); Fm[0] += 1; Fm[4] += 1; Fm[8] += 1;
+        invT(Fm, &o.Finv[9 * c]);
+        o.Jt[c] = detT(Fm);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Momentum equation  (SM/linGeomTotalDispSolid/linGeomTotalDispSolid.C:141-149)
+//
+//   rho*fvm::d2dt2(D) == fvm::laplacian(impKf,D) - fvc::laplacian(impKf,D) + fvc::div(sigma)
+//                        + rho*g + stabilisation
+//
+// Assembled directly in the sign of the final system A D = b ( "A == B" is A - B, [OF-ext] ):
+//   upper_f = -impKf_f*nonOrthDeltaCoeffs_f*magSf_f ;  diag_P = sum_f (-upper_f)  (+ d2dt2)
+//   internalCoeffs_b = -impKf_b*magSf_b*gradientInternalCoeffs_b (added to diag per component)
+//   boundaryCoeffs_b = +impKf_b*magSf_b*gradientBoundaryCoeffs_b (added to source)
+//   source = d2dt2 source - V*fvcLaplacian + V*div(sigma) + V*rho*g + V*stabilisation
+// The non-orthogonal correction of fvm::laplacian (source -= V div(gammaMagSf*correction)) and the one
+// inside fvc::laplacian's corrected snGrad are the same field with opposite sign: they are left out.
+// ------------------------------------------------------------------------------------------------
+void assembleMatrix(s4f_oracle& o) {
+    const int N = o.N, F = o.F, B = o.B;
+    o.upper.assign(F, 0.0); o.diag.assign(N, 0.0);
+    o.intCoeffs.assign(3 * B, 0.0);
+    for (int f = 0; f < F; f++) {
+        double a = o.impKf[f] * o.nod[f] * o.magSf[f];
+        o.upper[f] = -a; o.diag[o.own[f]] += a; o.diag[o.nei[f]] += a;
+    }
+    // d2dt2: [OF-ext] EulerD2dt2Scheme::fvmD2dt2 (variable deltaT form)
+    if (o.ctl.d2dt2Scheme == S4F_D2DT2_EULER) {
+        double dt = o.ctl.deltaT, dt0 = o.ctl.deltaT0 > 0 ? o.ctl.deltaT0 : dt;
+        double coefft = (dt + dt0) / (2 * dt), rDeltaT2 = 4.0 / ((dt + dt0) * (dt + dt0));
+        for (int c = 0; c < N; c++) o.diag[c] += coefft * rDeltaT2 * o.V[c] * o.law.rho;
+    }
+    for (int p = 0; p < o.nPatches; p++) for (int i = 0; i < o.pSize[p]; i++) {
+        int b = o.pStart[p] + i, f = F + b;
+        double n[3], k[3], delta; patchGeom(o, b, n, k, delta);
+        double gm = o.impKf[f] * o.magSf[f];
+        double dlap = o.nod[f];   // tsnGradScheme_().deltaCoeffs(vf) boundary value
+        if (o.bcKind[p] == S4F_BC_FIXED_DISPLACEMENT) {
+            for (int c = 0; c < 3; c++) o.intCoeffs[3 * b + c] = gm * dlap;     // -gm*(-deltaCoeffs)
+        } else if (o.bcKind[p] == S4F_BC_SOLID_SYMMETRY) {
+            // [OF-ext] basicSymmetry: gradientInternalCoeffs = -deltaCoeffs*snGradTransformDiag, diag = |n_c|
+            for (int c = 0; c < 3; c++) o.intCoeffs[3 * b + c] = gm * dlap * std::fabs(n[c]);
+        }   // fixedGradient: 0
+    }
+    // per-component diagonal after addBoundaryDiag
+    o.diagC.assign(3 * N, 0.0);
+    for (int c = 0; c < N; c++) for (int q = 0; q < 3; q++) o.diagC[3 * c + q] = o.diag[c];
+    for (int b = 0; b < B; b++) for (int q = 0; q < 3; q++) o.diagC[3 * o.faceCells[b] + q] += o.intCoeffs[3 * b + q];
+    o.matrixValid = true;
+}
+
+void assembleSource(s4f_oracle& o) {
+    const int N = o.N, F = o.F, B = o.B;
+    const bool TL = (o.ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP);
+    o.source.assign(3 * N, 0.0);
+    dvec& s = o.source;
+    // d2dt2 source (Euler): rDeltaT2*V*rho*((coefft+coefft00)*D.old - coefft00*D.oldOld)
+    if (o.ctl.d2dt2Scheme == S4F_D2DT2_EULER) {
+        double dt = o.ctl.deltaT, dt0 = o.ctl.deltaT0 > 0 ? o.ctl.deltaT0 : dt;
+        double coefft = (dt + dt0) / (2 * dt), coefft00 = (dt + dt0) / (2 * dt0), rDeltaT2 = 4.0 / ((dt + dt0) * (dt + dt0));
+        for (int c = 0; c < N; c++) for (int q = 0; q < 3; q++)
+            s[3 * c + q] += rDeltaT2 * o.V[c] * o.law.rho * ((coefft + coefft00) * o.Dold[3 * c + q] - coefft00 * o.DoldOld[3 * c + q]);
+    }
+    // - V*fvc::laplacian(impKf, D): compact part, face flux impKf*magSf*delta*(D_N - D_P)
+    for (int f = 0; f < F; f++) {
+        int P = o.own[f], Nn = o.nei[f];
+        double a = -o.upper[f];
+        for (int q = 0; q < 3; q++) {
+            double flux = a * (o.D[3 * Nn + q] - o.D[3 * P + q]);
+            s[3 * P + q] -= flux; s[3 * Nn + q] += flux;
+        }
+    }
+    // + V*fvc::div(sigma)  [OF-ext] gaussDivScheme, linear:  Sf & (w sigma_P + (1-w) sigma_N)
+    // TL: the cell tensor is J*Finv & sigma (nonLinGeomTotalLagTotalDispSolid.C:206)
+    dvec T;   // full tensor per cell/boundary face
+    T.resize(9 * (N + B));
+    for (int c = 0; c < N + B; c++) {
+        double sg[9]; S2T(&o.sigma[6 * c], sg);
+        if (TL) { double t[9]; mulTT(&o.Finv[9 * c], sg, t); for (int q = 0; q < 9; q++) T[9 * c + q] = o.Jt[c] * t[q]; }
+        else for (int q = 0; q < 9; q++) T[9 * c + q] = sg[q];
+    }
+    for (int f = 0; f < F; f++) {
+        int P = o.own[f], Nn = o.nei[f];
+        double wf = o.w[f], Tf[9];
+        for (int q = 0; q < 9; q++) Tf[q] = wf * T[9 * P + q] + (1 - wf) * T[9 * Nn + q];
+        double fl[3]; vT(&o.Sf[3 * f], Tf, fl);
+        for (int q = 0; q < 3; q++) { s[3 * P + q] += fl[q]; s[3 * Nn + q] -= fl[q]; }
+    }
+    for (int b = 0; b < B; b++) {
+        double fl[3]; vT(&o.Sf[3 * (F + b)], &T[9 * (N + b)], fl);
+        for (int q = 0; q < 3; q++) s[3 * o.faceCells[b] + q] += fl[q];
+    }
+    // + V*rho*g
+    for (int c = 0; c < N; c++) for (int q = 0; q < 3; q++) s[3 * c + q] += o.V[c] * o.law.rho * o.ctl.g[q];
+    // + V*stabilisation: RhieChow, SM/solidModel/momentumStabilisation/momentumStabilisation.C:112-114
+    // (gamma = scaleFactor*impK), :119 (linear interpolate), :198-206 (zero on non-coupled boundaries),
+    // :210-217  fvc::laplacian(gammaf, D) - fvc::div(gammaf*(Sf & interpolate(gradD)))
+    if (o.ctl.stabilisation == S4F_STAB_RHIE_CHOW) {
+        const double sf = o.ctl.stabScaleFactor;
+        for (int f = 0; f < F; f++) {
+            int P = o.own[f], Nn = o.nei[f];
+            double wf = o.w[f];
+            double gP = sf * o.impK[P], gN = sf * o.impK[Nn];
+            double gf = wf * gP + (1 - wf) * gN;
+            if (std::fabs(o.impK[P] - o.impK[Nn]) > SMALL) gf = 0.01 * 0.5 * (o.impK[P] + o.impK[Nn]);   // :137-150
+            double gradf[9];
+            for (int q = 0; q < 9; q++) gradf[q] = wf * o.gradD[9 * P + q] + (1 - wf) * o.gradD[9 * Nn + q];
+            double Sg[3], cg[3]; vT(&o.Sf[3 * f], gradf, Sg); vT(&o.corr[3 * f], gradf, cg);
+            for (int q = 0; q < 3; q++) {
+                double sn = o.nod[f] * (o.D[3 * Nn + q] - o.D[3 * P + q]) + cg[q];   // corrected snGrad
+                double flux = gf * (o.magSf[f] * sn - Sg[q]);
+                s[3 * P + q] += flux; s[3 * Nn + q] -= flux;
+            }
+        }
+    }
+    // boundary: - impKf_b*magSf_b*snGrad_b (from -V*fvc::laplacian) and + boundaryCoeffs (addBoundarySource)
+    o.bouCoeffs.assign(3 * B, 0.0);
+    for (int p = 0; p < o.nPatches; p++) for (int i = 0; i < o.pSize[p]; i++) {
+        int b = o.pStart[p] + i, f = F + b, P = o.faceCells[b];
+        double n[3], k[3], delta; patchGeom(o, b, n, k, delta);
+        double gm = o.impKf[f] * o.magSf[f];
+        double sn[3]; bcSnGrad(o, p, b, o.gradD, sn);
+        double gbc[3];   // gradientBoundaryCoeffs
+        if (o.bcKind[p] == S4F_BC_SOLID_TRACTION) { for (int q = 0; q < 3; q++) gbc[q] = o.tracGrad[3 * b + q]; }
+        else if (o.bcKind[p] == S4F_BC_FIXED_DISPLACEMENT) {
+            // deltaCoeffs*(*this - (k & gradD_P))   fixedDisplacement...C:328-356
+            double kg[3]; vT(k, &o.gradD[9 * P], kg);
+            for (int q = 0; q < 3; q++) gbc[q] = delta * (o.D[3 * (N + b) + q] - kg[q]);
+        } else {
+            // [OF-ext] transformFvPatchField: snGrad() - cmptMultiply(gradientInternalCoeffs, patchInternalField)
+            for (int q = 0; q < 3; q++) gbc[q] = sn[q] + o.nod[f] * std::fabs(n[q]) * o.D[3 * P + q];
+        }
+        for (int q = 0; q < 3; q++) {
+            o.bouCoeffs[3 * b + q] = gm * gbc[q];
+            s[3 * P + q] += -gm * sn[q] + o.bouCoeffs[3 * b + q];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// [OF-ext] lduMatrix::Amul, PCG, DIC/FDIC, diagonal preconditioner, solverPerformance, normFactor
+// ------------------------------------------------------------------------------------------------
+void Amul(const s4f_oracle& o, const double* diag, const double* x, double* y) {
+    const int N = o.N, F = o.F;
+    for (int c = 0; c < N; c++) y[c] = diag[c] * x[c];
+    for (int f = 0; f < F; f++) {
+        int l = o.own[f], u = o.nei[f];
+        y[u] += o.upper[f] * x[l];   // lower == upper (symmetric)
+        y[l] += o.upper[f] * x[u];
+    }
+}
+
+struct Precond {
+    int kind; dvec rD;
+    void init(const s4f_oracle& o, const double* diag, int k) {
+        kind = k; const int N = o.N, F = o.F;
+        if (kind == S4F_PRECOND_DIC) {
+            rD.assign(diag, diag + N);
+            for (int f = 0; f < F; f++) rD[o.nei[f]] -= o.upper[f] * o.upper[f] / rD[o.own[f]];
+            for (int c = 0; c < N; c++) rD[c] = 1.0 / rD[c];
+        } else if (kind == S4F_PRECOND_DIAGONAL) {
+            rD.resize(N); for (int c = 0; c < N; c++) rD[c] = 1.0 / diag[c];
+        }
+    }
+    void apply(const s4f_oracle& o, double* w, const double* r) const {
+        const int N = o.N, F = o.F;
+        if (kind == S4F_PRECOND_NONE) { std::memcpy(w, r, sizeof(double) * N); return; }
+        for (int c = 0; c < N; c++) w[c] = rD[c] * r[c];
+        if (kind == S4F_PRECOND_DIC) {
+            for (int f = 0; f < F; f++) w[o.nei[f]] -= rD[o.nei[f]] * o.upper[f] * w[o.own[f]];
+            for (int f = F - 1; f >= 0; f--) w[o.own[f]] -= rD[o.own[f]] * o.upper[f] * w[o.nei[f]];
+        }
+    }
+};
+
+SolverPerf solvePCG(s4f_oracle& o, const double* diag, double* psi, const double* source) {
+    const int N = o.N, F = o.F;
+    SolverPerf perf{0, 0, 0};
+    dvec pA(N, 0.0), wA(N), rA(N), sumA(N);
+    double wArA = 1e300, wArAold = wArA;   // solverPerf.great_
+    Amul(o, diag, psi, wA.data());
+    for (int c = 0; c < N; c++) rA[c] = source[c] - wA[c];
+    // normFactor: sumA * gAverage(psi)
+    for (int c = 0; c < N; c++) sumA[c] = diag[c];
+    for (int f = 0; f < F; f++) { sumA[o.own[f]] += o.upper[f]; sumA[o.nei[f]] += o.upper[f]; }
+    double avg = 0; for (int c = 0; c < N; c++) avg += psi[c]; avg /= N;
+    double nf = 0;
+    for (int c = 0; c < N; c++) { double t = sumA[c] * avg; nf += std::fabs(wA[c] - t) + std::fabs(source[c] - t); }
+    nf += 1e-20;
+    double sm = 0; for (int c = 0; c < N; c++) sm += std::fabs(rA[c]);
+    perf.initRes = sm / nf; perf.finalRes = perf.initRes;
+    auto converged = [&](double fr) { return fr < o.ctl.tolerance || (o.ctl.relTol > 1e-20 && fr < o.ctl.relTol * perf.initRes); };
+    if (!converged(perf.finalRes)) {
+        Precond pre; pre.init(o, diag, o.ctl.preconditioner == S4F_PRECOND_CHEBYSHEV ? S4F_PRECOND_DIAGONAL : o.ctl.preconditioner);
+        do {
+            wArAold = wArA;
+            pre.apply(o, wA.data(), rA.data());
+            wArA = 0; for (int c = 0; c < N; c++) wArA += wA[c] * rA[c];
+            if (perf.nIter == 0) { for (int c = 0; c < N; c++) pA[c] = wA[c]; }
+            else { double beta = wArA / wArAold; for (int c = 0; c < N; c++) pA[c] = wA[c] + beta * pA[c]; }
+            Amul(o, diag, pA.data(), wA.data());
+            double wApA = 0; for (int c = 0; c < N; c++) wApA += wA[c] * pA[c];
+            if (std::fabs(wApA) / nf < VSMALL) break;   // checkSingularity
+            double alpha = wArA / wApA;
+            for (int c = 0; c < N; c++) { psi[c] += alpha * pA[c]; rA[c] -= alpha * wA[c]; }
+            sm = 0; for (int c = 0; c < N; c++) sm += std::fabs(rA[c]);
+            perf.finalRes = sm / nf;
+        } while (++perf.nIter < o.ctl.maxIter && !converged(perf.finalRes));
+    }
+    return perf;
+}
+
+// [OF-ext] fvMatrix<vector>::solveSegregated: per solved component, addBoundaryDiag, solve.
+void solveSegregated(s4f_oracle& o, double* psi /*AoS [3N]*/, const double* source /*AoS*/) {
+    const int N = o.N;
+    dvec x(N), b(N), dg(N);
+    for (int q = 0; q < 3; q++) {
+        o.perf[q] = SolverPerf{0, 0, 0};
+        if (!o.solD[q]) continue;
+        for (int c = 0; c < N; c++) { x[c] = psi[3 * c + q]; b[c] = source[3 * c + q]; dg[c] = o.diagC[3 * c + q]; }
+        o.perf[q] = solvePCG(o, dg.data(), x.data(), b.data());
+        for (int c = 0; c < N; c++) psi[3 * c + q] = x[c];
+        o.totalInner += o.perf[q].nIter;
+    }
+}
+
+// solidModel::relaxField, SM/solidModel/solidModel.C:823-906 (fixed: D.relax() incl. boundary values)
+void relaxField(s4f_oracle& o, int iCorr) {
+    const int n3 = 3 * o.NB();
+    if (o.ctl.relaxationMethod == S4F_RELAX_FIXED) {
+        double a = o.ctl.fieldRelaxD;
+        if (a != 1.0) for (int i = 0; i < n3; i++) o.D[i] = o.Dprev[i] + a * (o.D[i] - o.Dprev[i]);
+    } else {
+        if ((int)o.aitkenRes.size() != n3) { o.aitkenRes.assign(n3, 0.0); o.aitkenResPrev.assign(n3, 0.0); o.aitkenAlpha.assign(o.NB(), 1.0); }
+        o.aitkenResPrev = o.aitkenRes;
+        for (int i = 0; i < n3; i++) o.aitkenRes[i] = o.Dprev[i] - o.D[i];
+        if (iCorr == 0) { std::fill(o.aitkenAlpha.begin(), o.aitkenAlpha.end(), o.ctl.fieldRelaxD); }
+        else for (int c = 0; c < o.NB(); c++) {
+            double dl[3], num = 0, den = 0;
+            for (int q = 0; q < 3; q++) { dl[q] = o.aitkenResPrev[3 * c + q] - o.aitkenRes[3 * c + q]; num += o.aitkenResPrev[3 * c + q] * dl[q]; den += dl[q] * dl[q]; }
+            double a = o.aitkenAlpha[c] * num / (den + SMALL);
+            o.aitkenAlpha[c] = std::max(0.0, std::min(2.0, a));
+        }
+        for (int c = 0; c < o.NB(); c++) for (int q = 0; q < 3; q++) o.D[3 * c + q] -= o.aitkenAlpha[c] * o.aitkenRes[3 * c + q];
+    }
+}
+
+// solidModel::converged, SM/solidModel/solidModelTemplates.C:27-188 (total approach: incremental()==false
+// for the total-displacement models)
+bool convergedCheck(s4f_oracle& o, int iCorr, s4fgpu_stats* st) {
+    const int N = o.N;
+    double denom = 0, dmax = 0, res = 0;
+    const bool incremental = (o.ctl.solidModel == S4F_MODEL_NONLIN_TL || o.ctl.solidModel == S4F_MODEL_NONLIN_UL);
+    for (int c = 0; c < N; c++) {
+        double a[3], m[3], r[3];
+        for (int q = 0; q < 3; q++) { a[q] = o.D[3 * c + q] - o.Dold[3 * c + q]; m[q] = o.D[3 * c + q]; r[q] = o.D[3 * c + q] - o.Dprev[3 * c + q]; }
+        denom = std::max(denom, incremental ? mag3(m) : mag3(a)); dmax = std::max(dmax, mag3(m)); res = std::max(res, mag3(r));
+    }
+    if (denom < SMALL) denom = std::max(dmax, SMALL);
+    double residualvf = res / denom;
+    double matRes = lawResidual(o);
+    double ir[3] = {o.perf[0].initRes, o.perf[1].initRes, o.perf[2].initRes};
+    double spir = mag3(ir);
+    bool conv = false;
+    if (iCorr > 1 && matRes < o.ctl.materialTolerance) {
+        if (spir < o.ctl.solutionTolerance && residualvf < o.ctl.solutionTolerance) conv = true;
+        else if (residualvf < o.ctl.alternativeTolerance) conv = true;
+        else if (spir < o.ctl.alternativeTolerance) conv = true;
+    }
+    if (st) {
+        for (int q = 0; q < 3; q++) { st->initialResidual[q] = o.perf[q].initRes; st->finalResidual[q] = o.perf[q].finalRes; st->nIterations[q] = o.perf[q].nIter; }
+        st->solverPerfInitRes = spir; st->relResidual = residualvf; st->materialResidual = matRes; st->converged = conv;
+        st->totalInnerIterations = o.totalInner;
+    }
+    return conv;
+}
+
+// one pass of the do-loop body, linGeomTotalDispSolid.C:135-192 / nonLinGeomTotalLagTotalDispSolid.C:195-236
+void outerIteration(s4f_oracle& o, int iCorr) {
+    o.Dprev = o.D;                               // D().storePrevIter()
+    bcUpdateCoeffs(o);                           // fvMatrix ctor -> updateCoeffs
+    if (!o.matrixValid) assembleMatrix(o);       // impKf is constant (update commented out :186-192)
+    assembleSource(o);
+    solveSegregated(o, o.D.data(), o.source.data());
+    bcEvaluate(o);                               // D.correctBoundaryConditions()
+    relaxField(o, iCorr);
+    calcGrad(o);                                 // mechanical().grad(D, gradD)
+    if (o.ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP) updateKinematics(o);
+    lawCorrect(o);                               // mechanical().correct(sigma)
+}
+
+void allocFields(s4f_oracle& o) {
+    const int n = o.NB();
+    auto z = [&](dvec& v, int nc) { if ((int)v.size() != nc * n) v.assign((size_t)nc * n, 0.0); };
+    z(o.D, 3); z(o.Dprev, 3); z(o.Dold, 3); z(o.DoldOld, 3); z(o.gradD, 9); z(o.gradDold, 9); z(o.sigma, 6); z(o.sigmaOld, 6);
+    z(o.epsilon, 6); z(o.sigmaHyd, 1);
+    if ((int)o.Ft.size() != 9 * n) {
+        o.Ft.assign(9 * n, 0.0); o.Finv.assign(9 * n, 0.0); o.Jt.assign(n, 1.0);
+        o.lawF.assign(9 * n, 0.0); o.lawFold.assign(9 * n, 0.0); o.relF.assign(9 * n, 0.0);
+        for (int c = 0; c < n; c++) for (int d = 0; d < 3; d++) { o.Ft[9 * c + 4 * d] = 1; o.Finv[9 * c + 4 * d] = 1; o.lawF[9 * c + 4 * d] = 1; o.lawFold[9 * c + 4 * d] = 1; o.relF[9 * c + 4 * d] = 1; }
+        o.lawJ.assign(n, 1.0); o.lawJold.assign(n, 1.0);
+        o.bEbar.assign(6 * n, 0.0); o.bEbarOld.assign(6 * n, 0.0); o.bEbarTrial.assign(6 * n, 0.0);
+        for (int c = 0; c < n; c++) { for (int d : {0, 3, 5}) { o.bEbar[6 * c + d] = 1; o.bEbarOld[6 * c + d] = 1; o.bEbarTrial[6 * c + d] = 1; } }
+        o.sigmaY.assign(n, 0.0); o.DSigmaY.assign(n, 0.0); o.epsPEq.assign(n, 0.0); o.DEpsPEq.assign(n, 0.0);
+        o.epsPOld.assign(6 * n, 0.0); o.epsPEqOld.assign(n, 0.0); o.sigmaYOld.assign(n, 0.0);
+        o.epsP.assign(6 * n, 0.0); o.DEpsP.assign(6 * n, 0.0); o.DEpsPprev.assign(6 * n, 0.0); o.DLambda.assign(n, 0.0); o.plasticN.assign(6 * n, 0.0);
+    }
+}
+
+void setupLaw(s4f_oracle& o) {
+    const int n = o.NB(), F = o.F, B = o.B;
+    // impK: linearElastic.C:204-245 (2mu+lambda), neoHookeanElastic.C:101-119 and Mises at DLambda=0: 4/3 mu + K
+    double impK = (o.law.kind == S4F_LAW_LINEAR_ELASTIC || o.law.kind == S4F_LAW_LINEAR_ELASTIC_MISES_PLASTIC)
+                      ? 2.0 * o.law.mu + o.law.lambda : (4.0 / 3.0) * o.law.mu + o.law.K;
+    o.impK.assign(n, impK);
+    // impKf = fvc::interpolate(impK), mechanicalModel.C:409-415
+    o.impKf.assign(F + B, 0.0);
+    for (int f = 0; f < F; f++) o.impKf[f] = o.w[f] * o.impK[o.own[f]] + (1 - o.w[f]) * o.impK[o.nei[f]];
+    for (int b = 0; b < B; b++) o.impKf[F + b] = o.impK[o.N + b];
+    o.Hp = 0;
+    if (o.law.nTable == 2) o.Hp = (o.law.tableSigY[1] - o.law.tableSigY[0]) / (o.law.tableEps[1] - o.law.tableEps[0]);
+    if (o.law.nTable >= 1) { std::fill(o.sigmaY.begin(), o.sigmaY.end(), tableLookup(o.law, 0.0)); o.sigmaYOld = o.sigmaY; }
+    o.matrixValid = false;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C API (mirrors include/s4fgpu.h with the s4fo_ prefix)
+// ================================================================================================
+extern "C" {
+
+s4f_oracle* s4fo_create() { return new s4f_oracle(); }
+void s4fo_destroy(s4f_oracle* o) { delete o; }
+const char* s4fo_last_error(s4f_oracle* o) { return o->err.c_str(); }
+
+int s4fo_set_mesh(s4f_oracle* o, int nCells, int nInternalFaces, const int* owner, const int* neighbour, int nPatches,
+                  const int* patchStart, const int* patchSize, const int* patchKind, const int* patchNbrRank,
+                  const int* faceCells, const int* solutionD) {
+    (void)patchNbrRank;
+    o->N = nCells; o->F = nInternalFaces; o->nPatches = nPatches;
+    o->own.assign(owner, owner + o->F); o->nei.assign(neighbour, neighbour + o->F);
+    o->pStart.assign(patchStart, patchStart + nPatches); o->pSize.assign(patchSize, patchSize + nPatches);
+    o->pKind.assign(patchKind, patchKind + nPatches);
+    o->B = 0; for (int p = 0; p < nPatches; p++) o->B = std::max(o->B, patchStart[p] + patchSize[p]);
+    o->faceCells.assign(faceCells, faceCells + o->B);
+    for (int i = 0; i < 3; i++) o->solD[i] = solutionD[i];
+    o->bcKind.assign(nPatches, S4F_BC_SOLID_TRACTION);
+    o->bcValue.assign(3 * o->B, 0.0); o->bcPressure.assign(o->B, 0.0); o->tracGrad.assign(3 * o->B, 0.0);
+    for (int f = 0; f < o->F; f++) if (!(owner[f] < neighbour[f])) { o->err = "owner >= neighbour"; return 1; }
+    return 0;
+}
+
+int s4fo_set_geometry(s4f_oracle* o, const double* C, const double* V, const double* Sf, const double* magSf,
+                      const double* Cf, const double* weights, const double* nod, const double* corr, const double* CnbrB) {
+    const int N = o->N, FB = o->F + o->B;
+    o->C.assign(C, C + 3 * N); o->V.assign(V, V + N); o->Sf.assign(Sf, Sf + 3 * FB); o->magSf.assign(magSf, magSf + FB);
+    o->Cf.assign(Cf, Cf + 3 * FB); o->w.assign(weights, weights + FB); o->nod.assign(nod, nod + FB);
+    o->corr.assign(corr, corr + 3 * FB); o->CnbrB.assign(CnbrB, CnbrB + 3 * o->B);
+    makeLeastSquaresVectors(*o);
+    allocFields(*o);
+    o->matrixValid = false;
+    return 0;
+}
+
+int s4fo_set_law(s4f_oracle* o, const s4fgpu_law* law) { o->law = *law; allocFields(*o); setupLaw(*o); return 0; }
+int s4fo_set_controls(s4f_oracle* o, const s4fgpu_controls* c) { o->ctl = *c; o->matrixValid = false; return 0; }
+
+int s4fo_set_bc(s4f_oracle* o, int patch, int kind, const double* value, const double* pressure) {
+    if (patch < 0 || patch >= o->nPatches) { o->err = "bad patch"; return 1; }
+    o->bcKind[patch] = kind; o->matrixValid = false;
+    const int s = o->pStart[patch], n = o->pSize[patch];
+    for (int i = 0; i < n; i++) {
+        for (int q = 0; q < 3; q++) o->bcValue[3 * (s + i) + q] = value ? value[3 * i + q] : 0.0;
+        o->bcPressure[s + i] = pressure ? pressure[i] : 0.0;
+    }
+    return 0;
+}
+
+static dvec* fieldPtr(s4f_oracle* o, int field, int& ncomp, int& off, int& count) {
+    const int N = o->N, B = o->B, F = o->F;
+    off = 0; count = N;
+    switch (field) {
+        case S4F_FIELD_D: ncomp = 3; return &o->D;
+        case S4F_FIELD_D_OLD: ncomp = 3; return &o->Dold;
+        case S4F_FIELD_D_OLDOLD: ncomp = 3; return &o->DoldOld;
+        case S4F_FIELD_GRAD_D: ncomp = 9; return &o->gradD;
+        case S4F_FIELD_GRAD_D_OLD: ncomp = 9; return &o->gradDold;
+        case S4F_FIELD_SIGMA: ncomp = 6; return &o->sigma;
+        case S4F_FIELD_D_B: ncomp = 3; off = N; count = B; return &o->D;
+        case S4F_FIELD_GRAD_D_B: ncomp = 9; off = N; count = B; return &o->gradD;
+        case S4F_FIELD_SIGMA_B: ncomp = 6; off = N; count = B; return &o->sigma;
+        case S4F_FIELD_SOURCE: ncomp = 3; return &o->source;
+        case S4F_FIELD_DIAG: ncomp = 3; return &o->diagC;
+        case S4F_FIELD_UPPER: ncomp = 1; count = F; return &o->upper;
+        case S4F_FIELD_EPSILON_P_EQ: ncomp = 1; return &o->epsPEq;
+        case S4F_FIELD_SIGMA_Y: ncomp = 1; return &o->sigmaY;
+        case S4F_FIELD_BEBAR: ncomp = 6; return &o->bEbar;
+        case S4F_FIELD_DLAMBDA: ncomp = 1; return &o->DLambda;
+        case S4F_FIELD_J: ncomp = 1; return &o->lawJ;
+        case S4F_FIELD_F: ncomp = 9; return &o->lawF;
+        case S4F_FIELD_DEPSILON_P: ncomp = 6; return &o->DEpsP;
+        case S4F_FIELD_EPSILON_P: ncomp = 6; return &o->epsP;
+        case S4F_FIELD_TRACTION_GRADIENT_B: ncomp = 3; count = B; return &o->tracGrad;
+    }
+    return nullptr;
+}
+int s4fo_upload(s4f_oracle* o, int field, const double* host) {
+    int nc, off, cnt; dvec* v = fieldPtr(o, field, nc, off, cnt);
+    if (!v) { o->err = "bad field"; return 1; }
+    if ((int)v->size() < nc * (off + cnt)) v->resize((size_t)nc * (off + cnt), 0.0);
+    std::memcpy(v->data() + (size_t)nc * off, host, sizeof(double) * nc * cnt); return 0;
+}
+int s4fo_download(s4f_oracle* o, int field, double* host) {
+    int nc, off, cnt; dvec* v = fieldPtr(o, field, nc, off, cnt);
+    if (!v || (int)v->size() < nc * (off + cnt)) { o->err = "bad field / not available"; return 1; }
+    std::memcpy(host, v->data() + (size_t)nc * off, sizeof(double) * nc * cnt); return 0;
+}
+
+// linGeomTotalDispSolid.C:82-84: D.correctBoundaryConditions(); D.storePrevIter(); mechanical().grad(D, gradD)
+int s4fo_initialise(s4f_oracle* o) {
+    allocFields(*o);
+    bcUpdateCoeffs(*o);
+    bcEvaluate(*o);
+    o->Dprev = o->D;
+    calcGrad(*o);
+    if (o->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP) updateKinematics(*o);
+    assembleMatrix(*o);
+    return 0;
+}
+
+int s4fo_new_timestep(s4f_oracle* o, double deltaT) {
+    o->ctl.deltaT0 = o->ctl.deltaT; o->ctl.deltaT = deltaT;
+    o->DoldOld = o->Dold; o->Dold = o->D; o->gradDold = o->gradD; o->sigmaOld = o->sigma;
+    o->lawFold = o->lawF; o->lawJold = o->lawJ; o->bEbarOld = o->bEbar;
+    o->epsPOld = o->epsP; o->epsPEqOld = o->epsPEq; o->sigmaYOld = o->sigmaY;
+    if (o->ctl.d2dt2Scheme != S4F_D2DT2_STEADY_STATE) o->matrixValid = false;
+    return 0;
+}
+
+int s4fo_outer_iteration(s4f_oracle* o, s4fgpu_stats* st) {
+    outerIteration(*o, o->iCorrLast);
+    convergedCheck(*o, o->iCorrLast, st);
+    o->iCorrLast++;
+    if (st) st->nCorr = o->iCorrLast;
+    return 0;
+}
+
+// solidModel::evolve loop: do { ... } while (!converged(iCorr,...) && ++iCorr < nCorr)
+int s4fo_evolve(s4f_oracle* o, s4fgpu_stats* st) {
+    int iCorr = 0; bool conv;
+    s4fgpu_stats loc{}; if (!st) st = &loc;
+    do { outerIteration(*o, iCorr); conv = convergedCheck(*o, iCorr, st); } while (!conv && ++iCorr < o->ctl.nCorrectors);
+    st->nCorr = conv ? iCorr + 1 : iCorr; o->iCorrLast = 0;
+    return 0;
+}
+
+// updateTotalFields: neoHookeanElasticMisesPlastic.C:1526-1536 (history commit)
+int s4fo_update_total_fields(s4f_oracle* o) {
+    if (o->law.kind == S4F_LAW_NEO_HOOKEAN_MISES_PLASTIC) {
+        const int n = o->NB();
+        for (int c = 0; c < n; c++) { o->sigmaY[c] += o->DSigmaY[c]; o->epsPEq[c] += o->DEpsPEq[c]; }
+        for (int i = 0; i < 6 * n; i++) o->epsP[i] += o->DEpsP[i];
+    }
+    return 0;
+}
+
+int s4fo_op_grad(s4f_oracle* o) { calcGrad(*o); if (o->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP) updateKinematics(*o); return 0; }
+int s4fo_op_correct(s4f_oracle* o) { lawCorrect(*o); return 0; }
+int s4fo_op_assemble(s4f_oracle* o) { bcUpdateCoeffs(*o); assembleMatrix(*o); assembleSource(*o); return 0; }
+int s4fo_op_amul(s4f_oracle* o, int cmpt, const double* x, double* y) {
+    if (!o->matrixValid) assembleMatrix(*o);
+    dvec dg(o->N); for (int c = 0; c < o->N; c++) dg[c] = o->diagC[3 * c + cmpt];
+    Amul(*o, dg.data(), x, y); return 0;
+}
+int s4fo_op_solve(s4f_oracle* o, double* psi, const double* source, s4fgpu_stats* st) {
+    if (!o->matrixValid) assembleMatrix(*o);
+    solveSegregated(*o, psi, source);
+    if (st) for (int q = 0; q < 3; q++) { st->initialResidual[q] = o->perf[q].initRes; st->finalResidual[q] = o->perf[q].finalRes; st->nIterations[q] = o->perf[q].nIter; }
+    return 0;
+}
+// least-squares vectors for inspection (lsP [3(F+B)], lsN [3F])
+int s4fo_get_ls_vectors(s4f_oracle* o, double* lsP, double* lsN) {
+    std::memcpy(lsP, o->lsP.data(), sizeof(double) * o->lsP.size());
+    std::memcpy(lsN, o->lsN.data(), sizeof(double) * o->lsN.size()); return 0;
+}
+double s4fo_table_lookup(const s4fgpu_law* law, double x) { return tableLookup(*law, x); }
+
+}  // extern "C"
