@@ -1,0 +1,215 @@
+// s4f_ctx.h -- host-side context of libs4fgpu.so: device-resident mirror of one fvMesh + fields.
+//
+// Index space of every "vol field" on the device (SoA, one array per component, leading dimension ld):
+//   [0, N)            cells of this rank
+//   [N, N+G)          ghost cells = neighbour cells across processor-patch faces (filled by halo exchange)
+//   [N+G, N+G+B)      boundary-face values (one slot per boundary face; processor faces unused)
+// so that OpenFOAM's "field algebra acts on internal field and boundary field alike" becomes one
+// kernel over one index range, and boundary faces can sit in the cell-centric rows as ordinary
+// entries whose column is the boundary-value slot.
+//
+// Rows (cell-centric, atomic-free): SELL-32 ("sliced ELLPACK", slice = one warp of 32 consecutive
+// cells).  Entry (slice s, k, lane) lives at slicePtr[s] + 32*k + lane, so a warp reads every
+// per-entry array fully coalesced.  Entries of a row: internal-face neighbours, processor-face
+// neighbours (ghost columns), boundary faces (boundary-slot columns).  Padding entries have
+// col = row and all coefficients zero.
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/s4fgpu.h"
+
+#define S4F_CHECK_CUDA(ctx, call)                                                              \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                         std::to_string(__LINE__) + ")";                                       \
+            return 2;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+#define S4F_CHECK_NCCL(ctx, call)                                                              \
+    do {                                                                                       \
+        ncclResult_t e_ = (call);                                                              \
+        if (e_ != ncclSuccess) {                                                               \
+            (ctx)->err = std::string(#call) + ": " + ncclGetErrorString(e_);                   \
+            return 3;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+    }
+    cudaError_t alloc(size_t count, bool zero = true) {
+        if (count == n && p) { return zero ? cudaMemset(p, 0, n * sizeof(T)) : cudaSuccess; }
+        release();
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        n = count;
+        return zero ? cudaMemset(p, 0, n * sizeof(T)) : cudaSuccess;
+    }
+    cudaError_t upload(const std::vector<T>& h) {
+        cudaError_t e = alloc(h.size(), false);
+        if (e != cudaSuccess || h.empty()) return e;
+        return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    }
+};
+
+// scalar block of the fused 3-component PCG, one per solve, in device memory.
+// All per-component quantities are [3].
+struct PcgScalars {
+    double part[16];       // finished reduction results of the last reducing kernel (raw sums)
+    double rho[3];         // wArA
+    double rhoOld[3];      // wArAold
+    double wApA[3];
+    double normFactor[3];
+    double initRes[3];
+    double finalRes[3];
+    double avg[3];         // gAverage(psi)
+    double alpha[3], beta[3];
+    int active[3];         // component still iterating
+    int nIter[3];
+    int anyActive;
+    int pad;
+};
+
+// reduction scalars of the outer loop (converged(): solidModelTemplates.C:27-188)
+struct OuterScalars {
+    double maxDelta;       // gMax |D - D.prevIter|
+    double maxIncr;        // gMax |D - D.oldTime|
+    double maxMag;         // gMax |D|
+    double matNum, matDen; // material residual numerator / denominator
+    double maxMagBE;       // gMax |bEbarTrial| (neoHookeanElasticMisesPlastic.C:1030)
+    double minJ, maxJ;
+};
+
+struct s4fgpu_ctx {
+    std::string err;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int numSMs = 148;
+    long long launches = 0;
+
+    // ---- parallel ----
+    ncclComm_t comm = nullptr;
+    int nRanks = 1, rank = 0;
+    double nGlobalCells = -1;
+
+    // ---- host copy of the mesh description ----
+    int N = 0, F = 0, B = 0, G = 0, nPatches = 0;
+    int ld = 0;                       // leading dimension of vol-field component arrays (>= N+G+B)
+    std::vector<int> own, nei, faceCells, pStart, pSize, pKind, pNbr, bcKind;
+    int solD[3] = {1, 1, 1};
+    std::vector<int> ghostOfFace;     // [B] ghost cell index (N+g) for processor faces, -1 otherwise
+    bool meshSet = false, geomSet = false, lawSet = false, ctlSet = false;
+    bool nonOrth = false;
+    std::vector<double> hC, hV, hSf, hMagSf, hCf, hW, hNod, hCorr, hCnbrB;
+
+    s4fgpu_law law{};
+    s4fgpu_controls ctl{};
+    double Hp = 0;                    // linear hardening modulus (2-point table)
+
+    // ---- SELL-32 rows ----
+    int nSlices = 0;
+    long long nEntries = 0;           // padded
+    long long nnzOff = 0;             // true off-diagonal entries (internal + processor faces)
+    DevBuf<int> slicePtr;             // [nSlices+1] (entry offsets, multiples of 32), fits int for < 2^31 entries
+    DevBuf<int> col;                  // [nEntries]
+    DevBuf<double> eW;                // interpolation weight of the row cell's own value
+    DevBuf<double> eSf;               // [3*nEntries] outward area vector (SoA: x | y | z)
+    DevBuf<double> eLs;               // [3*nEntries] least-squares vector (SoA)
+    DevBuf<double> eDn;               // magSf*nonOrthDeltaCoeffs (0 on boundary-face entries)
+    DevBuf<double> eCorr;             // [3*nEntries] magSf*nonOrthCorrectionVector, outward sense (only if nonOrth)
+    DevBuf<double> eA;                // laplacian coefficient impKf*magSf*delta  (= -upper)
+    DevBuf<double> eRc;               // RhieChow compact coefficient gamma_f*magSf*delta
+    DevBuf<double> eGam;              // RhieChow gamma_f
+    DevBuf<double> V, rV;             // cell volumes [ld]
+
+    // ---- boundary faces (B-arrays, SoA) and boundary-cell lists ----
+    DevBuf<int> bFaceCell, bKind;     // [B] ; bKind = S4F_BC_* of the face's patch
+    DevBuf<double> bN, bK, bSf;       // [3B] unit normal, patch correction vector k, area vector
+    DevBuf<double> bDelta, bNod, bMagSf; // [B]
+    DevBuf<double> bcValue, bcPressure, tracGrad, bSn; // [3B],[B],[3B],[3B]
+    DevBuf<int> bcCells, bcPtr, bcFaces; // boundary cells, CSR of their (non-processor) boundary faces
+    int nBCells = 0;
+
+    // ---- halo exchange ----
+    struct Nbr { int rank; int patch; int count; int sendOff; int ghostOff; };
+    std::vector<Nbr> nbrs;
+    DevBuf<int> sendCells;            // [G] local cells adjacent to processor faces, in patch order
+    DevBuf<double> sendBuf, recvBuf;  // [9*G] staging
+
+    // ---- fields (SoA, ld per component) ----
+    DevBuf<double> D, Dprev, Dold, DoldOld;       // 3*ld
+    DevBuf<double> gradD, gradDold;               // 9*ld
+    DevBuf<double> sigma, sigmaOld;               // 6*ld
+    DevBuf<double> impK;                          // ld
+    DevBuf<double> T9;                            // 9*ld: J*Finv & sigma (TL)  [cells + boundary]
+    DevBuf<double> Finv, Jt;                      // 9*ld, ld (TL solver kinematics)
+    // law history
+    DevBuf<double> lawF, lawFold, lawJ, lawJold, bEbar, bEbarOld, sigmaY, sigmaYOld, DSigmaY, epsPEq, epsPEqOld,
+        DEpsPEq, epsP, epsPOld, DEpsP, DEpsPprev, DLambda, plasticN, epsilon;
+    // ---- fvMatrix ----
+    DevBuf<double> diag0;             // ld: sum of laplacian coefficients + d2dt2
+    DevBuf<double> diagC;             // 3*ld: per-component diagonal after addBoundaryDiag
+    DevBuf<double> source;            // 3*ld
+    bool matrixValid = false;
+    // ---- PCG work vectors ----
+    DevBuf<double> pA, wA, rA;        // 3*ld each
+    DevBuf<double> cheb0, cheb1;      // 3*ld polynomial-preconditioner work
+    DevBuf<double> aitRes, aitResPrev, aitAlpha;  // Aitken relaxation state (solidModel.C:842-897)
+    DevBuf<PcgScalars> pcgS;
+    DevBuf<OuterScalars> outS;
+    DevBuf<double> partials;          // per-block partial sums
+    DevBuf<unsigned int> ticket;
+    DevBuf<double> staging;           // AoS <-> SoA staging, 9*max(N,B,F)
+    DevBuf<double> flushBuf;          // L2 flush buffer for time_kernel
+    PcgScalars* hPcgS = nullptr;      // pinned mirrors
+    OuterScalars* hOutS = nullptr;
+    double lambdaMax = 2.0;           // Chebyshev: bound of the Jacobi-scaled spectrum
+
+    int iCorr = 0;
+    long long totalInner = 0;
+    s4fgpu_stats last{};
+
+    int NT() const { return N + G + B; }
+    int bOff() const { return N + G; }
+};
+
+// ---- internal entry points (defined across the .cu files) ----
+int s4f_build_rows(s4fgpu_ctx* c);                   // SELL rows + boundary lists + geometry upload
+int s4f_alloc_fields(s4fgpu_ctx* c);
+int s4f_setup_law(s4fgpu_ctx* c);
+int s4f_assemble_matrix(s4fgpu_ctx* c);
+int s4f_assemble_source(s4fgpu_ctx* c);
+int s4f_bc_update_coeffs(s4fgpu_ctx* c);
+int s4f_bc_evaluate(s4fgpu_ctx* c);
+int s4f_relax_and_residual(s4fgpu_ctx* c, int iCorr);
+int s4f_grad(s4fgpu_ctx* c);
+int s4f_kinematics(s4fgpu_ctx* c);
+int s4f_law_correct(s4fgpu_ctx* c);
+int s4f_solve_segregated(s4fgpu_ctx* c, double* psi, const double* source);   // device SoA pointers
+int s4f_halo_exchange(s4fgpu_ctx* c, double* field, int ncomp);
+int s4f_outer_iteration(s4fgpu_ctx* c, int iCorr);
+int s4f_read_outer_scalars(s4fgpu_ctx* c, s4fgpu_stats* st, bool* converged, int iCorr);
+int s4f_aos_to_soa(s4fgpu_ctx* c, const double* hostAoS, double* devSoA, int count, int ncomp, int offset);
+int s4f_soa_to_aos(s4fgpu_ctx* c, const double* devSoA, double* hostAoS, int count, int ncomp, int offset);
+int s4f_time_pcg_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, double* ms, double* bytes);
+int s4f_time_fv_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, double* ms, double* bytes);
+int s4f_amul_device(s4fgpu_ctx* c, const double* x3, double* w3, int mask);
+int s4f_alloc_model_fields(s4fgpu_ctx* c);
+int s4f_upload_bc(s4fgpu_ctx* c);

@@ -1,0 +1,114 @@
+// s4f_dev.cuh -- device helpers: warp-shuffle grid reductions with a deterministic last-block
+// finish, small tensor algebra in OpenFOAM component order, launch geometry.
+#pragma once
+#include <cuda_runtime.h>
+
+#define S4F_SMALL 1e-15
+#define S4F_BLOCK 256
+
+// grid of persistent blocks: a multiple of the SM count (148 on B200)
+static inline int s4f_grid(int numSMs, long long work, int blocksPerSM = 8) {
+    long long need = (work + S4F_BLOCK - 1) / S4F_BLOCK;
+    long long g = (long long)numSMs * blocksPerSM;
+    if (need < g) g = need;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+struct OpSum { __device__ static double f(double a, double b) { return a + b; } __device__ static double id() { return 0.0; } };
+struct OpMax { __device__ static double f(double a, double b) { return a > b ? a : b; } __device__ static double id() { return -1e300; } };
+
+template <class Op>
+__device__ __forceinline__ double warp_reduce(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = Op::f(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-level reduce of NV values; result valid in thread 0.
+template <int NV, class Op>
+__device__ __forceinline__ void block_reduce(double (&v)[NV]) {
+    __shared__ double sh[NV][S4F_BLOCK / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        double x = warp_reduce<Op>(v[i]);
+        if (lane == 0) sh[i][wid] = x;
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            double x = (lane < (int)(blockDim.x >> 5)) ? sh[i][lane] : Op::id();
+            x = warp_reduce<Op>(x);
+            v[i] = x;
+        }
+    }
+    __syncthreads();
+}
+
+// Grid reduce: every block deposits its NV partials; the last block to arrive (ticket) combines
+// them in a fixed order (deterministic for a fixed grid) and calls fin(tot) from thread 0.
+template <int NV, class Op, class Fin>
+__device__ __forceinline__ void grid_reduce(double (&v)[NV], double* partials, unsigned int* ticket, Fin fin) {
+    block_reduce<NV, Op>(v);
+    __shared__ bool isLast;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) partials[(size_t)i * gridDim.x + blockIdx.x] = v[i];
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        isLast = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (isLast) {
+        __threadfence();
+        double tot[NV];
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            double a = Op::id();
+            for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) a = Op::f(a, __ldcg(&partials[(size_t)i * gridDim.x + b]));
+            tot[i] = a;
+        }
+        block_reduce<NV, Op>(tot);
+        if (threadIdx.x == 0) { *ticket = 0u; fin(tot); }
+    }
+}
+
+// ---- tensor algebra: tensor 9 row-major, symmTensor 6 = XX XY XZ YY YZ ZZ ----------------------
+__device__ __forceinline__ void t_symm(const double* T, double* S) {
+    S[0] = T[0]; S[1] = 0.5 * (T[1] + T[3]); S[2] = 0.5 * (T[2] + T[6]);
+    S[3] = T[4]; S[4] = 0.5 * (T[5] + T[7]); S[5] = T[8];
+}
+__device__ __forceinline__ double s_tr(const double* S) { return S[0] + S[3] + S[5]; }
+__device__ __forceinline__ void s_dev(const double* S, double* D) {
+    const double t = s_tr(S) / 3.0;
+    D[0] = S[0] - t; D[1] = S[1]; D[2] = S[2]; D[3] = S[3] - t; D[4] = S[4]; D[5] = S[5] - t;
+}
+__device__ __forceinline__ double s_magSqr(const double* S) {
+    return S[0] * S[0] + 2 * S[1] * S[1] + 2 * S[2] * S[2] + S[3] * S[3] + 2 * S[4] * S[4] + S[5] * S[5];
+}
+__device__ __forceinline__ double s_det(const double* S) {
+    return S[0] * S[3] * S[5] + S[1] * S[4] * S[2] + S[2] * S[1] * S[4] - S[0] * S[4] * S[4] - S[1] * S[1] * S[5] - S[2] * S[3] * S[2];
+}
+__device__ __forceinline__ double t_det(const double* T) {
+    return T[0] * (T[4] * T[8] - T[5] * T[7]) - T[1] * (T[3] * T[8] - T[5] * T[6]) + T[2] * (T[3] * T[7] - T[4] * T[6]);
+}
+__device__ __forceinline__ void t_inv(const double* T, double* R) {
+    const double d = t_det(T);
+    R[0] = (T[4] * T[8] - T[5] * T[7]) / d; R[1] = (T[2] * T[7] - T[1] * T[8]) / d; R[2] = (T[1] * T[5] - T[2] * T[4]) / d;
+    R[3] = (T[5] * T[6] - T[3] * T[8]) / d; R[4] = (T[0] * T[8] - T[2] * T[6]) / d; R[5] = (T[2] * T[3] - T[0] * T[5]) / d;
+    R[6] = (T[3] * T[7] - T[4] * T[6]) / d; R[7] = (T[1] * T[6] - T[0] * T[7]) / d; R[8] = (T[0] * T[4] - T[1] * T[3]) / d;
+}
+__device__ __forceinline__ void t_mul(const double* A, const double* B, double* R) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) R[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+__device__ __forceinline__ void s_to_t(const double* S, double* T) {
+    T[0] = S[0]; T[1] = S[1]; T[2] = S[2]; T[3] = S[1]; T[4] = S[3]; T[5] = S[4]; T[6] = S[2]; T[7] = S[4]; T[8] = S[5];
+}
+__device__ __forceinline__ void t_transpose(const double* A, double* R) {
+    R[0] = A[0]; R[1] = A[3]; R[2] = A[6]; R[3] = A[1]; R[4] = A[4]; R[5] = A[7]; R[6] = A[2]; R[7] = A[5]; R[8] = A[8];
+}

@@ -1,0 +1,645 @@
+// s4f_fv.cu -- finite-volume face loops as atomic-free cell-centric gathers over the SELL-32 rows:
+//   * assembly of fvm::laplacian(impKf, D) (coefficients once, they only change with impKf),
+//   * the explicit right-hand side: - fvc::laplacian(impKf, D) + fvc::div(sigma) + rho g + Rhie-Chow,
+//   * fvc::grad(D) (least squares / Gauss linear) with the boundary normal-gradient correction,
+//   * the D boundary conditions (solidTraction, fixedDisplacement, solidSymmetry),
+//   * field relaxation and the residual reductions of solidModel::converged().
+// Reference lines are cited at each kernel; the CPU restatement of the same operators in the
+// reference's own LDU face-loop form is oracle/s4f_oracle.cpp.
+#include <cmath>
+
+#include "s4f_ctx.h"
+#include "s4f_dev.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// fvm::laplacian(impKf, D): coefficient per row entry a = impKf_f * magSf_f * nonOrthDeltaCoeffs_f
+// ([OF-ext] gaussLaplacianScheme::fvmLaplacianUncorrected: upper = a, diag = -sum a; the momentum
+// equation "A == B" flips the sign: off-diagonal -a, diagonal +sum a), impKf = linear interpolate of
+// impK (mechanicalModel.C:409-415).  Also the Rhie-Chow face coefficient gamma_f
+// (momentumStabilisation.C:112-150, :198-206).   d2dt2Coeff*V added to the diagonal.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(S4F_BLOCK) k_assemble_laplacian(
+    const int* __restrict__ slicePtr, const int* __restrict__ col, const double* __restrict__ eW, const double* __restrict__ eDn,
+    const double* __restrict__ impK, const double* __restrict__ V, double* __restrict__ eA, double* __restrict__ eRc,
+    double* __restrict__ eGam, double* __restrict__ diag0, int N, int bOff, int nSlices, double stabScale, int stabOn,
+    double d2dt2Coeff) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (int s = warp; s < nSlices; s += nWarps) {
+        const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
+        const int row = s * 32 + lane;
+        const double kP = (row < N) ? impK[row] : 0.0;
+        double sum = 0;
+        for (int k = 0; k < width; k++) {
+            const int e = base + 32 * k + lane;
+            const int cc = col[e];
+            const double w = eW[e], dn = eDn[e];
+            const double kN = impK[cc];
+            const double kf = w * kP + (1.0 - w) * kN;
+            const double a = kf * dn;
+            eA[e] = a;
+            sum += a;
+            double gf = 0.0;
+            if (stabOn && cc < bOff) {   // zero on non-coupled boundary faces
+                gf = w * (stabScale * kP) + (1.0 - w) * (stabScale * kN);
+                if (fabs(kP - kN) > S4F_SMALL) gf = 0.01 * 0.5 * (kP + kN);   // material interface
+            }
+            eGam[e] = gf;
+            eRc[e] = gf * dn;
+        }
+        if (row < N) diag0[row] = sum + d2dt2Coeff * V[row];
+    }
+}
+
+__global__ void k_diag_copy(const double* __restrict__ diag0, double* __restrict__ diagC, int N, int ld) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double d = diag0[i];
+    diagC[i] = d; diagC[(size_t)ld + i] = d; diagC[2 * (size_t)ld + i] = d;
+}
+
+// addBoundaryDiag: internalCoeffs = impKf_b*magSf_b*deltaCoeffs_b for fixedValue, times |n_c| for the
+// symmetry plane ([OF-ext] basicSymmetry snGradTransformDiag), zero for fixedGradient.
+__global__ void k_diag_boundary(const int* __restrict__ bcCells, const int* __restrict__ bcPtr, const int* __restrict__ bcFaces,
+                                const int* __restrict__ bKind, const double* __restrict__ bN, const double* __restrict__ bDelta,
+                                const double* __restrict__ bMagSf, const double* __restrict__ impK, double* __restrict__ diagC,
+                                int nBCells, int B, int bOff, int ld) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nBCells) return;
+    const int P = bcCells[i];
+    double add[3] = {0, 0, 0};
+    for (int j = bcPtr[i]; j < bcPtr[i + 1]; j++) {
+        const int b = bcFaces[j];
+        const int kind = bKind[b];
+        const double gm = impK[bOff + b] * bMagSf[b] * bDelta[b];
+        if (kind == S4F_BC_FIXED_DISPLACEMENT) { add[0] += gm; add[1] += gm; add[2] += gm; }
+        else if (kind == S4F_BC_SOLID_SYMMETRY) {
+            add[0] += gm * fabs(bN[b]); add[1] += gm * fabs(bN[(size_t)B + b]); add[2] += gm * fabs(bN[2 * (size_t)B + b]);
+        }
+    }
+    diagC[P] += add[0]; diagC[(size_t)ld + P] += add[1]; diagC[2 * (size_t)ld + P] += add[2];
+}
+
+// ------------------------------------------------------------------------------------------------
+// updateCoeffs() of the patches (triggered by the fvMatrix constructor):
+//  solidTraction  gradient() = tractionBoundarySnGrad: linGeomTotalDispSolid.C:235-271
+//                 ((t - n p) - (n & (sigma_b - impK gradD_b)))/impK ;  TL form with the deformed normal
+//                 nonLinGeomTotalLagTotalDispSolid.C:284-328
+//  fixedDisplacement  value = totalDisp: fixedDisplacementFvPatchVectorField.C:258-294
+// ------------------------------------------------------------------------------------------------
+__global__ void k_bc_update(const int* __restrict__ bKind, const double* __restrict__ bN, const double* __restrict__ bcValue,
+                            const double* __restrict__ bcPressure, const double* __restrict__ impK, const double* __restrict__ sigma,
+                            const double* __restrict__ gradD, const double* __restrict__ Finv, double* __restrict__ tracGrad,
+                            double* __restrict__ D, int B, int bOff, int ld, int TL) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int kind = bKind[b];
+    const size_t j = (size_t)bOff + b;
+    if (kind == S4F_BC_FIXED_DISPLACEMENT) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) D[(size_t)c * ld + j] = bcValue[(size_t)c * B + b];
+    } else if (kind == S4F_BC_SOLID_TRACTION) {
+        double n[3], t[3], g[9], s[6];
+#pragma unroll
+        for (int c = 0; c < 3; c++) { n[c] = bN[(size_t)c * B + b]; t[c] = bcValue[(size_t)c * B + b]; }
+#pragma unroll
+        for (int q = 0; q < 9; q++) g[q] = gradD[(size_t)q * ld + j];
+#pragma unroll
+        for (int q = 0; q < 6; q++) s[q] = sigma[(size_t)q * ld + j];
+        const double p = bcPressure[b], k = impK[j], rk = 1.0 / k;
+        double out[3];
+        if (!TL) {
+            double M[9]; s_to_t(s, M);
+#pragma unroll
+            for (int q = 0; q < 9; q++) M[q] -= k * g[q];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const double nM = n[0] * M[c] + n[1] * M[3 + c] + n[2] * M[6 + c];
+                out[c] = ((t[c] - n[c] * p) - nM) * rk;
+            }
+        } else {
+            double Fi[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) Fi[q] = Finv[(size_t)q * ld + j];
+            double nc[3];   // Finv.T() & n
+#pragma unroll
+            for (int c = 0; c < 3; c++) nc[c] = Fi[c] * n[0] + Fi[3 + c] * n[1] + Fi[6 + c] * n[2];
+            const double m = sqrt(nc[0] * nc[0] + nc[1] * nc[1] + nc[2] * nc[2]);
+            nc[0] /= m; nc[1] /= m; nc[2] /= m;
+            const double ns[3] = {s[0] * nc[0] + s[1] * nc[1] + s[2] * nc[2], s[1] * nc[0] + s[3] * nc[1] + s[4] * nc[2],
+                                  s[2] * nc[0] + s[4] * nc[1] + s[5] * nc[2]};
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const double ng = n[0] * g[c] + n[1] * g[3 + c] + n[2] * g[6 + c];
+                out[c] = ((t[c] - nc[c] * p) - ns[c] + k * ng) * rk;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) tracGrad[(size_t)c * B + b] = out[c];
+    }
+}
+
+// snGrad() of boundary face b with the registered grad(D) at the face cell:
+//  solidTraction: gradient();  fixedDisplacement: (D_b - (D_P + k & gradD_P)) deltaCoeffs (fixedDisplacement...C:297-326)
+//  solidSymmetry: (transform(I - 2nn, DP) - DP) deltaCoeffs/2  (solidSymmetry...C:148-196)
+__device__ __forceinline__ void bc_sngrad(int kind, int b, int P, int B, int bOff, int ld, const double* __restrict__ bN,
+                                          const double* __restrict__ bK, const double* __restrict__ bDelta,
+                                          const double* __restrict__ tracGrad, const double* __restrict__ D,
+                                          const double* __restrict__ gradD, double* sn, double* kgOut) {
+    if (kind == S4F_BC_SOLID_TRACTION) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) sn[c] = tracGrad[(size_t)c * B + b];
+        if (kgOut) {
+            double k[3] = {bK[b], bK[(size_t)B + b], bK[2 * (size_t)B + b]};
+#pragma unroll
+            for (int c = 0; c < 3; c++) kgOut[c] = k[0] * gradD[(size_t)c * ld + P] + k[1] * gradD[(size_t)(3 + c) * ld + P] + k[2] * gradD[(size_t)(6 + c) * ld + P];
+        }
+        return;
+    }
+    const double k[3] = {bK[b], bK[(size_t)B + b], bK[2 * (size_t)B + b]};
+    const double delta = bDelta[b];
+    double kg[3], DP[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        kg[c] = k[0] * gradD[(size_t)c * ld + P] + k[1] * gradD[(size_t)(3 + c) * ld + P] + k[2] * gradD[(size_t)(6 + c) * ld + P];
+        DP[c] = D[(size_t)c * ld + P] + kg[c];
+        if (kgOut) kgOut[c] = kg[c];
+    }
+    if (kind == S4F_BC_FIXED_DISPLACEMENT) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) sn[c] = (D[(size_t)c * ld + bOff + b] - DP[c]) * delta;
+    } else {
+        const double n[3] = {bN[b], bN[(size_t)B + b], bN[2 * (size_t)B + b]};
+        const double nDP = n[0] * DP[0] + n[1] * DP[1] + n[2] * DP[2];
+#pragma unroll
+        for (int c = 0; c < 3; c++) sn[c] = ((DP[c] - 2.0 * n[c] * nDP) - DP[c]) * (delta / 2.0);
+    }
+}
+
+// snGrad of every boundary face stored for the gradient's boundary correction (uses the OLD grad(D):
+// gradD = fvc::grad(D) is assigned after the evaluation)
+__global__ void k_bc_sngrad_store(const int* __restrict__ bFaceCell, const int* __restrict__ bKind, const double* __restrict__ bN,
+                                  const double* __restrict__ bK, const double* __restrict__ bDelta, const double* __restrict__ tracGrad,
+                                  const double* __restrict__ D, const double* __restrict__ gradD, double* __restrict__ bSn, int B,
+                                  int bOff, int ld) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int kind = bKind[b];
+    if (kind == S4F_BC_PROCESSOR) return;
+    double sn[3];
+    bc_sngrad(kind, b, bFaceCell[b], B, bOff, ld, bN, bK, bDelta, tracGrad, D, gradD, sn, nullptr);
+#pragma unroll
+    for (int c = 0; c < 3; c++) bSn[(size_t)c * B + b] = sn[c];
+}
+
+// evaluate(): solidTraction D_b = D_P + k & gradD_P + gradient()/deltaCoeffs (solidTraction...C:398-463);
+// solidSymmetry D_b = (DP + transform(I-2nn, DP))/2 (solidSymmetry...C:200-260)
+__global__ void k_bc_evaluate(const int* __restrict__ bFaceCell, const int* __restrict__ bKind, const double* __restrict__ bN,
+                              const double* __restrict__ bK, const double* __restrict__ bDelta, const double* __restrict__ tracGrad,
+                              double* __restrict__ D, const double* __restrict__ gradD, int B, int bOff, int ld) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int kind = bKind[b];
+    if (kind != S4F_BC_SOLID_TRACTION && kind != S4F_BC_SOLID_SYMMETRY) return;
+    const int P = bFaceCell[b];
+    const double k[3] = {bK[b], bK[(size_t)B + b], bK[2 * (size_t)B + b]};
+    double DP[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double kg = k[0] * gradD[(size_t)c * ld + P] + k[1] * gradD[(size_t)(3 + c) * ld + P] + k[2] * gradD[(size_t)(6 + c) * ld + P];
+        DP[c] = D[(size_t)c * ld + P] + kg;
+    }
+    if (kind == S4F_BC_SOLID_TRACTION) {
+        const double delta = bDelta[b];
+#pragma unroll
+        for (int c = 0; c < 3; c++) D[(size_t)c * ld + bOff + b] = DP[c] + tracGrad[(size_t)c * B + b] / delta;
+    } else {
+        const double n[3] = {bN[b], bN[(size_t)B + b], bN[2 * (size_t)B + b]};
+        const double nDP = n[0] * DP[0] + n[1] * DP[1] + n[2] * DP[2];
+#pragma unroll
+        for (int c = 0; c < 3; c++) D[(size_t)c * ld + bOff + b] = (DP[c] + (DP[c] - 2.0 * n[c] * nDP)) / 2.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Explicit right-hand side, one gather per cell over its faces:
+//   - V fvc::laplacian(impKf,D) [compact part; the non-orthogonal parts of fvm and fvc cancel]
+//   + V fvc::div(sigma)        [OF-ext] gaussDivScheme + linear:  Sf & (w T_P + (1-w) T_N); boundary Sf_b & T_b
+//   + V rho g + d2dt2 old-time terms
+//   + V RhieChow = sum_f gamma_f [ magSf (delta (D_N-D_P) + corr & gradD_f) - Sf & gradD_f ]   (momentumStabilisation.C:210-217)
+// T is sigma (6 comps, TENSOR9=false) or J Finv & sigma (9 comps, total-Lagrangian, TENSOR9=true).
+// ------------------------------------------------------------------------------------------------
+template <bool TENSOR9, bool STAB, bool NONORTH>
+__global__ void __launch_bounds__(S4F_BLOCK) k_source(
+    const int* __restrict__ slicePtr, const int* __restrict__ col, const double* __restrict__ eA, const double* __restrict__ eW,
+    const double* __restrict__ eSf, const double* __restrict__ eRc, const double* __restrict__ eGam, const double* __restrict__ eCorr,
+    const double* __restrict__ D, const double* __restrict__ T, const double* __restrict__ gradD, const double* __restrict__ V,
+    const double* __restrict__ Dold, const double* __restrict__ DoldOld, double* __restrict__ source, int N, int ld, long long nE,
+    int nSlices, double rhoGx, double rhoGy, double rhoGz, double cOld, double cOldOld) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    constexpr int NT = TENSOR9 ? 9 : 6;
+    for (int s = warp; s < nSlices; s += nWarps) {
+        const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
+        const int row = s * 32 + lane;
+        const int r = (row < N) ? row : 0;
+        double DP[3], TP[NT], gP[9];
+#pragma unroll
+        for (int c = 0; c < 3; c++) DP[c] = D[(size_t)c * ld + r];
+#pragma unroll
+        for (int q = 0; q < NT; q++) TP[q] = T[(size_t)q * ld + r];
+        if (STAB) {
+#pragma unroll
+            for (int q = 0; q < 9; q++) gP[q] = gradD[(size_t)q * ld + r];
+        }
+        double acc[3] = {0, 0, 0};
+        for (int k = 0; k < width; k++) {
+            const long long e = (long long)base + 32 * k + lane;
+            const int cc = col[e];
+            const double a = eA[e], w = eW[e], w1 = 1.0 - w;
+            const double S[3] = {eSf[e], eSf[nE + e], eSf[2 * nE + e]};
+            double dD[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) dD[c] = D[(size_t)c * ld + cc] - DP[c];
+            double Tf[NT];
+#pragma unroll
+            for (int q = 0; q < NT; q++) Tf[q] = w * TP[q] + w1 * T[(size_t)q * ld + cc];
+            double fl[3];
+            if (TENSOR9) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) fl[c] = S[0] * Tf[c] + S[1] * Tf[3 + c] + S[2] * Tf[6 + c];
+            } else {
+                fl[0] = S[0] * Tf[0] + S[1] * Tf[1] + S[2] * Tf[2];
+                fl[1] = S[0] * Tf[1] + S[1] * Tf[3] + S[2] * Tf[4];
+                fl[2] = S[0] * Tf[2] + S[1] * Tf[4] + S[2] * Tf[5];
+            }
+            double st[3] = {0, 0, 0};
+            if (STAB) {
+                const double rc = eRc[e], gam = eGam[e];
+                double m[3] = {-S[0], -S[1], -S[2]};
+                if (NONORTH) { m[0] += eCorr[e]; m[1] += eCorr[nE + e]; m[2] += eCorr[2 * nE + e]; }
+                double gf[9];
+#pragma unroll
+                for (int q = 0; q < 9; q++) gf[q] = w * gP[q] + w1 * gradD[(size_t)q * ld + cc];
+#pragma unroll
+                for (int c = 0; c < 3; c++) st[c] = rc * dD[c] + gam * (m[0] * gf[c] + m[1] * gf[3 + c] + m[2] * gf[6 + c]);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) acc[c] += fl[c] - a * dD[c] + st[c];
+        }
+        if (row < N) {
+            const double v = V[row];
+            const double rg[3] = {rhoGx, rhoGy, rhoGz};
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                double sv = acc[c] + v * rg[c];
+                if (cOld != 0.0) sv += v * (cOld * Dold[(size_t)c * ld + row] - cOldOld * DoldOld[(size_t)c * ld + row]);
+                source[(size_t)c * ld + row] = sv;
+            }
+        }
+    }
+}
+
+// boundary part of the laplacian pair: - impKf_b magSf_b snGrad_b (explicit) + boundaryCoeffs
+// (addBoundarySource), boundaryCoeffs = impKf_b magSf_b gradientBoundaryCoeffs_b with
+//   fixedGradient: gradient();  fixedDisplacement: deltaCoeffs (D_b - k & gradD_P)  (fixedDisplacement...C:328-356)
+//   symmetry [OF-ext] transformFvPatchField: snGrad() + deltaCoeffs |n_c| D_P,c
+__global__ void k_source_boundary(const int* __restrict__ bcCells, const int* __restrict__ bcPtr, const int* __restrict__ bcFaces,
+                                  const int* __restrict__ bKind, const double* __restrict__ bN, const double* __restrict__ bK,
+                                  const double* __restrict__ bDelta, const double* __restrict__ bMagSf, const double* __restrict__ impK,
+                                  const double* __restrict__ tracGrad, const double* __restrict__ D, const double* __restrict__ gradD,
+                                  double* __restrict__ source, int nBCells, int B, int bOff, int ld) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nBCells) return;
+    const int P = bcCells[i];
+    double add[3] = {0, 0, 0};
+    for (int j = bcPtr[i]; j < bcPtr[i + 1]; j++) {
+        const int b = bcFaces[j];
+        const int kind = bKind[b];
+        const double gm = impK[bOff + b] * bMagSf[b];
+        double sn[3], kg[3];
+        bc_sngrad(kind, b, P, B, bOff, ld, bN, bK, bDelta, tracGrad, D, gradD, sn, kg);
+        double gbc[3];
+        if (kind == S4F_BC_SOLID_TRACTION) { gbc[0] = sn[0]; gbc[1] = sn[1]; gbc[2] = sn[2]; }
+        else if (kind == S4F_BC_FIXED_DISPLACEMENT) {
+            const double delta = bDelta[b];
+#pragma unroll
+            for (int c = 0; c < 3; c++) gbc[c] = delta * (D[(size_t)c * ld + bOff + b] - kg[c]);
+        } else {
+            const double delta = bDelta[b];
+#pragma unroll
+            for (int c = 0; c < 3; c++) gbc[c] = sn[c] + delta * fabs(bN[(size_t)c * B + b]) * D[(size_t)c * ld + P];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) add[c] += -gm * sn[c] + gm * gbc[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) source[(size_t)c * ld + P] += add[c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// fvc::grad(D).  Least squares: grad_P = sum_e ls_e (D_e - D_P)  (extendedLeastSquaresGrad.C:103-152 in
+// gather form; boundary faces are row entries whose column is the boundary-value slot).
+// Gauss linear: grad_P = (1/V) sum_e Sf_e (w D_P + (1-w) D_e).     mechanicalModel::grad, mechanicalModel.C:571-582
+// ------------------------------------------------------------------------------------------------
+template <bool GAUSS>
+__global__ void __launch_bounds__(S4F_BLOCK) k_grad(const int* __restrict__ slicePtr, const int* __restrict__ col,
+                                                    const double* __restrict__ eVec /* eLs or eSf */, const double* __restrict__ eW,
+                                                    const double* __restrict__ D, const double* __restrict__ rV,
+                                                    double* __restrict__ gradD, int N, int ld, long long nE, int nSlices) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (int s = warp; s < nSlices; s += nWarps) {
+        const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
+        const int row = s * 32 + lane;
+        const int r = (row < N) ? row : 0;
+        const double DP[3] = {D[r], D[(size_t)ld + r], D[2 * (size_t)ld + r]};
+        double g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 2
+        for (int k = 0; k < width; k++) {
+            const long long e = (long long)base + 32 * k + lane;
+            const int cc = col[e];
+            const double v[3] = {eVec[e], eVec[nE + e], eVec[2 * nE + e]};
+            double d[3];
+            if (GAUSS) {
+                const double w = eW[e];
+#pragma unroll
+                for (int c = 0; c < 3; c++) d[c] = w * DP[c] + (1.0 - w) * D[(size_t)c * ld + cc];
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; c++) d[c] = D[(size_t)c * ld + cc] - DP[c];
+            }
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) g[3 * i + j] += v[i] * d[j];
+        }
+        if (row < N) {
+            const double sc = GAUSS ? rV[row] : 1.0;
+#pragma unroll
+            for (int q = 0; q < 9; q++) gradD[(size_t)q * ld + row] = g[q] * sc;
+        }
+    }
+}
+
+// gaussGrad::correctBoundaryConditions: grad_b = grad_P + n (snGrad_b - n & grad_P)
+__global__ void k_grad_boundary(const int* __restrict__ bFaceCell, const int* __restrict__ bKind, const double* __restrict__ bN,
+                                const double* __restrict__ bSn, double* __restrict__ gradD, int B, int bOff, int ld) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (bKind[b] == S4F_BC_PROCESSOR) return;
+    const int P = bFaceCell[b];
+    const double n[3] = {bN[b], bN[(size_t)B + b], bN[2 * (size_t)B + b]};
+    double g[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) g[q] = gradD[(size_t)q * ld + P];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const double ng = n[0] * g[j] + n[1] * g[3 + j] + n[2] * g[6 + j];
+        const double corr = bSn[(size_t)j * B + b] - ng;
+#pragma unroll
+        for (int i = 0; i < 3; i++) g[3 * i + j] += n[i] * corr;
+    }
+#pragma unroll
+    for (int q = 0; q < 9; q++) gradD[(size_t)q * ld + bOff + b] = g[q];
+}
+
+// ------------------------------------------------------------------------------------------------
+// relaxField (fixed): D = D.prevIter + alpha (D - D.prevIter) on cells and boundary values
+// (solidModel.C:823-906 -> [OF-ext] GeometricField::relax), fused with the three gMax reductions of
+// converged(): solidModelTemplates.C:42-103.
+// ------------------------------------------------------------------------------------------------
+struct FinOuter {
+    OuterScalars* S;
+    __device__ void operator()(const double* tot) const { S->maxDelta = tot[0]; S->maxIncr = tot[1]; S->maxMag = tot[2]; }
+};
+__global__ void __launch_bounds__(S4F_BLOCK) k_relax_residual(double* __restrict__ D, const double* __restrict__ Dprev,
+                                                              const double* __restrict__ Dold, int N, int bOff, int B, int ld,
+                                                              double alpha, OuterScalars* S, double* partials, unsigned int* ticket) {
+    double v[3] = {0, 0, 0};
+    const int total = N + B;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int i = (t < N) ? t : bOff + (t - N);
+        double d[3], dp[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            dp[c] = Dprev[(size_t)c * ld + i];
+            d[c] = D[(size_t)c * ld + i];
+            if (alpha != 1.0) { d[c] = dp[c] + alpha * (d[c] - dp[c]); D[(size_t)c * ld + i] = d[c]; }
+        }
+        if (t < N) {
+            const double o[3] = {Dold[i], Dold[(size_t)ld + i], Dold[2 * (size_t)ld + i]};
+            const double a = sqrt((d[0] - dp[0]) * (d[0] - dp[0]) + (d[1] - dp[1]) * (d[1] - dp[1]) + (d[2] - dp[2]) * (d[2] - dp[2]));
+            const double bb = sqrt((d[0] - o[0]) * (d[0] - o[0]) + (d[1] - o[1]) * (d[1] - o[1]) + (d[2] - o[2]) * (d[2] - o[2]));
+            const double m = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            v[0] = fmax(v[0], a); v[1] = fmax(v[1], bb); v[2] = fmax(v[2], m);
+        }
+    }
+    grid_reduce<3, OpMax>(v, partials, ticket, FinOuter{S});
+}
+
+// Aitken relaxation (solidModel.C:842-897): cell-wise alpha, incl. boundary values
+__global__ void __launch_bounds__(S4F_BLOCK) k_relax_aitken(double* __restrict__ D, const double* __restrict__ Dprev,
+                                                            const double* __restrict__ Dold, double* __restrict__ res,
+                                                            double* __restrict__ resPrev, double* __restrict__ aAlpha, int N, int bOff,
+                                                            int B, int ld, int first, double alpha0, OuterScalars* S, double* partials,
+                                                            unsigned int* ticket) {
+    double v[3] = {0, 0, 0};
+    const int total = N + B;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int i = (t < N) ? t : bOff + (t - N);
+        double d[3], dp[3], rn[3], rp[3];
+        double num = 0, den = 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const size_t j = (size_t)c * ld + i;
+            dp[c] = Dprev[j]; d[c] = D[j];
+            rp[c] = res[j];               // aitkenResidual_.storePrevIter()
+            rn[c] = dp[c] - d[c];
+            const double dl = rp[c] - rn[c];
+            num += rp[c] * dl; den += dl * dl;
+        }
+        double a;
+        if (first) a = alpha0;
+        else { a = aAlpha[i] * num / (den + S4F_SMALL); a = fmax(0.0, fmin(2.0, a)); }
+        aAlpha[i] = a;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const size_t j = (size_t)c * ld + i;
+            resPrev[j] = rp[c]; res[j] = rn[c];
+            d[c] -= a * rn[c];
+            D[j] = d[c];
+        }
+        if (t < N) {
+            const double o[3] = {Dold[i], Dold[(size_t)ld + i], Dold[2 * (size_t)ld + i]};
+            const double x = sqrt((d[0] - dp[0]) * (d[0] - dp[0]) + (d[1] - dp[1]) * (d[1] - dp[1]) + (d[2] - dp[2]) * (d[2] - dp[2]));
+            const double bb = sqrt((d[0] - o[0]) * (d[0] - o[0]) + (d[1] - o[1]) * (d[1] - o[1]) + (d[2] - o[2]) * (d[2] - o[2]));
+            const double m = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            v[0] = fmax(v[0], x); v[1] = fmax(v[1], bb); v[2] = fmax(v[2], m);
+        }
+    }
+    grid_reduce<3, OpMax>(v, partials, ticket, FinOuter{S});
+}
+
+}  // namespace
+
+// ================================================================================================
+// host drivers
+// ================================================================================================
+
+static double d2dt2_diag_coeff(const s4fgpu_ctx* c, double* cOld, double* cOldOld) {
+    *cOld = 0; *cOldOld = 0;
+    if (c->ctl.d2dt2Scheme != S4F_D2DT2_EULER) return 0.0;
+    // [OF-ext] EulerD2dt2Scheme::fvmD2dt2 with variable deltaT
+    const double dt = c->ctl.deltaT, dt0 = c->ctl.deltaT0 > 0 ? c->ctl.deltaT0 : dt;
+    const double coefft = (dt + dt0) / (2 * dt), coefft00 = (dt + dt0) / (2 * dt0), rDeltaT2 = 4.0 / ((dt + dt0) * (dt + dt0));
+    *cOld = rDeltaT2 * c->law.rho * (coefft + coefft00);
+    *cOldOld = rDeltaT2 * c->law.rho * coefft00;
+    return coefft * rDeltaT2 * c->law.rho;
+}
+
+int s4f_upload_bc(s4fgpu_ctx* c) {
+    std::vector<int> kinds(std::max(c->B, 1), S4F_BC_SOLID_TRACTION);
+    for (int p = 0; p < c->nPatches; p++)
+        for (int i = 0; i < c->pSize[p]; i++) kinds[c->pStart[p] + i] = (c->pKind[p] == S4F_PATCH_PROCESSOR) ? S4F_BC_PROCESSOR : c->bcKind[p];
+    S4F_CHECK_CUDA(c, c->bKind.upload(kinds));
+    return 0;
+}
+
+int s4f_assemble_matrix(s4fgpu_ctx* c) {
+    double cOld, cOldOld;
+    const double dcoef = d2dt2_diag_coeff(c, &cOld, &cOldOld);
+    const int gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
+    k_assemble_laplacian<<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eW.p, c->eDn.p, c->impK.p, c->V.p, c->eA.p, c->eRc.p,
+                                                             c->eGam.p, c->diag0.p, c->N, c->bOff(), c->nSlices, c->ctl.stabScaleFactor,
+                                                             c->ctl.stabilisation == S4F_STAB_RHIE_CHOW ? 1 : 0, dcoef);
+    k_diag_copy<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->diag0.p, c->diagC.p, c->N, c->ld);
+    c->launches += 2;
+    if (c->nBCells > 0) {
+        k_diag_boundary<<<(c->nBCells + 127) / 128, 128, 0, c->stream>>>(c->bcCells.p, c->bcPtr.p, c->bcFaces.p, c->bKind.p, c->bN.p, c->bDelta.p,
+                                                                       c->bMagSf.p, c->impK.p, c->diagC.p, c->nBCells, c->B, c->bOff(), c->ld);
+        c->launches++;
+    }
+    c->matrixValid = true;
+    S4F_CHECK_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int s4f_bc_update_coeffs(s4fgpu_ctx* c) {
+    if (c->B == 0) return 0;
+    const int TL = c->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP;
+    k_bc_update<<<(c->B + 127) / 128, 128, 0, c->stream>>>(c->bKind.p, c->bN.p, c->bcValue.p, c->bcPressure.p, c->impK.p, c->sigma.p, c->gradD.p,
+                                                          c->Finv.p, c->tracGrad.p, c->D.p, c->B, c->bOff(), c->ld, TL);
+    c->launches++;
+    return 0;
+}
+
+int s4f_bc_evaluate(s4fgpu_ctx* c) {
+    if (c->B == 0) return 0;
+    k_bc_evaluate<<<(c->B + 127) / 128, 128, 0, c->stream>>>(c->bFaceCell.p, c->bKind.p, c->bN.p, c->bK.p, c->bDelta.p, c->tracGrad.p, c->D.p,
+                                                            c->gradD.p, c->B, c->bOff(), c->ld);
+    c->launches++;
+    return 0;
+}
+
+template <bool T9>
+static void launch_source(s4fgpu_ctx* c, const double* T, double cOld, double cOldOld) {
+    const int gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
+    const bool stab = c->ctl.stabilisation == S4F_STAB_RHIE_CHOW;
+    const double rg[3] = {c->law.rho * c->ctl.g[0], c->law.rho * c->ctl.g[1], c->law.rho * c->ctl.g[2]};
+#define S4F_LAUNCH_SRC(STAB, NO)                                                                                                   \
+    k_source<T9, STAB, NO><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->eW.p, c->eSf.p, c->eRc.p, c->eGam.p, \
+                                                               c->eCorr.p, c->D.p, T, c->gradD.p, c->V.p, c->Dold.p, c->DoldOld.p,     \
+                                                               c->source.p, c->N, c->ld, c->nEntries, c->nSlices, rg[0], rg[1], rg[2], \
+                                                               cOld, cOldOld)
+    if (stab && c->nonOrth) S4F_LAUNCH_SRC(true, true);
+    else if (stab) S4F_LAUNCH_SRC(true, false);
+    else S4F_LAUNCH_SRC(false, false);
+#undef S4F_LAUNCH_SRC
+    c->launches++;
+}
+
+int s4f_assemble_source(s4fgpu_ctx* c) {
+    double cOld, cOldOld;
+    d2dt2_diag_coeff(c, &cOld, &cOldOld);
+    if (c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP) launch_source<false>(c, c->sigma.p, cOld, cOldOld);
+    else launch_source<true>(c, c->T9.p, cOld, cOldOld);
+    if (c->nBCells > 0) {
+        k_source_boundary<<<(c->nBCells + 127) / 128, 128, 0, c->stream>>>(c->bcCells.p, c->bcPtr.p, c->bcFaces.p, c->bKind.p, c->bN.p, c->bK.p,
+                                                                         c->bDelta.p, c->bMagSf.p, c->impK.p, c->tracGrad.p, c->D.p, c->gradD.p,
+                                                                         c->source.p, c->nBCells, c->B, c->bOff(), c->ld);
+        c->launches++;
+    }
+    S4F_CHECK_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int s4f_grad(s4fgpu_ctx* c) {
+    const int gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
+    if (c->B > 0) {
+        k_bc_sngrad_store<<<(c->B + 127) / 128, 128, 0, c->stream>>>(c->bFaceCell.p, c->bKind.p, c->bN.p, c->bK.p, c->bDelta.p, c->tracGrad.p, c->D.p,
+                                                                    c->gradD.p, c->bSn.p, c->B, c->bOff(), c->ld);
+        c->launches++;
+    }
+    if (c->ctl.gradScheme == S4F_GRAD_GAUSS_LINEAR)
+        k_grad<true><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eSf.p, c->eW.p, c->D.p, c->rV.p, c->gradD.p, c->N, c->ld, c->nEntries, c->nSlices);
+    else
+        k_grad<false><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eLs.p, c->eW.p, c->D.p, c->rV.p, c->gradD.p, c->N, c->ld, c->nEntries, c->nSlices);
+    c->launches++;
+    if (c->B > 0) {
+        k_grad_boundary<<<(c->B + 127) / 128, 128, 0, c->stream>>>(c->bFaceCell.p, c->bKind.p, c->bN.p, c->bSn.p, c->gradD.p, c->B, c->bOff(), c->ld);
+        c->launches++;
+    }
+    S4F_CHECK_CUDA(c, cudaGetLastError());
+    return s4f_halo_exchange(c, c->gradD.p, 9);
+}
+
+int s4f_relax_and_residual(s4fgpu_ctx* c, int iCorr) {
+    const int grid = s4f_grid(c->numSMs, c->N + c->B);
+    if (c->ctl.relaxationMethod == S4F_RELAX_AITKEN) {
+        const size_t ld = c->ld;
+        if (c->aitRes.n != 3 * ld) { S4F_CHECK_CUDA(c, c->aitRes.alloc(3 * ld)); S4F_CHECK_CUDA(c, c->aitResPrev.alloc(3 * ld)); S4F_CHECK_CUDA(c, c->aitAlpha.alloc(ld)); }
+        k_relax_aitken<<<grid, S4F_BLOCK, 0, c->stream>>>(c->D.p, c->Dprev.p, c->Dold.p, c->aitRes.p, c->aitResPrev.p, c->aitAlpha.p, c->N, c->bOff(), c->B,
+                                                         c->ld, iCorr == 0, c->ctl.fieldRelaxD, c->outS.p, c->partials.p, c->ticket.p);
+    } else {
+        k_relax_residual<<<grid, S4F_BLOCK, 0, c->stream>>>(c->D.p, c->Dprev.p, c->Dold.p, c->N, c->bOff(), c->B, c->ld, c->ctl.fieldRelaxD,
+                                                           c->outS.p, c->partials.p, c->ticket.p);
+    }
+    c->launches++;
+    if (c->nRanks > 1) S4F_CHECK_NCCL(c, ncclAllReduce((double*)c->outS.p, (double*)c->outS.p, 3, ncclDouble, ncclMax, c->comm, c->stream));
+    S4F_CHECK_CUDA(c, cudaGetLastError());
+    return s4f_halo_exchange(c, c->D.p, 3);
+}
+
+// ---- timing of the face-loop kernels (bench.py roofline) ----------------------------------------
+int s4f_time_fv_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, double* msOut, double* bytesOut) {
+    if (flushL2 && c->flushBuf.n < (size_t)48 * 1024 * 1024) S4F_CHECK_CUDA(c, c->flushBuf.alloc((size_t)48 * 1024 * 1024));
+    cudaEvent_t e0, e1;
+    S4F_CHECK_CUDA(c, cudaEventCreate(&e0)); S4F_CHECK_CUDA(c, cudaEventCreate(&e1));
+    double total = 0;
+    for (int r = -3; r < reps; r++) {
+        if (flushL2) S4F_CHECK_CUDA(c, cudaMemsetAsync(c->flushBuf.p, 0, c->flushBuf.n * sizeof(double), c->stream));
+        S4F_CHECK_CUDA(c, cudaEventRecord(e0, c->stream));
+        int rc = 0;
+        if (kernel == S4F_KERNEL_GRAD) rc = s4f_grad(c);
+        else if (kernel == S4F_KERNEL_LAW) rc = s4f_law_correct(c);
+        else rc = s4f_assemble_source(c);
+        if (rc) return rc;
+        S4F_CHECK_CUDA(c, cudaEventRecord(e1, c->stream));
+        S4F_CHECK_CUDA(c, cudaEventSynchronize(e1));
+        float ms; S4F_CHECK_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
+        if (r >= 0) total += ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *msOut = total / reps;
+    const double N = c->N, nnz = (double)c->nnzOff + (c->B - c->G);   // row entries incl. boundary faces
+    if (kernel == S4F_KERNEL_GRAD) *bytesOut = 24 * N + nnz * (4 + 24) + 72 * N + 0.125 * N;                 // D, (col, ls), gradD out
+    else if (kernel == S4F_KERNEL_LAW) *bytesOut = (72 + 48) * N;                                              // gradD in, sigma out (Hooke)
+    else *bytesOut = (24 + 48 + 72) * N + nnz * (4 + 8 + 8 + 24 + 8 + 8) + 8 * N + 24 * N + 0.125 * N;        // D,sigma,gradD | col,a,w,Sf,rc,gam | V | out
+    return 0;
+}

@@ -1,0 +1,400 @@
+// s4f_law.cu -- per-cell (and per-boundary-face) mechanicalLaw stress update, one thread per
+// field entry, all whole-field temporaries of the reference fused away:
+//   linearElastic                    ML/linearGeometryLaws/linearElastic/linearElastic.C:318-339
+//   neoHookeanElastic                ML/nonLinearGeometryLaws/neoHookeanElastic/neoHookeanElastic.C:275-303
+//   neoHookeanElasticMisesPlastic    ML/nonLinearGeometryLaws/neoHookeanElasticMisesPlastic/...C:991-1223
+//   linearElasticMisesPlastic        ML/linearGeometryLaws/linearElasticMisesPlastic/...C:953-1078
+// plus the total-Lagrangian flux tensor J Finv & sigma (nonLinGeomTotalLagTotalDispSolid.C:206, :225-232).
+// The index set is cells [0,N) and boundary-value slots [bOff, bOff+B): OpenFOAM's field algebra
+// evaluates the law on the boundary patches too (explicit loops :1120-1193 for the plastic law).
+#include <cmath>
+
+#include "s4f_ctx.h"
+#include "s4f_dev.cuh"
+
+namespace {
+
+struct HardeningTable { int n; double eps[64]; double sig[64]; };
+
+// s4f interpolationTable<scalar>::operator() with outOfBounds clamp, NUM/interpolationTable/interpolationTable.C:493-632
+__device__ __forceinline__ double table_lookup(const HardeningTable& T, double x) {
+    const int n = T.n;
+    if (n <= 1) return T.sig[0];
+    if (x < T.eps[0]) return T.sig[0];
+    if (x >= T.eps[n - 1]) return T.sig[n - 1];
+    int lo = 0, hi = 0;
+    for (int i = 0; i < n; i++) {
+        if (x >= T.eps[i]) { lo = hi = i; } else { hi = i; break; }
+    }
+    if (lo == hi) return T.sig[hi];
+    return T.sig[lo] + (T.sig[hi] - T.sig[lo]) * (x - T.eps[lo]) / (T.eps[hi] - T.eps[lo]);
+}
+
+#define SQRT23 0.81649658092772603   // sqrt(2/3)
+
+__device__ __forceinline__ double cur_yield(const HardeningTable& T, double epsPEq, double J) {
+    return J * table_lookup(T, fmax(epsPEq, S4F_SMALL));                       // curYieldStress :139-150
+}
+__device__ __forceinline__ double yield_fn(const HardeningTable& T, double epsOld, double magS, double DLambda, double muBar, double J) {
+    return magS - 2 * muBar * DLambda - SQRT23 * cur_yield(T, epsOld + SQRT23 * DLambda, J);   // yieldFunction :153-183
+}
+// newtonLoop :186-247 (LoopTol 1e-8, MaxNewtonIter 200, finiteDiff 0.25e-6)
+__device__ void newton_loop(const HardeningTable& T, double& DLambda, double& curSigmaY, double epsOld, double magS, double muBar,
+                            double J, double maxMagDEps) {
+    int i = 0;
+    double fTrial = yield_fn(T, epsOld, magS, DLambda, muBar, J);
+    double residual = 1.0;
+    do {
+        const double fStep = yield_fn(T, epsOld, magS, DLambda + 0.25e-6, muBar, J);
+        const double deriv = (fStep - fTrial) / 0.25e-6;
+        residual = fTrial / deriv;
+        DLambda -= residual;
+        residual /= maxMagDEps;
+        fTrial = yield_fn(T, epsOld, magS, DLambda, muBar, J);
+    } while ((fabs(residual) > 1e-8) && ++i < 200);
+    curSigmaY = cur_yield(T, epsOld + SQRT23 * DLambda, J) / J;
+}
+// Ibar: Rubin-Attia cubic enforcing det(bEbar) = 1, :250-395
+__device__ __forceinline__ double ibar_of(const double* devB) {
+    const double detd = s_det(devB), fac1 = 2.0 * s_magSqr(devB) / 3.0;
+    double alpha1;
+    if (fabs(fac1) < S4F_SMALL) alpha1 = 3.0;
+    else {
+        const double fac2 = (4.0 * (1.0 - detd)) / pow(fac1, 1.5);
+        if (fac2 >= 1.0) alpha1 = 3.0 * sqrt(fac1) * cosh(acosh(fac2) / 3.0);
+        else alpha1 = 3.0 * sqrt(fac1) * cos(acos(fac2) / 3.0);
+    }
+    return alpha1 / 3.0;
+}
+
+__device__ __forceinline__ int field_index(int t, int N, int bOff) { return (t < N) ? t : bOff + (t - N); }
+
+template <int NC>
+__device__ __forceinline__ void ld_soa(const double* __restrict__ f, int ld, int i, double* v) {
+#pragma unroll
+    for (int q = 0; q < NC; q++) v[q] = f[(size_t)q * ld + i];
+}
+template <int NC>
+__device__ __forceinline__ void st_soa(double* __restrict__ f, int ld, int i, const double* v) {
+#pragma unroll
+    for (int q = 0; q < NC; q++) f[(size_t)q * ld + i] = v[q];
+}
+
+// ---- linearElastic: epsilon = symm(gradD); sigma = 2 mu dev(eps) + K tr(eps) I + sigma0 ---------
+struct S6 { double v[6]; };
+__global__ void __launch_bounds__(S4F_BLOCK) k_law_linear_elastic(const double* __restrict__ gradD, double* __restrict__ sigma, int N,
+                                                                  int bOff, int B, int ld, double mu, double K, S6 sigma0) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N + B; t += gridDim.x * blockDim.x) {
+        const int i = field_index(t, N, bOff);
+        double g[9], e[6], de[6], s[6];
+        ld_soa<9>(gradD, ld, i, g);
+        t_symm(g, e);
+        const double sh = K * s_tr(e);
+        s_dev(e, de);
+#pragma unroll
+        for (int q = 0; q < 6; q++) s[q] = 2.0 * mu * de[q] + sigma0.v[q];
+        s[0] += sh; s[3] += sh; s[5] += sh;
+        st_soa<6>(sigma, ld, i, s);
+    }
+}
+
+// ---- neoHookeanElastic ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(S4F_BLOCK) k_law_neo_hookean(const double* __restrict__ gradD, double* __restrict__ sigma,
+                                                               double* __restrict__ Jout, int N, int bOff, int B, int ld, double mu, double K) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N + B; t += gridDim.x * blockDim.x) {
+        const int i = field_index(t, N, bOff);
+        double g[9], Fm[9], FT[9], FFT[9], b[6], s[6];
+        ld_soa<9>(gradD, ld, i, g);
+        t_transpose(g, Fm); Fm[0] += 1; Fm[4] += 1; Fm[8] += 1;          // F = I + gradD.T()  mechanicalLaw.C:1130-1135
+        const double J = t_det(Fm);
+        t_transpose(Fm, FT); t_mul(Fm, FT, FFT); t_symm(FFT, b);
+        const double sc = pow(J, -2.0 / 3.0);
+#pragma unroll
+        for (int q = 0; q < 6; q++) b[q] *= sc;
+        s_dev(b, s);
+        const double sh = 0.5 * K * (pow(J, 2.0) - 1.0);
+        const double rJ = 1.0 / J;
+#pragma unroll
+        for (int q = 0; q < 6; q++) s[q] *= mu;
+        s[0] += sh; s[3] += sh; s[5] += sh;
+#pragma unroll
+        for (int q = 0; q < 6; q++) s[q] *= rJ;
+        st_soa<6>(sigma, ld, i, s);
+        Jout[i] = J;
+    }
+}
+
+// ---- neoHookeanElasticMisesPlastic ---------------------------------------------------------------
+// trial state shared by the two passes: F, J, relF = F & inv(F.old), relFbar, bEbarTrial = transform(relFbar, bEbar.old)
+__device__ __forceinline__ void mises_trial(const double* __restrict__ gradD, const double* __restrict__ Fold, const double* __restrict__ Jold,
+                                            const double* __restrict__ bEbarOld, int ld, int i, double* Fm, double& J, double* bt) {
+    double g[9], Fo[9], Fi[9], relF[9], bo6[6], bo[9], t1[9], rT[9], t2[9];
+    ld_soa<9>(gradD, ld, i, g);
+    t_transpose(g, Fm); Fm[0] += 1; Fm[4] += 1; Fm[8] += 1;
+    ld_soa<9>(Fold, ld, i, Fo);
+    t_inv(Fo, Fi); t_mul(Fm, Fi, relF);
+    J = t_det(Fm);
+    const double relJ = J / Jold[i];
+    const double sc = pow(relJ, -1.0 / 3.0);
+#pragma unroll
+    for (int q = 0; q < 9; q++) relF[q] *= sc;
+    ld_soa<6>(bEbarOld, ld, i, bo6);
+    s_to_t(bo6, bo); t_mul(relF, bo, t1); t_transpose(relF, rT); t_mul(t1, rT, t2);
+    t_symm(t2, bt);
+}
+
+struct FinMaxBE { OuterScalars* S; __device__ void operator()(const double* tot) const { S->maxMagBE = tot[0]; } };
+__global__ void __launch_bounds__(S4F_BLOCK) k_mises_max_be(const double* __restrict__ gradD, const double* __restrict__ Fold,
+                                                            const double* __restrict__ Jold, const double* __restrict__ bEbarOld, int N, int ld,
+                                                            OuterScalars* S, double* partials, unsigned int* ticket) {
+    double v[1] = {0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {   // gMax over the internal field :1030
+        double Fm[9], J, bt[6];
+        mises_trial(gradD, Fold, Jold, bEbarOld, ld, i, Fm, J, bt);
+        v[0] = fmax(v[0], sqrt(s_magSqr(bt)));
+    }
+    grid_reduce<1, OpMax>(v, partials, ticket, FinMaxBE{S});
+}
+
+struct FinMat { OuterScalars* S; __device__ void operator()(const double* tot) const { S->matNum = tot[0]; S->matDen = tot[1]; } };
+
+struct MisesPtrs {
+    const double* gradD; const double* Fold; const double* Jold; const double* bEbarOld;
+    const double* sigmaY; const double* epsPEq;
+    double* F; double* J; double* bEbar; double* sigma; double* DSigmaY; double* DEpsPEq; double* DEpsP; double* DEpsPprev;
+    double* DLambda; double* plasticN;
+};
+__global__ void __launch_bounds__(S4F_BLOCK) k_law_mises(MisesPtrs p, int N, int bOff, int B, int ld, double mu, double K, double Hp,
+                                                         int consistent, double relax, HardeningTable T, OuterScalars* S,
+                                                         double* partials, unsigned int* ticket) {
+    const bool nonLinearPlasticity = T.n > 2;
+    const double magHp = fabs(Hp);
+    const double maxMagBE = fmax(S->maxMagBE, S4F_SMALL);
+    double v[2] = {0, 0};
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N + B; t += gridDim.x * blockDim.x) {
+        const int i = field_index(t, N, bOff);
+        double Fm[9], J, bt[6];
+        mises_trial(p.gradD, p.Fold, p.Jold, p.bEbarOld, ld, i, Fm, J, bt);
+        double dv[6], sT[6];
+        s_dev(bt, dv);
+#pragma unroll
+        for (int q = 0; q < 6; q++) sT[q] = mu * dv[q];
+        const double Ibar = s_tr(bt) / 3.0, muBar = Ibar * mu;
+        const double sigY = p.sigmaY[i];
+        const double magS = sqrt(s_magSqr(sT));
+        const double fTrial = magS - SQRT23 * J * sigY;
+        double pn[6];
+        ld_soa<6>(p.plasticN, ld, i, pn);
+        if (magS > S4F_SMALL) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) pn[q] = sT[q] / magS;
+        }
+        double DLambda = p.DLambda[i], DSigY = p.DSigmaY[i];
+        if (fTrial < S4F_SMALL) { DSigY = 0; DLambda = 0; }
+        else if (nonLinearPlasticity) {
+            double curSigmaY = 0;
+            newton_loop(T, DLambda, curSigmaY, p.epsPEq[i], magS, muBar, J, maxMagBE);
+            DSigY = curSigmaY - sigY;
+        } else {
+            DLambda = fTrial / (2 * muBar);
+            if (magHp > S4F_SMALL) { DLambda /= 1.0 + Hp / (3 * muBar); DSigY = SQRT23 * DLambda * Hp; }
+        }
+        double prev[6], dep[6], s[6], devB[6];
+        ld_soa<6>(p.DEpsP, ld, i, prev);                 // DEpsilonP_.storePrevIter()
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            double x = Ibar * DLambda * pn[q];
+            if (relax != 1.0) x = prev[q] + relax * (x - prev[q]);   // DEpsilonP_.relax()
+            dep[q] = x;
+            s[q] = sT[q] - 2 * mu * x;
+            devB[q] = s[q] / mu;
+        }
+        const double Ib = consistent ? ibar_of(devB) : Ibar;
+        double be[6];
+#pragma unroll
+        for (int q = 0; q < 6; q++) be[q] = devB[q];
+        be[0] += Ib; be[3] += Ib; be[5] += Ib;
+        const double sh = 0.5 * K * (pow(J, 2.0) - 1.0);
+        s[0] += sh; s[3] += sh; s[5] += sh;
+        const double rJ = 1.0 / J;
+#pragma unroll
+        for (int q = 0; q < 6; q++) s[q] *= rJ;
+        st_soa<9>(p.F, ld, i, Fm); p.J[i] = J;
+        st_soa<6>(p.bEbar, ld, i, be); st_soa<6>(p.sigma, ld, i, s);
+        st_soa<6>(p.DEpsPprev, ld, i, prev); st_soa<6>(p.DEpsP, ld, i, dep); st_soa<6>(p.plasticN, ld, i, pn);
+        p.DLambda[i] = DLambda; p.DSigmaY[i] = DSigY; p.DEpsPEq[i] = SQRT23 * DLambda;
+        if (t < N) {   // residual(): :1502-1521, internal field
+            double d[6];
+#pragma unroll
+            for (int q = 0; q < 6; q++) d[q] = dep[q] - prev[q];
+            v[0] = fmax(v[0], sqrt(s_magSqr(d)));
+            v[1] = fmax(v[1], S4F_SMALL + sqrt(s_magSqr(prev)));
+        }
+    }
+    grid_reduce<2, OpMax>(v, partials, ticket, FinMat{S});
+}
+
+// ---- linearElasticMisesPlastic ----------------------------------------------------------------------
+__global__ void __launch_bounds__(S4F_BLOCK) k_lin_mises_max_eps(const double* __restrict__ gradD, int N, int ld, OuterScalars* S,
+                                                                 double* partials, unsigned int* ticket) {
+    double v[1] = {0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        double g[9], e[6];
+        ld_soa<9>(gradD, ld, i, g); t_symm(g, e);
+        v[0] = fmax(v[0], sqrt(s_magSqr(e)));
+    }
+    grid_reduce<1, OpMax>(v, partials, ticket, FinMaxBE{S});
+}
+struct LinMisesPtrs {
+    const double* gradD; const double* epsPOld; const double* sigmaYOld; const double* epsPEqOld;
+    double* epsilon; double* sigma; double* sigmaY; double* DSigmaY; double* epsPEq; double* DEpsPEq; double* epsP; double* DEpsP;
+    double* DEpsPprev; double* DLambda; double* plasticN;
+};
+__global__ void __launch_bounds__(S4F_BLOCK) k_law_lin_mises(LinMisesPtrs p, int N, int bOff, int B, int ld, double mu, double K, double Hp,
+                                                             HardeningTable T, OuterScalars* S, double* partials, unsigned int* ticket) {
+    const bool nonLinearPlasticity = T.n > 2;
+    const double maxMagBE = fmax(S->maxMagBE, S4F_SMALL);
+    double v[2] = {0, 0};
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N + B; t += gridDim.x * blockDim.x) {
+        const int i = field_index(t, N, bOff);
+        double g[9], eps[6], e[6], epo[6], dpo[6], sT[6];
+        ld_soa<9>(p.gradD, ld, i, g); t_symm(g, eps); s_dev(eps, e);
+        ld_soa<6>(p.epsPOld, ld, i, epo); s_dev(epo, dpo);
+#pragma unroll
+        for (int q = 0; q < 6; q++) sT[q] = 2.0 * mu * (e[q] - dpo[q]);
+        const double sYold = p.sigmaYOld[i];
+        const double magS = sqrt(s_magSqr(sT));
+        const double fT = magS - SQRT23 * sYold;
+        double pn[6] = {1, 0, 0, 1, 0, 1};
+        double DLambda = p.DLambda[i], DSigY = p.DSigmaY[i], sY = p.sigmaY[i];
+        if (fT < S4F_SMALL) { DLambda = 0; DSigY = 0; sY = sYold; }
+        else {
+            if (magS > S4F_SMALL) {
+#pragma unroll
+                for (int q = 0; q < 6; q++) pn[q] = sT[q] / magS;
+            }
+            if (nonLinearPlasticity) {
+                newton_loop(T, DLambda, sY, p.epsPEqOld[i], magS, mu, 1.0, maxMagBE);
+                DSigY = sY - sYold;
+            } else {
+                DLambda = fT / (2 * mu);
+                if (fabs(Hp) > S4F_SMALL) { DLambda /= 1.0 + Hp / (3 * mu); DSigY = SQRT23 * DLambda * Hp; sY = sYold + DSigY; }
+            }
+        }
+        double prev[6], dep[6], ep[6], s[6];
+        ld_soa<6>(p.DEpsP, ld, i, prev);
+#pragma unroll
+        for (int q = 0; q < 6; q++) { dep[q] = DLambda * pn[q]; ep[q] = epo[q] + dep[q]; s[q] = sT[q] - 2 * mu * dep[q]; }
+        const double sh = K * s_tr(eps);
+        s[0] += sh; s[3] += sh; s[5] += sh;
+        st_soa<6>(p.epsilon, ld, i, eps); st_soa<6>(p.sigma, ld, i, s); st_soa<6>(p.epsP, ld, i, ep);
+        st_soa<6>(p.DEpsPprev, ld, i, prev); st_soa<6>(p.DEpsP, ld, i, dep); st_soa<6>(p.plasticN, ld, i, pn);
+        p.DLambda[i] = DLambda; p.DSigmaY[i] = DSigY; p.sigmaY[i] = sY;
+        p.DEpsPEq[i] = SQRT23 * DLambda; p.epsPEq[i] = p.epsPEqOld[i] + SQRT23 * DLambda;
+        if (t < N) {
+            double d[6];
+#pragma unroll
+            for (int q = 0; q < 6; q++) d[q] = dep[q] - prev[q];
+            v[0] = fmax(v[0], sqrt(s_magSqr(d)));
+            v[1] = fmax(v[1], S4F_SMALL + sqrt(s_magSqr(prev)));
+        }
+    }
+    grid_reduce<2, OpMax>(v, partials, ticket, FinMat{S});
+}
+
+// ---- total-Lagrangian flux tensor: F = I + gradD.T(); Finv; J; T = J Finv & sigma ------------------
+__global__ void __launch_bounds__(S4F_BLOCK) k_tl_flux_tensor(const double* __restrict__ gradD, const double* __restrict__ sigma,
+                                                              double* __restrict__ T9, double* __restrict__ Finv, double* __restrict__ Jt,
+                                                              int N, int bOff, int B, int ld) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N + B; t += gridDim.x * blockDim.x) {
+        const int i = field_index(t, N, bOff);
+        double g[9], Fm[9], Fi[9], s6[6], s9[9], T[9];
+        ld_soa<9>(gradD, ld, i, g);
+        t_transpose(g, Fm); Fm[0] += 1; Fm[4] += 1; Fm[8] += 1;
+        t_inv(Fm, Fi);
+        const double J = t_det(Fm);
+        ld_soa<6>(sigma, ld, i, s6); s_to_t(s6, s9);
+        t_mul(Fi, s9, T);
+#pragma unroll
+        for (int q = 0; q < 9; q++) T[q] *= J;
+        st_soa<9>(T9, ld, i, T);
+        Jt[i] = J;
+        if (t >= N) st_soa<9>(Finv, ld, i, Fi);      // only the traction BC reads Finv, on boundary faces
+    }
+}
+
+__global__ void k_axpy(double* __restrict__ y, const double* __restrict__ x, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) y[i] += x[i];
+}
+
+HardeningTable make_table(const s4fgpu_law& L) {
+    HardeningTable T; T.n = L.nTable;
+    for (int i = 0; i < 64; i++) { T.eps[i] = L.tableEps[i]; T.sig[i] = L.tableSigY[i]; }
+    return T;
+}
+
+}  // namespace
+
+// mechanicalModel::correct(sigma) (mechanicalModel.C:476-483), followed -- for the finite-strain
+// solid models -- by the flux tensor the momentum equation needs, and the halo exchange of the result.
+int s4f_law_correct(s4fgpu_ctx* c) {
+    const int N = c->N, B = c->B, bOff = c->bOff(), ld = c->ld;
+    const int grid = s4f_grid(c->numSMs, N + B), gridN = s4f_grid(c->numSMs, N);
+    const s4fgpu_law& L = c->law;
+    if (L.kind == S4F_LAW_LINEAR_ELASTIC) {
+        S6 s0; for (int q = 0; q < 6; q++) s0.v[q] = L.sigma0[q];
+        k_law_linear_elastic<<<grid, S4F_BLOCK, 0, c->stream>>>(c->gradD.p, c->sigma.p, N, bOff, B, ld, L.mu, L.K, s0);
+        c->launches++;
+    } else if (L.kind == S4F_LAW_NEO_HOOKEAN_ELASTIC) {
+        k_law_neo_hookean<<<grid, S4F_BLOCK, 0, c->stream>>>(c->gradD.p, c->sigma.p, c->lawJ.p, N, bOff, B, ld, L.mu, L.K);
+        c->launches++;
+    } else if (L.kind == S4F_LAW_NEO_HOOKEAN_MISES_PLASTIC) {
+        HardeningTable T = make_table(L);
+        if (T.n > 2) {
+            k_mises_max_be<<<gridN, S4F_BLOCK, 0, c->stream>>>(c->gradD.p, c->lawFold.p, c->lawJold.p, c->bEbarOld.p, N, ld, c->outS.p, c->partials.p, c->ticket.p);
+            c->launches++;
+            if (c->nRanks > 1) S4F_CHECK_NCCL(c, ncclAllReduce(&((OuterScalars*)c->outS.p)->maxMagBE, &((OuterScalars*)c->outS.p)->maxMagBE, 1, ncclDouble, ncclMax, c->comm, c->stream));
+        }
+        MisesPtrs p{c->gradD.p, c->lawFold.p, c->lawJold.p, c->bEbarOld.p, c->sigmaY.p, c->epsPEq.p, c->lawF.p, c->lawJ.p, c->bEbar.p, c->sigma.p,
+                    c->DSigmaY.p, c->DEpsPEq.p, c->DEpsP.p, c->DEpsPprev.p, c->DLambda.p, c->plasticN.p};
+        k_law_mises<<<grid, S4F_BLOCK, 0, c->stream>>>(p, N, bOff, B, ld, L.mu, L.K, c->Hp, L.updateBEbarConsistent, L.DEpsilonPRelax, T, c->outS.p,
+                                                      c->partials.p, c->ticket.p);
+        c->launches++;
+        if (c->nRanks > 1) S4F_CHECK_NCCL(c, ncclAllReduce(&((OuterScalars*)c->outS.p)->matNum, &((OuterScalars*)c->outS.p)->matNum, 2, ncclDouble, ncclMax, c->comm, c->stream));
+    } else if (L.kind == S4F_LAW_LINEAR_ELASTIC_MISES_PLASTIC) {
+        HardeningTable T = make_table(L);
+        if (T.n > 2) {
+            k_lin_mises_max_eps<<<gridN, S4F_BLOCK, 0, c->stream>>>(c->gradD.p, N, ld, c->outS.p, c->partials.p, c->ticket.p);
+            c->launches++;
+            if (c->nRanks > 1) S4F_CHECK_NCCL(c, ncclAllReduce(&((OuterScalars*)c->outS.p)->maxMagBE, &((OuterScalars*)c->outS.p)->maxMagBE, 1, ncclDouble, ncclMax, c->comm, c->stream));
+        }
+        LinMisesPtrs p{c->gradD.p, c->epsPOld.p, c->sigmaYOld.p, c->epsPEqOld.p, c->epsilon.p, c->sigma.p, c->sigmaY.p, c->DSigmaY.p, c->epsPEq.p,
+                       c->DEpsPEq.p, c->epsP.p, c->DEpsP.p, c->DEpsPprev.p, c->DLambda.p, c->plasticN.p};
+        k_law_lin_mises<<<grid, S4F_BLOCK, 0, c->stream>>>(p, N, bOff, B, ld, L.mu, L.K, c->Hp, T, c->outS.p, c->partials.p, c->ticket.p);
+        c->launches++;
+        if (c->nRanks > 1) S4F_CHECK_NCCL(c, ncclAllReduce(&((OuterScalars*)c->outS.p)->matNum, &((OuterScalars*)c->outS.p)->matNum, 2, ncclDouble, ncclMax, c->comm, c->stream));
+    } else {
+        c->err = "unknown mechanical law"; return 1;
+    }
+    S4F_CHECK_CUDA(c, cudaGetLastError());
+    if (c->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP) {
+        k_tl_flux_tensor<<<grid, S4F_BLOCK, 0, c->stream>>>(c->gradD.p, c->sigma.p, c->T9.p, c->Finv.p, c->Jt.p, N, bOff, B, ld);
+        c->launches++;
+        return s4f_halo_exchange(c, c->T9.p, 9);
+    }
+    return s4f_halo_exchange(c, c->sigma.p, 6);
+}
+
+// solidModel::updateTotalFields -> neoHookeanElasticMisesPlastic::updateTotalFields :1526-1536
+int s4f_update_total_fields_impl(s4fgpu_ctx* c) {
+    if (c->law.kind == S4F_LAW_NEO_HOOKEAN_MISES_PLASTIC) {
+        const long long ld = c->ld;
+        k_axpy<<<(unsigned)((ld + 255) / 256), 256, 0, c->stream>>>(c->sigmaY.p, c->DSigmaY.p, ld);
+        k_axpy<<<(unsigned)((ld + 255) / 256), 256, 0, c->stream>>>(c->epsPEq.p, c->DEpsPEq.p, ld);
+        k_axpy<<<(unsigned)((6 * ld + 255) / 256), 256, 0, c->stream>>>(c->epsP.p, c->DEpsP.p, 6 * ld);
+        c->launches += 3;
+        S4F_CHECK_CUDA(c, cudaGetLastError());
+    }
+    return 0;
+}

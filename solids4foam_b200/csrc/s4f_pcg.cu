@@ -1,0 +1,588 @@
+// s4f_pcg.cu -- the Krylov solve: [OF-ext] fvMatrix<vector>::solveSegregated -> PCG, restated as ONE
+// fused solve of the three displacement components.
+//
+// OpenFOAM solves x, y, z one after the other, each reading the whole matrix per iteration.  The
+// components share every off-diagonal coefficient (only the boundary part of the diagonal and the
+// source differ), so here one pass over the SELL-32 rows serves all three: each component keeps its
+// own alpha/beta/residual and its own `active` flag (it stops updating exactly where OpenFOAM's
+// solver for that component would return), which makes the per-component iterates identical to three
+// separate solves.  Algorithm per component (PCG.C): wA = A psi; rA = b - wA; normFactor
+// (lduMatrix::solver::normFactor); loop { wA = M^-1 rA; wArA = wA.rA; pA = wA + beta pA; wA = A pA;
+// alpha = wArA/(wA.pA); psi += alpha pA; rA -= alpha wA; res = sum|rA|/normFactor }.
+//
+// Kernels per iteration (diagonal preconditioner, M^-1 = 1/diag folded into the vector kernels):
+//   k_pcg_p    pA = rA/diag + beta pA                                   (stream, 3 comps)
+//   k_pcg_amul wA = A pA  + partial sums of wA.pA                       (SELL-32 gather, matrix read once for 3 comps)
+//   k_pcg_xr   psi += alpha pA; rA -= alpha wA + partial sums |rA|, rA.rA/diag
+// Dot products are warp-shuffle/block reductions finished deterministically by the last block; the
+// scalar recurrences (alpha, beta, convergence flags, iteration counters) live in device memory, so
+// the host only polls a flag every `checkEvery` iterations.  With NCCL the raw sums are all-reduced
+// and a one-thread kernel finishes the scalar step.
+#include <cmath>
+#include <cstring>
+
+#include "s4f_ctx.h"
+#include "s4f_dev.cuh"
+
+namespace {
+
+struct PcgParams {
+    double tolerance, relTol;
+    int maxIter;
+    int solD[3];
+    int defer;       // 1: multi-rank, totals are all-reduced before the scalar step
+    int precond;
+};
+
+enum { PH_AVG = 0, PH_INIT = 1, PH_AMUL = 2, PH_XR = 3, PH_DOT = 4 };
+
+__device__ __forceinline__ bool conv_check(const PcgParams& P, double fr, double ir) {
+    return fr < P.tolerance || (P.relTol > 1e-20 && fr < P.relTol * ir);
+}
+
+// scalar step after a reduction; tot = global sums
+__device__ void pcg_scalar_step(int phase, PcgScalars* S, const double* tot, const PcgParams& P, double nCellsGlobal) {
+    if (phase == PH_AVG) {
+        for (int c = 0; c < 3; c++) S->avg[c] = tot[c] / nCellsGlobal;
+    } else if (phase == PH_INIT) {
+        int any = 0;
+        for (int c = 0; c < 3; c++) {
+            S->normFactor[c] = tot[3 + c] + 1e-20;
+            S->initRes[c] = P.solD[c] ? tot[c] / S->normFactor[c] : 0.0;
+            S->finalRes[c] = S->initRes[c];
+            S->rho[c] = tot[6 + c];
+            S->rhoOld[c] = 1e300;
+            S->nIter[c] = 0;
+            S->alpha[c] = 0; S->beta[c] = 0;
+            S->active[c] = (P.solD[c] && !conv_check(P, S->finalRes[c], S->initRes[c]) && P.maxIter > 0) ? 1 : 0;
+            any |= S->active[c];
+        }
+        S->anyActive = any;
+    } else if (phase == PH_AMUL) {
+        for (int c = 0; c < 3; c++) if (S->active[c]) {
+            S->wApA[c] = tot[c];
+            // checkSingularity: |wApA|/normFactor < VSMALL -> stop this component
+            if (fabs(tot[c]) / S->normFactor[c] < 1e-300) { S->alpha[c] = 0.0; S->active[c] = 0; }
+            else S->alpha[c] = S->rho[c] / tot[c];
+        }
+    } else if (phase == PH_XR) {
+        int any = 0;
+        for (int c = 0; c < 3; c++) {
+            if (S->active[c]) {
+                S->finalRes[c] = tot[c] / S->normFactor[c];
+                S->rhoOld[c] = S->rho[c];
+                S->rho[c] = tot[3 + c];
+                S->nIter[c] += 1;
+                if (!(S->nIter[c] < P.maxIter && !conv_check(P, S->finalRes[c], S->initRes[c]))) S->active[c] = 0;
+                else S->beta[c] = S->rho[c] / S->rhoOld[c];
+            }
+            any |= S->active[c];
+        }
+        S->anyActive = any;
+    } else if (phase == PH_DOT) {   // generic preconditioner path: rho = wA.rA
+        for (int c = 0; c < 3; c++) if (S->active[c]) {
+            if (S->nIter[c] > 0) S->rhoOld[c] = S->rho[c];
+            S->rho[c] = tot[c];
+            S->beta[c] = (S->nIter[c] > 0) ? S->rho[c] / S->rhoOld[c] : 0.0;
+        }
+    }
+}
+
+struct Fin {
+    int phase; PcgScalars* S; PcgParams P; double nGlob; int nv;
+    __device__ void operator()(const double* tot) const {
+        if (P.defer) { for (int i = 0; i < nv; i++) S->part[i] = tot[i]; }
+        else pcg_scalar_step(phase, S, tot, P, nGlob);
+    }
+};
+
+__global__ void k_pcg_scalar_step(int phase, PcgScalars* S, PcgParams P, double nGlob) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double tot[16];
+        for (int i = 0; i < 16; i++) tot[i] = S->part[i];
+        pcg_scalar_step(phase, S, tot, P, nGlob);
+    }
+}
+
+// gAverage(psi) numerator
+__global__ void __launch_bounds__(S4F_BLOCK) k_pcg_sum(const double* __restrict__ x, int N, int ld, PcgScalars* S, PcgParams P,
+                                                       double nGlob, double* partials, unsigned int* ticket) {
+    double v[3] = {0, 0, 0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        v[0] += x[i]; v[1] += x[(size_t)ld + i]; v[2] += x[2 * (size_t)ld + i];
+    }
+    grid_reduce<3, OpSum>(v, partials, ticket, Fin{PH_AVG, S, P, nGlob, 3});
+}
+
+// wA = A psi ; rA = b - wA ; sums |rA|, |wA - sumA*avg| + |b - sumA*avg|, rA.rA/diag
+__global__ void __launch_bounds__(S4F_BLOCK) k_pcg_init(const int* __restrict__ slicePtr, const int* __restrict__ col,
+                                                        const double* __restrict__ eA, const double* __restrict__ diagC,
+                                                        const double* __restrict__ x, const double* __restrict__ b,
+                                                        double* __restrict__ r, int N, int ld, int nSlices, PcgScalars* S,
+                                                        PcgParams P, double nGlob, double* partials, unsigned int* ticket) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    const double avg0 = S->avg[0], avg1 = S->avg[1], avg2 = S->avg[2];
+    double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = warp; s < nSlices; s += nWarps) {
+        const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
+        const int row = s * 32 + lane;
+        double a0 = 0, a1 = 0, a2 = 0, sa = 0;
+        for (int k = 0; k < width; k++) {
+            const int e = base + 32 * k + lane;
+            const int cc = col[e];
+            const double a = eA[e];
+            a0 += a * x[cc]; a1 += a * x[(size_t)ld + cc]; a2 += a * x[2 * (size_t)ld + cc];
+            sa += a;
+        }
+        if (row < N) {
+            const double acc[3] = {a0, a1, a2};
+            const double av[3] = {avg0, avg1, avg2};
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                if (!P.solD[c]) continue;
+                const double d = diagC[(size_t)c * ld + row];
+                const double w = d * x[(size_t)c * ld + row] - acc[c];
+                const double bb = b[(size_t)c * ld + row];
+                const double rr = bb - w;
+                r[(size_t)c * ld + row] = rr;
+                const double t = (d - sa) * av[c];
+                v[c] += fabs(rr);
+                v[3 + c] += fabs(w - t) + fabs(bb - t);
+                v[6 + c] += (P.precond == S4F_PRECOND_NONE) ? rr * rr : rr * rr / d;
+            }
+        }
+    }
+    grid_reduce<9, OpSum>(v, partials, ticket, Fin{PH_INIT, S, P, nGlob, 9});
+}
+
+// pA = rA/diag + beta pA   (first iteration: pA = rA/diag)
+__global__ void __launch_bounds__(S4F_BLOCK) k_pcg_p(const double* __restrict__ diagC, const double* __restrict__ r,
+                                                     double* __restrict__ p, int N, int ld, const PcgScalars* __restrict__ S) {
+    if (!S->anyActive) return;
+    int act[3]; double beta[3]; int first[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { act[c] = S->active[c]; beta[c] = S->beta[c]; first[c] = (S->nIter[c] == 0); }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (!act[c]) continue;
+            const size_t j = (size_t)c * ld + i;
+            const double z = r[j] / diagC[j];
+            p[j] = first[c] ? z : z + beta[c] * p[j];
+        }
+    }
+}
+
+// generic-preconditioner variant: pA = wA + beta pA (wA holds M^-1 rA)
+__global__ void __launch_bounds__(S4F_BLOCK) k_pcg_p_generic(const double* __restrict__ z, double* __restrict__ p, int N, int ld,
+                                                             const PcgScalars* __restrict__ S) {
+    if (!S->anyActive) return;
+    int act[3]; double beta[3]; int first[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { act[c] = S->active[c]; beta[c] = S->beta[c]; first[c] = (S->nIter[c] == 0); }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (!act[c]) continue;
+            const size_t j = (size_t)c * ld + i;
+            p[j] = first[c] ? z[j] : z[j] + beta[c] * p[j];
+        }
+    }
+}
+
+// wA = A pA, sums wA.pA   -- THE SpMV: SELL-32 gather, matrix entries read once for three vectors
+template <bool DOT>
+__global__ void __launch_bounds__(S4F_BLOCK) k_amul3(const int* __restrict__ slicePtr, const int* __restrict__ col,
+                                                     const double* __restrict__ eA, const double* __restrict__ diagC,
+                                                     const double* __restrict__ p, double* __restrict__ w, int N, int ld,
+                                                     int nSlices, PcgScalars* S, PcgParams P, double nGlob, double* partials,
+                                                     unsigned int* ticket, int cmptMask) {
+    int act[3];
+    if (DOT) {
+        if (!S->anyActive) return;
+#pragma unroll
+        for (int c = 0; c < 3; c++) act[c] = S->active[c];
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; c++) act[c] = (cmptMask >> c) & 1;
+    }
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    const double* __restrict__ p0 = p;
+    const double* __restrict__ p1 = p + (size_t)ld;
+    const double* __restrict__ p2 = p + 2 * (size_t)ld;
+    double v[3] = {0, 0, 0};
+    for (int s = warp; s < nSlices; s += nWarps) {
+        const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
+        const int row = s * 32 + lane;
+        double a0 = 0, a1 = 0, a2 = 0;
+        const int* cp = col + base + lane;
+        const double* ap = eA + base + lane;
+        if (act[0] && act[1] && act[2]) {
+#pragma unroll 2
+            for (int k = 0; k < width; k++) {
+                const int cc = cp[32 * k];
+                const double a = ap[32 * k];
+                a0 += a * p0[cc]; a1 += a * p1[cc]; a2 += a * p2[cc];
+            }
+        } else {
+            for (int k = 0; k < width; k++) {
+                const int cc = cp[32 * k];
+                const double a = ap[32 * k];
+                if (act[0]) a0 += a * p0[cc];
+                if (act[1]) a1 += a * p1[cc];
+                if (act[2]) a2 += a * p2[cc];
+            }
+        }
+        if (row < N) {
+            const double acc[3] = {a0, a1, a2};
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                if (!act[c]) continue;
+                const size_t j = (size_t)c * ld + row;
+                const double pp = p[j];
+                const double ww = diagC[j] * pp - acc[c];
+                w[j] = ww;
+                if (DOT) v[c] += ww * pp;
+            }
+        }
+    }
+    if (DOT) grid_reduce<3, OpSum>(v, partials, ticket, Fin{PH_AMUL, S, P, nGlob, 3});
+}
+
+// scalar (single-vector) Amul, for the roofline number the metric quotes
+__global__ void __launch_bounds__(S4F_BLOCK) k_amul1(const int* __restrict__ slicePtr, const int* __restrict__ col,
+                                                     const double* __restrict__ eA, const double* __restrict__ diag,
+                                                     const double* __restrict__ p, double* __restrict__ w, int N, int nSlices) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (int s = warp; s < nSlices; s += nWarps) {
+        const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
+        const int row = s * 32 + lane;
+        double a0 = 0;
+        const int* cp = col + base + lane;
+        const double* ap = eA + base + lane;
+#pragma unroll 2
+        for (int k = 0; k < width; k++) a0 += ap[32 * k] * p[cp[32 * k]];
+        if (row < N) w[row] = diag[row] * p[row] - a0;
+    }
+}
+
+// psi += alpha pA; rA -= alpha wA; sums |rA| and rA.rA/diag (the next wArA for the diagonal preconditioner)
+__global__ void __launch_bounds__(S4F_BLOCK) k_pcg_xr(const double* __restrict__ diagC, double* __restrict__ x, double* __restrict__ r,
+                                                      const double* __restrict__ p, const double* __restrict__ w, int N, int ld,
+                                                      PcgScalars* S, PcgParams P, double nGlob, double* partials, unsigned int* ticket) {
+    if (!S->anyActive) return;
+    int act[3]; double alpha[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { act[c] = S->active[c]; alpha[c] = S->alpha[c]; }
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (!act[c]) continue;
+            const size_t j = (size_t)c * ld + i;
+            x[j] += alpha[c] * p[j];
+            const double rr = r[j] - alpha[c] * w[j];
+            r[j] = rr;
+            v[c] += fabs(rr);
+            if (P.precond == S4F_PRECOND_DIAGONAL) v[3 + c] += rr * rr / diagC[j];
+            else if (P.precond == S4F_PRECOND_NONE) v[3 + c] += rr * rr;
+        }
+    }
+    grid_reduce<6, OpSum>(v, partials, ticket, Fin{PH_XR, S, P, nGlob, 6});
+}
+
+// rho = wA.rA for preconditioners whose result is not local (Chebyshev)
+__global__ void __launch_bounds__(S4F_BLOCK) k_pcg_dot_zr(const double* __restrict__ z, const double* __restrict__ r, int N, int ld,
+                                                          PcgScalars* S, PcgParams P, double nGlob, double* partials, unsigned int* ticket) {
+    if (!S->anyActive) return;
+    int act[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) act[c] = S->active[c];
+    double v[3] = {0, 0, 0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) if (act[c]) { const size_t j = (size_t)c * ld + i; v[c] += z[j] * r[j]; }
+    }
+    grid_reduce<3, OpSum>(v, partials, ticket, Fin{PH_DOT, S, P, nGlob, 3});
+}
+
+// Chebyshev polynomial preconditioner on the Jacobi-scaled operator D^-1 A, spectrum in
+// [lmin, lmax]: z_k = z_{k-1} + ... three-term recurrence; each step is one fused Amul.
+//   y = D^-1 r ; z0 = y/theta ; then  z_{k+1} = z_k + c1_k (z_k - z_{k-1}) + c2_k D^-1 (r - A z_k)
+__global__ void __launch_bounds__(S4F_BLOCK) k_cheb_first(const double* __restrict__ diagC, const double* __restrict__ r,
+                                                          double* __restrict__ z, int N, int ld, double invTheta,
+                                                          const PcgScalars* __restrict__ S) {
+    if (!S->anyActive) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
+#pragma unroll
+        for (int c = 0; c < 3; c++) if (S->active[c]) { const size_t j = (size_t)c * ld + i; z[j] = invTheta * r[j] / diagC[j]; }
+}
+__global__ void __launch_bounds__(S4F_BLOCK) k_cheb_step(const int* __restrict__ slicePtr, const int* __restrict__ col,
+                                                         const double* __restrict__ eA, const double* __restrict__ diagC,
+                                                         const double* __restrict__ r, const double* __restrict__ zk,
+                                                         const double* __restrict__ zkm1, double* __restrict__ zkp1, int N, int ld,
+                                                         int nSlices, double c1, double c2, const PcgScalars* __restrict__ S) {
+    if (!S->anyActive) return;
+    int act[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) act[c] = S->active[c];
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (int s = warp; s < nSlices; s += nWarps) {
+        const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
+        const int row = s * 32 + lane;
+        double a[3] = {0, 0, 0};
+        for (int k = 0; k < width; k++) {
+            const int e = base + 32 * k + lane;
+            const int cc = col[e];
+            const double av = eA[e];
+#pragma unroll
+            for (int c = 0; c < 3; c++) if (act[c]) a[c] += av * zk[(size_t)c * ld + cc];
+        }
+        if (row < N) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                if (!act[c]) continue;
+                const size_t j = (size_t)c * ld + row;
+                const double d = diagC[j];
+                const double Az = d * zk[j] - a[c];
+                const double prev = zkm1 ? zkm1[j] : 0.0;
+                zkp1[j] = zk[j] + c1 * (zk[j] - prev) + c2 * (r[j] - Az) / d;
+            }
+        }
+    }
+}
+
+// pack boundary-cell values of an ncomp-component SoA field into the send buffer
+__global__ void k_pack(const double* __restrict__ f, const int* __restrict__ sendCells, double* __restrict__ buf, int G, int ld, int ncomp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G * ncomp) return;
+    int q = i / G, g = i % G;
+    buf[i] = f[(size_t)q * ld + sendCells[g]];
+}
+__global__ void k_unpack(double* __restrict__ f, const double* __restrict__ buf, int G, int N, int ld, int ncomp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G * ncomp) return;
+    int q = i / G, g = i % G;
+    f[(size_t)q * ld + N + g] = buf[i];
+}
+
+PcgParams make_params(const s4fgpu_ctx* c) {
+    PcgParams P;
+    P.tolerance = c->ctl.tolerance; P.relTol = c->ctl.relTol; P.maxIter = c->ctl.maxIter;
+    for (int i = 0; i < 3; i++) P.solD[i] = c->solD[i];
+    P.defer = (c->nRanks > 1) ? 1 : 0;
+    P.precond = c->ctl.preconditioner;
+    return P;
+}
+
+}  // namespace
+
+// Halo exchange of an ncomp-component SoA field: pack boundary-cell values, one grouped
+// ncclSend/ncclRecv per neighbour, unpack into the ghost range [N, N+G).   Replaces the
+// processor-patch initEvaluate/evaluate (and initMatrixInterfaces/updateMatrixInterfaces in Amul).
+int s4f_halo_exchange(s4fgpu_ctx* c, double* field, int ncomp) {
+    if (c->nRanks <= 1 || c->G == 0) return 0;
+    const int G = c->G;
+    if (c->sendBuf.n < (size_t)ncomp * G) { S4F_CHECK_CUDA(c, c->sendBuf.alloc((size_t)ncomp * G)); S4F_CHECK_CUDA(c, c->recvBuf.alloc((size_t)ncomp * G)); }
+    k_pack<<<(G * ncomp + 255) / 256, 256, 0, c->stream>>>(field, c->sendCells.p, c->sendBuf.p, G, c->ld, ncomp);
+    c->launches++;
+    // buffers are component-major over all G ghosts: per neighbour send one strided piece per component
+    S4F_CHECK_NCCL(c, ncclGroupStart());
+    for (const auto& nb : c->nbrs)
+        for (int q = 0; q < ncomp; q++) {
+            S4F_CHECK_NCCL(c, ncclSend(c->sendBuf.p + (size_t)q * G + nb.sendOff, nb.count, ncclDouble, nb.rank, c->comm, c->stream));
+            S4F_CHECK_NCCL(c, ncclRecv(c->recvBuf.p + (size_t)q * G + nb.sendOff, nb.count, ncclDouble, nb.rank, c->comm, c->stream));
+        }
+    S4F_CHECK_NCCL(c, ncclGroupEnd());
+    k_unpack<<<(G * ncomp + 255) / 256, 256, 0, c->stream>>>(field, c->recvBuf.p, G, c->N, c->ld, ncomp);
+    c->launches++;
+    return 0;
+}
+
+static int allreduce_part(s4fgpu_ctx* c, int n, int phase, const PcgParams& P, double nGlob) {
+    if (c->nRanks <= 1) return 0;
+    S4F_CHECK_NCCL(c, ncclAllReduce((double*)c->pcgS.p, (double*)c->pcgS.p, n, ncclDouble, ncclSum, c->comm, c->stream));
+    k_pcg_scalar_step<<<1, 32, 0, c->stream>>>(phase, c->pcgS.p, P, nGlob);
+    c->launches++;
+    return 0;
+}
+
+static int amul3(s4fgpu_ctx* c, const double* p, double* w, bool dot, const PcgParams& P, double nGlob, int mask) {
+    const int grid = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
+    if (dot)
+        k_amul3<true><<<grid, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, p, w, c->N, c->ld, c->nSlices,
+                                                          c->pcgS.p, P, nGlob, c->partials.p, c->ticket.p, mask);
+    else
+        k_amul3<false><<<grid, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, p, w, c->N, c->ld, c->nSlices,
+                                                           c->pcgS.p, P, nGlob, c->partials.p, c->ticket.p, mask);
+    c->launches++;
+    return 0;
+}
+
+// y = A x for one component (host-visible operator, parity tests): device SoA x (3*ld) -> w
+int s4f_amul_device(s4fgpu_ctx* c, const double* x3, double* w3, int mask) {
+    PcgParams P = make_params(c);
+    int rc = s4f_halo_exchange(c, const_cast<double*>(x3), 3);
+    if (rc) return rc;
+    return amul3(c, x3, w3, false, P, 1.0, mask);
+}
+
+static double global_cells(s4fgpu_ctx* c) {
+    // gAverage divides by the global cell count; obtained once per mesh via NCCL
+    if (c->nRanks <= 1) return (double)c->N;
+    if (c->nGlobalCells > 0) return c->nGlobalCells;
+    double* d = (double*)c->pcgS.p;
+    double h = (double)c->N;
+    cudaMemcpyAsync(d, &h, sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    ncclAllReduce(d, d, 1, ncclDouble, ncclSum, c->comm, c->stream);
+    cudaMemcpyAsync(&h, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    c->nGlobalCells = h;
+    return h;
+}
+
+// Chebyshev preconditioner application: z (in wA) = q(D^-1 A) D^-1 r, degree = chebyshevDegree
+static int cheb_apply(s4fgpu_ctx* c, const PcgParams& P) {
+    const int N = c->N, ld = c->ld;
+    const int gridV = s4f_grid(c->numSMs, N), gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
+    const double lmax = c->lambdaMax, lmin = lmax / 30.0;     // smoother-style interval
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin);
+    const int deg = c->ctl.chebyshevDegree < 1 ? 1 : c->ctl.chebyshevDegree;
+    double* bufs[3] = {c->cheb0.p, c->cheb1.p, c->wA.p};
+    int cur = 0, prev = -1;
+    k_cheb_first<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->diagC.p, c->rA.p, bufs[cur], N, ld, 1.0 / theta, c->pcgS.p);
+    c->launches++;
+    double sigma1 = theta / delta, rhoK = 1.0 / sigma1;
+    for (int k = 1; k < deg; k++) {
+        const double rhoN = 1.0 / (2.0 * sigma1 - rhoK);
+        const double c1 = rhoN * rhoK, c2 = 2.0 * rhoN / delta;
+        int nxt = 0;
+        while (nxt == cur || nxt == prev) nxt++;
+        int rc = s4f_halo_exchange(c, bufs[cur], 3); if (rc) return rc;
+        k_cheb_step<<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, c->rA.p, bufs[cur],
+                                                        prev < 0 ? nullptr : bufs[prev], bufs[nxt], N, ld, c->nSlices, c1, c2, c->pcgS.p);
+        c->launches++;
+        rhoK = rhoN; prev = cur; cur = nxt;
+    }
+    double* zk = bufs[cur];
+    if (zk != c->wA.p) S4F_CHECK_CUDA(c, cudaMemcpyAsync(c->wA.p, zk, 3 * (size_t)ld * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
+// fvMatrix<vector>::solveSegregated for device SoA psi (3*ld, ghosts/boundary slots untouched) and source
+int s4f_solve_segregated(s4fgpu_ctx* c, double* psi, const double* source) {
+    const int N = c->N, ld = c->ld;
+    PcgParams P = make_params(c);
+    const double nGlob = global_cells(c);
+    const int gridV = s4f_grid(c->numSMs, N), gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
+    PcgScalars* S = c->pcgS.p;
+    const bool fusedJacobi = (P.precond == S4F_PRECOND_DIAGONAL || P.precond == S4F_PRECOND_NONE || P.precond == S4F_PRECOND_DIC);
+    if (P.precond == S4F_PRECOND_DIC) P.precond = S4F_PRECOND_DIAGONAL;   // GPU stand-in, reported
+    if (P.precond == S4F_PRECOND_CHEBYSHEV && c->cheb0.n != 3 * (size_t)ld) {
+        S4F_CHECK_CUDA(c, c->cheb0.alloc(3 * (size_t)ld)); S4F_CHECK_CUDA(c, c->cheb1.alloc(3 * (size_t)ld));
+    }
+
+    k_pcg_sum<<<gridV, S4F_BLOCK, 0, c->stream>>>(psi, N, ld, S, P, nGlob, c->partials.p, c->ticket.p);
+    c->launches++;
+    int rc = allreduce_part(c, 3, PH_AVG, P, nGlob); if (rc) return rc;
+    rc = s4f_halo_exchange(c, psi, 3); if (rc) return rc;
+    k_pcg_init<<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, psi, source, c->rA.p, N, ld, c->nSlices,
+                                                   S, P, nGlob, c->partials.p, c->ticket.p);
+    c->launches++;
+    rc = allreduce_part(c, 9, PH_INIT, P, nGlob); if (rc) return rc;
+
+    const int checkEvery = c->ctl.checkEvery > 0 ? c->ctl.checkEvery : 4;
+    int it = 0;
+    for (;;) {
+        S4F_CHECK_CUDA(c, cudaMemcpyAsync(c->hPcgS, S, sizeof(PcgScalars), cudaMemcpyDeviceToHost, c->stream));
+        S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (!c->hPcgS->anyActive || it >= P.maxIter) break;
+        for (int k = 0; k < checkEvery; k++, it++) {
+            if (fusedJacobi) {
+                if (c->ctl.preconditioner == S4F_PRECOND_NONE)
+                    k_pcg_p_generic<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->rA.p, c->pA.p, N, ld, S);
+                else
+                    k_pcg_p<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->diagC.p, c->rA.p, c->pA.p, N, ld, S);
+                c->launches++;
+            } else {
+                rc = cheb_apply(c, P); if (rc) return rc;
+                k_pcg_dot_zr<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->wA.p, c->rA.p, N, ld, S, P, nGlob, c->partials.p, c->ticket.p);
+                c->launches++;
+                rc = allreduce_part(c, 3, PH_DOT, P, nGlob); if (rc) return rc;
+                k_pcg_p_generic<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->wA.p, c->pA.p, N, ld, S);
+                c->launches++;
+            }
+            rc = s4f_halo_exchange(c, c->pA.p, 3); if (rc) return rc;
+            rc = amul3(c, c->pA.p, c->wA.p, true, P, nGlob, 7); if (rc) return rc;
+            rc = allreduce_part(c, 3, PH_AMUL, P, nGlob); if (rc) return rc;
+            k_pcg_xr<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->diagC.p, psi, c->rA.p, c->pA.p, c->wA.p, N, ld, S, P, nGlob, c->partials.p, c->ticket.p);
+            c->launches++;
+            rc = allreduce_part(c, 6, PH_XR, P, nGlob); if (rc) return rc;
+        }
+    }
+    for (int q = 0; q < 3; q++) {
+        c->last.initialResidual[q] = c->hPcgS->initRes[q];
+        c->last.finalResidual[q] = c->hPcgS->finalRes[q];
+        c->last.nIterations[q] = c->hPcgS->nIter[q];
+        c->totalInner += c->hPcgS->nIter[q];
+    }
+    S4F_CHECK_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+// ---- kernel timing for the roofline numbers (bench.py) ----------------------------------------
+int s4f_time_pcg_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, double* msOut, double* bytesOut) {
+    const int N = c->N, ld = c->ld;
+    PcgParams P = make_params(c);
+    if (P.precond == S4F_PRECOND_DIC || P.precond == S4F_PRECOND_CHEBYSHEV) P.precond = S4F_PRECOND_DIAGONAL;
+    const int gridV = s4f_grid(c->numSMs, N), gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
+    const double nnz = (double)c->nnzOff;
+    // make every component "active" with harmless scalars
+    PcgScalars h; memset(&h, 0, sizeof(h));
+    for (int q = 0; q < 3; q++) { h.active[q] = 1; h.alpha[q] = 1e-30; h.beta[q] = 0.5; h.nIter[q] = 1; h.rho[q] = 1; h.rhoOld[q] = 1; h.normFactor[q] = 1; h.initRes[q] = 1; }
+    h.anyActive = 1;
+    PcgParams Pn = P; Pn.maxIter = 1 << 30; Pn.tolerance = 0; Pn.relTol = 0; Pn.defer = 0;
+    if (flushL2 && c->flushBuf.n == 0) S4F_CHECK_CUDA(c, c->flushBuf.alloc((size_t)48 * 1024 * 1024));   // 384 MB > 126 MB L2
+    cudaEvent_t e0, e1;
+    S4F_CHECK_CUDA(c, cudaEventCreate(&e0)); S4F_CHECK_CUDA(c, cudaEventCreate(&e1));
+    double total = 0;
+    for (int r = -3; r < reps; r++) {
+        S4F_CHECK_CUDA(c, cudaMemcpyAsync(c->pcgS.p, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+        if (flushL2) S4F_CHECK_CUDA(c, cudaMemsetAsync(c->flushBuf.p, 0, c->flushBuf.n * sizeof(double), c->stream));
+        S4F_CHECK_CUDA(c, cudaEventRecord(e0, c->stream));
+        if (kernel == S4F_KERNEL_SPMV1) {
+            k_amul1<<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, c->pA.p, c->wA.p, N, c->nSlices);
+            c->launches++;
+        } else if (kernel == S4F_KERNEL_SPMV3) {
+            k_amul3<true><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, c->pA.p, c->wA.p, N, ld, c->nSlices,
+                                                              c->pcgS.p, Pn, 1.0, c->partials.p, c->ticket.p, 7);
+            c->launches++;
+        } else {
+            k_pcg_p<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->diagC.p, c->rA.p, c->pA.p, N, ld, c->pcgS.p);
+            k_amul3<true><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, c->pA.p, c->wA.p, N, ld, c->nSlices,
+                                                              c->pcgS.p, Pn, 1.0, c->partials.p, c->ticket.p, 7);
+            k_pcg_xr<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->diagC.p, c->D.p, c->rA.p, c->pA.p, c->wA.p, N, ld, c->pcgS.p, Pn, 1.0, c->partials.p, c->ticket.p);
+            c->launches += 3;
+        }
+        S4F_CHECK_CUDA(c, cudaEventRecord(e1, c->stream));
+        S4F_CHECK_CUDA(c, cudaEventSynchronize(e1));
+        float ms; S4F_CHECK_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
+        if (r >= 0) total += ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *msOut = total / reps;
+    // algorithmic bytes: fp64 values, int32 columns, one slice pointer per 32 rows
+    if (kernel == S4F_KERNEL_SPMV1) *bytesOut = 12.0 * nnz + (8 + 8 + 8 + 0.125) * N;             // a,col | diag, x, y, slicePtr
+    else if (kernel == S4F_KERNEL_SPMV3) *bytesOut = 12.0 * nnz + (24 + 24 + 24 + 0.125) * N;
+    else *bytesOut = (12.0 * nnz + (24 + 24 + 24 + 0.125) * N) + (24 + 24 + 24 + 24.0) * N + (24 * 4 + 24 * 2 + 24.0) * N;
+    // restore a clean D (k_pcg_xr touched it with alpha = 1e-30 * p: negligible but not zero) is left to the caller
+    return 0;
+}

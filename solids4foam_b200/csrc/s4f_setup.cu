@@ -1,0 +1,295 @@
+// s4f_setup.cu -- once-per-mesh mirror: lduAddressing -> SELL-32 cell-centric rows, per-entry
+// geometry, least-squares vectors, boundary lists, halo lists; field allocation; AoS<->SoA transfer.
+//
+// Reference data this mirrors: fvMesh owner()/neighbour()/boundary() and the geometric fields
+// ([OF-ext] surfaceInterpolation weights / nonOrthDeltaCoeffs / nonOrthCorrectionVectors); the
+// least-squares vectors follow NUM/extendedLeastSquaresGrad/extendedLeastSquaresVectors.C:121-158
+// (dd tensor, 1/|d|^2 weights, true boundary deltas) and :229-272 (lsP / lsN), restated per
+// (cell, neighbour) pair:  ls = invDd_P & d / |d|^2  with d pointing from the row cell outwards.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "s4f_ctx.h"
+#include "s4f_dev.cuh"
+
+namespace {
+
+inline void invSymm(const double* S, double* R) {
+    double d = S[0] * S[3] * S[5] + 2.0 * S[1] * S[4] * S[2] - S[0] * S[4] * S[4] - S[1] * S[1] * S[5] - S[2] * S[3] * S[2];
+    R[0] = (S[3] * S[5] - S[4] * S[4]) / d; R[1] = (S[2] * S[4] - S[1] * S[5]) / d; R[2] = (S[1] * S[4] - S[2] * S[3]) / d;
+    R[3] = (S[0] * S[5] - S[2] * S[2]) / d; R[4] = (S[1] * S[2] - S[0] * S[4]) / d; R[5] = (S[0] * S[3] - S[1] * S[1]) / d;
+}
+
+__global__ void k_aos_to_soa(const double* __restrict__ aos, double* __restrict__ soa, int count, int ncomp, int ld, int offset) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long total = (long long)count * ncomp;
+    if (i >= total) return;
+    int cell = (int)(i / ncomp), q = (int)(i % ncomp);
+    soa[(size_t)q * ld + offset + cell] = aos[i];
+}
+__global__ void k_soa_to_aos(const double* __restrict__ soa, double* __restrict__ aos, int count, int ncomp, int ld, int offset) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long total = (long long)count * ncomp;
+    if (i >= total) return;
+    int cell = (int)(i / ncomp), q = (int)(i % ncomp);
+    aos[i] = soa[(size_t)q * ld + offset + cell];
+}
+__global__ void k_fill(double* p, double v, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+int s4f_aos_to_soa(s4fgpu_ctx* c, const double* hostAoS, double* devSoA, int count, int ncomp, int offset) {
+    if (count == 0) return 0;
+    size_t n = (size_t)count * ncomp;
+    if (c->staging.n < n) S4F_CHECK_CUDA(c, c->staging.alloc(n, false));
+    S4F_CHECK_CUDA(c, cudaMemcpyAsync(c->staging.p, hostAoS, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_aos_to_soa<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->staging.p, devSoA, count, ncomp, c->ld, offset);
+    c->launches++;
+    S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int s4f_soa_to_aos(s4fgpu_ctx* c, const double* devSoA, double* hostAoS, int count, int ncomp, int offset) {
+    if (count == 0) return 0;
+    size_t n = (size_t)count * ncomp;
+    if (c->staging.n < n) S4F_CHECK_CUDA(c, c->staging.alloc(n, false));
+    k_soa_to_aos<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(devSoA, c->staging.p, count, ncomp, c->ld, offset);
+    c->launches++;
+    S4F_CHECK_CUDA(c, cudaMemcpyAsync(hostAoS, c->staging.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int s4f_build_rows(s4fgpu_ctx* c) {
+    const int N = c->N, F = c->F, B = c->B;
+    // ---- ghosts: one per processor-patch face, in patch order ----
+    c->ghostOfFace.assign(B, -1);
+    c->nbrs.clear();
+    int G = 0;
+    std::vector<int> sendCells;
+    for (int p = 0; p < c->nPatches; p++) {
+        if (c->pKind[p] != S4F_PATCH_PROCESSOR) continue;
+        s4fgpu_ctx::Nbr nb;
+        nb.rank = c->pNbr[p]; nb.patch = p; nb.count = c->pSize[p]; nb.sendOff = G; nb.ghostOff = N + G;
+        for (int i = 0; i < c->pSize[p]; i++) {
+            int b = c->pStart[p] + i;
+            c->ghostOfFace[b] = N + G + i;
+            sendCells.push_back(c->faceCells[b]);
+        }
+        G += c->pSize[p];
+        c->nbrs.push_back(nb);
+    }
+    c->G = G;
+    const int bOff = N + G;
+    c->ld = ((N + G + B + 31) / 32) * 32;
+    if (c->ld == 0) c->ld = 32;
+
+    // ---- rows: lower neighbours, upper neighbours, boundary/processor faces ----
+    std::vector<int> cnt(N, 0);
+    for (int f = 0; f < F; f++) { cnt[c->own[f]]++; cnt[c->nei[f]]++; }
+    for (int b = 0; b < B; b++) cnt[c->faceCells[b]]++;
+    std::vector<long long> rowPtr(N + 1, 0);
+    for (int i = 0; i < N; i++) rowPtr[i + 1] = rowPtr[i] + cnt[i];
+    const long long nnz = rowPtr[N];
+    std::vector<int> rCol(nnz), rFace(nnz);
+    std::vector<signed char> rSign(nnz);
+    std::vector<long long> cur(rowPtr.begin(), rowPtr.end() - 1);
+    for (int f = 0; f < F; f++) { long long e = cur[c->nei[f]]++; rCol[e] = c->own[f]; rFace[e] = f; rSign[e] = -1; }
+    for (int f = 0; f < F; f++) { long long e = cur[c->own[f]]++; rCol[e] = c->nei[f]; rFace[e] = f; rSign[e] = +1; }
+    for (int b = 0; b < B; b++) {
+        long long e = cur[c->faceCells[b]]++;
+        rCol[e] = (c->ghostOfFace[b] >= 0) ? c->ghostOfFace[b] : bOff + b;
+        rFace[e] = F + b; rSign[e] = +1;
+    }
+    c->nnzOff = 2LL * F + G;
+
+    // ---- SELL-32 ----
+    const int nSlices = (N + 31) / 32;
+    c->nSlices = nSlices;
+    std::vector<int> slicePtr(nSlices + 1, 0);
+    for (int s = 0; s < nSlices; s++) {
+        int w = 0;
+        for (int r = s * 32; r < std::min(N, s * 32 + 32); r++) w = std::max(w, cnt[r]);
+        long long next = (long long)slicePtr[s] + 32LL * w;
+        if (next > 2147483647LL) { c->err = "mesh too large for int32 entry offsets"; return 1; }
+        slicePtr[s + 1] = (int)next;
+    }
+    const long long nE = slicePtr[nSlices];
+    c->nEntries = nE;
+
+    // least-squares dd tensor per cell
+    const double* C = c->hC.data();
+    auto otherPoint = [&](long long e, int P, double* d) {
+        int f = rFace[e];
+        const double* X;
+        if (f < F) X = &C[3 * (size_t)rCol[e]];
+        else X = &c->hCnbrB[3 * (size_t)(f - F)];     // Cf on ordinary patches, neighbour centre on processor faces
+        d[0] = X[0] - C[3 * (size_t)P]; d[1] = X[1] - C[3 * (size_t)P + 1]; d[2] = X[2] - C[3 * (size_t)P + 2];
+    };
+    std::vector<double> invDd(6 * (size_t)N);
+    for (int P = 0; P < N; P++) {
+        double t[6] = {0, 0, 0, 0, 0, 0};
+        for (long long e = rowPtr[P]; e < rowPtr[P + 1]; e++) {
+            double d[3]; otherPoint(e, P, d);
+            double r = 1.0 / (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            t[0] += r * d[0] * d[0]; t[1] += r * d[0] * d[1]; t[2] += r * d[0] * d[2];
+            t[3] += r * d[1] * d[1]; t[4] += r * d[1] * d[2]; t[5] += r * d[2] * d[2];
+        }
+        // [OF-ext] inv(symmTensorField): regularise the empty directions of 2-D cases
+        if (!c->solD[0]) t[0] += 1; if (!c->solD[1]) t[3] += 1; if (!c->solD[2]) t[5] += 1;
+        double r[6]; invSymm(t, r);
+        if (!c->solD[0]) r[0] -= 1; if (!c->solD[1]) r[3] -= 1; if (!c->solD[2]) r[5] -= 1;
+        for (int k = 0; k < 6; k++) invDd[6 * (size_t)P + k] = r[k];
+    }
+
+    std::vector<int> hCol(nE);
+    std::vector<double> hW(nE, 1.0), hSf(3 * nE, 0.0), hLs(3 * nE, 0.0), hDn(nE, 0.0), hCorr;
+    bool nonOrth = false;
+    for (size_t i = 0; i < c->hCorr.size(); i++) if (std::fabs(c->hCorr[i]) > 1e-12) { nonOrth = true; break; }
+    c->nonOrth = nonOrth;
+    if (nonOrth) hCorr.assign(3 * nE, 0.0);
+    for (int s = 0; s < nSlices; s++) {
+        const int width = (slicePtr[s + 1] - slicePtr[s]) / 32;
+        for (int lane = 0; lane < 32; lane++) {
+            const int P = s * 32 + lane;
+            for (int k = 0; k < width; k++) {
+                const long long E = (long long)slicePtr[s] + 32LL * k + lane;
+                if (P >= N) { hCol[E] = 0; continue; }
+                if (k >= cnt[P]) { hCol[E] = P; continue; }        // padding
+                const long long e = rowPtr[P] + k;
+                const int f = rFace[e];
+                const double sg = rSign[e];
+                hCol[E] = rCol[e];
+                const bool bnd = (f >= F) && (c->ghostOfFace[f - F] < 0);
+                if (bnd) hW[E] = 0.0;
+                else hW[E] = (sg > 0) ? c->hW[f] : 1.0 - c->hW[f];
+                for (int q = 0; q < 3; q++) hSf[(size_t)q * nE + E] = sg * c->hSf[3 * (size_t)f + q];
+                if (!bnd) {
+                    hDn[E] = c->hMagSf[f] * c->hNod[f];
+                    if (nonOrth) for (int q = 0; q < 3; q++) hCorr[(size_t)q * nE + E] = sg * c->hMagSf[f] * c->hCorr[3 * (size_t)f + q];
+                }
+                double d[3]; otherPoint(e, P, d);
+                const double r = 1.0 / (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                const double* iv = &invDd[6 * (size_t)P];
+                hLs[0 * nE + E] = r * (iv[0] * d[0] + iv[1] * d[1] + iv[2] * d[2]);
+                hLs[1 * nE + E] = r * (iv[1] * d[0] + iv[3] * d[1] + iv[4] * d[2]);
+                hLs[2 * nE + E] = r * (iv[2] * d[0] + iv[4] * d[1] + iv[5] * d[2]);
+            }
+        }
+    }
+    S4F_CHECK_CUDA(c, c->slicePtr.upload(slicePtr));
+    S4F_CHECK_CUDA(c, c->col.upload(hCol));
+    S4F_CHECK_CUDA(c, c->eW.upload(hW));
+    S4F_CHECK_CUDA(c, c->eSf.upload(hSf));
+    S4F_CHECK_CUDA(c, c->eLs.upload(hLs));
+    S4F_CHECK_CUDA(c, c->eDn.upload(hDn));
+    if (nonOrth) S4F_CHECK_CUDA(c, c->eCorr.upload(hCorr)); else c->eCorr.release();
+    S4F_CHECK_CUDA(c, c->eA.alloc(nE)); S4F_CHECK_CUDA(c, c->eRc.alloc(nE)); S4F_CHECK_CUDA(c, c->eGam.alloc(nE));
+
+    // volumes
+    std::vector<double> hV(c->ld, 1.0), hrV(c->ld, 1.0);
+    for (int i = 0; i < N; i++) { hV[i] = c->hV[i]; hrV[i] = 1.0 / c->hV[i]; }
+    S4F_CHECK_CUDA(c, c->V.upload(hV)); S4F_CHECK_CUDA(c, c->rV.upload(hrV));
+
+    // ---- boundary faces ----
+    std::vector<int> hFaceCell(std::max(B, 1), 0);
+    std::vector<double> hN(3 * (size_t)std::max(B, 1), 0.0), hK(3 * (size_t)std::max(B, 1), 0.0), hBSf(3 * (size_t)std::max(B, 1), 0.0),
+        hDelta(std::max(B, 1), 0.0), hMag(std::max(B, 1), 0.0);
+    for (int b = 0; b < B; b++) {
+        const int f = F + b, P = c->faceCells[b];
+        hFaceCell[b] = P;
+        double n[3], d[3], nd = 0;
+        for (int q = 0; q < 3; q++) { n[q] = c->hSf[3 * (size_t)f + q] / c->hMagSf[f]; d[q] = c->hCf[3 * (size_t)f + q] - C[3 * (size_t)P + q]; nd += n[q] * d[q]; }
+        for (int q = 0; q < 3; q++) {
+            hN[(size_t)q * B + b] = n[q];
+            hK[(size_t)q * B + b] = d[q] - n[q] * nd;           // patchCorrectionVectors.C:24-36
+            hBSf[(size_t)q * B + b] = c->hSf[3 * (size_t)f + q];
+        }
+        hDelta[b] = c->hNod[f]; hMag[b] = c->hMagSf[f];
+    }
+    S4F_CHECK_CUDA(c, c->bFaceCell.upload(hFaceCell));
+    S4F_CHECK_CUDA(c, c->bN.upload(hN)); S4F_CHECK_CUDA(c, c->bK.upload(hK)); S4F_CHECK_CUDA(c, c->bSf.upload(hBSf));
+    S4F_CHECK_CUDA(c, c->bDelta.upload(hDelta)); S4F_CHECK_CUDA(c, c->bMagSf.upload(hMag));
+    S4F_CHECK_CUDA(c, c->bcValue.alloc(3 * (size_t)std::max(B, 1))); S4F_CHECK_CUDA(c, c->bcPressure.alloc(std::max(B, 1)));
+    S4F_CHECK_CUDA(c, c->tracGrad.alloc(3 * (size_t)std::max(B, 1))); S4F_CHECK_CUDA(c, c->bSn.alloc(3 * (size_t)std::max(B, 1)));
+    S4F_CHECK_CUDA(c, c->bKind.alloc(std::max(B, 1)));
+
+    // boundary cells and their (non-processor) faces, ascending face order
+    {
+        std::vector<int> nb(N, 0);
+        for (int b = 0; b < B; b++) if (c->ghostOfFace[b] < 0) nb[c->faceCells[b]]++;
+        std::vector<int> cells, ptr(1, 0), faces;
+        std::vector<int> slot(N, -1);
+        for (int i = 0; i < N; i++) if (nb[i] > 0) { slot[i] = (int)cells.size(); cells.push_back(i); ptr.push_back(ptr.back() + nb[i]); }
+        faces.resize(ptr.back());
+        std::vector<int> cur2(ptr.begin(), ptr.end() - 1);
+        for (int b = 0; b < B; b++) if (c->ghostOfFace[b] < 0) faces[cur2[slot[c->faceCells[b]]]++] = b;
+        c->nBCells = (int)cells.size();
+        if (cells.empty()) { cells.push_back(0); faces.push_back(0); }
+        S4F_CHECK_CUDA(c, c->bcCells.upload(cells)); S4F_CHECK_CUDA(c, c->bcPtr.upload(ptr)); S4F_CHECK_CUDA(c, c->bcFaces.upload(faces));
+    }
+    // halo
+    if (G > 0) {
+        S4F_CHECK_CUDA(c, c->sendCells.upload(sendCells));
+        S4F_CHECK_CUDA(c, c->sendBuf.alloc(9 * (size_t)G)); S4F_CHECK_CUDA(c, c->recvBuf.alloc(9 * (size_t)G));
+    }
+    return 0;
+}
+
+int s4f_alloc_fields(s4fgpu_ctx* c) {
+    const size_t ld = c->ld;
+    if (c->D.n == 3 * ld && c->gradD.n == 9 * ld) return 0;
+    auto A = [&](DevBuf<double>& b, int nc) { return b.alloc(nc * ld); };
+    S4F_CHECK_CUDA(c, A(c->D, 3)); S4F_CHECK_CUDA(c, A(c->Dprev, 3)); S4F_CHECK_CUDA(c, A(c->Dold, 3)); S4F_CHECK_CUDA(c, A(c->DoldOld, 3));
+    S4F_CHECK_CUDA(c, A(c->gradD, 9)); S4F_CHECK_CUDA(c, A(c->gradDold, 9));
+    S4F_CHECK_CUDA(c, A(c->sigma, 6)); S4F_CHECK_CUDA(c, A(c->sigmaOld, 6));
+    S4F_CHECK_CUDA(c, A(c->impK, 1));
+    S4F_CHECK_CUDA(c, A(c->diag0, 1)); S4F_CHECK_CUDA(c, A(c->diagC, 3)); S4F_CHECK_CUDA(c, A(c->source, 3));
+    S4F_CHECK_CUDA(c, A(c->pA, 3)); S4F_CHECK_CUDA(c, A(c->wA, 3)); S4F_CHECK_CUDA(c, A(c->rA, 3));
+    S4F_CHECK_CUDA(c, c->pcgS.alloc(1)); S4F_CHECK_CUDA(c, c->outS.alloc(1));
+    S4F_CHECK_CUDA(c, c->partials.alloc(32 * 4096)); S4F_CHECK_CUDA(c, c->ticket.alloc(8));
+    if (!c->hPcgS) S4F_CHECK_CUDA(c, cudaMallocHost((void**)&c->hPcgS, sizeof(PcgScalars)));
+    if (!c->hOutS) S4F_CHECK_CUDA(c, cudaMallocHost((void**)&c->hOutS, sizeof(OuterScalars)));
+    return 0;
+}
+
+// fields that only finite-strain models / plastic laws need; called from set_law / set_controls
+int s4f_alloc_model_fields(s4fgpu_ctx* c) {
+    const size_t ld = c->ld;
+    const bool TL = c->ctlSet && c->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP;
+    const int kind = c->law.kind;
+    auto A = [&](DevBuf<double>& b, int nc) { return (b.n == nc * ld) ? cudaSuccess : b.alloc(nc * ld); };
+    auto fillI = [&](DevBuf<double>& b, int nc, const int* diagIdx, int nd) {
+        for (int i = 0; i < nd; i++) {
+            k_fill<<<(unsigned)((ld + 255) / 256), 256, 0, c->stream>>>(b.p + (size_t)diagIdx[i] * ld, 1.0, (long long)ld);
+            c->launches++;
+        }
+    };
+    const int dT[3] = {0, 4, 8}, dS[3] = {0, 3, 5}, d1[1] = {0};
+    if (TL) {
+        if (c->Finv.n != 9 * ld) { S4F_CHECK_CUDA(c, A(c->Finv, 9)); fillI(c->Finv, 9, dT, 3); }
+        if (c->Jt.n != ld) { S4F_CHECK_CUDA(c, A(c->Jt, 1)); fillI(c->Jt, 1, d1, 1); }
+        S4F_CHECK_CUDA(c, A(c->T9, 9));
+    }
+    if (c->lawSet && kind != S4F_LAW_LINEAR_ELASTIC) {
+        if (kind != S4F_LAW_LINEAR_ELASTIC_MISES_PLASTIC) {
+            if (c->lawF.n != 9 * ld) { S4F_CHECK_CUDA(c, A(c->lawF, 9)); fillI(c->lawF, 9, dT, 3); S4F_CHECK_CUDA(c, A(c->lawFold, 9)); fillI(c->lawFold, 9, dT, 3); }
+            if (c->lawJ.n != ld) { S4F_CHECK_CUDA(c, A(c->lawJ, 1)); fillI(c->lawJ, 1, d1, 1); S4F_CHECK_CUDA(c, A(c->lawJold, 1)); fillI(c->lawJold, 1, d1, 1); }
+        }
+        if (kind == S4F_LAW_NEO_HOOKEAN_MISES_PLASTIC || kind == S4F_LAW_LINEAR_ELASTIC_MISES_PLASTIC) {
+            if (c->bEbar.n != 6 * ld) {
+                S4F_CHECK_CUDA(c, A(c->bEbar, 6)); fillI(c->bEbar, 6, dS, 3); S4F_CHECK_CUDA(c, A(c->bEbarOld, 6)); fillI(c->bEbarOld, 6, dS, 3);
+            }
+            S4F_CHECK_CUDA(c, A(c->sigmaY, 1)); S4F_CHECK_CUDA(c, A(c->sigmaYOld, 1)); S4F_CHECK_CUDA(c, A(c->DSigmaY, 1));
+            S4F_CHECK_CUDA(c, A(c->epsPEq, 1)); S4F_CHECK_CUDA(c, A(c->epsPEqOld, 1)); S4F_CHECK_CUDA(c, A(c->DEpsPEq, 1));
+            S4F_CHECK_CUDA(c, A(c->epsP, 6)); S4F_CHECK_CUDA(c, A(c->epsPOld, 6)); S4F_CHECK_CUDA(c, A(c->DEpsP, 6)); S4F_CHECK_CUDA(c, A(c->DEpsPprev, 6));
+            S4F_CHECK_CUDA(c, A(c->DLambda, 1)); S4F_CHECK_CUDA(c, A(c->plasticN, 6)); S4F_CHECK_CUDA(c, A(c->epsilon, 6));
+        }
+    }
+    S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}

@@ -1,0 +1,164 @@
+"""Host-side mirror of the reference's solidModel interface for the GPU path.
+
+``SolidModel.New(case)`` plays ``solidModel::New`` (SM/solidModel/solidModel.C:1673-1749): it looks
+the model name up in a table and constructs it; the constructor mirrors mesh, geometry, law and
+boundary conditions into the device once (``s4fgpu_set_*``) and performs the constructor's consistent
+start (linGeomTotalDispSolid.C:82-84).  ``evolve()`` / ``updateTotalFields()`` / ``D()`` / ``sigma()``
+/ ``gradD()`` / ``setTraction()`` keep the reference names (solidModel.H:570-798).
+Everything numerical happens behind the C-ABI in CUDA; this file is plumbing only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import case as K
+from ._lib import lib
+
+KERNELS = dict(spmv1=0, spmv3=1, pcg_iter=2, grad=3, law=4, rhs=5)
+
+
+class SolidModel:
+    # run-time selection table: solidProperties "solidModel" -> enum behind the C-ABI.  The plugin
+    # registers the same names with the prefix "gpu" (foam_plugin/).
+    _table: Dict[str, int] = {
+        "gpuLinearGeometryTotalDisplacement": K.MODEL_LIN_GEOM_TOTAL_DISP,
+        "linearGeometryTotalDisplacement": K.MODEL_LIN_GEOM_TOTAL_DISP,
+        "gpuNonLinearGeometryTotalLagrangianTotalDisplacement": K.MODEL_NONLIN_TL_TOTAL_DISP,
+        "nonLinearGeometryTotalLagrangianTotalDisplacement": K.MODEL_NONLIN_TL_TOTAL_DISP,
+    }
+
+    @classmethod
+    def New(cls, case: K.SolidCase, solidModel: Optional[str] = None, device: int = 0, comm=None) -> "SolidModel":
+        if solidModel is not None:
+            if solidModel not in cls._table:
+                raise KeyError(f"Unknown solidModel type {solidModel}\nValid solidModel types are: {sorted(cls._table)}")
+            case.controls.solidModel = cls._table[solidModel]
+        return cls(case, device=device, comm=comm)
+
+    def __init__(self, case: K.SolidCase, device: int = 0, comm=None):
+        self.L = lib()
+        self.case = case
+        self.h = C.c_void_p()
+        rc = self.L.s4fgpu_create(C.byref(self.h), device)
+        if rc != 0:
+            raise RuntimeError("s4fgpu_create: " + self.L.s4fgpu_last_error(None).decode())
+        if comm is not None:
+            nRanks, rank, uid = comm
+            self._check(self.L.s4fgpu_comm_init(self.h, nRanks, rank, uid))
+        K.apply_case(self.L, "s4fgpu_", self.h, case, self._check)
+        self._check(self.L.s4fgpu_initialise(self.h))
+
+    # ---- plumbing ----
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise RuntimeError("libs4fgpu: " + self.L.s4fgpu_last_error(self.h).decode())
+
+    def close(self) -> None:
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.s4fgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def get(self, name: str) -> np.ndarray:
+        out = np.zeros(K.field_size(self.case.mesh, name))
+        self._check(self.L.s4fgpu_download(self.h, K.FIELD[name], K._dptr(out)))
+        return out
+
+    def set(self, name: str, a) -> None:
+        a = np.ascontiguousarray(a, dtype=np.float64).reshape(K.field_size(self.case.mesh, name))
+        self._check(self.L.s4fgpu_upload(self.h, K.FIELD[name], K._dptr(a)))
+
+    def set_controls(self, controls: K.Controls) -> None:
+        self.case.controls = controls
+        self._check(self.L.s4fgpu_set_controls(self.h, C.byref(controls)))
+
+    def set_bc(self, patch_name: str, bc: K.BC) -> None:
+        m = self.case.mesh
+        ip = [p.name for p in m.patches].index(patch_name)
+        p = m.patches[ip]
+        val = None if bc.value is None else np.ascontiguousarray(np.broadcast_to(bc.value, (p.size, 3)), dtype=np.float64)
+        pr = None if bc.pressure is None else np.ascontiguousarray(np.broadcast_to(bc.pressure, (p.size,)), dtype=np.float64)
+        self._check(self.L.s4fgpu_set_bc(self.h, ip, bc.kind, None if val is None else K._dptr(val),
+                                         None if pr is None else K._dptr(pr)))
+
+    # ---- reference-named interface ----
+    def setTraction(self, patch_name: str, traction, pressure=None) -> None:
+        """solidModel::setTraction (solidModel.C:1752-1817): new traction on a solidTraction patch."""
+        self.set_bc(patch_name, K.solidTraction(traction, pressure))
+
+    def initialise(self) -> None:
+        self._check(self.L.s4fgpu_initialise(self.h))
+
+    def new_timestep(self, deltaT: float = 1.0) -> None:
+        self._check(self.L.s4fgpu_new_timestep(self.h, deltaT))
+
+    def outer_iteration(self) -> dict:
+        st = K.Stats()
+        self._check(self.L.s4fgpu_outer_iteration(self.h, C.byref(st)))
+        return st.as_dict()
+
+    def evolve(self) -> dict:
+        st = K.Stats()
+        self._check(self.L.s4fgpu_evolve(self.h, C.byref(st)))
+        return st.as_dict()
+
+    def updateTotalFields(self) -> None:
+        self._check(self.L.s4fgpu_update_total_fields(self.h))
+
+    update_total_fields = updateTotalFields
+
+    def D(self) -> np.ndarray:
+        return self.get("D")
+
+    def gradD(self) -> np.ndarray:
+        return self.get("gradD")
+
+    def sigma(self) -> np.ndarray:
+        return self.get("sigma")
+
+    # ---- single operators ----
+    def op_grad(self) -> None:
+        self._check(self.L.s4fgpu_op_grad(self.h))
+
+    def op_correct(self) -> None:
+        self._check(self.L.s4fgpu_op_correct(self.h))
+
+    def op_assemble(self) -> None:
+        self._check(self.L.s4fgpu_op_assemble(self.h))
+
+    def op_amul(self, cmpt: int, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros_like(x)
+        self._check(self.L.s4fgpu_op_amul(self.h, cmpt, K._dptr(x), K._dptr(y)))
+        return y
+
+    def op_solve(self, psi: np.ndarray, source: np.ndarray):
+        psi = np.ascontiguousarray(psi, dtype=np.float64).copy()
+        source = np.ascontiguousarray(source, dtype=np.float64)
+        st = K.Stats()
+        self._check(self.L.s4fgpu_op_solve(self.h, K._dptr(psi), K._dptr(source), C.byref(st)))
+        return psi, st.as_dict()
+
+    def time_kernel(self, kernel: str, reps: int = 20, flush_l2: bool = True):
+        ms, by = C.c_double(), C.c_double()
+        self._check(self.L.s4fgpu_time_kernel(self.h, KERNELS[kernel], reps, 1 if flush_l2 else 0, C.byref(ms), C.byref(by)))
+        return ms.value, by.value
+
+    def launch_count(self) -> int:
+        return int(self.L.s4fgpu_launch_count(self.h))
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = lib().s4fgpu_get_unique_id(buf)
+    if rc != 0:
+        raise RuntimeError("ncclGetUniqueId failed")
+    return buf.raw
