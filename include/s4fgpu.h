@@ -253,6 +253,12 @@ enum {
 int s4fgpu_time_kernel(s4fgpu_handle h, int kernel, int reps, int flushL2,
                        double* msPerLaunch, double* algoBytesPerLaunch);
 
+/* CUDA-event timer on the library's own stream (torch.cuda.Event only sees torch's stream), and a
+ * stream synchronise.  timer_stop returns the device time in milliseconds since timer_start. */
+int s4fgpu_timer_start(s4fgpu_handle h);
+int s4fgpu_timer_stop(s4fgpu_handle h, double* ms);
+int s4fgpu_synchronize(s4fgpu_handle h);
+
 /* number of kernel launches issued by this handle since creation (bench.py gpu_launches) */
 long long s4fgpu_launch_count(s4fgpu_handle h);
 

@@ -28,6 +28,8 @@
 #include <string>
 #include <vector>
 
+#include <omp.h>
+
 #include "../include/s4fgpu.h"
 
 namespace {
@@ -144,10 +146,45 @@ struct s4f_oracle {
     long long totalInner = 0;
     int iCorrLast = 0;
 
+    // Host threading for the timing baseline only (nThreads == 1: the literal serial LDU loops).
+    // Cells are cut into nThreads contiguous index ranges ("ranks"); a face loop runs each range's
+    // own faces in parallel and the few faces that straddle two ranges afterwards, serially; DIC is
+    // applied per range and ignores the straddling faces, which is how OpenFOAM's DIC behaves across
+    // MPI ranks (block Jacobi).
+    int nThreads = 1;
+    ivec cellStart, faceStart, crossFaces;
+
     int NB() const { return N + B; }
 };
 
 namespace {
+
+
+void buildPartition(s4f_oracle& o) {
+    const int T = o.nThreads, N = o.N, F = o.F;
+    o.cellStart.assign(T + 1, 0); o.faceStart.assign(T + 1, 0); o.crossFaces.clear();
+    for (int t = 0; t <= T; t++) o.cellStart[t] = (int)((long long)N * t / T);
+    int f = 0;
+    for (int t = 0; t < T; t++) {            // faces are sorted by owner
+        o.faceStart[t] = f;
+        while (f < F && o.own[f] < o.cellStart[t + 1]) { if (o.nei[f] >= o.cellStart[t + 1]) o.crossFaces.push_back(f); f++; }
+    }
+    o.faceStart[T] = F;
+}
+
+// internal-face loop with owner/neighbour scatter: body(f) may write to own[f] and nei[f]
+template <class Body>
+inline void forAllInternalFaces(const s4f_oracle& o, Body body) {
+    if (o.nThreads <= 1) { for (int f = 0; f < o.F; f++) body(f); return; }
+#pragma omp parallel num_threads(o.nThreads)
+    {
+        const int t = omp_get_thread_num();
+        const int cEnd = o.cellStart[t + 1];
+        for (int f = o.faceStart[t]; f < o.faceStart[t + 1]; f++) if (o.nei[f] < cEnd) body(f);
+    }
+    for (size_t i = 0; i < o.crossFaces.size(); i++) body(o.crossFaces[i]);
+}
+#define S4FO_PAR_FOR _Pragma("omp parallel for schedule(static) num_threads(o.nThreads) if (o.nThreads > 1)")
 
 // ------------------------------------------------------------------------------------------------
 // least-squares vectors: NUM/extendedLeastSquaresGrad/extendedLeastSquaresVectors.C:121-158 (dd),
@@ -309,21 +346,21 @@ void calcGrad(s4f_oracle& o) {
     const int N = o.N, F = o.F, B = o.B;
     dvec g(9 * (N + B), 0.0);
     if (o.ctl.gradScheme == S4F_GRAD_LEAST_SQUARES) {
-        for (int f = 0; f < F; f++) {
+        forAllInternalFaces(o, [&](int f) {
             int P = o.own[f], Nn = o.nei[f];
             double dv[3] = {o.D[3 * Nn] - o.D[3 * P], o.D[3 * Nn + 1] - o.D[3 * P + 1], o.D[3 * Nn + 2] - o.D[3 * P + 2]};
             for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
                 g[9 * P + 3 * i + j] += o.lsP[3 * f + i] * dv[j];
                 g[9 * Nn + 3 * i + j] -= o.lsN[3 * f + i] * dv[j];
             }
-        }
+        });
         for (int b = 0; b < B; b++) {
             int P = o.faceCells[b];
             double dv[3] = {o.D[3 * (N + b)] - o.D[3 * P], o.D[3 * (N + b) + 1] - o.D[3 * P + 1], o.D[3 * (N + b) + 2] - o.D[3 * P + 2]};
             for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) g[9 * P + 3 * i + j] += o.lsP[3 * (F + b) + i] * dv[j];
         }
     } else {
-        for (int f = 0; f < F; f++) {
+        forAllInternalFaces(o, [&](int f) {
             int P = o.own[f], Nn = o.nei[f];
             double wf = o.w[f];
             for (int j = 0; j < 3; j++) {
@@ -333,7 +370,7 @@ void calcGrad(s4f_oracle& o) {
                     g[9 * P + 3 * i + j] += t; g[9 * Nn + 3 * i + j] -= t;
                 }
             }
-        }
+        });
         for (int b = 0; b < B; b++) {
             int P = o.faceCells[b];
             for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) g[9 * P + 3 * i + j] += o.Sf[3 * (F + b) + i] * o.D[3 * (N + b) + j];
@@ -363,6 +400,7 @@ void calcGrad(s4f_oracle& o) {
 void lawLinearElastic(s4f_oracle& o) {
     const int n = o.NB();
     const double mu = o.law.mu, K = o.law.K;
+    S4FO_PAR_FOR
     for (int c = 0; c < n; c++) {
         double e[6]; symm(&o.gradD[9 * c], e);
         for (int q = 0; q < 6; q++) o.epsilon[6 * c + q] = e[q];
@@ -663,30 +701,31 @@ void assembleSource(s4f_oracle& o) {
             s[3 * c + q] += rDeltaT2 * o.V[c] * o.law.rho * ((coefft + coefft00) * o.Dold[3 * c + q] - coefft00 * o.DoldOld[3 * c + q]);
     }
     // - V*fvc::laplacian(impKf, D): compact part, face flux impKf*magSf*delta*(D_N - D_P)
-    for (int f = 0; f < F; f++) {
+    forAllInternalFaces(o, [&](int f) {
         int P = o.own[f], Nn = o.nei[f];
         double a = -o.upper[f];
         for (int q = 0; q < 3; q++) {
             double flux = a * (o.D[3 * Nn + q] - o.D[3 * P + q]);
             s[3 * P + q] -= flux; s[3 * Nn + q] += flux;
         }
-    }
+    });
     // + V*fvc::div(sigma)  [OF-ext] gaussDivScheme, linear:  Sf & (w sigma_P + (1-w) sigma_N)
     // TL: the cell tensor is J*Finv & sigma (nonLinGeomTotalLagTotalDispSolid.C:206)
     dvec T;   // full tensor per cell/boundary face
     T.resize(9 * (N + B));
+    S4FO_PAR_FOR
     for (int c = 0; c < N + B; c++) {
         double sg[9]; S2T(&o.sigma[6 * c], sg);
         if (TL) { double t[9]; mulTT(&o.Finv[9 * c], sg, t); for (int q = 0; q < 9; q++) T[9 * c + q] = o.Jt[c] * t[q]; }
         else for (int q = 0; q < 9; q++) T[9 * c + q] = sg[q];
     }
-    for (int f = 0; f < F; f++) {
+    forAllInternalFaces(o, [&](int f) {
         int P = o.own[f], Nn = o.nei[f];
         double wf = o.w[f], Tf[9];
         for (int q = 0; q < 9; q++) Tf[q] = wf * T[9 * P + q] + (1 - wf) * T[9 * Nn + q];
         double fl[3]; vT(&o.Sf[3 * f], Tf, fl);
         for (int q = 0; q < 3; q++) { s[3 * P + q] += fl[q]; s[3 * Nn + q] -= fl[q]; }
-    }
+    });
     for (int b = 0; b < B; b++) {
         double fl[3]; vT(&o.Sf[3 * (F + b)], &T[9 * (N + b)], fl);
         for (int q = 0; q < 3; q++) s[3 * o.faceCells[b] + q] += fl[q];
@@ -698,7 +737,7 @@ void assembleSource(s4f_oracle& o) {
     // :210-217  fvc::laplacian(gammaf, D) - fvc::div(gammaf*(Sf & interpolate(gradD)))
     if (o.ctl.stabilisation == S4F_STAB_RHIE_CHOW) {
         const double sf = o.ctl.stabScaleFactor;
-        for (int f = 0; f < F; f++) {
+        forAllInternalFaces(o, [&](int f) {
             int P = o.own[f], Nn = o.nei[f];
             double wf = o.w[f];
             double gP = sf * o.impK[P], gN = sf * o.impK[Nn];
@@ -712,7 +751,7 @@ void assembleSource(s4f_oracle& o) {
                 double flux = gf * (o.magSf[f] * sn - Sg[q]);
                 s[3 * P + q] += flux; s[3 * Nn + q] -= flux;
             }
-        }
+        });
     }
     // boundary: - impKf_b*magSf_b*snGrad_b (from -V*fvc::laplacian) and + boundaryCoeffs (addBoundarySource)
     o.bouCoeffs.assign(3 * B, 0.0);
@@ -743,12 +782,14 @@ void assembleSource(s4f_oracle& o) {
 // ------------------------------------------------------------------------------------------------
 void Amul(const s4f_oracle& o, const double* diag, const double* x, double* y) {
     const int N = o.N, F = o.F;
+    S4FO_PAR_FOR
     for (int c = 0; c < N; c++) y[c] = diag[c] * x[c];
-    for (int f = 0; f < F; f++) {
+    (void)F;
+    forAllInternalFaces(o, [&](int f) {
         int l = o.own[f], u = o.nei[f];
         y[u] += o.upper[f] * x[l];   // lower == upper (symmetric)
         y[l] += o.upper[f] * x[u];
-    }
+    });
 }
 
 struct Precond {
@@ -757,7 +798,16 @@ struct Precond {
         kind = k; const int N = o.N, F = o.F;
         if (kind == S4F_PRECOND_DIC) {
             rD.assign(diag, diag + N);
-            for (int f = 0; f < F; f++) rD[o.nei[f]] -= o.upper[f] * o.upper[f] / rD[o.own[f]];
+            if (o.nThreads <= 1) {
+                for (int f = 0; f < F; f++) rD[o.nei[f]] -= o.upper[f] * o.upper[f] / rD[o.own[f]];
+            } else {
+#pragma omp parallel num_threads(o.nThreads)
+                {
+                    const int t = omp_get_thread_num(), cEnd = o.cellStart[t + 1];
+                    for (int f = o.faceStart[t]; f < o.faceStart[t + 1]; f++)
+                        if (o.nei[f] < cEnd) rD[o.nei[f]] -= o.upper[f] * o.upper[f] / rD[o.own[f]];
+                }
+            }
             for (int c = 0; c < N; c++) rD[c] = 1.0 / rD[c];
         } else if (kind == S4F_PRECOND_DIAGONAL) {
             rD.resize(N); for (int c = 0; c < N; c++) rD[c] = 1.0 / diag[c];
@@ -766,10 +816,22 @@ struct Precond {
     void apply(const s4f_oracle& o, double* w, const double* r) const {
         const int N = o.N, F = o.F;
         if (kind == S4F_PRECOND_NONE) { std::memcpy(w, r, sizeof(double) * N); return; }
+        S4FO_PAR_FOR
         for (int c = 0; c < N; c++) w[c] = rD[c] * r[c];
         if (kind == S4F_PRECOND_DIC) {
-            for (int f = 0; f < F; f++) w[o.nei[f]] -= rD[o.nei[f]] * o.upper[f] * w[o.own[f]];
-            for (int f = F - 1; f >= 0; f--) w[o.own[f]] -= rD[o.own[f]] * o.upper[f] * w[o.nei[f]];
+            if (o.nThreads <= 1) {
+                for (int f = 0; f < F; f++) w[o.nei[f]] -= rD[o.nei[f]] * o.upper[f] * w[o.own[f]];
+                for (int f = F - 1; f >= 0; f--) w[o.own[f]] -= rD[o.own[f]] * o.upper[f] * w[o.nei[f]];
+            } else {
+#pragma omp parallel num_threads(o.nThreads)
+                {
+                    const int t = omp_get_thread_num(), cEnd = o.cellStart[t + 1];
+                    for (int f = o.faceStart[t]; f < o.faceStart[t + 1]; f++)
+                        if (o.nei[f] < cEnd) w[o.nei[f]] -= rD[o.nei[f]] * o.upper[f] * w[o.own[f]];
+                    for (int f = o.faceStart[t + 1] - 1; f >= o.faceStart[t]; f--)
+                        if (o.nei[f] < cEnd) w[o.own[f]] -= rD[o.own[f]] * o.upper[f] * w[o.nei[f]];
+                }
+            }
         }
     }
 };
@@ -796,15 +858,26 @@ SolverPerf solvePCG(s4f_oracle& o, const double* diag, double* psi, const double
         do {
             wArAold = wArA;
             pre.apply(o, wA.data(), rA.data());
-            wArA = 0; for (int c = 0; c < N; c++) wArA += wA[c] * rA[c];
-            if (perf.nIter == 0) { for (int c = 0; c < N; c++) pA[c] = wA[c]; }
-            else { double beta = wArA / wArAold; for (int c = 0; c < N; c++) pA[c] = wA[c] + beta * pA[c]; }
+            wArA = 0;
+#pragma omp parallel for schedule(static) reduction(+ : wArA) num_threads(o.nThreads) if (o.nThreads > 1)
+            for (int c = 0; c < N; c++) wArA += wA[c] * rA[c];
+            if (perf.nIter == 0) {
+                S4FO_PAR_FOR
+                for (int c = 0; c < N; c++) pA[c] = wA[c];
+            } else {
+                double beta = wArA / wArAold;
+                S4FO_PAR_FOR
+                for (int c = 0; c < N; c++) pA[c] = wA[c] + beta * pA[c];
+            }
             Amul(o, diag, pA.data(), wA.data());
-            double wApA = 0; for (int c = 0; c < N; c++) wApA += wA[c] * pA[c];
+            double wApA = 0;
+#pragma omp parallel for schedule(static) reduction(+ : wApA) num_threads(o.nThreads) if (o.nThreads > 1)
+            for (int c = 0; c < N; c++) wApA += wA[c] * pA[c];
             if (std::fabs(wApA) / nf < VSMALL) break;   // checkSingularity
             double alpha = wArA / wApA;
-            for (int c = 0; c < N; c++) { psi[c] += alpha * pA[c]; rA[c] -= alpha * wA[c]; }
-            sm = 0; for (int c = 0; c < N; c++) sm += std::fabs(rA[c]);
+            sm = 0;
+#pragma omp parallel for schedule(static) reduction(+ : sm) num_threads(o.nThreads) if (o.nThreads > 1)
+            for (int c = 0; c < N; c++) { psi[c] += alpha * pA[c]; rA[c] -= alpha * wA[c]; sm += std::fabs(rA[c]); }
             perf.finalRes = sm / nf;
         } while (++perf.nIter < o.ctl.maxIter && !converged(perf.finalRes));
     }
@@ -1086,5 +1159,12 @@ int s4fo_get_ls_vectors(s4f_oracle* o, double* lsP, double* lsN) {
     std::memcpy(lsN, o->lsN.data(), sizeof(double) * o->lsN.size()); return 0;
 }
 double s4fo_table_lookup(const s4fgpu_law* law, double x) { return tableLookup(*law, x); }
+// host threads for the timing baseline (0 = all cores); 1 restores the literal serial loops
+int s4fo_set_threads(s4f_oracle* o, int n) {
+    if (n <= 0) n = omp_get_max_threads();
+    o->nThreads = n;
+    if (n > 1) buildPartition(*o);
+    return n;
+}
 
 }  // extern "C"

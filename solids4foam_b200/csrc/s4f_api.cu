@@ -123,6 +123,7 @@ int s4fgpu_destroy(s4fgpu_handle c) {
     if (c->comm) ncclCommDestroy(c->comm);
     if (c->hPcgS) cudaFreeHost(c->hPcgS);
     if (c->hOutS) cudaFreeHost(c->hOutS);
+    if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
     cudaStream_t s = c->stream;
     delete c;
     cudaStreamDestroy(s);
@@ -406,5 +407,27 @@ int s4fgpu_time_kernel(s4fgpu_handle c, int kernel, int reps, int flushL2, doubl
 }
 
 long long s4fgpu_launch_count(s4fgpu_handle c) { return c ? c->launches : 0; }
+
+int s4fgpu_timer_start(s4fgpu_handle c) {
+    S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
+    if (!c->ev0) { S4F_CHECK_CUDA(c, cudaEventCreate(&c->ev0)); S4F_CHECK_CUDA(c, cudaEventCreate(&c->ev1)); }
+    S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+    S4F_CHECK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    return 0;
+}
+int s4fgpu_timer_stop(s4fgpu_handle c, double* ms) {
+    S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
+    S4F_REQUIRE(c, c->ev0, "timer_stop without timer_start");
+    S4F_CHECK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    S4F_CHECK_CUDA(c, cudaEventSynchronize(c->ev1));
+    float f; S4F_CHECK_CUDA(c, cudaEventElapsedTime(&f, c->ev0, c->ev1));
+    *ms = f;
+    return 0;
+}
+int s4fgpu_synchronize(s4fgpu_handle c) {
+    S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
+    S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
 
 }  // extern "C"

@@ -103,6 +103,7 @@ struct s4fgpu_ctx {
     cudaStream_t stream = nullptr;
     int numSMs = 148;
     long long launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     // ---- parallel ----
     ncclComm_t comm = nullptr;

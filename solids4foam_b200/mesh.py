@@ -301,6 +301,8 @@ def hex_box(nx: int, ny: int, nz: int, L: float = 1.0, H: float = 1.0, W: float 
     """
     if i1 is None:
         i1 = nx
+    if point_map is None:
+        return _hex_box_rectilinear(nx, ny, nz, L, H, W, i0, i1, rank, nRanks, names, kinds)
     mx = i1 - i0
     has_lo = i0 > 0
     has_hi = i1 < nx
@@ -471,6 +473,92 @@ def hex_box(nx: int, ny: int, nz: int, L: float = 1.0, H: float = 1.0, W: float 
     gk, gj, gI = ck, cj, ci + i0
     cellGlobal = (gI + nx * (gj + ny * gk)).astype(np.int64)
     return _finish_mesh(nCells, owner, neighbour, faceCells, patches, C, V, Sf, Cf, Cnbr, solutionD,
+                        cellGlobal=cellGlobal, rank=rank, nRanks=nRanks,
+                        meta=dict(nx=nx, ny=ny, nz=nz, L=L, H=H, W=W, i0=i0, i1=i1))
+
+
+def _hex_box_rectilinear(nx, ny, nz, L, H, W, i0, i1, rank, nRanks, names, kinds) -> FvMesh:
+    """Closed-form geometry of an undistorted box (same numbering as ``hex_box``; used for the large
+    benchmark meshes where building points and faces would dominate the run)."""
+    mx = i1 - i0
+    dx, dy, dz = L / nx, H / ny, W / nz
+    has_lo, has_hi = i0 > 0, i1 < nx
+    nCells = mx * ny * nz
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(mx), indexing="ij")
+    ci, cj, ck = i.ravel(), j.ravel(), k.ravel()
+    del i, j, k
+    C = np.stack([(ci + i0 + 0.5) * dx, (cj + 0.5) * dy, (ck + 0.5) * dz], axis=1)
+    V = np.full(nCells, dx * dy * dz)
+    hasx, hasy, hasz = ci < mx - 1, cj < ny - 1, ck < nz - 1
+    cnt = hasx.astype(np.int64) + hasy + hasz
+    start = np.cumsum(cnt) - cnt
+    F = int(cnt.sum())
+    owner = np.empty(F, dtype=np.int32)
+    neighbour = np.empty(F, dtype=np.int32)
+    Sf = np.zeros((F, 3))
+    Cf = np.empty((F, 3))
+    cid = np.arange(nCells, dtype=np.int64)
+    for d, (sel, off, stride, area) in enumerate(((hasx, 0, 1, dy * dz), (hasy, hasx, mx, dx * dz),
+                                                  (hasz, hasx.astype(np.int64) + hasy, mx * ny, dx * dy))):
+        f = start[sel] + (off[sel] if not isinstance(off, int) else off)
+        owner[f] = cid[sel]
+        neighbour[f] = cid[sel] + stride
+        Sf[f, d] = area
+        cf = C[sel].copy()
+        cf[:, d] += 0.5 * (dx, dy, dz)[d]
+        Cf[f] = cf
+    # boundary sides
+    def side(s):
+        d, hi = s // 2, s % 2
+        if d == 0:
+            kk, jj = np.meshgrid(np.arange(nz), np.arange(ny), indexing="ij")
+            jj, kk = jj.ravel(), kk.ravel()
+            cells = ((mx - 1) if hi else 0) + mx * (jj + ny * kk)
+        elif d == 1:
+            kk, ii = np.meshgrid(np.arange(nz), np.arange(mx), indexing="ij")
+            ii, kk = ii.ravel(), kk.ravel()
+            cells = ii + mx * (((ny - 1) if hi else 0) + ny * kk)
+        else:
+            jj, ii = np.meshgrid(np.arange(ny), np.arange(mx), indexing="ij")
+            ii, jj = ii.ravel(), jj.ravel()
+            cells = ii + mx * (jj + ny * ((nz - 1) if hi else 0))
+        area = (dy * dz, dx * dz, dx * dy)[d]
+        sf = np.zeros((cells.size, 3))
+        sf[:, d] = area if hi else -area
+        cf = C[cells].copy()
+        cf[:, d] += (0.5 if hi else -0.5) * (dx, dy, dz)[d]
+        cn = C[cells].copy()
+        cn[:, d] += (1.0 if hi else -1.0) * (dx, dy, dz)[d]
+        return cells.astype(np.int64), sf, cf, cn
+    patches: List[PatchInfo] = []
+    b_cells, b_Sf, b_Cf, b_Cn = [], [], [], []
+    solutionD = np.ones(3, dtype=np.int32)
+    startB = 0
+
+    def add(name, kind, s, nbr=-1):
+        nonlocal startB
+        cells, sf, cf, cn = side(s)
+        patches.append(PatchInfo(name, kind, startB, cells.size, nbr))
+        b_cells.append(cells); b_Sf.append(sf); b_Cf.append(cf)
+        b_Cn.append(cn if kind == PROCESSOR else cf)
+        startB += cells.size
+    for s in range(6):
+        if (s == 0 and has_lo) or (s == 1 and has_hi):
+            continue
+        if kinds[s] == EMPTY:
+            solutionD[s // 2] = 0
+            continue
+        add(names[s], kinds[s], s)
+    if has_lo:
+        add(f"procBoundary{rank}to{rank - 1}", PROCESSOR, 0, rank - 1)
+    if has_hi:
+        add(f"procBoundary{rank}to{rank + 1}", PROCESSOR, 1, rank + 1)
+    faceCells = np.concatenate(b_cells)
+    SfA = np.concatenate([Sf] + b_Sf)
+    CfA = np.concatenate([Cf] + b_Cf)
+    Cnbr = np.concatenate(b_Cn)
+    cellGlobal = ((ci + i0) + nx * (cj + ny * ck)).astype(np.int64)
+    return _finish_mesh(nCells, owner, neighbour, faceCells, patches, C, V, SfA, CfA, Cnbr, solutionD,
                         cellGlobal=cellGlobal, rank=rank, nRanks=nRanks,
                         meta=dict(nx=nx, ny=ny, nz=nz, L=L, H=H, W=W, i0=i0, i1=i1))
 

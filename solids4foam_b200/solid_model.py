@@ -152,6 +152,17 @@ class SolidModel:
         self._check(self.L.s4fgpu_time_kernel(self.h, KERNELS[kernel], reps, 1 if flush_l2 else 0, C.byref(ms), C.byref(by)))
         return ms.value, by.value
 
+    def timer_start(self) -> None:
+        self._check(self.L.s4fgpu_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self._check(self.L.s4fgpu_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def synchronize(self) -> None:
+        self._check(self.L.s4fgpu_synchronize(self.h))
+
     def launch_count(self) -> int:
         return int(self.L.s4fgpu_launch_count(self.h))
 
