@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""Short driver for ncu: builds the hex-cantilever case and launches every hot kernel a few times
+through the C-ABI timing entry (s4fgpu_time_kernel), plus a few outer iterations.
+
+    ncu --set full --clock-control none --import-source on -k regex:'k_amul3|k_source|k_grad|k_pcg' \
+        -c 12 -o gpurun_out/prof python profiles/prof_kernels.py 800,100,100
+
+Numbers printed under ncu are NOT bench values."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from solids4foam_b200 import case as K  # noqa: E402
+from solids4foam_b200 import cases  # noqa: E402
+from solids4foam_b200.solid_model import SolidModel  # noqa: E402
+
+
+def main():
+    dims = tuple(int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "800,100,100").split(","))
+    outer = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    pre = getattr(K, "PRECOND_" + (sys.argv[3] if len(sys.argv) > 3 else "DIAGONAL"))
+    g = SolidModel(cases.cantilever(*dims, preconditioner=pre, maxIter=20 if outer else 1000))
+    for _ in range(outer):
+        g.outer_iteration()
+    for name in ("spmv3", "spmv1", "pcg_iter", "grad", "rhs", "law"):
+        ms, by = g.time_kernel(name, reps=2, flush_l2=False)
+        print(f"{name:9s} {ms:8.4f} ms  {by / ms / 1e6:8.1f} GB/s (under a profiler: not a bench value)")
+
+
+if __name__ == "__main__":
+    main()

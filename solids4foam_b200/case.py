@@ -229,7 +229,7 @@ def _iptr(a: np.ndarray):
 
 def apply_case(lib, prefix: str, handle, case: SolidCase, check) -> None:
     """Mirror mesh, geometry, law, controls and BCs through the C-ABI (``prefix`` = ``s4fgpu_``; the
-    tests reuse this plumbing for the oracle's ``s4fo_`` mirror of the same interface)."""
+    tests reuse this plumbing, with another prefix, for their CPU checker's mirror of the same interface)."""
     m = case.mesh
     f = lambda n: getattr(lib, prefix + n)
     own = np.ascontiguousarray(m.owner, dtype=np.int32)

@@ -1,0 +1,435 @@
+"""CPU tests of the oracle (oracle/s4f_oracle.cpp) against the known-answer material the reference ships.
+
+The reference holds no golden fields for this path; what it does hold are closed forms:
+  * Kirsch plate-with-hole stress/displacement  (plateHoleAnalyticalSolution.C:43-122),
+  * the patch test's exact constant strain       (tutorials/solids/linearElasticity/patchTest/README.md:102-113),
+  * the laws' own formulas on single-cell states (linearElastic.C:318-339, neoHookeanElastic.C:275-303,
+    neoHookeanElasticMisesPlastic.C:991-1223) and the neckingBar hardening table,
+plus independent numerics (scipy.sparse) for the [OF-ext] pieces: Amul, PCG, DIC.
+The committed fixtures under tests/golden/ (made by tests/golden/make_golden.py from those closed forms)
+are checked here too.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from oracle.binding import OracleSolid, lib as oracle_lib_fn
+from solids4foam_b200 import case as K
+from solids4foam_b200 import cases
+from solids4foam_b200 import mesh as M
+from s4f_testutil import rel_l2
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+# ---------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------
+def one_cell_case(law, model=K.MODEL_LIN_GEOM_TOTAL_DISP, **ctl):
+    mesh = M.hex_box(2, 1, 1, 2.0, 1.0, 1.0, names=("a", "b", "c", "d", "e", "f"))
+    bcs = {p.name: K.solidTraction((0.0, 0.0, 0.0)) for p in mesh.patches}
+    return K.SolidCase(mesh, bcs, law, K.default_controls(solidModel=model, **ctl))
+
+
+def ldu_to_csr(mesh, upper, diag):
+    """[OF-ext] lduMatrix -> scipy CSR (symmetric: lower == upper)."""
+    N = mesh.nCells
+    o, n = mesh.owner, mesh.neighbour
+    A = sp.coo_matrix((np.concatenate([upper, upper, diag]),
+                       (np.concatenate([o, n, np.arange(N)]), np.concatenate([n, o, np.arange(N)]))), shape=(N, N))
+    return A.tocsr()
+
+
+def sym6(S):
+    return np.array([[S[0], S[1], S[2]], [S[1], S[3], S[4]], [S[2], S[4], S[5]]])
+
+
+# ---------------------------------------------------------------------------------------------
+# hardening table: s4f interpolationTable (NUM/interpolationTable/interpolationTable.C:493-632)
+# ---------------------------------------------------------------------------------------------
+def test_hardening_table_necking_bar():
+    L = oracle_lib_fn()
+    law = K.mechanical_law("neoHookeanElasticMisesPlastic", E=200e9, nu=0.3, table=K.NECKING_BAR_TABLE)
+    eps = np.array([e for e, _ in K.NECKING_BAR_TABLE])
+    sig = np.array([s for _, s in K.NECKING_BAR_TABLE])
+    for x in (-1.0, 0.0, 1e-15, 0.003, 0.006, 0.0125, 0.1, 0.4999, 0.5, 0.75, 1.0, 3.0):
+        got = L.s4fo_table_lookup(law, x)
+        want = np.interp(x, eps, sig)          # piece-wise linear, clamped at both ends
+        assert got == pytest.approx(want, rel=1e-14), x
+    with open(os.path.join(GOLDEN, "necking_bar_table.json")) as f:
+        g = json.load(f)
+    for x, want in zip(g["x"], g["sigmaY"]):
+        assert L.s4fo_table_lookup(law, x) == pytest.approx(want, rel=1e-14)
+
+
+# ---------------------------------------------------------------------------------------------
+# laws on a uniform state
+# ---------------------------------------------------------------------------------------------
+def _law_sigma(law, gradD, model=K.MODEL_LIN_GEOM_TOTAL_DISP):
+    o = OracleSolid(one_cell_case(law, model))
+    g = np.tile(np.asarray(gradD, dtype=float).reshape(1, 9), (o.case.mesh.nCells, 1))
+    o.set("gradD", g)
+    o.op_correct()
+    return o, o.get("sigma")[0]
+
+
+def test_linear_elastic_closed_forms():
+    E, nu = 200e9, 0.3
+    law = K.mechanical_law("linearElastic", E=E, nu=nu)
+    mu, lam = E / (2 * (1 + nu)), nu * E / ((1 + nu) * (1 - 2 * nu))
+    assert law.mu == pytest.approx(mu) and law.lambda_ == pytest.approx(lam) and law.K == pytest.approx(lam + 2 * mu / 3)
+    # uniaxial strain e_xx: sigma_xx = (2mu+lambda) e, sigma_yy = lambda e
+    _, s = _law_sigma(law, [1e-3, 0, 0, 0, 0, 0, 0, 0, 0])
+    assert s[0] == pytest.approx((2 * mu + lam) * 1e-3, rel=1e-13)
+    assert s[3] == pytest.approx(lam * 1e-3, rel=1e-13) and s[5] == pytest.approx(lam * 1e-3, rel=1e-13)
+    # simple shear dDy/dx = g (gradD_01): sigma_xy = mu g
+    _, s = _law_sigma(law, [0, 2e-3, 0, 0, 0, 0, 0, 0, 0])
+    assert s[1] == pytest.approx(mu * 2e-3, rel=1e-13)
+    assert abs(s[0]) < 1e-3 and abs(s[3]) < 1e-3
+    # rigid rotation (skew gradD): no stress in the small-strain law
+    _, s = _law_sigma(law, [0, 1e-3, 0, -1e-3, 0, 0, 0, 0, 0])
+    assert np.abs(s).max() < 1e-3
+    # plane stress parameters (linearElastic.C:105-118)
+    lawPS = K.mechanical_law("linearElastic", E=E, nu=nu, planeStress=True)
+    assert lawPS.lambda_ == pytest.approx(nu * E / ((1 + nu) * (1 - nu)))
+    assert lawPS.K == pytest.approx(E / (3 * (1 - nu)))
+    # sigma0
+    law0 = K.mechanical_law("linearElastic", E=E, nu=nu, sigma0=[1e5, 2e5, 3e5, 4e5, 5e5, 6e5])
+    _, s = _law_sigma(law0, [0] * 9)
+    assert np.allclose(s, [1e5, 2e5, 3e5, 4e5, 5e5, 6e5])
+
+
+def test_neo_hookean_closed_forms():
+    E, nu = 3e6, 0.3
+    law = K.mechanical_law("neoHookeanElastic", E=E, nu=nu)
+    mu = E / (2 * (1 + nu))
+    Kb = nu * E / ((1 + nu) * (1 - 2 * nu)) + 2 * mu / 3          # neoHookeanElastic.C:70-78
+    assert law.mu == pytest.approx(mu) and law.K == pytest.approx(Kb)
+    # volumetric stretch F = a I: s = 0, sigma = K (J^2-1)/(2J) I
+    a = 1.1
+    _, s = _law_sigma(law, np.diag([a - 1] * 3).ravel(), K.MODEL_NONLIN_TL_TOTAL_DISP)
+    J = a**3
+    assert np.allclose(s[[0, 3, 5]], 0.5 * Kb * (J * J - 1) / J, rtol=1e-12)
+    assert np.abs(s[[1, 2, 4]]).max() < 1e-6
+    # simple shear F = I + g e_x (x) e_y  (gradD_ij = d_i D_j -> gradD[1,0] = g): J = 1,
+    # b = F F^T = [[1+g^2, g, 0],[g,1,0],[0,0,1]], sigma = mu dev(b)
+    g = 0.2
+    gD = np.zeros((3, 3)); gD[1, 0] = g
+    _, s = _law_sigma(law, gD.ravel(), K.MODEL_NONLIN_TL_TOTAL_DISP)
+    b = np.array([[1 + g * g, g, 0], [g, 1, 0], [0, 0, 1.0]])
+    want = mu * (b - np.trace(b) / 3 * np.eye(3))
+    assert np.allclose(sym6(s), want, rtol=1e-12, atol=1e-9)
+    # rigid rotation: F = R -> b = I, J = 1 -> zero stress (objectivity)
+    th = 0.3
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    _, s = _law_sigma(law, (R - np.eye(3)).T.ravel(), K.MODEL_NONLIN_TL_TOTAL_DISP)
+    assert np.abs(s).max() < 1e-8 * mu
+
+
+def test_mises_plastic_uniaxial_return_map():
+    """neoHookeanElasticMisesPlastic below / above yield on an isochoric stretch, against the radial-return
+    closed form with linear hardening (two-point table -> Hp, ...MisesPlastic.C:922-930, :1107-1115)."""
+    E, nu = 200e9, 0.3
+    sy0, Hp = 400e6, 2e9
+    law = K.mechanical_law("neoHookeanElasticMisesPlastic", E=E, nu=nu, table=[(0.0, sy0), (1.0, sy0 + Hp)])
+    mu = E / (2 * (1 + nu))
+    for lam in (1.0005, 1.01):       # elastic, plastic
+        Fm = np.diag([lam, lam**-0.5, lam**-0.5])
+        o, s = _law_sigma(law, (Fm - np.eye(3)).T.ravel(), K.MODEL_NONLIN_TL_TOTAL_DISP)
+        bt = Fm @ Fm.T                                  # J = 1, bEbar_old = I
+        sT = mu * (bt - np.trace(bt) / 3 * np.eye(3))
+        magS = np.sqrt((sT * sT).sum())
+        muBar = mu * np.trace(bt) / 3
+        f = magS - np.sqrt(2 / 3) * sy0
+        if f < 0:
+            want = sT
+            assert o.get("DLambda")[0] == 0.0
+        else:
+            dl = f / (2 * muBar) / (1 + Hp / (3 * muBar))
+            n = sT / magS
+            want = sT - 2 * mu * (np.trace(bt) / 3) * dl * n
+            assert o.get("DLambda")[0] == pytest.approx(dl, rel=1e-12)
+            # consistency: |s| = sqrt(2/3) (sy0 + Hp sqrt(2/3) dl) up to the muBar/mu factor of the update
+        dev = sym6(s) - np.trace(sym6(s)) / 3 * np.eye(3)
+        assert np.allclose(dev, want, rtol=1e-10, atol=1.0)
+        assert abs(np.trace(sym6(s))) < 1e-3 * mu           # J = 1 -> sigmaHyd = 0
+        be = sym6(o.get("bEbar")[0])
+        assert np.linalg.det(be) == pytest.approx(1.0, abs=1e-10)   # Rubin-Attia Ibar (:250-395)
+
+
+def test_mises_tabulated_newton_satisfies_yield_surface():
+    """Tabulated hardening (neckingBar, 8 points): after newtonLoop (:186-247) the stress sits on the
+    updated yield surface |s| = sqrt(2/3) J sigmaY(epsPEq_old + sqrt(2/3) DLambda)."""
+    law = K.mechanical_law("neoHookeanElasticMisesPlastic", E=200e9, nu=0.3, table=K.NECKING_BAR_TABLE)
+    mu = law.mu
+    lam = 1.02
+    Fm = np.diag([lam, lam**-0.5, lam**-0.5])
+    o, s = _law_sigma(law, (Fm - np.eye(3)).T.ravel(), K.MODEL_NONLIN_TL_TOTAL_DISP)
+    dl = o.get("DLambda")[0]
+    assert dl > 0
+    bt = Fm @ Fm.T
+    sT = mu * (bt - np.trace(bt) / 3 * np.eye(3))
+    muBar = mu * np.trace(bt) / 3
+    eps = np.array([e for e, _ in K.NECKING_BAR_TABLE]); sig = np.array([x for _, x in K.NECKING_BAR_TABLE])
+    sy = np.interp(np.sqrt(2 / 3) * dl, eps, sig)
+    resid = np.sqrt((sT * sT).sum()) - 2 * muBar * dl - np.sqrt(2 / 3) * sy
+    assert abs(resid) < 1e-6 * sy
+
+
+def test_linear_elastic_mises_small_strain_return():
+    E, nu, sy0, Hp = 200e9, 0.3, 300e6, 5e9
+    law = K.mechanical_law("linearElasticMisesPlastic", E=E, nu=nu, table=[(0.0, sy0), (1.0, sy0 + Hp)])
+    mu, Kb = law.mu, law.K
+    eps = np.diag([4e-3, -2e-3, -2e-3])
+    o, s = _law_sigma(law, eps.ravel())
+    sT = 2 * mu * eps
+    magS = np.sqrt((sT * sT).sum())
+    dl = (magS - np.sqrt(2 / 3) * sy0) / (2 * mu) / (1 + Hp / (3 * mu))
+    want = sT - 2 * mu * dl * sT / magS + Kb * np.trace(eps) * np.eye(3)
+    assert np.allclose(sym6(s), want, rtol=1e-11)
+    assert o.get("epsilonPEq")[0] == pytest.approx(np.sqrt(2 / 3) * dl, rel=1e-11)
+
+
+# ---------------------------------------------------------------------------------------------
+# gradient: exact for linear fields (least squares and Gauss on orthogonal meshes)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scheme", [K.GRAD_LEAST_SQUARES, K.GRAD_GAUSS_LINEAR])
+def test_gradient_of_linear_field(scheme):
+    c = cases.cantilever(6, 4, 3, gradScheme=scheme)
+    m = c.mesh
+    Bm = np.array([[1e-3, 2e-3, -1e-3], [3e-3, -2e-3, 5e-4], [7e-4, 1e-3, 2e-3]])   # D_j = sum_i x_i B_ij
+    for p in m.patches:
+        cf = m.Cf[m.nInternalFaces:][p.start:p.start + p.size]
+        c.bcs[p.name] = K.fixedDisplacement(cf @ Bm)
+    o = OracleSolid(c)
+    o.set("D", m.C @ Bm)
+    o.initialise()
+    o.op_grad()        # second pass: boundary snGrad now uses the exact gradient
+    g = o.get("gradD").reshape(-1, 3, 3)
+    assert np.abs(g - Bm[None]).max() < 1e-14
+    gb = o.get("gradD_b").reshape(-1, 3, 3)
+    assert np.abs(gb - Bm[None]).max() < 1e-14
+
+
+def test_least_squares_vectors_distorted_mesh_reproduce_linear_field():
+    c = cases.patch_test(n=5)
+    o = OracleSolid(c)
+    m = c.mesh
+    lsP, lsN = o.ls_vectors()
+    F = m.nInternalFaces
+    a = np.array([0.3, -0.2, 0.0])
+    phi = m.C @ a
+    g = np.zeros((m.nCells, 3))
+    d = phi[m.neighbour] - phi[m.owner]
+    np.add.at(g, m.owner, lsP[:F] * d[:, None])
+    np.add.at(g, m.neighbour, -lsN * d[:, None])
+    phib = m.Cf[F:] @ a
+    np.add.at(g, m.faceCells, lsP[F:] * (phib - phi[m.faceCells])[:, None])
+    assert np.abs(g[:, :2] - a[None, :2]).max() < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------
+# patch test (README.md:102-113): exact constant strain on distorted cells
+# ---------------------------------------------------------------------------------------------
+def test_patch_test_constant_strain_oracle():
+    o = OracleSolid(cases.patch_test(n=4))
+    st = o.evolve()
+    assert st["converged"]
+    gD = o.get("gradD").reshape(-1, 3, 3)
+    eps = 0.5 * (gD + gD.transpose(0, 2, 1))
+    assert np.abs(eps[:, 0, 0] - 2e-6).max() < 1e-13
+    assert np.abs(eps[:, 1, 1] - 6e-6).max() < 1e-13
+    assert np.abs(eps[:, 0, 1] - 4e-6).max() < 1e-13
+    with open(os.path.join(GOLDEN, "patch_test.json")) as f:
+        g = json.load(f)
+    sig = o.get("sigma")
+    assert np.allclose(sig, np.asarray(g["sigma"])[None, :], rtol=1e-9, atol=1e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+# Kirsch plate hole (config C1): discretisation-level agreement, 2nd-order mesh convergence
+# ---------------------------------------------------------------------------------------------
+def test_plate_hole_against_kirsch():
+    errs = []
+    for refine in (1, 2):
+        c = cases.plate_hole(refine=refine)
+        o = OracleSolid(c)
+        st = o.evolve()
+        assert st["converged"], st
+        Da = cases.kirsch_displacement(c.mesh.C)
+        sa = cases.kirsch_stress(c.mesh.C)
+        eD = rel_l2(o.get("D")[:, :2], Da[:, :2])
+        eS = rel_l2(o.get("sigma")[:, [0, 1, 3]], sa[:, [0, 1, 3]])
+        errs.append((eD, eS))
+    assert errs[0][0] < 0.02 and errs[0][1] < 0.06
+    assert errs[1][0] < errs[0][0] and errs[1][1] < errs[0][1]        # converges with the mesh
+    g = np.load(os.path.join(GOLDEN, "kirsch_points.npz"))
+    assert np.allclose(cases.kirsch_stress(g["points"]), g["sigma"], rtol=1e-13, atol=1e-6)
+    assert np.allclose(cases.kirsch_displacement(g["points"]), g["D"], rtol=1e-13, atol=1e-20)
+
+
+# ---------------------------------------------------------------------------------------------
+# [OF-ext] lduMatrix::Amul, PCG, DIC against independent numerics
+# ---------------------------------------------------------------------------------------------
+def _assembled(case):
+    o = OracleSolid(case)
+    o.op_assemble()
+    m = case.mesh
+    upper = o.get("upper")
+    diag = o.get("diag")
+    return o, m, upper, diag
+
+
+def test_amul_matches_scipy():
+    o, m, upper, diag = _assembled(cases.plate_hole())
+    rng = np.random.default_rng(0)
+    for q in range(2):
+        A = ldu_to_csr(m, upper, diag[:, q])
+        x = rng.standard_normal(m.nCells)
+        assert rel_l2(o.op_amul(q, x), A @ x) < 1e-14
+        # momentum matrix: symmetric positive definite M-matrix
+        assert (A - A.T).nnz == 0 or abs(A - A.T).max() < 1e-6 * abs(A).max()
+        assert (upper <= 0).all() and (diag[:, q] > 0).all()
+
+
+@pytest.mark.parametrize("pre", [K.PRECOND_NONE, K.PRECOND_DIAGONAL, K.PRECOND_DIC])
+def test_pcg_solution_matches_direct_solve(pre):
+    c = cases.cantilever(10, 4, 4, preconditioner=pre, tolerance=1e-14, relTol=0.0, maxIter=5000)
+    o, m, upper, diag = _assembled(c)
+    rng = np.random.default_rng(1)
+    b = rng.standard_normal((m.nCells, 3))
+    psi, st = o.op_solve(np.zeros((m.nCells, 3)), b)
+    for q in range(3):
+        A = ldu_to_csr(m, upper, diag[:, q]).tocsc()
+        x = spla.spsolve(A, b[:, q])
+        assert rel_l2(psi[:, q], x) < 1e-9
+        assert 0 < st["nIterations"][q] < 5000
+
+
+def test_dic_preconditioner_reduces_iterations_and_matches_python_restatement():
+    its = {}
+    for pre in (K.PRECOND_NONE, K.PRECOND_DIAGONAL, K.PRECOND_DIC):
+        c = cases.cantilever(20, 6, 6, preconditioner=pre, tolerance=1e-10, relTol=0.0)
+        o, m, upper, diag = _assembled(c)
+        b = np.random.default_rng(2).standard_normal((m.nCells, 3))
+        _, st = o.op_solve(np.zeros((m.nCells, 3)), b)
+        its[pre] = st["nIterations"][1]
+    assert its[K.PRECOND_DIC] < 0.6 * its[K.PRECOND_DIAGONAL]
+    # literal python restatement of DIC-PCG ([OF-ext] DICPreconditioner::calcReciprocalD / precondition,
+    # PCG.C) on a small system: same iteration count, same iterate
+    c = cases.cantilever(5, 3, 2, preconditioner=K.PRECOND_DIC, tolerance=1e-12, relTol=0.0)
+    o, m, upper, diag = _assembled(c)
+    b = np.random.default_rng(3).standard_normal((m.nCells, 3))
+    psi, st = o.op_solve(np.zeros((m.nCells, 3)), b)
+    l, u, N, F = m.owner, m.neighbour, m.nCells, m.nInternalFaces
+    dg = diag[:, 0]
+    rD = dg.copy()
+    for f in range(F):
+        rD[u[f]] -= upper[f] ** 2 / rD[l[f]]
+    rD = 1.0 / rD
+    A = ldu_to_csr(m, upper, dg)
+
+    def precond(r):
+        w = rD * r
+        for f in range(F):
+            w[u[f]] -= rD[u[f]] * upper[f] * w[l[f]]
+        for f in range(F - 1, -1, -1):
+            w[l[f]] -= rD[l[f]] * upper[f] * w[u[f]]
+        return w
+    x = np.zeros(N); r = b[:, 0] - A @ x
+    sumA = np.asarray(A.sum(axis=1)).ravel()
+    nf = np.abs(A @ x - sumA * x.mean()).sum() + np.abs(b[:, 0] - sumA * x.mean()).sum() + 1e-20
+    p = np.zeros(N); rho_old = 1.0; it = 0
+    while True:
+        w = precond(r); rho = w @ r
+        p = w if it == 0 else w + (rho / rho_old) * p
+        Ap = A @ p; alpha = rho / (Ap @ p)
+        x += alpha * p; r -= alpha * Ap; rho_old = rho; it += 1
+        if np.abs(r).sum() / nf < 1e-12 or it >= 1000:
+            break
+    assert it == st["nIterations"][0]
+    assert rel_l2(psi[:, 0], x) < 1e-10
+
+
+def test_pcg_rounding_sensitivity():
+    """A relTol-0.1 solve of the ill-conditioned bending problem amplifies round-off-level input changes:
+    the reason later outer iterates are only loosely comparable between two correct implementations."""
+    res = []
+    for eps in (0.0, 1e-15):
+        c = cases.cantilever(16, 4, 4)
+        o = OracleSolid(c)
+        if eps:
+            tr = np.zeros((c.mesh.patch("loaded").size, 3)); tr[:, 1] = -1e6 * (1 + eps)
+            o.set_bc("loaded", K.solidTraction(tr))
+        for _ in range(3):
+            o.outer_iteration()
+        res.append(o.get("D"))
+    d = rel_l2(res[1], res[0])
+    assert d < 1e-2          # bounded ...
+    # ... while the converged solution is insensitive (checked by the evolve parity tests)
+
+
+def test_threaded_oracle_matches_serial_without_dic():
+    """The OpenMP partitioning used for the timing baseline must not change results (DIC excepted: it
+    becomes block-Jacobi across the thread ranges, as across MPI ranks in OpenFOAM)."""
+    L = oracle_lib_fn()
+    outs = []
+    for nt in (1, 4):
+        c = cases.cantilever(12, 4, 4, preconditioner=K.PRECOND_DIAGONAL)
+        o = OracleSolid(c)
+        L.s4fo_set_threads(o.h, nt)
+        st = o.outer_iteration()     # first iterate: round-off-level agreement (later ones: see above)
+        outs.append((o.get("D"), st["nIterations"]))
+    assert outs[1][1] == outs[0][1]
+    assert rel_l2(outs[1][0], outs[0][0]) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------
+# whole-loop behaviour
+# ---------------------------------------------------------------------------------------------
+def test_cantilever_converges_to_beam_theory_envelope():
+    """3-D cantilever tip deflection vs Euler-Bernoulli/Timoshenko (cantileverStressDisplacement.C:56-117 is
+    the 2-D plane-strain form; for the 3-D beam this is a sanity envelope, not a pin)."""
+    Lb, H, W, P = 4.0, 1.0, 1.0, -1e6
+    c = cases.cantilever(16, 6, 6, L=Lb, H=H, W=W, traction=(0.0, P, 0.0), preconditioner=K.PRECOND_DIC,
+                         nCorrectors=20000)
+    o = OracleSolid(c)
+    st = o.evolve()
+    assert st["converged"], st
+    E, nu = 200e9, 0.3
+    I = W * H**3 / 12
+    Fy = P * H * W
+    xe = Lb - 0.5 * Lb / 16                                   # centres of the last cell layer
+    tip = Fy * xe**2 * (3 * Lb - xe) / (6 * E * I) + Fy * xe / (5.0 / 6.0 * E / (2 * (1 + nu)) * H * W)
+    D = o.get("D")
+    m = c.mesh
+    uy = D[m.C[:, 0] > Lb - Lb / 16, 1].mean()
+    assert uy == pytest.approx(tip, rel=0.12)
+
+
+def test_euler_d2dt2_free_vibration_conserves_sign_and_is_bounded():
+    c = cases.cantilever(8, 3, 3, L=2.0, d2dt2Scheme=K.D2DT2_EULER, deltaT=1e-4, deltaT0=1e-4, nCorrectors=50)
+    o = OracleSolid(c)
+    tip = []
+    for _ in range(5):
+        o.new_timestep(1e-4)
+        o.evolve()
+        tip.append(o.get("D")[:, 1].min())
+    assert all(t < 0 for t in tip) and tip[-1] < tip[0]       # accelerating downwards from rest
+
+
+def test_neo_hookean_tl_small_load_matches_linear_elastic():
+    """For vanishing load the total-Lagrangian neo-Hookean model reduces to Hooke's law."""
+    kw = dict(nx=8, ny=3, nz=3, L=2.0)
+    tight = dict(solutionTolerance=1e-10, alternativeTolerance=1e-10, tolerance=1e-12, nCorrectors=4000,
+                 preconditioner=K.PRECOND_DIC)
+    lin = cases.cantilever(traction=(0.0, -1.0, 0.0), E=3e6, nu=0.3, **kw, **tight)
+    neo = cases.neo_hookean_cantilever(traction=(0.0, -1.0, 0.0), **kw, **tight)
+    a, b = OracleSolid(lin), OracleSolid(neo)
+    sa, sb = a.evolve(), b.evolve()
+    assert sa["converged"] and sb["converged"]
+    assert rel_l2(b.get("D"), a.get("D")) < 1e-4
