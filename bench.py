@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", default=None, help="nx,ny,nz (default 800,100,100)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precond", default="diagonal", choices=["diagonal", "none", "chebyshev"])
+    ap.add_argument("--precond", default="diagonal", choices=["diagonal", "none", "chebyshev", "gamg", "gamg32"])
     return ap.parse_args()
 
 
@@ -166,8 +166,10 @@ def main():
             uid = torch.tensor(list(nccl_unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(uid, 0)
         comm = (world, rank, bytes(uid.cpu().tolist()))
-    pre = dict(diagonal=K.PRECOND_DIAGONAL, none=K.PRECOND_NONE, chebyshev=K.PRECOND_CHEBYSHEV)[args.precond]
-    case = cases.cantilever(*dims, rank=rank, nRanks=world, preconditioner=pre)
+    pre = dict(diagonal=K.PRECOND_DIAGONAL, none=K.PRECOND_NONE, chebyshev=K.PRECOND_CHEBYSHEV, gamg=K.PRECOND_GAMG,
+               gamg32=K.PRECOND_GAMG)[args.precond]
+    case = cases.cantilever(*dims, rank=rank, nRanks=world, preconditioner=pre,
+                            gamgSinglePrecision=1 if args.precond == "gamg32" else 0)
     mesh = case.mesh
     g = SolidModel(case, device=local_rank, comm=comm)
 
@@ -239,7 +241,12 @@ def main():
     # ---- roofline of the dominant kernel (3-component fused SpMV), timed alone
     peak, peak_src = peaks()
     kern = {}
-    for name in ("spmv3", "spmv1", "pcg_iter", "grad", "rhs", "law"):
+    names = ["spmv3", "spmv3_rows", "spmv1", "pcg_p", "pcg_xr", "pcg_iter", "grad", "rhs", "law"]
+    gamg = None
+    if args.precond.startswith("gamg"):
+        names.append("gamg_vcycle")
+        gamg = g.gamg_info()
+    for name in names:
         ms_k, by = g.time_kernel(name, reps=20, flush_l2=False)
         kern[name] = dict(ms=ms_k, algo_bytes=by, gbs=by / (ms_k * 1e-3) / 1e9, frac=by / (ms_k * 1e-3) / 1e9 / peak)
     roof = dict(bound="hbm", achieved=kern["spmv3"]["gbs"], peak=peak, unit="GB/s", frac=kern["spmv3"]["frac"], traffic=None,
@@ -255,6 +262,8 @@ def main():
                 clocks=clocks, gpu_launches=int(launches),
                 e2e=dict(value=e2e_val, unit="iter/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
                 roofline=roof, kernels=kern)
+    if gamg:
+        line["config"]["gamg"] = gamg
 
     if world == 1 and not args.no_cpu_baseline:
         sample = CPU_SAMPLE if nCellsFull > CPU_SAMPLE[0] * CPU_SAMPLE[1] * CPU_SAMPLE[2] else dims

@@ -75,7 +75,10 @@ enum {
     S4F_PRECOND_NONE = 0,
     S4F_PRECOND_DIAGONAL = 1,   /* [OF-ext] diagonalPreconditioner (Jacobi) */
     S4F_PRECOND_DIC = 2,        /* [OF-ext] DICPreconditioner / FDIC (oracle: exact; GPU: see DESIGN.md) */
-    S4F_PRECOND_CHEBYSHEV = 3   /* GPU polynomial preconditioner (no reference counterpart) */
+    S4F_PRECOND_CHEBYSHEV = 3,  /* GPU polynomial preconditioner (no reference counterpart) */
+    S4F_PRECOND_GAMG = 4        /* [OF-ext] GAMG (agglomeration multigrid) used as PCG preconditioner: pair-wise
+                                   agglomeration like faceAreaPair, Galerkin coarse matrices, V-cycle with a
+                                   Chebyshev-Jacobi smoother, dense solve on the coarsest level */
 };
 
 /* field ids for upload / download */
@@ -139,6 +142,10 @@ typedef struct {
     double deltaT, deltaT0;
     int chebyshevDegree;   /* S4F_PRECOND_CHEBYSHEV only */
     int checkEvery;        /* host polls the device-side convergence flags every n PCG iterations */
+    int gamgSinglePrecision;   /* S4F_PRECOND_GAMG: 1 = V-cycle in fp32 (PCG itself stays fp64), 0 = fp64 */
+    double gamgOverCorrection; /* S4F_PRECOND_GAMG: fixed scaling of the coarse-grid correction (<= 0: 1.8) */
+    int gamgSmootherDegree;    /* S4F_PRECOND_GAMG: Chebyshev-Jacobi degree of the pre- and post-smoother (<= 0: 2) */
+    int gamgCycle;             /* S4F_PRECOND_GAMG: 0 = V-cycle, 1 = W-cycle */
 } s4fgpu_controls;
 
 /* result of one outer (momentum-correction) iteration / of evolve(); the numbers of the
@@ -248,10 +255,19 @@ enum {
     S4F_KERNEL_PCG_ITER = 2,   /* one fused 3-component PCG iteration (all kernels) */
     S4F_KERNEL_GRAD = 3,
     S4F_KERNEL_LAW = 4,
-    S4F_KERNEL_RHS = 5
+    S4F_KERNEL_RHS = 5,
+    S4F_KERNEL_PCG_P = 6,      /* pA = rD rA + beta pA */
+    S4F_KERNEL_PCG_XR = 7,     /* psi += alpha pA; rA -= alpha wA; residual sums */
+    S4F_KERNEL_SPMV3_ROWS = 8, /* 3-component Amul, earlier row-per-thread mapping (kept for comparison) */
+    S4F_KERNEL_GAMG_VCYCLE = 9 /* one application of the GAMG preconditioner (all levels) */
 };
 int s4fgpu_time_kernel(s4fgpu_handle h, int kernel, int reps, int flushL2,
                        double* msPerLaunch, double* algoBytesPerLaunch);
+
+/* The GAMG hierarchy of the current matrix (built on first use): number of levels, cells per level
+ * (sizes[maxLevels]), algorithmic bytes of one V-cycle and the host set-up time. */
+int s4fgpu_gamg_info(s4fgpu_handle h, int* nLevels, int* sizes, int maxLevels, double* bytesPerApply,
+                     double* setupSeconds);
 
 /* CUDA-event timer on the library's own stream (torch.cuda.Event only sees torch's stream), and a
  * stream synchronise.  timer_stop returns the device time in milliseconds since timer_start. */

@@ -854,7 +854,11 @@ SolverPerf solvePCG(s4f_oracle& o, const double* diag, double* psi, const double
     perf.initRes = sm / nf; perf.finalRes = perf.initRes;
     auto converged = [&](double fr) { return fr < o.ctl.tolerance || (o.ctl.relTol > 1e-20 && fr < o.ctl.relTol * perf.initRes); };
     if (!converged(perf.finalRes)) {
-        Precond pre; pre.init(o, diag, o.ctl.preconditioner == S4F_PRECOND_CHEBYSHEV ? S4F_PRECOND_DIAGONAL : o.ctl.preconditioner);
+        // GPU-only preconditioners map onto the reference's own: Chebyshev -> diagonal, GAMG -> DIC
+        int pk = o.ctl.preconditioner;
+        if (pk == S4F_PRECOND_CHEBYSHEV) pk = S4F_PRECOND_DIAGONAL;
+        if (pk == S4F_PRECOND_GAMG) pk = S4F_PRECOND_DIC;
+        Precond pre; pre.init(o, diag, pk);
         do {
             wArAold = wArA;
             pre.apply(o, wA.data(), rA.data());

@@ -28,7 +28,7 @@ D2DT2_STEADY_STATE, D2DT2_EULER, D2DT2_BACKWARD = 0, 1, 2
 STAB_NONE, STAB_RHIE_CHOW = 0, 1
 RELAX_FIXED, RELAX_AITKEN = 0, 1
 SOLVER_PCG, SOLVER_PBICGSTAB = 0, 1
-PRECOND_NONE, PRECOND_DIAGONAL, PRECOND_DIC, PRECOND_CHEBYSHEV = 0, 1, 2, 3
+PRECOND_NONE, PRECOND_DIAGONAL, PRECOND_DIC, PRECOND_CHEBYSHEV, PRECOND_GAMG = 0, 1, 2, 3, 4
 
 FIELD = dict(D=0, D_old=1, D_oldOld=2, gradD=3, sigma=4, D_b=5, gradD_b=6, sigma_b=7, source=8, diag=9,
              upper=10, epsilonPEq=11, sigmaY=12, bEbar=13, DLambda=14, J=15, F=16, gradD_old=17,
@@ -69,7 +69,9 @@ class Controls(C.Structure):
                 ("nCorrectors", C.c_int), ("solutionTolerance", C.c_double),
                 ("alternativeTolerance", C.c_double), ("materialTolerance", C.c_double),
                 ("g", C.c_double * 3), ("deltaT", C.c_double), ("deltaT0", C.c_double),
-                ("chebyshevDegree", C.c_int), ("checkEvery", C.c_int)]
+                ("chebyshevDegree", C.c_int), ("checkEvery", C.c_int),
+                ("gamgSinglePrecision", C.c_int), ("gamgOverCorrection", C.c_double),
+                ("gamgSmootherDegree", C.c_int), ("gamgCycle", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -109,6 +111,10 @@ def default_controls(**kw) -> Controls:
     c.deltaT0 = 1.0
     c.chebyshevDegree = 4
     c.checkEvery = 4
+    c.gamgSinglePrecision = 0
+    c.gamgOverCorrection = 1.8
+    c.gamgSmootherDegree = 2
+    c.gamgCycle = 0
     for k, v in kw.items():
         if k == "g":
             for i in range(3):

@@ -1,0 +1,601 @@
+// s4f_amg.cu -- GAMG-type preconditioner of the displacement PCG solve.
+//
+// Reference behaviour: fvSolution "solver PCG; preconditioner GAMG" / "solver GAMG" ([OF-ext] GAMGSolver,
+// GAMGPreconditioner, pairGAMGAgglomeration "faceAreaPair"): cells are agglomerated pair-wise by their
+// strongest face coefficient, coarse matrices are the sums of the fine coefficients (Galerkin product
+// with piece-wise constant restriction/prolongation), a V-cycle of smoothing sweeps is applied.  This is
+// the B200 restatement of that algorithm, not OpenFOAM's code:
+//   * set-up (once per matrix, host): three pair-wise passes per level -> aggregates of <= 8 cells, so
+//     the level sizes fall 8x and the whole hierarchy adds only ~1/7 of the fine-level traffic;
+//   * every level is a SELL-32 cell-centric row store like the fine level (atomic-free gathers), the
+//     three displacement components share each matrix read (they differ only in the diagonal);
+//   * smoother: Chebyshev-Jacobi polynomial (symmetric, so the V-cycle is a valid PCG preconditioner,
+//     and a pure SpMV chain -- no sequential sweep as in GaussSeidel/DIC);
+//   * coarse-grid correction scaled by a fixed factor (OpenFOAM's scaleCorrection computes it from two
+//     global dot products per level; a constant keeps the preconditioner linear and costs nothing);
+//   * coarsest level (<= 512 cells): dense inverse applied by one small kernel;
+//   * optional fp32 V-cycle: the preconditioner only has to be an SPD approximation, PCG stays fp64.
+// Multi-rank: the hierarchy is rank-local (couplings across processor patches are dropped in the
+// preconditioner only, i.e. block-Jacobi over ranks, like DIC in OpenFOAM); Amul in PCG is exact.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "s4f_ctx.h"
+#include "s4f_dev.cuh"
+
+namespace {
+
+// ================================================================================================
+// host: agglomeration
+// ================================================================================================
+struct HostLevel {
+    int n = 0;
+    std::vector<int> own, nei;          // faces, upper-triangular order
+    std::vector<double> a;              // positive face coefficient (= -upper)
+    std::vector<double> diag[3];
+    std::vector<int> parent;            // aggregate of each cell in the next (coarser) level
+};
+
+// one pair-wise pass: greedy matching of every still-unmatched cell with its strongest unmatched
+// neighbour ([OF-ext] pairGAMGAgglomeration::agglomerate, restated); returns the number of aggregates
+int pairwise_pass(const HostLevel& L, std::vector<int>& agg) {
+    const int n = L.n;
+    const size_t F = L.own.size();
+    std::vector<int> ptr(n + 1, 0);
+    for (size_t f = 0; f < F; f++) { ptr[L.own[f] + 1]++; ptr[L.nei[f] + 1]++; }
+    for (int i = 0; i < n; i++) ptr[i + 1] += ptr[i];
+    std::vector<int> adj(2 * F);
+    std::vector<float> wgt(2 * F);
+    {
+        std::vector<int> cur(ptr.begin(), ptr.end() - 1);
+        for (size_t f = 0; f < F; f++) {   // lower neighbours first, then upper: the fine-level row order
+            int e = cur[L.nei[f]]++; adj[e] = L.own[f]; wgt[e] = (float)L.a[f];
+        }
+        for (size_t f = 0; f < F; f++) {
+            int e = cur[L.own[f]]++; adj[e] = L.nei[f]; wgt[e] = (float)L.a[f];
+        }
+    }
+    agg.assign(n, -1);
+    int nc = 0;
+    for (int i = 0; i < n; i++) {
+        if (agg[i] >= 0) continue;
+        int best = -1; float bw = 0.f;
+        for (int e = ptr[i]; e < ptr[i + 1]; e++) {
+            const int j = adj[e];
+            if (agg[j] < 0 && j != i && wgt[e] > bw * 1.0000001f) { bw = wgt[e]; best = j; }
+        }
+        agg[i] = nc;
+        if (best >= 0) agg[best] = nc;
+        nc++;
+    }
+    return nc;
+}
+
+// Galerkin coarse level for piece-wise constant transfer: coarse face = sum of the fine faces between
+// two aggregates, coarse diagonal = sum of fine diagonals - 2 * (faces inside the aggregate)
+void galerkin(const HostLevel& L, const std::vector<int>& agg, int nc, HostLevel& C) {
+    C.n = nc;
+    for (int q = 0; q < 3; q++) C.diag[q].assign(nc, 0.0);
+    for (int i = 0; i < L.n; i++) for (int q = 0; q < 3; q++) C.diag[q][agg[i]] += L.diag[q][i];
+    const size_t F = L.own.size();
+    std::vector<int> cnt(nc + 1, 0);
+    for (size_t f = 0; f < F; f++) {
+        const int a = agg[L.own[f]], b = agg[L.nei[f]];
+        if (a != b) cnt[std::min(a, b) + 1]++;
+    }
+    for (int i = 0; i < nc; i++) cnt[i + 1] += cnt[i];
+    std::vector<int> hi(cnt[nc]);
+    std::vector<double> w(cnt[nc]);
+    {
+        std::vector<int> cur(cnt.begin(), cnt.end() - 1);
+        for (size_t f = 0; f < F; f++) {
+            const int a = agg[L.own[f]], b = agg[L.nei[f]];
+            if (a == b) { for (int q = 0; q < 3; q++) C.diag[q][a] -= 2.0 * L.a[f]; continue; }
+            const int e = cur[std::min(a, b)]++;
+            hi[e] = std::max(a, b); w[e] = L.a[f];
+        }
+    }
+    C.own.clear(); C.nei.clear(); C.a.clear();
+    C.own.reserve(cnt[nc] / 2 + 16); C.nei.reserve(cnt[nc] / 2 + 16); C.a.reserve(cnt[nc] / 2 + 16);
+    std::vector<std::pair<int, double>> row;
+    for (int i = 0; i < nc; i++) {
+        row.clear();
+        for (int e = cnt[i]; e < cnt[i + 1]; e++) row.emplace_back(hi[e], w[e]);
+        std::sort(row.begin(), row.end(), [](const std::pair<int, double>& x, const std::pair<int, double>& y) { return x.first < y.first; });
+        for (size_t k = 0; k < row.size();) {
+            size_t m = k; double s = 0;
+            while (m < row.size() && row[m].first == row[k].first) s += row[m++].second;
+            C.own.push_back(i); C.nei.push_back(row[k].first); C.a.push_back(s);
+            k = m;
+        }
+    }
+}
+
+// dense inverse of the coarsest matrix (SPD) by Cholesky, per component
+bool dense_inverse(const HostLevel& L, int q, std::vector<double>& inv) {
+    const int n = L.n;
+    std::vector<double> A((size_t)n * n, 0.0);
+    for (int i = 0; i < n; i++) A[(size_t)i * n + i] = L.diag[q][i];
+    for (size_t f = 0; f < L.own.size(); f++) {
+        A[(size_t)L.own[f] * n + L.nei[f]] -= L.a[f];
+        A[(size_t)L.nei[f] * n + L.own[f]] -= L.a[f];
+    }
+    // a pure-Neumann component (no fixed patch) has a singular matrix: regularise like a tiny spring
+    double dmax = 0; for (int i = 0; i < n; i++) dmax = std::max(dmax, A[(size_t)i * n + i]);
+    for (int i = 0; i < n; i++) A[(size_t)i * n + i] += 1e-10 * dmax;
+    // Cholesky A = L L^T in place (lower)
+    for (int j = 0; j < n; j++) {
+        double d = A[(size_t)j * n + j];
+        for (int k = 0; k < j; k++) d -= A[(size_t)j * n + k] * A[(size_t)j * n + k];
+        if (!(d > 0)) return false;
+        d = std::sqrt(d); A[(size_t)j * n + j] = d;
+        for (int i = j + 1; i < n; i++) {
+            double s = A[(size_t)i * n + j];
+            for (int k = 0; k < j; k++) s -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+            A[(size_t)i * n + j] = s / d;
+        }
+    }
+    inv.assign((size_t)n * n, 0.0);
+    std::vector<double> y(n);
+    for (int c = 0; c < n; c++) {        // solve L L^T x = e_c
+        for (int i = 0; i < n; i++) {
+            double s = (i == c) ? 1.0 : 0.0;
+            for (int k = 0; k < i; k++) s -= A[(size_t)i * n + k] * y[k];
+            y[i] = s / A[(size_t)i * n + i];
+        }
+        for (int i = n - 1; i >= 0; i--) {
+            double s = y[i];
+            for (int k = i + 1; k < n; k++) s -= A[(size_t)k * n + i] * inv[(size_t)k * n + c];
+            inv[(size_t)i * n + c] = s / A[(size_t)i * n + i];
+        }
+    }
+    return true;
+}
+
+// ================================================================================================
+// device kernels (T = float | double for the V-cycle arithmetic; TB = type of the right-hand side
+// seen by a level: the fp64 PCG residual on level 0, T below; TO = type of the smoother output)
+// ================================================================================================
+struct Cheb { double c1, c2; };
+
+// x = d = (1/theta) rD b      (first smoothing step from a zero initial guess)
+template <class T, class TB>
+__global__ void __launch_bounds__(S4F_BLOCK) k_amg_first(const T* __restrict__ rD, const TB* __restrict__ b, T* __restrict__ x,
+                                                         T* __restrict__ d, int n, int ld, int ldb, T invTheta) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const T v = invTheta * rD[(size_t)q * ld + i] * (T)b[(size_t)q * ldb + i];
+            x[(size_t)q * ld + i] = v; d[(size_t)q * ld + i] = v;
+        }
+    }
+}
+
+// one Chebyshev-Jacobi step:  r = b - A x;  d' = c1 d + c2 rD r;  x' = x + d'   (out of place in x)
+// MODE 0: as written; MODE 1: residual only (xo = r, nothing else written).
+// Mapping as in the PCG SpMV (k_amul3c): three consecutive warps share a slice, one component each.
+#define S4F_AMG_BLOCK 192
+template <class T, class TB, class TO, int MODE>
+__global__ void __launch_bounds__(S4F_AMG_BLOCK) k_amg_step(const int* __restrict__ slicePtr, const int* __restrict__ col,
+                                                            const T* __restrict__ a, const T* __restrict__ dg, const T* __restrict__ rD,
+                                                            const TB* __restrict__ b, const T* __restrict__ x, T* __restrict__ d,
+                                                            TO* __restrict__ xo, int n, int ld, int ldb, int ldo, int nSlices, T c1, T c2) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int q = wib % 3, sub = wib / 3;
+    constexpr int SPB = S4F_AMG_BLOCK / 96;
+    const T* __restrict__ xq = x + (size_t)q * ld;
+    for (int s = blockIdx.x * SPB + sub; s < nSlices; s += gridDim.x * SPB) {
+        const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
+        const int row = s * 32 + lane;
+        T s0 = 0, s1 = 0;
+        const int* cp = col + base + lane;
+        const T* ap = a + base + lane;
+        int k = 0;
+        for (; k + 1 < width; k += 2) {
+            const int c0 = cp[32 * k], c1i = cp[32 * k + 32];
+            const T e0 = ap[32 * k], e1 = ap[32 * k + 32];
+            s0 += e0 * xq[c0]; s1 += e1 * xq[c1i];
+        }
+        if (k < width) s0 += ap[32 * k] * xq[cp[32 * k]];
+        if (row < n) {
+            const size_t j = (size_t)q * ld + row;
+            const T xv = xq[row];
+            const T r = (T)b[(size_t)q * ldb + row] - (dg[j] * xv - (s0 + s1));
+            if (MODE == 1) { xo[(size_t)q * ldo + row] = (TO)r; }
+            else {
+                const T dn = (c1 != (T)0 ? c1 * d[j] : (T)0) + c2 * rD[j] * r;
+                d[j] = dn;
+                xo[(size_t)q * ldo + row] = (TO)(xv + dn);
+            }
+        }
+    }
+}
+
+// b_c[I] = sum over the children of I of t[child]
+template <class T>
+__global__ void k_amg_restrict(const int* __restrict__ childPtr, const int* __restrict__ child, const T* __restrict__ t,
+                               T* __restrict__ bc, int nc, int ld, int ldc) {
+    const int I = blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= nc) return;
+    T s0 = 0, s1 = 0, s2 = 0;
+    for (int e = childPtr[I]; e < childPtr[I + 1]; e++) {
+        const int i = child[e];
+        s0 += t[i]; s1 += t[(size_t)ld + i]; s2 += t[2 * (size_t)ld + i];
+    }
+    bc[I] = s0; bc[(size_t)ldc + I] = s1; bc[2 * (size_t)ldc + I] = s2;
+}
+
+// x[i] += omega * e[parent[i]]
+template <class T>
+__global__ void __launch_bounds__(S4F_BLOCK) k_amg_prolong(const int* __restrict__ parent, const T* __restrict__ e, T* __restrict__ x,
+                                                           int n, int ld, int ldc, T omega) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int I = parent[i];
+#pragma unroll
+        for (int q = 0; q < 3; q++) x[(size_t)q * ld + i] += omega * e[(size_t)q * ldc + I];
+    }
+}
+
+// coarsest level: x = Ainv_q b, one warp per (row, component)
+template <class T, class TB, class TO>
+__global__ void k_amg_dense(const T* __restrict__ inv, const TB* __restrict__ b, TO* __restrict__ x, int n, int ldb, int ldo) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (gw >= 3 * n) return;
+    const int q = gw / n, i = gw % n;
+    const T* row = inv + ((size_t)q * n + i) * n;
+    T s = 0;
+    for (int k = lane; k < n; k += 32) s += row[k] * (T)b[(size_t)q * ldb + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) x[(size_t)q * ldo + i] = (TO)s;
+}
+
+template <class T>
+__global__ void k_amg_convert(const double* __restrict__ in, T* __restrict__ out, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (T)in[i];
+}
+template <class T>
+__global__ void k_amg_diag(const double* __restrict__ diagC, T* __restrict__ dg, T* __restrict__ rD, int n, int ldIn, int ld) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        const double v = diagC[(size_t)q * ldIn + i];
+        dg[(size_t)q * ld + i] = (T)v; rD[(size_t)q * ld + i] = (T)(1.0 / v);
+    }
+}
+__global__ void k_gather_upper(const int* __restrict__ faceEntry, const double* __restrict__ eA, double* __restrict__ upper, int F) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < F) upper[f] = -eA[faceEntry[f]];
+}
+
+// ================================================================================================
+// hierarchy
+// ================================================================================================
+template <class T>
+struct Level {
+    int n = 0, ld = 0, nSlices = 0;
+    const int* slicePtr = nullptr; const int* col = nullptr; const T* a = nullptr;   // level 0 aliases the fine rows
+    DevBuf<int> slicePtrB, colB; DevBuf<T> aB;
+    DevBuf<T> dg, rD;                   // 3*ld
+    DevBuf<int> parent;                 // [n] -> next level
+    DevBuf<int> childPtr, child;        // children lists of THIS level's cells in the finer level
+    DevBuf<T> b, x, x2, d, t;           // 3*ld work vectors
+};
+
+}  // namespace
+
+struct S4fAmg {
+    virtual ~S4fAmg() {}
+    virtual int apply(s4fgpu_ctx* c, const double* r3, double* z3) = 0;
+    std::vector<int> sizes;
+    double bytesPerApply = 0;
+    double setupSeconds = 0;
+};
+
+namespace {
+
+template <class T>
+struct Hierarchy : S4fAmg {
+    std::vector<std::unique_ptr<Level<T>>> lv;
+    DevBuf<T> denseInv;                 // 3 * nC * nC
+    int deg = 2, cycle = 0;
+    double omega = 1.8;
+    double theta = 0, delta = 0;
+
+    int build_level_rows(s4fgpu_ctx* c, Level<T>& L, const HostLevel& H) {
+        const int n = H.n;
+        L.n = n; L.ld = ((n + 31) / 32) * 32; L.nSlices = (n + 31) / 32;
+        std::vector<int> cnt(n, 0);
+        const size_t F = H.own.size();
+        for (size_t f = 0; f < F; f++) { cnt[H.own[f]]++; cnt[H.nei[f]]++; }
+        std::vector<long long> rowPtr(n + 1, 0);
+        for (int i = 0; i < n; i++) rowPtr[i + 1] = rowPtr[i] + cnt[i];
+        std::vector<int> rc(rowPtr[n]); std::vector<double> rv(rowPtr[n]);
+        {
+            std::vector<long long> cur(rowPtr.begin(), rowPtr.end() - 1);
+            for (size_t f = 0; f < F; f++) { long long e = cur[H.nei[f]]++; rc[e] = H.own[f]; rv[e] = H.a[f]; }
+            for (size_t f = 0; f < F; f++) { long long e = cur[H.own[f]]++; rc[e] = H.nei[f]; rv[e] = H.a[f]; }
+        }
+        std::vector<int> sp(L.nSlices + 1, 0);
+        for (int s = 0; s < L.nSlices; s++) {
+            int w = 0;
+            for (int r = s * 32; r < std::min(n, s * 32 + 32); r++) w = std::max(w, cnt[r]);
+            sp[s + 1] = sp[s] + 32 * w;
+        }
+        const size_t nE = sp[L.nSlices];
+        std::vector<int> hc(std::max<size_t>(nE, 1), 0); std::vector<T> ha(std::max<size_t>(nE, 1), (T)0);
+        for (int s = 0; s < L.nSlices; s++) {
+            const int w = (sp[s + 1] - sp[s]) / 32;
+            for (int lane = 0; lane < 32; lane++) {
+                const int P = s * 32 + lane;
+                for (int k = 0; k < w; k++) {
+                    const size_t E = (size_t)sp[s] + 32 * k + lane;
+                    if (P >= n) { hc[E] = 0; continue; }
+                    if (k >= cnt[P]) { hc[E] = P; continue; }
+                    hc[E] = rc[rowPtr[P] + k]; ha[E] = (T)rv[rowPtr[P] + k];
+                }
+            }
+        }
+        S4F_CHECK_CUDA(c, L.slicePtrB.upload(sp)); S4F_CHECK_CUDA(c, L.colB.upload(hc)); S4F_CHECK_CUDA(c, L.aB.upload(ha));
+        L.slicePtr = L.slicePtrB.p; L.col = L.colB.p; L.a = L.aB.p;
+        std::vector<T> hd(3 * (size_t)L.ld, (T)1), hr(3 * (size_t)L.ld, (T)1);
+        for (int q = 0; q < 3; q++) for (int i = 0; i < n; i++) { hd[(size_t)q * L.ld + i] = (T)H.diag[q][i]; hr[(size_t)q * L.ld + i] = (T)(1.0 / H.diag[q][i]); }
+        S4F_CHECK_CUDA(c, L.dg.upload(hd)); S4F_CHECK_CUDA(c, L.rD.upload(hr));
+        return 0;
+    }
+    int alloc_work(s4fgpu_ctx* c, Level<T>& L) {
+        const size_t m = 3 * (size_t)L.ld;
+        S4F_CHECK_CUDA(c, L.b.alloc(m)); S4F_CHECK_CUDA(c, L.x.alloc(m)); S4F_CHECK_CUDA(c, L.x2.alloc(m));
+        S4F_CHECK_CUDA(c, L.d.alloc(m)); S4F_CHECK_CUDA(c, L.t.alloc(m));
+        return 0;
+    }
+    int set_transfer(s4fgpu_ctx* c, Level<T>& fine, Level<T>& coarse, const std::vector<int>& parent, int nc) {
+        S4F_CHECK_CUDA(c, fine.parent.upload(parent));
+        std::vector<int> ptr(nc + 1, 0), ch(parent.size());
+        for (size_t i = 0; i < parent.size(); i++) ptr[parent[i] + 1]++;
+        for (int i = 0; i < nc; i++) ptr[i + 1] += ptr[i];
+        std::vector<int> cur(ptr.begin(), ptr.end() - 1);
+        for (size_t i = 0; i < parent.size(); i++) ch[cur[parent[i]]++] = (int)i;
+        S4F_CHECK_CUDA(c, coarse.childPtr.upload(ptr)); S4F_CHECK_CUDA(c, coarse.child.upload(ch));
+        return 0;
+    }
+
+    static int step_grid(const s4fgpu_ctx* c, const Level<T>& L) {
+        long long need = ((long long)L.nSlices + 1) / 2, g = (long long)c->numSMs * 10;
+        if (need < g) g = need;
+        return (int)(g < 1 ? 1 : g);
+    }
+    // algorithmic bytes of one application (for the roofline report): every array read / written once
+    double bytes_per_apply(int fineLdUnused) const {
+        (void)fineLdUnused;
+        double tot = 0;
+        const double sT = sizeof(T);
+        for (size_t l = 0; l + 1 < lv.size(); l++) {
+            const Level<T>& L = *lv[l];
+            const double n = L.n, nz = nnz[l], sB = (l == 0) ? 8.0 : sT, sO = (l == 0) ? 8.0 : sT, nc = lv[l + 1]->n;
+            const double mat = nz * (4 + sT) + n * 0.125;
+            tot += 3 * n * (sT + sB + 2 * sT);                                         // first
+            tot += (deg - 1) * (mat + 3 * n * (sB + 5 * sT + sT));                      // pre steps
+            tot += mat + 3 * n * (sB + 3 * sT);                                        // residual
+            tot += 3 * n * sT + 3 * nc * sT + 4 * n;                                   // restrict
+            tot += 4 * n + 6 * n * sT + 3 * nc * sT;                                   // prolong
+            tot += mat + 3 * n * (sB + 4 * sT + sT);                                   // post step 0 (no d read)
+            tot += (deg - 1) * (mat + 3 * n * (sB + 5 * sT)) + (deg > 1 ? 3 * n * sO : 0);   // post steps
+        }
+        return tot;
+    }
+    std::vector<double> nnz;
+
+    // ---- smoothing on one level ---------------------------------------------------------------
+    template <class TB, class TO>
+    void step(s4fgpu_ctx* c, Level<T>& L, const TB* b, int ldb, const T* xin, TO* xout, int ldo, double c1, double c2) {
+        const int grid = step_grid(c, L);
+        k_amg_step<T, TB, TO, 0><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, L.rD.p, b, xin, L.d.p, xout, L.n, L.ld, ldb, ldo,
+                                                                     L.nSlices, (T)c1, (T)c2);
+        c->launches++;
+    }
+    // Chebyshev-Jacobi of degree `deg`; fromZero: x0 = 0.  Result ends in *xres (L.x or L.x2), or, when
+    // `out` is given (level 0), the last step writes the fp64 output directly.
+    template <class TB>
+    T* smooth(s4fgpu_ctx* c, Level<T>& L, const TB* b, int ldb, bool fromZero, T* xcur, double* out, int ldo) {
+        const double sigma = theta / delta;
+        double rho = 1.0 / sigma;
+        T* other = (xcur == L.x.p) ? L.x2.p : L.x.p;
+        int k0 = 0;
+        if (fromZero) {
+            const int grid = s4f_grid(c->numSMs, L.n);
+            k_amg_first<T, TB><<<grid, S4F_BLOCK, 0, c->stream>>>(L.rD.p, b, xcur, L.d.p, L.n, L.ld, ldb, (T)(1.0 / theta));
+            c->launches++;
+            k0 = 1;
+        }
+        for (int k = k0; k < deg; k++) {
+            double c1, c2;
+            if (k == 0) { c1 = 0.0; c2 = 1.0 / theta; }
+            else { const double rhon = 1.0 / (2.0 * sigma - rho); c1 = rhon * rho; c2 = 2.0 * rhon / delta; rho = rhon; }
+            const bool last = (k == deg - 1);
+            if (last && out) { step<TB, double>(c, L, b, ldb, xcur, out, ldo, c1, c2); return nullptr; }
+            step<TB, T>(c, L, b, ldb, xcur, other, L.ld, c1, c2);
+            std::swap(xcur, other);
+        }
+        return xcur;
+    }
+
+    template <class TB>
+    int cycle_level(s4fgpu_ctx* c, size_t l, const TB* b, int ldb, double* out, int ldo) {
+        Level<T>& L = *lv[l];
+        if (l + 1 == lv.size()) {     // coarsest: dense inverse
+            const int warps = 3 * L.n, blocks = (warps * 32 + 255) / 256;
+            if (out) k_amg_dense<T, TB, double><<<blocks, 256, 0, c->stream>>>(denseInv.p, b, out, L.n, ldb, ldo);
+            else k_amg_dense<T, TB, T><<<blocks, 256, 0, c->stream>>>(denseInv.p, b, L.x.p, L.n, ldb, L.ld);
+            c->launches++;
+            return 0;
+        }
+        Level<T>& C = *lv[l + 1];
+        T* x = smooth<TB>(c, L, b, ldb, true, L.x.p, nullptr, 0);                 // pre-smoothing from zero
+        {                                                                          // residual
+            const int grid = step_grid(c, L);
+            k_amg_step<T, TB, T, 1><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, L.rD.p, b, x, L.d.p, L.t.p, L.n, L.ld, ldb, L.ld,
+                                                                       L.nSlices, (T)0, (T)0);
+            k_amg_restrict<T><<<(C.n + 127) / 128, 128, 0, c->stream>>>(C.childPtr.p, C.child.p, L.t.p, C.b.p, C.n, L.ld, C.ld);
+            c->launches += 2;
+        }
+        int rc = cycle_level<T>(c, l + 1, C.b.p, C.ld, nullptr, 0); if (rc) return rc;
+        {
+            const int grid = s4f_grid(c->numSMs, L.n);
+            k_amg_prolong<T><<<grid, S4F_BLOCK, 0, c->stream>>>(L.parent.p, C.x.p, x, L.n, L.ld, C.ld, (T)omega);
+            c->launches++;
+        }
+        if (cycle == 1 && l + 2 < lv.size()) {   // W-cycle: a second coarse correction on the updated residual
+            const int grid = step_grid(c, L);
+            k_amg_step<T, TB, T, 1><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, L.rD.p, b, x, L.d.p, L.t.p, L.n, L.ld, ldb, L.ld,
+                                                                       L.nSlices, (T)0, (T)0);
+            k_amg_restrict<T><<<(C.n + 127) / 128, 128, 0, c->stream>>>(C.childPtr.p, C.child.p, L.t.p, C.b.p, C.n, L.ld, C.ld);
+            c->launches += 2;
+            rc = cycle_level<T>(c, l + 1, C.b.p, C.ld, nullptr, 0); if (rc) return rc;
+            const int gridp = s4f_grid(c->numSMs, L.n);
+            k_amg_prolong<T><<<gridp, S4F_BLOCK, 0, c->stream>>>(L.parent.p, C.x.p, x, L.n, L.ld, C.ld, (T)omega);
+            c->launches++;
+        }
+        T* xr = smooth<TB>(c, L, b, ldb, false, x, out, ldo);                      // post-smoothing
+        if (!out && xr != L.x.p) {   // callers read the level result from L.x
+            S4F_CHECK_CUDA(c, cudaMemcpyAsync(L.x.p, xr, 3 * (size_t)L.ld * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
+        }
+        return 0;
+    }
+
+    int apply(s4fgpu_ctx* c, const double* r3, double* z3) override {
+        int rc = cycle_level<double>(c, 0, r3, c->ld, z3, c->ld);
+        if (rc) return rc;
+        S4F_CHECK_CUDA(c, cudaGetLastError());
+        return 0;
+    }
+};
+
+template <class T>
+int build(s4fgpu_ctx* c, std::vector<HostLevel>& H) {
+    auto* A = new Hierarchy<T>();
+    std::unique_ptr<S4fAmg> guard(A);
+    A->deg = c->ctl.gamgSmootherDegree > 0 ? c->ctl.gamgSmootherDegree : 2;
+    A->cycle = c->ctl.gamgCycle;
+    A->omega = c->ctl.gamgOverCorrection > 0 ? c->ctl.gamgOverCorrection : 1.8;
+    const double lmax = 2.0, lmin = 0.3 * lmax;      // Gershgorin bound of D^-1 A for the M-matrices of every level
+    A->theta = 0.5 * (lmax + lmin); A->delta = 0.5 * (lmax - lmin);
+    for (size_t l = 0; l < H.size(); l++) {
+        A->lv.emplace_back(new Level<T>());
+        Level<T>& L = *A->lv.back();
+        int rc;
+        if (l == 0) {
+            L.n = c->N; L.ld = c->ld; L.nSlices = c->nSlices;
+            L.slicePtr = c->slicePtr.p; L.col = c->col.p;
+            if (sizeof(T) == sizeof(double)) L.a = reinterpret_cast<const T*>(c->eA.p);
+            else {
+                S4F_CHECK_CUDA(c, L.aB.alloc((size_t)c->nEntries, false));
+                k_amg_convert<T><<<(unsigned)((c->nEntries + 255) / 256), 256, 0, c->stream>>>(c->eA.p, L.aB.p, c->nEntries);
+                L.a = L.aB.p;
+            }
+            S4F_CHECK_CUDA(c, L.dg.alloc(3 * (size_t)L.ld)); S4F_CHECK_CUDA(c, L.rD.alloc(3 * (size_t)L.ld));
+            k_amg_diag<T><<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->diagC.p, L.dg.p, L.rD.p, c->N, c->ld, L.ld);
+            c->launches += 2;
+        } else {
+            if ((rc = A->build_level_rows(c, L, H[l]))) return rc;
+        }
+        if ((rc = A->alloc_work(c, L))) return rc;
+        if (l > 0) { if ((rc = A->set_transfer(c, *A->lv[l - 1], L, H[l - 1].parent, H[l].n))) return rc; }
+        A->sizes.push_back(H[l].n);
+        A->nnz.push_back(l == 0 ? (double)c->nnzOff : 2.0 * (double)H[l].own.size());
+    }
+    // dense inverse on the coarsest level
+    const HostLevel& HC = H.back();
+    std::vector<T> inv(3 * (size_t)HC.n * HC.n);
+    for (int q = 0; q < 3; q++) {
+        std::vector<double> iq;
+        if (!dense_inverse(HC, q, iq)) { c->err = "GAMG: coarsest-level matrix is not positive definite"; return 1; }
+        for (size_t i = 0; i < iq.size(); i++) inv[(size_t)q * HC.n * HC.n + i] = (T)iq[i];
+    }
+    S4F_CHECK_CUDA(c, A->denseInv.upload(inv));
+    S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+    A->bytesPerApply = A->bytes_per_apply(c->ld);
+    c->amg = guard.release();
+    return 0;
+}
+
+}  // namespace
+
+int s4f_download_upper(s4fgpu_ctx* c, double* hostUpper) {
+    if (c->F == 0) return 0;
+    DevBuf<double> up;
+    S4F_CHECK_CUDA(c, up.alloc((size_t)c->F, false));
+    k_gather_upper<<<(c->F + 255) / 256, 256, 0, c->stream>>>(c->faceEntry.p, c->eA.p, up.p, c->F);
+    c->launches++;
+    S4F_CHECK_CUDA(c, cudaMemcpyAsync(hostUpper, up.p, (size_t)c->F * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+void s4f_amg_destroy(s4fgpu_ctx* c) {
+    delete c->amg;
+    c->amg = nullptr;
+}
+
+// Build the hierarchy from the assembled fine matrix (upper() and the per-component diagonals).
+int s4f_amg_setup(s4fgpu_ctx* c) {
+    s4f_amg_destroy(c);
+    const auto t0 = std::chrono::steady_clock::now();
+    const int N = c->N, F = c->F;
+    std::vector<HostLevel> H(1);
+    HostLevel& L0 = H[0];
+    L0.n = N; L0.own = c->own; L0.nei = c->nei; L0.a.resize(F);
+    {
+        int rc = s4f_download_upper(c, L0.a.data()); if (rc) return rc;
+        for (int f = 0; f < F; f++) L0.a[f] = -L0.a[f];
+        std::vector<double> d(3 * (size_t)c->ld);
+        S4F_CHECK_CUDA(c, cudaMemcpy(d.data(), c->diagC.p, d.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int q = 0; q < 3; q++) L0.diag[q].assign(d.begin() + (size_t)q * c->ld, d.begin() + (size_t)q * c->ld + N);
+    }
+    const int coarsest = 512;
+    while (H.back().n > coarsest && H.size() < 12) {
+        // three pair-wise passes -> aggregates of up to 8 cells
+        HostLevel cur;                      // intermediate levels are discarded
+        const HostLevel* src = &H.back();
+        std::vector<int> total(src->n);
+        for (int i = 0; i < src->n; i++) total[i] = i;
+        HostLevel tmpA, tmpB;
+        int nc = src->n;
+        for (int pass = 0; pass < 3; pass++) {
+            std::vector<int> agg;
+            const int ncNew = pairwise_pass(*src, agg);
+            HostLevel& dst = (pass % 2 == 0) ? tmpA : tmpB;
+            galerkin(*src, agg, ncNew, dst);
+            for (size_t i = 0; i < total.size(); i++) total[i] = agg[total[i]];
+            src = &dst; nc = ncNew;
+            if (nc <= coarsest / 4) break;
+        }
+        if (nc >= H.back().n) break;        // no coarsening possible (no faces)
+        H.back().parent = total;
+        HostLevel next = *src;
+        H.push_back(std::move(next));
+    }
+    int rc;
+    if (c->ctl.gamgSinglePrecision) rc = build<float>(c, H);
+    else rc = build<double>(c, H);
+    if (!rc) c->amg->setupSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
+int s4f_amg_info(s4fgpu_ctx* c, int* nLevels, int* sizes, int maxLevels, double* bytesPerApply, double* setupSeconds) {
+    if (!c->amg) { c->err = "GAMG hierarchy missing"; return 1; }
+    *nLevels = (int)c->amg->sizes.size();
+    for (int i = 0; i < *nLevels && i < maxLevels; i++) sizes[i] = c->amg->sizes[i];
+    *bytesPerApply = c->amg->bytesPerApply; *setupSeconds = c->amg->setupSeconds;
+    return 0;
+}
+
+int s4f_amg_apply(s4fgpu_ctx* c, const double* r3, double* z3) {
+    if (!c->amg) { c->err = "GAMG hierarchy missing"; return 1; }
+    return c->amg->apply(c, r3, z3);
+}

@@ -3,6 +3,7 @@
 // convergence logic of solidModel::converged, solidModelTemplates.C:27-188).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "s4f_ctx.h"
@@ -111,6 +112,7 @@ int s4fgpu_create(s4fgpu_handle* out, int device) {
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_createError = cudaGetErrorString(e); delete c; return 2; }
     c->numSMs = prop.multiProcessorCount;
+    if (const char* v = getenv("S4F_AMUL_VARIANT")) c->amulVariant = atoi(v);
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { g_createError = cudaGetErrorString(e); delete c; return 2; }
     *out = c;
     return 0;
@@ -120,6 +122,7 @@ int s4fgpu_destroy(s4fgpu_handle c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    s4f_amg_destroy(c);
     if (c->comm) ncclCommDestroy(c->comm);
     if (c->hPcgS) cudaFreeHost(c->hPcgS);
     if (c->hOutS) cudaFreeHost(c->hOutS);
@@ -204,7 +207,7 @@ int s4fgpu_set_controls(s4fgpu_handle c, const s4fgpu_controls* ctl) {
                 "set_controls: this build implements linearGeometryTotalDisplacement and nonLinearGeometryTotalLagrangianTotalDisplacement");
     S4F_REQUIRE(c, ctl->solver == S4F_SOLVER_PCG, "set_controls: only PCG (the momentum matrix is symmetric)");
     S4F_REQUIRE(c, ctl->d2dt2Scheme == S4F_D2DT2_STEADY_STATE || ctl->d2dt2Scheme == S4F_D2DT2_EULER, "set_controls: d2dt2 scheme steadyState or Euler");
-    c->ctl = *ctl; c->ctlSet = true; c->matrixValid = false;
+    c->ctl = *ctl; c->ctlSet = true; c->matrixValid = false; c->amgValid = false;
     if (c->geomSet) return s4f_alloc_model_fields(c);
     return 0;
 }
@@ -267,6 +270,10 @@ int s4fgpu_upload(s4fgpu_handle c, int field, const double* host) {
 int s4fgpu_download(s4fgpu_handle c, int field, double* host) {
     S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
     S4F_REQUIRE(c, c->geomSet, "download: call set_geometry first");
+    if (field == S4F_FIELD_UPPER) {
+        if (!c->matrixValid) { int rc = s4f_assemble_matrix(c); if (rc) return rc; }
+        return s4f_download_upper(c, host);
+    }
     if (field == S4F_FIELD_TRACTION_GRADIENT_B) {
         std::vector<double> t(3 * (size_t)c->B);
         S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -401,12 +408,20 @@ int s4fgpu_time_kernel(s4fgpu_handle c, int kernel, int reps, int flushL2, doubl
     S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
     S4F_REQUIRE(c, c->geomSet && c->matrixValid, "time_kernel: initialise first");
     S4F_REQUIRE(c, reps > 0, "time_kernel: reps");
-    if (kernel == S4F_KERNEL_SPMV1 || kernel == S4F_KERNEL_SPMV3 || kernel == S4F_KERNEL_PCG_ITER)
+    if (kernel == S4F_KERNEL_SPMV1 || kernel == S4F_KERNEL_SPMV3 || kernel == S4F_KERNEL_PCG_ITER || kernel == S4F_KERNEL_PCG_P ||
+        kernel == S4F_KERNEL_PCG_XR || kernel == S4F_KERNEL_SPMV3_ROWS)
         return s4f_time_pcg_kernels(c, kernel, reps, flushL2, msPerLaunch, algoBytesPerLaunch);
     return s4f_time_fv_kernels(c, kernel, reps, flushL2, msPerLaunch, algoBytesPerLaunch);
 }
 
 long long s4fgpu_launch_count(s4fgpu_handle c) { return c ? c->launches : 0; }
+
+int s4fgpu_gamg_info(s4fgpu_handle c, int* nLevels, int* sizes, int maxLevels, double* bytesPerApply, double* setupSeconds) {
+    S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
+    S4F_REQUIRE(c, c->geomSet && c->matrixValid, "gamg_info: initialise first");
+    if (!c->amgValid) { int rc = s4f_amg_setup(c); if (rc) return rc; c->amgValid = true; }
+    return s4f_amg_info(c, nLevels, sizes, maxLevels, bytesPerApply, setupSeconds);
+}
 
 int s4fgpu_timer_start(s4fgpu_handle c) {
     S4F_CHECK_CUDA(c, cudaSetDevice(c->device));

@@ -139,6 +139,7 @@ struct s4fgpu_ctx {
     DevBuf<double> eRc;               // RhieChow compact coefficient gamma_f*magSf*delta
     DevBuf<double> eGam;              // RhieChow gamma_f
     DevBuf<double> V, rV;             // cell volumes [ld]
+    DevBuf<int> faceEntry;            // [F] entry index of internal face f in its owner's row (-> lduMatrix upper())
 
     // ---- boundary faces (B-arrays, SoA) and boundary-cell lists ----
     DevBuf<int> bFaceCell, bKind;     // [B] ; bKind = S4F_BC_* of the face's patch
@@ -167,6 +168,8 @@ struct s4fgpu_ctx {
     // ---- fvMatrix ----
     DevBuf<double> diag0;             // ld: sum of laplacian coefficients + d2dt2
     DevBuf<double> diagC;             // 3*ld: per-component diagonal after addBoundaryDiag
+    DevBuf<double> rDiagC;            // 3*ld: 1/diagC ([OF-ext] diagonalPreconditioner rD)
+    int amulVariant = 0;              // 0: component-per-warp SpMV, 1: row-per-thread (S4F_AMUL_VARIANT)
     DevBuf<double> source;            // 3*ld
     bool matrixValid = false;
     // ---- PCG work vectors ----
@@ -182,6 +185,8 @@ struct s4fgpu_ctx {
     PcgScalars* hPcgS = nullptr;      // pinned mirrors
     OuterScalars* hOutS = nullptr;
     double lambdaMax = 2.0;           // Chebyshev: bound of the Jacobi-scaled spectrum
+    struct S4fAmg* amg = nullptr;     // GAMG hierarchy (s4f_amg.cu), rebuilt with the matrix
+    bool amgValid = false;
 
     int iCorr = 0;
     long long totalInner = 0;
@@ -214,3 +219,8 @@ int s4f_time_fv_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, double
 int s4f_amul_device(s4fgpu_ctx* c, const double* x3, double* w3, int mask);
 int s4f_alloc_model_fields(s4fgpu_ctx* c);
 int s4f_upload_bc(s4fgpu_ctx* c);
+int s4f_amg_setup(s4fgpu_ctx* c);                                   // after s4f_assemble_matrix
+int s4f_amg_apply(s4fgpu_ctx* c, const double* r3, double* z3);     // z = M^-1 r, 3 components, stride ld
+void s4f_amg_destroy(s4fgpu_ctx* c);
+int s4f_amg_info(s4fgpu_ctx* c, int* nLevels, int* sizes, int maxLevels, double* bytesPerApply, double* setupSeconds);
+int s4f_download_upper(s4fgpu_ctx* c, double* hostUpper);           // lduMatrix upper() [F]

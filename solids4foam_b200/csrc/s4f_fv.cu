@@ -61,6 +61,13 @@ __global__ void k_diag_copy(const double* __restrict__ diag0, double* __restrict
     diagC[i] = d; diagC[(size_t)ld + i] = d; diagC[2 * (size_t)ld + i] = d;
 }
 
+__global__ void k_diag_recip(const double* __restrict__ diagC, double* __restrict__ rD, int N, int ld) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+#pragma unroll
+    for (int q = 0; q < 3; q++) rD[(size_t)q * ld + i] = 1.0 / diagC[(size_t)q * ld + i];
+}
+
 // addBoundaryDiag: internalCoeffs = impKf_b*magSf_b*deltaCoeffs_b for fixedValue, times |n_c| for the
 // symmetry plane ([OF-ext] basicSymmetry snGradTransformDiag), zero for fixedGradient.
 __global__ void k_diag_boundary(const int* __restrict__ bcCells, const int* __restrict__ bcPtr, const int* __restrict__ bcFaces,
@@ -525,7 +532,10 @@ int s4f_assemble_matrix(s4fgpu_ctx* c) {
                                                                        c->bMagSf.p, c->impK.p, c->diagC.p, c->nBCells, c->B, c->bOff(), c->ld);
         c->launches++;
     }
+    k_diag_recip<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->diagC.p, c->rDiagC.p, c->N, c->ld);
+    c->launches++;
     c->matrixValid = true;
+    c->amgValid = false;
     S4F_CHECK_CUDA(c, cudaGetLastError());
     return 0;
 }
@@ -618,6 +628,10 @@ int s4f_relax_and_residual(s4fgpu_ctx* c, int iCorr) {
 
 // ---- timing of the face-loop kernels (bench.py roofline) ----------------------------------------
 int s4f_time_fv_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, double* msOut, double* bytesOut) {
+    if (kernel == S4F_KERNEL_GAMG_VCYCLE && !c->amgValid) {
+        int rc = s4f_amg_setup(c); if (rc) return rc;
+        c->amgValid = true;
+    }
     if (flushL2 && c->flushBuf.n < (size_t)48 * 1024 * 1024) S4F_CHECK_CUDA(c, c->flushBuf.alloc((size_t)48 * 1024 * 1024));
     cudaEvent_t e0, e1;
     S4F_CHECK_CUDA(c, cudaEventCreate(&e0)); S4F_CHECK_CUDA(c, cudaEventCreate(&e1));
@@ -628,6 +642,7 @@ int s4f_time_fv_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, double
         int rc = 0;
         if (kernel == S4F_KERNEL_GRAD) rc = s4f_grad(c);
         else if (kernel == S4F_KERNEL_LAW) rc = s4f_law_correct(c);
+        else if (kernel == S4F_KERNEL_GAMG_VCYCLE) rc = s4f_amg_apply(c, c->rA.p, c->wA.p);
         else rc = s4f_assemble_source(c);
         if (rc) return rc;
         S4F_CHECK_CUDA(c, cudaEventRecord(e1, c->stream));
@@ -640,6 +655,7 @@ int s4f_time_fv_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, double
     const double N = c->N, nnz = (double)c->nnzOff + (c->B - c->G);   // row entries incl. boundary faces
     if (kernel == S4F_KERNEL_GRAD) *bytesOut = 24 * N + nnz * (4 + 24) + 72 * N + 0.125 * N;                 // D, (col, ls), gradD out
     else if (kernel == S4F_KERNEL_LAW) *bytesOut = (72 + 48) * N;                                              // gradD in, sigma out (Hooke)
+    else if (kernel == S4F_KERNEL_GAMG_VCYCLE) { int nl, sz[16]; double st; int rc = s4f_amg_info(c, &nl, sz, 16, bytesOut, &st); if (rc) return rc; }
     else *bytesOut = (24 + 48 + 72) * N + nnz * (4 + 8 + 8 + 24 + 8 + 8) + 8 * N + 24 * N + 0.125 * N;        // D,sigma,gradD | col,a,w,Sf,rc,gam | V | out
     return 0;
 }

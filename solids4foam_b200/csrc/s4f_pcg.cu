@@ -69,19 +69,19 @@ __device__ void pcg_scalar_step(int phase, PcgScalars* S, const double* tot, con
         int any = 0;
         for (int c = 0; c < 3; c++) {
             if (S->active[c]) {
+                const bool local = (P.precond == S4F_PRECOND_DIAGONAL || P.precond == S4F_PRECOND_NONE);
                 S->finalRes[c] = tot[c] / S->normFactor[c];
                 S->rhoOld[c] = S->rho[c];
-                S->rho[c] = tot[3 + c];
+                if (local) S->rho[c] = tot[3 + c];      // wArA of the next iteration comes with this reduction
                 S->nIter[c] += 1;
                 if (!(S->nIter[c] < P.maxIter && !conv_check(P, S->finalRes[c], S->initRes[c]))) S->active[c] = 0;
-                else S->beta[c] = S->rho[c] / S->rhoOld[c];
+                else if (local) S->beta[c] = S->rho[c] / S->rhoOld[c];
             }
             any |= S->active[c];
         }
         S->anyActive = any;
     } else if (phase == PH_DOT) {   // generic preconditioner path: rho = wA.rA
-        for (int c = 0; c < 3; c++) if (S->active[c]) {
-            if (S->nIter[c] > 0) S->rhoOld[c] = S->rho[c];
+        for (int c = 0; c < 3; c++) if (S->active[c]) {   // rhoOld was saved by PH_XR
             S->rho[c] = tot[c];
             S->beta[c] = (S->nIter[c] > 0) ? S->rho[c] / S->rhoOld[c] : 0.0;
         }
@@ -117,8 +117,9 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_pcg_sum(const double* __restrict_
 // wA = A psi ; rA = b - wA ; sums |rA|, |wA - sumA*avg| + |b - sumA*avg|, rA.rA/diag
 __global__ void __launch_bounds__(S4F_BLOCK) k_pcg_init(const int* __restrict__ slicePtr, const int* __restrict__ col,
                                                         const double* __restrict__ eA, const double* __restrict__ diagC,
-                                                        const double* __restrict__ x, const double* __restrict__ b,
-                                                        double* __restrict__ r, int N, int ld, int nSlices, PcgScalars* S,
+                                                        const double* __restrict__ rDiag, const double* __restrict__ x,
+                                                        const double* __restrict__ b, double* __restrict__ r, int N, int ld,
+                                                        int nSlices, PcgScalars* S,
                                                         PcgParams P, double nGlob, double* partials, unsigned int* ticket) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -150,28 +151,42 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_pcg_init(const int* __restrict__ 
                 const double t = (d - sa) * av[c];
                 v[c] += fabs(rr);
                 v[3 + c] += fabs(w - t) + fabs(bb - t);
-                v[6 + c] += (P.precond == S4F_PRECOND_NONE) ? rr * rr : rr * rr / d;
+                v[6 + c] += (P.precond == S4F_PRECOND_NONE) ? rr * rr : (rDiag[(size_t)c * ld + row] * rr) * rr;
             }
         }
     }
     grid_reduce<9, OpSum>(v, partials, ticket, Fin{PH_INIT, S, P, nGlob, 9});
 }
 
-// pA = rA/diag + beta pA   (first iteration: pA = rA/diag)
-__global__ void __launch_bounds__(S4F_BLOCK) k_pcg_p(const double* __restrict__ diagC, const double* __restrict__ r,
+// ---- streaming vector kernels: two cells per thread (128-bit loads), all loads of a component issued
+// before its arithmetic.  Only rows [0,N) are touched: [N, ld) holds ghost and boundary-value slots.
+__device__ __forceinline__ double2 ld2(const double* p, size_t i) { return *reinterpret_cast<const double2*>(p + i); }
+__device__ __forceinline__ void st2(double* p, size_t i, double2 v) { *reinterpret_cast<double2*>(p + i) = v; }
+
+// pA = rD rA + beta pA   (first iteration: pA = rD rA);  rD = 1/diag ([OF-ext] diagonalPreconditioner)
+__global__ void __launch_bounds__(S4F_BLOCK) k_pcg_p(const double* __restrict__ rD, const double* __restrict__ r,
                                                      double* __restrict__ p, int N, int ld, const PcgScalars* __restrict__ S) {
     if (!S->anyActive) return;
-    int act[3]; double beta[3]; int first[3];
+    int act[3]; double beta[3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) { act[c] = S->active[c]; beta[c] = S->beta[c]; first[c] = (S->nIter[c] == 0); }
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    for (int c = 0; c < 3; c++) { act[c] = S->active[c]; beta[c] = (S->nIter[c] == 0) ? 0.0 : S->beta[c]; }
+    const int n2 = N >> 1;
+    for (int i2 = blockIdx.x * blockDim.x + threadIdx.x; i2 < n2; i2 += gridDim.x * blockDim.x) {
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             if (!act[c]) continue;
-            const size_t j = (size_t)c * ld + i;
-            const double z = r[j] / diagC[j];
-            p[j] = first[c] ? z : z + beta[c] * p[j];
+            const size_t j = (size_t)c * ld + 2 * (size_t)i2;
+            const double2 rr = ld2(r, j), dd = ld2(rD, j);
+            double2 pp = make_double2(0.0, 0.0);
+            if (beta[c] != 0.0) pp = ld2(p, j);
+            pp.x = dd.x * rr.x + beta[c] * pp.x; pp.y = dd.y * rr.y + beta[c] * pp.y;
+            st2(p, j, pp);
         }
+    }
+    if ((N & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int i = N - 1;
+#pragma unroll
+        for (int c = 0; c < 3; c++) if (act[c]) { const size_t j = (size_t)c * ld + i; p[j] = rD[j] * r[j] + (beta[c] != 0.0 ? beta[c] * p[j] : 0.0); }
     }
 }
 
@@ -179,16 +194,26 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_pcg_p(const double* __restrict__ 
 __global__ void __launch_bounds__(S4F_BLOCK) k_pcg_p_generic(const double* __restrict__ z, double* __restrict__ p, int N, int ld,
                                                              const PcgScalars* __restrict__ S) {
     if (!S->anyActive) return;
-    int act[3]; double beta[3]; int first[3];
+    int act[3]; double beta[3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) { act[c] = S->active[c]; beta[c] = S->beta[c]; first[c] = (S->nIter[c] == 0); }
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    for (int c = 0; c < 3; c++) { act[c] = S->active[c]; beta[c] = (S->nIter[c] == 0) ? 0.0 : S->beta[c]; }
+    const int n2 = N >> 1;
+    for (int i2 = blockIdx.x * blockDim.x + threadIdx.x; i2 < n2; i2 += gridDim.x * blockDim.x) {
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             if (!act[c]) continue;
-            const size_t j = (size_t)c * ld + i;
-            p[j] = first[c] ? z[j] : z[j] + beta[c] * p[j];
+            const size_t j = (size_t)c * ld + 2 * (size_t)i2;
+            const double2 zz = ld2(z, j);
+            double2 pp = make_double2(0.0, 0.0);
+            if (beta[c] != 0.0) pp = ld2(p, j);
+            pp.x = zz.x + beta[c] * pp.x; pp.y = zz.y + beta[c] * pp.y;
+            st2(p, j, pp);
         }
+    }
+    if ((N & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int i = N - 1;
+#pragma unroll
+        for (int c = 0; c < 3; c++) if (act[c]) { const size_t j = (size_t)c * ld + i; p[j] = z[j] + (beta[c] != 0.0 ? beta[c] * p[j] : 0.0); }
     }
 }
 
@@ -253,6 +278,55 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_amul3(const int* __restrict__ sli
     if (DOT) grid_reduce<3, OpSum>(v, partials, ticket, Fin{PH_AMUL, S, P, nGlob, 3});
 }
 
+// wA = A pA, sums wA.pA -- component-per-warp mapping: three consecutive warps of a block take the SAME
+// slice, one displacement component each.  Per thread this is the scalar SpMV (few registers, full
+// occupancy, two independent loads per entry in flight); the matrix entries of a slice are fetched
+// from HBM once and reach the other two warps through L1/L2, so the HBM traffic is that of the fused
+// 3-component product.  Components whose solve has finished are skipped (no traffic for them).
+#define S4F_AMUL_BLOCK 192
+template <bool DOT>
+__global__ void __launch_bounds__(S4F_AMUL_BLOCK) k_amul3c(const int* __restrict__ slicePtr, const int* __restrict__ col,
+                                                           const double* __restrict__ eA, const double* __restrict__ diagC,
+                                                           const double* __restrict__ p, double* __restrict__ w, int N, int ld,
+                                                           int nSlices, PcgScalars* S, PcgParams P, double nGlob, double* partials,
+                                                           unsigned int* ticket, int cmptMask) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int q = wib % 3, sub = wib / 3;
+    int active;
+    if (DOT) { if (!S->anyActive) return; active = S->active[q]; }
+    else active = (cmptMask >> q) & 1;
+    double v[3] = {0, 0, 0};
+    if (active) {
+        const double* __restrict__ pq = p + (size_t)q * ld;
+        const double* __restrict__ dq = diagC + (size_t)q * ld;
+        double* __restrict__ wq = w + (size_t)q * ld;
+        double acc = 0;
+        constexpr int SPB = S4F_AMUL_BLOCK / 96;      // slices per block step
+        for (int s = blockIdx.x * SPB + sub; s < nSlices; s += gridDim.x * SPB) {
+            const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
+            const int row = s * 32 + lane;
+            double a0 = 0, a1 = 0;
+            const int* cp = col + base + lane;
+            const double* ap = eA + base + lane;
+            int k = 0;
+            for (; k + 1 < width; k += 2) {
+                const int c0 = cp[32 * k], c1 = cp[32 * k + 32];
+                const double e0 = ap[32 * k], e1 = ap[32 * k + 32];
+                a0 += e0 * pq[c0]; a1 += e1 * pq[c1];
+            }
+            if (k < width) a0 += ap[32 * k] * pq[cp[32 * k]];
+            if (row < N) {
+                const double pp = pq[row];
+                const double ww = dq[row] * pp - (a0 + a1);
+                wq[row] = ww;
+                if (DOT) acc += ww * pp;
+            }
+        }
+        v[q] = acc;
+    }
+    if (DOT) grid_reduce<3, OpSum>(v, partials, ticket, Fin{PH_AMUL, S, P, nGlob, 3});
+}
+
 // scalar (single-vector) Amul, for the roofline number the metric quotes
 __global__ void __launch_bounds__(S4F_BLOCK) k_amul1(const int* __restrict__ slicePtr, const int* __restrict__ col,
                                                      const double* __restrict__ eA, const double* __restrict__ diag,
@@ -272,8 +346,8 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_amul1(const int* __restrict__ sli
     }
 }
 
-// psi += alpha pA; rA -= alpha wA; sums |rA| and rA.rA/diag (the next wArA for the diagonal preconditioner)
-__global__ void __launch_bounds__(S4F_BLOCK) k_pcg_xr(const double* __restrict__ diagC, double* __restrict__ x, double* __restrict__ r,
+// psi += alpha pA; rA -= alpha wA; sums |rA| and (rD rA).rA (the next wArA for the diagonal preconditioner)
+__global__ void __launch_bounds__(S4F_BLOCK) k_pcg_xr(const double* __restrict__ rD, double* __restrict__ x, double* __restrict__ r,
                                                       const double* __restrict__ p, const double* __restrict__ w, int N, int ld,
                                                       PcgScalars* S, PcgParams P, double nGlob, double* partials, unsigned int* ticket) {
     if (!S->anyActive) return;
@@ -281,7 +355,25 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_pcg_xr(const double* __restrict__
 #pragma unroll
     for (int c = 0; c < 3; c++) { act[c] = S->active[c]; alpha[c] = S->alpha[c]; }
     double v[6] = {0, 0, 0, 0, 0, 0};
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const int n2 = N >> 1;
+    for (int i2 = blockIdx.x * blockDim.x + threadIdx.x; i2 < n2; i2 += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (!act[c]) continue;
+            const size_t j = (size_t)c * ld + 2 * (size_t)i2;
+            double2 xx = ld2(x, j), rr = ld2(r, j);
+            const double2 pp = ld2(p, j), ww = ld2(w, j);
+            double2 dd = make_double2(1.0, 1.0);
+            if (P.precond == S4F_PRECOND_DIAGONAL) dd = ld2(rD, j);
+            xx.x += alpha[c] * pp.x; xx.y += alpha[c] * pp.y;
+            rr.x -= alpha[c] * ww.x; rr.y -= alpha[c] * ww.y;
+            st2(x, j, xx); st2(r, j, rr);
+            v[c] += fabs(rr.x) + fabs(rr.y);
+            if (P.precond == S4F_PRECOND_DIAGONAL || P.precond == S4F_PRECOND_NONE) v[3 + c] += (dd.x * rr.x) * rr.x + (dd.y * rr.y) * rr.y;
+        }
+    }
+    if ((N & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int i = N - 1;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             if (!act[c]) continue;
@@ -290,7 +382,7 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_pcg_xr(const double* __restrict__
             const double rr = r[j] - alpha[c] * w[j];
             r[j] = rr;
             v[c] += fabs(rr);
-            if (P.precond == S4F_PRECOND_DIAGONAL) v[3 + c] += rr * rr / diagC[j];
+            if (P.precond == S4F_PRECOND_DIAGONAL) v[3 + c] += (rD[j] * rr) * rr;
             else if (P.precond == S4F_PRECOND_NONE) v[3 + c] += rr * rr;
         }
     }
@@ -416,6 +508,20 @@ static int allreduce_part(s4fgpu_ctx* c, int n, int phase, const PcgParams& P, d
 }
 
 static int amul3(s4fgpu_ctx* c, const double* p, double* w, bool dot, const PcgParams& P, double nGlob, int mask) {
+    if (c->amulVariant == 0) {      // component-per-warp mapping (default)
+        long long need = ((long long)c->nSlices + 1) / 2;
+        long long g = (long long)c->numSMs * 10;          // 10 x 192 threads = 1920 resident threads per SM
+        if (need < g) g = need;
+        if (g < 1) g = 1;
+        if (dot)
+            k_amul3c<true><<<(int)g, S4F_AMUL_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, p, w, c->N, c->ld, c->nSlices,
+                                                                     c->pcgS.p, P, nGlob, c->partials.p, c->ticket.p, mask);
+        else
+            k_amul3c<false><<<(int)g, S4F_AMUL_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, p, w, c->N, c->ld, c->nSlices,
+                                                                      c->pcgS.p, P, nGlob, c->partials.p, c->ticket.p, mask);
+        c->launches++;
+        return 0;
+    }
     const int grid = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
     if (dot)
         k_amul3<true><<<grid, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, p, w, c->N, c->ld, c->nSlices,
@@ -482,19 +588,23 @@ int s4f_solve_segregated(s4fgpu_ctx* c, double* psi, const double* source) {
     const int N = c->N, ld = c->ld;
     PcgParams P = make_params(c);
     const double nGlob = global_cells(c);
-    const int gridV = s4f_grid(c->numSMs, N), gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
+    const int gridV = s4f_grid(c->numSMs, N), gridV2 = s4f_grid(c->numSMs, (N + 1) / 2), gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
     PcgScalars* S = c->pcgS.p;
     const bool fusedJacobi = (P.precond == S4F_PRECOND_DIAGONAL || P.precond == S4F_PRECOND_NONE || P.precond == S4F_PRECOND_DIC);
     if (P.precond == S4F_PRECOND_DIC) P.precond = S4F_PRECOND_DIAGONAL;   // GPU stand-in, reported
     if (P.precond == S4F_PRECOND_CHEBYSHEV && c->cheb0.n != 3 * (size_t)ld) {
         S4F_CHECK_CUDA(c, c->cheb0.alloc(3 * (size_t)ld)); S4F_CHECK_CUDA(c, c->cheb1.alloc(3 * (size_t)ld));
     }
+    if (P.precond == S4F_PRECOND_GAMG && !c->amgValid) {
+        int rca = s4f_amg_setup(c); if (rca) return rca;
+        c->amgValid = true;
+    }
 
     k_pcg_sum<<<gridV, S4F_BLOCK, 0, c->stream>>>(psi, N, ld, S, P, nGlob, c->partials.p, c->ticket.p);
     c->launches++;
     int rc = allreduce_part(c, 3, PH_AVG, P, nGlob); if (rc) return rc;
     rc = s4f_halo_exchange(c, psi, 3); if (rc) return rc;
-    k_pcg_init<<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, psi, source, c->rA.p, N, ld, c->nSlices,
+    k_pcg_init<<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, c->rDiagC.p, psi, source, c->rA.p, N, ld, c->nSlices,
                                                    S, P, nGlob, c->partials.p, c->ticket.p);
     c->launches++;
     rc = allreduce_part(c, 9, PH_INIT, P, nGlob); if (rc) return rc;
@@ -508,22 +618,24 @@ int s4f_solve_segregated(s4fgpu_ctx* c, double* psi, const double* source) {
         for (int k = 0; k < checkEvery; k++, it++) {
             if (fusedJacobi) {
                 if (c->ctl.preconditioner == S4F_PRECOND_NONE)
-                    k_pcg_p_generic<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->rA.p, c->pA.p, N, ld, S);
+                    k_pcg_p_generic<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rA.p, c->pA.p, N, ld, S);
                 else
-                    k_pcg_p<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->diagC.p, c->rA.p, c->pA.p, N, ld, S);
+                    k_pcg_p<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rDiagC.p, c->rA.p, c->pA.p, N, ld, S);
                 c->launches++;
             } else {
-                rc = cheb_apply(c, P); if (rc) return rc;
+                if (P.precond == S4F_PRECOND_GAMG) rc = s4f_amg_apply(c, c->rA.p, c->wA.p);
+                else rc = cheb_apply(c, P);
+                if (rc) return rc;
                 k_pcg_dot_zr<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->wA.p, c->rA.p, N, ld, S, P, nGlob, c->partials.p, c->ticket.p);
                 c->launches++;
                 rc = allreduce_part(c, 3, PH_DOT, P, nGlob); if (rc) return rc;
-                k_pcg_p_generic<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->wA.p, c->pA.p, N, ld, S);
+                k_pcg_p_generic<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->wA.p, c->pA.p, N, ld, S);
                 c->launches++;
             }
             rc = s4f_halo_exchange(c, c->pA.p, 3); if (rc) return rc;
             rc = amul3(c, c->pA.p, c->wA.p, true, P, nGlob, 7); if (rc) return rc;
             rc = allreduce_part(c, 3, PH_AMUL, P, nGlob); if (rc) return rc;
-            k_pcg_xr<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->diagC.p, psi, c->rA.p, c->pA.p, c->wA.p, N, ld, S, P, nGlob, c->partials.p, c->ticket.p);
+            k_pcg_xr<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rDiagC.p, psi, c->rA.p, c->pA.p, c->wA.p, N, ld, S, P, nGlob, c->partials.p, c->ticket.p);
             c->launches++;
             rc = allreduce_part(c, 6, PH_XR, P, nGlob); if (rc) return rc;
         }
@@ -539,20 +651,35 @@ int s4f_solve_segregated(s4fgpu_ctx* c, double* psi, const double* source) {
 }
 
 // ---- kernel timing for the roofline numbers (bench.py) ----------------------------------------
+namespace {
+__global__ void k_fill_pattern(double* __restrict__ a, int N, int ld, double base, double amp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+#pragma unroll
+    for (int c = 0; c < 3; c++) a[(size_t)c * ld + i] = base + amp * (double)((i * 7 + c * 3) % 11);
+}
+}  // namespace
+
 int s4f_time_pcg_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, double* msOut, double* bytesOut) {
     const int N = c->N, ld = c->ld;
     PcgParams P = make_params(c);
-    if (P.precond == S4F_PRECOND_DIC || P.precond == S4F_PRECOND_CHEBYSHEV) P.precond = S4F_PRECOND_DIAGONAL;
-    const int gridV = s4f_grid(c->numSMs, N), gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
+    P.precond = S4F_PRECOND_DIAGONAL;
+    const int gridV2 = s4f_grid(c->numSMs, (N + 1) / 2), gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
     const double nnz = (double)c->nnzOff;
-    // make every component "active" with harmless scalars
+    // non-trivial vectors; every component "active" with harmless scalars.  The x vector of the xr kernel is
+    // the source field (rebuilt by every outer iteration), not D.
+    k_fill_pattern<<<(N + 255) / 256, 256, 0, c->stream>>>(c->pA.p, N, ld, 1.0, 1e-3);
+    k_fill_pattern<<<(N + 255) / 256, 256, 0, c->stream>>>(c->rA.p, N, ld, -0.5, 2e-3);
+    c->launches += 2;
     PcgScalars h; memset(&h, 0, sizeof(h));
-    for (int q = 0; q < 3; q++) { h.active[q] = 1; h.alpha[q] = 1e-30; h.beta[q] = 0.5; h.nIter[q] = 1; h.rho[q] = 1; h.rhoOld[q] = 1; h.normFactor[q] = 1; h.initRes[q] = 1; }
+    for (int q = 0; q < 3; q++) { h.active[q] = 1; h.alpha[q] = 1e-3; h.beta[q] = 0.5; h.nIter[q] = 1; h.rho[q] = 1; h.rhoOld[q] = 1; h.normFactor[q] = 1; h.initRes[q] = 1; }
     h.anyActive = 1;
     PcgParams Pn = P; Pn.maxIter = 1 << 30; Pn.tolerance = 0; Pn.relTol = 0; Pn.defer = 0;
     if (flushL2 && c->flushBuf.n == 0) S4F_CHECK_CUDA(c, c->flushBuf.alloc((size_t)48 * 1024 * 1024));   // 384 MB > 126 MB L2
     cudaEvent_t e0, e1;
     S4F_CHECK_CUDA(c, cudaEventCreate(&e0)); S4F_CHECK_CUDA(c, cudaEventCreate(&e1));
+    const int savedVariant = c->amulVariant;
+    if (kernel == S4F_KERNEL_SPMV3_ROWS) c->amulVariant = 1;
     double total = 0;
     for (int r = -3; r < reps; r++) {
         S4F_CHECK_CUDA(c, cudaMemcpyAsync(c->pcgS.p, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
@@ -561,28 +688,38 @@ int s4f_time_pcg_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, doubl
         if (kernel == S4F_KERNEL_SPMV1) {
             k_amul1<<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, c->pA.p, c->wA.p, N, c->nSlices);
             c->launches++;
-        } else if (kernel == S4F_KERNEL_SPMV3) {
-            k_amul3<true><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, c->pA.p, c->wA.p, N, ld, c->nSlices,
-                                                              c->pcgS.p, Pn, 1.0, c->partials.p, c->ticket.p, 7);
+        } else if (kernel == S4F_KERNEL_SPMV3 || kernel == S4F_KERNEL_SPMV3_ROWS) {
+            amul3(c, c->pA.p, c->wA.p, true, Pn, 1.0, 7);
+        } else if (kernel == S4F_KERNEL_PCG_P) {
+            k_pcg_p<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rDiagC.p, c->rA.p, c->pA.p, N, ld, c->pcgS.p);
+            c->launches++;
+        } else if (kernel == S4F_KERNEL_PCG_XR) {
+            k_pcg_xr<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rDiagC.p, c->source.p, c->rA.p, c->pA.p, c->wA.p, N, ld, c->pcgS.p, Pn, 1.0, c->partials.p, c->ticket.p);
             c->launches++;
         } else {
-            k_pcg_p<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->diagC.p, c->rA.p, c->pA.p, N, ld, c->pcgS.p);
-            k_amul3<true><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, c->pA.p, c->wA.p, N, ld, c->nSlices,
-                                                              c->pcgS.p, Pn, 1.0, c->partials.p, c->ticket.p, 7);
-            k_pcg_xr<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->diagC.p, c->D.p, c->rA.p, c->pA.p, c->wA.p, N, ld, c->pcgS.p, Pn, 1.0, c->partials.p, c->ticket.p);
-            c->launches += 3;
+            k_pcg_p<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rDiagC.p, c->rA.p, c->pA.p, N, ld, c->pcgS.p);
+            c->launches++;
+            amul3(c, c->pA.p, c->wA.p, true, Pn, 1.0, 7);
+            k_pcg_xr<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rDiagC.p, c->source.p, c->rA.p, c->pA.p, c->wA.p, N, ld, c->pcgS.p, Pn, 1.0, c->partials.p, c->ticket.p);
+            c->launches++;
         }
         S4F_CHECK_CUDA(c, cudaEventRecord(e1, c->stream));
         S4F_CHECK_CUDA(c, cudaEventSynchronize(e1));
         float ms; S4F_CHECK_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
         if (r >= 0) total += ms;
     }
+    c->amulVariant = savedVariant;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    S4F_CHECK_CUDA(c, cudaGetLastError());
     *msOut = total / reps;
     // algorithmic bytes: fp64 values, int32 columns, one slice pointer per 32 rows
-    if (kernel == S4F_KERNEL_SPMV1) *bytesOut = 12.0 * nnz + (8 + 8 + 8 + 0.125) * N;             // a,col | diag, x, y, slicePtr
-    else if (kernel == S4F_KERNEL_SPMV3) *bytesOut = 12.0 * nnz + (24 + 24 + 24 + 0.125) * N;
-    else *bytesOut = (12.0 * nnz + (24 + 24 + 24 + 0.125) * N) + (24 + 24 + 24 + 24.0) * N + (24 * 4 + 24 * 2 + 24.0) * N;
-    // restore a clean D (k_pcg_xr touched it with alpha = 1e-30 * p: negligible but not zero) is left to the caller
+    const double spmv3 = 12.0 * nnz + (24 + 24 + 24 + 0.125) * N;             // a,col | diag, p, w, slicePtr
+    const double pk = (24 + 24 + 24 + 24.0) * N;                             // r, rD, p in | p out
+    const double xr = (24 * 5 + 24 * 2.0) * N;                               // x, r, p, w, rD in | x, r out
+    if (kernel == S4F_KERNEL_SPMV1) *bytesOut = 12.0 * nnz + (8 + 8 + 8 + 0.125) * N;
+    else if (kernel == S4F_KERNEL_SPMV3 || kernel == S4F_KERNEL_SPMV3_ROWS) *bytesOut = spmv3;
+    else if (kernel == S4F_KERNEL_PCG_P) *bytesOut = pk;
+    else if (kernel == S4F_KERNEL_PCG_XR) *bytesOut = xr;
+    else *bytesOut = spmv3 + pk + xr;
     return 0;
 }

@@ -146,7 +146,7 @@ int s4f_build_rows(s4fgpu_ctx* c) {
         for (int k = 0; k < 6; k++) invDd[6 * (size_t)P + k] = r[k];
     }
 
-    std::vector<int> hCol(nE);
+    std::vector<int> hCol(nE), hFaceEntry(std::max(F, 1), 0);
     std::vector<double> hW(nE, 1.0), hSf(3 * nE, 0.0), hLs(3 * nE, 0.0), hDn(nE, 0.0), hCorr;
     bool nonOrth = false;
     for (size_t i = 0; i < c->hCorr.size(); i++) if (std::fabs(c->hCorr[i]) > 1e-12) { nonOrth = true; break; }
@@ -164,6 +164,7 @@ int s4f_build_rows(s4fgpu_ctx* c) {
                 const int f = rFace[e];
                 const double sg = rSign[e];
                 hCol[E] = rCol[e];
+                if (f < F && sg > 0) hFaceEntry[f] = (int)E;
                 const bool bnd = (f >= F) && (c->ghostOfFace[f - F] < 0);
                 if (bnd) hW[E] = 0.0;
                 else hW[E] = (sg > 0) ? c->hW[f] : 1.0 - c->hW[f];
@@ -183,6 +184,7 @@ int s4f_build_rows(s4fgpu_ctx* c) {
     }
     S4F_CHECK_CUDA(c, c->slicePtr.upload(slicePtr));
     S4F_CHECK_CUDA(c, c->col.upload(hCol));
+    S4F_CHECK_CUDA(c, c->faceEntry.upload(hFaceEntry));
     S4F_CHECK_CUDA(c, c->eW.upload(hW));
     S4F_CHECK_CUDA(c, c->eSf.upload(hSf));
     S4F_CHECK_CUDA(c, c->eLs.upload(hLs));
@@ -248,7 +250,7 @@ int s4f_alloc_fields(s4fgpu_ctx* c) {
     S4F_CHECK_CUDA(c, A(c->gradD, 9)); S4F_CHECK_CUDA(c, A(c->gradDold, 9));
     S4F_CHECK_CUDA(c, A(c->sigma, 6)); S4F_CHECK_CUDA(c, A(c->sigmaOld, 6));
     S4F_CHECK_CUDA(c, A(c->impK, 1));
-    S4F_CHECK_CUDA(c, A(c->diag0, 1)); S4F_CHECK_CUDA(c, A(c->diagC, 3)); S4F_CHECK_CUDA(c, A(c->source, 3));
+    S4F_CHECK_CUDA(c, A(c->diag0, 1)); S4F_CHECK_CUDA(c, A(c->diagC, 3)); S4F_CHECK_CUDA(c, A(c->rDiagC, 3)); S4F_CHECK_CUDA(c, A(c->source, 3));
     S4F_CHECK_CUDA(c, A(c->pA, 3)); S4F_CHECK_CUDA(c, A(c->wA, 3)); S4F_CHECK_CUDA(c, A(c->rA, 3));
     S4F_CHECK_CUDA(c, c->pcgS.alloc(1)); S4F_CHECK_CUDA(c, c->outS.alloc(1));
     S4F_CHECK_CUDA(c, c->partials.alloc(32 * 4096)); S4F_CHECK_CUDA(c, c->ticket.alloc(8));

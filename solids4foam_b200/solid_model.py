@@ -17,7 +17,7 @@ import numpy as np
 from . import case as K
 from ._lib import lib
 
-KERNELS = dict(spmv1=0, spmv3=1, pcg_iter=2, grad=3, law=4, rhs=5)
+KERNELS = dict(spmv1=0, spmv3=1, pcg_iter=2, grad=3, law=4, rhs=5, pcg_p=6, pcg_xr=7, spmv3_rows=8, gamg_vcycle=9)
 
 
 class SolidModel:
@@ -162,6 +162,11 @@ class SolidModel:
 
     def synchronize(self) -> None:
         self._check(self.L.s4fgpu_synchronize(self.h))
+
+    def gamg_info(self) -> dict:
+        n, sizes, by, st = C.c_int(), (C.c_int * 16)(), C.c_double(), C.c_double()
+        self._check(self.L.s4fgpu_gamg_info(self.h, C.byref(n), sizes, 16, C.byref(by), C.byref(st)))
+        return dict(levels=[sizes[i] for i in range(n.value)], bytes_per_vcycle=by.value, setup_seconds=st.value)
 
     def launch_count(self) -> int:
         return int(self.L.s4fgpu_launch_count(self.h))

@@ -139,3 +139,66 @@ def test_patch_test_constant_strain():
     assert np.abs(eps[:, 0, 1] - 4e-6).max() < 1e-14 * 1e3
 
 
+
+
+# ---------------------------------------------------------------------------------------------
+# GAMG-preconditioned PCG (the reference's other preconditioner family: [OF-ext] GAMGPreconditioner).
+# The oracle answers with DIC-PCG; both are converged tightly, so the solutions must agree although the
+# iteration counts differ (both are reported).
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("single", [0, 1])
+@pytest.mark.parametrize("case_fn,kw", [
+    (cases.cantilever, dict(nx=40, ny=10, nz=10)),      # 4000 cells: two coarse levels
+    (cases.plate_hole, dict()),                          # 2-D, non-orthogonal, symmetry planes (per-component diagonals)
+    (cases.cantilever, dict(nx=6, ny=4, nz=4)),          # < 512 cells: the dense coarsest solve alone
+])
+def test_gamg_pcg_solves_the_assembled_system(case_fn, kw, single):
+    kw = dict(kw, tolerance=1e-12, relTol=0.0, maxIter=400)
+    g, o, mesh = _pair(case_fn, preconditioner=K.PRECOND_GAMG, gamgSinglePrecision=single, **kw)
+    gj = _pair(case_fn, preconditioner=K.PRECOND_DIAGONAL, **kw)[0]
+    D = _analytic_D(mesh)
+    if mesh.solutionD[2] == 0:
+        D[:, 2] = 0
+    for s in (g, o, gj):
+        s.set("D", D)
+        s.initialise()
+        s.op_correct()
+        s.op_assemble()
+    assert rel_l2(g.get("upper"), o.get("upper")) < OP_TOL          # lduMatrix upper() through the face->entry map
+    src = o.get("source")
+    psi_g, st_g = g.op_solve(D, src)
+    psi_o, st_o = o.op_solve(D, src)          # DIC-PCG
+    psi_j, st_j = gj.op_solve(D, src)         # Jacobi-PCG on the GPU
+    nsol = 3 if mesh.solutionD[2] else 2
+    for q in range(nsol):
+        assert st_g["finalResidual"][q] < 1e-12 and st_o["finalResidual"][q] < 1e-12
+        assert st_g["nIterations"][q] < st_j["nIterations"][q]
+        assert st_g["nIterations"][q] <= st_o["nIterations"][q]
+    assert rel_l2(psi_g[:, :nsol], psi_o[:, :nsol]) < 1e-9
+    info = g.gamg_info()
+    assert info["levels"][0] == mesh.nCells and info["levels"][-1] <= 512
+    print("GAMG levels", info["levels"], "iterations gamg/dic/jacobi", st_g["nIterations"], st_o["nIterations"], st_j["nIterations"])
+
+
+def test_gamg_evolve_matches_oracle_dic():
+    """Whole momentum loop with the GPU's GAMG-PCG against the oracle's DIC-PCG, both converged tightly:
+    the outer solution does not depend on the inner preconditioner."""
+    kw = dict(nx=8, ny=6, nz=6, L=1.0, fieldRelaxD=0.9, nCorrectors=4000, **TIGHT)
+    g, o, mesh = _pair(cases.cantilever, preconditioner=K.PRECOND_GAMG, **kw)
+    sg, so = g.evolve(), o.evolve()
+    assert sg["converged"] and so["converged"], (sg, so)
+    assert rel_l2(g.get("D"), o.get("D")) < SOLVE_TOL
+    assert rel_l2(g.get("sigma"), o.get("sigma")) < SOLVE_TOL
+    assert sg["totalInnerIterations"] < so["totalInnerIterations"]
+
+
+def test_chebyshev_pcg_solves_the_assembled_system():
+    kw = dict(nx=20, ny=6, nz=6, tolerance=1e-12, relTol=0.0, maxIter=2000)
+    g, o, mesh = _pair(cases.cantilever, preconditioner=K.PRECOND_CHEBYSHEV, **kw)
+    for s in (g, o):
+        s.op_assemble()
+    src = np.random.default_rng(11).standard_normal((mesh.nCells, 3))
+    psi_g, st_g = g.op_solve(np.zeros((mesh.nCells, 3)), src)
+    psi_o, st_o = o.op_solve(np.zeros((mesh.nCells, 3)), src)
+    assert rel_l2(psi_g, psi_o) < 1e-8
+    assert max(st_g["nIterations"]) < max(st_o["nIterations"])     # oracle falls back to the diagonal preconditioner
