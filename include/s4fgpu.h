@@ -258,8 +258,7 @@ enum {
     S4F_KERNEL_RHS = 5,
     S4F_KERNEL_PCG_P = 6,      /* pA = rD rA + beta pA */
     S4F_KERNEL_PCG_XR = 7,     /* psi += alpha pA; rA -= alpha wA; residual sums */
-    S4F_KERNEL_SPMV3_ROWS = 8, /* 3-component Amul, earlier row-per-thread mapping (kept for comparison) */
-    S4F_KERNEL_GAMG_VCYCLE = 9 /* one application of the GAMG preconditioner (all levels) */
+    S4F_KERNEL_GAMG_VCYCLE = 8 /* one application of the GAMG preconditioner (all levels) */
 };
 int s4fgpu_time_kernel(s4fgpu_handle h, int kernel, int reps, int flushL2,
                        double* msPerLaunch, double* algoBytesPerLaunch);

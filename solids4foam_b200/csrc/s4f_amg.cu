@@ -176,39 +176,46 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_amg_first(const T* __restrict__ r
 
 // one Chebyshev-Jacobi step:  r = b - A x;  d' = c1 d + c2 rD r;  x' = x + d'   (out of place in x)
 // MODE 0: as written; MODE 1: residual only (xo = r, nothing else written).
-// Mapping as in the PCG SpMV (k_amul3c): three consecutive warps share a slice, one component each.
-#define S4F_AMG_BLOCK 192
+// Row per thread, entries in groups of eight with all index/coefficient loads issued before the gathers
+// (the mapping of the PCG SpMV k_amul3, see there).
+#define S4F_AMG_BLOCK 256
 template <class T, class TB, class TO, int MODE>
-__global__ void __launch_bounds__(S4F_AMG_BLOCK) k_amg_step(const int* __restrict__ slicePtr, const int* __restrict__ col,
-                                                            const T* __restrict__ a, const T* __restrict__ dg, const T* __restrict__ rD,
-                                                            const TB* __restrict__ b, const T* __restrict__ x, T* __restrict__ d,
-                                                            TO* __restrict__ xo, int n, int ld, int ldb, int ldo, int nSlices, T c1, T c2) {
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int q = wib % 3, sub = wib / 3;
-    constexpr int SPB = S4F_AMG_BLOCK / 96;
-    const T* __restrict__ xq = x + (size_t)q * ld;
-    for (int s = blockIdx.x * SPB + sub; s < nSlices; s += gridDim.x * SPB) {
+__global__ void __launch_bounds__(S4F_AMG_BLOCK, 4) k_amg_step(const int* __restrict__ slicePtr, const int* __restrict__ col,
+                                                               const T* __restrict__ a, const T* __restrict__ dg, const T* __restrict__ rD,
+                                                               const TB* __restrict__ b, const T* __restrict__ x, T* __restrict__ d,
+                                                               TO* __restrict__ xo, int n, int ld, int ldb, int ldo, int nSlices, T c1, T c2) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (int s = warp; s < nSlices; s += nWarps) {
         const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
         const int row = s * 32 + lane;
-        T s0 = 0, s1 = 0;
-        const int* cp = col + base + lane;
-        const T* ap = a + base + lane;
-        int k = 0;
-        for (; k + 1 < width; k += 2) {
-            const int c0 = cp[32 * k], c1i = cp[32 * k + 32];
-            const T e0 = ap[32 * k], e1 = ap[32 * k + 32];
-            s0 += e0 * xq[c0]; s1 += e1 * xq[c1i];
+        T s0 = 0, s1 = 0, s2 = 0;
+        for (int k0 = 0; k0 < width; k0 += 8) {
+            int cc[8]; T e[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const bool ok = k0 + k < width;
+                const int idx = base + 32 * (ok ? k0 + k : k0) + lane;
+                cc[k] = col[idx];
+                e[k] = ok ? a[idx] : (T)0;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) { s0 += e[k] * x[cc[k]]; s1 += e[k] * x[cc[k] + ld]; s2 += e[k] * x[cc[k] + 2 * ld]; }
         }
-        if (k < width) s0 += ap[32 * k] * xq[cp[32 * k]];
         if (row < n) {
-            const size_t j = (size_t)q * ld + row;
-            const T xv = xq[row];
-            const T r = (T)b[(size_t)q * ldb + row] - (dg[j] * xv - (s0 + s1));
-            if (MODE == 1) { xo[(size_t)q * ldo + row] = (TO)r; }
-            else {
-                const T dn = (c1 != (T)0 ? c1 * d[j] : (T)0) + c2 * rD[j] * r;
-                d[j] = dn;
-                xo[(size_t)q * ldo + row] = (TO)(xv + dn);
+            const T acc[3] = {s0, s1, s2};
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const int j = q * ld + row;
+                const T xv = x[j];
+                const T r = (T)b[(size_t)q * ldb + row] - (dg[j] * xv - acc[q]);
+                if (MODE == 1) { xo[(size_t)q * ldo + row] = (TO)r; }
+                else {
+                    const T dn = (c1 != (T)0 ? c1 * d[j] : (T)0) + c2 * rD[j] * r;
+                    d[j] = dn;
+                    xo[(size_t)q * ldo + row] = (TO)(xv + dn);
+                }
             }
         }
     }
@@ -365,11 +372,7 @@ struct Hierarchy : S4fAmg {
         return 0;
     }
 
-    static int step_grid(const s4fgpu_ctx* c, const Level<T>& L) {
-        long long need = ((long long)L.nSlices + 1) / 2, g = (long long)c->numSMs * 10;
-        if (need < g) g = need;
-        return (int)(g < 1 ? 1 : g);
-    }
+    static int step_grid(const s4fgpu_ctx* c, const Level<T>& L) { return s4f_grid(c->numSMs, (long long)L.nSlices * 32, 4); }
     // algorithmic bytes of one application (for the roofline report): every array read / written once
     double bytes_per_apply(int fineLdUnused) const {
         (void)fineLdUnused;

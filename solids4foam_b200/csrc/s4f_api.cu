@@ -112,7 +112,7 @@ int s4fgpu_create(s4fgpu_handle* out, int device) {
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_createError = cudaGetErrorString(e); delete c; return 2; }
     c->numSMs = prop.multiProcessorCount;
-    if (const char* v = getenv("S4F_AMUL_VARIANT")) c->amulVariant = atoi(v);
+    if (const char* v = getenv("S4F_SRC_VARIANT")) c->srcVariant = atoi(v);
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { g_createError = cudaGetErrorString(e); delete c; return 2; }
     *out = c;
     return 0;
@@ -409,7 +409,7 @@ int s4fgpu_time_kernel(s4fgpu_handle c, int kernel, int reps, int flushL2, doubl
     S4F_REQUIRE(c, c->geomSet && c->matrixValid, "time_kernel: initialise first");
     S4F_REQUIRE(c, reps > 0, "time_kernel: reps");
     if (kernel == S4F_KERNEL_SPMV1 || kernel == S4F_KERNEL_SPMV3 || kernel == S4F_KERNEL_PCG_ITER || kernel == S4F_KERNEL_PCG_P ||
-        kernel == S4F_KERNEL_PCG_XR || kernel == S4F_KERNEL_SPMV3_ROWS)
+        kernel == S4F_KERNEL_PCG_XR)
         return s4f_time_pcg_kernels(c, kernel, reps, flushL2, msPerLaunch, algoBytesPerLaunch);
     return s4f_time_fv_kernels(c, kernel, reps, flushL2, msPerLaunch, algoBytesPerLaunch);
 }

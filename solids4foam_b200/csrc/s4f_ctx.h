@@ -169,7 +169,7 @@ struct s4fgpu_ctx {
     DevBuf<double> diag0;             // ld: sum of laplacian coefficients + d2dt2
     DevBuf<double> diagC;             // 3*ld: per-component diagonal after addBoundaryDiag
     DevBuf<double> rDiagC;            // 3*ld: 1/diagC ([OF-ext] diagonalPreconditioner rD)
-    int amulVariant = 0;              // 0: component-per-warp SpMV, 1: row-per-thread (S4F_AMUL_VARIANT)
+    int srcVariant = 0;               // 0: component-per-warp RHS kernel, 1: row-per-thread (S4F_SRC_VARIANT)
     DevBuf<double> source;            // 3*ld
     bool matrixValid = false;
     // ---- PCG work vectors ----

@@ -311,6 +311,70 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_source(
     }
 }
 
+// The same right-hand side with the component-per-warp mapping of the SpMV (s4f_pcg.cu, k_amul3c): three
+// consecutive warps share a slice and produce one displacement component each, so a thread gathers only
+// the column of T and of grad(D) its component needs (7 neighbour values per entry instead of 18+) and
+// keeps few registers; the per-entry geometry (col, a, w, Sf, rc, gamma) is fetched from HBM once and
+// reaches the other two warps through L1.  Arithmetic and summation order per component are those of
+// k_source above.
+#define S4F_SRC_BLOCK 192
+template <bool TENSOR9, bool STAB, bool NONORTH>
+__global__ void __launch_bounds__(S4F_SRC_BLOCK) k_source_c(
+    const int* __restrict__ slicePtr, const int* __restrict__ col, const double* __restrict__ eA, const double* __restrict__ eW,
+    const double* __restrict__ eSf, const double* __restrict__ eRc, const double* __restrict__ eGam, const double* __restrict__ eCorr,
+    const double* __restrict__ D, const double* __restrict__ T, const double* __restrict__ gradD, const double* __restrict__ V,
+    const double* __restrict__ Dold, const double* __restrict__ DoldOld, double* __restrict__ source, int N, int ld, long long nE,
+    int nSlices, double rhoGx, double rhoGy, double rhoGz, double cOld, double cOldOld) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int q = wib % 3, sub = wib / 3;
+    constexpr int SPB = S4F_SRC_BLOCK / 96;
+    int t0, t1, t2;
+    if (TENSOR9) { t0 = q; t1 = 3 + q; t2 = 6 + q; }
+    else { t0 = q; t1 = (q == 0) ? 1 : (q == 1 ? 3 : 4); t2 = (q == 0) ? 2 : (q == 1 ? 4 : 5); }   // column q of a symmTensor
+    const double* __restrict__ Dq = D + (size_t)q * ld;
+    const double* __restrict__ T0 = T + (size_t)t0 * ld;
+    const double* __restrict__ T1 = T + (size_t)t1 * ld;
+    const double* __restrict__ T2 = T + (size_t)t2 * ld;
+    const double* __restrict__ G0 = gradD + (size_t)q * ld;
+    const double* __restrict__ G1 = gradD + (size_t)(3 + q) * ld;
+    const double* __restrict__ G2 = gradD + (size_t)(6 + q) * ld;
+    const double rg = (q == 0) ? rhoGx : (q == 1 ? rhoGy : rhoGz);
+    for (int s = blockIdx.x * SPB + sub; s < nSlices; s += gridDim.x * SPB) {
+        const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
+        const int row = s * 32 + lane;
+        const int r = (row < N) ? row : 0;
+        const double DP = Dq[r], TP0 = T0[r], TP1 = T1[r], TP2 = T2[r];
+        double gP0 = 0, gP1 = 0, gP2 = 0;
+        if (STAB) { gP0 = G0[r]; gP1 = G1[r]; gP2 = G2[r]; }
+        double acc = 0;
+#pragma unroll 2
+        for (int k = 0; k < width; k++) {
+            const long long e = (long long)base + 32 * k + lane;
+            const int cc = col[e];
+            const double a = eA[e], w = eW[e], w1 = 1.0 - w;
+            const double S0 = eSf[e], S1 = eSf[nE + e], S2 = eSf[2 * nE + e];
+            const double dD = Dq[cc] - DP;
+            const double Tf0 = w * TP0 + w1 * T0[cc], Tf1 = w * TP1 + w1 * T1[cc], Tf2 = w * TP2 + w1 * T2[cc];
+            const double fl = S0 * Tf0 + S1 * Tf1 + S2 * Tf2;
+            double st = 0;
+            if (STAB) {
+                const double rc = eRc[e], gam = eGam[e];
+                double m0 = -S0, m1 = -S1, m2 = -S2;
+                if (NONORTH) { m0 += eCorr[e]; m1 += eCorr[nE + e]; m2 += eCorr[2 * nE + e]; }
+                const double gf0 = w * gP0 + w1 * G0[cc], gf1 = w * gP1 + w1 * G1[cc], gf2 = w * gP2 + w1 * G2[cc];
+                st = rc * dD + gam * (m0 * gf0 + m1 * gf1 + m2 * gf2);
+            }
+            acc += fl - a * dD + st;
+        }
+        if (row < N) {
+            const double v = V[row];
+            double sv = acc + v * rg;
+            if (cOld != 0.0) sv += v * (cOld * Dold[(size_t)q * ld + row] - cOldOld * DoldOld[(size_t)q * ld + row]);
+            source[(size_t)q * ld + row] = sv;
+        }
+    }
+}
+
 // boundary part of the laplacian pair: - impKf_b magSf_b snGrad_b (explicit) + boundaryCoeffs
 // (addBoundarySource), boundaryCoeffs = impKf_b magSf_b gradientBoundaryCoeffs_b with
 //   fixedGradient: gradient();  fixedDisplacement: deltaCoeffs (D_b - k & gradD_P)  (fixedDisplacement...C:328-356)
@@ -354,37 +418,45 @@ __global__ void k_source_boundary(const int* __restrict__ bcCells, const int* __
 // Gauss linear: grad_P = (1/V) sum_e Sf_e (w D_P + (1-w) D_e).     mechanicalModel::grad, mechanicalModel.C:571-582
 // ------------------------------------------------------------------------------------------------
 template <bool GAUSS>
-__global__ void __launch_bounds__(S4F_BLOCK) k_grad(const int* __restrict__ slicePtr, const int* __restrict__ col,
-                                                    const double* __restrict__ eVec /* eLs or eSf */, const double* __restrict__ eW,
-                                                    const double* __restrict__ D, const double* __restrict__ rV,
-                                                    double* __restrict__ gradD, int N, int ld, long long nE, int nSlices) {
+__global__ void __launch_bounds__(S4F_BLOCK, GAUSS ? 2 : 3) k_grad(const int* __restrict__ slicePtr, const int* __restrict__ col,
+                                                       const double* __restrict__ eVec /* eLs or eSf */, const double* __restrict__ eW,
+                                                       const double* __restrict__ D, const double* __restrict__ rV,
+                                                       double* __restrict__ gradD, int N, int ld, long long nE, int nSlices) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    constexpr int G = 4;    // entries whose index / vector loads are issued together, before the gathers
     for (int s = warp; s < nSlices; s += nWarps) {
         const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
         const int row = s * 32 + lane;
         const int r = (row < N) ? row : 0;
         const double DP[3] = {D[r], D[(size_t)ld + r], D[2 * (size_t)ld + r]};
         double g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll 2
-        for (int k = 0; k < width; k++) {
-            const long long e = (long long)base + 32 * k + lane;
-            const int cc = col[e];
-            const double v[3] = {eVec[e], eVec[nE + e], eVec[2 * nE + e]};
-            double d[3];
-            if (GAUSS) {
-                const double w = eW[e];
+        for (int k0 = 0; k0 < width; k0 += G) {
+            int cc[G]; double v[G][3]; double wv[G];
 #pragma unroll
-                for (int c = 0; c < 3; c++) d[c] = w * DP[c] + (1.0 - w) * D[(size_t)c * ld + cc];
-            } else {
-#pragma unroll
-                for (int c = 0; c < 3; c++) d[c] = D[(size_t)c * ld + cc] - DP[c];
+            for (int k = 0; k < G; k++) {
+                const bool ok = k0 + k < width;
+                const long long e = (long long)base + 32 * (ok ? k0 + k : k0) + lane;
+                cc[k] = col[e];
+                v[k][0] = ok ? eVec[e] : 0.0; v[k][1] = ok ? eVec[nE + e] : 0.0; v[k][2] = ok ? eVec[2 * nE + e] : 0.0;
+                if (GAUSS) wv[k] = eW[e];
             }
 #pragma unroll
-            for (int i = 0; i < 3; i++)
+            for (int k = 0; k < G; k++) {
+                double d[3];
+                if (GAUSS) {
 #pragma unroll
-                for (int j = 0; j < 3; j++) g[3 * i + j] += v[i] * d[j];
+                    for (int c = 0; c < 3; c++) d[c] = wv[k] * DP[c] + (1.0 - wv[k]) * D[(size_t)c * ld + cc[k]];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) d[c] = D[(size_t)c * ld + cc[k]] - DP[c];
+                }
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = 0; j < 3; j++) g[3 * i + j] += v[k][i] * d[j];
+            }
         }
         if (row < N) {
             const double sc = GAUSS ? rV[row] : 1.0;
@@ -559,9 +631,25 @@ int s4f_bc_evaluate(s4fgpu_ctx* c) {
 
 template <bool T9>
 static void launch_source(s4fgpu_ctx* c, const double* T, double cOld, double cOldOld) {
-    const int gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
     const bool stab = c->ctl.stabilisation == S4F_STAB_RHIE_CHOW;
     const double rg[3] = {c->law.rho * c->ctl.g[0], c->law.rho * c->ctl.g[1], c->law.rho * c->ctl.g[2]};
+    if (c->srcVariant == 0) {
+        long long need = ((long long)c->nSlices + 1) / 2, g = (long long)c->numSMs * 10;
+        if (need < g) g = need;
+        const int grid = (int)(g < 1 ? 1 : g);
+#define S4F_LAUNCH_SRC(STAB, NO)                                                                                                     \
+    k_source_c<T9, STAB, NO><<<grid, S4F_SRC_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->eW.p, c->eSf.p, c->eRc.p,    \
+                                                                    c->eGam.p, c->eCorr.p, c->D.p, T, c->gradD.p, c->V.p, c->Dold.p,  \
+                                                                    c->DoldOld.p, c->source.p, c->N, c->ld, c->nEntries, c->nSlices,  \
+                                                                    rg[0], rg[1], rg[2], cOld, cOldOld)
+        if (stab && c->nonOrth) S4F_LAUNCH_SRC(true, true);
+        else if (stab) S4F_LAUNCH_SRC(true, false);
+        else S4F_LAUNCH_SRC(false, false);
+#undef S4F_LAUNCH_SRC
+        c->launches++;
+        return;
+    }
+    const int gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
 #define S4F_LAUNCH_SRC(STAB, NO)                                                                                                   \
     k_source<T9, STAB, NO><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->eW.p, c->eSf.p, c->eRc.p, c->eGam.p, \
                                                                c->eCorr.p, c->D.p, T, c->gradD.p, c->V.p, c->Dold.p, c->DoldOld.p,     \
@@ -590,7 +678,7 @@ int s4f_assemble_source(s4fgpu_ctx* c) {
 }
 
 int s4f_grad(s4fgpu_ctx* c) {
-    const int gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
+    const int gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32, 3);
     if (c->B > 0) {
         k_bc_sngrad_store<<<(c->B + 127) / 128, 128, 0, c->stream>>>(c->bFaceCell.p, c->bKind.p, c->bN.p, c->bK.p, c->bDelta.p, c->tracGrad.p, c->D.p,
                                                                     c->gradD.p, c->bSn.p, c->B, c->bOff(), c->ld);

@@ -217,13 +217,18 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_pcg_p_generic(const double* __res
     }
 }
 
-// wA = A pA, sums wA.pA   -- THE SpMV: SELL-32 gather, matrix entries read once for three vectors
+// wA = A pA, sums wA.pA   -- THE SpMV: SELL-32 gather, one row per thread, matrix entries read once for
+// the three vectors.  The entries of a row are taken in groups of eight: all column indices and
+// coefficients of a group are loaded before the first dependent gather is issued (16 independent
+// loads, then 24 independent gathers per thread), which is what hides the HBM/L2 latency at the
+// occupancy 64 registers allow (measured: profiles/microbench/spmv_variants.cu, 0.78 of the copy peak
+// against 0.61 for a 2-way unrolled loop).
 template <bool DOT>
-__global__ void __launch_bounds__(S4F_BLOCK) k_amul3(const int* __restrict__ slicePtr, const int* __restrict__ col,
-                                                     const double* __restrict__ eA, const double* __restrict__ diagC,
-                                                     const double* __restrict__ p, double* __restrict__ w, int N, int ld,
-                                                     int nSlices, PcgScalars* S, PcgParams P, double nGlob, double* partials,
-                                                     unsigned int* ticket, int cmptMask) {
+__global__ void __launch_bounds__(S4F_BLOCK, 4) k_amul3(const int* __restrict__ slicePtr, const int* __restrict__ col,
+                                                        const double* __restrict__ eA, const double* __restrict__ diagC,
+                                                        const double* __restrict__ p, double* __restrict__ w, int N, int ld,
+                                                        int nSlices, PcgScalars* S, PcgParams P, double nGlob, double* partials,
+                                                        unsigned int* ticket, int cmptMask) {
     int act[3];
     if (DOT) {
         if (!S->anyActive) return;
@@ -236,93 +241,35 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_amul3(const int* __restrict__ sli
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nWarps = (gridDim.x * blockDim.x) >> 5;
-    const double* __restrict__ p0 = p;
-    const double* __restrict__ p1 = p + (size_t)ld;
-    const double* __restrict__ p2 = p + 2 * (size_t)ld;
     double v[3] = {0, 0, 0};
     for (int s = warp; s < nSlices; s += nWarps) {
         const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
         const int row = s * 32 + lane;
         double a0 = 0, a1 = 0, a2 = 0;
-        const int* cp = col + base + lane;
-        const double* ap = eA + base + lane;
-        if (act[0] && act[1] && act[2]) {
-#pragma unroll 2
-            for (int k = 0; k < width; k++) {
-                const int cc = cp[32 * k];
-                const double a = ap[32 * k];
-                a0 += a * p0[cc]; a1 += a * p1[cc]; a2 += a * p2[cc];
+        for (int k0 = 0; k0 < width; k0 += 8) {
+            int cc[8]; double e[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const bool ok = k0 + k < width;
+                const int idx = base + 32 * (ok ? k0 + k : k0) + lane;
+                cc[k] = col[idx];
+                e[k] = ok ? eA[idx] : 0.0;
             }
-        } else {
-            for (int k = 0; k < width; k++) {
-                const int cc = cp[32 * k];
-                const double a = ap[32 * k];
-                if (act[0]) a0 += a * p0[cc];
-                if (act[1]) a1 += a * p1[cc];
-                if (act[2]) a2 += a * p2[cc];
-            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) { a0 += e[k] * p[cc[k]]; a1 += e[k] * p[cc[k] + ld]; a2 += e[k] * p[cc[k] + 2 * ld]; }
         }
         if (row < N) {
             const double acc[3] = {a0, a1, a2};
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 if (!act[c]) continue;
-                const size_t j = (size_t)c * ld + row;
+                const int j = c * ld + row;
                 const double pp = p[j];
                 const double ww = diagC[j] * pp - acc[c];
                 w[j] = ww;
                 if (DOT) v[c] += ww * pp;
             }
         }
-    }
-    if (DOT) grid_reduce<3, OpSum>(v, partials, ticket, Fin{PH_AMUL, S, P, nGlob, 3});
-}
-
-// wA = A pA, sums wA.pA -- component-per-warp mapping: three consecutive warps of a block take the SAME
-// slice, one displacement component each.  Per thread this is the scalar SpMV (few registers, full
-// occupancy, two independent loads per entry in flight); the matrix entries of a slice are fetched
-// from HBM once and reach the other two warps through L1/L2, so the HBM traffic is that of the fused
-// 3-component product.  Components whose solve has finished are skipped (no traffic for them).
-#define S4F_AMUL_BLOCK 192
-template <bool DOT>
-__global__ void __launch_bounds__(S4F_AMUL_BLOCK) k_amul3c(const int* __restrict__ slicePtr, const int* __restrict__ col,
-                                                           const double* __restrict__ eA, const double* __restrict__ diagC,
-                                                           const double* __restrict__ p, double* __restrict__ w, int N, int ld,
-                                                           int nSlices, PcgScalars* S, PcgParams P, double nGlob, double* partials,
-                                                           unsigned int* ticket, int cmptMask) {
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int q = wib % 3, sub = wib / 3;
-    int active;
-    if (DOT) { if (!S->anyActive) return; active = S->active[q]; }
-    else active = (cmptMask >> q) & 1;
-    double v[3] = {0, 0, 0};
-    if (active) {
-        const double* __restrict__ pq = p + (size_t)q * ld;
-        const double* __restrict__ dq = diagC + (size_t)q * ld;
-        double* __restrict__ wq = w + (size_t)q * ld;
-        double acc = 0;
-        constexpr int SPB = S4F_AMUL_BLOCK / 96;      // slices per block step
-        for (int s = blockIdx.x * SPB + sub; s < nSlices; s += gridDim.x * SPB) {
-            const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
-            const int row = s * 32 + lane;
-            double a0 = 0, a1 = 0;
-            const int* cp = col + base + lane;
-            const double* ap = eA + base + lane;
-            int k = 0;
-            for (; k + 1 < width; k += 2) {
-                const int c0 = cp[32 * k], c1 = cp[32 * k + 32];
-                const double e0 = ap[32 * k], e1 = ap[32 * k + 32];
-                a0 += e0 * pq[c0]; a1 += e1 * pq[c1];
-            }
-            if (k < width) a0 += ap[32 * k] * pq[cp[32 * k]];
-            if (row < N) {
-                const double pp = pq[row];
-                const double ww = dq[row] * pp - (a0 + a1);
-                wq[row] = ww;
-                if (DOT) acc += ww * pp;
-            }
-        }
-        v[q] = acc;
     }
     if (DOT) grid_reduce<3, OpSum>(v, partials, ticket, Fin{PH_AMUL, S, P, nGlob, 3});
 }
@@ -508,21 +455,7 @@ static int allreduce_part(s4fgpu_ctx* c, int n, int phase, const PcgParams& P, d
 }
 
 static int amul3(s4fgpu_ctx* c, const double* p, double* w, bool dot, const PcgParams& P, double nGlob, int mask) {
-    if (c->amulVariant == 0) {      // component-per-warp mapping (default)
-        long long need = ((long long)c->nSlices + 1) / 2;
-        long long g = (long long)c->numSMs * 10;          // 10 x 192 threads = 1920 resident threads per SM
-        if (need < g) g = need;
-        if (g < 1) g = 1;
-        if (dot)
-            k_amul3c<true><<<(int)g, S4F_AMUL_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, p, w, c->N, c->ld, c->nSlices,
-                                                                     c->pcgS.p, P, nGlob, c->partials.p, c->ticket.p, mask);
-        else
-            k_amul3c<false><<<(int)g, S4F_AMUL_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, p, w, c->N, c->ld, c->nSlices,
-                                                                      c->pcgS.p, P, nGlob, c->partials.p, c->ticket.p, mask);
-        c->launches++;
-        return 0;
-    }
-    const int grid = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
+    const int grid = s4f_grid(c->numSMs, (long long)c->nSlices * 32, 4);
     if (dot)
         k_amul3<true><<<grid, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, p, w, c->N, c->ld, c->nSlices,
                                                           c->pcgS.p, P, nGlob, c->partials.p, c->ticket.p, mask);
@@ -678,8 +611,6 @@ int s4f_time_pcg_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, doubl
     if (flushL2 && c->flushBuf.n == 0) S4F_CHECK_CUDA(c, c->flushBuf.alloc((size_t)48 * 1024 * 1024));   // 384 MB > 126 MB L2
     cudaEvent_t e0, e1;
     S4F_CHECK_CUDA(c, cudaEventCreate(&e0)); S4F_CHECK_CUDA(c, cudaEventCreate(&e1));
-    const int savedVariant = c->amulVariant;
-    if (kernel == S4F_KERNEL_SPMV3_ROWS) c->amulVariant = 1;
     double total = 0;
     for (int r = -3; r < reps; r++) {
         S4F_CHECK_CUDA(c, cudaMemcpyAsync(c->pcgS.p, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
@@ -688,7 +619,7 @@ int s4f_time_pcg_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, doubl
         if (kernel == S4F_KERNEL_SPMV1) {
             k_amul1<<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, c->pA.p, c->wA.p, N, c->nSlices);
             c->launches++;
-        } else if (kernel == S4F_KERNEL_SPMV3 || kernel == S4F_KERNEL_SPMV3_ROWS) {
+        } else if (kernel == S4F_KERNEL_SPMV3) {
             amul3(c, c->pA.p, c->wA.p, true, Pn, 1.0, 7);
         } else if (kernel == S4F_KERNEL_PCG_P) {
             k_pcg_p<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rDiagC.p, c->rA.p, c->pA.p, N, ld, c->pcgS.p);
@@ -708,7 +639,6 @@ int s4f_time_pcg_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, doubl
         float ms; S4F_CHECK_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
         if (r >= 0) total += ms;
     }
-    c->amulVariant = savedVariant;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     S4F_CHECK_CUDA(c, cudaGetLastError());
     *msOut = total / reps;
@@ -717,7 +647,7 @@ int s4f_time_pcg_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, doubl
     const double pk = (24 + 24 + 24 + 24.0) * N;                             // r, rD, p in | p out
     const double xr = (24 * 5 + 24 * 2.0) * N;                               // x, r, p, w, rD in | x, r out
     if (kernel == S4F_KERNEL_SPMV1) *bytesOut = 12.0 * nnz + (8 + 8 + 8 + 0.125) * N;
-    else if (kernel == S4F_KERNEL_SPMV3 || kernel == S4F_KERNEL_SPMV3_ROWS) *bytesOut = spmv3;
+    else if (kernel == S4F_KERNEL_SPMV3) *bytesOut = spmv3;
     else if (kernel == S4F_KERNEL_PCG_P) *bytesOut = pk;
     else if (kernel == S4F_KERNEL_PCG_XR) *bytesOut = xr;
     else *bytesOut = spmv3 + pk + xr;
