@@ -24,7 +24,10 @@ def main():
     g = SolidModel(cases.cantilever(*dims, preconditioner=pre, maxIter=20 if outer else 1000))
     for _ in range(outer):
         g.outer_iteration()
-    for name in ("spmv3", "spmv1", "pcg_iter", "grad", "rhs", "law"):
+    names = ["spmv3", "spmv1", "pcg_p", "pcg_xr", "pcg_iter", "grad", "rhs", "law"]
+    if pre == K.PRECOND_GAMG:
+        names.append("gamg_vcycle")
+    for name in names:
         ms, by = g.time_kernel(name, reps=2, flush_l2=False)
         print(f"{name:9s} {ms:8.4f} ms  {by / ms / 1e6:8.1f} GB/s (under a profiler: not a bench value)")
 
