@@ -112,7 +112,6 @@ int s4fgpu_create(s4fgpu_handle* out, int device) {
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_createError = cudaGetErrorString(e); delete c; return 2; }
     c->numSMs = prop.multiProcessorCount;
-    if (const char* v = getenv("S4F_SRC_VARIANT")) c->srcVariant = atoi(v);
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { g_createError = cudaGetErrorString(e); delete c; return 2; }
     *out = c;
     return 0;

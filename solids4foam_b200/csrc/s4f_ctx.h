@@ -136,8 +136,9 @@ struct s4fgpu_ctx {
     DevBuf<double> eDn;               // magSf*nonOrthDeltaCoeffs (0 on boundary-face entries)
     DevBuf<double> eCorr;             // [3*nEntries] magSf*nonOrthCorrectionVector, outward sense (only if nonOrth)
     DevBuf<double> eA;                // laplacian coefficient impKf*magSf*delta  (= -upper)
-    DevBuf<double> eRc;               // RhieChow compact coefficient gamma_f*magSf*delta
     DevBuf<double> eGam;              // RhieChow gamma_f
+    DevBuf<double> eU, eC0, eVc;      // factored RHS coefficients (k_source_f): (1-w) Sf [3*nE], gamma magSf delta - a, gamma (1-w) corr [3*nE]
+    DevBuf<double> rowK;              // [6*ld] per-row sums U (3), Vv (3) of the factored RHS
     DevBuf<double> V, rV;             // cell volumes [ld]
     DevBuf<int> faceEntry;            // [F] entry index of internal face f in its owner's row (-> lduMatrix upper())
 
@@ -169,7 +170,6 @@ struct s4fgpu_ctx {
     DevBuf<double> diag0;             // ld: sum of laplacian coefficients + d2dt2
     DevBuf<double> diagC;             // 3*ld: per-component diagonal after addBoundaryDiag
     DevBuf<double> rDiagC;            // 3*ld: 1/diagC ([OF-ext] diagonalPreconditioner rD)
-    int srcVariant = 0;               // 0: component-per-warp RHS kernel, 1: row-per-thread (S4F_SRC_VARIANT)
     DevBuf<double> source;            // 3*ld
     bool matrixValid = false;
     // ---- PCG work vectors ----

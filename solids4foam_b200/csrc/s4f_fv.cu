@@ -22,9 +22,10 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(S4F_BLOCK) k_assemble_laplacian(
     const int* __restrict__ slicePtr, const int* __restrict__ col, const double* __restrict__ eW, const double* __restrict__ eDn,
-    const double* __restrict__ impK, const double* __restrict__ V, double* __restrict__ eA, double* __restrict__ eRc,
-    double* __restrict__ eGam, double* __restrict__ diag0, int N, int bOff, int nSlices, double stabScale, int stabOn,
-    double d2dt2Coeff) {
+    const double* __restrict__ eSf, const double* __restrict__ eCorr /* may be null */, const double* __restrict__ impK,
+    const double* __restrict__ V, double* __restrict__ eA, double* __restrict__ eGam, double* __restrict__ eU, double* __restrict__ eC0,
+    double* __restrict__ eVc /* null when orthogonal */, double* __restrict__ rowK, double* __restrict__ diag0, int N, int bOff, int ld,
+    long long nE, int nSlices, double stabScale, int stabOn, double d2dt2Coeff) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nWarps = (gridDim.x * blockDim.x) >> 5;
@@ -32,25 +33,46 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_assemble_laplacian(
         const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
         const int row = s * 32 + lane;
         const double kP = (row < N) ? impK[row] : 0.0;
-        double sum = 0;
+        double sum = 0, sU[3] = {0, 0, 0}, sV[3] = {0, 0, 0};
         for (int k = 0; k < width; k++) {
-            const int e = base + 32 * k + lane;
+            const long long e = (long long)base + 32 * k + lane;
             const int cc = col[e];
-            const double w = eW[e], dn = eDn[e];
+            const double w = eW[e], dn = eDn[e], w1 = 1.0 - w;
             const double kN = impK[cc];
-            const double kf = w * kP + (1.0 - w) * kN;
+            const double kf = w * kP + w1 * kN;
             const double a = kf * dn;
             eA[e] = a;
             sum += a;
             double gf = 0.0;
             if (stabOn && cc < bOff) {   // zero on non-coupled boundary faces
-                gf = w * (stabScale * kP) + (1.0 - w) * (stabScale * kN);
+                gf = w * (stabScale * kP) + w1 * (stabScale * kN);
                 if (fabs(kP - kN) > S4F_SMALL) gf = 0.01 * 0.5 * (kP + kN);   // material interface
             }
             eGam[e] = gf;
-            eRc[e] = gf * dn;
+            // factored right-hand-side coefficients (see k_source_f): the neighbour value of T enters with
+            // u = (1-w) Sf, of D with c0 = gamma_f magSf delta - a, of grad(D) with -gamma (1-w) Sf (+ vc);
+            // the row's own values with the sums U, Vv, C0 over its entries.
+            const double c0 = gf * dn - a;
+            eC0[e] = c0;
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const double Sq = eSf[(size_t)q * nE + e];
+                eU[(size_t)q * nE + e] = w1 * Sq;
+                sU[q] += w * Sq;
+                double m = -Sq;
+                if (eCorr) {
+                    const double cq = eCorr[(size_t)q * nE + e];
+                    m += cq;
+                    eVc[(size_t)q * nE + e] = gf * w1 * cq;
+                }
+                sV[q] += gf * w * m;
+            }
         }
-        if (row < N) diag0[row] = sum + d2dt2Coeff * V[row];
+        if (row < N) {
+            diag0[row] = sum + d2dt2Coeff * V[row];
+#pragma unroll
+            for (int q = 0; q < 3; q++) { rowK[(size_t)q * ld + row] = sU[q]; rowK[(size_t)(3 + q) * ld + row] = sV[q]; }
+        }
     }
 }
 
@@ -238,93 +260,26 @@ __global__ void k_bc_evaluate(const int* __restrict__ bFaceCell, const int* __re
 //   + V rho g + d2dt2 old-time terms
 //   + V RhieChow = sum_f gamma_f [ magSf (delta (D_N-D_P) + corr & gradD_f) - Sf & gradD_f ]   (momentumStabilisation.C:210-217)
 // T is sigma (6 comps, TENSOR9=false) or J Finv & sigma (9 comps, total-Lagrangian, TENSOR9=true).
+//
+// Factored form.  With m = corr - Sf and the face values w X_P + (1-w) X_N the sum over the faces of a cell
+// separates into a part that only needs the NEIGHBOUR values and per-entry coefficients fixed at assembly,
+//      sum_e [ u_e & T_N(:,q) + c0_e (D_N,q - D_P,q) - gamma_e (u_e & gradD_N(:,q)) + vc_e & gradD_N(:,q) ],
+//      u = (1-w) Sf,  c0 = gamma magSf delta - a,  vc = gamma (1-w) corr  (non-orthogonal meshes only),
+// and a part in the cell's OWN values with per-row sums U = sum w Sf, Vv = sum gamma w m:
+//      U & T_P(:,q) + Vv & gradD_P(:,q).
+// Per entry that is 6 streamed doubles + 7 gathered values + 7 FMAs per component, no face interpolation in
+// the loop.  Mapping: three consecutive warps share a slice and produce one displacement component each
+// (a thread gathers only the column of T and grad(D) its component needs); entries are taken in pairs with
+// the streamed loads issued ahead of the gathers.
 // ------------------------------------------------------------------------------------------------
-template <bool TENSOR9, bool STAB, bool NONORTH>
-__global__ void __launch_bounds__(S4F_BLOCK) k_source(
-    const int* __restrict__ slicePtr, const int* __restrict__ col, const double* __restrict__ eA, const double* __restrict__ eW,
-    const double* __restrict__ eSf, const double* __restrict__ eRc, const double* __restrict__ eGam, const double* __restrict__ eCorr,
-    const double* __restrict__ D, const double* __restrict__ T, const double* __restrict__ gradD, const double* __restrict__ V,
-    const double* __restrict__ Dold, const double* __restrict__ DoldOld, double* __restrict__ source, int N, int ld, long long nE,
-    int nSlices, double rhoGx, double rhoGy, double rhoGz, double cOld, double cOldOld) {
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nWarps = (gridDim.x * blockDim.x) >> 5;
-    constexpr int NT = TENSOR9 ? 9 : 6;
-    for (int s = warp; s < nSlices; s += nWarps) {
-        const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
-        const int row = s * 32 + lane;
-        const int r = (row < N) ? row : 0;
-        double DP[3], TP[NT], gP[9];
-#pragma unroll
-        for (int c = 0; c < 3; c++) DP[c] = D[(size_t)c * ld + r];
-#pragma unroll
-        for (int q = 0; q < NT; q++) TP[q] = T[(size_t)q * ld + r];
-        if (STAB) {
-#pragma unroll
-            for (int q = 0; q < 9; q++) gP[q] = gradD[(size_t)q * ld + r];
-        }
-        double acc[3] = {0, 0, 0};
-        for (int k = 0; k < width; k++) {
-            const long long e = (long long)base + 32 * k + lane;
-            const int cc = col[e];
-            const double a = eA[e], w = eW[e], w1 = 1.0 - w;
-            const double S[3] = {eSf[e], eSf[nE + e], eSf[2 * nE + e]};
-            double dD[3];
-#pragma unroll
-            for (int c = 0; c < 3; c++) dD[c] = D[(size_t)c * ld + cc] - DP[c];
-            double Tf[NT];
-#pragma unroll
-            for (int q = 0; q < NT; q++) Tf[q] = w * TP[q] + w1 * T[(size_t)q * ld + cc];
-            double fl[3];
-            if (TENSOR9) {
-#pragma unroll
-                for (int c = 0; c < 3; c++) fl[c] = S[0] * Tf[c] + S[1] * Tf[3 + c] + S[2] * Tf[6 + c];
-            } else {
-                fl[0] = S[0] * Tf[0] + S[1] * Tf[1] + S[2] * Tf[2];
-                fl[1] = S[0] * Tf[1] + S[1] * Tf[3] + S[2] * Tf[4];
-                fl[2] = S[0] * Tf[2] + S[1] * Tf[4] + S[2] * Tf[5];
-            }
-            double st[3] = {0, 0, 0};
-            if (STAB) {
-                const double rc = eRc[e], gam = eGam[e];
-                double m[3] = {-S[0], -S[1], -S[2]};
-                if (NONORTH) { m[0] += eCorr[e]; m[1] += eCorr[nE + e]; m[2] += eCorr[2 * nE + e]; }
-                double gf[9];
-#pragma unroll
-                for (int q = 0; q < 9; q++) gf[q] = w * gP[q] + w1 * gradD[(size_t)q * ld + cc];
-#pragma unroll
-                for (int c = 0; c < 3; c++) st[c] = rc * dD[c] + gam * (m[0] * gf[c] + m[1] * gf[3 + c] + m[2] * gf[6 + c]);
-            }
-#pragma unroll
-            for (int c = 0; c < 3; c++) acc[c] += fl[c] - a * dD[c] + st[c];
-        }
-        if (row < N) {
-            const double v = V[row];
-            const double rg[3] = {rhoGx, rhoGy, rhoGz};
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                double sv = acc[c] + v * rg[c];
-                if (cOld != 0.0) sv += v * (cOld * Dold[(size_t)c * ld + row] - cOldOld * DoldOld[(size_t)c * ld + row]);
-                source[(size_t)c * ld + row] = sv;
-            }
-        }
-    }
-}
-
-// The same right-hand side with the component-per-warp mapping of the SpMV (s4f_pcg.cu, k_amul3c): three
-// consecutive warps share a slice and produce one displacement component each, so a thread gathers only
-// the column of T and of grad(D) its component needs (7 neighbour values per entry instead of 18+) and
-// keeps few registers; the per-entry geometry (col, a, w, Sf, rc, gamma) is fetched from HBM once and
-// reaches the other two warps through L1.  Arithmetic and summation order per component are those of
-// k_source above.
 #define S4F_SRC_BLOCK 192
 template <bool TENSOR9, bool STAB, bool NONORTH>
-__global__ void __launch_bounds__(S4F_SRC_BLOCK) k_source_c(
-    const int* __restrict__ slicePtr, const int* __restrict__ col, const double* __restrict__ eA, const double* __restrict__ eW,
-    const double* __restrict__ eSf, const double* __restrict__ eRc, const double* __restrict__ eGam, const double* __restrict__ eCorr,
-    const double* __restrict__ D, const double* __restrict__ T, const double* __restrict__ gradD, const double* __restrict__ V,
-    const double* __restrict__ Dold, const double* __restrict__ DoldOld, double* __restrict__ source, int N, int ld, long long nE,
-    int nSlices, double rhoGx, double rhoGy, double rhoGz, double cOld, double cOldOld) {
+__global__ void __launch_bounds__(S4F_SRC_BLOCK, 4) k_source_f(
+    const int* __restrict__ slicePtr, const int* __restrict__ col, const double* __restrict__ eU, const double* __restrict__ eC0,
+    const double* __restrict__ eGam, const double* __restrict__ eVc, const double* __restrict__ rowK, const double* __restrict__ D,
+    const double* __restrict__ T, const double* __restrict__ gradD, const double* __restrict__ V, const double* __restrict__ Dold,
+    const double* __restrict__ DoldOld, double* __restrict__ source, int N, int ld, long long nE, int nSlices, double rhoGx,
+    double rhoGy, double rhoGz, double cOld, double cOldOld) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int q = wib % 3, sub = wib / 3;
     constexpr int SPB = S4F_SRC_BLOCK / 96;
@@ -338,37 +293,45 @@ __global__ void __launch_bounds__(S4F_SRC_BLOCK) k_source_c(
     const double* __restrict__ G0 = gradD + (size_t)q * ld;
     const double* __restrict__ G1 = gradD + (size_t)(3 + q) * ld;
     const double* __restrict__ G2 = gradD + (size_t)(6 + q) * ld;
+    const double* __restrict__ eU0 = eU;
+    const double* __restrict__ eU1 = eU + nE;
+    const double* __restrict__ eU2 = eU + 2 * nE;
     const double rg = (q == 0) ? rhoGx : (q == 1 ? rhoGy : rhoGz);
+    constexpr int G = 2;
     for (int s = blockIdx.x * SPB + sub; s < nSlices; s += gridDim.x * SPB) {
         const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
         const int row = s * 32 + lane;
-        const int r = (row < N) ? row : 0;
-        const double DP = Dq[r], TP0 = T0[r], TP1 = T1[r], TP2 = T2[r];
-        double gP0 = 0, gP1 = 0, gP2 = 0;
-        if (STAB) { gP0 = G0[r]; gP1 = G1[r]; gP2 = G2[r]; }
+        const double DP = Dq[row < N ? row : 0];      // the laplacian keeps its difference form c0 (D_N - D_P): no cancellation
         double acc = 0;
-#pragma unroll 2
-        for (int k = 0; k < width; k++) {
-            const long long e = (long long)base + 32 * k + lane;
-            const int cc = col[e];
-            const double a = eA[e], w = eW[e], w1 = 1.0 - w;
-            const double S0 = eSf[e], S1 = eSf[nE + e], S2 = eSf[2 * nE + e];
-            const double dD = Dq[cc] - DP;
-            const double Tf0 = w * TP0 + w1 * T0[cc], Tf1 = w * TP1 + w1 * T1[cc], Tf2 = w * TP2 + w1 * T2[cc];
-            const double fl = S0 * Tf0 + S1 * Tf1 + S2 * Tf2;
-            double st = 0;
-            if (STAB) {
-                const double rc = eRc[e], gam = eGam[e];
-                double m0 = -S0, m1 = -S1, m2 = -S2;
-                if (NONORTH) { m0 += eCorr[e]; m1 += eCorr[nE + e]; m2 += eCorr[2 * nE + e]; }
-                const double gf0 = w * gP0 + w1 * G0[cc], gf1 = w * gP1 + w1 * G1[cc], gf2 = w * gP2 + w1 * G2[cc];
-                st = rc * dD + gam * (m0 * gf0 + m1 * gf1 + m2 * gf2);
+        for (int k0 = 0; k0 < width; k0 += G) {
+            int cc[G]; double u0[G], u1[G], u2[G], c0[G], gm[G], v0[G], v1[G], v2[G];
+#pragma unroll
+            for (int k = 0; k < G; k++) {
+                const bool ok = k0 + k < width;
+                const long long e = (long long)base + 32 * (ok ? k0 + k : k0) + lane;
+                cc[k] = col[e];
+                u0[k] = ok ? eU0[e] : 0.0; u1[k] = ok ? eU1[e] : 0.0; u2[k] = ok ? eU2[e] : 0.0;
+                c0[k] = ok ? eC0[e] : 0.0;
+                if (STAB) gm[k] = ok ? eGam[e] : 0.0;
+                if (STAB && NONORTH) { v0[k] = ok ? eVc[e] : 0.0; v1[k] = ok ? eVc[nE + e] : 0.0; v2[k] = ok ? eVc[2 * nE + e] : 0.0; }
             }
-            acc += fl - a * dD + st;
+#pragma unroll
+            for (int k = 0; k < G; k++) {
+                const int n = cc[k];
+                double t = u0[k] * T0[n] + u1[k] * T1[n] + u2[k] * T2[n] + c0[k] * (Dq[n] - DP);
+                if (STAB) {
+                    const double g0 = G0[n], g1 = G1[n], g2 = G2[n];
+                    t -= gm[k] * (u0[k] * g0 + u1[k] * g1 + u2[k] * g2);
+                    if (NONORTH) t += v0[k] * g0 + v1[k] * g1 + v2[k] * g2;
+                }
+                acc += t;
+            }
         }
         if (row < N) {
+            double sv = acc + rowK[row] * T0[row] + rowK[(size_t)ld + row] * T1[row] + rowK[2 * (size_t)ld + row] * T2[row];
+            if (STAB) sv += rowK[3 * (size_t)ld + row] * G0[row] + rowK[4 * (size_t)ld + row] * G1[row] + rowK[5 * (size_t)ld + row] * G2[row];
             const double v = V[row];
-            double sv = acc + v * rg;
+            sv += v * rg;
             if (cOld != 0.0) sv += v * (cOld * Dold[(size_t)q * ld + row] - cOldOld * DoldOld[(size_t)q * ld + row]);
             source[(size_t)q * ld + row] = sv;
         }
@@ -594,9 +557,10 @@ int s4f_assemble_matrix(s4fgpu_ctx* c) {
     double cOld, cOldOld;
     const double dcoef = d2dt2_diag_coeff(c, &cOld, &cOldOld);
     const int gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
-    k_assemble_laplacian<<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eW.p, c->eDn.p, c->impK.p, c->V.p, c->eA.p, c->eRc.p,
-                                                             c->eGam.p, c->diag0.p, c->N, c->bOff(), c->nSlices, c->ctl.stabScaleFactor,
-                                                             c->ctl.stabilisation == S4F_STAB_RHIE_CHOW ? 1 : 0, dcoef);
+    k_assemble_laplacian<<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eW.p, c->eDn.p, c->eSf.p, c->nonOrth ? c->eCorr.p : nullptr,
+                                                             c->impK.p, c->V.p, c->eA.p, c->eGam.p, c->eU.p, c->eC0.p, c->nonOrth ? c->eVc.p : nullptr,
+                                                             c->rowK.p, c->diag0.p, c->N, c->bOff(), c->ld, c->nEntries, c->nSlices,
+                                                             c->ctl.stabScaleFactor, c->ctl.stabilisation == S4F_STAB_RHIE_CHOW ? 1 : 0, dcoef);
     k_diag_copy<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->diag0.p, c->diagC.p, c->N, c->ld);
     c->launches += 2;
     if (c->nBCells > 0) {
@@ -633,28 +597,14 @@ template <bool T9>
 static void launch_source(s4fgpu_ctx* c, const double* T, double cOld, double cOldOld) {
     const bool stab = c->ctl.stabilisation == S4F_STAB_RHIE_CHOW;
     const double rg[3] = {c->law.rho * c->ctl.g[0], c->law.rho * c->ctl.g[1], c->law.rho * c->ctl.g[2]};
-    if (c->srcVariant == 0) {
-        long long need = ((long long)c->nSlices + 1) / 2, g = (long long)c->numSMs * 10;
-        if (need < g) g = need;
-        const int grid = (int)(g < 1 ? 1 : g);
-#define S4F_LAUNCH_SRC(STAB, NO)                                                                                                     \
-    k_source_c<T9, STAB, NO><<<grid, S4F_SRC_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->eW.p, c->eSf.p, c->eRc.p,    \
-                                                                    c->eGam.p, c->eCorr.p, c->D.p, T, c->gradD.p, c->V.p, c->Dold.p,  \
-                                                                    c->DoldOld.p, c->source.p, c->N, c->ld, c->nEntries, c->nSlices,  \
-                                                                    rg[0], rg[1], rg[2], cOld, cOldOld)
-        if (stab && c->nonOrth) S4F_LAUNCH_SRC(true, true);
-        else if (stab) S4F_LAUNCH_SRC(true, false);
-        else S4F_LAUNCH_SRC(false, false);
-#undef S4F_LAUNCH_SRC
-        c->launches++;
-        return;
-    }
-    const int gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
-#define S4F_LAUNCH_SRC(STAB, NO)                                                                                                   \
-    k_source<T9, STAB, NO><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->eW.p, c->eSf.p, c->eRc.p, c->eGam.p, \
-                                                               c->eCorr.p, c->D.p, T, c->gradD.p, c->V.p, c->Dold.p, c->DoldOld.p,     \
-                                                               c->source.p, c->N, c->ld, c->nEntries, c->nSlices, rg[0], rg[1], rg[2], \
-                                                               cOld, cOldOld)
+    long long need = ((long long)c->nSlices + 1) / 2, g = (long long)c->numSMs * 8;
+    if (need < g) g = need;
+    const int grid = (int)(g < 1 ? 1 : g);
+#define S4F_LAUNCH_SRC(STAB, NO)                                                                                                      \
+    k_source_f<T9, STAB, NO><<<grid, S4F_SRC_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eU.p, c->eC0.p, c->eGam.p, c->eVc.p,   \
+                                                                    c->rowK.p, c->D.p, T, c->gradD.p, c->V.p, c->Dold.p, c->DoldOld.p, \
+                                                                    c->source.p, c->N, c->ld, c->nEntries, c->nSlices, rg[0], rg[1],   \
+                                                                    rg[2], cOld, cOldOld)
     if (stab && c->nonOrth) S4F_LAUNCH_SRC(true, true);
     else if (stab) S4F_LAUNCH_SRC(true, false);
     else S4F_LAUNCH_SRC(false, false);
@@ -744,6 +694,6 @@ int s4f_time_fv_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, double
     if (kernel == S4F_KERNEL_GRAD) *bytesOut = 24 * N + nnz * (4 + 24) + 72 * N + 0.125 * N;                 // D, (col, ls), gradD out
     else if (kernel == S4F_KERNEL_LAW) *bytesOut = (72 + 48) * N;                                              // gradD in, sigma out (Hooke)
     else if (kernel == S4F_KERNEL_GAMG_VCYCLE) { int nl, sz[16]; double st; int rc = s4f_amg_info(c, &nl, sz, 16, bytesOut, &st); if (rc) return rc; }
-    else *bytesOut = (24 + 48 + 72) * N + nnz * (4 + 8 + 8 + 24 + 8 + 8) + 8 * N + 24 * N + 0.125 * N;        // D,sigma,gradD | col,a,w,Sf,rc,gam | V | out
+    else *bytesOut = (24 + 48 + 72) * N + nnz * (4 + 24 + 8 + 8) + (48 + 8 + 24 + 0.125) * N;                   // D,sigma,gradD | col,u,c0,gamma | rowK, V, out
     return 0;
 }

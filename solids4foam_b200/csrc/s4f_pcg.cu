@@ -542,7 +542,9 @@ int s4f_solve_segregated(s4fgpu_ctx* c, double* psi, const double* source) {
     c->launches++;
     rc = allreduce_part(c, 9, PH_INIT, P, nGlob); if (rc) return rc;
 
-    const int checkEvery = c->ctl.checkEvery > 0 ? c->ctl.checkEvery : 4;
+    // the host polls the device-side flags every checkEvery iterations (an idle iteration costs three early-exit
+    // launches); a multigrid / polynomial application is far dearer than a poll, so those poll every iteration
+    const int checkEvery = fusedJacobi ? (c->ctl.checkEvery > 0 ? c->ctl.checkEvery : 4) : 1;
     int it = 0;
     for (;;) {
         S4F_CHECK_CUDA(c, cudaMemcpyAsync(c->hPcgS, S, sizeof(PcgScalars), cudaMemcpyDeviceToHost, c->stream));

@@ -190,7 +190,10 @@ int s4f_build_rows(s4fgpu_ctx* c) {
     S4F_CHECK_CUDA(c, c->eLs.upload(hLs));
     S4F_CHECK_CUDA(c, c->eDn.upload(hDn));
     if (nonOrth) S4F_CHECK_CUDA(c, c->eCorr.upload(hCorr)); else c->eCorr.release();
-    S4F_CHECK_CUDA(c, c->eA.alloc(nE)); S4F_CHECK_CUDA(c, c->eRc.alloc(nE)); S4F_CHECK_CUDA(c, c->eGam.alloc(nE));
+    S4F_CHECK_CUDA(c, c->eA.alloc(nE)); S4F_CHECK_CUDA(c, c->eGam.alloc(nE));
+    S4F_CHECK_CUDA(c, c->eU.alloc(3 * (size_t)nE)); S4F_CHECK_CUDA(c, c->eC0.alloc(nE));
+    if (nonOrth) S4F_CHECK_CUDA(c, c->eVc.alloc(3 * (size_t)nE)); else c->eVc.release();
+    S4F_CHECK_CUDA(c, c->rowK.alloc(6 * (size_t)c->ld));
 
     // volumes
     std::vector<double> hV(c->ld, 1.0), hrV(c->ld, 1.0);

@@ -202,3 +202,74 @@ def test_chebyshev_pcg_solves_the_assembled_system():
     psi_o, st_o = o.op_solve(np.zeros((mesh.nCells, 3)), src)
     assert rel_l2(psi_g, psi_o) < 1e-8
     assert max(st_g["nIterations"]) < max(st_o["nIterations"])     # oracle falls back to the diagonal preconditioner
+
+
+# ---------------------------------------------------------------------------------------------
+# finite-strain configurations (BASELINE.json configs 3 and 4): total-Lagrangian solid model,
+# neoHookeanElastic and neoHookeanElasticMisesPlastic laws, div(J Finv & sigma)
+# ---------------------------------------------------------------------------------------------
+def _finite_strain_D(mesh, amp):
+    L = mesh.C[:, 0].max() + 1e-9
+    x, y, z = mesh.C[:, 0], mesh.C[:, 1], mesh.C[:, 2]
+    D = amp * np.stack([0.3 * x / L + 0.05 * np.sin(2 * np.pi * y), -0.5 * (x / L) ** 2 + 0.02 * z, 0.04 * x * z / L], axis=1)
+    return D
+
+
+@pytest.mark.parametrize("case_fn,kw,amp", [
+    (cases.neo_hookean_cantilever, dict(nx=12, ny=4, nz=4), 0.5),          # C3: large rotations / stretches
+    (cases.notched_bar, dict(nx=16, ny=4, nz=4), 0.02),                    # C4: past yield in the notch, non-orthogonal mesh
+])
+def test_finite_strain_operators(case_fn, kw, amp):
+    g, o, mesh = _pair(case_fn, **kw)
+    D = _finite_strain_D(mesh, amp)
+    for s in (g, o):
+        s.set("D", D)
+        s.initialise()
+    assert rel_l2(g.get("gradD"), o.get("gradD")) < OP_TOL
+    for s in (g, o):
+        s.op_correct()
+    assert rel_l2(g.get("sigma"), o.get("sigma")) < 1e-11
+    assert rel_l2(g.get("sigma_b"), o.get("sigma_b")) < 1e-11
+    assert rel_l2(g.get("J"), o.get("J")) < OP_TOL
+    if case_fn is cases.notched_bar:
+        dl_g, dl_o = g.get("DLambda"), o.get("DLambda")
+        assert (dl_o > 0).sum() > 0.05 * mesh.nCells            # a real plastic zone
+        assert np.abs(dl_g - dl_o).max() < 1e-9 * max(dl_o.max(), 1e-30) + 1e-14
+        assert rel_l2(g.get("bEbar"), o.get("bEbar")) < 1e-11
+    for s in (g, o):
+        s.op_assemble()
+    src_g, src_o = g.get("source"), o.get("source")
+    assert np.abs(src_g - src_o).max() / np.abs(src_o).max() < 1e-10
+    assert rel_l2(g.get("tractionGradient_b"), o.get("tractionGradient_b")) < 1e-10
+
+
+def test_neo_hookean_tl_evolve_matches_oracle():
+    kw = dict(nx=8, ny=4, nz=4, L=2.0, traction=(0.0, -8e3, 0.0), fieldRelaxD=0.9, nCorrectors=6000, **TIGHT)
+    g, o, mesh = _pair(cases.neo_hookean_cantilever, preconditioner=K.PRECOND_GAMG, **kw)
+    sg, so = g.evolve(), o.evolve()
+    assert sg["converged"] and so["converged"], (sg, so)
+    Do = o.get("D")
+    assert np.abs(Do[:, 1]).max() > 0.02 * 2.0              # genuinely geometrically non-linear (tip deflection > 2% L)
+    assert rel_l2(g.get("D"), Do) < SOLVE_TOL
+    assert rel_l2(g.get("sigma"), o.get("sigma")) < SOLVE_TOL
+
+
+def test_notched_bar_mises_two_load_steps_match_oracle():
+    """J2 return mapping through two load increments incl. the history commit (updateTotalFields)."""
+    kw = dict(nx=12, ny=4, nz=4, L=2.0, elongation=0.0, fieldRelaxD=1.0, nCorrectors=3000, **TIGHT)
+    g, o, mesh = _pair(cases.notched_bar, preconditioner=K.PRECOND_GAMG, **kw)
+    pulled = mesh.patch("pulled")
+    for step, el in enumerate((0.002, 0.004)):
+        disp = np.zeros((pulled.size, 3)); disp[:, 0] = el * 2.0
+        for s in (g, o):
+            s.new_timestep(1.0)
+            s.set_bc("pulled", K.fixedDisplacement(disp))
+        sg, so = g.evolve(), o.evolve()
+        assert sg["converged"] and so["converged"], (step, sg, so)
+        assert rel_l2(g.get("D"), o.get("D")) < SOLVE_TOL
+        assert rel_l2(g.get("sigma"), o.get("sigma")) < 5 * SOLVE_TOL
+        for s in (g, o):
+            s.update_total_fields()
+        ep_o = o.get("epsilonPEq")
+        assert np.abs(g.get("epsilonPEq") - ep_o).max() < 1e-6 * max(ep_o.max(), 1e-30) + 1e-12
+    assert ep_o.max() > 1e-4
