@@ -260,6 +260,32 @@ __global__ void k_amg_dense(const T* __restrict__ inv, const TB* __restrict__ b,
     if (lane == 0) x[(size_t)q * ldo + i] = (TO)s;
 }
 
+// halo of a level-0 work vector (type T): boundary-cell values -> staging, staging -> ghost slots [N, N+G)
+template <class T>
+__global__ void k_amg_pack(const T* __restrict__ f, const int* __restrict__ sendCells, T* __restrict__ buf, int G, int ld) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * G) return;
+    const int q = i / G, g = i % G;
+    buf[i] = f[(size_t)q * ld + sendCells[g]];
+}
+template <class T>
+__global__ void k_amg_unpack(T* __restrict__ f, const T* __restrict__ buf, int G, int N, int ld) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * G) return;
+    const int q = i / G, g = i % G;
+    f[(size_t)q * ld + N + g] = buf[i];
+}
+// all-gathered level-1 right-hand sides ([rank][3][maxLoc]) -> the replicated level-1 vector
+template <class T>
+__global__ void k_amg_scatter_gathered(const T* __restrict__ recv, T* __restrict__ b, const int* __restrict__ off, const int* __restrict__ cnt,
+                                       int world, int maxLoc, int ldc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (r >= world || i >= cnt[r]) return;
+#pragma unroll
+    for (int q = 0; q < 3; q++) b[(size_t)q * ldc + off[r] + i] = recv[((size_t)r * 3 + q) * maxLoc + i];
+}
+
 template <class T>
 __global__ void k_amg_convert(const double* __restrict__ in, T* __restrict__ out, long long n) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -313,6 +339,29 @@ struct Hierarchy : S4fAmg {
     int deg = 2, cycle = 0;
     double omega = 1.8;
     double theta = 0, delta = 0;
+    // multi-rank: level 0 is this rank's part of the mesh (ghost columns, halo exchange per SpMV); levels >= 1
+    // are the GLOBAL coarse levels, replicated on every rank and fed by an all-gather of the restricted residual
+    bool dist = false;
+    int n1Local = 0, n1Off = 0, maxLoc = 0;
+    DevBuf<T> hsend, hrecv, gsend, grecv;
+    DevBuf<int> rankOff, rankCnt;
+
+    static ncclDataType_t nccl_t() { return sizeof(T) == 4 ? ncclFloat : ncclDouble; }
+    int halo0(s4fgpu_ctx* c, T* x) {
+        if (!dist || c->G == 0) return 0;
+        const int G = c->G;
+        k_amg_pack<T><<<(3 * G + 255) / 256, 256, 0, c->stream>>>(x, c->sendCells.p, hsend.p, G, c->ld);
+        S4F_CHECK_NCCL(c, ncclGroupStart());
+        for (const auto& nb : c->nbrs)
+            for (int q = 0; q < 3; q++) {
+                S4F_CHECK_NCCL(c, ncclSend(hsend.p + (size_t)q * G + nb.sendOff, nb.count, nccl_t(), nb.rank, c->comm, c->stream));
+                S4F_CHECK_NCCL(c, ncclRecv(hrecv.p + (size_t)q * G + nb.sendOff, nb.count, nccl_t(), nb.rank, c->comm, c->stream));
+            }
+        S4F_CHECK_NCCL(c, ncclGroupEnd());
+        k_amg_unpack<T><<<(3 * G + 255) / 256, 256, 0, c->stream>>>(x, hrecv.p, G, c->N, c->ld);
+        c->launches += 2;
+        return 0;
+    }
 
     int build_level_rows(s4fgpu_ctx* c, Level<T>& L, const HostLevel& H) {
         const int n = H.n;
@@ -361,13 +410,15 @@ struct Hierarchy : S4fAmg {
         S4F_CHECK_CUDA(c, L.d.alloc(m)); S4F_CHECK_CUDA(c, L.t.alloc(m));
         return 0;
     }
-    int set_transfer(s4fgpu_ctx* c, Level<T>& fine, Level<T>& coarse, const std::vector<int>& parent, int nc) {
+    // parent[i] = coarse cell of fine cell i (global numbering); the children lists cover the coarse cells
+    // [off, off+nc) that this rank's fine cells feed (off = 0, nc = all on replicated / serial levels)
+    int set_transfer(s4fgpu_ctx* c, Level<T>& fine, Level<T>& coarse, const std::vector<int>& parent, int nc, int off = 0) {
         S4F_CHECK_CUDA(c, fine.parent.upload(parent));
         std::vector<int> ptr(nc + 1, 0), ch(parent.size());
-        for (size_t i = 0; i < parent.size(); i++) ptr[parent[i] + 1]++;
+        for (size_t i = 0; i < parent.size(); i++) ptr[parent[i] - off + 1]++;
         for (int i = 0; i < nc; i++) ptr[i + 1] += ptr[i];
         std::vector<int> cur(ptr.begin(), ptr.end() - 1);
-        for (size_t i = 0; i < parent.size(); i++) ch[cur[parent[i]]++] = (int)i;
+        for (size_t i = 0; i < parent.size(); i++) ch[cur[parent[i] - off]++] = (int)i;
         S4F_CHECK_CUDA(c, coarse.childPtr.upload(ptr)); S4F_CHECK_CUDA(c, coarse.child.upload(ch));
         return 0;
     }
@@ -398,6 +449,7 @@ struct Hierarchy : S4fAmg {
     template <class TB, class TO>
     void step(s4fgpu_ctx* c, Level<T>& L, const TB* b, int ldb, const T* xin, TO* xout, int ldo, double c1, double c2) {
         const int grid = step_grid(c, L);
+        if (dist && &L == lv[0].get()) halo0(c, const_cast<T*>(xin));
         k_amg_step<T, TB, TO, 0><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, L.rD.p, b, xin, L.d.p, xout, L.n, L.ld, ldb, ldo,
                                                                      L.nSlices, (T)c1, (T)c2);
         c->launches++;
@@ -428,6 +480,31 @@ struct Hierarchy : S4fAmg {
         return xcur;
     }
 
+    // t = b - A x on level l, restricted into the right-hand side of level l+1
+    template <class TB>
+    int residual_restrict(s4fgpu_ctx* c, size_t l, const TB* b, int ldb, T* x) {
+        Level<T>& L = *lv[l];
+        Level<T>& C = *lv[l + 1];
+        const int grid = step_grid(c, L);
+        const bool d0 = dist && l == 0;
+        if (d0) { int rc = halo0(c, x); if (rc) return rc; }
+        k_amg_step<T, TB, T, 1><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, L.rD.p, b, x, L.d.p, L.t.p, L.n, L.ld, ldb, L.ld,
+                                                                       L.nSlices, (T)0, (T)0);
+        c->launches++;
+        if (!d0) {
+            k_amg_restrict<T><<<(C.n + 127) / 128, 128, 0, c->stream>>>(C.childPtr.p, C.child.p, L.t.p, C.b.p, C.n, L.ld, C.ld);
+            c->launches++;
+            return 0;
+        }
+        // this rank's aggregates -> packed [3][maxLoc]; all-gather over NVLink; scatter into the replicated vector
+        k_amg_restrict<T><<<(n1Local + 127) / 128, 128, 0, c->stream>>>(C.childPtr.p, C.child.p, L.t.p, gsend.p, n1Local, L.ld, maxLoc);
+        S4F_CHECK_NCCL(c, ncclAllGather(gsend.p, grecv.p, 3 * (size_t)maxLoc, nccl_t(), c->comm, c->stream));
+        dim3 g2((maxLoc + 255) / 256, c->nRanks);
+        k_amg_scatter_gathered<T><<<g2, 256, 0, c->stream>>>(grecv.p, C.b.p, rankOff.p, rankCnt.p, c->nRanks, maxLoc, C.ld);
+        c->launches += 2;
+        return 0;
+    }
+
     template <class TB>
     int cycle_level(s4fgpu_ctx* c, size_t l, const TB* b, int ldb, double* out, int ldo) {
         Level<T>& L = *lv[l];
@@ -440,13 +517,7 @@ struct Hierarchy : S4fAmg {
         }
         Level<T>& C = *lv[l + 1];
         T* x = smooth<TB>(c, L, b, ldb, true, L.x.p, nullptr, 0);                 // pre-smoothing from zero
-        {                                                                          // residual
-            const int grid = step_grid(c, L);
-            k_amg_step<T, TB, T, 1><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, L.rD.p, b, x, L.d.p, L.t.p, L.n, L.ld, ldb, L.ld,
-                                                                       L.nSlices, (T)0, (T)0);
-            k_amg_restrict<T><<<(C.n + 127) / 128, 128, 0, c->stream>>>(C.childPtr.p, C.child.p, L.t.p, C.b.p, C.n, L.ld, C.ld);
-            c->launches += 2;
-        }
+        { int rr = residual_restrict<TB>(c, l, b, ldb, x); if (rr) return rr; }
         int rc = cycle_level<T>(c, l + 1, C.b.p, C.ld, nullptr, 0); if (rc) return rc;
         {
             const int grid = s4f_grid(c->numSMs, L.n);
@@ -454,11 +525,7 @@ struct Hierarchy : S4fAmg {
             c->launches++;
         }
         if (cycle == 1 && l + 2 < lv.size()) {   // W-cycle: a second coarse correction on the updated residual
-            const int grid = step_grid(c, L);
-            k_amg_step<T, TB, T, 1><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, L.rD.p, b, x, L.d.p, L.t.p, L.n, L.ld, ldb, L.ld,
-                                                                       L.nSlices, (T)0, (T)0);
-            k_amg_restrict<T><<<(C.n + 127) / 128, 128, 0, c->stream>>>(C.childPtr.p, C.child.p, L.t.p, C.b.p, C.n, L.ld, C.ld);
-            c->launches += 2;
+            rc = residual_restrict<TB>(c, l, b, ldb, x); if (rc) return rc;
             rc = cycle_level<T>(c, l + 1, C.b.p, C.ld, nullptr, 0); if (rc) return rc;
             const int gridp = s4f_grid(c->numSMs, L.n);
             k_amg_prolong<T><<<gridp, S4F_BLOCK, 0, c->stream>>>(L.parent.p, C.x.p, x, L.n, L.ld, C.ld, (T)omega);
@@ -479,10 +546,20 @@ struct Hierarchy : S4fAmg {
     }
 };
 
+struct DistInfo { bool on = false; int n1Local = 0, n1Off = 0, maxLoc = 0; std::vector<int> off, cnt; };
+
 template <class T>
-int build(s4fgpu_ctx* c, std::vector<HostLevel>& H) {
+int build(s4fgpu_ctx* c, std::vector<HostLevel>& H, const DistInfo& di) {
     auto* A = new Hierarchy<T>();
     std::unique_ptr<S4fAmg> guard(A);
+    A->dist = di.on; A->n1Local = di.n1Local; A->n1Off = di.n1Off; A->maxLoc = di.maxLoc;
+    if (di.on) {
+        const size_t G = std::max(c->G, 1);
+        S4F_CHECK_CUDA(c, A->hsend.alloc(3 * G)); S4F_CHECK_CUDA(c, A->hrecv.alloc(3 * G));
+        S4F_CHECK_CUDA(c, A->gsend.alloc(3 * (size_t)std::max(di.maxLoc, 1)));
+        S4F_CHECK_CUDA(c, A->grecv.alloc(3 * (size_t)std::max(di.maxLoc, 1) * c->nRanks));
+        S4F_CHECK_CUDA(c, A->rankOff.upload(di.off)); S4F_CHECK_CUDA(c, A->rankCnt.upload(di.cnt));
+    }
     A->deg = c->ctl.gamgSmootherDegree > 0 ? c->ctl.gamgSmootherDegree : 2;
     A->cycle = c->ctl.gamgCycle;
     A->omega = c->ctl.gamgOverCorrection > 0 ? c->ctl.gamgOverCorrection : 1.8;
@@ -508,7 +585,8 @@ int build(s4fgpu_ctx* c, std::vector<HostLevel>& H) {
             if ((rc = A->build_level_rows(c, L, H[l]))) return rc;
         }
         if ((rc = A->alloc_work(c, L))) return rc;
-        if (l > 0) { if ((rc = A->set_transfer(c, *A->lv[l - 1], L, H[l - 1].parent, H[l].n))) return rc; }
+        if (l == 1 && di.on) { if ((rc = A->set_transfer(c, *A->lv[0], L, H[0].parent, di.n1Local, di.n1Off))) return rc; }
+        else if (l > 0) { if ((rc = A->set_transfer(c, *A->lv[l - 1], L, H[l - 1].parent, H[l].n))) return rc; }
         A->sizes.push_back(H[l].n);
         A->nnz.push_back(l == 0 ? (double)c->nnzOff : 2.0 * (double)H[l].own.size());
     }
@@ -545,15 +623,141 @@ void s4f_amg_destroy(s4fgpu_ctx* c) {
     c->amg = nullptr;
 }
 
+namespace {
+
+// three pair-wise passes -> aggregates of up to 8 cells; `total` maps the cells of src to the coarse cells of out
+int coarsen3(const HostLevel& srcIn, int stopBelow, std::vector<int>& total, HostLevel& out) {
+    const HostLevel* src = &srcIn;
+    total.resize(src->n);
+    for (int i = 0; i < src->n; i++) total[i] = i;
+    HostLevel tmpA, tmpB;
+    int nc = src->n;
+    for (int pass = 0; pass < 3; pass++) {
+        std::vector<int> agg;
+        const int ncNew = pairwise_pass(*src, agg);
+        HostLevel& dst = (pass % 2 == 0) ? tmpA : tmpB;
+        galerkin(*src, agg, ncNew, dst);
+        for (size_t i = 0; i < total.size(); i++) total[i] = agg[total[i]];
+        src = &dst; nc = ncNew;
+        if (nc <= stopBelow) break;
+    }
+    out = *src;
+    return nc;
+}
+
+// equal-sized host blocks, all-gathered through device staging (set-up only)
+int allgather_host(s4fgpu_ctx* c, const void* send, size_t bytes, void* recv) {
+    DevBuf<char> ds, dr;
+    S4F_CHECK_CUDA(c, ds.alloc(std::max<size_t>(bytes, 1), false)); S4F_CHECK_CUDA(c, dr.alloc(std::max<size_t>(bytes, 1) * c->nRanks, false));
+    if (bytes) S4F_CHECK_CUDA(c, cudaMemcpyAsync(ds.p, send, bytes, cudaMemcpyHostToDevice, c->stream));
+    S4F_CHECK_NCCL(c, ncclAllGather(ds.p, dr.p, std::max<size_t>(bytes, 1), ncclChar, c->comm, c->stream));
+    S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (bytes) S4F_CHECK_CUDA(c, cudaMemcpy(recv, dr.p, bytes * c->nRanks, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// one int per processor-patch face, sent to / received from the rank across the face (patch order)
+int exchange_ghost_ints(s4fgpu_ctx* c, const std::vector<int>& send, std::vector<int>& recv) {
+    const int G = c->G;
+    recv.assign(G, 0);
+    if (G == 0) return 0;
+    DevBuf<int> ds, dr;
+    S4F_CHECK_CUDA(c, ds.upload(send)); S4F_CHECK_CUDA(c, dr.alloc(G));
+    S4F_CHECK_NCCL(c, ncclGroupStart());
+    for (const auto& nb : c->nbrs) {
+        S4F_CHECK_NCCL(c, ncclSend(ds.p + nb.sendOff, nb.count, ncclInt, nb.rank, c->comm, c->stream));
+        S4F_CHECK_NCCL(c, ncclRecv(dr.p + nb.sendOff, nb.count, ncclInt, nb.rank, c->comm, c->stream));
+    }
+    S4F_CHECK_NCCL(c, ncclGroupEnd());
+    S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+    S4F_CHECK_CUDA(c, cudaMemcpy(recv.data(), dr.p, G * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+__global__ void k_gather_entries(const int* __restrict__ idx, const double* __restrict__ eA, double* __restrict__ out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = eA[idx[i]];
+}
+
+// Multi-rank: aggregate this rank's cells, learn the aggregates of the ghost cells, form this rank's rows of
+// the global level-1 matrix (incl. the couplings across processor patches) and all-gather the pieces, so that
+// every rank holds the same global level 1 and continues the coarsening identically.
+int build_global_level1(s4fgpu_ctx* c, HostLevel& L0, HostLevel& H1, DistInfo& di) {
+    const int N = c->N, G = c->G, world = c->nRanks, rank = c->rank;
+    std::vector<int> parentLoc; HostLevel dummy;
+    const int n1Local = coarsen3(L0, 0, parentLoc, dummy);
+    std::vector<int> cnt(world);
+    int rc = allgather_host(c, &n1Local, sizeof(int), cnt.data()); if (rc) return rc;
+    std::vector<int> off(world + 1, 0);
+    for (int r = 0; r < world; r++) off[r + 1] = off[r] + cnt[r];
+    const int n1Global = off[world], myOff = off[rank];
+    // aggregates of the ghost cells + coefficients of the processor faces
+    std::vector<int> sendP(std::max(G, 1), 0), ghostParent, sendCellsH(std::max(G, 1), 0), entryH(std::max(G, 1), 0);
+    for (const auto& nb : c->nbrs)
+        for (int i = 0; i < nb.count; i++) {
+            const int cell = c->faceCells[c->pStart[nb.patch] + i];
+            sendCellsH[nb.sendOff + i] = cell;
+            sendP[nb.sendOff + i] = myOff + parentLoc[cell];
+        }
+    sendP.resize(G); 
+    if ((rc = exchange_ghost_ints(c, sendP, ghostParent))) return rc;
+    std::vector<double> aPf(std::max(G, 1), 0.0);
+    if (G > 0) {
+        DevBuf<double> d; S4F_CHECK_CUDA(c, d.alloc(G));
+        k_gather_entries<<<(G + 255) / 256, 256, 0, c->stream>>>(c->procEntry.p, c->eA.p, d.p, G);
+        c->launches++;
+        S4F_CHECK_CUDA(c, cudaMemcpyAsync(aPf.data(), d.p, G * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    // augmented level: local cells + ghost cells, internal faces + processor faces
+    HostLevel aug; aug.n = N + G;
+    aug.own = L0.own; aug.nei = L0.nei; aug.a = L0.a;
+    for (int g = 0; g < G; g++) { aug.own.push_back(sendCellsH[g]); aug.nei.push_back(N + g); aug.a.push_back(aPf[g]); }
+    for (int q = 0; q < 3; q++) { aug.diag[q] = L0.diag[q]; aug.diag[q].resize(N + G, 0.0); }
+    std::vector<int> agg(N + G);
+    for (int i = 0; i < N; i++) agg[i] = myOff + parentLoc[i];
+    for (int g = 0; g < G; g++) agg[N + g] = ghostParent[g];
+    HostLevel part; galerkin(aug, agg, n1Global, part);
+    // the faces this rank contributes: owner (lower id) among its own aggregates
+    std::vector<int> fo, fn; std::vector<double> fa;
+    for (size_t f = 0; f < part.own.size(); f++)
+        if (part.own[f] >= myOff && part.own[f] < myOff + n1Local) { fo.push_back(part.own[f]); fn.push_back(part.nei[f]); fa.push_back(part.a[f]); }
+    int nF = (int)fo.size();
+    std::vector<int> nFs(world);
+    if ((rc = allgather_host(c, &nF, sizeof(int), nFs.data()))) return rc;
+    int maxF = 1, maxLoc = 1;
+    for (int r = 0; r < world; r++) { maxF = std::max(maxF, nFs[r]); maxLoc = std::max(maxLoc, cnt[r]); }
+    std::vector<int> si(2 * (size_t)maxF, 0), ri(2 * (size_t)maxF * world);
+    std::vector<double> sd((size_t)maxF + 3 * (size_t)maxLoc, 0.0), rd(((size_t)maxF + 3 * (size_t)maxLoc) * world);
+    for (int f = 0; f < nF; f++) { si[f] = fo[f]; si[maxF + f] = fn[f]; sd[f] = fa[f]; }
+    for (int q = 0; q < 3; q++) for (int i = 0; i < n1Local; i++) sd[(size_t)maxF + (size_t)q * maxLoc + i] = part.diag[q][myOff + i];
+    if ((rc = allgather_host(c, si.data(), si.size() * sizeof(int), ri.data()))) return rc;
+    if ((rc = allgather_host(c, sd.data(), sd.size() * sizeof(double), rd.data()))) return rc;
+    H1 = HostLevel(); H1.n = n1Global;
+    for (int q = 0; q < 3; q++) H1.diag[q].assign(n1Global, 0.0);
+    for (int r = 0; r < world; r++) {
+        const int* pi = ri.data() + (size_t)r * 2 * maxF;
+        const double* pd = rd.data() + (size_t)r * ((size_t)maxF + 3 * (size_t)maxLoc);
+        for (int f = 0; f < nFs[r]; f++) { H1.own.push_back(pi[f]); H1.nei.push_back(pi[maxF + f]); H1.a.push_back(pd[f]); }
+        for (int q = 0; q < 3; q++) for (int i = 0; i < cnt[r]; i++) H1.diag[q][off[r] + i] = pd[(size_t)maxF + (size_t)q * maxLoc + i];
+    }
+    L0.parent.assign(agg.begin(), agg.begin() + N);
+    di.on = true; di.n1Local = n1Local; di.n1Off = myOff; di.maxLoc = maxLoc;
+    di.off.assign(off.begin(), off.begin() + world); di.cnt = cnt;
+    return 0;
+}
+
+}  // namespace
+
 // Build the hierarchy from the assembled fine matrix (upper() and the per-component diagonals).
 int s4f_amg_setup(s4fgpu_ctx* c) {
     s4f_amg_destroy(c);
     const auto t0 = std::chrono::steady_clock::now();
     const int N = c->N, F = c->F;
     std::vector<HostLevel> H(1);
-    HostLevel& L0 = H[0];
-    L0.n = N; L0.own = c->own; L0.nei = c->nei; L0.a.resize(F);
     {
+        HostLevel& L0 = H[0];
+        L0.n = N; L0.own = c->own; L0.nei = c->nei; L0.a.resize(F);
         int rc = s4f_download_upper(c, L0.a.data()); if (rc) return rc;
         for (int f = 0; f < F; f++) L0.a[f] = -L0.a[f];
         std::vector<double> d(3 * (size_t)c->ld);
@@ -561,31 +765,22 @@ int s4f_amg_setup(s4fgpu_ctx* c) {
         for (int q = 0; q < 3; q++) L0.diag[q].assign(d.begin() + (size_t)q * c->ld, d.begin() + (size_t)q * c->ld + N);
     }
     const int coarsest = 512;
+    DistInfo di;
+    if (c->nRanks > 1) {
+        HostLevel H1;
+        int rc = build_global_level1(c, H[0], H1, di); if (rc) return rc;
+        H.push_back(std::move(H1));
+    }
     while (H.back().n > coarsest && H.size() < 12) {
-        // three pair-wise passes -> aggregates of up to 8 cells
-        HostLevel cur;                      // intermediate levels are discarded
-        const HostLevel* src = &H.back();
-        std::vector<int> total(src->n);
-        for (int i = 0; i < src->n; i++) total[i] = i;
-        HostLevel tmpA, tmpB;
-        int nc = src->n;
-        for (int pass = 0; pass < 3; pass++) {
-            std::vector<int> agg;
-            const int ncNew = pairwise_pass(*src, agg);
-            HostLevel& dst = (pass % 2 == 0) ? tmpA : tmpB;
-            galerkin(*src, agg, ncNew, dst);
-            for (size_t i = 0; i < total.size(); i++) total[i] = agg[total[i]];
-            src = &dst; nc = ncNew;
-            if (nc <= coarsest / 4) break;
-        }
+        std::vector<int> total; HostLevel next;
+        const int nc = coarsen3(H.back(), coarsest / 4, total, next);
         if (nc >= H.back().n) break;        // no coarsening possible (no faces)
         H.back().parent = total;
-        HostLevel next = *src;
         H.push_back(std::move(next));
     }
     int rc;
-    if (c->ctl.gamgSinglePrecision) rc = build<float>(c, H);
-    else rc = build<double>(c, H);
+    if (c->ctl.gamgSinglePrecision) rc = build<float>(c, H, di);
+    else rc = build<double>(c, H, di);
     if (!rc) c->amg->setupSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return rc;
 }

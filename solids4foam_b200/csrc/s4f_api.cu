@@ -47,8 +47,6 @@ int s4f_setup_law(s4fgpu_ctx* c) {
     return 0;
 }
 
-// T = J Finv & sigma and boundary Finv, needed before the first traction update of a TL model
-int s4f_kinematics(s4fgpu_ctx* c) { return 0; }
 
 int s4f_outer_iteration(s4fgpu_ctx* c, int iCorr) {
     int rc;
@@ -292,14 +290,12 @@ int s4fgpu_initialise(s4fgpu_handle c) {
     int rc;
     if ((rc = s4f_alloc_model_fields(c))) return rc;
     if ((rc = s4f_upload_bc(c))) return rc;
-    if (c->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP) {   // boundary Finv for the traction update
-        if ((rc = s4f_law_correct(c))) return rc;
-    }
     if ((rc = s4f_bc_update_coeffs(c))) return rc;
     if ((rc = s4f_bc_evaluate(c))) return rc;
     if ((rc = d2d(c, c->Dprev.p, c->D.p, 3 * (size_t)c->ld))) return rc;
     if ((rc = s4f_halo_exchange(c, c->D.p, 3))) return rc;
     if ((rc = s4f_grad(c))) return rc;
+    if ((rc = s4f_kinematics(c))) return rc;                     // F, Finv, J of the finite-strain models (ctor, restart branch)
     if ((rc = s4f_assemble_matrix(c))) return rc;
     c->iCorr = 0;
     S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -356,6 +352,7 @@ int s4fgpu_op_grad(s4fgpu_handle c) {
     S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
     int rc = s4f_halo_exchange(c, c->D.p, 3); if (rc) return rc;
     rc = s4f_grad(c); if (rc) return rc;
+    rc = s4f_kinematics(c); if (rc) return rc;
     S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }

@@ -141,6 +141,7 @@ struct s4fgpu_ctx {
     DevBuf<double> rowK;              // [6*ld] per-row sums U (3), Vv (3) of the factored RHS
     DevBuf<double> V, rV;             // cell volumes [ld]
     DevBuf<int> faceEntry;            // [F] entry index of internal face f in its owner's row (-> lduMatrix upper())
+    DevBuf<int> procEntry;            // [G] entry index of processor-patch face g (ghost order) in its cell's row
 
     // ---- boundary faces (B-arrays, SoA) and boundary-cell lists ----
     DevBuf<int> bFaceCell, bKind;     // [B] ; bKind = S4F_BC_* of the face's patch

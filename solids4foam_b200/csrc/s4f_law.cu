@@ -386,6 +386,17 @@ int s4f_law_correct(s4fgpu_ctx* c) {
     return s4f_halo_exchange(c, c->sigma.p, 6);
 }
 
+// Solver-level kinematics of the total-Lagrangian models: F = I + gradD.T(), Finv, J and the flux tensor
+// J Finv & sigma (nonLinGeomTotalLagTotalDispSolid.C:225-232) from the current gradD and sigma.
+int s4f_kinematics(s4fgpu_ctx* c) {
+    if (c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP) return 0;
+    const int grid = s4f_grid(c->numSMs, c->N + c->B);
+    k_tl_flux_tensor<<<grid, S4F_BLOCK, 0, c->stream>>>(c->gradD.p, c->sigma.p, c->T9.p, c->Finv.p, c->Jt.p, c->N, c->bOff(), c->B, c->ld);
+    c->launches++;
+    S4F_CHECK_CUDA(c, cudaGetLastError());
+    return s4f_halo_exchange(c, c->T9.p, 9);
+}
+
 // solidModel::updateTotalFields -> neoHookeanElasticMisesPlastic::updateTotalFields :1526-1536
 int s4f_update_total_fields_impl(s4fgpu_ctx* c) {
     if (c->law.kind == S4F_LAW_NEO_HOOKEAN_MISES_PLASTIC) {

@@ -146,7 +146,7 @@ int s4f_build_rows(s4fgpu_ctx* c) {
         for (int k = 0; k < 6; k++) invDd[6 * (size_t)P + k] = r[k];
     }
 
-    std::vector<int> hCol(nE), hFaceEntry(std::max(F, 1), 0);
+    std::vector<int> hCol(nE), hFaceEntry(std::max(F, 1), 0), hProcEntry(std::max(G, 1), 0);
     std::vector<double> hW(nE, 1.0), hSf(3 * nE, 0.0), hLs(3 * nE, 0.0), hDn(nE, 0.0), hCorr;
     bool nonOrth = false;
     for (size_t i = 0; i < c->hCorr.size(); i++) if (std::fabs(c->hCorr[i]) > 1e-12) { nonOrth = true; break; }
@@ -165,6 +165,7 @@ int s4f_build_rows(s4fgpu_ctx* c) {
                 const double sg = rSign[e];
                 hCol[E] = rCol[e];
                 if (f < F && sg > 0) hFaceEntry[f] = (int)E;
+                if (f >= F && c->ghostOfFace[f - F] >= 0) hProcEntry[c->ghostOfFace[f - F] - N] = (int)E;
                 const bool bnd = (f >= F) && (c->ghostOfFace[f - F] < 0);
                 if (bnd) hW[E] = 0.0;
                 else hW[E] = (sg > 0) ? c->hW[f] : 1.0 - c->hW[f];
@@ -185,6 +186,7 @@ int s4f_build_rows(s4fgpu_ctx* c) {
     S4F_CHECK_CUDA(c, c->slicePtr.upload(slicePtr));
     S4F_CHECK_CUDA(c, c->col.upload(hCol));
     S4F_CHECK_CUDA(c, c->faceEntry.upload(hFaceEntry));
+    S4F_CHECK_CUDA(c, c->procEntry.upload(hProcEntry));
     S4F_CHECK_CUDA(c, c->eW.upload(hW));
     S4F_CHECK_CUDA(c, c->eSf.upload(hSf));
     S4F_CHECK_CUDA(c, c->eLs.upload(hLs));

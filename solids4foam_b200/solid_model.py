@@ -67,8 +67,13 @@ class SolidModel:
         except Exception:
             pass
 
-    def get(self, name: str) -> np.ndarray:
-        out = np.zeros(K.field_size(self.case.mesh, name))
+    def get(self, name: str, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Download a field into host memory (``out``: caller-owned buffer, e.g. pinned, of the field's shape)."""
+        shape = K.field_size(self.case.mesh, name)
+        if out is None:
+            out = np.empty(shape)
+        elif out.shape != tuple(shape) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError(f"out must be a C-contiguous float64 array of shape {shape}")
         self._check(self.L.s4fgpu_download(self.h, K.FIELD[name], K._dptr(out)))
         return out
 
