@@ -258,7 +258,8 @@ enum {
     S4F_KERNEL_RHS = 5,
     S4F_KERNEL_PCG_P = 6,      /* pA = rD rA + beta pA */
     S4F_KERNEL_PCG_XR = 7,     /* psi += alpha pA; rA -= alpha wA; residual sums */
-    S4F_KERNEL_GAMG_VCYCLE = 8 /* one application of the GAMG preconditioner (all levels) */
+    S4F_KERNEL_GAMG_VCYCLE = 8,/* one application of the GAMG preconditioner (all levels) */
+    S4F_KERNEL_GAMG_STEP0 = 9  /* the fine-level Chebyshev-Jacobi smoothing step of the V-cycle, alone */
 };
 int s4fgpu_time_kernel(s4fgpu_handle h, int kernel, int reps, int flushL2,
                        double* msPerLaunch, double* algoBytesPerLaunch);

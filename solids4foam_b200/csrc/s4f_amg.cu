@@ -325,6 +325,8 @@ struct Level {
 struct S4fAmg {
     virtual ~S4fAmg() {}
     virtual int apply(s4fgpu_ctx* c, const double* r3, double* z3) = 0;
+    virtual int step0(s4fgpu_ctx* c, const double* r3) = 0;   // one fine-level smoothing step alone (timing)
+    double step0Bytes = 0;
     std::vector<int> sizes;
     double bytesPerApply = 0;
     double setupSeconds = 0;
@@ -538,6 +540,17 @@ struct Hierarchy : S4fAmg {
         return 0;
     }
 
+    // the fine-level Chebyshev-Jacobi step kernel on its own (no halo): the dominant kernel of the V-cycle
+    int step0(s4fgpu_ctx* c, const double* r3) override {
+        Level<T>& L = *lv[0];
+        if (lv.size() < 2) return 0;
+        const int grid = step_grid(c, L);
+        k_amg_step<T, double, T, 0><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, L.rD.p, r3, L.x.p, L.d.p, L.x2.p, L.n, L.ld,
+                                                                            c->ld, L.ld, L.nSlices, (T)0.3, (T)0.5);
+        c->launches++;
+        return 0;
+    }
+
     int apply(s4fgpu_ctx* c, const double* r3, double* z3) override {
         int rc = cycle_level<double>(c, 0, r3, c->ld, z3, c->ld);
         if (rc) return rc;
@@ -601,6 +614,7 @@ int build(s4fgpu_ctx* c, std::vector<HostLevel>& H, const DistInfo& di) {
     S4F_CHECK_CUDA(c, A->denseInv.upload(inv));
     S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
     A->bytesPerApply = A->bytes_per_apply(c->ld);
+    A->step0Bytes = A->nnz[0] * (4 + sizeof(T)) + 0.125 * c->N + 3.0 * c->N * (8 + 5 * sizeof(T) + sizeof(T));   // col,a | b(fp64) x d dg rD in, d x' out
     c->amg = guard.release();
     return 0;
 }
@@ -791,6 +805,12 @@ int s4f_amg_info(s4fgpu_ctx* c, int* nLevels, int* sizes, int maxLevels, double*
     for (int i = 0; i < *nLevels && i < maxLevels; i++) sizes[i] = c->amg->sizes[i];
     *bytesPerApply = c->amg->bytesPerApply; *setupSeconds = c->amg->setupSeconds;
     return 0;
+}
+
+int s4f_amg_step0(s4fgpu_ctx* c, const double* r3, double* bytes) {
+    if (!c->amg) { c->err = "GAMG hierarchy missing"; return 1; }
+    if (bytes) *bytes = c->amg->step0Bytes;
+    return c->amg->step0(c, r3);
 }
 
 int s4f_amg_apply(s4fgpu_ctx* c, const double* r3, double* z3) {

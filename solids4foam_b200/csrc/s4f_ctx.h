@@ -222,6 +222,7 @@ int s4f_alloc_model_fields(s4fgpu_ctx* c);
 int s4f_upload_bc(s4fgpu_ctx* c);
 int s4f_amg_setup(s4fgpu_ctx* c);                                   // after s4f_assemble_matrix
 int s4f_amg_apply(s4fgpu_ctx* c, const double* r3, double* z3);     // z = M^-1 r, 3 components, stride ld
+int s4f_amg_step0(s4fgpu_ctx* c, const double* r3, double* bytes);
 void s4f_amg_destroy(s4fgpu_ctx* c);
 int s4f_amg_info(s4fgpu_ctx* c, int* nLevels, int* sizes, int maxLevels, double* bytesPerApply, double* setupSeconds);
 int s4f_download_upper(s4fgpu_ctx* c, double* hostUpper);           // lduMatrix upper() [F]

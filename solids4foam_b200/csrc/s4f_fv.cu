@@ -666,7 +666,7 @@ int s4f_relax_and_residual(s4fgpu_ctx* c, int iCorr) {
 
 // ---- timing of the face-loop kernels (bench.py roofline) ----------------------------------------
 int s4f_time_fv_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, double* msOut, double* bytesOut) {
-    if (kernel == S4F_KERNEL_GAMG_VCYCLE && !c->amgValid) {
+    if ((kernel == S4F_KERNEL_GAMG_VCYCLE || kernel == S4F_KERNEL_GAMG_STEP0) && !c->amgValid) {
         int rc = s4f_amg_setup(c); if (rc) return rc;
         c->amgValid = true;
     }
@@ -681,6 +681,7 @@ int s4f_time_fv_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, double
         if (kernel == S4F_KERNEL_GRAD) rc = s4f_grad(c);
         else if (kernel == S4F_KERNEL_LAW) rc = s4f_law_correct(c);
         else if (kernel == S4F_KERNEL_GAMG_VCYCLE) rc = s4f_amg_apply(c, c->rA.p, c->wA.p);
+        else if (kernel == S4F_KERNEL_GAMG_STEP0) rc = s4f_amg_step0(c, c->rA.p, nullptr);
         else rc = s4f_assemble_source(c);
         if (rc) return rc;
         S4F_CHECK_CUDA(c, cudaEventRecord(e1, c->stream));
@@ -693,6 +694,7 @@ int s4f_time_fv_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, double
     const double N = c->N, nnz = (double)c->nnzOff + (c->B - c->G);   // row entries incl. boundary faces
     if (kernel == S4F_KERNEL_GRAD) *bytesOut = 24 * N + nnz * (4 + 24) + 72 * N + 0.125 * N;                 // D, (col, ls), gradD out
     else if (kernel == S4F_KERNEL_LAW) *bytesOut = (72 + 48) * N;                                              // gradD in, sigma out (Hooke)
+    else if (kernel == S4F_KERNEL_GAMG_STEP0) { int rc = s4f_amg_step0(c, c->rA.p, bytesOut); if (rc) return rc; }
     else if (kernel == S4F_KERNEL_GAMG_VCYCLE) { int nl, sz[16]; double st; int rc = s4f_amg_info(c, &nl, sz, 16, bytesOut, &st); if (rc) return rc; }
     else *bytesOut = (24 + 48 + 72) * N + nnz * (4 + 24 + 8 + 8) + (48 + 8 + 24 + 0.125) * N;                   // D,sigma,gradD | col,u,c0,gamma | rowK, V, out
     return 0;

@@ -9,12 +9,12 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("precond", ["DIAGONAL", "GAMG"])
-def test_two_gpu_slab_decomposition_matches_oracle(precond):
+@pytest.mark.parametrize("precond,dims", [("DIAGONAL", "16 6 6"), ("GAMG", "16 6 6"), ("GAMG", "36 12 12")])
+def test_two_gpu_slab_decomposition_matches_oracle(precond, dims):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(HERE, "dist_gpu_check.py"), "16", "6", "6", precond]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+           "--master-port", "29517", os.path.join(HERE, "dist_gpu_check.py")] + dims.split() + [precond]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
