@@ -26,7 +26,7 @@ def main():
         g.outer_iteration()
     names = ["spmv3", "spmv1", "pcg_p", "pcg_xr", "pcg_iter", "grad", "rhs", "law"]
     if pre == K.PRECOND_GAMG:
-        names.append("gamg_vcycle")
+        names += ["gamg_vcycle", "gamg_step0"]
     for name in names:
         ms, by = g.time_kernel(name, reps=2, flush_l2=False)
         print(f"{name:9s} {ms:8.4f} ms  {by / ms / 1e6:8.1f} GB/s (under a profiler: not a bench value)")

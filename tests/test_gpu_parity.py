@@ -273,3 +273,63 @@ def test_notched_bar_mises_two_load_steps_match_oracle():
         ep_o = o.get("epsilonPEq")
         assert np.abs(g.get("epsilonPEq") - ep_o).max() < 1e-6 * max(ep_o.max(), 1e-30) + 1e-12
     assert ep_o.max() > 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# remaining options of the path: Aitken relaxation, Euler d2dt2, Gauss gradient, small-strain J2
+# ---------------------------------------------------------------------------------------------
+EXACT_PCG = dict(tolerance=1e-14, relTol=0.0, maxIter=3000)     # inner solves converged: outer iterates become deterministic
+
+
+def test_aitken_relaxation_matches_oracle():
+    """solidModel::relaxField, Aitken branch (solidModel.C:842-897), iterate by iterate."""
+    kw = dict(nx=8, ny=4, nz=4, L=1.0, relaxationMethod=K.RELAX_AITKEN, fieldRelaxD=0.8, **EXACT_PCG)
+    g, o, mesh = _pair(cases.cantilever, **kw)
+    for it in range(6):
+        sg, so = g.outer_iteration(), o.outer_iteration()
+        assert rel_l2(g.get("D"), o.get("D")) < 1e-8, it
+        assert abs(sg["relResidual"] - so["relResidual"]) < 1e-6 * so["relResidual"] + 1e-300
+
+
+def test_euler_d2dt2_time_steps_match_oracle():
+    """rho*fvm::d2dt2(D) with the Euler scheme: diagonal and old-time source terms over three time steps."""
+    kw = dict(nx=8, ny=3, nz=3, L=2.0, d2dt2Scheme=K.D2DT2_EULER, deltaT=2e-4, deltaT0=2e-4, nCorrectors=40,
+              g=(0.0, -9.81, 0.0), **EXACT_PCG)
+    g, o, mesh = _pair(cases.cantilever, **kw)
+    for step in range(3):
+        for s in (g, o):
+            s.new_timestep(2e-4)
+        sg, so = g.evolve(), o.evolve()
+        assert sg["nCorr"] == so["nCorr"]
+        assert rel_l2(g.get("D"), o.get("D")) < 1e-8, step
+        assert rel_l2(g.get("sigma"), o.get("sigma")) < 1e-7, step
+    assert np.abs(o.get("D")).max() > 0
+
+
+def test_gauss_gradient_evolve_matches_oracle():
+    kw = dict(nx=8, ny=6, nz=6, L=1.0, fieldRelaxD=0.9, nCorrectors=4000, gradScheme=K.GRAD_GAUSS_LINEAR, **TIGHT)
+    g, o, mesh = _pair(cases.cantilever, preconditioner=K.PRECOND_GAMG, **kw)
+    sg, so = g.evolve(), o.evolve()
+    assert sg["converged"] and so["converged"]
+    assert rel_l2(g.get("D"), o.get("D")) < SOLVE_TOL
+    assert rel_l2(g.get("sigma"), o.get("sigma")) < SOLVE_TOL
+
+
+def test_linear_elastic_mises_plastic_law_matches_oracle():
+    """linearElasticMisesPlastic (small-strain radial return, tabulated hardening -> per-cell Newton loop)."""
+    def case_fn(**kw):
+        c = cases.cantilever(nx=12, ny=4, nz=4, **kw)
+        c.law = K.mechanical_law("linearElasticMisesPlastic", rho=7800.0, E=200e9, nu=0.3, table=K.NECKING_BAR_TABLE)
+        return c
+    g, o, mesh = _pair(case_fn)
+    D = _finite_strain_D(mesh, 0.03)
+    for s in (g, o):
+        s.set("D", D)
+        s.initialise()
+        s.op_correct()
+    dl = o.get("DLambda")
+    assert (dl > 0).mean() > 0.1
+    assert np.abs(g.get("DLambda") - dl).max() < 1e-9 * dl.max()
+    assert rel_l2(g.get("sigma"), o.get("sigma")) < 1e-11
+    assert rel_l2(g.get("sigma_b"), o.get("sigma_b")) < 1e-11
+    assert rel_l2(g.get("epsilonPEq"), o.get("epsilonPEq")) < 1e-9
