@@ -103,7 +103,9 @@ enum {
     S4F_FIELD_GRAD_D_OLD = 17,   /* tensor [N] */
     S4F_FIELD_DEPSILON_P = 18,   /* symmTensor [N] */
     S4F_FIELD_TRACTION_GRADIENT_B = 19, /* vector [B]: fixedGradient gradient() of traction patches */
-    S4F_FIELD_EPSILON_P = 20     /* symmTensor [N] */
+    S4F_FIELD_EPSILON_P = 20,    /* symmTensor [N] */
+    S4F_FIELD_DD = 21,           /* vector [N]  displacement increment (incremental solid models only) */
+    S4F_FIELD_GRAD_DD = 22       /* tensor [N] */
 };
 
 /* ---- parameter blocks ---------------------------------------------------------------------- */

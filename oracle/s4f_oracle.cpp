@@ -130,7 +130,11 @@ struct s4f_oracle {
     // BC data (B-arrays)
     dvec bcValue, bcPressure, tracGrad;
     // vol fields: internal [0,N) then boundary [N,N+B)
-    dvec D, Dprev, Dold, DoldOld, gradD, gradDold, sigma, sigmaOld;
+    // D / gradD hold the SOLUTION field of the model: D for the total-displacement models, DD for the
+    // incremental ones (nonLinGeomTotalLagSolid solves DD: SM/nonLinGeomTotalLagSolid/...C:152-161); the
+    // incremental models keep the total displacement and its gradient in Dtot / gradDtot
+    // (D = D.oldTime() + DD :190, gradD = gradD.oldTime() + gradDD :196).
+    dvec D, Dprev, Dold, DoldOld, gradD, gradDold, sigma, sigmaOld, Dtot, gradDtot;
     dvec impK, impKf;              // impK (N+B), impKf (F+B)
     dvec Ft, Finv, Jt;             // solver-level F, Finv, J of the TL models
     // law history
@@ -155,6 +159,8 @@ struct s4f_oracle {
     ivec cellStart, faceStart, crossFaces;
 
     int NB() const { return N + B; }
+    bool incremental() const { return ctl.solidModel == S4F_MODEL_NONLIN_TL || ctl.solidModel == S4F_MODEL_NONLIN_UL; }
+    const dvec& gradForLaw() const { return incremental() ? gradDtot : gradD; }   // the registered "grad(D)"
 };
 
 namespace {
@@ -402,7 +408,7 @@ void lawLinearElastic(s4f_oracle& o) {
     const double mu = o.law.mu, K = o.law.K;
     S4FO_PAR_FOR
     for (int c = 0; c < n; c++) {
-        double e[6]; symm(&o.gradD[9 * c], e);
+        double e[6]; symm(&o.gradForLaw()[9 * c], e);
         for (int q = 0; q < 6; q++) o.epsilon[6 * c + q] = e[q];
         double sh = K * trS(e);
         o.sigmaHyd[c] = sh;
@@ -414,11 +420,13 @@ void lawLinearElastic(s4f_oracle& o) {
 }
 
 // mechanicalLaw::updateF, TL total displacement branch: F = I + gradD.T(); relF = F & inv(F.old)
-// ML/mechanicalLaw/mechanicalLaw.C:1130-1140
+// ML/mechanicalLaw/mechanicalLaw.C:1130-1140.  The incremental TL branch (:1097-1108) forms F = F.old + gradDD.T(),
+// which is the same tensor up to round-off because gradD = gradD.old + gradDD; the total form is used for both.
 void lawUpdateF(s4f_oracle& o) {
     const int n = o.NB();
+    const dvec& gD = o.gradForLaw();
     for (int c = 0; c < n; c++) {
-        double Ft[9]; transposeT(&o.gradD[9 * c], Ft);
+        double Ft[9]; transposeT(&gD[9 * c], Ft);
         Ft[0] += 1; Ft[4] += 1; Ft[8] += 1;
         for (int q = 0; q < 9; q++) o.lawF[9 * c + q] = Ft[q];
         double Fi[9]; invT(&o.lawFold[9 * c], Fi);
@@ -559,7 +567,7 @@ void lawLinearElasticMises(s4f_oracle& o) {
     const double mu = o.law.mu, K = o.law.K;
     double maxMagBE = 0;
     for (int c = 0; c < n; c++) {
-        symm(&o.gradD[9 * c], &o.epsilon[6 * c]);                         // updateEpsilon()
+        symm(&o.gradForLaw()[9 * c], &o.epsilon[6 * c]);                  // updateEpsilon()
         if (c < N) maxMagBE = std::max(maxMagBE, std::sqrt(magSqrS(&o.epsilon[6 * c])));
     }
     maxMagBE = std::max(maxMagBE, SMALL);
@@ -633,9 +641,10 @@ double lawResidual(const s4f_oracle& o) {
 // SM/nonLinGeomTotalLagTotalDispSolid/nonLinGeomTotalLagTotalDispSolid.C:225-232
 void updateKinematics(s4f_oracle& o) {
     const int n = o.NB();
+    const dvec& gD = o.gradForLaw();
     for (int c = 0; c < n; c++) {
         double* Fm = &o.Ft[9 * c];
-        transposeT(&o.gradD[9 * c], Fm); Fm[0] += 1; Fm[4] += 1; Fm[8] += 1;
+        transposeT(&gD[9 * c], Fm); Fm[0] += 1; Fm[4] += 1; Fm[8] += 1;
         invT(Fm, &o.Finv[9 * c]);
         o.Jt[c] = detT(Fm);
     }
@@ -953,7 +962,15 @@ bool convergedCheck(s4f_oracle& o, int iCorr, s4fgpu_stats* st) {
     return conv;
 }
 
-// one pass of the do-loop body, linGeomTotalDispSolid.C:135-192 / nonLinGeomTotalLagTotalDispSolid.C:195-236
+// incremental models: D = D.oldTime() + DD; gradD = gradD.oldTime() + gradDD  (nonLinGeomTotalLagSolid.C:190-196)
+void updateTotals(s4f_oracle& o, bool disp, bool grad) {
+    if (!o.incremental()) return;
+    if (disp) for (size_t i = 0; i < o.Dtot.size(); i++) o.Dtot[i] = o.Dold[i] + o.D[i];
+    if (grad) for (size_t i = 0; i < o.gradDtot.size(); i++) o.gradDtot[i] = o.gradDold[i] + o.gradD[i];
+}
+
+// one pass of the do-loop body, linGeomTotalDispSolid.C:135-192 / nonLinGeomTotalLagTotalDispSolid.C:195-236 /
+// nonLinGeomTotalLagSolid.C:147-223
 void outerIteration(s4f_oracle& o, int iCorr) {
     o.Dprev = o.D;                               // D().storePrevIter()
     bcUpdateCoeffs(o);                           // fvMatrix ctor -> updateCoeffs
@@ -962,7 +979,9 @@ void outerIteration(s4f_oracle& o, int iCorr) {
     solveSegregated(o, o.D.data(), o.source.data());
     bcEvaluate(o);                               // D.correctBoundaryConditions()
     relaxField(o, iCorr);
+    updateTotals(o, true, false);
     calcGrad(o);                                 // mechanical().grad(D, gradD)
+    updateTotals(o, false, true);
     if (o.ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP) updateKinematics(o);
     lawCorrect(o);                               // mechanical().correct(sigma)
 }
@@ -971,6 +990,7 @@ void allocFields(s4f_oracle& o) {
     const int n = o.NB();
     auto z = [&](dvec& v, int nc) { if ((int)v.size() != nc * n) v.assign((size_t)nc * n, 0.0); };
     z(o.D, 3); z(o.Dprev, 3); z(o.Dold, 3); z(o.DoldOld, 3); z(o.gradD, 9); z(o.gradDold, 9); z(o.sigma, 6); z(o.sigmaOld, 6);
+    z(o.Dtot, 3); z(o.gradDtot, 9);
     z(o.epsilon, 6); z(o.sigmaHyd, 1);
     if ((int)o.Ft.size() != 9 * n) {
         o.Ft.assign(9 * n, 0.0); o.Finv.assign(9 * n, 0.0); o.Jt.assign(n, 1.0);
@@ -1059,14 +1079,16 @@ static dvec* fieldPtr(s4f_oracle* o, int field, int& ncomp, int& off, int& count
     const int N = o->N, B = o->B, F = o->F;
     off = 0; count = N;
     switch (field) {
-        case S4F_FIELD_D: ncomp = 3; return &o->D;
+        case S4F_FIELD_D: ncomp = 3; return o->incremental() ? &o->Dtot : &o->D;
+        case S4F_FIELD_DD: ncomp = 3; return o->incremental() ? &o->D : nullptr;
+        case S4F_FIELD_GRAD_DD: ncomp = 9; return o->incremental() ? &o->gradD : nullptr;
         case S4F_FIELD_D_OLD: ncomp = 3; return &o->Dold;
         case S4F_FIELD_D_OLDOLD: ncomp = 3; return &o->DoldOld;
-        case S4F_FIELD_GRAD_D: ncomp = 9; return &o->gradD;
+        case S4F_FIELD_GRAD_D: ncomp = 9; return o->incremental() ? &o->gradDtot : &o->gradD;
         case S4F_FIELD_GRAD_D_OLD: ncomp = 9; return &o->gradDold;
         case S4F_FIELD_SIGMA: ncomp = 6; return &o->sigma;
-        case S4F_FIELD_D_B: ncomp = 3; off = N; count = B; return &o->D;
-        case S4F_FIELD_GRAD_D_B: ncomp = 9; off = N; count = B; return &o->gradD;
+        case S4F_FIELD_D_B: ncomp = 3; off = N; count = B; return o->incremental() ? &o->Dtot : &o->D;
+        case S4F_FIELD_GRAD_D_B: ncomp = 9; off = N; count = B; return o->incremental() ? &o->gradDtot : &o->gradD;
         case S4F_FIELD_SIGMA_B: ncomp = 6; off = N; count = B; return &o->sigma;
         case S4F_FIELD_SOURCE: ncomp = 3; return &o->source;
         case S4F_FIELD_DIAG: ncomp = 3; return &o->diagC;
@@ -1102,6 +1124,7 @@ int s4fo_initialise(s4f_oracle* o) {
     bcEvaluate(*o);
     o->Dprev = o->D;
     calcGrad(*o);
+    updateTotals(*o, false, true);
     if (o->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP) updateKinematics(*o);
     assembleMatrix(*o);
     return 0;
@@ -1109,7 +1132,10 @@ int s4fo_initialise(s4f_oracle* o) {
 
 int s4fo_new_timestep(s4f_oracle* o, double deltaT) {
     o->ctl.deltaT0 = o->ctl.deltaT; o->ctl.deltaT = deltaT;
-    o->DoldOld = o->Dold; o->Dold = o->D; o->gradDold = o->gradD; o->sigmaOld = o->sigma;
+    o->DoldOld = o->Dold;
+    if (o->incremental()) { o->Dold = o->Dtot; o->gradDold = o->gradDtot; }      // the total fields roll; DD keeps its value as the initial guess
+    else { o->Dold = o->D; o->gradDold = o->gradD; }
+    o->sigmaOld = o->sigma;
     o->lawFold = o->lawF; o->lawJold = o->lawJ; o->bEbarOld = o->bEbar;
     o->epsPOld = o->epsP; o->epsPEqOld = o->epsPEq; o->sigmaYOld = o->sigmaY;
     if (o->ctl.d2dt2Scheme != S4F_D2DT2_STEADY_STATE) o->matrixValid = false;
@@ -1143,7 +1169,7 @@ int s4fo_update_total_fields(s4f_oracle* o) {
     return 0;
 }
 
-int s4fo_op_grad(s4f_oracle* o) { calcGrad(*o); if (o->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP) updateKinematics(*o); return 0; }
+int s4fo_op_grad(s4f_oracle* o) { calcGrad(*o); updateTotals(*o, false, true); if (o->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP) updateKinematics(*o); return 0; }
 int s4fo_op_correct(s4f_oracle* o) { lawCorrect(*o); return 0; }
 int s4fo_op_assemble(s4f_oracle* o) { bcUpdateCoeffs(*o); assembleMatrix(*o); assembleSource(*o); return 0; }
 int s4fo_op_amul(s4f_oracle* o, int cmpt, const double* x, double* y) {

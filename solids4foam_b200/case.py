@@ -32,12 +32,13 @@ PRECOND_NONE, PRECOND_DIAGONAL, PRECOND_DIC, PRECOND_CHEBYSHEV, PRECOND_GAMG = 0
 
 FIELD = dict(D=0, D_old=1, D_oldOld=2, gradD=3, sigma=4, D_b=5, gradD_b=6, sigma_b=7, source=8, diag=9,
              upper=10, epsilonPEq=11, sigmaY=12, bEbar=13, DLambda=14, J=15, F=16, gradD_old=17,
-             DEpsilonP=18, tractionGradient_b=19, epsilonP=20)
+             DEpsilonP=18, tractionGradient_b=19, epsilonP=20, DD=21, gradDD=22)
 # (ncomp, 'N' | 'B' | 'F')
 FIELD_SHAPE = dict(D=(3, "N"), D_old=(3, "N"), D_oldOld=(3, "N"), gradD=(9, "N"), sigma=(6, "N"), D_b=(3, "B"),
                    gradD_b=(9, "B"), sigma_b=(6, "B"), source=(3, "N"), diag=(3, "N"), upper=(1, "F"),
                    epsilonPEq=(1, "N"), sigmaY=(1, "N"), bEbar=(6, "N"), DLambda=(1, "N"), J=(1, "N"), F=(9, "N"),
-                   gradD_old=(9, "N"), DEpsilonP=(6, "N"), tractionGradient_b=(3, "B"), epsilonP=(6, "N"))
+                   gradD_old=(9, "N"), DEpsilonP=(6, "N"), tractionGradient_b=(3, "B"), epsilonP=(6, "N"),
+                   DD=(3, "N"), gradDD=(9, "N"))
 
 MODEL_NAMES = {
     # reference TypeName -> (gpu TypeName registered by the plugin, enum)

@@ -57,7 +57,9 @@ int s4f_outer_iteration(s4fgpu_ctx* c, int iCorr) {
     if ((rc = s4f_solve_segregated(c, c->D.p, c->source.p))) return rc;          // DEqn.solve()
     if ((rc = s4f_bc_evaluate(c))) return rc;                                    // D.correctBoundaryConditions()
     if ((rc = s4f_relax_and_residual(c, iCorr))) return rc;                      // relaxField + residual reductions
+    if ((rc = s4f_update_totals(c, true, false))) return rc;                     // incremental: D = D.oldTime() + DD
     if ((rc = s4f_grad(c))) return rc;                                           // mechanical().grad(D, gradD)
+    if ((rc = s4f_update_totals(c, false, true))) return rc;                     // incremental: gradD = gradD.oldTime() + gradDD
     if ((rc = s4f_law_correct(c))) return rc;                                    // mechanical().correct(sigma)
     return 0;
 }
@@ -200,8 +202,12 @@ int s4fgpu_set_law(s4fgpu_handle c, const s4fgpu_law* law) {
 int s4fgpu_set_controls(s4fgpu_handle c, const s4fgpu_controls* ctl) {
     S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
     S4F_REQUIRE(c, ctl, "set_controls: null");
-    S4F_REQUIRE(c, ctl->solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP || ctl->solidModel == S4F_MODEL_NONLIN_TL_TOTAL_DISP,
-                "set_controls: this build implements linearGeometryTotalDisplacement and nonLinearGeometryTotalLagrangianTotalDisplacement");
+    S4F_REQUIRE(c, ctl->solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP || ctl->solidModel == S4F_MODEL_NONLIN_TL_TOTAL_DISP ||
+                   ctl->solidModel == S4F_MODEL_NONLIN_TL,
+                "set_controls: this build implements linearGeometryTotalDisplacement, nonLinearGeometryTotalLagrangianTotalDisplacement "
+                "and nonLinearGeometryTotalLagrangian (the updated-Lagrangian model needs mesh motion: not available)");
+    S4F_REQUIRE(c, ctl->solidModel != S4F_MODEL_NONLIN_TL || ctl->d2dt2Scheme == S4F_D2DT2_STEADY_STATE,
+                "set_controls: nonLinearGeometryTotalLagrangian is available with the steadyState d2dt2 scheme");
     S4F_REQUIRE(c, ctl->solver == S4F_SOLVER_PCG, "set_controls: only PCG (the momentum matrix is symmetric)");
     S4F_REQUIRE(c, ctl->d2dt2Scheme == S4F_D2DT2_STEADY_STATE || ctl->d2dt2Scheme == S4F_D2DT2_EULER, "set_controls: d2dt2 scheme steadyState or Euler");
     c->ctl = *ctl; c->ctlSet = true; c->matrixValid = false; c->amgValid = false;
@@ -231,14 +237,16 @@ int s4fgpu_set_bc(s4fgpu_handle c, int patch, int kind, const double* value, con
 static int field_lookup(s4fgpu_ctx* c, int field, double** p, int* ncomp, int* offset, int* count) {
     *offset = 0; *count = c->N;
     switch (field) {
-        case S4F_FIELD_D: *p = c->D.p; *ncomp = 3; break;
+        case S4F_FIELD_D: *p = c->incremental() ? c->Dtot.p : c->D.p; *ncomp = 3; break;
+        case S4F_FIELD_DD: *p = c->incremental() ? c->D.p : nullptr; *ncomp = 3; break;
+        case S4F_FIELD_GRAD_DD: *p = c->incremental() ? c->gradD.p : nullptr; *ncomp = 9; break;
         case S4F_FIELD_D_OLD: *p = c->Dold.p; *ncomp = 3; break;
         case S4F_FIELD_D_OLDOLD: *p = c->DoldOld.p; *ncomp = 3; break;
-        case S4F_FIELD_GRAD_D: *p = c->gradD.p; *ncomp = 9; break;
+        case S4F_FIELD_GRAD_D: *p = c->incremental() ? c->gradDtot.p : c->gradD.p; *ncomp = 9; break;
         case S4F_FIELD_GRAD_D_OLD: *p = c->gradDold.p; *ncomp = 9; break;
         case S4F_FIELD_SIGMA: *p = c->sigma.p; *ncomp = 6; break;
-        case S4F_FIELD_D_B: *p = c->D.p; *ncomp = 3; *offset = c->bOff(); *count = c->B; break;
-        case S4F_FIELD_GRAD_D_B: *p = c->gradD.p; *ncomp = 9; *offset = c->bOff(); *count = c->B; break;
+        case S4F_FIELD_D_B: *p = c->incremental() ? c->Dtot.p : c->D.p; *ncomp = 3; *offset = c->bOff(); *count = c->B; break;
+        case S4F_FIELD_GRAD_D_B: *p = c->incremental() ? c->gradDtot.p : c->gradD.p; *ncomp = 9; *offset = c->bOff(); *count = c->B; break;
         case S4F_FIELD_SIGMA_B: *p = c->sigma.p; *ncomp = 6; *offset = c->bOff(); *count = c->B; break;
         case S4F_FIELD_SOURCE: *p = c->source.p; *ncomp = 3; break;
         case S4F_FIELD_DIAG: *p = c->diagC.p; *ncomp = 3; break;
@@ -295,6 +303,7 @@ int s4fgpu_initialise(s4fgpu_handle c) {
     if ((rc = d2d(c, c->Dprev.p, c->D.p, 3 * (size_t)c->ld))) return rc;
     if ((rc = s4f_halo_exchange(c, c->D.p, 3))) return rc;
     if ((rc = s4f_grad(c))) return rc;
+    if ((rc = s4f_update_totals(c, false, true))) return rc;
     if ((rc = s4f_kinematics(c))) return rc;                     // F, Finv, J of the finite-strain models (ctor, restart branch)
     if ((rc = s4f_assemble_matrix(c))) return rc;
     c->iCorr = 0;
@@ -307,8 +316,13 @@ int s4fgpu_new_timestep(s4fgpu_handle c, double deltaT) {
     const size_t ld = c->ld;
     c->ctl.deltaT0 = c->ctl.deltaT; c->ctl.deltaT = deltaT;
     int rc = 0;
-    rc |= d2d(c, c->DoldOld.p, c->Dold.p, 3 * ld); rc |= d2d(c, c->Dold.p, c->D.p, 3 * ld);
-    rc |= d2d(c, c->gradDold.p, c->gradD.p, 9 * ld); rc |= d2d(c, c->sigmaOld.p, c->sigma.p, 6 * ld);
+    rc |= d2d(c, c->DoldOld.p, c->Dold.p, 3 * ld);
+    if (c->incremental()) {     // the total fields roll; DD keeps its value as the initial guess of the next step
+        rc |= d2d(c, c->Dold.p, c->Dtot.p, 3 * ld); rc |= d2d(c, c->gradDold.p, c->gradDtot.p, 9 * ld);
+    } else {
+        rc |= d2d(c, c->Dold.p, c->D.p, 3 * ld); rc |= d2d(c, c->gradDold.p, c->gradD.p, 9 * ld);
+    }
+    rc |= d2d(c, c->sigmaOld.p, c->sigma.p, 6 * ld);
     if (c->lawF.p) { rc |= d2d(c, c->lawFold.p, c->lawF.p, 9 * ld); rc |= d2d(c, c->lawJold.p, c->lawJ.p, ld); }
     if (c->bEbar.p) {
         rc |= d2d(c, c->bEbarOld.p, c->bEbar.p, 6 * ld); rc |= d2d(c, c->epsPOld.p, c->epsP.p, 6 * ld);
@@ -352,6 +366,7 @@ int s4fgpu_op_grad(s4fgpu_handle c) {
     S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
     int rc = s4f_halo_exchange(c, c->D.p, 3); if (rc) return rc;
     rc = s4f_grad(c); if (rc) return rc;
+    rc = s4f_update_totals(c, false, true); if (rc) return rc;
     rc = s4f_kinematics(c); if (rc) return rc;
     S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;

@@ -160,6 +160,9 @@ struct s4fgpu_ctx {
     // ---- fields (SoA, ld per component) ----
     DevBuf<double> D, Dprev, Dold, DoldOld;       // 3*ld
     DevBuf<double> gradD, gradDold;               // 9*ld
+    // D / gradD hold the SOLUTION field: D for the total-displacement models, DD for the incremental ones
+    // (nonLinGeomTotalLagSolid.C:152-161), which keep D = D.oldTime() + DD and gradD = gradD.oldTime() + gradDD here
+    DevBuf<double> Dtot, gradDtot;                // 3*ld, 9*ld (incremental models only)
     DevBuf<double> sigma, sigmaOld;               // 6*ld
     DevBuf<double> impK;                          // ld
     DevBuf<double> T9;                            // 9*ld: J*Finv & sigma (TL)  [cells + boundary]
@@ -193,6 +196,8 @@ struct s4fgpu_ctx {
     long long totalInner = 0;
     s4fgpu_stats last{};
 
+    bool incremental() const { return ctl.solidModel == S4F_MODEL_NONLIN_TL || ctl.solidModel == S4F_MODEL_NONLIN_UL; }
+    const double* gradForLaw() const { return incremental() ? gradDtot.p : gradD.p; }   // the registered "grad(D)"
     int NT() const { return N + G + B; }
     int bOff() const { return N + G; }
 };
@@ -208,6 +213,7 @@ int s4f_bc_evaluate(s4fgpu_ctx* c);
 int s4f_relax_and_residual(s4fgpu_ctx* c, int iCorr);
 int s4f_grad(s4fgpu_ctx* c);
 int s4f_kinematics(s4fgpu_ctx* c);
+int s4f_update_totals(s4fgpu_ctx* c, bool disp, bool grad);
 int s4f_law_correct(s4fgpu_ctx* c);
 int s4f_solve_segregated(s4fgpu_ctx* c, double* psi, const double* source);   // device SoA pointers
 int s4f_halo_exchange(s4fgpu_ctx* c, double* field, int ncomp);

@@ -122,14 +122,16 @@ __global__ void k_diag_boundary(const int* __restrict__ bcCells, const int* __re
 __global__ void k_bc_update(const int* __restrict__ bKind, const double* __restrict__ bN, const double* __restrict__ bcValue,
                             const double* __restrict__ bcPressure, const double* __restrict__ impK, const double* __restrict__ sigma,
                             const double* __restrict__ gradD, const double* __restrict__ Finv, double* __restrict__ tracGrad,
-                            double* __restrict__ D, int B, int bOff, int ld, int TL) {
+                            double* __restrict__ D, const double* __restrict__ DoldIncr /* null unless the field is DD */, int B,
+                            int bOff, int ld, int TL) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int kind = bKind[b];
     const size_t j = (size_t)bOff + b;
     if (kind == S4F_BC_FIXED_DISPLACEMENT) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) D[(size_t)c * ld + j] = bcValue[(size_t)c * B + b];
+        for (int c = 0; c < 3; c++)      // DD field: disp -= Dold.boundaryField()  (fixedDisplacement...C:279-287)
+            D[(size_t)c * ld + j] = bcValue[(size_t)c * B + b] - (DoldIncr ? DoldIncr[(size_t)c * ld + j] : 0.0);
     } else if (kind == S4F_BC_SOLID_TRACTION) {
         double n[3], t[3], g[9], s[6];
 #pragma unroll
@@ -580,7 +582,8 @@ int s4f_bc_update_coeffs(s4fgpu_ctx* c) {
     if (c->B == 0) return 0;
     const int TL = c->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP;
     k_bc_update<<<(c->B + 127) / 128, 128, 0, c->stream>>>(c->bKind.p, c->bN.p, c->bcValue.p, c->bcPressure.p, c->impK.p, c->sigma.p, c->gradD.p,
-                                                          c->Finv.p, c->tracGrad.p, c->D.p, c->B, c->bOff(), c->ld, TL);
+                                                          c->Finv.p, c->tracGrad.p, c->D.p, c->incremental() ? c->Dold.p : nullptr, c->B,
+                                                          c->bOff(), c->ld, TL);
     c->launches++;
     return 0;
 }
@@ -645,6 +648,23 @@ int s4f_grad(s4fgpu_ctx* c) {
     }
     S4F_CHECK_CUDA(c, cudaGetLastError());
     return s4f_halo_exchange(c, c->gradD.p, 9);
+}
+
+namespace {
+__global__ void k_sum2(double* __restrict__ out, const double* __restrict__ a, const double* __restrict__ b, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + b[i];
+}
+}  // namespace
+
+// incremental models: D = D.oldTime() + DD; gradD = gradD.oldTime() + gradDD  (nonLinGeomTotalLagSolid.C:190-196)
+int s4f_update_totals(s4fgpu_ctx* c, bool disp, bool grad) {
+    if (!c->incremental()) return 0;
+    const long long ld = c->ld;
+    if (disp) { k_sum2<<<(unsigned)((3 * ld + 255) / 256), 256, 0, c->stream>>>(c->Dtot.p, c->Dold.p, c->D.p, 3 * ld); c->launches++; }
+    if (grad) { k_sum2<<<(unsigned)((9 * ld + 255) / 256), 256, 0, c->stream>>>(c->gradDtot.p, c->gradDold.p, c->gradD.p, 9 * ld); c->launches++; }
+    S4F_CHECK_CUDA(c, cudaGetLastError());
+    return 0;
 }
 
 int s4f_relax_and_residual(s4fgpu_ctx* c, int iCorr) {

@@ -342,21 +342,22 @@ int s4f_law_correct(s4fgpu_ctx* c) {
     const int N = c->N, B = c->B, bOff = c->bOff(), ld = c->ld;
     const int grid = s4f_grid(c->numSMs, N + B), gridN = s4f_grid(c->numSMs, N);
     const s4fgpu_law& L = c->law;
+    const double* gD = c->gradForLaw();
     if (L.kind == S4F_LAW_LINEAR_ELASTIC) {
         S6 s0; for (int q = 0; q < 6; q++) s0.v[q] = L.sigma0[q];
-        k_law_linear_elastic<<<grid, S4F_BLOCK, 0, c->stream>>>(c->gradD.p, c->sigma.p, N, bOff, B, ld, L.mu, L.K, s0);
+        k_law_linear_elastic<<<grid, S4F_BLOCK, 0, c->stream>>>(gD, c->sigma.p, N, bOff, B, ld, L.mu, L.K, s0);
         c->launches++;
     } else if (L.kind == S4F_LAW_NEO_HOOKEAN_ELASTIC) {
-        k_law_neo_hookean<<<grid, S4F_BLOCK, 0, c->stream>>>(c->gradD.p, c->sigma.p, c->lawJ.p, N, bOff, B, ld, L.mu, L.K);
+        k_law_neo_hookean<<<grid, S4F_BLOCK, 0, c->stream>>>(gD, c->sigma.p, c->lawJ.p, N, bOff, B, ld, L.mu, L.K);
         c->launches++;
     } else if (L.kind == S4F_LAW_NEO_HOOKEAN_MISES_PLASTIC) {
         HardeningTable T = make_table(L);
         if (T.n > 2) {
-            k_mises_max_be<<<gridN, S4F_BLOCK, 0, c->stream>>>(c->gradD.p, c->lawFold.p, c->lawJold.p, c->bEbarOld.p, N, ld, c->outS.p, c->partials.p, c->ticket.p);
+            k_mises_max_be<<<gridN, S4F_BLOCK, 0, c->stream>>>(gD, c->lawFold.p, c->lawJold.p, c->bEbarOld.p, N, ld, c->outS.p, c->partials.p, c->ticket.p);
             c->launches++;
             if (c->nRanks > 1) S4F_CHECK_NCCL(c, ncclAllReduce(&((OuterScalars*)c->outS.p)->maxMagBE, &((OuterScalars*)c->outS.p)->maxMagBE, 1, ncclDouble, ncclMax, c->comm, c->stream));
         }
-        MisesPtrs p{c->gradD.p, c->lawFold.p, c->lawJold.p, c->bEbarOld.p, c->sigmaY.p, c->epsPEq.p, c->lawF.p, c->lawJ.p, c->bEbar.p, c->sigma.p,
+        MisesPtrs p{gD, c->lawFold.p, c->lawJold.p, c->bEbarOld.p, c->sigmaY.p, c->epsPEq.p, c->lawF.p, c->lawJ.p, c->bEbar.p, c->sigma.p,
                     c->DSigmaY.p, c->DEpsPEq.p, c->DEpsP.p, c->DEpsPprev.p, c->DLambda.p, c->plasticN.p};
         k_law_mises<<<grid, S4F_BLOCK, 0, c->stream>>>(p, N, bOff, B, ld, L.mu, L.K, c->Hp, L.updateBEbarConsistent, L.DEpsilonPRelax, T, c->outS.p,
                                                       c->partials.p, c->ticket.p);
@@ -365,11 +366,11 @@ int s4f_law_correct(s4fgpu_ctx* c) {
     } else if (L.kind == S4F_LAW_LINEAR_ELASTIC_MISES_PLASTIC) {
         HardeningTable T = make_table(L);
         if (T.n > 2) {
-            k_lin_mises_max_eps<<<gridN, S4F_BLOCK, 0, c->stream>>>(c->gradD.p, N, ld, c->outS.p, c->partials.p, c->ticket.p);
+            k_lin_mises_max_eps<<<gridN, S4F_BLOCK, 0, c->stream>>>(gD, N, ld, c->outS.p, c->partials.p, c->ticket.p);
             c->launches++;
             if (c->nRanks > 1) S4F_CHECK_NCCL(c, ncclAllReduce(&((OuterScalars*)c->outS.p)->maxMagBE, &((OuterScalars*)c->outS.p)->maxMagBE, 1, ncclDouble, ncclMax, c->comm, c->stream));
         }
-        LinMisesPtrs p{c->gradD.p, c->epsPOld.p, c->sigmaYOld.p, c->epsPEqOld.p, c->epsilon.p, c->sigma.p, c->sigmaY.p, c->DSigmaY.p, c->epsPEq.p,
+        LinMisesPtrs p{gD, c->epsPOld.p, c->sigmaYOld.p, c->epsPEqOld.p, c->epsilon.p, c->sigma.p, c->sigmaY.p, c->DSigmaY.p, c->epsPEq.p,
                        c->DEpsPEq.p, c->epsP.p, c->DEpsP.p, c->DEpsPprev.p, c->DLambda.p, c->plasticN.p};
         k_law_lin_mises<<<grid, S4F_BLOCK, 0, c->stream>>>(p, N, bOff, B, ld, L.mu, L.K, c->Hp, T, c->outS.p, c->partials.p, c->ticket.p);
         c->launches++;
@@ -379,7 +380,7 @@ int s4f_law_correct(s4fgpu_ctx* c) {
     }
     S4F_CHECK_CUDA(c, cudaGetLastError());
     if (c->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP) {
-        k_tl_flux_tensor<<<grid, S4F_BLOCK, 0, c->stream>>>(c->gradD.p, c->sigma.p, c->T9.p, c->Finv.p, c->Jt.p, N, bOff, B, ld);
+        k_tl_flux_tensor<<<grid, S4F_BLOCK, 0, c->stream>>>(gD, c->sigma.p, c->T9.p, c->Finv.p, c->Jt.p, N, bOff, B, ld);
         c->launches++;
         return s4f_halo_exchange(c, c->T9.p, 9);
     }
@@ -391,7 +392,7 @@ int s4f_law_correct(s4fgpu_ctx* c) {
 int s4f_kinematics(s4fgpu_ctx* c) {
     if (c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP) return 0;
     const int grid = s4f_grid(c->numSMs, c->N + c->B);
-    k_tl_flux_tensor<<<grid, S4F_BLOCK, 0, c->stream>>>(c->gradD.p, c->sigma.p, c->T9.p, c->Finv.p, c->Jt.p, c->N, c->bOff(), c->B, c->ld);
+    k_tl_flux_tensor<<<grid, S4F_BLOCK, 0, c->stream>>>(c->gradForLaw(), c->sigma.p, c->T9.p, c->Finv.p, c->Jt.p, c->N, c->bOff(), c->B, c->ld);
     c->launches++;
     S4F_CHECK_CUDA(c, cudaGetLastError());
     return s4f_halo_exchange(c, c->T9.p, 9);

@@ -28,6 +28,8 @@ class SolidModel:
         "linearGeometryTotalDisplacement": K.MODEL_LIN_GEOM_TOTAL_DISP,
         "gpuNonLinearGeometryTotalLagrangianTotalDisplacement": K.MODEL_NONLIN_TL_TOTAL_DISP,
         "nonLinearGeometryTotalLagrangianTotalDisplacement": K.MODEL_NONLIN_TL_TOTAL_DISP,
+        "gpuNonLinearGeometryTotalLagrangian": K.MODEL_NONLIN_TL,
+        "nonLinearGeometryTotalLagrangian": K.MODEL_NONLIN_TL,
     }
 
     @classmethod

@@ -333,3 +333,22 @@ def test_linear_elastic_mises_plastic_law_matches_oracle():
     assert rel_l2(g.get("sigma"), o.get("sigma")) < 1e-11
     assert rel_l2(g.get("sigma_b"), o.get("sigma_b")) < 1e-11
     assert rel_l2(g.get("epsilonPEq"), o.get("epsilonPEq")) < 1e-9
+
+
+def test_incremental_tl_model_two_load_steps_match_oracle():
+    """nonLinearGeometryTotalLagrangian: the DD solver (nonLinGeomTotalLagSolid.C:125-260) over two load steps."""
+    kw = dict(nx=8, ny=4, nz=4, L=2.0, traction=(0.0, 0.0, 0.0), fieldRelaxD=0.9, nCorrectors=8000,
+              solidModel=K.MODEL_NONLIN_TL, **TIGHT)
+    g, o, mesh = _pair(cases.neo_hookean_cantilever, preconditioner=K.PRECOND_GAMG, **kw)
+    n = mesh.patch("loaded").size
+    for step, t in enumerate((-4e3, -8e3)):
+        tr = np.zeros((n, 3)); tr[:, 1] = t
+        for s in (g, o):
+            s.new_timestep(1.0)
+            s.set_bc("loaded", K.solidTraction(tr))
+        sg, so = g.evolve(), o.evolve()
+        assert sg["converged"] and so["converged"], (step, sg, so)
+        assert rel_l2(g.get("D"), o.get("D")) < SOLVE_TOL
+        assert rel_l2(g.get("DD"), o.get("DD")) < 5 * SOLVE_TOL
+        assert rel_l2(g.get("sigma"), o.get("sigma")) < SOLVE_TOL
+    assert np.abs(o.get("D")[:, 1]).max() > 0.08

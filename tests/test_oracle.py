@@ -433,3 +433,29 @@ def test_neo_hookean_tl_small_load_matches_linear_elastic():
     sa, sb = a.evolve(), b.evolve()
     assert sa["converged"] and sb["converged"]
     assert rel_l2(b.get("D"), a.get("D")) < 1e-4
+
+
+def test_incremental_and_total_tl_models_reach_the_same_equilibrium():
+    """nonLinearGeometryTotalLagrangian (solves DD, nonLinGeomTotalLagSolid.C:152-161) and
+    ...TotalDisplacement (solves D, nonLinGeomTotalLagTotalDispSolid.C:201-209) discretise the same momentum
+    balance; without the Rhie-Chow term (which smooths D in one and DD in the other) the converged fields of a
+    two-step loading must coincide."""
+    tight = dict(solutionTolerance=1e-10, alternativeTolerance=1e-10, tolerance=1e-13)
+    kw = dict(nx=8, ny=4, nz=4, L=2.0, fieldRelaxD=0.9, nCorrectors=20000, preconditioner=K.PRECOND_DIC,
+              stabilisation=K.STAB_NONE, **tight)
+    res = {}
+    for model in (K.MODEL_NONLIN_TL_TOTAL_DISP, K.MODEL_NONLIN_TL):
+        c = cases.neo_hookean_cantilever(traction=(0.0, 0.0, 0.0), solidModel=model, **kw)
+        o = OracleSolid(c)
+        n = c.mesh.patch("loaded").size
+        for t in (-4e3, -8e3):
+            tr = np.zeros((n, 3)); tr[:, 1] = t
+            o.new_timestep(1.0)
+            o.set_bc("loaded", K.solidTraction(tr))
+            st = o.evolve()
+            assert st["converged"]
+        res[model] = (o.get("D"), o.get("sigma"))
+        if model == K.MODEL_NONLIN_TL:
+            assert 0.3 < np.abs(o.get("DD")).max() / np.abs(o.get("D")).max() < 0.7     # the increment of the second step
+    a, b = res[K.MODEL_NONLIN_TL_TOTAL_DISP], res[K.MODEL_NONLIN_TL]
+    assert rel_l2(b[0], a[0]) < 1e-6 and rel_l2(b[1], a[1]) < 1e-6
