@@ -52,6 +52,23 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic(kernel_prefix, n_cells):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the fine-level launch of a kernel, from the
+    committed ncu --set full capture (profiles/r1c_ncu_dram_traffic.json); None when the capture is of another workload."""
+    p = os.path.join(ROOT, "profiles", "r1c_ncu_dram_traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f)
+        if t.get("cells") != n_cells:
+            return None, None
+        for name, launches in t["kernels"].items():
+            if name.startswith(kernel_prefix):
+                return float(launches[0]["dram_bytes"]), "profiles/r1c_ncu_dram_traffic.json (" + name + ", launch %d)" % launches[0]["launch"]
+    except Exception:
+        pass
+    return None, None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -258,7 +275,13 @@ def main():
     dom_name = {"gamg_step0": "k_amg_step (fine-level Chebyshev-Jacobi step of the GAMG V-cycle: 3-component SELL-32 SpMV + update; "
                               "4 launches per PCG iteration, the largest share of the step)",
                 "spmv3": "k_amul3 (3-component SELL-32 SpMV + dot)"}[dom]
-    roof = dict(bound="hbm", achieved=kern[dom]["gbs"], peak=peak, unit="GB/s", frac=kern[dom]["frac"], traffic=None,
+    traffic, traffic_src = (None, None)
+    if world == 1:
+        pref = {"gamg_step0": "k_amg_step<float" if args.precond == "gamg32" else "k_amg_step<double, double, double, 0>",
+                "spmv3": "k_amul3"}[dom]
+        traffic, traffic_src = ncu_traffic(pref, N)
+    roof = dict(bound="hbm", achieved=kern[dom]["gbs"], peak=peak, unit="GB/s", frac=kern[dom]["frac"], traffic=traffic,
+                traffic_source=traffic_src,
                 kernel=dom_name, peak_source=peak_src, algo_bytes_per_launch=kern[dom]["algo_bytes"], launch_ms=kern[dom]["ms"],
                 l2="inputs (matrix+vectors >= 1.2 GB at 8M cells) exceed the 126 MB L2; no flush needed",
                 spmv3=dict(achieved=kern["spmv3"]["gbs"], frac=kern["spmv3"]["frac"], launch_ms=kern["spmv3"]["ms"]))
