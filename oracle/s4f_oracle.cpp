@@ -135,6 +135,8 @@ struct s4f_oracle {
     // incremental models keep the total displacement and its gradient in Dtot / gradDtot
     // (D = D.oldTime() + DD :190, gradD = gradD.oldTime() + gradDD :196).
     dvec D, Dprev, Dold, DoldOld, gradD, gradDold, sigma, sigmaOld, Dtot, gradDtot;
+    dvec Dooo, Doooo;              // third / fourth old-time level (backward d2dt2 only)
+    int timeIndex = 0;             // number of new_timestep() calls (runTime.timeIndex())
     dvec impK, impKf;              // impK (N+B), impKf (F+B)
     dvec Ft, Finv, Jt;             // solver-level F, Finv, J of the TL models
     // law history
@@ -650,6 +652,41 @@ void updateKinematics(s4f_oracle& o) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// rho*fvm::d2dt2(D) as "diag coefficient * V" and "V * (h1 D.o + h2 D.oo + h3 D.ooo + h4 D.oooo)".
+//  Euler   [OF-ext] EulerD2dt2Scheme::fvmD2dt2 (variable deltaT form)
+//  backward  numerics/backwardD2dt2Scheme/backwardD2dt2Scheme.C:309-395: fvm = coefft*rho*rDeltaT*
+//    backwardDdt.fvmDdt(D); source += rDeltaT*rho*V*(coefft0*backwardDdt.fvcDdt(D.o) - coefft00*
+//    backwardDdt.fvcDdt(D.oo)), coefficients :350-356 with deltaT0_(vf) = GREAT while D.o and D.oo carry the
+//    same time index (:48-68), i.e. during the first time step; constant deltaT only (:316-322).
+//    [OF-ext] backwardDdtScheme: fvmDdt diag = b rDeltaT V, source = rDeltaT V (b0 D.o - b00 D.oo);
+//    fvcDdt(X) = rDeltaT (b X - b0 X.o + b00 X.oo), b = 1.5, b0 = 2, b00 = 0.5 at constant deltaT (D is
+//    constructed with two old-time levels, solidModel.C:1247).  The levels D.ooo and D.oooo that the nested
+//    fvcDdt calls reach are created by GeometricField::oldTime() as copies of D.oo at the first evaluation.
+// ------------------------------------------------------------------------------------------------
+struct D2dt2Coeffs { double diag, h[4]; };
+D2dt2Coeffs d2dt2Coeffs(const s4fgpu_controls& ctl, double rho, int timeIndex) {
+    D2dt2Coeffs k{0, {0, 0, 0, 0}};
+    const double dt = ctl.deltaT, dt0 = ctl.deltaT0 > 0 ? ctl.deltaT0 : dt;
+    if (ctl.d2dt2Scheme == S4F_D2DT2_EULER) {
+        const double coefft = (dt + dt0) / (2 * dt), coefft00 = (dt + dt0) / (2 * dt0), rDeltaT2 = 4.0 / ((dt + dt0) * (dt + dt0));
+        k.diag = coefft * rDeltaT2 * rho;
+        k.h[0] = rDeltaT2 * rho * (coefft + coefft00); k.h[1] = -rDeltaT2 * rho * coefft00;
+    } else if (ctl.d2dt2Scheme == S4F_D2DT2_BACKWARD) {
+        const bool first = timeIndex <= 1;            // deltaT0_(vf) == GREAT
+        const double c = first ? 1.0 : 1.0 + dt / (dt + dt0), c00 = first ? 0.0 : dt * dt / (dt0 * (dt + dt0)), c0 = c + c00;
+        const double b = 1.0 + dt / (dt + dt0), b00 = dt * dt / (dt0 * (dt + dt0)), b0 = b + b00;
+        const double r = rho / (dt * dt);
+        k.diag = r * c * b;
+        k.h[0] = r * (c * b0 + c0 * b);
+        k.h[1] = r * (-c * b00 - c0 * b0 - c00 * b);
+        k.h[2] = r * (c0 * b00 + c00 * b0);
+        k.h[3] = -r * c00 * b00;
+    }
+    return k;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Momentum equation  (SM/linGeomTotalDispSolid/linGeomTotalDispSolid.C:141-149)
 //
@@ -672,11 +709,9 @@ void assembleMatrix(s4f_oracle& o) {
         double a = o.impKf[f] * o.nod[f] * o.magSf[f];
         o.upper[f] = -a; o.diag[o.own[f]] += a; o.diag[o.nei[f]] += a;
     }
-    // d2dt2: [OF-ext] EulerD2dt2Scheme::fvmD2dt2 (variable deltaT form)
-    if (o.ctl.d2dt2Scheme == S4F_D2DT2_EULER) {
-        double dt = o.ctl.deltaT, dt0 = o.ctl.deltaT0 > 0 ? o.ctl.deltaT0 : dt;
-        double coefft = (dt + dt0) / (2 * dt), rDeltaT2 = 4.0 / ((dt + dt0) * (dt + dt0));
-        for (int c = 0; c < N; c++) o.diag[c] += coefft * rDeltaT2 * o.V[c] * o.law.rho;
+    if (o.ctl.d2dt2Scheme != S4F_D2DT2_STEADY_STATE) {
+        const D2dt2Coeffs k = d2dt2Coeffs(o.ctl, o.law.rho, o.timeIndex);
+        for (int c = 0; c < N; c++) o.diag[c] += k.diag * o.V[c];
     }
     for (int p = 0; p < o.nPatches; p++) for (int i = 0; i < o.pSize[p]; i++) {
         int b = o.pStart[p] + i, f = F + b;
@@ -702,12 +737,14 @@ void assembleSource(s4f_oracle& o) {
     const bool TL = (o.ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP);
     o.source.assign(3 * N, 0.0);
     dvec& s = o.source;
-    // d2dt2 source (Euler): rDeltaT2*V*rho*((coefft+coefft00)*D.old - coefft00*D.oldOld)
-    if (o.ctl.d2dt2Scheme == S4F_D2DT2_EULER) {
-        double dt = o.ctl.deltaT, dt0 = o.ctl.deltaT0 > 0 ? o.ctl.deltaT0 : dt;
-        double coefft = (dt + dt0) / (2 * dt), coefft00 = (dt + dt0) / (2 * dt0), rDeltaT2 = 4.0 / ((dt + dt0) * (dt + dt0));
+    // d2dt2 old-time terms
+    if (o.ctl.d2dt2Scheme != S4F_D2DT2_STEADY_STATE) {
+        const D2dt2Coeffs k = d2dt2Coeffs(o.ctl, o.law.rho, o.timeIndex);
+        const bool deep = o.ctl.d2dt2Scheme == S4F_D2DT2_BACKWARD && o.timeIndex > 1;   // before: D.ooo = D.oooo = D.oo (copies)
+        const dvec& D3 = deep ? o.Dooo : o.DoldOld;
+        const dvec& D4 = deep ? o.Doooo : o.DoldOld;
         for (int c = 0; c < N; c++) for (int q = 0; q < 3; q++)
-            s[3 * c + q] += rDeltaT2 * o.V[c] * o.law.rho * ((coefft + coefft00) * o.Dold[3 * c + q] - coefft00 * o.DoldOld[3 * c + q]);
+            s[3 * c + q] += o.V[c] * (k.h[0] * o.Dold[3 * c + q] + k.h[1] * o.DoldOld[3 * c + q] + k.h[2] * D3[3 * c + q] + k.h[3] * D4[3 * c + q]);
     }
     // - V*fvc::laplacian(impKf, D): compact part, face flux impKf*magSf*delta*(D_N - D_P)
     forAllInternalFaces(o, [&](int f) {
@@ -897,6 +934,81 @@ SolverPerf solvePCG(s4f_oracle& o, const double* diag, double* psi, const double
     return perf;
 }
 
+
+// [OF-ext] PBiCGStab::scalarSolve (van der Vorst's preconditioned BiCGStab as OpenFOAM states it: the
+// residual after the first half step, sA, is tested for convergence and ends the solve with psi += alpha yA;
+// omega = (tA.sA)/(tA.tA); checkSingularity is applied to |rA0.rA| and |omega| un-normalised).  Selected with
+// fvSolution "solver PBiCGStab" (12x PBiCG / 1x PBiCGStab in the tutorials).
+SolverPerf solvePBiCGStab(s4f_oracle& o, const double* diag, double* psi, const double* source) {
+    const int N = o.N, F = o.F;
+    SolverPerf perf{0, 0, 0};
+    dvec pA(N, 0.0), yA(N), rA(N), sumA(N);
+    Amul(o, diag, psi, yA.data());
+    for (int c = 0; c < N; c++) rA[c] = source[c] - yA[c];
+    for (int c = 0; c < N; c++) sumA[c] = diag[c];
+    for (int f = 0; f < F; f++) { sumA[o.own[f]] += o.upper[f]; sumA[o.nei[f]] += o.upper[f]; }
+    double avg = 0; for (int c = 0; c < N; c++) avg += psi[c]; avg /= N;
+    double nf = 0;
+    for (int c = 0; c < N; c++) { double t = sumA[c] * avg; nf += std::fabs(yA[c] - t) + std::fabs(source[c] - t); }
+    nf += 1e-20;
+    double sm = 0; for (int c = 0; c < N; c++) sm += std::fabs(rA[c]);
+    perf.initRes = sm / nf; perf.finalRes = perf.initRes;
+    auto converged = [&](double fr) { return fr < o.ctl.tolerance || (o.ctl.relTol > 1e-20 && fr < o.ctl.relTol * perf.initRes); };
+    if (converged(perf.finalRes)) return perf;
+    int pk = o.ctl.preconditioner;
+    if (pk == S4F_PRECOND_CHEBYSHEV) pk = S4F_PRECOND_DIAGONAL;
+    if (pk == S4F_PRECOND_GAMG) pk = S4F_PRECOND_DIC;
+    Precond pre; pre.init(o, diag, pk);
+    dvec AyA(N), sA(N), zA(N), tA(N);
+    const dvec rA0(rA);
+    double rA0rA = 0, alpha = 0, omega = 0;
+    auto dot = [&](const dvec& a, const dvec& b) {
+        double s = 0;
+#pragma omp parallel for schedule(static) reduction(+ : s) num_threads(o.nThreads) if (o.nThreads > 1)
+        for (int c = 0; c < N; c++) s += a[c] * b[c];
+        return s;
+    };
+    auto sumMag = [&](const dvec& a) {
+        double s = 0;
+#pragma omp parallel for schedule(static) reduction(+ : s) num_threads(o.nThreads) if (o.nThreads > 1)
+        for (int c = 0; c < N; c++) s += std::fabs(a[c]);
+        return s;
+    };
+    do {
+        const double rA0rAold = rA0rA;
+        rA0rA = dot(rA0, rA);
+        if (!(std::fabs(rA0rA) > VSMALL)) break;
+        if (perf.nIter == 0) pA = rA;
+        else {
+            if (!(std::fabs(omega) > VSMALL)) break;
+            const double beta = (rA0rA / rA0rAold) * (alpha / omega);
+            S4FO_PAR_FOR
+            for (int c = 0; c < N; c++) pA[c] = rA[c] + beta * (pA[c] - omega * AyA[c]);
+        }
+        pre.apply(o, yA.data(), pA.data());
+        Amul(o, diag, yA.data(), AyA.data());
+        const double rA0AyA = dot(rA0, AyA);
+        alpha = rA0rA / rA0AyA;
+        S4FO_PAR_FOR
+        for (int c = 0; c < N; c++) sA[c] = rA[c] - alpha * AyA[c];
+        perf.finalRes = sumMag(sA) / nf;
+        if (converged(perf.finalRes)) {
+            S4FO_PAR_FOR
+            for (int c = 0; c < N; c++) psi[c] += alpha * yA[c];
+            perf.nIter++;
+            return perf;
+        }
+        pre.apply(o, zA.data(), sA.data());
+        Amul(o, diag, zA.data(), tA.data());
+        const double tAtA = dot(tA, tA);
+        omega = dot(tA, sA) / tAtA;
+        S4FO_PAR_FOR
+        for (int c = 0; c < N; c++) { psi[c] += alpha * yA[c] + omega * zA[c]; rA[c] = sA[c] - omega * tA[c]; }
+        perf.finalRes = sumMag(rA) / nf;
+    } while (++perf.nIter < o.ctl.maxIter && !converged(perf.finalRes));
+    return perf;
+}
+
 // [OF-ext] fvMatrix<vector>::solveSegregated: per solved component, addBoundaryDiag, solve.
 void solveSegregated(s4f_oracle& o, double* psi /*AoS [3N]*/, const double* source /*AoS*/) {
     const int N = o.N;
@@ -905,7 +1017,8 @@ void solveSegregated(s4f_oracle& o, double* psi /*AoS [3N]*/, const double* sour
         o.perf[q] = SolverPerf{0, 0, 0};
         if (!o.solD[q]) continue;
         for (int c = 0; c < N; c++) { x[c] = psi[3 * c + q]; b[c] = source[3 * c + q]; dg[c] = o.diagC[3 * c + q]; }
-        o.perf[q] = solvePCG(o, dg.data(), x.data(), b.data());
+        o.perf[q] = (o.ctl.solver == S4F_SOLVER_PBICGSTAB) ? solvePBiCGStab(o, dg.data(), x.data(), b.data())
+                                                       : solvePCG(o, dg.data(), x.data(), b.data());
         for (int c = 0; c < N; c++) psi[3 * c + q] = x[c];
         o.totalInner += o.perf[q].nIter;
     }
@@ -1132,6 +1245,11 @@ int s4fo_initialise(s4f_oracle* o) {
 
 int s4fo_new_timestep(s4f_oracle* o, double deltaT) {
     o->ctl.deltaT0 = o->ctl.deltaT; o->ctl.deltaT = deltaT;
+    if (o->ctl.d2dt2Scheme == S4F_D2DT2_BACKWARD) {     // GeometricField::storeOldTimes over the four-level chain
+        if (o->timeIndex >= 2) { o->Doooo = o->Dooo; o->Dooo = o->DoldOld; }
+        else { o->Doooo = o->DoldOld; o->Dooo = o->DoldOld; }
+    }
+    o->timeIndex++;
     o->DoldOld = o->Dold;
     if (o->incremental()) { o->Dold = o->Dtot; o->gradDold = o->gradDtot; }      // the total fields roll; DD keeps its value as the initial guess
     else { o->Dold = o->D; o->gradDold = o->gradD; }

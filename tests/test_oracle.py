@@ -459,3 +459,143 @@ def test_incremental_and_total_tl_models_reach_the_same_equilibrium():
             assert 0.3 < np.abs(o.get("DD")).max() / np.abs(o.get("D")).max() < 0.7     # the increment of the second step
     a, b = res[K.MODEL_NONLIN_TL_TOTAL_DISP], res[K.MODEL_NONLIN_TL]
     assert rel_l2(b[0], a[0]) < 1e-6 and rel_l2(b[1], a[1]) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# [OF-ext] PBiCGStab (fvSolution "solver PBiCGStab") and s4f's backward d2dt2 scheme
+# ---------------------------------------------------------------------------------------------
+def _pbicgstab_python(A, rD, b, x0, tol, relTol, maxIter):
+    """Independent restatement of PBiCGStab.C with a diagonal preconditioner (numpy, one component)."""
+    x = x0.copy()
+    yA = A @ x
+    rA = b - yA
+    avg = x.mean()
+    sumA = np.asarray(A.sum(axis=1)).ravel()
+    nf = np.abs(yA - sumA * avg).sum() + np.abs(b - sumA * avg).sum() + 1e-20
+    init = np.abs(rA).sum() / nf
+    conv = lambda fr: fr < tol or (relTol > 1e-20 and fr < relTol * init)
+    if conv(init):
+        return x, 0
+    rA0 = rA.copy()
+    pA = np.zeros_like(x); AyA = np.zeros_like(x)
+    rA0rA = alpha = omega = 0.0
+    n = 0
+    while True:
+        old = rA0rA
+        rA0rA = rA0 @ rA
+        if n == 0:
+            pA = rA.copy()
+        else:
+            beta = (rA0rA / old) * (alpha / omega)
+            pA = rA + beta * (pA - omega * AyA)
+        yA = rD * pA
+        AyA = A @ yA
+        alpha = rA0rA / (rA0 @ AyA)
+        sA = rA - alpha * AyA
+        if conv(np.abs(sA).sum() / nf):
+            return x + alpha * yA, n + 1
+        zA = rD * sA
+        tA = A @ zA
+        omega = (tA @ sA) / (tA @ tA)
+        x = x + alpha * yA + omega * zA
+        rA = sA - omega * tA
+        n += 1
+        if not (n < maxIter and not conv(np.abs(rA).sum() / nf)):
+            return x, n
+
+
+@pytest.mark.parametrize("pre", [K.PRECOND_NONE, K.PRECOND_DIAGONAL, K.PRECOND_DIC])
+def test_pbicgstab_solution_matches_direct_solve(pre):
+    c = cases.cantilever(10, 4, 4, solver=K.SOLVER_PBICGSTAB, preconditioner=pre, tolerance=1e-13, relTol=0.0, maxIter=5000)
+    o, m, upper, diag = _assembled(c)
+    rng = np.random.default_rng(2)
+    b = rng.standard_normal((m.nCells, 3))
+    psi, st = o.op_solve(np.zeros((m.nCells, 3)), b)
+    for q in range(3):
+        A = ldu_to_csr(m, upper, diag[:, q]).tocsc()
+        assert rel_l2(psi[:, q], spla.spsolve(A, b[:, q])) < 1e-8
+        assert 0 < st["nIterations"][q] < 5000
+
+
+def test_pbicgstab_iterates_match_python_restatement():
+    """Same iterates as a line-by-line numpy PBiCGStab (diagonal preconditioner) after a fixed number of
+    iterations (BiCGStab amplifies round-off, so only the first iterations are compared), and the same exit on
+    the half step (sA converged: psi += alpha yA only) under relTol 0.1."""
+    rng = np.random.default_rng(3)
+    for relTol, tol, maxIter in ((0.0, 0.0, 1), (0.0, 0.0, 2), (0.0, 0.0, 4), (0.0, 0.0, 8), (0.1, 1e-30, 400)):
+        c = cases.cantilever(9, 4, 3, solver=K.SOLVER_PBICGSTAB, preconditioner=K.PRECOND_DIAGONAL, tolerance=tol,
+                             relTol=relTol, maxIter=maxIter)
+        o, m, upper, diag = _assembled(c)
+        b = rng.standard_normal((m.nCells, 3))
+        x0 = np.zeros((m.nCells, 3))
+        psi, st = o.op_solve(x0, b)
+        for q in range(3):
+            A = ldu_to_csr(m, upper, diag[:, q])
+            x, n = _pbicgstab_python(A, 1.0 / diag[:, q], b[:, q], x0[:, q], tol, relTol, maxIter)
+            assert st["nIterations"][q] == n
+            assert rel_l2(psi[:, q], x) < 1e-8, (maxIter, q)
+
+
+def test_pbicgstab_drives_the_outer_loop_to_the_pcg_solution():
+    tight = dict(solutionTolerance=1e-9, alternativeTolerance=1e-9, tolerance=1e-12, nCorrectors=3000, preconditioner=K.PRECOND_DIC)
+    a = OracleSolid(cases.cantilever(8, 3, 3, L=2.0, **tight))
+    b = OracleSolid(cases.cantilever(8, 3, 3, L=2.0, solver=K.SOLVER_PBICGSTAB, **tight))
+    sa, sb = a.evolve(), b.evolve()
+    assert sa["converged"] and sb["converged"]
+    assert rel_l2(b.get("D"), a.get("D")) < 1e-6
+
+
+def _free_body(nx=4, ny=3, nz=3, **ctl):
+    """A box with every patch traction free: a rigid translation produces no stress, so the assembled source is the
+    d2dt2 old-time term alone and diag is the d2dt2 coefficient (the laplacian rows sum to zero)."""
+    mesh = M.hex_box(nx, ny, nz, 2.0, 1.0, 1.0, names=("a", "b", "c", "d", "e", "f"))
+    bcs = {p.name: K.solidTraction((0.0, 0.0, 0.0)) for p in mesh.patches}
+    law = K.mechanical_law("linearElastic", rho=7800.0, E=200e9, nu=0.3)
+    return K.SolidCase(mesh, bcs, law, K.default_controls(**ctl))
+
+
+def test_backward_d2dt2_is_exact_for_quadratic_motion():
+    """backwardD2dt2Scheme.C:309-395 = backward ddt applied twice: exact for D(t) = a t^2 once four old levels
+    exist, i.e.  A D(t_n) - source = rho V 2a  for a rigid translation of a traction-free body."""
+    dt, a = 1e-3, np.array([3.0, -2.0, 0.5])
+    c = _free_body(d2dt2Scheme=K.D2DT2_BACKWARD, deltaT=dt, deltaT0=dt, stabilisation=K.STAB_NONE)
+    o = OracleSolid(c)
+    m = c.mesh
+    N = m.nCells
+    rigid = lambda t: np.tile(a * t * t, (N, 1))
+    for step in range(1, 7):                 # D(t_step) is written at each level before the roll
+        o.new_timestep(dt)
+        o.set("D", rigid(step * dt))
+        o.initialise()                       # boundary values and gradient of the rigid field (zero strain)
+        o.op_assemble()
+        src, diag = o.get("source"), o.get("diag")
+        upper = o.get("upper")
+        res = np.stack([ldu_to_csr(m, upper, diag[:, q]) @ rigid(step * dt)[:, q] for q in range(3)], axis=1) - src
+        exact = c.law.rho * m.V[:, None] * 2.0 * a[None, :]
+        if step >= 5:                        # D.o .. D.oooo all hold values of the quadratic
+            assert np.abs(res - exact).max() < 1e-6 * np.abs(exact).max(), step
+    # coefficients of the start-up step (deltaT0_(vf) = GREAT: coefft = 1) against the formula
+    o0 = OracleSolid(_free_body(stabilisation=K.STAB_NONE)); o0.op_assemble()
+    lap = o0.get("diag")[:, 0]                      # laplacian part of the diagonal (steadyState)
+    o2 = OracleSolid(c)
+    o2.new_timestep(dt); o2.op_assemble()
+    assert o2.get("diag")[:, 0] - lap == pytest.approx(1.5 * c.law.rho * m.V / dt**2, rel=1e-9)
+    o2.new_timestep(dt); o2.op_assemble()
+    assert o2.get("diag")[:, 0] - lap == pytest.approx(2.25 * c.law.rho * m.V / dt**2, rel=1e-9)
+
+
+def test_backward_d2dt2_free_vibration_is_less_damped_than_euler():
+    """Cantilever released under gravity: the second-order backward scheme keeps more kinetic energy than Euler."""
+    tips = {}
+    for scheme in (K.D2DT2_EULER, K.D2DT2_BACKWARD):
+        c = cases.cantilever(8, 3, 3, L=2.0, d2dt2Scheme=scheme, deltaT=2e-4, deltaT0=2e-4, nCorrectors=200,
+                             traction=(0.0, 0.0, 0.0), g=(0.0, -9.81, 0.0), preconditioner=K.PRECOND_DIC, tolerance=1e-12)
+        o = OracleSolid(c)
+        tip = []
+        for _ in range(12):
+            o.new_timestep(2e-4)
+            o.evolve()
+            tip.append(o.get("D")[:, 1].min())
+        tips[scheme] = np.array(tip)
+    assert (tips[K.D2DT2_BACKWARD] < 0).all() and (tips[K.D2DT2_EULER] < 0).all()
+    assert tips[K.D2DT2_BACKWARD][-1] < tips[K.D2DT2_EULER][-1]          # has fallen further
