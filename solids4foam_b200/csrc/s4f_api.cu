@@ -194,7 +194,7 @@ int s4fgpu_set_law(s4fgpu_handle c, const s4fgpu_law* law) {
     S4F_REQUIRE(c, law->nTable >= 0 && law->nTable <= 64, "set_law: table too long");
     if (law->kind == S4F_LAW_NEO_HOOKEAN_MISES_PLASTIC || law->kind == S4F_LAW_LINEAR_ELASTIC_MISES_PLASTIC)
         S4F_REQUIRE(c, law->nTable >= 1, "set_law: plasticity law needs the (epsilonP sigmaY) table");
-    c->law = *law; c->lawSet = true;
+    c->law = *law; c->lawSet = true; c->histValid = false;
     if (c->geomSet) return s4f_setup_law(c);
     return 0;
 }
@@ -208,9 +208,11 @@ int s4fgpu_set_controls(s4fgpu_handle c, const s4fgpu_controls* ctl) {
                 "and nonLinearGeometryTotalLagrangian (the updated-Lagrangian model needs mesh motion: not available)");
     S4F_REQUIRE(c, ctl->solidModel != S4F_MODEL_NONLIN_TL || ctl->d2dt2Scheme == S4F_D2DT2_STEADY_STATE,
                 "set_controls: nonLinearGeometryTotalLagrangian is available with the steadyState d2dt2 scheme");
-    S4F_REQUIRE(c, ctl->solver == S4F_SOLVER_PCG, "set_controls: only PCG (the momentum matrix is symmetric)");
-    S4F_REQUIRE(c, ctl->d2dt2Scheme == S4F_D2DT2_STEADY_STATE || ctl->d2dt2Scheme == S4F_D2DT2_EULER, "set_controls: d2dt2 scheme steadyState or Euler");
-    c->ctl = *ctl; c->ctlSet = true; c->matrixValid = false; c->amgValid = false;
+    S4F_REQUIRE(c, ctl->solver == S4F_SOLVER_PCG || ctl->solver == S4F_SOLVER_PBICGSTAB, "set_controls: solver PCG or PBiCGStab");
+    S4F_REQUIRE(c, ctl->d2dt2Scheme >= S4F_D2DT2_STEADY_STATE && ctl->d2dt2Scheme <= S4F_D2DT2_BACKWARD, "set_controls: unknown d2dt2 scheme");
+    if (ctl->d2dt2Scheme == S4F_D2DT2_BACKWARD && ctl->deltaT0 > 0)     // backwardD2dt2Scheme.C:316-322
+        S4F_REQUIRE(c, std::fabs(ctl->deltaT - ctl->deltaT0) <= 1e-15 + 1e-12 * ctl->deltaT, "set_controls: backwardD2dt2Scheme not implemented for variable time steps");
+    c->ctl = *ctl; c->ctlSet = true; c->matrixValid = false; c->amgValid = false; c->histValid = false;
     if (c->geomSet) return s4f_alloc_model_fields(c);
     return 0;
 }
@@ -269,6 +271,7 @@ int s4fgpu_upload(s4fgpu_handle c, int field, const double* host) {
     S4F_REQUIRE(c, c->geomSet, "upload: call set_geometry first");
     double* p; int nc, off, cnt;
     int rc = field_lookup(c, field, &p, &nc, &off, &cnt); if (rc) return rc;
+    if (field == S4F_FIELD_D_OLD || field == S4F_FIELD_D_OLDOLD) c->histValid = false;
     return s4f_aos_to_soa(c, host, p, cnt, nc, off);
 }
 
@@ -314,8 +317,15 @@ int s4fgpu_initialise(s4fgpu_handle c) {
 int s4fgpu_new_timestep(s4fgpu_handle c, double deltaT) {
     S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
     const size_t ld = c->ld;
+    if (c->ctl.d2dt2Scheme == S4F_D2DT2_BACKWARD && c->timeIndex >= 1)
+        S4F_REQUIRE(c, std::fabs(deltaT - c->ctl.deltaT) <= 1e-15 + 1e-12 * deltaT, "new_timestep: backwardD2dt2Scheme not implemented for variable time steps");
     c->ctl.deltaT0 = c->ctl.deltaT; c->ctl.deltaT = deltaT;
     int rc = 0;
+    if (c->ctl.d2dt2Scheme == S4F_D2DT2_BACKWARD) {       // GeometricField::storeOldTimes over the four-level chain
+        rc |= d2d(c, c->Doooo.p, c->timeIndex >= 2 ? c->Dooo.p : c->DoldOld.p, 3 * ld);
+        rc |= d2d(c, c->Dooo.p, c->DoldOld.p, 3 * ld);
+    }
+    c->timeIndex++; c->histValid = false;
     rc |= d2d(c, c->DoldOld.p, c->Dold.p, 3 * ld);
     if (c->incremental()) {     // the total fields roll; DD keeps its value as the initial guess of the next step
         rc |= d2d(c, c->Dold.p, c->Dtot.p, 3 * ld); rc |= d2d(c, c->gradDold.p, c->gradDtot.p, 9 * ld);

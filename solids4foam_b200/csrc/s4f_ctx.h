@@ -81,6 +81,8 @@ struct PcgScalars {
     double finalRes[3];
     double avg[3];         // gAverage(psi)
     double alpha[3], beta[3];
+    double omega[3];       // PBiCGStab
+    int half[3];           // PBiCGStab: sA converged on the half step -> psi += alpha yA, then stop
     int active[3];         // component still iterating
     int nIter[3];
     int anyActive;
@@ -159,6 +161,10 @@ struct s4fgpu_ctx {
 
     // ---- fields (SoA, ld per component) ----
     DevBuf<double> D, Dprev, Dold, DoldOld;       // 3*ld
+    DevBuf<double> Dooo, Doooo;                   // 3*ld: third / fourth old-time level (backward d2dt2 only)
+    DevBuf<double> d2Hist;                        // 3*ld: old-time part of rho*fvm::d2dt2(D) per unit volume (transient schemes)
+    bool histValid = false;
+    int timeIndex = 0;                            // new_timestep() calls = runTime.timeIndex()
     DevBuf<double> gradD, gradDold;               // 9*ld
     // D / gradD hold the SOLUTION field: D for the total-displacement models, DD for the incremental ones
     // (nonLinGeomTotalLagSolid.C:152-161), which keep D = D.oldTime() + DD and gradD = gradD.oldTime() + gradDD here
@@ -179,6 +185,7 @@ struct s4fgpu_ctx {
     // ---- PCG work vectors ----
     DevBuf<double> pA, wA, rA;        // 3*ld each
     DevBuf<double> cheb0, cheb1;      // 3*ld polynomial-preconditioner work
+    DevBuf<double> bi[6];             // 3*ld each: PBiCGStab rA0, yA, AyA, sA, zA, tA
     DevBuf<double> aitRes, aitResPrev, aitAlpha;  // Aitken relaxation state (solidModel.C:842-897)
     DevBuf<PcgScalars> pcgS;
     DevBuf<OuterScalars> outS;
@@ -208,6 +215,7 @@ int s4f_alloc_fields(s4fgpu_ctx* c);
 int s4f_setup_law(s4fgpu_ctx* c);
 int s4f_assemble_matrix(s4fgpu_ctx* c);
 int s4f_assemble_source(s4fgpu_ctx* c);
+int s4f_d2dt2_history(s4fgpu_ctx* c);               // d2Hist from the old-time levels (lazy, once per time step)
 int s4f_bc_update_coeffs(s4fgpu_ctx* c);
 int s4f_bc_evaluate(s4fgpu_ctx* c);
 int s4f_relax_and_residual(s4fgpu_ctx* c, int iCorr);

@@ -279,9 +279,9 @@ template <bool TENSOR9, bool STAB, bool NONORTH>
 __global__ void __launch_bounds__(S4F_SRC_BLOCK, 4) k_source_f(
     const int* __restrict__ slicePtr, const int* __restrict__ col, const double* __restrict__ eU, const double* __restrict__ eC0,
     const double* __restrict__ eGam, const double* __restrict__ eVc, const double* __restrict__ rowK, const double* __restrict__ D,
-    const double* __restrict__ T, const double* __restrict__ gradD, const double* __restrict__ V, const double* __restrict__ Dold,
-    const double* __restrict__ DoldOld, double* __restrict__ source, int N, int ld, long long nE, int nSlices, double rhoGx,
-    double rhoGy, double rhoGz, double cOld, double cOldOld) {
+    const double* __restrict__ T, const double* __restrict__ gradD, const double* __restrict__ V,
+    const double* __restrict__ hist /* old-time d2dt2 terms per unit volume, null for steadyState */, double* __restrict__ source, int N,
+    int ld, long long nE, int nSlices, double rhoGx, double rhoGy, double rhoGz) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int q = wib % 3, sub = wib / 3;
     constexpr int SPB = S4F_SRC_BLOCK / 96;
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(S4F_SRC_BLOCK, 4) k_source_f(
             if (STAB) sv += rowK[3 * (size_t)ld + row] * G0[row] + rowK[4 * (size_t)ld + row] * G1[row] + rowK[5 * (size_t)ld + row] * G2[row];
             const double v = V[row];
             sv += v * rg;
-            if (cOld != 0.0) sv += v * (cOld * Dold[(size_t)q * ld + row] - cOldOld * DoldOld[(size_t)q * ld + row]);
+            if (hist) sv += v * hist[(size_t)q * ld + row];
             source[(size_t)q * ld + row] = sv;
         }
     }
@@ -536,15 +536,52 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_relax_aitken(double* __restrict__
 // host drivers
 // ================================================================================================
 
-static double d2dt2_diag_coeff(const s4fgpu_ctx* c, double* cOld, double* cOldOld) {
-    *cOld = 0; *cOldOld = 0;
-    if (c->ctl.d2dt2Scheme != S4F_D2DT2_EULER) return 0.0;
-    // [OF-ext] EulerD2dt2Scheme::fvmD2dt2 with variable deltaT
-    const double dt = c->ctl.deltaT, dt0 = c->ctl.deltaT0 > 0 ? c->ctl.deltaT0 : dt;
-    const double coefft = (dt + dt0) / (2 * dt), coefft00 = (dt + dt0) / (2 * dt0), rDeltaT2 = 4.0 / ((dt + dt0) * (dt + dt0));
-    *cOld = rDeltaT2 * c->law.rho * (coefft + coefft00);
-    *cOldOld = rDeltaT2 * c->law.rho * coefft00;
-    return coefft * rDeltaT2 * c->law.rho;
+// rho*fvm::d2dt2(D) as  diag += k.diag V  and  source += V (h0 D.o + h1 D.oo + h2 D.ooo + h3 D.oooo):
+//  Euler     [OF-ext] EulerD2dt2Scheme::fvmD2dt2 (variable deltaT form)
+//  backward  numerics/backwardD2dt2Scheme/backwardD2dt2Scheme.C:309-395 (coefficients :350-356; deltaT0_(vf) = GREAT
+//            during the first time step :48-68) around [OF-ext] backwardDdtScheme::fvmDdt / fvcDdt; see the oracle.
+struct D2dt2Coeffs { double diag, h[4]; };
+static D2dt2Coeffs d2dt2_coeffs(const s4fgpu_ctx* c) {
+    D2dt2Coeffs k{0, {0, 0, 0, 0}};
+    const double dt = c->ctl.deltaT, dt0 = c->ctl.deltaT0 > 0 ? c->ctl.deltaT0 : dt, rho = c->law.rho;
+    if (c->ctl.d2dt2Scheme == S4F_D2DT2_EULER) {
+        const double coefft = (dt + dt0) / (2 * dt), coefft00 = (dt + dt0) / (2 * dt0), rDeltaT2 = 4.0 / ((dt + dt0) * (dt + dt0));
+        k.diag = coefft * rDeltaT2 * rho;
+        k.h[0] = rDeltaT2 * rho * (coefft + coefft00); k.h[1] = -rDeltaT2 * rho * coefft00;
+    } else if (c->ctl.d2dt2Scheme == S4F_D2DT2_BACKWARD) {
+        const bool first = c->timeIndex <= 1;
+        const double cc = first ? 1.0 : 1.0 + dt / (dt + dt0), c00 = first ? 0.0 : dt * dt / (dt0 * (dt + dt0)), c0 = cc + c00;
+        const double b = 1.0 + dt / (dt + dt0), b00 = dt * dt / (dt0 * (dt + dt0)), b0 = b + b00;
+        const double r = rho / (dt * dt);
+        k.diag = r * cc * b;
+        k.h[0] = r * (cc * b0 + c0 * b);
+        k.h[1] = r * (-cc * b00 - c0 * b0 - c00 * b);
+        k.h[2] = r * (c0 * b00 + c00 * b0);
+        k.h[3] = -r * c00 * b00;
+    }
+    return k;
+}
+
+namespace {
+__global__ void k_d2dt2_hist(const double* __restrict__ D1, const double* __restrict__ D2, const double* __restrict__ D3,
+                             const double* __restrict__ D4, double* __restrict__ hist, long long n, double h0, double h1, double h2,
+                             double h3) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) hist[i] = h0 * D1[i] + h1 * D2[i] + h2 * D3[i] + h3 * D4[i];
+}
+}  // namespace
+
+int s4f_d2dt2_history(s4fgpu_ctx* c) {
+    if (c->ctl.d2dt2Scheme == S4F_D2DT2_STEADY_STATE || c->histValid) return 0;
+    const D2dt2Coeffs k = d2dt2_coeffs(c);
+    const bool deep = c->ctl.d2dt2Scheme == S4F_D2DT2_BACKWARD && c->timeIndex > 1;   // before: D.ooo = D.oooo = copies of D.oo
+    const long long n = 3 * (long long)c->ld;
+    k_d2dt2_hist<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->Dold.p, c->DoldOld.p, deep ? c->Dooo.p : c->DoldOld.p,
+                                                                     deep ? c->Doooo.p : c->DoldOld.p, c->d2Hist.p, n, k.h[0], k.h[1],
+                                                                     k.h[2], k.h[3]);
+    c->launches++;
+    c->histValid = true;
+    return 0;
 }
 
 int s4f_upload_bc(s4fgpu_ctx* c) {
@@ -556,8 +593,7 @@ int s4f_upload_bc(s4fgpu_ctx* c) {
 }
 
 int s4f_assemble_matrix(s4fgpu_ctx* c) {
-    double cOld, cOldOld;
-    const double dcoef = d2dt2_diag_coeff(c, &cOld, &cOldOld);
+    const double dcoef = d2dt2_coeffs(c).diag;
     const int gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
     k_assemble_laplacian<<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eW.p, c->eDn.p, c->eSf.p, c->nonOrth ? c->eCorr.p : nullptr,
                                                              c->impK.p, c->V.p, c->eA.p, c->eGam.p, c->eU.p, c->eC0.p, c->nonOrth ? c->eVc.p : nullptr,
@@ -597,17 +633,17 @@ int s4f_bc_evaluate(s4fgpu_ctx* c) {
 }
 
 template <bool T9>
-static void launch_source(s4fgpu_ctx* c, const double* T, double cOld, double cOldOld) {
+static void launch_source(s4fgpu_ctx* c, const double* T) {
     const bool stab = c->ctl.stabilisation == S4F_STAB_RHIE_CHOW;
     const double rg[3] = {c->law.rho * c->ctl.g[0], c->law.rho * c->ctl.g[1], c->law.rho * c->ctl.g[2]};
     long long need = ((long long)c->nSlices + 1) / 2, g = (long long)c->numSMs * 8;
     if (need < g) g = need;
     const int grid = (int)(g < 1 ? 1 : g);
+    const double* hist = c->ctl.d2dt2Scheme == S4F_D2DT2_STEADY_STATE ? nullptr : c->d2Hist.p;
 #define S4F_LAUNCH_SRC(STAB, NO)                                                                                                      \
     k_source_f<T9, STAB, NO><<<grid, S4F_SRC_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eU.p, c->eC0.p, c->eGam.p, c->eVc.p,   \
-                                                                    c->rowK.p, c->D.p, T, c->gradD.p, c->V.p, c->Dold.p, c->DoldOld.p, \
-                                                                    c->source.p, c->N, c->ld, c->nEntries, c->nSlices, rg[0], rg[1],   \
-                                                                    rg[2], cOld, cOldOld)
+                                                                    c->rowK.p, c->D.p, T, c->gradD.p, c->V.p, hist, c->source.p, c->N, \
+                                                                    c->ld, c->nEntries, c->nSlices, rg[0], rg[1], rg[2])
     if (stab && c->nonOrth) S4F_LAUNCH_SRC(true, true);
     else if (stab) S4F_LAUNCH_SRC(true, false);
     else S4F_LAUNCH_SRC(false, false);
@@ -616,10 +652,9 @@ static void launch_source(s4fgpu_ctx* c, const double* T, double cOld, double cO
 }
 
 int s4f_assemble_source(s4fgpu_ctx* c) {
-    double cOld, cOldOld;
-    d2dt2_diag_coeff(c, &cOld, &cOldOld);
-    if (c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP) launch_source<false>(c, c->sigma.p, cOld, cOldOld);
-    else launch_source<true>(c, c->T9.p, cOld, cOldOld);
+    int rh = s4f_d2dt2_history(c); if (rh) return rh;
+    if (c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP) launch_source<false>(c, c->sigma.p);
+    else launch_source<true>(c, c->T9.p);
     if (c->nBCells > 0) {
         k_source_boundary<<<(c->nBCells + 127) / 128, 128, 0, c->stream>>>(c->bcCells.p, c->bcPtr.p, c->bcFaces.p, c->bKind.p, c->bN.p, c->bK.p,
                                                                          c->bDelta.p, c->bMagSf.p, c->impK.p, c->tracGrad.p, c->D.p, c->gradD.p,

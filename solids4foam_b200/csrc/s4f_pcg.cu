@@ -18,6 +18,8 @@
 // scalar recurrences (alpha, beta, convergence flags, iteration counters) live in device memory, so
 // the host only polls a flag every `checkEvery` iterations.  With NCCL the raw sums are all-reduced
 // and a one-thread kernel finishes the scalar step.
+// fvSolution "solver PBiCGStab" ([OF-ext] PBiCGStab.C) runs through the same kernels with its own vector updates
+// (solve_pbicgstab below): two preconditioner applications and two SpMVs per iteration, the half-step exit on sA.
 #include <cmath>
 #include <cstring>
 
@@ -34,7 +36,7 @@ struct PcgParams {
     int precond;
 };
 
-enum { PH_AVG = 0, PH_INIT = 1, PH_AMUL = 2, PH_XR = 3, PH_DOT = 4 };
+enum { PH_AVG = 0, PH_INIT = 1, PH_AMUL = 2, PH_XR = 3, PH_DOT = 4, PH_BI_RHO = 5, PH_BI_ALPHA = 6, PH_BI_S = 7, PH_BI_OMEGA = 8, PH_BI_XR = 9 };
 
 __device__ __forceinline__ bool conv_check(const PcgParams& P, double fr, double ir) {
     return fr < P.tolerance || (P.relTol > 1e-20 && fr < P.relTol * ir);
@@ -53,7 +55,7 @@ __device__ void pcg_scalar_step(int phase, PcgScalars* S, const double* tot, con
             S->rho[c] = tot[6 + c];
             S->rhoOld[c] = 1e300;
             S->nIter[c] = 0;
-            S->alpha[c] = 0; S->beta[c] = 0;
+            S->alpha[c] = 0; S->beta[c] = 0; S->omega[c] = 0; S->half[c] = 0;
             S->active[c] = (P.solD[c] && !conv_check(P, S->finalRes[c], S->initRes[c]) && P.maxIter > 0) ? 1 : 0;
             any |= S->active[c];
         }
@@ -76,6 +78,43 @@ __device__ void pcg_scalar_step(int phase, PcgScalars* S, const double* tot, con
                 S->nIter[c] += 1;
                 if (!(S->nIter[c] < P.maxIter && !conv_check(P, S->finalRes[c], S->initRes[c]))) S->active[c] = 0;
                 else if (local) S->beta[c] = S->rho[c] / S->rhoOld[c];
+            }
+            any |= S->active[c];
+        }
+        S->anyActive = any;
+    } else if (phase == PH_BI_RHO) {      // rA0rA; singularity tests; beta   (PBiCGStab.C do-loop head)
+        int any = 0;
+        for (int c = 0; c < 3; c++) {
+            if (S->active[c]) {
+                S->rhoOld[c] = S->rho[c];
+                S->rho[c] = tot[c];
+                if (!(fabs(tot[c]) > 1e-300)) S->active[c] = 0;
+                else if (S->nIter[c] > 0) {
+                    if (!(fabs(S->omega[c]) > 1e-300)) S->active[c] = 0;
+                    else S->beta[c] = (S->rho[c] / S->rhoOld[c]) * (S->alpha[c] / S->omega[c]);
+                }
+            }
+            any |= S->active[c];
+        }
+        S->anyActive = any;
+    } else if (phase == PH_BI_ALPHA) {    // alpha = rA0rA / rA0AyA
+        for (int c = 0; c < 3; c++) if (S->active[c]) { S->wApA[c] = tot[c]; S->alpha[c] = S->rho[c] / tot[c]; }
+    } else if (phase == PH_BI_S) {        // convergence test on sA: exit with psi += alpha yA
+        for (int c = 0; c < 3; c++) if (S->active[c]) {
+            S->finalRes[c] = tot[c] / S->normFactor[c];
+            if (conv_check(P, S->finalRes[c], S->initRes[c])) { S->half[c] = 1; S->active[c] = 0; S->nIter[c] += 1; }
+        }
+        // anyActive stays set: the half-step components are finished by the update kernel of this iteration
+    } else if (phase == PH_BI_OMEGA) {    // omega = (tA.sA)/(tA.tA)
+        for (int c = 0; c < 3; c++) if (S->active[c]) S->omega[c] = tot[3 + c] / tot[c];
+    } else if (phase == PH_BI_XR) {
+        int any = 0;
+        for (int c = 0; c < 3; c++) {
+            S->half[c] = 0;
+            if (S->active[c]) {
+                S->finalRes[c] = tot[c] / S->normFactor[c];
+                S->nIter[c] += 1;
+                if (!(S->nIter[c] < P.maxIter && !conv_check(P, S->finalRes[c], S->initRes[c]))) S->active[c] = 0;
             }
             any |= S->active[c];
         }
@@ -223,12 +262,14 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_pcg_p_generic(const double* __res
 // loads, then 24 independent gathers per thread), which is what hides the HBM/L2 latency at the
 // occupancy 64 registers allow (measured: profiles/microbench/spmv_variants.cu, 0.78 of the copy peak
 // against 0.61 for a 2-way unrolled loop).
-template <bool DOT>
+// DOT 0: none (cmptMask selects the components); 1: sums w.dotv (PCG: dotv = p; PBiCGStab: dotv = rA0);
+// 2: sums w.w and w.dotv (PBiCGStab omega).  `phase` names the scalar step the finished sums feed.
+template <int DOT>
 __global__ void __launch_bounds__(S4F_BLOCK, 4) k_amul3(const int* __restrict__ slicePtr, const int* __restrict__ col,
                                                         const double* __restrict__ eA, const double* __restrict__ diagC,
                                                         const double* __restrict__ p, double* __restrict__ w, int N, int ld,
                                                         int nSlices, PcgScalars* S, PcgParams P, double nGlob, double* partials,
-                                                        unsigned int* ticket, int cmptMask) {
+                                                        unsigned int* ticket, int cmptMask, const double* __restrict__ dotv, int phase) {
     int act[3];
     if (DOT) {
         if (!S->anyActive) return;
@@ -241,7 +282,9 @@ __global__ void __launch_bounds__(S4F_BLOCK, 4) k_amul3(const int* __restrict__ 
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nWarps = (gridDim.x * blockDim.x) >> 5;
-    double v[3] = {0, 0, 0};
+    double v[DOT == 2 ? 6 : 3];
+#pragma unroll
+    for (int i = 0; i < (DOT == 2 ? 6 : 3); i++) v[i] = 0;
     for (int s = warp; s < nSlices; s += nWarps) {
         const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
         const int row = s * 32 + lane;
@@ -267,11 +310,12 @@ __global__ void __launch_bounds__(S4F_BLOCK, 4) k_amul3(const int* __restrict__ 
                 const double pp = p[j];
                 const double ww = diagC[j] * pp - acc[c];
                 w[j] = ww;
-                if (DOT) v[c] += ww * pp;
+                if constexpr (DOT == 1) v[c] += ww * (dotv == p ? pp : dotv[j]);
+                if constexpr (DOT == 2) { v[c] += ww * ww; v[3 + c] += ww * dotv[j]; }
             }
         }
     }
-    if (DOT) grid_reduce<3, OpSum>(v, partials, ticket, Fin{PH_AMUL, S, P, nGlob, 3});
+    if constexpr (DOT != 0) grid_reduce<(DOT == 2 ? 6 : 3), OpSum>(v, partials, ticket, Fin{phase, S, P, nGlob, DOT == 2 ? 6 : 3});
 }
 
 // scalar (single-vector) Amul, for the roofline number the metric quotes
@@ -399,6 +443,93 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_cheb_step(const int* __restrict__
     }
 }
 
+
+// ---- PBiCGStab vector kernels ([OF-ext] PBiCGStab.C), three components with their own flags ----------
+// rA0.rA
+__global__ void __launch_bounds__(S4F_BLOCK) k_bi_rho(const double* __restrict__ r0, const double* __restrict__ r, int N, int ld, PcgScalars* S,
+                                                      PcgParams P, double nGlob, double* partials, unsigned int* ticket) {
+    if (!S->anyActive) return;
+    int act[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) act[c] = S->active[c];
+    double v[3] = {0, 0, 0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) if (act[c]) { const size_t j = (size_t)c * ld + i; v[c] += r0[j] * r[j]; }
+    }
+    grid_reduce<3, OpSum>(v, partials, ticket, Fin{PH_BI_RHO, S, P, nGlob, 3});
+}
+
+// pA = rA + beta (pA - omega AyA)  (first iteration: pA = rA);  yA = M^-1 pA for the local preconditioners
+// (rD = 1/diag, or null for none); with a non-local preconditioner y is null and M^-1 is applied afterwards
+__global__ void __launch_bounds__(S4F_BLOCK) k_bi_p(const double* __restrict__ r, const double* __restrict__ AyA, const double* __restrict__ rD,
+                                                    double* __restrict__ p, double* __restrict__ y, int N, int ld, const PcgScalars* __restrict__ S) {
+    if (!S->anyActive) return;
+    int act[3], first[3]; double beta[3], omega[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { act[c] = S->active[c]; first[c] = S->nIter[c] == 0; beta[c] = S->beta[c]; omega[c] = S->omega[c]; }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (!act[c]) continue;
+            const size_t j = (size_t)c * ld + i;
+            double pp = r[j];
+            if (!first[c]) pp += beta[c] * (p[j] - omega[c] * AyA[j]);
+            p[j] = pp;
+            if (y) y[j] = rD ? rD[j] * pp : pp;
+        }
+    }
+}
+
+// sA = rA - alpha AyA ; sums |sA| ;  zA = M^-1 sA for the local preconditioners
+__global__ void __launch_bounds__(S4F_BLOCK) k_bi_s(const double* __restrict__ r, const double* __restrict__ AyA, const double* __restrict__ rD,
+                                                    double* __restrict__ sA, double* __restrict__ z, int N, int ld, PcgScalars* S, PcgParams P,
+                                                    double nGlob, double* partials, unsigned int* ticket) {
+    if (!S->anyActive) return;
+    int act[3]; double alpha[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { act[c] = S->active[c]; alpha[c] = S->alpha[c]; }
+    double v[3] = {0, 0, 0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (!act[c]) continue;
+            const size_t j = (size_t)c * ld + i;
+            const double ss = r[j] - alpha[c] * AyA[j];
+            sA[j] = ss;
+            if (z) z[j] = rD ? rD[j] * ss : ss;
+            v[c] += fabs(ss);
+        }
+    }
+    grid_reduce<3, OpSum>(v, partials, ticket, Fin{PH_BI_S, S, P, nGlob, 3});
+}
+
+// psi += alpha yA + omega zA ; rA = sA - omega tA ; sums |rA|.   Components that converged on the half step
+// only take psi += alpha yA.
+__global__ void __launch_bounds__(S4F_BLOCK) k_bi_xr(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ y,
+                                                     const double* __restrict__ z, const double* __restrict__ sA, const double* __restrict__ tA,
+                                                     int N, int ld, PcgScalars* S, PcgParams P, double nGlob, double* partials,
+                                                     unsigned int* ticket) {
+    if (!S->anyActive) return;
+    int act[3], half[3]; double alpha[3], omega[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { act[c] = S->active[c]; half[c] = S->half[c]; alpha[c] = S->alpha[c]; omega[c] = S->omega[c]; }
+    double v[3] = {0, 0, 0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const size_t j = (size_t)c * ld + i;
+            if (act[c]) {
+                x[j] += alpha[c] * y[j] + omega[c] * z[j];
+                const double rr = sA[j] - omega[c] * tA[j];
+                r[j] = rr;
+                v[c] += fabs(rr);
+            } else if (half[c]) x[j] += alpha[c] * y[j];
+        }
+    }
+    grid_reduce<3, OpSum>(v, partials, ticket, Fin{PH_BI_XR, S, P, nGlob, 3});
+}
+
 // pack boundary-cell values of an ncomp-component SoA field into the send buffer
 __global__ void k_pack(const double* __restrict__ f, const int* __restrict__ sendCells, double* __restrict__ buf, int G, int ld, int ncomp) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -454,14 +585,16 @@ static int allreduce_part(s4fgpu_ctx* c, int n, int phase, const PcgParams& P, d
     return 0;
 }
 
-static int amul3(s4fgpu_ctx* c, const double* p, double* w, bool dot, const PcgParams& P, double nGlob, int mask) {
+static int amul3(s4fgpu_ctx* c, const double* p, double* w, bool dot, const PcgParams& P, double nGlob, int mask,
+                 const double* dotv = nullptr, int phase = PH_AMUL, bool twoDots = false) {
     const int grid = s4f_grid(c->numSMs, (long long)c->nSlices * 32, 4);
-    if (dot)
-        k_amul3<true><<<grid, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, p, w, c->N, c->ld, c->nSlices,
-                                                          c->pcgS.p, P, nGlob, c->partials.p, c->ticket.p, mask);
-    else
-        k_amul3<false><<<grid, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, p, w, c->N, c->ld, c->nSlices,
-                                                           c->pcgS.p, P, nGlob, c->partials.p, c->ticket.p, mask);
+#define S4F_AMUL3(DOT)                                                                                                              \
+    k_amul3<DOT><<<grid, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, p, w, c->N, c->ld, c->nSlices, c->pcgS.p, \
+                                                    P, nGlob, c->partials.p, c->ticket.p, mask, dotv ? dotv : p, phase)
+    if (!dot) S4F_AMUL3(0);
+    else if (twoDots) S4F_AMUL3(2);
+    else S4F_AMUL3(1);
+#undef S4F_AMUL3
     c->launches++;
     return 0;
 }
@@ -489,15 +622,15 @@ static double global_cells(s4fgpu_ctx* c) {
 }
 
 // Chebyshev preconditioner application: z (in wA) = q(D^-1 A) D^-1 r, degree = chebyshevDegree
-static int cheb_apply(s4fgpu_ctx* c, const PcgParams& P) {
+static int cheb_apply(s4fgpu_ctx* c, const PcgParams& P, const double* r, double* z) {
     const int N = c->N, ld = c->ld;
     const int gridV = s4f_grid(c->numSMs, N), gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
     const double lmax = c->lambdaMax, lmin = lmax / 30.0;     // smoother-style interval
     const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin);
     const int deg = c->ctl.chebyshevDegree < 1 ? 1 : c->ctl.chebyshevDegree;
-    double* bufs[3] = {c->cheb0.p, c->cheb1.p, c->wA.p};
+    double* bufs[3] = {c->cheb0.p, c->cheb1.p, z};
     int cur = 0, prev = -1;
-    k_cheb_first<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->diagC.p, c->rA.p, bufs[cur], N, ld, 1.0 / theta, c->pcgS.p);
+    k_cheb_first<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->diagC.p, r, bufs[cur], N, ld, 1.0 / theta, c->pcgS.p);
     c->launches++;
     double sigma1 = theta / delta, rhoK = 1.0 / sigma1;
     for (int k = 1; k < deg; k++) {
@@ -506,13 +639,61 @@ static int cheb_apply(s4fgpu_ctx* c, const PcgParams& P) {
         int nxt = 0;
         while (nxt == cur || nxt == prev) nxt++;
         int rc = s4f_halo_exchange(c, bufs[cur], 3); if (rc) return rc;
-        k_cheb_step<<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, c->rA.p, bufs[cur],
+        k_cheb_step<<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, r, bufs[cur],
                                                         prev < 0 ? nullptr : bufs[prev], bufs[nxt], N, ld, c->nSlices, c1, c2, c->pcgS.p);
         c->launches++;
         rhoK = rhoN; prev = cur; cur = nxt;
     }
     double* zk = bufs[cur];
-    if (zk != c->wA.p) S4F_CHECK_CUDA(c, cudaMemcpyAsync(c->wA.p, zk, 3 * (size_t)ld * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    if (zk != z) S4F_CHECK_CUDA(c, cudaMemcpyAsync(z, zk, 3 * (size_t)ld * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
+
+// [OF-ext] PBiCGStab::scalarSolve for the three components at once (set-up of rA, normFactor, initial residual
+// already done by k_pcg_sum / k_pcg_init).  M^-1 is the diagonal (or nothing), the Chebyshev polynomial or the
+// GAMG V-cycle; DIC is stood in for by the diagonal as in the PCG path.
+static int solve_pbicgstab(s4fgpu_ctx* c, double* psi, PcgParams P, double nGlob) {
+    const int N = c->N, ld = c->ld;
+    const int gridV = s4f_grid(c->numSMs, N);
+    PcgScalars* S = c->pcgS.p;
+    for (auto& b : c->bi) if (b.n != 3 * (size_t)ld) S4F_CHECK_CUDA(c, b.alloc(3 * (size_t)ld));
+    double *rA0 = c->bi[0].p, *yA = c->bi[1].p, *AyA = c->bi[2].p, *sA = c->bi[3].p, *zA = c->bi[4].p, *tA = c->bi[5].p;
+    const bool local = (P.precond == S4F_PRECOND_DIAGONAL || P.precond == S4F_PRECOND_NONE);
+    const double* rD = (P.precond == S4F_PRECOND_NONE) ? nullptr : c->rDiagC.p;
+    S4F_CHECK_CUDA(c, cudaMemcpyAsync(rA0, c->rA.p, 3 * (size_t)ld * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    auto precondition = [&](const double* in, double* out) -> int {
+        if (P.precond == S4F_PRECOND_GAMG) return s4f_amg_apply(c, in, out);
+        return cheb_apply(c, P, in, out);
+    };
+    int rc, it = 0;
+    for (;;) {
+        S4F_CHECK_CUDA(c, cudaMemcpyAsync(c->hPcgS, S, sizeof(PcgScalars), cudaMemcpyDeviceToHost, c->stream));
+        S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (!c->hPcgS->anyActive || it >= P.maxIter) break;
+        const int burst = local ? (c->ctl.checkEvery > 0 ? c->ctl.checkEvery : 4) : 1;
+        for (int k = 0; k < burst; k++, it++) {
+            k_bi_rho<<<gridV, S4F_BLOCK, 0, c->stream>>>(rA0, c->rA.p, N, ld, S, P, nGlob, c->partials.p, c->ticket.p);
+            c->launches++;
+            if ((rc = allreduce_part(c, 3, PH_BI_RHO, P, nGlob))) return rc;
+            k_bi_p<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->rA.p, AyA, rD, c->pA.p, local ? yA : nullptr, N, ld, S);
+            c->launches++;
+            if (!local && (rc = precondition(c->pA.p, yA))) return rc;
+            if ((rc = s4f_halo_exchange(c, yA, 3))) return rc;
+            if ((rc = amul3(c, yA, AyA, true, P, nGlob, 7, rA0, PH_BI_ALPHA))) return rc;
+            if ((rc = allreduce_part(c, 3, PH_BI_ALPHA, P, nGlob))) return rc;
+            k_bi_s<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->rA.p, AyA, rD, sA, local ? zA : nullptr, N, ld, S, P, nGlob, c->partials.p, c->ticket.p);
+            c->launches++;
+            if ((rc = allreduce_part(c, 3, PH_BI_S, P, nGlob))) return rc;
+            if (!local && (rc = precondition(sA, zA))) return rc;
+            if ((rc = s4f_halo_exchange(c, zA, 3))) return rc;
+            if ((rc = amul3(c, zA, tA, true, P, nGlob, 7, sA, PH_BI_OMEGA, true))) return rc;
+            if ((rc = allreduce_part(c, 6, PH_BI_OMEGA, P, nGlob))) return rc;
+            k_bi_xr<<<gridV, S4F_BLOCK, 0, c->stream>>>(psi, c->rA.p, yA, zA, sA, tA, N, ld, S, P, nGlob, c->partials.p, c->ticket.p);
+            c->launches++;
+            if ((rc = allreduce_part(c, 3, PH_BI_XR, P, nGlob))) return rc;
+        }
+    }
     return 0;
 }
 
@@ -542,6 +723,18 @@ int s4f_solve_segregated(s4fgpu_ctx* c, double* psi, const double* source) {
     c->launches++;
     rc = allreduce_part(c, 9, PH_INIT, P, nGlob); if (rc) return rc;
 
+    if (c->ctl.solver == S4F_SOLVER_PBICGSTAB) {
+        rc = solve_pbicgstab(c, psi, P, nGlob); if (rc) return rc;
+        for (int q = 0; q < 3; q++) {
+            c->last.initialResidual[q] = c->hPcgS->initRes[q];
+            c->last.finalResidual[q] = c->hPcgS->finalRes[q];
+            c->last.nIterations[q] = c->hPcgS->nIter[q];
+            c->totalInner += c->hPcgS->nIter[q];
+        }
+        S4F_CHECK_CUDA(c, cudaGetLastError());
+        return 0;
+    }
+
     // the host polls the device-side flags every checkEvery iterations (an idle iteration costs three early-exit
     // launches); a multigrid / polynomial application is far dearer than a poll, so those poll every iteration
     const int checkEvery = fusedJacobi ? (c->ctl.checkEvery > 0 ? c->ctl.checkEvery : 4) : 1;
@@ -559,7 +752,7 @@ int s4f_solve_segregated(s4fgpu_ctx* c, double* psi, const double* source) {
                 c->launches++;
             } else {
                 if (P.precond == S4F_PRECOND_GAMG) rc = s4f_amg_apply(c, c->rA.p, c->wA.p);
-                else rc = cheb_apply(c, P);
+                else rc = cheb_apply(c, P, c->rA.p, c->wA.p);
                 if (rc) return rc;
                 k_pcg_dot_zr<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->wA.p, c->rA.p, N, ld, S, P, nGlob, c->partials.p, c->ticket.p);
                 c->launches++;

@@ -278,6 +278,8 @@ int s4f_alloc_model_fields(s4fgpu_ctx* c) {
     };
     const int dT[3] = {0, 4, 8}, dS[3] = {0, 3, 5}, d1[1] = {0};
     if (c->ctlSet && c->incremental()) { S4F_CHECK_CUDA(c, A(c->Dtot, 3)); S4F_CHECK_CUDA(c, A(c->gradDtot, 9)); }
+    if (c->ctlSet && c->ctl.d2dt2Scheme != S4F_D2DT2_STEADY_STATE) { S4F_CHECK_CUDA(c, A(c->d2Hist, 3)); c->histValid = false; }
+    if (c->ctlSet && c->ctl.d2dt2Scheme == S4F_D2DT2_BACKWARD) { S4F_CHECK_CUDA(c, A(c->Dooo, 3)); S4F_CHECK_CUDA(c, A(c->Doooo, 3)); }
     if (TL) {
         if (c->Finv.n != 9 * ld) { S4F_CHECK_CUDA(c, A(c->Finv, 9)); fillI(c->Finv, 9, dT, 3); }
         if (c->Jt.n != ld) { S4F_CHECK_CUDA(c, A(c->Jt, 1)); fillI(c->Jt, 1, d1, 1); }

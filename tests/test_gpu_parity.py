@@ -352,3 +352,61 @@ def test_incremental_tl_model_two_load_steps_match_oracle():
         assert rel_l2(g.get("DD"), o.get("DD")) < 5 * SOLVE_TOL
         assert rel_l2(g.get("sigma"), o.get("sigma")) < SOLVE_TOL
     assert np.abs(o.get("D")[:, 1]).max() > 0.08
+
+
+# ---------------------------------------------------------------------------------------------
+# fvSolution "solver PBiCGStab" and fvSchemes "d2dt2Schemes backward"
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("pre", [K.PRECOND_DIAGONAL, K.PRECOND_NONE])
+def test_pbicgstab_first_iterations_match_oracle(pre):
+    """[OF-ext] PBiCGStab.C: same iterates after a fixed number of iterations (BiCGStab amplifies round-off, so
+    only short runs are compared to round-off level) and the same exit on the half step under relTol 0.1."""
+    rng = np.random.default_rng(11)
+    for relTol, tol, maxIter in ((0.0, 0.0, 1), (0.0, 0.0, 2), (0.0, 0.0, 5), (0.1, 1e-30, 400)):
+        g, o, mesh = _pair(cases.cantilever, nx=12, ny=5, nz=4, solver=K.SOLVER_PBICGSTAB, preconditioner=pre,
+                           tolerance=tol, relTol=relTol, maxIter=maxIter)
+        b = rng.standard_normal((mesh.nCells, 3))
+        x0 = np.zeros((mesh.nCells, 3))
+        psi_g, st_g = g.op_solve(x0, b)
+        psi_o, st_o = o.op_solve(x0, b)
+        assert st_g["nIterations"] == st_o["nIterations"], (maxIter, st_g, st_o)
+        assert np.allclose(st_g["finalResidual"], st_o["finalResidual"], rtol=1e-6, atol=1e-30)
+        assert rel_l2(psi_g, psi_o) < 1e-8, maxIter
+
+
+@pytest.mark.parametrize("pre", [K.PRECOND_DIAGONAL, K.PRECOND_GAMG, K.PRECOND_CHEBYSHEV])
+def test_pbicgstab_converged_beam_matches_pcg_oracle(pre):
+    """Whole momentum loop with PBiCGStab on the device (diagonal, GAMG and polynomial preconditioners) against the
+    oracle's DIC-PCG: converged fields within north_star's 1e-6."""
+    tight = dict(solutionTolerance=1e-10, alternativeTolerance=1e-10, tolerance=1e-13, nCorrectors=5000)
+    from oracle.binding import OracleSolid
+    from solids4foam_b200.solid_model import SolidModel
+    g = SolidModel(cases.cantilever(10, 4, 4, L=2.0, solver=K.SOLVER_PBICGSTAB, preconditioner=pre, **tight))
+    o = OracleSolid(cases.cantilever(10, 4, 4, L=2.0, preconditioner=K.PRECOND_DIC, **tight))
+    sg, so = g.evolve(), o.evolve()
+    assert sg["converged"] and so["converged"]
+    assert rel_l2(g.get("D"), o.get("D")) < SOLVE_TOL
+    assert rel_l2(g.get("sigma"), o.get("sigma")) < SOLVE_TOL
+
+
+def test_backward_d2dt2_time_steps_match_oracle():
+    """rho*fvm::d2dt2(D) with s4f's backward scheme (backwardD2dt2Scheme.C:309-395): start-up coefficients of the
+    first step, then the four-level old-time chain, over six time steps of a beam released under gravity."""
+    dt = 2e-4
+    kw = dict(nx=8, ny=3, nz=3, L=2.0, d2dt2Scheme=K.D2DT2_BACKWARD, deltaT=dt, deltaT0=dt, nCorrectors=40,
+              g=(0.0, -9.81, 0.0), **EXACT_PCG)
+    g, o, mesh = _pair(cases.cantilever, **kw)
+    for step in range(6):
+        for s in (g, o):
+            s.new_timestep(dt)
+        sg, so = g.evolve(), o.evolve()
+        assert sg["nCorr"] == so["nCorr"]
+        assert rel_l2(g.get("D"), o.get("D")) < 1e-8, step
+        assert rel_l2(g.get("sigma"), o.get("sigma")) < 1e-7, step
+    assert np.abs(o.get("D")).max() > 0
+    # operator level: diagonal and source of the seventh step
+    for s in (g, o):
+        s.new_timestep(dt)
+        s.op_assemble()
+    assert rel_l2(g.get("diag"), o.get("diag")) < OP_TOL
+    assert np.abs(g.get("source") - o.get("source")).max() / np.abs(o.get("source")).max() < 1e-11
