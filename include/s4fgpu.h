@@ -105,7 +105,9 @@ enum {
     S4F_FIELD_TRACTION_GRADIENT_B = 19, /* vector [B]: fixedGradient gradient() of traction patches */
     S4F_FIELD_EPSILON_P = 20,    /* symmTensor [N] */
     S4F_FIELD_DD = 21,           /* vector [N]  displacement increment (incremental solid models only) */
-    S4F_FIELD_GRAD_DD = 22       /* tensor [N] */
+    S4F_FIELD_GRAD_DD = 22,      /* tensor [N] */
+    S4F_FIELD_RHO = 23,          /* scalar [N]  density field of the updated-Lagrangian model (rho_ = rho_.oldTime()/relJ_) */
+    S4F_FIELD_DD_B = 24          /* vector [B]  boundary values of DD */
 };
 
 /* ---- parameter blocks ---------------------------------------------------------------------- */
@@ -195,6 +197,24 @@ int s4fgpu_set_geometry(s4fgpu_handle h, const double* C, const double* V, const
                         const double* magSf, const double* Cf, const double* weights,
                         const double* nonOrthDeltaCoeffs, const double* nonOrthCorrVec,
                         const double* CnbrB);
+
+/* ---- point mesh: vol -> point interpolation and mesh motion --------------------------------- */
+
+/* polyMesh points() and faces() of the fv faces mirrored by set_mesh (internal faces, then the boundary
+ * faces in patch order; faceVertsPtr [F+B+1] CSR offsets into faceVerts).  Builds pointCells and the
+ * boundary pointFaces addressing that volPointInterpolation needs.  Re-callable with moved points (same
+ * topology): the inverse-distance weights are recomputed from the geometry of the last set_geometry.
+ * Reference: mesh().points()/faces() as used by enhancedVolPointInterpolation.C:60-250
+ * (src/blockCoupledSolids4FoamTools/enhancedVolPointInterpolation) and solidModel::moveMesh
+ * (SM/solidModel/solidModel.C:2008-2148). */
+int s4fgpu_set_points(s4fgpu_handle h, int nPoints, const double* points, const int* faceVertsPtr,
+                      const int* faceVerts);
+
+/* mechanicalModel::interpolate(D, pointD) (mechanicalModel.C:786-826) -> volToPoint().interpolate(vf, pf)
+ * (enhancedVolPointInterpolate.C:425-447): inverse-distance weighting from the cell centres for internal
+ * points, from the boundary-face values for points on non-empty, non-coupled patches, then the
+ * symmetry-plane point constraint.  field = S4F_FIELD_D or S4F_FIELD_DD; pointField [3*nPoints] host. */
+int s4fgpu_interpolate_to_points(s4fgpu_handle h, int field, double* pointField);
 
 /* ---- models ---------------------------------------------------------------------------------- */
 

@@ -102,8 +102,21 @@ class OracleSolid:
         self._check(self.L.s4fo_evolve(self.h, C.byref(st)))
         return st.as_dict()
 
+    def interpolate_to_points(self, name: str = "D") -> np.ndarray:
+        out = np.empty((self.case.mesh.points.shape[0], 3))
+        self._check(self.L.s4fo_interpolate_to_points(self.h, K.FIELD[name], K._dptr(out)))
+        return out
+
     def update_total_fields(self):
+        if self.case.controls.solidModel == K.MODEL_NONLIN_UL:
+            pointDD = self.interpolate_to_points("DD")
+            self._check(self.L.s4fo_update_total_fields(self.h))
+            K.move_mesh(self.L, "s4fo_", self.h, self.case, pointDD, self._check)
+            self.pointDD = pointDD
+            return
         self._check(self.L.s4fo_update_total_fields(self.h))
+
+    updateTotalFields = update_total_fields
 
     def op_grad(self):
         self._check(self.L.s4fo_op_grad(self.h))

@@ -136,6 +136,12 @@ struct s4f_oracle {
     // (D = D.oldTime() + DD :190, gradD = gradD.oldTime() + gradDD :196).
     dvec D, Dprev, Dold, DoldOld, gradD, gradDold, sigma, sigmaOld, Dtot, gradDtot;
     dvec Dooo, Doooo;              // third / fourth old-time level (backward d2dt2 only)
+    // updated-Lagrangian model (SM/nonLinGeomUpdatedLagSolid): the old-time chains that
+    // fvm::d2dt2(rho, DD) + fvc::d2dt2(rho, D.oldTime()) reach, and the density field with its old times
+    dvec Dooooo, DDo, DDoo, DDooo, DDoooo, rho, rhoO, rhoOO;
+    // polyMesh points/faces for vol->point interpolation
+    int nPoints = 0;
+    dvec points; ivec fvPtr, fv, pcPtr, pcCells, pbPtr, pbFaces;
     int timeIndex = 0;             // number of new_timestep() calls (runTime.timeIndex())
     dvec impK, impKf;              // impK (N+B), impKf (F+B)
     dvec Ft, Finv, Jt;             // solver-level F, Finv, J of the TL models
@@ -162,6 +168,7 @@ struct s4f_oracle {
 
     int NB() const { return N + B; }
     bool incremental() const { return ctl.solidModel == S4F_MODEL_NONLIN_TL || ctl.solidModel == S4F_MODEL_NONLIN_UL; }
+    bool UL() const { return ctl.solidModel == S4F_MODEL_NONLIN_UL; }
     const dvec& gradForLaw() const { return incremental() ? gradDtot : gradD; }   // the registered "grad(D)"
 };
 
@@ -350,13 +357,14 @@ void bcEvaluate(s4f_oracle& o) {
 // [OF-ext] Gauss linear; then gaussGrad::correctBoundaryConditions: grad_b = grad_P + n (snGrad_b - n & grad_P).
 // mechanicalModel::grad, mechanicalModel.C:571-582.
 // ------------------------------------------------------------------------------------------------
-void calcGrad(s4f_oracle& o) {
+// cell values of fvc::grad(X) for a vol field X given as [internal | boundary] values
+void gradInterior(const s4f_oracle& o, const dvec& X, dvec& g) {
     const int N = o.N, F = o.F, B = o.B;
-    dvec g(9 * (N + B), 0.0);
+    g.assign(9 * (size_t)(N + B), 0.0);
     if (o.ctl.gradScheme == S4F_GRAD_LEAST_SQUARES) {
         forAllInternalFaces(o, [&](int f) {
             int P = o.own[f], Nn = o.nei[f];
-            double dv[3] = {o.D[3 * Nn] - o.D[3 * P], o.D[3 * Nn + 1] - o.D[3 * P + 1], o.D[3 * Nn + 2] - o.D[3 * P + 2]};
+            double dv[3] = {X[3 * Nn] - X[3 * P], X[3 * Nn + 1] - X[3 * P + 1], X[3 * Nn + 2] - X[3 * P + 2]};
             for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
                 g[9 * P + 3 * i + j] += o.lsP[3 * f + i] * dv[j];
                 g[9 * Nn + 3 * i + j] -= o.lsN[3 * f + i] * dv[j];
@@ -364,7 +372,7 @@ void calcGrad(s4f_oracle& o) {
         });
         for (int b = 0; b < B; b++) {
             int P = o.faceCells[b];
-            double dv[3] = {o.D[3 * (N + b)] - o.D[3 * P], o.D[3 * (N + b) + 1] - o.D[3 * P + 1], o.D[3 * (N + b) + 2] - o.D[3 * P + 2]};
+            double dv[3] = {X[3 * (N + b)] - X[3 * P], X[3 * (N + b) + 1] - X[3 * P + 1], X[3 * (N + b) + 2] - X[3 * P + 2]};
             for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) g[9 * P + 3 * i + j] += o.lsP[3 * (F + b) + i] * dv[j];
         }
     } else {
@@ -372,7 +380,7 @@ void calcGrad(s4f_oracle& o) {
             int P = o.own[f], Nn = o.nei[f];
             double wf = o.w[f];
             for (int j = 0; j < 3; j++) {
-                double vf = wf * o.D[3 * P + j] + (1 - wf) * o.D[3 * Nn + j];
+                double vf = wf * X[3 * P + j] + (1 - wf) * X[3 * Nn + j];
                 for (int i = 0; i < 3; i++) {
                     double t = o.Sf[3 * f + i] * vf;
                     g[9 * P + 3 * i + j] += t; g[9 * Nn + 3 * i + j] -= t;
@@ -381,10 +389,15 @@ void calcGrad(s4f_oracle& o) {
         });
         for (int b = 0; b < B; b++) {
             int P = o.faceCells[b];
-            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) g[9 * P + 3 * i + j] += o.Sf[3 * (F + b) + i] * o.D[3 * (N + b) + j];
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) g[9 * P + 3 * i + j] += o.Sf[3 * (F + b) + i] * X[3 * (N + b) + j];
         }
         for (int c = 0; c < N; c++) for (int q = 0; q < 9; q++) g[9 * c + q] /= o.V[c];
     }
+}
+
+void calcGrad(s4f_oracle& o) {
+    const int N = o.N;
+    dvec g; gradInterior(o, o.D, g);
     // boundary: extrapolate then correct the normal component with the BC's snGrad (which reads the
     // OLD registered grad(D) -- the assignment gradD = fvc::grad(D) happens after the evaluation)
     for (int p = 0; p < o.nPatches; p++) for (int i2 = 0; i2 < o.pSize[p]; i2++) {
@@ -397,6 +410,23 @@ void calcGrad(s4f_oracle& o) {
         for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) gb[3 * i + j] += n[i] * (sn[j] - ng[j]);
     }
     o.gradD.swap(g);
+}
+
+// fvc::grad of a temporary with calculated patches, e.g. gradD() = fvc::grad(D().oldTime() + DD()) after the
+// updated-Lagrangian loop (nonLinGeomUpdatedLagSolid.C:243): snGrad_b = deltaCoeffs (X_b - X_P) [OF-ext] fvPatchField::snGrad
+void gradCalculated(const s4f_oracle& o, const dvec& X, dvec& g) {
+    const int N = o.N, F = o.F;
+    gradInterior(o, X, g);
+    for (int b = 0; b < o.B; b++) {
+        const int P = o.faceCells[b];
+        double n[3], k[3], delta; patchGeom(o, b, n, k, delta);
+        (void)F;
+        double sn[3]; for (int j = 0; j < 3; j++) sn[j] = delta * (X[3 * (N + b) + j] - X[3 * P + j]);
+        double* gb = &g[9 * (N + b)];
+        for (int q = 0; q < 9; q++) gb[q] = g[9 * P + q];
+        double ng[3]; vT(n, gb, ng);
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) gb[3 * i + j] += n[i] * (sn[j] - ng[j]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -427,6 +457,15 @@ void lawLinearElastic(s4f_oracle& o) {
 void lawUpdateF(s4f_oracle& o) {
     const int n = o.NB();
     const dvec& gD = o.gradForLaw();
+    if (o.UL()) {          // updated Lagrangian :1055-1072: relF = I + gradDD.T(); F = relF & F.oldTime()
+        for (int c = 0; c < n; c++) {
+            double* rF = &o.relF[9 * c];
+            transposeT(&o.gradD[9 * c], rF);
+            rF[0] += 1; rF[4] += 1; rF[8] += 1;
+            mulTT(rF, &o.lawFold[9 * c], &o.lawF[9 * c]);
+        }
+        return;
+    }
     for (int c = 0; c < n; c++) {
         double Ft[9]; transposeT(&gD[9 * c], Ft);
         Ft[0] += 1; Ft[4] += 1; Ft[8] += 1;
@@ -643,7 +682,9 @@ double lawResidual(const s4f_oracle& o) {
 // SM/nonLinGeomTotalLagTotalDispSolid/nonLinGeomTotalLagTotalDispSolid.C:225-232
 void updateKinematics(s4f_oracle& o) {
     const int n = o.NB();
-    const dvec& gD = o.gradForLaw();
+    // updated Lagrangian: the relative kinematics relF = I + gradDD.T(), relFinv, relJ take the place of F, Finv, J in
+    // fvc::div(relJ*relFinv & sigma) and in the traction boundary (nonLinGeomUpdatedLagSolid.C:188, :199-215, :283-288)
+    const dvec& gD = o.UL() ? o.gradD : o.gradForLaw();
     for (int c = 0; c < n; c++) {
         double* Fm = &o.Ft[9 * c];
         transposeT(&gD[9 * c], Fm); Fm[0] += 1; Fm[4] += 1; Fm[8] += 1;
@@ -687,6 +728,52 @@ D2dt2Coeffs d2dt2Coeffs(const s4fgpu_controls& ctl, double rho, int timeIndex) {
     return k;
 }
 
+// Updated-Lagrangian inertia, SM/nonLinGeomUpdatedLagSolid/nonLinGeomUpdatedLagSolid.C:173-176:
+//     fvm::d2dt2(rho_, DD()) + fvc::d2dt2(rho_, D().oldTime())
+// with the density FIELD rho_ (rho_ = rho_.oldTime()/relJ_ in updateTotalFields :362) on the mesh of the current
+// (updated) configuration, mesh.moving() == false.  Returned: the diagonal coefficient (to be multiplied by
+// rho_P V_P) and, per cell, the explicit part per unit volume (to be multiplied by V_P) INCLUDING rho_P*g.
+//  backward  NUM/backwardD2dt2Scheme/backwardD2dt2Scheme.C:149-222 (fvc, rho field) and :391-470 (fvm, rho field):
+//      fvm = c rho rDeltaT fvmDdt(DD);  source += rDeltaT V (c0 rho.o ddt(DD.o) - c00 rho.oo ddt(DD.oo))
+//      fvc = rDeltaT (c rho ddt(Y) - c0 rho.o ddt(Y.o) + c00 rho.oo ddt(Y.oo)),  Y = D.oldTime()
+//      ddt(X) = rDeltaT (b X - b0 X.o + b00 X.oo)  [OF-ext] backwardDdtScheme, b = 1.5, b0 = 2, b00 = 0.5
+//    deltaT0_(vf) == GREAT (c = c0 = 1, c00 = 0) while vf.oldTime() and vf.oldTime().oldTime() carry the same time
+//    index (:48-68): during time step 1 for vf = DD, during time steps 1 and 2 for vf = D.oldTime().  All old-time
+//    levels are created in the constructor (:143-145) as copies of the initial field.
+//  Euler     [OF-ext] EulerD2dt2Scheme, rho-field overloads on a static mesh:
+//      fvm: diag = coefft rDeltaT2 rho V, source = rDeltaT2 V rho ((coefft + coefft00) DD.o - coefft00 DD.oo)
+//      fvc: rDeltaT2 rho (coefft Y - (coefft + coefft00) Y.o + coefft00 Y.oo)
+double ulD2dt2(const s4f_oracle& o, dvec& hist) {
+    const int N = o.N;
+    hist.assign(3 * (size_t)N, 0.0);
+    for (int c = 0; c < N; c++) for (int q = 0; q < 3; q++) hist[3 * c + q] = o.rho[c] * o.ctl.g[q];     // rho_*g()
+    if (o.ctl.d2dt2Scheme == S4F_D2DT2_STEADY_STATE) return 0.0;
+    const double dt = o.ctl.deltaT, dt0 = o.ctl.deltaT0 > 0 ? o.ctl.deltaT0 : dt;
+    if (o.ctl.d2dt2Scheme == S4F_D2DT2_EULER) {
+        const double cf = (dt + dt0) / (2 * dt), cf00 = (dt + dt0) / (2 * dt0), r2 = 4.0 / ((dt + dt0) * (dt + dt0));
+        for (int c = 0; c < N; c++) for (int q = 0; q < 3; q++) {
+            const int i = 3 * c + q;
+            hist[i] += r2 * o.rho[c] * ((cf + cf00) * o.DDo[i] - cf00 * o.DDoo[i])
+                     - r2 * o.rho[c] * (cf * o.Dold[i] - (cf + cf00) * o.DoldOld[i] + cf00 * o.Dooo[i]);
+        }
+        return cf * r2;
+    }
+    const bool firstM = o.timeIndex <= 1, firstC = o.timeIndex <= 2;
+    const double kb = 1.0 + dt / (dt + dt0), kb00 = dt * dt / (dt0 * (dt + dt0)), kb0 = kb + kb00;
+    const double cm = firstM ? 1.0 : kb, cm00 = firstM ? 0.0 : kb00, cm0 = cm + cm00;
+    const double cc = firstC ? 1.0 : kb, cc00 = firstC ? 0.0 : kb00, cc0 = cc + cc00;
+    const double r = 1.0 / (dt * dt);
+    auto ddt = [&](const dvec& X, const dvec& Xo, const dvec& Xoo, int i) { return kb * X[i] - kb0 * Xo[i] + kb00 * Xoo[i]; };
+    for (int c = 0; c < N; c++) for (int q = 0; q < 3; q++) {
+        const int i = 3 * c + q;
+        hist[i] += r * (cm * o.rho[c] * (kb0 * o.DDo[i] - kb00 * o.DDoo[i])
+                        + cm0 * o.rhoO[c] * ddt(o.DDo, o.DDoo, o.DDooo, i) - cm00 * o.rhoOO[c] * ddt(o.DDoo, o.DDooo, o.DDoooo, i)
+                        - cc * o.rho[c] * ddt(o.Dold, o.DoldOld, o.Dooo, i) + cc0 * o.rhoO[c] * ddt(o.DoldOld, o.Dooo, o.Doooo, i)
+                        - cc00 * o.rhoOO[c] * ddt(o.Dooo, o.Doooo, o.Dooooo, i));
+    }
+    return r * cm * kb;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Momentum equation  (SM/linGeomTotalDispSolid/linGeomTotalDispSolid.C:141-149)
 //
@@ -709,7 +796,10 @@ void assembleMatrix(s4f_oracle& o) {
         double a = o.impKf[f] * o.nod[f] * o.magSf[f];
         o.upper[f] = -a; o.diag[o.own[f]] += a; o.diag[o.nei[f]] += a;
     }
-    if (o.ctl.d2dt2Scheme != S4F_D2DT2_STEADY_STATE) {
+    if (o.UL()) {
+        dvec hist; const double kd = ulD2dt2(o, hist);
+        for (int c = 0; c < N; c++) o.diag[c] += kd * o.rho[c] * o.V[c];
+    } else if (o.ctl.d2dt2Scheme != S4F_D2DT2_STEADY_STATE) {
         const D2dt2Coeffs k = d2dt2Coeffs(o.ctl, o.law.rho, o.timeIndex);
         for (int c = 0; c < N; c++) o.diag[c] += k.diag * o.V[c];
     }
@@ -738,7 +828,10 @@ void assembleSource(s4f_oracle& o) {
     o.source.assign(3 * N, 0.0);
     dvec& s = o.source;
     // d2dt2 old-time terms
-    if (o.ctl.d2dt2Scheme != S4F_D2DT2_STEADY_STATE) {
+    if (o.UL()) {
+        dvec hist; ulD2dt2(o, hist);
+        for (int c = 0; c < N; c++) for (int q = 0; q < 3; q++) s[3 * c + q] += o.V[c] * hist[3 * c + q];
+    } else if (o.ctl.d2dt2Scheme != S4F_D2DT2_STEADY_STATE) {
         const D2dt2Coeffs k = d2dt2Coeffs(o.ctl, o.law.rho, o.timeIndex);
         const bool deep = o.ctl.d2dt2Scheme == S4F_D2DT2_BACKWARD && o.timeIndex > 1;   // before: D.ooo = D.oooo = D.oo (copies)
         const dvec& D3 = deep ? o.Dooo : o.DoldOld;
@@ -776,8 +869,8 @@ void assembleSource(s4f_oracle& o) {
         double fl[3]; vT(&o.Sf[3 * (F + b)], &T[9 * (N + b)], fl);
         for (int q = 0; q < 3; q++) s[3 * o.faceCells[b] + q] += fl[q];
     }
-    // + V*rho*g
-    for (int c = 0; c < N; c++) for (int q = 0; q < 3; q++) s[3 * c + q] += o.V[c] * o.law.rho * o.ctl.g[q];
+    // + V*rho*g  (updated Lagrangian: the rho_ field, already in hist)
+    if (!o.UL()) for (int c = 0; c < N; c++) for (int q = 0; q < 3; q++) s[3 * c + q] += o.V[c] * o.law.rho * o.ctl.g[q];
     // + V*stabilisation: RhieChow, SM/solidModel/momentumStabilisation/momentumStabilisation.C:112-114
     // (gamma = scaleFactor*impK), :119 (linear interpolate), :198-206 (zero on non-coupled boundaries),
     // :210-217  fvc::laplacian(gammaf, D) - fvc::div(gammaf*(Sf & interpolate(gradD)))
@@ -1105,6 +1198,8 @@ void allocFields(s4f_oracle& o) {
     z(o.D, 3); z(o.Dprev, 3); z(o.Dold, 3); z(o.DoldOld, 3); z(o.gradD, 9); z(o.gradDold, 9); z(o.sigma, 6); z(o.sigmaOld, 6);
     z(o.Dtot, 3); z(o.gradDtot, 9);
     z(o.epsilon, 6); z(o.sigmaHyd, 1);
+    z(o.Dooo, 3); z(o.Doooo, 3); z(o.Dooooo, 3); z(o.DDo, 3); z(o.DDoo, 3); z(o.DDooo, 3); z(o.DDoooo, 3);
+    if ((int)o.rho.size() != n) { o.rho.assign(n, o.law.rho); o.rhoO = o.rho; o.rhoOO = o.rho; }
     if ((int)o.Ft.size() != 9 * n) {
         o.Ft.assign(9 * n, 0.0); o.Finv.assign(9 * n, 0.0); o.Jt.assign(n, 1.0);
         o.lawF.assign(9 * n, 0.0); o.lawFold.assign(9 * n, 0.0); o.relF.assign(9 * n, 0.0);
@@ -1118,16 +1213,21 @@ void allocFields(s4f_oracle& o) {
     }
 }
 
-void setupLaw(s4f_oracle& o) {
+// impK and impKf = fvc::interpolate(impK) (mechanicalModel.C:409-415); the face values follow the mesh weights
+void setupImpK(s4f_oracle& o) {
     const int n = o.NB(), F = o.F, B = o.B;
     // impK: linearElastic.C:204-245 (2mu+lambda), neoHookeanElastic.C:101-119 and Mises at DLambda=0: 4/3 mu + K
     double impK = (o.law.kind == S4F_LAW_LINEAR_ELASTIC || o.law.kind == S4F_LAW_LINEAR_ELASTIC_MISES_PLASTIC)
                       ? 2.0 * o.law.mu + o.law.lambda : (4.0 / 3.0) * o.law.mu + o.law.K;
     o.impK.assign(n, impK);
-    // impKf = fvc::interpolate(impK), mechanicalModel.C:409-415
     o.impKf.assign(F + B, 0.0);
     for (int f = 0; f < F; f++) o.impKf[f] = o.w[f] * o.impK[o.own[f]] + (1 - o.w[f]) * o.impK[o.nei[f]];
     for (int b = 0; b < B; b++) o.impKf[F + b] = o.impK[o.N + b];
+}
+
+void setupLaw(s4f_oracle& o) {
+    setupImpK(o);
+    std::fill(o.rho.begin(), o.rho.end(), o.law.rho); o.rhoO = o.rho; o.rhoOO = o.rho;     // rho_(mechanical().rho())
     o.Hp = 0;
     if (o.law.nTable == 2) o.Hp = (o.law.tableSigY[1] - o.law.tableSigY[0]) / (o.law.tableEps[1] - o.law.tableEps[0]);
     if (o.law.nTable >= 1) { std::fill(o.sigmaY.begin(), o.sigmaY.end(), tableLookup(o.law, 0.0)); o.sigmaYOld = o.sigmaY; }
@@ -1168,9 +1268,92 @@ int s4fo_set_geometry(s4f_oracle* o, const double* C, const double* V, const dou
     o->C.assign(C, C + 3 * N); o->V.assign(V, V + N); o->Sf.assign(Sf, Sf + 3 * FB); o->magSf.assign(magSf, magSf + FB);
     o->Cf.assign(Cf, Cf + 3 * FB); o->w.assign(weights, weights + FB); o->nod.assign(nod, nod + FB);
     o->corr.assign(corr, corr + 3 * FB); o->CnbrB.assign(CnbrB, CnbrB + 3 * o->B);
+    const bool again = !o->impK.empty() && (int)o->D.size() == 3 * o->NB();   // mesh motion: fields, BC data and history stay
     makeLeastSquaresVectors(*o);
     allocFields(*o);
+    if (again) setupImpK(*o);
     o->matrixValid = false;
+    return 0;
+}
+
+// polyMesh points and faces; pointCells [OF-ext primitiveMesh::pointCells] and the boundary pointFaces
+// (enhancedVolPointInterpolation.C:60-160: boundary faces of non-empty, non-coupled patches)
+int s4fo_set_points(s4f_oracle* o, int nPoints, const double* points, const int* faceVertsPtr, const int* faceVerts) {
+    const int F = o->F, B = o->B;
+    o->nPoints = nPoints; o->points.assign(points, points + 3 * (size_t)nPoints);
+    o->fvPtr.assign(faceVertsPtr, faceVertsPtr + F + B + 1); o->fv.assign(faceVerts, faceVerts + faceVertsPtr[F + B]);
+    std::vector<std::vector<int>> pc(nPoints), pb(nPoints);
+    auto add = [](std::vector<int>& v, int x) { if (std::find(v.begin(), v.end(), x) == v.end()) v.push_back(x); };
+    for (int f = 0; f < F + B; f++) for (int j = o->fvPtr[f]; j < o->fvPtr[f + 1]; j++) {
+        const int p = o->fv[j];
+        if (p < 0 || p >= nPoints) { o->err = "set_points: vertex out of range"; return 1; }
+        add(pc[p], f < F ? o->own[f] : o->faceCells[f - F]);
+        if (f < F) add(pc[p], o->nei[f]);
+    }
+    for (int ip = 0; ip < o->nPatches; ip++) {
+        if (o->pKind[ip] == S4F_PATCH_PROCESSOR) continue;
+        for (int i = 0; i < o->pSize[ip]; i++) {
+            const int b = o->pStart[ip] + i;
+            for (int j = o->fvPtr[F + b]; j < o->fvPtr[F + b + 1]; j++) pb[o->fv[j]].push_back(b);
+        }
+    }
+    o->pcPtr.assign(1, 0); o->pcCells.clear(); o->pbPtr.assign(1, 0); o->pbFaces.clear();
+    for (int p = 0; p < nPoints; p++) {
+        std::sort(pc[p].begin(), pc[p].end());
+        o->pcCells.insert(o->pcCells.end(), pc[p].begin(), pc[p].end()); o->pcPtr.push_back((int)o->pcCells.size());
+        o->pbFaces.insert(o->pbFaces.end(), pb[p].begin(), pb[p].end()); o->pbPtr.push_back((int)o->pbFaces.size());
+    }
+    return 0;
+}
+
+// volToPoint().interpolate(vf, pf), enhancedVolPointInterpolate.C:425-447: interpolateInternalField :125-158 with the
+// inverse-distance weights of enhancedVolPointInterpolation.C:165-198 for points off the patches, interpolateBoundaryField
+// :262-330 with the weights of :201-245 from the boundary-face values for patch points, then pointConstraints::constrain
+// ([OF-ext]: symmetryPlane points lose their normal component, transform(I - nn, pf)).
+int s4fo_interpolate_to_points(s4f_oracle* o, int field, double* out) {
+    if (o->nPoints == 0) { o->err = "interpolate_to_points: call set_points first"; return 1; }
+    const dvec* X = nullptr;
+    if (field == S4F_FIELD_D) X = o->incremental() ? &o->Dtot : &o->D;
+    else if (field == S4F_FIELD_DD && o->incremental()) X = &o->D;
+    if (!X) { o->err = "interpolate_to_points: field must be D or DD"; return 1; }
+    const int N = o->N, F = o->F;
+    for (int p = 0; p < o->nPoints; p++) {
+        const double* x = &o->points[3 * (size_t)p];
+        double acc[3] = {0, 0, 0}, sw = 0;
+        if (o->pbPtr[p + 1] > o->pbPtr[p]) {
+            for (int j = o->pbPtr[p]; j < o->pbPtr[p + 1]; j++) {
+                const int b = o->pbFaces[j];
+                const double* cf = &o->Cf[3 * (size_t)(F + b)];
+                const double d[3] = {x[0] - cf[0], x[1] - cf[1], x[2] - cf[2]};
+                const double w = 1.0 / mag3(d);
+                for (int q = 0; q < 3; q++) acc[q] += w * (*X)[3 * (size_t)(N + b) + q];
+                sw += w;
+            }
+        } else {
+            for (int j = o->pcPtr[p]; j < o->pcPtr[p + 1]; j++) {
+                const int c = o->pcCells[j];
+                const double d[3] = {x[0] - o->C[3 * (size_t)c], x[1] - o->C[3 * (size_t)c + 1], x[2] - o->C[3 * (size_t)c + 2]};
+                const double w = 1.0 / mag3(d);
+                for (int q = 0; q < 3; q++) acc[q] += w * (*X)[3 * (size_t)c + q];
+                sw += w;
+            }
+        }
+        for (int q = 0; q < 3; q++) out[3 * (size_t)p + q] = acc[q] / sw;
+    }
+    for (int ip = 0; ip < o->nPatches; ip++) {
+        if (o->pKind[ip] != S4F_PATCH_SYMMETRY || o->pSize[ip] == 0) continue;
+        double n[3] = {0, 0, 0};                      // symmetryPlanePolyPatch::n(): the (planar) patch normal
+        for (int i = 0; i < o->pSize[ip]; i++) for (int q = 0; q < 3; q++) n[q] += o->Sf[3 * (size_t)(F + o->pStart[ip] + i) + q];
+        const double m = mag3(n); for (int q = 0; q < 3; q++) n[q] /= m;
+        for (int i = 0; i < o->pSize[ip]; i++) {
+            const int b = o->pStart[ip] + i;
+            for (int j = o->fvPtr[F + b]; j < o->fvPtr[F + b + 1]; j++) {
+                double* v = &out[3 * (size_t)o->fv[j]];
+                const double nv = dot3(n, v);
+                for (int q = 0; q < 3; q++) v[q] -= n[q] * nv;
+            }
+        }
+    }
     return 0;
 }
 
@@ -1215,6 +1398,8 @@ static dvec* fieldPtr(s4f_oracle* o, int field, int& ncomp, int& off, int& count
         case S4F_FIELD_DEPSILON_P: ncomp = 6; return &o->DEpsP;
         case S4F_FIELD_EPSILON_P: ncomp = 6; return &o->epsP;
         case S4F_FIELD_TRACTION_GRADIENT_B: ncomp = 3; count = B; return &o->tracGrad;
+        case S4F_FIELD_RHO: ncomp = 1; return &o->rho;
+        case S4F_FIELD_DD_B: ncomp = 3; off = N; count = B; return o->incremental() ? &o->D : nullptr;
     }
     return nullptr;
 }
@@ -1245,9 +1430,20 @@ int s4fo_initialise(s4f_oracle* o) {
 
 int s4fo_new_timestep(s4f_oracle* o, double deltaT) {
     o->ctl.deltaT0 = o->ctl.deltaT; o->ctl.deltaT = deltaT;
-    if (o->ctl.d2dt2Scheme == S4F_D2DT2_BACKWARD) {     // GeometricField::storeOldTimes over the four-level chain
+    if (o->ctl.d2dt2Scheme == S4F_D2DT2_BACKWARD && !o->UL()) {     // GeometricField::storeOldTimes over the four-level chain
         if (o->timeIndex >= 2) { o->Doooo = o->Dooo; o->Dooo = o->DoldOld; }
         else { o->Doooo = o->DoldOld; o->Dooo = o->DoldOld; }
+    }
+    if (o->UL()) {     // GeometricField::storeOldTimes over the chains created in the constructor (:143-145)
+        if (o->timeIndex == 0) {
+            o->Dooo = o->DoldOld; o->Doooo = o->DoldOld; o->Dooooo = o->DoldOld;
+            o->DDo = o->D; o->DDoo = o->D; o->DDooo = o->D; o->DDoooo = o->D;
+            o->rhoO = o->rho; o->rhoOO = o->rho;
+        }
+        o->Dooooo = o->Doooo; o->Doooo = o->Dooo; o->Dooo = o->DoldOld;
+        o->DDoooo = o->DDooo; o->DDooo = o->DDoo; o->DDoo = o->DDo; o->DDo = o->D;
+        o->rhoOO = o->rhoO; o->rhoO = o->rho;
+        o->matrixValid = false;       // rho_ and the mesh changed in updateTotalFields
     }
     o->timeIndex++;
     o->DoldOld = o->Dold;
@@ -1279,6 +1475,15 @@ int s4fo_evolve(s4f_oracle* o, s4fgpu_stats* st) {
 
 // updateTotalFields: neoHookeanElasticMisesPlastic.C:1526-1536 (history commit)
 int s4fo_update_total_fields(s4f_oracle* o) {
+    if (o->UL()) {
+        // after the loop, nonLinGeomUpdatedLagSolid.C:243: gradD() = fvc::grad(D().oldTime() + DD()) (calculated patches)
+        gradCalculated(*o, o->Dtot, o->gradDtot);
+        // updateTotalFields :360-374: rho_ = rho_.oldTime()/relJ_; the mesh motion itself is done by the host
+        // (s4fo_interpolate_to_points -> new points -> s4fo_set_geometry), then solidModel::updateTotalFields()
+        const int n = o->NB();
+        for (int c = 0; c < n; c++) o->rho[c] = o->rhoO[c] / o->Jt[c];
+        o->matrixValid = false;
+    }
     if (o->law.kind == S4F_LAW_NEO_HOOKEAN_MISES_PLASTIC) {
         const int n = o->NB();
         for (int c = 0; c < n; c++) { o->sigmaY[c] += o->DSigmaY[c]; o->epsPEq[c] += o->DEpsPEq[c]; }

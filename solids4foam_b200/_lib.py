@@ -20,7 +20,8 @@ EXPORTS = ["s4fgpu_create", "s4fgpu_destroy", "s4fgpu_last_error", "s4fgpu_versi
            "s4fgpu_set_bc", "s4fgpu_upload", "s4fgpu_download", "s4fgpu_initialise", "s4fgpu_new_timestep",
            "s4fgpu_outer_iteration", "s4fgpu_evolve", "s4fgpu_update_total_fields", "s4fgpu_op_grad",
            "s4fgpu_op_correct", "s4fgpu_op_assemble", "s4fgpu_op_amul", "s4fgpu_op_solve", "s4fgpu_time_kernel",
-           "s4fgpu_launch_count", "s4fgpu_gamg_info", "s4fgpu_timer_start", "s4fgpu_timer_stop", "s4fgpu_synchronize"]
+           "s4fgpu_launch_count", "s4fgpu_gamg_info", "s4fgpu_timer_start", "s4fgpu_timer_stop", "s4fgpu_synchronize",
+           "s4fgpu_set_points", "s4fgpu_interpolate_to_points"]
 
 
 def _preload_nccl():

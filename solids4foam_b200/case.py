@@ -32,13 +32,13 @@ PRECOND_NONE, PRECOND_DIAGONAL, PRECOND_DIC, PRECOND_CHEBYSHEV, PRECOND_GAMG = 0
 
 FIELD = dict(D=0, D_old=1, D_oldOld=2, gradD=3, sigma=4, D_b=5, gradD_b=6, sigma_b=7, source=8, diag=9,
              upper=10, epsilonPEq=11, sigmaY=12, bEbar=13, DLambda=14, J=15, F=16, gradD_old=17,
-             DEpsilonP=18, tractionGradient_b=19, epsilonP=20, DD=21, gradDD=22)
+             DEpsilonP=18, tractionGradient_b=19, epsilonP=20, DD=21, gradDD=22, rho=23, DD_b=24)
 # (ncomp, 'N' | 'B' | 'F')
 FIELD_SHAPE = dict(D=(3, "N"), D_old=(3, "N"), D_oldOld=(3, "N"), gradD=(9, "N"), sigma=(6, "N"), D_b=(3, "B"),
                    gradD_b=(9, "B"), sigma_b=(6, "B"), source=(3, "N"), diag=(3, "N"), upper=(1, "F"),
                    epsilonPEq=(1, "N"), sigmaY=(1, "N"), bEbar=(6, "N"), DLambda=(1, "N"), J=(1, "N"), F=(9, "N"),
                    gradD_old=(9, "N"), DEpsilonP=(6, "N"), tractionGradient_b=(3, "B"), epsilonP=(6, "N"),
-                   DD=(3, "N"), gradDD=(9, "N"))
+                   DD=(3, "N"), gradDD=(9, "N"), rho=(1, "N"), DD_b=(3, "B"))
 
 MODEL_NAMES = {
     # reference TypeName -> (gpu TypeName registered by the plugin, enum)
@@ -253,6 +253,8 @@ def apply_case(lib, prefix: str, handle, case: SolidCase, check) -> None:
     arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in
             (m.C, m.V, m.Sf, m.magSf, m.Cf, m.weights, m.nonOrthDeltaCoeffs, m.nonOrthCorrVec, m.CnbrB)]
     check(f("set_geometry")(handle, *[_dptr(a) for a in arrs]))
+    if m.points is not None:
+        set_points(lib, prefix, handle, m, check)
     check(f("set_controls")(handle, C.byref(case.controls)))
     check(f("set_law")(handle, C.byref(case.law)))
     for ip, p in enumerate(m.patches):
@@ -268,6 +270,47 @@ def apply_case(lib, prefix: str, handle, case: SolidCase, check) -> None:
             pr = np.ascontiguousarray(np.broadcast_to(bc.pressure, (p.size,)), dtype=np.float64)
         check(f("set_bc")(handle, ip, bc.kind, None if val is None else _dptr(val),
                           None if pr is None else _dptr(pr)))
+
+
+def set_geometry(lib, prefix: str, handle, m: FvMesh, check) -> None:
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in
+            (m.C, m.V, m.Sf, m.magSf, m.Cf, m.weights, m.nonOrthDeltaCoeffs, m.nonOrthCorrVec, m.CnbrB)]
+    check(getattr(lib, prefix + "set_geometry")(handle, *[_dptr(a) for a in arrs]))
+
+
+def set_points(lib, prefix: str, handle, m: FvMesh, check) -> None:
+    pts = np.ascontiguousarray(m.points, dtype=np.float64)
+    fv = np.ascontiguousarray(m.faces, dtype=np.int32)
+    ptr = np.arange(0, fv.size + 1, fv.shape[1], dtype=np.int32)
+    check(getattr(lib, prefix + "set_points")(handle, pts.shape[0], _dptr(pts), _iptr(ptr), _iptr(fv)))
+
+
+def move_mesh(lib, prefix: str, handle, case: "SolidCase", pointDD: np.ndarray, check) -> None:
+    """solidModel::moveMesh (SM/solidModel/solidModel.C:2008-2148) on the host side of the boundary: symmetryPlane
+    points keep their plane (:2040-2080), newPoints = oldPoints + pointDD, mesh.movePoints(newPoints); the new geometry
+    is mirrored again (set_geometry keeps fields, boundary data and history; set_points refreshes the weights)."""
+    from . import mesh as M
+    m = case.mesh
+    pdd = np.array(pointDD, dtype=np.float64, copy=True)
+    F = m.nInternalFaces
+    for p in m.patches:
+        if p.kind != M.SYMMETRY_PLANE or p.size == 0:
+            continue
+        sl = slice(F + p.start, F + p.start + p.size)
+        nrm = m.Sf[sl] / m.magSf[sl, None]
+        pn = np.zeros((m.points.shape[0], 3)); cnt = np.zeros(m.points.shape[0])
+        for j in range(m.faces.shape[1]):                 # pointNormals: average of the adjacent face normals
+            np.add.at(pn, m.faces[sl][:, j], nrm); np.add.at(cnt, m.faces[sl][:, j], 1.0)
+        mp = np.nonzero(cnt > 0)[0]
+        pnn = pn[mp] / np.linalg.norm(pn[mp], axis=1)[:, None]
+        avgN = pnn.mean(axis=0)
+        for ax in range(3):
+            if abs(avgN[ax]) > 0.95:
+                pdd[mp, ax] = 0.0
+                break
+    case.mesh = M.move_points(m, m.points + pdd)
+    set_geometry(lib, prefix, handle, case.mesh, check)
+    set_points(lib, prefix, handle, case.mesh, check)
 
 
 def field_size(mesh: FvMesh, name: str) -> tuple:
@@ -297,7 +340,9 @@ def declare_api(lib, prefix: str, handle_t) -> None:
     f("op_assemble").argtypes = [handle_t]
     f("op_amul").argtypes = [handle_t, C.c_int, dp, dp]
     f("op_solve").argtypes = [handle_t, dp, dp, C.POINTER(Stats)]
+    f("set_points").argtypes = [handle_t, C.c_int, dp, ip, ip]
+    f("interpolate_to_points").argtypes = [handle_t, C.c_int, dp]
     for n in ("set_mesh", "set_geometry", "set_law", "set_controls", "set_bc", "upload", "download", "initialise",
               "new_timestep", "outer_iteration", "evolve", "update_total_fields", "op_grad", "op_correct",
-              "op_assemble", "op_amul", "op_solve"):
+              "op_assemble", "op_amul", "op_solve", "set_points", "interpolate_to_points"):
         f(n).restype = C.c_int

@@ -19,12 +19,14 @@ from . import mesh as M
 # ---- C2: hex cantilever --------------------------------------------------------------------------
 def cantilever(nx: int, ny: int, nz: int, rank: int = 0, nRanks: int = 1, L: float = 8.0, H: float = 1.0,
                W: float = 1.0, traction=(0.0, -1e6, 0.0), E: float = 200e9, nu: float = 0.3,
-               rho: float = 7800.0, **ctl) -> K.SolidCase:
+               rho: float = 7800.0, general: bool = False, **ctl) -> K.SolidCase:
     """x=0 fixedDisplacement (0 0 0); x=L solidTraction (0 -1e6 0); other faces traction free;
     linearElastic E 200e9 nu 0.3; steadyState; leastSquares; RhieChow 0.1; PCG relTol 0.1."""
     names = ("fixed", "loaded", "yMin", "yMax", "zMin", "zMax")
     if nRanks > 1:
         mesh = M.hex_box_decomposed(nx, ny, nz, L, H, W, rank, nRanks, names=names)
+    elif general:      # general builder: keeps points()/faces() (vol->point interpolation, mesh motion)
+        mesh = M.hex_box_general(nx, ny, nz, L, H, W, names=names)
     else:
         mesh = M.hex_box(nx, ny, nz, L, H, W, names=names)
     bcs = {}
@@ -133,9 +135,9 @@ def patch_test(n: int = 4, distort: float = 0.25, seed: int = 7, **ctl) -> K.Sol
 
 # ---- C3 / C4 -----------------------------------------------------------------------------------
 def neo_hookean_cantilever(nx, ny, nz, traction=(0.0, -50.0, 0.0), E=3e6, nu=0.3, rho=1000.0,
-                           L=8.0, H=1.0, W=1.0, **ctl) -> K.SolidCase:
+                           L=8.0, H=1.0, W=1.0, general=False, **ctl) -> K.SolidCase:
     """C3: tutorials/solids/hyperelasticity/cantileverBeam material, total-Lagrangian total displacement."""
-    base = cantilever(nx, ny, nz, L=L, H=H, W=W, traction=traction)
+    base = cantilever(nx, ny, nz, L=L, H=H, W=W, traction=traction, general=general)
     law = K.mechanical_law("neoHookeanElastic", rho=rho, E=E, nu=nu)
     c = dict(solidModel=K.MODEL_NONLIN_TL_TOTAL_DISP)
     c.update(ctl)
@@ -173,3 +175,32 @@ def notched_bar(nx, ny, nz, elongation=0.0016, L=8.0, H=1.0, W=1.0, rank=0, nRan
     c = dict(solidModel=K.MODEL_NONLIN_TL_TOTAL_DISP)
     c.update(ctl)
     return K.SolidCase(mesh, bcs, law, K.default_controls(**c), name=f"notchedBar_{nx}x{ny}x{nz}")
+
+
+# ---- C5: solid side of fluidSolidInteraction/beamInCrossFlow -----------------------------------------
+def beam_in_cross_flow(refine: int = 1, pressure: float = 50.0, deltaT: float = 0.1, **ctl) -> K.SolidCase:
+    """C5: tutorials/fluidSolidInteraction/beamInCrossFlow/constant/solid/polyMesh/blockMeshDict
+    (0.1 x 0.2 x 0.2 m beam standing on y = 0, 4 x 8 x 8 cells x refine), neoHookeanElastic E 1e4 nu 0.4 rho 1000
+    (constant/solid/mechanicalProperties), nonLinearGeometryUpdatedLagrangian, backward d2dt2, leastSquares
+    (system/solid/fvSchemes), relaxation 0.9 (fvSolution); bottom fixed, z = 0 symmetry plane, the other faces are
+    the FSI interface, here loaded by a PRESCRIBED uniform pressure on the upstream (x-) face (stand-in for the
+    fluid load; the caller ramps it)."""
+    nx, ny, nz = 4 * refine, 8 * refine, 8 * refine
+    names = ("upstream", "downstream", "bottom", "top", "side", "symmetry")      # symmetry plane at zMax, as in the tutorial
+    kinds = (M.PATCH, M.PATCH, M.PATCH, M.PATCH, M.PATCH, M.SYMMETRY_PLANE)
+    mesh = M.hex_box_general(nx, ny, nz, 0.1, 0.2, 0.2, names=names, kinds=kinds)
+    bcs = {}
+    for p in mesh.patches:
+        if p.name == "bottom":
+            bcs[p.name] = K.fixedDisplacement((0.0, 0.0, 0.0))
+        elif p.name == "symmetry":
+            bcs[p.name] = K.solidSymmetry()
+        elif p.name == "upstream":
+            bcs[p.name] = K.solidTraction((0.0, 0.0, 0.0), pressure=np.full(p.size, pressure))
+        else:
+            bcs[p.name] = K.solidTraction((0.0, 0.0, 0.0))
+    law = K.mechanical_law("neoHookeanElastic", rho=1000.0, E=1e4, nu=0.4)
+    c = dict(solidModel=K.MODEL_NONLIN_UL, d2dt2Scheme=K.D2DT2_BACKWARD, deltaT=deltaT, deltaT0=deltaT, fieldRelaxD=0.9,
+             nCorrectors=1000)
+    c.update(ctl)
+    return K.SolidCase(mesh, bcs, law, K.default_controls(**c), name=f"beamInCrossFlow_solid_x{refine}")

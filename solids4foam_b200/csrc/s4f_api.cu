@@ -178,13 +178,16 @@ int s4fgpu_set_geometry(s4fgpu_handle c, const double* C, const double* V, const
     c->hC.assign(C, C + 3 * N); c->hV.assign(V, V + N); c->hSf.assign(Sf, Sf + 3 * FB); c->hMagSf.assign(magSf, magSf + FB);
     c->hCf.assign(Cf, Cf + 3 * FB); c->hW.assign(weights, weights + FB); c->hNod.assign(nod, nod + FB); c->hCorr.assign(corr, corr + 3 * FB);
     c->hCnbrB.assign(CnbrB, CnbrB + 3 * (size_t)c->B);
+    // a second call on the same mesh is a geometry refresh after mesh motion (nonLinGeomUpdatedLagSolid.C:360-374 ->
+    // solidModel::moveMesh): fields, boundary data and the law history stay, everything derived from geometry is rebuilt
+    const bool again = c->geomSet;
     int rc = s4f_build_rows(c); if (rc) return rc;
     rc = s4f_alloc_fields(c); if (rc) return rc;
-    // host geometry copies are only needed to build the rows
+    // host geometry copies are only needed to build the rows (cell centres stay for the vol->point weights)
     std::vector<double>().swap(c->hSf); std::vector<double>().swap(c->hCf); std::vector<double>().swap(c->hCorr);
-    std::vector<double>().swap(c->hC); std::vector<double>().swap(c->hW); std::vector<double>().swap(c->hNod);
-    c->geomSet = true; c->matrixValid = false;
-    if (c->lawSet) { rc = s4f_setup_law(c); if (rc) return rc; }
+    std::vector<double>().swap(c->hW); std::vector<double>().swap(c->hNod);
+    c->geomSet = true; c->matrixValid = false; c->amgValid = false; c->histValid = false;
+    if (c->lawSet && !again) { rc = s4f_setup_law(c); if (rc) return rc; }
     return 0;
 }
 
@@ -202,10 +205,7 @@ int s4fgpu_set_law(s4fgpu_handle c, const s4fgpu_law* law) {
 int s4fgpu_set_controls(s4fgpu_handle c, const s4fgpu_controls* ctl) {
     S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
     S4F_REQUIRE(c, ctl, "set_controls: null");
-    S4F_REQUIRE(c, ctl->solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP || ctl->solidModel == S4F_MODEL_NONLIN_TL_TOTAL_DISP ||
-                   ctl->solidModel == S4F_MODEL_NONLIN_TL,
-                "set_controls: this build implements linearGeometryTotalDisplacement, nonLinearGeometryTotalLagrangianTotalDisplacement "
-                "and nonLinearGeometryTotalLagrangian (the updated-Lagrangian model needs mesh motion: not available)");
+    S4F_REQUIRE(c, ctl->solidModel >= S4F_MODEL_LIN_GEOM_TOTAL_DISP && ctl->solidModel <= S4F_MODEL_NONLIN_UL, "set_controls: unknown solidModel");
     S4F_REQUIRE(c, ctl->solidModel != S4F_MODEL_NONLIN_TL || ctl->d2dt2Scheme == S4F_D2DT2_STEADY_STATE,
                 "set_controls: nonLinearGeometryTotalLagrangian is available with the steadyState d2dt2 scheme");
     S4F_REQUIRE(c, ctl->solver == S4F_SOLVER_PCG || ctl->solver == S4F_SOLVER_PBICGSTAB, "set_controls: solver PCG or PBiCGStab");
@@ -260,6 +260,8 @@ static int field_lookup(s4fgpu_ctx* c, int field, double** p, int* ncomp, int* o
         case S4F_FIELD_F: *p = c->lawF.p; *ncomp = 9; break;
         case S4F_FIELD_DEPSILON_P: *p = c->DEpsP.p; *ncomp = 6; break;
         case S4F_FIELD_EPSILON_P: *p = c->epsP.p; *ncomp = 6; break;
+        case S4F_FIELD_RHO: *p = c->rhoF.p; *ncomp = 1; break;
+        case S4F_FIELD_DD_B: *p = c->incremental() ? c->D.p : nullptr; *ncomp = 3; *offset = c->bOff(); *count = c->B; break;
         default: c->err = "unknown / unsupported field id"; return 1;
     }
     if (!*p) { c->err = "field not allocated for the selected model / law"; return 1; }
@@ -298,6 +300,8 @@ int s4fgpu_initialise(s4fgpu_handle c) {
     S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
     S4F_REQUIRE(c, c->geomSet && c->lawSet && c->ctlSet, "initialise: mesh, geometry, law and controls must be set");
     S4F_REQUIRE(c, c->nRanks == 1 || c->comm, "initialise: parallel run without communicator");
+    S4F_REQUIRE(c, !c->UL() || c->law.kind == S4F_LAW_NEO_HOOKEAN_ELASTIC || c->law.kind == S4F_LAW_NEO_HOOKEAN_MISES_PLASTIC,
+                "initialise: nonLinearGeometryUpdatedLagrangian needs a finite-strain law (neoHookeanElastic, neoHookeanElasticMisesPlastic)");
     int rc;
     if ((rc = s4f_alloc_model_fields(c))) return rc;
     if ((rc = s4f_upload_bc(c))) return rc;
@@ -321,7 +325,18 @@ int s4fgpu_new_timestep(s4fgpu_handle c, double deltaT) {
         S4F_REQUIRE(c, std::fabs(deltaT - c->ctl.deltaT) <= 1e-15 + 1e-12 * deltaT, "new_timestep: backwardD2dt2Scheme not implemented for variable time steps");
     c->ctl.deltaT0 = c->ctl.deltaT; c->ctl.deltaT = deltaT;
     int rc = 0;
-    if (c->ctl.d2dt2Scheme == S4F_D2DT2_BACKWARD) {       // GeometricField::storeOldTimes over the four-level chain
+    if (c->UL()) {     // GeometricField::storeOldTimes over the chains created in the constructor (nonLinGeomUpdatedLagSolid.C:143-145)
+        if (c->timeIndex == 0) {
+            for (DevBuf<double>* b : {&c->Dooo, &c->Doooo, &c->Dooooo}) rc |= d2d(c, b->p, c->DoldOld.p, 3 * ld);
+            for (DevBuf<double>* b : {&c->DDo, &c->DDoo, &c->DDooo, &c->DDoooo}) rc |= d2d(c, b->p, c->D.p, 3 * ld);
+            rc |= d2d(c, c->rhoO.p, c->rhoF.p, ld); rc |= d2d(c, c->rhoOO.p, c->rhoF.p, ld);
+        }
+        rc |= d2d(c, c->Dooooo.p, c->Doooo.p, 3 * ld); rc |= d2d(c, c->Doooo.p, c->Dooo.p, 3 * ld); rc |= d2d(c, c->Dooo.p, c->DoldOld.p, 3 * ld);
+        rc |= d2d(c, c->DDoooo.p, c->DDooo.p, 3 * ld); rc |= d2d(c, c->DDooo.p, c->DDoo.p, 3 * ld); rc |= d2d(c, c->DDoo.p, c->DDo.p, 3 * ld);
+        rc |= d2d(c, c->DDo.p, c->D.p, 3 * ld);
+        rc |= d2d(c, c->rhoOO.p, c->rhoO.p, ld); rc |= d2d(c, c->rhoO.p, c->rhoF.p, ld);
+        c->matrixValid = false;
+    } else if (c->ctl.d2dt2Scheme == S4F_D2DT2_BACKWARD) {       // GeometricField::storeOldTimes over the four-level chain
         rc |= d2d(c, c->Doooo.p, c->timeIndex >= 2 ? c->Dooo.p : c->DoldOld.p, 3 * ld);
         rc |= d2d(c, c->Dooo.p, c->DoldOld.p, 3 * ld);
     }
@@ -365,6 +380,27 @@ int s4fgpu_evolve(s4fgpu_handle c, s4fgpu_stats* st) {
     c->iCorr = 0;
     if (st) *st = c->last;
     return 0;
+}
+
+int s4fgpu_set_points(s4fgpu_handle c, int nPoints, const double* points, const int* faceVertsPtr, const int* faceVerts) {
+    S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
+    S4F_REQUIRE(c, c->geomSet, "set_points: call set_geometry first");
+    S4F_REQUIRE(c, nPoints > 0 && points && faceVertsPtr && faceVerts, "set_points: bad arguments");
+    const int nF = c->F + c->B;
+    c->nPoints = nPoints;
+    c->hFvPtr.assign(faceVertsPtr, faceVertsPtr + nF + 1);
+    c->hFv.assign(faceVerts, faceVerts + faceVertsPtr[nF]);
+    return s4f_build_point_weights(c, points);
+}
+
+int s4fgpu_interpolate_to_points(s4fgpu_handle c, int field, double* pointField) {
+    S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
+    S4F_REQUIRE(c, c->nPoints > 0, "interpolate_to_points: call set_points first");
+    const double* X = nullptr;
+    if (field == S4F_FIELD_D) X = c->incremental() ? c->Dtot.p : c->D.p;
+    else if (field == S4F_FIELD_DD && c->incremental()) X = c->D.p;
+    S4F_REQUIRE(c, X, "interpolate_to_points: field must be D or DD");
+    return s4f_interpolate_to_points(c, X, pointField);
 }
 
 int s4fgpu_update_total_fields(s4fgpu_handle c) {

@@ -163,6 +163,18 @@ struct s4fgpu_ctx {
     DevBuf<double> D, Dprev, Dold, DoldOld;       // 3*ld
     DevBuf<double> Dooo, Doooo;                   // 3*ld: third / fourth old-time level (backward d2dt2 only)
     DevBuf<double> d2Hist;                        // 3*ld: old-time part of rho*fvm::d2dt2(D) per unit volume (transient schemes)
+    // updated-Lagrangian model: the chains fvm::d2dt2(rho, DD) + fvc::d2dt2(rho, D.oldTime()) reach, and the density field
+    DevBuf<double> Dooooo, DDo, DDoo, DDooo, DDoooo;   // 3*ld each
+    DevBuf<double> rhoF, rhoO, rhoOO;                  // ld each
+    // ---- point mesh (vol->point interpolation): CSR over points of source slots in the vol-field index space ----
+    int nPoints = 0;
+    std::vector<int> hFvPtr, hFv;                 // faces() of the fv faces
+    std::vector<double> hBSfHost;                 // [3B] boundary area vectors (patch normals of the point constraints)
+    bool rhoInit = false;
+    std::vector<double> hCfB;                     // [3B] boundary face centres of the last set_geometry (hC is kept too)
+    DevBuf<int> ptPtr, ptCol;                     // [nPoints+1], [nnzP]
+    DevBuf<double> ptW, ptN;                      // [nnzP] normalised inverse-distance weights; [3*nPoints] constraint normal (0 = none)
+    DevBuf<double> ptOut;                         // [3*nPoints]
     bool histValid = false;
     int timeIndex = 0;                            // new_timestep() calls = runTime.timeIndex()
     DevBuf<double> gradD, gradDold;               // 9*ld
@@ -204,6 +216,7 @@ struct s4fgpu_ctx {
     s4fgpu_stats last{};
 
     bool incremental() const { return ctl.solidModel == S4F_MODEL_NONLIN_TL || ctl.solidModel == S4F_MODEL_NONLIN_UL; }
+    bool UL() const { return ctl.solidModel == S4F_MODEL_NONLIN_UL; }
     const double* gradForLaw() const { return incremental() ? gradDtot.p : gradD.p; }   // the registered "grad(D)"
     int NT() const { return N + G + B; }
     int bOff() const { return N + G; }
@@ -240,3 +253,6 @@ int s4f_amg_step0(s4fgpu_ctx* c, const double* r3, double* bytes);
 void s4f_amg_destroy(s4fgpu_ctx* c);
 int s4f_amg_info(s4fgpu_ctx* c, int* nLevels, int* sizes, int maxLevels, double* bytesPerApply, double* setupSeconds);
 int s4f_download_upper(s4fgpu_ctx* c, double* hostUpper);           // lduMatrix upper() [F]
+int s4f_build_point_weights(s4fgpu_ctx* c, const double* points);   // vol->point CSR + weights (s4f_setup.cu)
+int s4f_interpolate_to_points(s4fgpu_ctx* c, const double* field3, double* hostOut);
+int s4f_grad_calculated(s4fgpu_ctx* c, const double* X, double* gradOut);   // fvc::grad of a field with calculated patches

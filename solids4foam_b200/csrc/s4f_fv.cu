@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_assemble_laplacian(
     const double* __restrict__ eSf, const double* __restrict__ eCorr /* may be null */, const double* __restrict__ impK,
     const double* __restrict__ V, double* __restrict__ eA, double* __restrict__ eGam, double* __restrict__ eU, double* __restrict__ eC0,
     double* __restrict__ eVc /* null when orthogonal */, double* __restrict__ rowK, double* __restrict__ diag0, int N, int bOff, int ld,
-    long long nE, int nSlices, double stabScale, int stabOn, double d2dt2Coeff) {
+    long long nE, int nSlices, double stabScale, int stabOn, double d2dt2Coeff, const double* __restrict__ rhoF /* UL: density field */) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nWarps = (gridDim.x * blockDim.x) >> 5;
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_assemble_laplacian(
             }
         }
         if (row < N) {
-            diag0[row] = sum + d2dt2Coeff * V[row];
+            diag0[row] = sum + d2dt2Coeff * (rhoF ? rhoF[row] : 1.0) * V[row];
 #pragma unroll
             for (int q = 0; q < 3; q++) { rowK[(size_t)q * ld + row] = sU[q]; rowK[(size_t)(3 + q) * ld + row] = sV[q]; }
         }
@@ -571,7 +571,70 @@ __global__ void k_d2dt2_hist(const double* __restrict__ D1, const double* __rest
 }
 }  // namespace
 
+// Updated-Lagrangian inertia fvm::d2dt2(rho_, DD()) + fvc::d2dt2(rho_, D().oldTime()) with the density field
+// (nonLinGeomUpdatedLagSolid.C:173-176; backwardD2dt2Scheme.C:149-222, :391-470; [OF-ext] EulerD2dt2Scheme rho-field
+// overloads): diagonal coefficient (times rho_P V_P) and the explicit part per unit volume incl. rho_P g.  The
+// restatement with its coefficient table is spelled out in the oracle (ulD2dt2).
+struct UlCoeffs { double diag; double m[4]; double mo[3]; double moo[3]; double c[3]; double co[3]; double coo[3]; double g[3]; int mode; };
+static UlCoeffs ul_coeffs(const s4fgpu_ctx* c) {
+    UlCoeffs k{}; k.mode = c->ctl.d2dt2Scheme;
+    for (int q = 0; q < 3; q++) k.g[q] = c->ctl.g[q];
+    const double dt = c->ctl.deltaT, dt0 = c->ctl.deltaT0 > 0 ? c->ctl.deltaT0 : dt;
+    if (k.mode == S4F_D2DT2_EULER) {
+        const double cf = (dt + dt0) / (2 * dt), cf00 = (dt + dt0) / (2 * dt0), r2 = 4.0 / ((dt + dt0) * (dt + dt0));
+        k.diag = cf * r2;
+        k.m[0] = r2 * (cf + cf00); k.m[1] = -r2 * cf00;                   // rho * (.. DD.o .. DD.oo)
+        k.c[0] = -r2 * cf; k.c[1] = r2 * (cf + cf00); k.c[2] = -r2 * cf00;   // rho * (.. D.o, D.oo, D.ooo)
+    } else if (k.mode == S4F_D2DT2_BACKWARD) {
+        const bool firstM = c->timeIndex <= 1, firstC = c->timeIndex <= 2;
+        const double kb = 1.0 + dt / (dt + dt0), kb00 = dt * dt / (dt0 * (dt + dt0)), kb0 = kb + kb00;
+        const double cm = firstM ? 1.0 : kb, cm00 = firstM ? 0.0 : kb00, cm0 = cm + cm00;
+        const double cc = firstC ? 1.0 : kb, cc00 = firstC ? 0.0 : kb00, cc0 = cc + cc00;
+        const double r = 1.0 / (dt * dt);
+        k.diag = r * cm * kb;
+        k.m[0] = r * cm * kb0; k.m[1] = -r * cm * kb00;                                      // rho    * (DD.o, DD.oo)
+        k.mo[0] = r * cm0 * kb; k.mo[1] = -r * cm0 * kb0; k.mo[2] = r * cm0 * kb00;          // rho.o  * (DD.o, DD.oo, DD.ooo)
+        k.moo[0] = -r * cm00 * kb; k.moo[1] = r * cm00 * kb0; k.moo[2] = -r * cm00 * kb00;   // rho.oo * (DD.oo, DD.ooo, DD.oooo)
+        k.c[0] = -r * cc * kb; k.c[1] = r * cc * kb0; k.c[2] = -r * cc * kb00;               // rho    * (D.o, D.oo, D.ooo)
+        k.co[0] = r * cc0 * kb; k.co[1] = -r * cc0 * kb0; k.co[2] = r * cc0 * kb00;          // rho.o  * (D.oo, D.ooo, D.oooo)
+        k.coo[0] = -r * cc00 * kb; k.coo[1] = r * cc00 * kb0; k.coo[2] = -r * cc00 * kb00;   // rho.oo * (D.ooo, D.oooo, D.ooooo)
+    }
+    return k;
+}
+namespace {
+struct UlPtrs { const double *rho, *rhoO, *rhoOO, *DDo, *DDoo, *DDooo, *DDoooo, *Do, *Doo, *Dooo, *Doooo, *Dooooo; };
+__global__ void k_d2dt2_hist_ul(UlPtrs p, UlCoeffs k, double* __restrict__ hist, int n, int ld) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double r = p.rho[i], ro = p.rhoO[i], roo = p.rhoOO[i];
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        const size_t j = (size_t)q * ld + i;
+        double h = r * k.g[q];
+        if (k.mode != S4F_D2DT2_STEADY_STATE) {
+            const double a1 = p.DDo[j], a2 = p.DDoo[j], d1 = p.Do[j], d2 = p.Doo[j], d3 = p.Dooo[j];
+            h += r * (k.m[0] * a1 + k.m[1] * a2) + r * (k.c[0] * d1 + k.c[1] * d2 + k.c[2] * d3);
+            if (k.mode == S4F_D2DT2_BACKWARD) {
+                const double a3 = p.DDooo[j], a4 = p.DDoooo[j], d4 = p.Doooo[j], d5 = p.Dooooo[j];
+                h += ro * (k.mo[0] * a1 + k.mo[1] * a2 + k.mo[2] * a3) + roo * (k.moo[0] * a2 + k.moo[1] * a3 + k.moo[2] * a4)
+                   + ro * (k.co[0] * d2 + k.co[1] * d3 + k.co[2] * d4) + roo * (k.coo[0] * d3 + k.coo[1] * d4 + k.coo[2] * d5);
+            }
+        }
+        hist[j] = h;
+    }
+}
+}  // namespace
+
 int s4f_d2dt2_history(s4fgpu_ctx* c) {
+    if (c->UL()) {
+        if (c->histValid) return 0;
+        const UlCoeffs k = ul_coeffs(c);
+        UlPtrs p{c->rhoF.p, c->rhoO.p, c->rhoOO.p, c->DDo.p, c->DDoo.p, c->DDooo.p, c->DDoooo.p, c->Dold.p, c->DoldOld.p, c->Dooo.p, c->Doooo.p, c->Dooooo.p};
+        k_d2dt2_hist_ul<<<(c->N + 255) / 256, 256, 0, c->stream>>>(p, k, c->d2Hist.p, c->N, c->ld);
+        c->launches++;
+        c->histValid = true;
+        return 0;
+    }
     if (c->ctl.d2dt2Scheme == S4F_D2DT2_STEADY_STATE || c->histValid) return 0;
     const D2dt2Coeffs k = d2dt2_coeffs(c);
     const bool deep = c->ctl.d2dt2Scheme == S4F_D2DT2_BACKWARD && c->timeIndex > 1;   // before: D.ooo = D.oooo = copies of D.oo
@@ -593,12 +656,13 @@ int s4f_upload_bc(s4fgpu_ctx* c) {
 }
 
 int s4f_assemble_matrix(s4fgpu_ctx* c) {
-    const double dcoef = d2dt2_coeffs(c).diag;
+    const double dcoef = c->UL() ? ul_coeffs(c).diag : d2dt2_coeffs(c).diag;
     const int gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
     k_assemble_laplacian<<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eW.p, c->eDn.p, c->eSf.p, c->nonOrth ? c->eCorr.p : nullptr,
                                                              c->impK.p, c->V.p, c->eA.p, c->eGam.p, c->eU.p, c->eC0.p, c->nonOrth ? c->eVc.p : nullptr,
                                                              c->rowK.p, c->diag0.p, c->N, c->bOff(), c->ld, c->nEntries, c->nSlices,
-                                                             c->ctl.stabScaleFactor, c->ctl.stabilisation == S4F_STAB_RHIE_CHOW ? 1 : 0, dcoef);
+                                                             c->ctl.stabScaleFactor, c->ctl.stabilisation == S4F_STAB_RHIE_CHOW ? 1 : 0, dcoef,
+                                                             c->UL() ? c->rhoF.p : nullptr);
     k_diag_copy<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->diag0.p, c->diagC.p, c->N, c->ld);
     c->launches += 2;
     if (c->nBCells > 0) {
@@ -635,11 +699,12 @@ int s4f_bc_evaluate(s4fgpu_ctx* c) {
 template <bool T9>
 static void launch_source(s4fgpu_ctx* c, const double* T) {
     const bool stab = c->ctl.stabilisation == S4F_STAB_RHIE_CHOW;
-    const double rg[3] = {c->law.rho * c->ctl.g[0], c->law.rho * c->ctl.g[1], c->law.rho * c->ctl.g[2]};
+    const double rs = c->UL() ? 0.0 : c->law.rho;          // updated Lagrangian: rho_*g() of the density field is part of d2Hist
+    const double rg[3] = {rs * c->ctl.g[0], rs * c->ctl.g[1], rs * c->ctl.g[2]};
     long long need = ((long long)c->nSlices + 1) / 2, g = (long long)c->numSMs * 8;
     if (need < g) g = need;
     const int grid = (int)(g < 1 ? 1 : g);
-    const double* hist = c->ctl.d2dt2Scheme == S4F_D2DT2_STEADY_STATE ? nullptr : c->d2Hist.p;
+    const double* hist = (c->ctl.d2dt2Scheme == S4F_D2DT2_STEADY_STATE && !c->UL()) ? nullptr : c->d2Hist.p;
 #define S4F_LAUNCH_SRC(STAB, NO)                                                                                                      \
     k_source_f<T9, STAB, NO><<<grid, S4F_SRC_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eU.p, c->eC0.p, c->eGam.p, c->eVc.p,   \
                                                                     c->rowK.p, c->D.p, T, c->gradD.p, c->V.p, hist, c->source.p, c->N, \
@@ -683,6 +748,37 @@ int s4f_grad(s4fgpu_ctx* c) {
     }
     S4F_CHECK_CUDA(c, cudaGetLastError());
     return s4f_halo_exchange(c, c->gradD.p, 9);
+}
+
+// fvc::grad of a temporary with calculated patches (gradD() = fvc::grad(D().oldTime() + DD()), nonLinGeomUpdatedLagSolid.C:243):
+// snGrad_b = deltaCoeffs (X_b - X_P), then the usual boundary correction
+namespace {
+__global__ void k_sngrad_calculated(const int* __restrict__ bFaceCell, const int* __restrict__ bKind, const double* __restrict__ bDelta,
+                                    const double* __restrict__ X, double* __restrict__ bSn, int B, int bOff, int ld) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B || bKind[b] == S4F_BC_PROCESSOR) return;
+    const int P = bFaceCell[b];
+#pragma unroll
+    for (int c = 0; c < 3; c++) bSn[(size_t)c * B + b] = bDelta[b] * (X[(size_t)c * ld + bOff + b] - X[(size_t)c * ld + P]);
+}
+}  // namespace
+int s4f_grad_calculated(s4fgpu_ctx* c, const double* X, double* gradOut) {
+    const int gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32, 3);
+    if (c->B > 0) {
+        k_sngrad_calculated<<<(c->B + 127) / 128, 128, 0, c->stream>>>(c->bFaceCell.p, c->bKind.p, c->bDelta.p, X, c->bSn.p, c->B, c->bOff(), c->ld);
+        c->launches++;
+    }
+    if (c->ctl.gradScheme == S4F_GRAD_GAUSS_LINEAR)
+        k_grad<true><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eSf.p, c->eW.p, X, c->rV.p, gradOut, c->N, c->ld, c->nEntries, c->nSlices);
+    else
+        k_grad<false><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eLs.p, c->eW.p, X, c->rV.p, gradOut, c->N, c->ld, c->nEntries, c->nSlices);
+    c->launches++;
+    if (c->B > 0) {
+        k_grad_boundary<<<(c->B + 127) / 128, 128, 0, c->stream>>>(c->bFaceCell.p, c->bKind.p, c->bN.p, c->bSn.p, gradOut, c->B, c->bOff(), c->ld);
+        c->launches++;
+    }
+    S4F_CHECK_CUDA(c, cudaGetLastError());
+    return 0;
 }
 
 namespace {

@@ -100,12 +100,22 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_law_linear_elastic(const double* 
 
 // ---- neoHookeanElastic ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(S4F_BLOCK) k_law_neo_hookean(const double* __restrict__ gradD, double* __restrict__ sigma,
-                                                               double* __restrict__ Jout, int N, int bOff, int B, int ld, double mu, double K) {
+                                                               double* __restrict__ Jout, int N, int bOff, int B, int ld, double mu, double K,
+                                                               const double* __restrict__ Fold /* updated Lagrangian only */,
+                                                               double* __restrict__ Fout) {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N + B; t += gridDim.x * blockDim.x) {
         const int i = field_index(t, N, bOff);
         double g[9], Fm[9], FT[9], FFT[9], b[6], s[6];
         ld_soa<9>(gradD, ld, i, g);
         t_transpose(g, Fm); Fm[0] += 1; Fm[4] += 1; Fm[8] += 1;          // F = I + gradD.T()  mechanicalLaw.C:1130-1135
+        if (Fold) {                                                       // UL: relF = I + gradDD.T(); F = relF & F.oldTime()  :1055-1072
+            double Fo[9], rF[9];
+            ld_soa<9>(Fold, ld, i, Fo);
+#pragma unroll
+            for (int q = 0; q < 9; q++) rF[q] = Fm[q];
+            t_mul(rF, Fo, Fm);
+            st_soa<9>(Fout, ld, i, Fm);
+        }
         const double J = t_det(Fm);
         t_transpose(Fm, FT); t_mul(Fm, FT, FFT); t_symm(FFT, b);
         const double sc = pow(J, -2.0 / 3.0);
@@ -127,12 +137,16 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_law_neo_hookean(const double* __r
 // ---- neoHookeanElasticMisesPlastic ---------------------------------------------------------------
 // trial state shared by the two passes: F, J, relF = F & inv(F.old), relFbar, bEbarTrial = transform(relFbar, bEbar.old)
 __device__ __forceinline__ void mises_trial(const double* __restrict__ gradD, const double* __restrict__ Fold, const double* __restrict__ Jold,
-                                            const double* __restrict__ bEbarOld, int ld, int i, double* Fm, double& J, double* bt) {
+                                            const double* __restrict__ bEbarOld, int ld, int i, double* Fm, double& J, double* bt, int UL) {
     double g[9], Fo[9], Fi[9], relF[9], bo6[6], bo[9], t1[9], rT[9], t2[9];
     ld_soa<9>(gradD, ld, i, g);
     t_transpose(g, Fm); Fm[0] += 1; Fm[4] += 1; Fm[8] += 1;
     ld_soa<9>(Fold, ld, i, Fo);
-    t_inv(Fo, Fi); t_mul(Fm, Fi, relF);
+    if (UL) {            // gradD is grad(DD) on the updated configuration: relF = I + gradDD.T(); F = relF & F.oldTime()
+#pragma unroll
+        for (int q = 0; q < 9; q++) relF[q] = Fm[q];
+        t_mul(relF, Fo, Fm);
+    } else { t_inv(Fo, Fi); t_mul(Fm, Fi, relF); }
     J = t_det(Fm);
     const double relJ = J / Jold[i];
     const double sc = pow(relJ, -1.0 / 3.0);
@@ -146,11 +160,11 @@ __device__ __forceinline__ void mises_trial(const double* __restrict__ gradD, co
 struct FinMaxBE { OuterScalars* S; __device__ void operator()(const double* tot) const { S->maxMagBE = tot[0]; } };
 __global__ void __launch_bounds__(S4F_BLOCK) k_mises_max_be(const double* __restrict__ gradD, const double* __restrict__ Fold,
                                                             const double* __restrict__ Jold, const double* __restrict__ bEbarOld, int N, int ld,
-                                                            OuterScalars* S, double* partials, unsigned int* ticket) {
+                                                            OuterScalars* S, double* partials, unsigned int* ticket, int UL) {
     double v[1] = {0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {   // gMax over the internal field :1030
         double Fm[9], J, bt[6];
-        mises_trial(gradD, Fold, Jold, bEbarOld, ld, i, Fm, J, bt);
+        mises_trial(gradD, Fold, Jold, bEbarOld, ld, i, Fm, J, bt, UL);
         v[0] = fmax(v[0], sqrt(s_magSqr(bt)));
     }
     grid_reduce<1, OpMax>(v, partials, ticket, FinMaxBE{S});
@@ -166,7 +180,7 @@ struct MisesPtrs {
 };
 __global__ void __launch_bounds__(S4F_BLOCK) k_law_mises(MisesPtrs p, int N, int bOff, int B, int ld, double mu, double K, double Hp,
                                                          int consistent, double relax, HardeningTable T, OuterScalars* S,
-                                                         double* partials, unsigned int* ticket) {
+                                                         double* partials, unsigned int* ticket, int UL) {
     const bool nonLinearPlasticity = T.n > 2;
     const double magHp = fabs(Hp);
     const double maxMagBE = fmax(S->maxMagBE, S4F_SMALL);
@@ -174,7 +188,7 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_law_mises(MisesPtrs p, int N, int
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N + B; t += gridDim.x * blockDim.x) {
         const int i = field_index(t, N, bOff);
         double Fm[9], J, bt[6];
-        mises_trial(p.gradD, p.Fold, p.Jold, p.bEbarOld, ld, i, Fm, J, bt);
+        mises_trial(p.gradD, p.Fold, p.Jold, p.bEbarOld, ld, i, Fm, J, bt, UL);
         double dv[6], sT[6];
         s_dev(bt, dv);
 #pragma unroll
@@ -342,25 +356,27 @@ int s4f_law_correct(s4fgpu_ctx* c) {
     const int N = c->N, B = c->B, bOff = c->bOff(), ld = c->ld;
     const int grid = s4f_grid(c->numSMs, N + B), gridN = s4f_grid(c->numSMs, N);
     const s4fgpu_law& L = c->law;
-    const double* gD = c->gradForLaw();
+    const int UL = c->UL() ? 1 : 0;
+    const double* gD = UL ? c->gradD.p : c->gradForLaw();        // UL laws read grad(DD) (mechanicalLaw.C:1064-1072)
     if (L.kind == S4F_LAW_LINEAR_ELASTIC) {
         S6 s0; for (int q = 0; q < 6; q++) s0.v[q] = L.sigma0[q];
         k_law_linear_elastic<<<grid, S4F_BLOCK, 0, c->stream>>>(gD, c->sigma.p, N, bOff, B, ld, L.mu, L.K, s0);
         c->launches++;
     } else if (L.kind == S4F_LAW_NEO_HOOKEAN_ELASTIC) {
-        k_law_neo_hookean<<<grid, S4F_BLOCK, 0, c->stream>>>(gD, c->sigma.p, c->lawJ.p, N, bOff, B, ld, L.mu, L.K);
+        k_law_neo_hookean<<<grid, S4F_BLOCK, 0, c->stream>>>(gD, c->sigma.p, c->lawJ.p, N, bOff, B, ld, L.mu, L.K, UL ? c->lawFold.p : nullptr,
+                                                            c->lawF.p);
         c->launches++;
     } else if (L.kind == S4F_LAW_NEO_HOOKEAN_MISES_PLASTIC) {
         HardeningTable T = make_table(L);
         if (T.n > 2) {
-            k_mises_max_be<<<gridN, S4F_BLOCK, 0, c->stream>>>(gD, c->lawFold.p, c->lawJold.p, c->bEbarOld.p, N, ld, c->outS.p, c->partials.p, c->ticket.p);
+            k_mises_max_be<<<gridN, S4F_BLOCK, 0, c->stream>>>(gD, c->lawFold.p, c->lawJold.p, c->bEbarOld.p, N, ld, c->outS.p, c->partials.p, c->ticket.p, UL);
             c->launches++;
             if (c->nRanks > 1) S4F_CHECK_NCCL(c, ncclAllReduce(&((OuterScalars*)c->outS.p)->maxMagBE, &((OuterScalars*)c->outS.p)->maxMagBE, 1, ncclDouble, ncclMax, c->comm, c->stream));
         }
         MisesPtrs p{gD, c->lawFold.p, c->lawJold.p, c->bEbarOld.p, c->sigmaY.p, c->epsPEq.p, c->lawF.p, c->lawJ.p, c->bEbar.p, c->sigma.p,
                     c->DSigmaY.p, c->DEpsPEq.p, c->DEpsP.p, c->DEpsPprev.p, c->DLambda.p, c->plasticN.p};
         k_law_mises<<<grid, S4F_BLOCK, 0, c->stream>>>(p, N, bOff, B, ld, L.mu, L.K, c->Hp, L.updateBEbarConsistent, L.DEpsilonPRelax, T, c->outS.p,
-                                                      c->partials.p, c->ticket.p);
+                                                      c->partials.p, c->ticket.p, UL);
         c->launches++;
         if (c->nRanks > 1) S4F_CHECK_NCCL(c, ncclAllReduce(&((OuterScalars*)c->outS.p)->matNum, &((OuterScalars*)c->outS.p)->matNum, 2, ncclDouble, ncclMax, c->comm, c->stream));
     } else if (L.kind == S4F_LAW_LINEAR_ELASTIC_MISES_PLASTIC) {
@@ -380,6 +396,7 @@ int s4f_law_correct(s4fgpu_ctx* c) {
     }
     S4F_CHECK_CUDA(c, cudaGetLastError());
     if (c->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP) {
+        // UL: relF = I + gradDD.T() takes the place of F: fvc::div(relJ*relFinv & sigma), nonLinGeomUpdatedLagSolid.C:188
         k_tl_flux_tensor<<<grid, S4F_BLOCK, 0, c->stream>>>(gD, c->sigma.p, c->T9.p, c->Finv.p, c->Jt.p, N, bOff, B, ld);
         c->launches++;
         return s4f_halo_exchange(c, c->T9.p, 9);
@@ -392,14 +409,32 @@ int s4f_law_correct(s4fgpu_ctx* c) {
 int s4f_kinematics(s4fgpu_ctx* c) {
     if (c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP) return 0;
     const int grid = s4f_grid(c->numSMs, c->N + c->B);
-    k_tl_flux_tensor<<<grid, S4F_BLOCK, 0, c->stream>>>(c->gradForLaw(), c->sigma.p, c->T9.p, c->Finv.p, c->Jt.p, c->N, c->bOff(), c->B, c->ld);
+    k_tl_flux_tensor<<<grid, S4F_BLOCK, 0, c->stream>>>(c->UL() ? c->gradD.p : c->gradForLaw(), c->sigma.p, c->T9.p, c->Finv.p, c->Jt.p, c->N, c->bOff(), c->B, c->ld);
     c->launches++;
     S4F_CHECK_CUDA(c, cudaGetLastError());
     return s4f_halo_exchange(c, c->T9.p, 9);
 }
 
 // solidModel::updateTotalFields -> neoHookeanElasticMisesPlastic::updateTotalFields :1526-1536
+namespace {
+__global__ void k_rho_update(double* __restrict__ rho, const double* __restrict__ rhoO, const double* __restrict__ relJ, int N, int bOff, int B) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N + B) return;
+    const int i = field_index(t, N, bOff);
+    rho[i] = rhoO[i] / relJ[i];
+}
+}  // namespace
+
 int s4f_update_total_fields_impl(s4fgpu_ctx* c) {
+    if (c->UL()) {
+        // after the loop (nonLinGeomUpdatedLagSolid.C:243): gradD() = fvc::grad(D().oldTime() + DD()); then
+        // updateTotalFields :360-374: rho_ = rho_.oldTime()/relJ_.  The mesh motion is done by the host side of the
+        // boundary (interpolate_to_points -> movePoints -> set_geometry / set_points).
+        int rc = s4f_grad_calculated(c, c->Dtot.p, c->gradDtot.p); if (rc) return rc;
+        k_rho_update<<<(c->N + c->B + 255) / 256, 256, 0, c->stream>>>(c->rhoF.p, c->rhoO.p, c->Jt.p, c->N, c->bOff(), c->B);
+        c->launches++;
+        c->matrixValid = false; c->histValid = false;
+    }
     if (c->law.kind == S4F_LAW_NEO_HOOKEAN_MISES_PLASTIC) {
         const long long ld = c->ld;
         k_axpy<<<(unsigned)((ld + 255) / 256), 256, 0, c->stream>>>(c->sigmaY.p, c->DSigmaY.p, ld);

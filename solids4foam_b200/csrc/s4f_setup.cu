@@ -221,9 +221,13 @@ int s4f_build_rows(s4fgpu_ctx* c) {
     S4F_CHECK_CUDA(c, c->bFaceCell.upload(hFaceCell));
     S4F_CHECK_CUDA(c, c->bN.upload(hN)); S4F_CHECK_CUDA(c, c->bK.upload(hK)); S4F_CHECK_CUDA(c, c->bSf.upload(hBSf));
     S4F_CHECK_CUDA(c, c->bDelta.upload(hDelta)); S4F_CHECK_CUDA(c, c->bMagSf.upload(hMag));
-    S4F_CHECK_CUDA(c, c->bcValue.alloc(3 * (size_t)std::max(B, 1))); S4F_CHECK_CUDA(c, c->bcPressure.alloc(std::max(B, 1)));
-    S4F_CHECK_CUDA(c, c->tracGrad.alloc(3 * (size_t)std::max(B, 1))); S4F_CHECK_CUDA(c, c->bSn.alloc(3 * (size_t)std::max(B, 1)));
-    S4F_CHECK_CUDA(c, c->bKind.alloc(std::max(B, 1)));
+    if (!c->geomSet || c->bcValue.n != 3 * (size_t)std::max(B, 1)) {      // a geometry refresh (mesh motion) keeps the boundary data
+        S4F_CHECK_CUDA(c, c->bcValue.alloc(3 * (size_t)std::max(B, 1))); S4F_CHECK_CUDA(c, c->bcPressure.alloc(std::max(B, 1)));
+        S4F_CHECK_CUDA(c, c->tracGrad.alloc(3 * (size_t)std::max(B, 1))); S4F_CHECK_CUDA(c, c->bSn.alloc(3 * (size_t)std::max(B, 1)));
+        S4F_CHECK_CUDA(c, c->bKind.alloc(std::max(B, 1)));
+    }
+    c->hCfB.assign(c->hCf.begin() + 3 * (size_t)F, c->hCf.end());
+    c->hBSfHost.assign(c->hSf.begin() + 3 * (size_t)F, c->hSf.end());
 
     // boundary cells and their (non-processor) faces, ascending face order
     {
@@ -280,6 +284,22 @@ int s4f_alloc_model_fields(s4fgpu_ctx* c) {
     if (c->ctlSet && c->incremental()) { S4F_CHECK_CUDA(c, A(c->Dtot, 3)); S4F_CHECK_CUDA(c, A(c->gradDtot, 9)); }
     if (c->ctlSet && c->ctl.d2dt2Scheme != S4F_D2DT2_STEADY_STATE) { S4F_CHECK_CUDA(c, A(c->d2Hist, 3)); c->histValid = false; }
     if (c->ctlSet && c->ctl.d2dt2Scheme == S4F_D2DT2_BACKWARD) { S4F_CHECK_CUDA(c, A(c->Dooo, 3)); S4F_CHECK_CUDA(c, A(c->Doooo, 3)); }
+    if (c->ctlSet && c->UL()) {
+        S4F_CHECK_CUDA(c, A(c->d2Hist, 3)); c->histValid = false;
+        S4F_CHECK_CUDA(c, A(c->Dooo, 3)); S4F_CHECK_CUDA(c, A(c->Doooo, 3)); S4F_CHECK_CUDA(c, A(c->Dooooo, 3));
+        S4F_CHECK_CUDA(c, A(c->DDo, 3)); S4F_CHECK_CUDA(c, A(c->DDoo, 3)); S4F_CHECK_CUDA(c, A(c->DDooo, 3)); S4F_CHECK_CUDA(c, A(c->DDoooo, 3));
+        if (c->rhoF.n != ld) {
+            S4F_CHECK_CUDA(c, A(c->rhoF, 1)); S4F_CHECK_CUDA(c, A(c->rhoO, 1)); S4F_CHECK_CUDA(c, A(c->rhoOO, 1));
+            c->rhoInit = false;
+        }
+        if (c->lawSet && !c->rhoInit) {      // rho_(mechanical().rho()), nonLinGeomUpdatedLagSolid.C:124-135
+            for (DevBuf<double>* b : {&c->rhoF, &c->rhoO, &c->rhoOO}) {
+                k_fill<<<(unsigned)((ld + 255) / 256), 256, 0, c->stream>>>(b->p, c->law.rho, (long long)ld);
+                c->launches++;
+            }
+            c->rhoInit = true;
+        }
+    }
     if (TL) {
         if (c->Finv.n != 9 * ld) { S4F_CHECK_CUDA(c, A(c->Finv, 9)); fillI(c->Finv, 9, dT, 3); }
         if (c->Jt.n != ld) { S4F_CHECK_CUDA(c, A(c->Jt, 1)); fillI(c->Jt, 1, d1, 1); }
@@ -300,6 +320,98 @@ int s4f_alloc_model_fields(s4fgpu_ctx* c) {
             S4F_CHECK_CUDA(c, A(c->DLambda, 1)); S4F_CHECK_CUDA(c, A(c->plasticN, 6)); S4F_CHECK_CUDA(c, A(c->epsilon, 6));
         }
     }
+    S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// vol -> point interpolation (enhancedVolPointInterpolation, src/blockCoupledSolids4FoamTools): per point a list of
+// source slots in the vol-field index space -- the cells around an internal point, the boundary-value slots of the
+// patch faces around a patch point -- with normalised inverse-distance weights
+// (enhancedVolPointInterpolation.C:165-198 makeInternalWeights, :201-245 makeBoundaryWeights); symmetry-plane points
+// carry the plane normal for the point constraint.  One thread per point, atomic-free gather.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void k_vol_to_point(const int* __restrict__ ptPtr, const int* __restrict__ ptCol, const double* __restrict__ ptW,
+                               const double* __restrict__ ptN, const double* __restrict__ X, double* __restrict__ out, int nPoints, int ld) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nPoints) return;
+    double a[3] = {0, 0, 0};
+    for (int j = ptPtr[p]; j < ptPtr[p + 1]; j++) {
+        const int s = ptCol[j];
+        const double w = ptW[j];
+        a[0] += w * X[s]; a[1] += w * X[(size_t)ld + s]; a[2] += w * X[2 * (size_t)ld + s];
+    }
+    const double n[3] = {ptN[3 * (size_t)p], ptN[3 * (size_t)p + 1], ptN[3 * (size_t)p + 2]};
+    const double na = n[0] * a[0] + n[1] * a[1] + n[2] * a[2];
+    out[3 * (size_t)p] = a[0] - n[0] * na; out[3 * (size_t)p + 1] = a[1] - n[1] * na; out[3 * (size_t)p + 2] = a[2] - n[2] * na;
+}
+}  // namespace
+
+int s4f_build_point_weights(s4fgpu_ctx* c, const double* points) {
+    const int N = c->N, F = c->F, B = c->B, nP = c->nPoints, bOff = c->bOff();
+    if (c->nRanks > 1) { c->err = "set_points: vol->point interpolation is not available on decomposed meshes yet"; return 1; }
+    std::vector<std::vector<int>> pc(nP), pb(nP);
+    auto add = [](std::vector<int>& v, int x) { if (std::find(v.begin(), v.end(), x) == v.end()) v.push_back(x); };
+    for (int f = 0; f < F + B; f++) for (int j = c->hFvPtr[f]; j < c->hFvPtr[f + 1]; j++) {
+        const int p = c->hFv[j];
+        if (p < 0 || p >= nP) { c->err = "set_points: vertex out of range"; return 1; }
+        add(pc[p], f < F ? c->own[f] : c->faceCells[f - F]);
+        if (f < F) add(pc[p], c->nei[f]);
+    }
+    std::vector<double> hN(3 * (size_t)std::max(nP, 1), 0.0);
+    for (int ip = 0; ip < c->nPatches; ip++) {
+        if (c->pKind[ip] == S4F_PATCH_PROCESSOR) continue;
+        double n[3] = {0, 0, 0};
+        for (int i = 0; i < c->pSize[ip]; i++) {
+            const int b = c->pStart[ip] + i;
+            for (int j = c->hFvPtr[F + b]; j < c->hFvPtr[F + b + 1]; j++) pb[c->hFv[j]].push_back(b);
+            for (int q = 0; q < 3; q++) n[q] += c->hBSfHost[3 * (size_t)b + q];
+        }
+        if (c->pKind[ip] == S4F_PATCH_SYMMETRY && c->pSize[ip] > 0) {       // symmetryPlanePolyPatch::n()
+            const double m = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            for (int i = 0; i < c->pSize[ip]; i++) {
+                const int b = c->pStart[ip] + i;
+                for (int j = c->hFvPtr[F + b]; j < c->hFvPtr[F + b + 1]; j++) for (int q = 0; q < 3; q++) hN[3 * (size_t)c->hFv[j] + q] = n[q] / m;
+            }
+        }
+    }
+    std::vector<int> ptr(1, 0), col; std::vector<double> w;
+    for (int p = 0; p < nP; p++) {
+        const double* x = &points[3 * (size_t)p];
+        const size_t s0 = w.size();
+        double sw = 0;
+        if (!pb[p].empty()) {
+            for (int b : pb[p]) {
+                const double* cf = &c->hCfB[3 * (size_t)b];
+                const double d = std::sqrt((x[0] - cf[0]) * (x[0] - cf[0]) + (x[1] - cf[1]) * (x[1] - cf[1]) + (x[2] - cf[2]) * (x[2] - cf[2]));
+                col.push_back(bOff + b); w.push_back(1.0 / d); sw += 1.0 / d;
+            }
+        } else {
+            std::sort(pc[p].begin(), pc[p].end());
+            for (int cell : pc[p]) {
+                const double* cc = &c->hC[3 * (size_t)cell];
+                const double d = std::sqrt((x[0] - cc[0]) * (x[0] - cc[0]) + (x[1] - cc[1]) * (x[1] - cc[1]) + (x[2] - cc[2]) * (x[2] - cc[2]));
+                col.push_back(cell); w.push_back(1.0 / d); sw += 1.0 / d;
+            }
+        }
+        for (size_t j = s0; j < w.size(); j++) w[j] /= sw;
+        ptr.push_back((int)w.size());
+    }
+    (void)N;
+    if (col.empty()) { col.push_back(0); w.push_back(0.0); }
+    S4F_CHECK_CUDA(c, c->ptPtr.upload(ptr)); S4F_CHECK_CUDA(c, c->ptCol.upload(col)); S4F_CHECK_CUDA(c, c->ptW.upload(w));
+    S4F_CHECK_CUDA(c, c->ptN.upload(hN));
+    if (c->ptOut.n != 3 * (size_t)std::max(nP, 1)) S4F_CHECK_CUDA(c, c->ptOut.alloc(3 * (size_t)std::max(nP, 1)));
+    return 0;
+}
+
+int s4f_interpolate_to_points(s4fgpu_ctx* c, const double* X, double* hostOut) {
+    const int nP = c->nPoints;
+    k_vol_to_point<<<(nP + 127) / 128, 128, 0, c->stream>>>(c->ptPtr.p, c->ptCol.p, c->ptW.p, c->ptN.p, X, c->ptOut.p, nP, c->ld);
+    c->launches++;
+    S4F_CHECK_CUDA(c, cudaGetLastError());
+    S4F_CHECK_CUDA(c, cudaMemcpyAsync(hostOut, c->ptOut.p, 3 * (size_t)nP * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }

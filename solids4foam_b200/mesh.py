@@ -74,6 +74,12 @@ class FvMesh:
     rank: int = 0
     nRanks: int = 1
     meta: Dict = field(default_factory=dict)
+    # polyMesh points() / faces() (quads) of the fv faces above, in the same order (internal faces, then the kept
+    # boundary faces); present for meshes made by the general builder.  ``topo`` keeps what a geometry rebuild after
+    # mesh motion needs (all faces incl. those of empty patches).
+    points: Optional[np.ndarray] = None      # [nPoints,3]
+    faces: Optional[np.ndarray] = None       # [F+B,4] int32
+    topo: Optional[Dict] = None
 
     @property
     def nInternalFaces(self) -> int:
@@ -280,8 +286,31 @@ def poly_mesh_from_hexes(points: np.ndarray, hexes: np.ndarray,
     kb = np.nonzero(keep)[0]
     Sf = np.concatenate([fAreas[:F], fAreas[F:][kb]])
     Cf = np.concatenate([fCtrs[:F], fCtrs[F:][kb]])
-    return _finish_mesh(nCells, own, nei, cells_b[kb], patches, C, V, Sf, Cf, None, solutionD,
+    mesh = _finish_mesh(nCells, own, nei, cells_b[kb], patches, C, V, Sf, Cf, None, solutionD,
                         cellGlobal=np.arange(nCells, dtype=np.int64))
+    mesh.points = points.copy()
+    mesh.faces = np.concatenate([faces_int, faces_b[kb]]).astype(np.int32)
+    mesh.topo = dict(faces_all=faces_all, own_all=own_all, kb=kb)
+    return mesh
+
+
+def move_points(mesh: FvMesh, new_points: np.ndarray) -> FvMesh:
+    """``fvMesh::movePoints`` for a mesh of the general builder: same topology, geometry recomputed from the new
+    points ([OF-ext] primitiveMesh face/cell geometry + surfaceInterpolation weights, deltaCoeffs, correction
+    vectors), as solidModel::moveMesh does at the end of an updated-Lagrangian step (solidModel.C:2008-2148)."""
+    if mesh.points is None or mesh.topo is None:
+        raise ValueError("move_points needs a mesh with points/faces (general builder)")
+    t = mesh.topo
+    pts = np.asarray(new_points, dtype=np.float64)
+    F = mesh.nInternalFaces
+    fCtrs, fAreas = face_centres_and_areas(pts, t["faces_all"])
+    C, V = cell_centres_and_volumes(mesh.nCells, fCtrs, fAreas, t["own_all"], mesh.neighbour.astype(np.int64))
+    Sf = np.concatenate([fAreas[:F], fAreas[F:][t["kb"]]])
+    Cf = np.concatenate([fCtrs[:F], fCtrs[F:][t["kb"]]])
+    new = _finish_mesh(mesh.nCells, mesh.owner.astype(np.int64), mesh.neighbour.astype(np.int64), mesh.faceCells, mesh.patches,
+                       C, V, Sf, Cf, None, mesh.solutionD, cellGlobal=mesh.cellGlobal)
+    new.points = pts.copy(); new.faces = mesh.faces; new.topo = t; new.meta = dict(mesh.meta)
+    return new
 
 
 # ----------------------------------------------------------------------------

@@ -30,6 +30,8 @@ class SolidModel:
         "nonLinearGeometryTotalLagrangianTotalDisplacement": K.MODEL_NONLIN_TL_TOTAL_DISP,
         "gpuNonLinearGeometryTotalLagrangian": K.MODEL_NONLIN_TL,
         "nonLinearGeometryTotalLagrangian": K.MODEL_NONLIN_TL,
+        "gpuNonLinearGeometryUpdatedLagrangian": K.MODEL_NONLIN_UL,
+        "nonLinearGeometryUpdatedLagrangian": K.MODEL_NONLIN_UL,
     }
 
     @classmethod
@@ -117,7 +119,28 @@ class SolidModel:
         self._check(self.L.s4fgpu_evolve(self.h, C.byref(st)))
         return st.as_dict()
 
+    def interpolate_to_points(self, name: str = "D") -> np.ndarray:
+        """mechanicalModel::interpolate(D, pointD) (mechanicalModel.C:786-826): vol -> point interpolation on the device."""
+        out = np.empty((self.case.mesh.points.shape[0], 3))
+        self._check(self.L.s4fgpu_interpolate_to_points(self.h, K.FIELD[name], K._dptr(out)))
+        return out
+
+    def pointD(self) -> np.ndarray:
+        return self.interpolate_to_points("D")
+
+    def movingMesh(self) -> bool:
+        """solidModel::movingMesh(): the updated-Lagrangian model moves the mesh at the end of every step."""
+        return self.case.controls.solidModel == K.MODEL_NONLIN_UL
+
     def updateTotalFields(self) -> None:
+        """solidModel::updateTotalFields; for the updated-Lagrangian model nonLinGeomUpdatedLagSolid::updateTotalFields
+        (nonLinGeomUpdatedLagSolid.C:360-374): density update, moveMesh(oldPoints, DD, pointDD), law history."""
+        if self.movingMesh():
+            pointDD = self.interpolate_to_points("DD")
+            self._check(self.L.s4fgpu_update_total_fields(self.h))
+            K.move_mesh(self.L, "s4fgpu_", self.h, self.case, pointDD, self._check)
+            self.pointDD = pointDD
+            return
         self._check(self.L.s4fgpu_update_total_fields(self.h))
 
     update_total_fields = updateTotalFields

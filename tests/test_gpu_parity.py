@@ -410,3 +410,93 @@ def test_backward_d2dt2_time_steps_match_oracle():
         s.op_assemble()
     assert rel_l2(g.get("diag"), o.get("diag")) < OP_TOL
     assert np.abs(g.get("source") - o.get("source")).max() / np.abs(o.get("source")).max() < 1e-11
+
+
+# ---------------------------------------------------------------------------------------------
+# nonLinearGeometryUpdatedLagrangian with vol->point interpolation and mesh motion (8f row f3)
+# ---------------------------------------------------------------------------------------------
+def test_vol_to_point_interpolation_matches_oracle():
+    """k_vol_to_point against the oracle's restatement of enhancedVolPointInterpolation (internal points, patch points,
+    symmetry-plane constraint) on the beamInCrossFlow block."""
+    g, o, mesh = _pair(cases.beam_in_cross_flow, refine=1)
+    rng = np.random.default_rng(5)
+    D = 1e-3 * rng.standard_normal((mesh.nCells, 3))
+    Db = 1e-3 * rng.standard_normal((mesh.nBoundaryFaces, 3))
+    for s in (g, o):
+        s.set("DD", D); s.set("DD_b", Db)
+    pg, po = g.interpolate_to_points("DD"), o.interpolate_to_points("DD")
+    assert np.abs(pg - po).max() < 1e-15 + 1e-13 * np.abs(po).max()
+    sym = np.abs(mesh.points[:, 2] - mesh.points[:, 2].max()) < 1e-12
+    assert sym.any() and np.abs(pg[sym, 2]).max() < 1e-18
+
+
+def test_updated_lagrangian_load_steps_match_oracle():
+    """nonLinGeomUpdatedLagSolid (nonLinGeomUpdatedLagSolid.C:159-273, :360-374): three load steps of the neo-Hookean
+    beam, mesh moved after every step on both sides (device vol->point interpolation, host movePoints, geometry
+    mirrored again).  Fields, density and the moved points agree within north_star's tolerance."""
+    kw = dict(nx=8, ny=4, nz=4, L=2.0, traction=(0.0, 0.0, 0.0), fieldRelaxD=0.9, nCorrectors=8000, general=True,
+              solidModel=K.MODEL_NONLIN_UL, **TIGHT)
+    from oracle.binding import OracleSolid
+    from solids4foam_b200.solid_model import SolidModel
+    cg, co = cases.neo_hookean_cantilever(preconditioner=K.PRECOND_GAMG, **kw), cases.neo_hookean_cantilever(preconditioner=K.PRECOND_DIC, **kw)
+    g, o = SolidModel.New(cg, "gpuNonLinearGeometryUpdatedLagrangian"), OracleSolid(co)
+    n = cg.mesh.patch("loaded").size
+    for step, t in enumerate((-4e3, -8e3, -12e3)):
+        tr = np.zeros((n, 3)); tr[:, 1] = t
+        for s in (g, o):
+            s.new_timestep(1.0)
+            s.set_bc("loaded", K.solidTraction(tr))
+        sg, so = g.evolve(), o.evolve()
+        assert sg["converged"] and so["converged"], (step, sg, so)
+        assert rel_l2(g.get("D"), o.get("D")) < SOLVE_TOL, step
+        assert rel_l2(g.get("DD"), o.get("DD")) < 5 * SOLVE_TOL, step
+        assert rel_l2(g.get("sigma"), o.get("sigma")) < SOLVE_TOL, step
+        assert rel_l2(g.get("F"), o.get("F")) < SOLVE_TOL, step
+        g.updateTotalFields(); o.update_total_fields()
+        assert rel_l2(g.get("rho"), o.get("rho")) < 1e-9
+        assert rel_l2(g.get("gradD"), o.get("gradD")) < 10 * SOLVE_TOL
+        assert np.abs(cg.mesh.points - co.mesh.points).max() < SOLVE_TOL * np.abs(o.get("D")).max()
+    assert np.abs(o.get("D")[:, 1]).max() > 0.1
+
+
+def test_updated_lagrangian_first_iterates_match_oracle_to_round_off():
+    """Operator-level check of the UL momentum equation: with an exact inner solve the first outer iterates of a step
+    on the MOVED mesh (density field, relF flux tensor, deformed-normal traction) agree to round-off."""
+    kw = dict(nx=6, ny=3, nz=3, L=2.0, traction=(0.0, -6e3, 0.0), general=True, solidModel=K.MODEL_NONLIN_UL, nCorrectors=60,
+              g=(0.0, -9.81, 0.0), **EXACT_PCG)
+    g, o, mesh = _pair(cases.neo_hookean_cantilever, **kw)
+    for s in (g, o):
+        s.new_timestep(1.0); s.evolve(); s.update_total_fields(); s.new_timestep(1.0)
+    for it in range(3):
+        sg, so = g.outer_iteration(), o.outer_iteration()
+        assert sg["nIterations"] == so["nIterations"]
+        assert rel_l2(g.get("DD"), o.get("DD")) < 1e-8, it
+        assert rel_l2(g.get("sigma"), o.get("sigma")) < 1e-8, it
+    for s in (g, o):
+        s.op_assemble()
+    assert rel_l2(g.get("diag"), o.get("diag")) < OP_TOL
+    assert np.abs(g.get("source") - o.get("source")).max() / np.abs(o.get("source")).max() < 1e-10
+
+
+def test_beam_in_cross_flow_updated_lagrangian_backward_matches_oracle():
+    """C5: solid side of fluidSolidInteraction/beamInCrossFlow -- neoHookeanElastic, updated Lagrangian,
+    backward d2dt2 with the density field (backwardD2dt2Scheme.C:149-222, :391-470), solidSymmetry plane, prescribed
+    pressure ramp on the upstream face; four time steps."""
+    kw = dict(refine=1, solutionTolerance=1e-9, alternativeTolerance=1e-9, tolerance=1e-13, relTol=1e-3, nCorrectors=4000)
+    from oracle.binding import OracleSolid
+    from solids4foam_b200.solid_model import SolidModel
+    cg, co = cases.beam_in_cross_flow(preconditioner=K.PRECOND_DIAGONAL, **kw), cases.beam_in_cross_flow(preconditioner=K.PRECOND_DIC, **kw)
+    g, o = SolidModel(cg), OracleSolid(co)
+    n = cg.mesh.patch("upstream").size
+    for step in range(1, 5):
+        bc = K.solidTraction(np.zeros((n, 3)), pressure=np.full(n, 50.0 * min(0.1 * step, 1.0)))
+        for s in (g, o):
+            s.new_timestep(0.1)
+            s.set_bc("upstream", bc)
+        sg, so = g.evolve(), o.evolve()
+        assert sg["converged"] and so["converged"], (step, sg, so)
+        assert rel_l2(g.get("D"), o.get("D")) < SOLVE_TOL, step
+        assert rel_l2(g.get("sigma"), o.get("sigma")) < 10 * SOLVE_TOL, step
+        g.updateTotalFields(); o.update_total_fields()
+        assert np.abs(g.pointDD - o.pointDD).max() < SOLVE_TOL * np.abs(o.pointDD).max()
+    assert o.get("D")[:, 0].max() > 1e-5

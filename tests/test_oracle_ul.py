@@ -1,0 +1,171 @@
+"""CPU tests of the oracle's updated-Lagrangian path: nonLinGeomUpdatedLagSolid
+(SM/nonLinGeomUpdatedLagSolid/nonLinGeomUpdatedLagSolid.C:159-273, :360-374), the vol->point interpolation that moves the
+mesh (enhancedVolPointInterpolation, solidModel::moveMesh SM/solidModel/solidModel.C:2008-2148) and the rho-field inertia
+terms (NUM/backwardD2dt2Scheme/backwardD2dt2Scheme.C:149-222, :391-470).
+
+The reference ships no golden fields for this model; the pins are physical identities: exactness for a homogeneous
+deformation, agreement with the total-Lagrangian formulations of the same problem, mass conservation, and the small-load
+limit of the dynamics.
+"""
+import numpy as np
+
+from oracle.binding import OracleSolid
+from solids4foam_b200 import case as K
+from solids4foam_b200 import cases
+from solids4foam_b200 import mesh as M
+from s4f_testutil import rel_l2
+
+NAMES = ("xMin", "xMax", "yMin", "yMax", "zMin", "zMax")
+TIGHT = dict(solutionTolerance=1e-10, alternativeTolerance=1e-10, tolerance=1e-14, relTol=1e-3, nCorrectors=3000,
+             preconditioner=K.PRECOND_DIC)
+
+
+def test_move_points_affine_map_scales_geometry():
+    mesh = M.hex_box_general(3, 4, 5, 1.0, 2.0, 1.5, names=NAMES)
+    A = np.eye(3) + np.array([[0.1, 0.05, 0.0], [0.0, -0.08, 0.02], [0.03, 0.0, 0.06]])
+    moved = M.move_points(mesh, mesh.points @ A.T)
+    assert np.allclose(moved.V, np.linalg.det(A) * mesh.V, rtol=1e-12)
+    assert np.allclose(moved.C, mesh.C @ A.T, atol=1e-13)
+    assert np.allclose(moved.Cf, mesh.Cf @ A.T, atol=1e-13)
+    # Nanson: Sf' = det(A) A^-T Sf
+    assert np.allclose(moved.Sf, np.linalg.det(A) * mesh.Sf @ np.linalg.inv(A), atol=1e-13)
+    assert moved.owner is mesh.owner or np.array_equal(moved.owner, mesh.owner)
+
+
+def test_vol_to_point_interpolation_of_a_linear_field():
+    """Inverse-distance weights reproduce a linear field at points whose donors are placed symmetrically: internal points
+    of a uniform hex mesh (8 cells) and points inside a flat patch (4 faces); at patch edges the donors are one-sided and
+    the value is that of the donors' centroid (enhancedVolPointInterpolation.C:165-245)."""
+    case = cases.neo_hookean_cantilever(6, 4, 4, general=True, solidModel=K.MODEL_NONLIN_TL_TOTAL_DISP, L=3.0, H=2.0, W=2.0)
+    o = OracleSolid(case)
+    m = case.mesh
+    G = np.array([[0.01, 0.02, -0.01], [0.0, 0.03, 0.01], [0.02, -0.01, 0.005]])
+    lin = lambda X: 0.1 + X @ G.T
+    F = m.nInternalFaces
+    o.set("D", lin(m.C)); o.set("D_b", lin(m.Cf[F:]))
+    pD = o.interpolate_to_points("D")
+    x, y, z = m.points.T
+    on = lambda a, hi: (np.abs(a) < 1e-12) | (np.abs(a - hi) < 1e-12)
+    nb = on(x, 3.0).astype(int) + on(y, 2.0).astype(int) + on(z, 2.0).astype(int)
+    exact = lin(m.points)
+    assert np.abs(pD - exact)[nb == 0].max() < 1e-14          # internal points
+    assert np.abs(pD - exact)[nb == 1].max() < 1e-14          # inside a patch
+    assert np.abs(pD - exact)[nb >= 2].max() > 1e-4           # edges/corners: one-sided donors
+    # an edge point along x between yMin and zMin sees 2 faces of each patch: the donors' centroid is (x, h/4, h/4)
+    h = 0.5
+    e = np.nonzero((nb == 2) & on(y, 2.0) & on(z, 2.0) & (np.abs(y) < 1e-12) & (np.abs(z) < 1e-12))[0][0]
+    assert np.allclose(pD[e], lin(m.points[e] + np.array([0.0, h / 4, h / 4])), atol=1e-14)
+
+
+def test_homogeneous_deformation_in_two_updated_lagrangian_steps():
+    """A prescribed affine motion x = A X in two increments: the first increment is exact (least-squares gradient, Gauss
+    divergence of a constant flux tensor and the Rhie-Chow term all vanish identically for a linear field), F = A1; the
+    second works on the moved mesh, F = relF & F.old = A2 A1 up to the one-sided vol->point weights at the patch edges;
+    rho J stays rho0 (updateTotalFields :362)."""
+    mesh = M.hex_box_general(4, 4, 4, 1, 1, 1, names=NAMES)
+    A1 = np.eye(3) + np.array([[0.04, 0.02, 0], [0.0, -0.01, 0.01], [0.005, 0, 0.02]])
+    A2 = np.eye(3) + np.array([[0.03, -0.01, 0.01], [0.01, 0.02, 0.0], [0.0, 0.01, -0.02]])
+    law = K.mechanical_law("neoHookeanElastic", rho=1000.0, E=3e6, nu=0.3)
+    ctl = K.default_controls(solidModel=K.MODEL_NONLIN_UL, **TIGHT)
+    F0 = mesh.nInternalFaces
+    Xb = {p.name: mesh.Cf[F0 + p.start:F0 + p.start + p.size].copy() for p in mesh.patches}
+    bcs = {n: K.fixedDisplacement(np.zeros((len(Xb[n]), 3))) for n in NAMES}
+    c = K.SolidCase(mesh, bcs, law, ctl)
+    o = OracleSolid(c)
+    V0 = mesh.V.sum()
+    for step, A in enumerate((A1, A2 @ A1)):
+        o.new_timestep(1.0)
+        for n in NAMES:
+            o.set_bc(n, K.fixedDisplacement(Xb[n] @ (A - np.eye(3)).T))
+        st = o.evolve()
+        assert st["converged"]
+        err = np.abs(o.get("F").reshape(-1, 3, 3) - A).max()
+        assert err < (1e-10 if step == 0 else 5e-4), err
+        # neoHookeanElastic.C:275-303 closed form of the Cauchy stress for F = A
+        J = np.linalg.det(A); b = A @ A.T * J ** (-2.0 / 3.0)
+        s = (law.mu * (b - np.trace(b) / 3 * np.eye(3)) + 0.5 * law.K * (J * J - 1) * np.eye(3)) / J
+        sig = o.get("sigma")
+        ref = np.array([s[0, 0], s[0, 1], s[0, 2], s[1, 1], s[1, 2], s[2, 2]])
+        assert np.abs(sig - ref).max() / np.abs(ref).max() < (1e-9 if step == 0 else 2e-2)
+        o.update_total_fields()
+        assert np.allclose(o.get("rho") * o.get("J"), 1000.0, rtol=1e-12)
+        assert abs(c.mesh.V.sum() / V0 - J) < 5e-3
+
+
+def test_updated_and_total_lagrangian_reach_the_same_equilibria():
+    """nonLinearGeometryUpdatedLagrangian (mesh moved every step, relF from grad(DD) on the moved mesh) against
+    nonLinearGeometryTotalLagrangian (DD on the reference mesh): the first step is the same discrete problem; later steps
+    differ by discretisation error only."""
+    res = {}
+    for model in (K.MODEL_NONLIN_TL, K.MODEL_NONLIN_UL):
+        c = cases.neo_hookean_cantilever(12, 3, 3, traction=(0, 0, 0), solidModel=model, general=True, L=4.0,
+                                         **dict(TIGHT, solutionTolerance=1e-8, alternativeTolerance=1e-8, nCorrectors=20000))
+        o = OracleSolid(c)
+        n = c.mesh.patch("loaded").size
+        steps = []
+        for t in (-4e3, -8e3, -12e3):
+            tr = np.zeros((n, 3)); tr[:, 1] = t
+            o.new_timestep(1.0)
+            o.set_bc("loaded", K.solidTraction(tr))
+            st = o.evolve()
+            assert st["converged"], st
+            o.update_total_fields()
+            steps.append((o.get("D"), o.get("sigma")))
+        res[model] = steps
+    tl, ul = res[K.MODEL_NONLIN_TL], res[K.MODEL_NONLIN_UL]
+    assert rel_l2(ul[0][0], tl[0][0]) < 1e-12 and rel_l2(ul[0][1], tl[0][1]) < 1e-12
+    assert np.abs(tl[2][0]).max() > 0.2           # a finite deflection (5 % of the span)
+    assert rel_l2(ul[2][0], tl[2][0]) < 5e-3
+    assert rel_l2(ul[2][1], tl[2][1]) < 2e-2
+
+
+def test_updated_lagrangian_dynamics_small_load_limit():
+    """fvm::d2dt2(rho, DD) + fvc::d2dt2(rho, D.oldTime()) with the density field against rho*fvm::d2dt2(D) of the
+    total-displacement model: for a load small enough that relJ = 1 and the mesh motion is negligible the two
+    discretise the same equation, except that the GREAT-deltaT0 start-up of the explicit chain lasts one step longer
+    (backwardD2dt2Scheme.C:48-68); with the same start-up in both the two agree to solver tolerance (checked while writing
+    the oracle).  Euler has no start-up: agreement to solver tolerance.  Rhie-Chow is off: it smooths D in one model and
+    DD in the other."""
+    for scheme, tol in ((K.D2DT2_EULER, 1e-6), (K.D2DT2_BACKWARD, 0.2)):
+        out = {}
+        for model in (K.MODEL_NONLIN_TL_TOTAL_DISP, K.MODEL_NONLIN_UL):
+            c = cases.neo_hookean_cantilever(10, 3, 3, traction=(0, -0.5, 0), solidModel=model, general=True, L=4.0,
+                                             d2dt2Scheme=scheme, deltaT=2e-3, deltaT0=2e-3, stabilisation=K.STAB_NONE,
+                                             **dict(TIGHT, solutionTolerance=1e-8, alternativeTolerance=1e-8))
+            o = OracleSolid(c)
+            hist = []
+            for _ in range(5):
+                o.new_timestep(2e-3)
+                st = o.evolve()
+                assert st["converged"]
+                o.update_total_fields()
+                hist.append(o.get("D"))
+            out[model] = hist
+        a, b = out[K.MODEL_NONLIN_TL_TOTAL_DISP], out[K.MODEL_NONLIN_UL]
+        assert np.abs(a[-1]).max() > 0
+        assert rel_l2(b[0], a[0]) < 1e-6            # first step: same start-up coefficients
+        assert rel_l2(b[-1], a[-1]) < tol, (scheme, rel_l2(b[-1], a[-1]))
+        # the beam is still accelerating (period >> 5 dt): the tip moves monotonically
+        tip = [np.abs(h[:, 1]).max() for h in b]
+        assert all(t1 > t0 for t0, t1 in zip(tip, tip[1:]))
+
+
+def test_beam_in_cross_flow_solid_side_runs_and_conserves_mass():
+    """C5: solid side of tutorials/fluidSolidInteraction/beamInCrossFlow with a prescribed pressure ramp."""
+    c = cases.beam_in_cross_flow(refine=1, solutionTolerance=1e-7, alternativeTolerance=1e-7, preconditioner=K.PRECOND_DIC)
+    o = OracleSolid(c)
+    m0 = (c.mesh.V * 1000.0).sum()
+    npatch = c.mesh.patch("upstream").size
+    for step in range(1, 4):
+        o.new_timestep(0.1)
+        o.set_bc("upstream", K.solidTraction(np.zeros((npatch, 3)), pressure=np.full(npatch, 50.0 * min(0.1 * step, 1.0))))
+        st = o.evolve()
+        assert st["converged"], st
+        o.update_total_fields()
+    D = o.get("D")
+    assert D[:, 0].max() > 1e-5 and D[:, 0].max() > 10 * abs(D[:, 0].min())        # pushed downstream
+    pD = o.interpolate_to_points("D")
+    sym = np.abs(c.mesh.points[:, 2] - c.mesh.points[:, 2].max()) < 1e-9
+    assert np.abs(pD[sym, 2]).max() < 1e-15                                          # points stay in the symmetry plane
+    assert np.abs(c.mesh.points[sym, 2] - 0.2).max() < 1e-12
+    assert abs((c.mesh.V * o.get("rho")).sum() / m0 - 1) < 1e-3                       # rho V = rho0 V0 up to the vol->point error
