@@ -32,6 +32,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
 
 FULL = (800, 100, 100)      # 8.0 M cells: the configuration the metric is quoted on
 CPU_SAMPLE = (400, 50, 50)  # 1.0 M cells: bounded CPU sample of the same case

@@ -28,6 +28,7 @@ int s4f_setup_law(s4fgpu_ctx* c) {
     const double impK = (L.kind == S4F_LAW_LINEAR_ELASTIC) ? 2.0 * L.mu + L.lambda : (4.0 / 3.0) * L.mu + L.K;
     std::vector<double> h(c->ld, impK);
     S4F_CHECK_CUDA(c, c->impK.upload(h));
+    c->impK0 = impK; c->mValid = false;
     c->Hp = 0;
     if (L.nTable == 2) c->Hp = (L.tableSigY[1] - L.tableSigY[0]) / (L.tableEps[1] - L.tableEps[0]);
     int rc = s4f_alloc_model_fields(c);
@@ -186,7 +187,7 @@ int s4fgpu_set_geometry(s4fgpu_handle c, const double* C, const double* V, const
     // host geometry copies are only needed to build the rows (cell centres stay for the vol->point weights)
     std::vector<double>().swap(c->hSf); std::vector<double>().swap(c->hCf); std::vector<double>().swap(c->hCorr);
     std::vector<double>().swap(c->hW); std::vector<double>().swap(c->hNod);
-    c->geomSet = true; c->matrixValid = false; c->amgValid = false; c->histValid = false;
+    c->geomSet = true; c->matrixValid = false; c->amgValid = false; c->histValid = false; c->mValid = false;
     if (c->lawSet && !again) { rc = s4f_setup_law(c); if (rc) return rc; }
     return 0;
 }
@@ -212,7 +213,7 @@ int s4fgpu_set_controls(s4fgpu_handle c, const s4fgpu_controls* ctl) {
     S4F_REQUIRE(c, ctl->d2dt2Scheme >= S4F_D2DT2_STEADY_STATE && ctl->d2dt2Scheme <= S4F_D2DT2_BACKWARD, "set_controls: unknown d2dt2 scheme");
     if (ctl->d2dt2Scheme == S4F_D2DT2_BACKWARD && ctl->deltaT0 > 0)     // backwardD2dt2Scheme.C:316-322
         S4F_REQUIRE(c, std::fabs(ctl->deltaT - ctl->deltaT0) <= 1e-15 + 1e-12 * ctl->deltaT, "set_controls: backwardD2dt2Scheme not implemented for variable time steps");
-    c->ctl = *ctl; c->ctlSet = true; c->matrixValid = false; c->amgValid = false; c->histValid = false;
+    c->ctl = *ctl; c->ctlSet = true; c->matrixValid = false; c->amgValid = false; c->histValid = false; c->mValid = false;
     if (c->geomSet) return s4f_alloc_model_fields(c);
     return 0;
 }
@@ -274,6 +275,7 @@ int s4fgpu_upload(s4fgpu_handle c, int field, const double* host) {
     double* p; int nc, off, cnt;
     int rc = field_lookup(c, field, &p, &nc, &off, &cnt); if (rc) return rc;
     if (field == S4F_FIELD_D_OLD || field == S4F_FIELD_D_OLDOLD) c->histValid = false;
+    c->mValid = false;
     return s4f_aos_to_soa(c, host, p, cnt, nc, off);
 }
 
@@ -309,6 +311,7 @@ int s4fgpu_initialise(s4fgpu_handle c) {
     if ((rc = s4f_bc_evaluate(c))) return rc;
     if ((rc = d2d(c, c->Dprev.p, c->D.p, 3 * (size_t)c->ld))) return rc;
     if ((rc = s4f_halo_exchange(c, c->D.p, 3))) return rc;
+    c->mValid = false;
     if ((rc = s4f_grad(c))) return rc;
     if ((rc = s4f_update_totals(c, false, true))) return rc;
     if ((rc = s4f_kinematics(c))) return rc;                     // F, Finv, J of the finite-strain models (ctor, restart branch)
@@ -411,6 +414,7 @@ int s4fgpu_update_total_fields(s4fgpu_handle c) {
 int s4fgpu_op_grad(s4fgpu_handle c) {
     S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
     int rc = s4f_halo_exchange(c, c->D.p, 3); if (rc) return rc;
+    c->mValid = false;
     rc = s4f_grad(c); if (rc) return rc;
     rc = s4f_update_totals(c, false, true); if (rc) return rc;
     rc = s4f_kinematics(c); if (rc) return rc;

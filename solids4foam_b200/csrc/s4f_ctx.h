@@ -183,7 +183,10 @@ struct s4fgpu_ctx {
     DevBuf<double> Dtot, gradDtot;                // 3*ld, 9*ld (incremental models only)
     DevBuf<double> sigma, sigmaOld;               // 6*ld
     DevBuf<double> impK;                          // ld
-    DevBuf<double> T9;                            // 9*ld: J*Finv & sigma (TL)  [cells + boundary]
+    DevBuf<double> T9;                            // 9*ld: J*Finv & sigma (TL)  [cells + boundary]; on orthogonal meshes the combined
+                                                  // tensor M = T - gamma grad(D) of the factored right-hand side (k_source_m)
+    bool mValid = false;                          // T9 holds M of the current sigma / grad(D)
+    double impK0 = 0;                             // the (uniform) implicit stiffness
     DevBuf<double> Finv, Jt;                      // 9*ld, ld (TL solver kinematics)
     // law history
     DevBuf<double> lawF, lawFold, lawJ, lawJold, bEbar, bEbarOld, sigmaY, sigmaYOld, DSigmaY, epsPEq, epsPEqOld,
@@ -217,6 +220,9 @@ struct s4fgpu_ctx {
 
     bool incremental() const { return ctl.solidModel == S4F_MODEL_NONLIN_TL || ctl.solidModel == S4F_MODEL_NONLIN_UL; }
     bool UL() const { return ctl.solidModel == S4F_MODEL_NONLIN_UL; }
+    // orthogonal mesh + uniform Rhie-Chow coefficient: the right-hand side gathers ONE tensor per neighbour (k_source_m)
+    bool fastRhs() const { return !nonOrth; }
+    double gamma0() const { return ctl.stabilisation == S4F_STAB_RHIE_CHOW ? ctl.stabScaleFactor * impK0 : 0.0; }
     const double* gradForLaw() const { return incremental() ? gradDtot.p : gradD.p; }   // the registered "grad(D)"
     int NT() const { return N + G + B; }
     int bOff() const { return N + G; }
@@ -234,6 +240,7 @@ int s4f_bc_evaluate(s4fgpu_ctx* c);
 int s4f_relax_and_residual(s4fgpu_ctx* c, int iCorr);
 int s4f_grad(s4fgpu_ctx* c);
 int s4f_kinematics(s4fgpu_ctx* c);
+int s4f_make_m(s4fgpu_ctx* c);                       // lin-geom: M = sigma - gamma grad(D) when no law kernel produced it
 int s4f_update_totals(s4fgpu_ctx* c, bool disp, bool grad);
 int s4f_law_correct(s4fgpu_ctx* c);
 int s4f_solve_segregated(s4fgpu_ctx* c, double* psi, const double* source);   // device SoA pointers

@@ -340,6 +340,89 @@ __global__ void __launch_bounds__(S4F_SRC_BLOCK, 4) k_source_f(
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Right-hand side on ORTHOGONAL meshes (no correction vectors) with the uniform Rhie-Chow coefficient gamma of a
+// single-law case: the neighbour part of the factored form above collapses to ONE gathered tensor per neighbour,
+//      M = T - gamma grad(D)   (cells, ghost cells);   M_b = T_b on boundary slots (gamma_f = 0 there),
+//      rhs_q(P) = sum_e [ u_e & M_N(:,q) + c0_e (D_N,q - D_P,q) ] + U & M_P(:,q) + V (rho g_q + hist_q),
+// because Vv = sum gamma w (corr - Sf) = -gamma U when corr = 0.  M is written by the kernel that produces the stress
+// (law kernels / the flux-tensor kernel), so the right-hand side streams 5 values per entry (col, u, c0) and gathers
+// 12 (M, D) instead of 6 + 18 (eGam; D, T, grad(D)).  One row per lane, a slice per warp, entries in pairs with the
+// streamed loads issued ahead of the gathers.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(S4F_BLOCK, 3) k_source_m(
+    const int* __restrict__ slicePtr, const int* __restrict__ col, const double* __restrict__ eU, const double* __restrict__ eC0,
+    const double* __restrict__ rowK, const double* __restrict__ D, const double* __restrict__ M, const double* __restrict__ V,
+    const double* __restrict__ hist, double* __restrict__ source, int N, int ld, long long nE, int nSlices, double rhoGx, double rhoGy,
+    double rhoGz) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    const double* __restrict__ eU1 = eU + nE;
+    const double* __restrict__ eU2 = eU + 2 * nE;
+    constexpr int G = 2;
+    for (int s = warp; s < nSlices; s += nWarps) {
+        const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
+        const int row = s * 32 + lane;
+        const int r = (row < N) ? row : 0;
+        const double DP[3] = {D[r], D[(size_t)ld + r], D[2 * (size_t)ld + r]};
+        double acc[3] = {0, 0, 0};
+        for (int k0 = 0; k0 < width; k0 += G) {
+            int cc[G]; double u0[G], u1[G], u2[G], c0[G];
+#pragma unroll
+            for (int k = 0; k < G; k++) {
+                const bool ok = k0 + k < width;
+                const long long e = (long long)base + 32 * (ok ? k0 + k : k0) + lane;
+                cc[k] = col[e];
+                u0[k] = ok ? eU[e] : 0.0; u1[k] = ok ? eU1[e] : 0.0; u2[k] = ok ? eU2[e] : 0.0;
+                c0[k] = ok ? eC0[e] : 0.0;
+            }
+            double m[G][9], d[G][3];
+#pragma unroll
+            for (int k = 0; k < G; k++) {
+                const int n = cc[k];
+#pragma unroll
+                for (int q = 0; q < 9; q++) m[k][q] = M[(size_t)q * ld + n];
+#pragma unroll
+                for (int q = 0; q < 3; q++) d[k][q] = D[(size_t)q * ld + n];
+            }
+#pragma unroll
+            for (int k = 0; k < G; k++)
+#pragma unroll
+                for (int q = 0; q < 3; q++)
+                    acc[q] += u0[k] * m[k][q] + u1[k] * m[k][3 + q] + u2[k] * m[k][6 + q] + c0[k] * (d[k][q] - DP[q]);
+        }
+        if (row < N) {
+            const double U0 = rowK[row], U1 = rowK[(size_t)ld + row], U2 = rowK[2 * (size_t)ld + row], v = V[row];
+            const double rg[3] = {rhoGx, rhoGy, rhoGz};
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                double sv = acc[q] + U0 * M[(size_t)q * ld + row] + U1 * M[(size_t)(3 + q) * ld + row] + U2 * M[(size_t)(6 + q) * ld + row];
+                sv += v * rg[q];
+                if (hist) sv += v * hist[(size_t)q * ld + row];
+                source[(size_t)q * ld + row] = sv;
+            }
+        }
+    }
+}
+
+// M = sigma - gamma grad(D) for the linear-geometry model when the stress was not produced by a law kernel
+// (uploaded / initial fields)
+__global__ void __launch_bounds__(S4F_BLOCK) k_make_m(const double* __restrict__ sigma, const double* __restrict__ gradD,
+                                                      double* __restrict__ M, int N, int bOff, int B, int ld, double gamma) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N + B; t += gridDim.x * blockDim.x) {
+        const int i = (t < N) ? t : bOff + (t - N);
+        double s6[6], s9[9];
+#pragma unroll
+        for (int q = 0; q < 6; q++) s6[q] = sigma[(size_t)q * ld + i];
+        s_to_t(s6, s9);
+        const double g = (t < N) ? gamma : 0.0;
+#pragma unroll
+        for (int q = 0; q < 9; q++) M[(size_t)q * ld + i] = s9[q] - g * gradD[(size_t)q * ld + i];
+    }
+}
+
 // boundary part of the laplacian pair: - impKf_b magSf_b snGrad_b (explicit) + boundaryCoeffs
 // (addBoundarySource), boundaryCoeffs = impKf_b magSf_b gradientBoundaryCoeffs_b with
 //   fixedGradient: gradient();  fixedDisplacement: deltaCoeffs (D_b - k & gradD_P)  (fixedDisplacement...C:328-356)
@@ -716,10 +799,32 @@ static void launch_source(s4fgpu_ctx* c, const double* T) {
     c->launches++;
 }
 
+int s4f_make_m(s4fgpu_ctx* c) {
+    k_make_m<<<s4f_grid(c->numSMs, c->N + c->B), S4F_BLOCK, 0, c->stream>>>(c->sigma.p, c->gradD.p, c->T9.p, c->N, c->bOff(), c->B, c->ld, c->gamma0());
+    c->launches++;
+    S4F_CHECK_CUDA(c, cudaGetLastError());
+    c->mValid = true;
+    return s4f_halo_exchange(c, c->T9.p, 9);
+}
+
 int s4f_assemble_source(s4fgpu_ctx* c) {
     int rh = s4f_d2dt2_history(c); if (rh) return rh;
-    if (c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP) launch_source<false>(c, c->sigma.p);
-    else launch_source<true>(c, c->T9.p);
+    if (c->fastRhs()) {
+        if (!c->mValid) {
+            int rc = (c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP) ? s4f_make_m(c) : s4f_kinematics(c);
+            if (rc) return rc;
+        }
+        const double rs = c->UL() ? 0.0 : c->law.rho;
+        const double* hist = (c->ctl.d2dt2Scheme == S4F_D2DT2_STEADY_STATE && !c->UL()) ? nullptr : c->d2Hist.p;
+        k_source_m<<<s4f_grid(c->numSMs, (long long)c->nSlices * 32, 6), S4F_BLOCK, 0, c->stream>>>(
+            c->slicePtr.p, c->col.p, c->eU.p, c->eC0.p, c->rowK.p, c->D.p, c->T9.p, c->V.p, hist, c->source.p, c->N, c->ld, c->nEntries,
+            c->nSlices, rs * c->ctl.g[0], rs * c->ctl.g[1], rs * c->ctl.g[2]);
+        c->launches++;
+    } else if (c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP) launch_source<false>(c, c->sigma.p);
+    else {
+        if (!c->mValid) { int rc = s4f_kinematics(c); if (rc) return rc; }     // T9 held M of an orthogonal mesh before the mesh moved
+        launch_source<true>(c, c->T9.p);
+    }
     if (c->nBCells > 0) {
         k_source_boundary<<<(c->nBCells + 127) / 128, 128, 0, c->stream>>>(c->bcCells.p, c->bcPtr.p, c->bcFaces.p, c->bKind.p, c->bN.p, c->bK.p,
                                                                          c->bDelta.p, c->bMagSf.p, c->impK.p, c->tracGrad.p, c->D.p, c->gradD.p,
@@ -844,9 +949,10 @@ int s4f_time_fv_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, double
     *msOut = total / reps;
     const double N = c->N, nnz = (double)c->nnzOff + (c->B - c->G);   // row entries incl. boundary faces
     if (kernel == S4F_KERNEL_GRAD) *bytesOut = 24 * N + nnz * (4 + 24) + 72 * N + 0.125 * N;                 // D, (col, ls), gradD out
-    else if (kernel == S4F_KERNEL_LAW) *bytesOut = (72 + 48) * N;                                              // gradD in, sigma out (Hooke)
+    else if (kernel == S4F_KERNEL_LAW) *bytesOut = (72 + 48 + (c->fastRhs() ? 72 : 0)) * N;                    // gradD in, sigma out (Hooke) [+ M out]
     else if (kernel == S4F_KERNEL_GAMG_STEP0) { int rc = s4f_amg_step0(c, c->rA.p, bytesOut); if (rc) return rc; }
     else if (kernel == S4F_KERNEL_GAMG_VCYCLE) { int nl, sz[16]; double st; int rc = s4f_amg_info(c, &nl, sz, 16, bytesOut, &st); if (rc) return rc; }
+    else if (c->fastRhs()) *bytesOut = (24 + 72) * N + nnz * (4 + 24 + 8) + (24 + 8 + 24 + 0.125) * N;          // D, M | col,u,c0 | U, V, out
     else *bytesOut = (24 + 48 + 72) * N + nnz * (4 + 24 + 8 + 8) + (48 + 8 + 24 + 0.125) * N;                   // D,sigma,gradD | col,u,c0,gamma | rowK, V, out
     return 0;
 }

@@ -82,8 +82,11 @@ __device__ __forceinline__ void st_soa(double* __restrict__ f, int ld, int i, co
 
 // ---- linearElastic: epsilon = symm(gradD); sigma = 2 mu dev(eps) + K tr(eps) I + sigma0 ---------
 struct S6 { double v[6]; };
+// M (nullable): the combined tensor sigma - gamma grad(D) of the right-hand side on orthogonal meshes (k_source_m), sigma_b on
+// the boundary slots
 __global__ void __launch_bounds__(S4F_BLOCK) k_law_linear_elastic(const double* __restrict__ gradD, double* __restrict__ sigma, int N,
-                                                                  int bOff, int B, int ld, double mu, double K, S6 sigma0) {
+                                                                  int bOff, int B, int ld, double mu, double K, S6 sigma0,
+                                                                  double* __restrict__ M, double gamma) {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N + B; t += gridDim.x * blockDim.x) {
         const int i = field_index(t, N, bOff);
         double g[9], e[6], de[6], s[6];
@@ -95,6 +98,13 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_law_linear_elastic(const double* 
         for (int q = 0; q < 6; q++) s[q] = 2.0 * mu * de[q] + sigma0.v[q];
         s[0] += sh; s[3] += sh; s[5] += sh;
         st_soa<6>(sigma, ld, i, s);
+        if (M) {
+            double s9[9]; s_to_t(s, s9);
+            const double gm = (t < N) ? gamma : 0.0;
+#pragma unroll
+            for (int q = 0; q < 9; q++) s9[q] -= gm * g[q];
+            st_soa<9>(M, ld, i, s9);
+        }
     }
 }
 
@@ -317,9 +327,11 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_law_lin_mises(LinMisesPtrs p, int
 }
 
 // ---- total-Lagrangian flux tensor: F = I + gradD.T(); Finv; J; T = J Finv & sigma ------------------
+// gradSol (nullable): gradient of the SOLUTION field (grad(D) or grad(DD)); when given, cells get T - gamma gradSol, the combined
+// tensor of the right-hand side on orthogonal meshes (k_source_m)
 __global__ void __launch_bounds__(S4F_BLOCK) k_tl_flux_tensor(const double* __restrict__ gradD, const double* __restrict__ sigma,
                                                               double* __restrict__ T9, double* __restrict__ Finv, double* __restrict__ Jt,
-                                                              int N, int bOff, int B, int ld) {
+                                                              int N, int bOff, int B, int ld, const double* __restrict__ gradSol, double gamma) {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N + B; t += gridDim.x * blockDim.x) {
         const int i = field_index(t, N, bOff);
         double g[9], Fm[9], Fi[9], s6[6], s9[9], T[9];
@@ -331,6 +343,11 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_tl_flux_tensor(const double* __re
         t_mul(Fi, s9, T);
 #pragma unroll
         for (int q = 0; q < 9; q++) T[q] *= J;
+        if (gradSol && t < N) {
+            double gs[9]; ld_soa<9>(gradSol, ld, i, gs);
+#pragma unroll
+            for (int q = 0; q < 9; q++) T[q] -= gamma * gs[q];
+        }
         st_soa<9>(T9, ld, i, T);
         Jt[i] = J;
         if (t >= N) st_soa<9>(Finv, ld, i, Fi);      // only the traction BC reads Finv, on boundary faces
@@ -360,8 +377,10 @@ int s4f_law_correct(s4fgpu_ctx* c) {
     const double* gD = UL ? c->gradD.p : c->gradForLaw();        // UL laws read grad(DD) (mechanicalLaw.C:1064-1072)
     if (L.kind == S4F_LAW_LINEAR_ELASTIC) {
         S6 s0; for (int q = 0; q < 6; q++) s0.v[q] = L.sigma0[q];
-        k_law_linear_elastic<<<grid, S4F_BLOCK, 0, c->stream>>>(gD, c->sigma.p, N, bOff, B, ld, L.mu, L.K, s0);
+        const bool emitM = c->fastRhs() && c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP;
+        k_law_linear_elastic<<<grid, S4F_BLOCK, 0, c->stream>>>(gD, c->sigma.p, N, bOff, B, ld, L.mu, L.K, s0, emitM ? c->T9.p : nullptr, c->gamma0());
         c->launches++;
+        if (emitM) { c->mValid = true; S4F_CHECK_CUDA(c, cudaGetLastError()); return s4f_halo_exchange(c, c->T9.p, 9); }
     } else if (L.kind == S4F_LAW_NEO_HOOKEAN_ELASTIC) {
         k_law_neo_hookean<<<grid, S4F_BLOCK, 0, c->stream>>>(gD, c->sigma.p, c->lawJ.p, N, bOff, B, ld, L.mu, L.K, UL ? c->lawFold.p : nullptr,
                                                             c->lawF.p);
@@ -397,10 +416,13 @@ int s4f_law_correct(s4fgpu_ctx* c) {
     S4F_CHECK_CUDA(c, cudaGetLastError());
     if (c->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP) {
         // UL: relF = I + gradDD.T() takes the place of F: fvc::div(relJ*relFinv & sigma), nonLinGeomUpdatedLagSolid.C:188
-        k_tl_flux_tensor<<<grid, S4F_BLOCK, 0, c->stream>>>(gD, c->sigma.p, c->T9.p, c->Finv.p, c->Jt.p, N, bOff, B, ld);
+        k_tl_flux_tensor<<<grid, S4F_BLOCK, 0, c->stream>>>(gD, c->sigma.p, c->T9.p, c->Finv.p, c->Jt.p, N, bOff, B, ld,
+                                                            c->fastRhs() ? c->gradD.p : nullptr, c->gamma0());
         c->launches++;
+        c->mValid = true;
         return s4f_halo_exchange(c, c->T9.p, 9);
     }
+    c->mValid = false;          // other laws under the linear-geometry model: M is formed by k_make_m before the next right-hand side
     return s4f_halo_exchange(c, c->sigma.p, 6);
 }
 
@@ -409,8 +431,10 @@ int s4f_law_correct(s4fgpu_ctx* c) {
 int s4f_kinematics(s4fgpu_ctx* c) {
     if (c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP) return 0;
     const int grid = s4f_grid(c->numSMs, c->N + c->B);
-    k_tl_flux_tensor<<<grid, S4F_BLOCK, 0, c->stream>>>(c->UL() ? c->gradD.p : c->gradForLaw(), c->sigma.p, c->T9.p, c->Finv.p, c->Jt.p, c->N, c->bOff(), c->B, c->ld);
+    k_tl_flux_tensor<<<grid, S4F_BLOCK, 0, c->stream>>>(c->UL() ? c->gradD.p : c->gradForLaw(), c->sigma.p, c->T9.p, c->Finv.p, c->Jt.p, c->N, c->bOff(), c->B, c->ld,
+                                                        c->fastRhs() ? c->gradD.p : nullptr, c->gamma0());
     c->launches++;
+    c->mValid = true;
     S4F_CHECK_CUDA(c, cudaGetLastError());
     return s4f_halo_exchange(c, c->T9.p, 9);
 }

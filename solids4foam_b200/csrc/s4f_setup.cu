@@ -300,6 +300,7 @@ int s4f_alloc_model_fields(s4fgpu_ctx* c) {
             c->rhoInit = true;
         }
     }
+    if (c->ctlSet && !TL) S4F_CHECK_CUDA(c, A(c->T9, 9));      // lin-geom: the combined tensor M of the factored right-hand side
     if (TL) {
         if (c->Finv.n != 9 * ld) { S4F_CHECK_CUDA(c, A(c->Finv, 9)); fillI(c->Finv, 9, dT, 3); }
         if (c->Jt.n != ld) { S4F_CHECK_CUDA(c, A(c->Jt, 1)); fillI(c->Jt, 1, d1, 1); }
