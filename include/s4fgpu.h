@@ -107,7 +107,9 @@ enum {
     S4F_FIELD_DD = 21,           /* vector [N]  displacement increment (incremental solid models only) */
     S4F_FIELD_GRAD_DD = 22,      /* tensor [N] */
     S4F_FIELD_RHO = 23,          /* scalar [N]  density field of the updated-Lagrangian model (rho_ = rho_.oldTime()/relJ_) */
-    S4F_FIELD_DD_B = 24          /* vector [B]  boundary values of DD */
+    S4F_FIELD_DD_B = 24,         /* vector [B]  boundary values of DD */
+    S4F_FIELD_SIGMA_HYD = 25,    /* scalar [N]  hydrostatic stress of the law (mechanicalLaw::sigmaHyd()) */
+    S4F_FIELD_GRAD_SIGMA_HYD = 26 /* vector [N] */
 };
 
 /* ---- parameter blocks ---------------------------------------------------------------------- */
@@ -124,6 +126,8 @@ typedef struct {
     double tableSigY[64];
     int updateBEbarConsistent; /* neoHookeanElasticMisesPlastic.C:846-853, default 1 */
     double DEpsilonPRelax;     /* fvSolution relaxationFactors fields DEpsilonP (1 = none) */
+    int solvePressureEqn;      /* mechanicalLaw.C:1525-1528: smooth sigmaHyd with the pressure Poisson equation :1374-1468 */
+    double pressureSmoothingScaleFactor; /* :1529-1532, default 100 */
 } s4fgpu_law;
 
 /* solidProperties <model>Coeffs + fvSchemes + fvSolution entries used on the path */
@@ -210,11 +214,17 @@ int s4fgpu_set_geometry(s4fgpu_handle h, const double* C, const double* V, const
 int s4fgpu_set_points(s4fgpu_handle h, int nPoints, const double* points, const int* faceVertsPtr,
                       const int* faceVerts);
 
-/* mechanicalModel::interpolate(D, pointD) (mechanicalModel.C:786-826) -> volToPoint().interpolate(vf, pf)
- * (enhancedVolPointInterpolate.C:425-447): inverse-distance weighting from the cell centres for internal
- * points, from the boundary-face values for points on non-empty, non-coupled patches, then the
- * symmetry-plane point constraint.  field = S4F_FIELD_D or S4F_FIELD_DD; pointField [3*nPoints] host. */
-int s4fgpu_interpolate_to_points(s4fgpu_handle h, int field, double* pointField);
+/* mode S4F_POINT_INTERP_PATCH: mechanicalModel::interpolate(D, pointD) (mechanicalModel.C:786-826) ->
+ * volToPoint().interpolate(vf, pf) (enhancedVolPointInterpolate.C:425-447): inverse-distance weighting from the
+ * cell centres for internal points, from the boundary-face values for points on non-empty, non-coupled patches,
+ * then the symmetry-plane point constraint (the interpolation solidModel::moveMesh uses).
+ * mode S4F_POINT_INTERP_GRAD: mechanicalModel::interpolate(D, gradD, pointD) (mechanicalModel.C:829-877) ->
+ * volToPoint().interpolate(vf, gradVf, pf) (enhancedVolPointInterpolate.C:351-418): every point from its
+ * pointCells with the cell gradient extrapolation, pf = sum w (vf + delta & gradVf) / sum w, w = 1/|delta| (the
+ * pointD / pointDD the solid models hand to the FSI coupling, e.g. nonLinGeomUpdatedLagSolid.C:249).
+ * field = S4F_FIELD_D or S4F_FIELD_DD; pointField [3*nPoints] host. */
+enum { S4F_POINT_INTERP_PATCH = 0, S4F_POINT_INTERP_GRAD = 1 };
+int s4fgpu_interpolate_to_points(s4fgpu_handle h, int field, int mode, double* pointField);
 
 /* ---- models ---------------------------------------------------------------------------------- */
 

@@ -102,9 +102,10 @@ class OracleSolid:
         self._check(self.L.s4fo_evolve(self.h, C.byref(st)))
         return st.as_dict()
 
-    def interpolate_to_points(self, name: str = "D") -> np.ndarray:
+    def interpolate_to_points(self, name: str = "D", with_gradient: bool = False) -> np.ndarray:
         out = np.empty((self.case.mesh.points.shape[0], 3))
-        self._check(self.L.s4fo_interpolate_to_points(self.h, K.FIELD[name], K._dptr(out)))
+        mode = K.POINT_INTERP_GRAD if with_gradient else K.POINT_INTERP_PATCH
+        self._check(self.L.s4fo_interpolate_to_points(self.h, K.FIELD[name], mode, K._dptr(out)))
         return out
 
     def update_total_fields(self):

@@ -112,6 +112,8 @@ double tableLookup(const s4fgpu_law& L, double x) {
 struct SolverPerf { double initRes, finalRes; int nIter; };
 
 }  // namespace
+struct s4f_oracle;
+namespace { void updateSigmaHydSmoothed(s4f_oracle& o, double impK); }
 
 struct s4f_oracle {
     std::string err;
@@ -139,6 +141,8 @@ struct s4f_oracle {
     // updated-Lagrangian model (SM/nonLinGeomUpdatedLagSolid): the old-time chains that
     // fvm::d2dt2(rho, DD) + fvc::d2dt2(rho, D.oldTime()) reach, and the density field with its old times
     dvec Dooooo, DDo, DDoo, DDooo, DDoooo, rho, rhoO, rhoOO;
+    dvec gradSigmaHyd, sigmaHydExp;     // pressure smoothing (mechanicalLaw.C:1366-1476)
+    SolverPerf perfP{0, 0, 0};
     // polyMesh points/faces for vol->point interpolation
     int nPoints = 0;
     dvec points; ivec fvPtr, fv, pcPtr, pcCells, pbPtr, pbFaces;
@@ -658,11 +662,27 @@ void lawLinearElasticMises(s4f_oracle& o) {
 }
 
 void lawCorrect(s4f_oracle& o) {
+    dvec prevHyd; if (o.law.solvePressureEqn) prevHyd = o.sigmaHyd;       // sigmaHyd persists: initial guess of the pressure solve
     switch (o.law.kind) {
         case S4F_LAW_LINEAR_ELASTIC: lawLinearElastic(o); break;
         case S4F_LAW_NEO_HOOKEAN_ELASTIC: lawNeoHookean(o); break;
         case S4F_LAW_NEO_HOOKEAN_MISES_PLASTIC: lawNeoHookeanMises(o); break;
         case S4F_LAW_LINEAR_ELASTIC_MISES_PLASTIC: lawLinearElasticMises(o); break;
+    }
+    if (o.law.solvePressureEqn) {
+        // the laws above evaluated sigma with the explicit hydrostatic stress (held in sigmaHyd); updateSigmaHyd
+        // (mechanicalLaw.C:1366-1468) replaces it by the solution of the pressure equation:
+        //   linearElastic.C:337-340   sigma = 2 mu dev(eps) + sigmaHyd I + sigma0
+        //   neoHookeanElastic.C:295-302, neoHookeanElasticMisesPlastic.C:1215-1222   sigma = (sigmaHyd I + s)/J
+        const bool lin = (o.law.kind == S4F_LAW_LINEAR_ELASTIC || o.law.kind == S4F_LAW_LINEAR_ELASTIC_MISES_PLASTIC);
+        const int n = o.NB();
+        o.sigmaHydExp = o.sigmaHyd;
+        o.sigmaHyd = prevHyd;
+        updateSigmaHydSmoothed(o, o.impK[0]);
+        for (int c = 0; c < n; c++) {
+            const double d = (o.sigmaHyd[c] - o.sigmaHydExp[c]) / (lin ? 1.0 : o.lawJ[c]);
+            o.sigma[6 * c] += d; o.sigma[6 * c + 3] += d; o.sigma[6 * c + 5] += d;
+        }
     }
 }
 
@@ -1103,6 +1123,58 @@ SolverPerf solvePBiCGStab(s4f_oracle& o, const double* diag, double* psi, const 
 }
 
 // [OF-ext] fvMatrix<vector>::solveSegregated: per solved component, addBoundaryDiag, solve.
+// mechanicalLaw::updateSigmaHyd, solvePressureEqn branch (ML/mechanicalLaw/mechanicalLaw.C:1374-1468):
+//   AD = DEqnA = DEqn.A() ([OF-ext] fvMatrix::A(): (diag + component average of internalCoeffs)/V, zero-gradient patches)
+//   rDAf = pressureSmoothingScaleFactor * linear interpolate(impK/AD)
+//   fvm::Sp(1, p) - fvm::laplacian(rDAf, p) == pExplicit - fvc::div(rDAf*(interpolate(grad p) & Sf))
+//   p: zeroGradient patches (:452-458) -> no boundary coefficients; the corrected-laplacian's non-orthogonal part is
+//   explicit, gamma magSf (corr & interpolate(fvc::grad(p))) [OF-ext gaussLaplacianScheme], and fvc::grad(p) of the
+//   current p is the stored grad(sigmaHyd) (:1467).  Then p.relax() (no factor given: none), grad p = fvc::grad(p).
+void updateSigmaHydSmoothed(s4f_oracle& o, double /*impK: uniform, o.impK holds the field*/) {
+    const int N = o.N, F = o.F, B = o.B;
+    if ((int)o.gradSigmaHyd.size() != 3 * (N + B)) o.gradSigmaHyd.assign(3 * (size_t)(N + B), 0.0);
+    dvec r(N + B);
+    for (int c = 0; c < N; c++) {
+        const double AD = (o.diagC[3 * c] + o.diagC[3 * c + 1] + o.diagC[3 * c + 2]) / 3.0 / o.V[c];
+        r[c] = o.impK[c] / AD;
+    }
+    for (int b = 0; b < B; b++) r[N + b] = o.impK[N + b] / (o.impK[o.faceCells[b]] / r[o.faceCells[b]]);
+    dvec up(F), dg(N), src(N);
+    for (int c = 0; c < N; c++) { dg[c] = o.V[c]; src[c] = o.V[c] * o.sigmaHydExp[c]; }
+    const double sc = o.law.pressureSmoothingScaleFactor;
+    for (int f = 0; f < F; f++) {
+        const int P = o.own[f], Nn = o.nei[f];
+        const double wf = o.w[f];
+        const double gam = sc * (wf * r[P] + (1 - wf) * r[Nn]);
+        const double a = gam * o.magSf[f] * o.nod[f];
+        up[f] = -a; dg[P] += a; dg[Nn] += a;
+        double gf[3]; for (int q = 0; q < 3; q++) gf[q] = wf * o.gradSigmaHyd[3 * P + q] + (1 - wf) * o.gradSigmaHyd[3 * Nn + q];
+        const double flux = gam * (o.magSf[f] * dot3(&o.corr[3 * f], gf) - dot3(&o.Sf[3 * f], gf));
+        src[P] += flux; src[Nn] -= flux;
+    }
+    for (int b = 0; b < B; b++) {       // - div term on the boundary: rDAf_b (grad p)_b & Sf_b  (zero once grad p is boundary-corrected)
+        const double gam = sc * r[N + b];
+        src[o.faceCells[b]] -= gam * dot3(&o.Sf[3 * (size_t)(F + b)], &o.gradSigmaHyd[3 * (size_t)(N + b)]);
+    }
+    dvec x(o.sigmaHyd.begin(), o.sigmaHyd.begin() + N);
+    o.upper.swap(up);
+    o.perfP = solvePCG(o, dg.data(), x.data(), src.data());
+    o.upper.swap(up);
+    for (int c = 0; c < N; c++) o.sigmaHyd[c] = x[c];
+    for (int b = 0; b < B; b++) o.sigmaHyd[N + b] = x[o.faceCells[b]];                  // zeroGradient
+    // grad(sigmaHyd) = fvc::grad(sigmaHyd): scalar gradient through the vector machinery (component 0)
+    dvec X(3 * (size_t)(N + B), 0.0), g;
+    for (int c = 0; c < N + B; c++) X[3 * c] = o.sigmaHyd[c];
+    gradInterior(o, X, g);
+    for (int c = 0; c < N; c++) for (int i = 0; i < 3; i++) o.gradSigmaHyd[3 * c + i] = g[9 * c + 3 * i];
+    for (int b = 0; b < B; b++) {       // gaussGrad::correctBoundaryConditions with snGrad = 0
+        const int P = o.faceCells[b];
+        double n[3], k[3], delta; patchGeom(o, b, n, k, delta);
+        const double ng = dot3(n, &o.gradSigmaHyd[3 * P]);
+        for (int i = 0; i < 3; i++) o.gradSigmaHyd[3 * (N + b) + i] = o.gradSigmaHyd[3 * P + i] - n[i] * ng;
+    }
+}
+
 void solveSegregated(s4f_oracle& o, double* psi /*AoS [3N]*/, const double* source /*AoS*/) {
     const int N = o.N;
     dvec x(N), b(N), dg(N);
@@ -1310,13 +1382,30 @@ int s4fo_set_points(s4f_oracle* o, int nPoints, const double* points, const int*
 // inverse-distance weights of enhancedVolPointInterpolation.C:165-198 for points off the patches, interpolateBoundaryField
 // :262-330 with the weights of :201-245 from the boundary-face values for patch points, then pointConstraints::constrain
 // ([OF-ext]: symmetryPlane points lose their normal component, transform(I - nn, pf)).
-int s4fo_interpolate_to_points(s4f_oracle* o, int field, double* out) {
+int s4fo_interpolate_to_points(s4f_oracle* o, int field, int mode, double* out) {
     if (o->nPoints == 0) { o->err = "interpolate_to_points: call set_points first"; return 1; }
-    const dvec* X = nullptr;
-    if (field == S4F_FIELD_D) X = o->incremental() ? &o->Dtot : &o->D;
-    else if (field == S4F_FIELD_DD && o->incremental()) X = &o->D;
+    const dvec* X = nullptr; const dvec* G = nullptr;
+    if (field == S4F_FIELD_D) { X = o->incremental() ? &o->Dtot : &o->D; G = o->incremental() ? &o->gradDtot : &o->gradD; }
+    else if (field == S4F_FIELD_DD && o->incremental()) { X = &o->D; G = &o->gradD; }
     if (!X) { o->err = "interpolate_to_points: field must be D or DD"; return 1; }
     const int N = o->N, F = o->F;
+    if (mode == S4F_POINT_INTERP_GRAD) {
+        // interpolate(vf, gradVf, pf), enhancedVolPointInterpolate.C:351-418: all points, cells only, no constraints
+        for (int p = 0; p < o->nPoints; p++) {
+            const double* x = &o->points[3 * (size_t)p];
+            double acc[3] = {0, 0, 0}, sw = 0;
+            for (int j = o->pcPtr[p]; j < o->pcPtr[p + 1]; j++) {
+                const int c = o->pcCells[j];
+                const double d[3] = {x[0] - o->C[3 * (size_t)c], x[1] - o->C[3 * (size_t)c + 1], x[2] - o->C[3 * (size_t)c + 2]};
+                const double w = 1.0 / mag3(d);
+                double dg[3]; vT(d, &(*G)[9 * (size_t)c], dg);             // delta & gradVf
+                for (int q = 0; q < 3; q++) acc[q] += w * ((*X)[3 * (size_t)c + q] + dg[q]);
+                sw += w;
+            }
+            for (int q = 0; q < 3; q++) out[3 * (size_t)p + q] = acc[q] / sw;
+        }
+        return 0;
+    }
     for (int p = 0; p < o->nPoints; p++) {
         const double* x = &o->points[3 * (size_t)p];
         double acc[3] = {0, 0, 0}, sw = 0;
@@ -1399,6 +1488,8 @@ static dvec* fieldPtr(s4f_oracle* o, int field, int& ncomp, int& off, int& count
         case S4F_FIELD_EPSILON_P: ncomp = 6; return &o->epsP;
         case S4F_FIELD_TRACTION_GRADIENT_B: ncomp = 3; count = B; return &o->tracGrad;
         case S4F_FIELD_RHO: ncomp = 1; return &o->rho;
+        case S4F_FIELD_SIGMA_HYD: ncomp = 1; return &o->sigmaHyd;
+        case S4F_FIELD_GRAD_SIGMA_HYD: ncomp = 3; return &o->gradSigmaHyd;
         case S4F_FIELD_DD_B: ncomp = 3; off = N; count = B; return o->incremental() ? &o->D : nullptr;
     }
     return nullptr;

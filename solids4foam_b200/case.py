@@ -29,16 +29,17 @@ STAB_NONE, STAB_RHIE_CHOW = 0, 1
 RELAX_FIXED, RELAX_AITKEN = 0, 1
 SOLVER_PCG, SOLVER_PBICGSTAB = 0, 1
 PRECOND_NONE, PRECOND_DIAGONAL, PRECOND_DIC, PRECOND_CHEBYSHEV, PRECOND_GAMG = 0, 1, 2, 3, 4
+POINT_INTERP_PATCH, POINT_INTERP_GRAD = 0, 1
 
 FIELD = dict(D=0, D_old=1, D_oldOld=2, gradD=3, sigma=4, D_b=5, gradD_b=6, sigma_b=7, source=8, diag=9,
              upper=10, epsilonPEq=11, sigmaY=12, bEbar=13, DLambda=14, J=15, F=16, gradD_old=17,
-             DEpsilonP=18, tractionGradient_b=19, epsilonP=20, DD=21, gradDD=22, rho=23, DD_b=24)
+             DEpsilonP=18, tractionGradient_b=19, epsilonP=20, DD=21, gradDD=22, rho=23, DD_b=24, sigmaHyd=25, gradSigmaHyd=26)
 # (ncomp, 'N' | 'B' | 'F')
 FIELD_SHAPE = dict(D=(3, "N"), D_old=(3, "N"), D_oldOld=(3, "N"), gradD=(9, "N"), sigma=(6, "N"), D_b=(3, "B"),
                    gradD_b=(9, "B"), sigma_b=(6, "B"), source=(3, "N"), diag=(3, "N"), upper=(1, "F"),
                    epsilonPEq=(1, "N"), sigmaY=(1, "N"), bEbar=(6, "N"), DLambda=(1, "N"), J=(1, "N"), F=(9, "N"),
                    gradD_old=(9, "N"), DEpsilonP=(6, "N"), tractionGradient_b=(3, "B"), epsilonP=(6, "N"),
-                   DD=(3, "N"), gradDD=(9, "N"), rho=(1, "N"), DD_b=(3, "B"))
+                   DD=(3, "N"), gradDD=(9, "N"), rho=(1, "N"), DD_b=(3, "B"), sigmaHyd=(1, "N"), gradSigmaHyd=(3, "N"))
 
 MODEL_NAMES = {
     # reference TypeName -> (gpu TypeName registered by the plugin, enum)
@@ -59,7 +60,8 @@ class Law(C.Structure):
     _fields_ = [("kind", C.c_int), ("rho", C.c_double), ("mu", C.c_double), ("K", C.c_double),
                 ("lambda_", C.c_double), ("sigma0", C.c_double * 6), ("nTable", C.c_int),
                 ("tableEps", C.c_double * 64), ("tableSigY", C.c_double * 64),
-                ("updateBEbarConsistent", C.c_int), ("DEpsilonPRelax", C.c_double)]
+                ("updateBEbarConsistent", C.c_int), ("DEpsilonPRelax", C.c_double),
+                ("solvePressureEqn", C.c_int), ("pressureSmoothingScaleFactor", C.c_double)]
 
 
 class Controls(C.Structure):
@@ -132,7 +134,8 @@ def default_controls(**kw) -> Controls:
 def mechanical_law(type: str, rho: float = 0.0, E: Optional[float] = None, nu: Optional[float] = None,
                    mu: Optional[float] = None, K: Optional[float] = None, planeStress: bool = False,
                    sigma0: Optional[Sequence[float]] = None, table: Optional[Sequence[Sequence[float]]] = None,
-                   updateBEbarConsistent: bool = True, DEpsilonPRelax: float = 1.0) -> Law:
+                   updateBEbarConsistent: bool = True, DEpsilonPRelax: float = 1.0, solvePressureEqn: bool = False,
+                   pressureSmoothingScaleFactor: float = 100.0) -> Law:
     """The mechanicalProperties entry -> POD parameters, with the reference constructors' formulas:
     linearElastic.C:62-133, neoHookeanElastic.C:51-85, neoHookeanElasticMisesPlastic.C:868-930,
     linearElasticMisesPlastic (same E,nu -> mu,K as linearElastic)."""
@@ -189,6 +192,8 @@ def mechanical_law(type: str, rho: float = 0.0, E: Optional[float] = None, nu: O
             L.tableSigY[i] = s
     L.updateBEbarConsistent = 1 if updateBEbarConsistent else 0
     L.DEpsilonPRelax = DEpsilonPRelax
+    L.solvePressureEqn = 1 if solvePressureEqn else 0        # mechanicalLaw.C:1525-1532
+    L.pressureSmoothingScaleFactor = pressureSmoothingScaleFactor
     return L
 
 
@@ -341,7 +346,7 @@ def declare_api(lib, prefix: str, handle_t) -> None:
     f("op_amul").argtypes = [handle_t, C.c_int, dp, dp]
     f("op_solve").argtypes = [handle_t, dp, dp, C.POINTER(Stats)]
     f("set_points").argtypes = [handle_t, C.c_int, dp, ip, ip]
-    f("interpolate_to_points").argtypes = [handle_t, C.c_int, dp]
+    f("interpolate_to_points").argtypes = [handle_t, C.c_int, C.c_int, dp]
     for n in ("set_mesh", "set_geometry", "set_law", "set_controls", "set_bc", "upload", "download", "initialise",
               "new_timestep", "outer_iteration", "evolve", "update_total_fields", "op_grad", "op_correct",
               "op_assemble", "op_amul", "op_solve", "set_points", "interpolate_to_points"):

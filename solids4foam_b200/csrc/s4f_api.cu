@@ -262,6 +262,8 @@ static int field_lookup(s4fgpu_ctx* c, int field, double** p, int* ncomp, int* o
         case S4F_FIELD_DEPSILON_P: *p = c->DEpsP.p; *ncomp = 6; break;
         case S4F_FIELD_EPSILON_P: *p = c->epsP.p; *ncomp = 6; break;
         case S4F_FIELD_RHO: *p = c->rhoF.p; *ncomp = 1; break;
+        case S4F_FIELD_SIGMA_HYD: *p = c->sigmaHyd.p; *ncomp = 1; break;
+        case S4F_FIELD_GRAD_SIGMA_HYD: *p = c->gradP.p; *ncomp = 3; break;
         case S4F_FIELD_DD_B: *p = c->incremental() ? c->D.p : nullptr; *ncomp = 3; *offset = c->bOff(); *count = c->B; break;
         default: c->err = "unknown / unsupported field id"; return 1;
     }
@@ -396,14 +398,15 @@ int s4fgpu_set_points(s4fgpu_handle c, int nPoints, const double* points, const 
     return s4f_build_point_weights(c, points);
 }
 
-int s4fgpu_interpolate_to_points(s4fgpu_handle c, int field, double* pointField) {
+int s4fgpu_interpolate_to_points(s4fgpu_handle c, int field, int mode, double* pointField) {
     S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
     S4F_REQUIRE(c, c->nPoints > 0, "interpolate_to_points: call set_points first");
-    const double* X = nullptr;
-    if (field == S4F_FIELD_D) X = c->incremental() ? c->Dtot.p : c->D.p;
-    else if (field == S4F_FIELD_DD && c->incremental()) X = c->D.p;
+    S4F_REQUIRE(c, mode == S4F_POINT_INTERP_PATCH || mode == S4F_POINT_INTERP_GRAD, "interpolate_to_points: unknown mode");
+    const double* X = nullptr; const double* G = nullptr;
+    if (field == S4F_FIELD_D) { X = c->incremental() ? c->Dtot.p : c->D.p; G = c->incremental() ? c->gradDtot.p : c->gradD.p; }
+    else if (field == S4F_FIELD_DD && c->incremental()) { X = c->D.p; G = c->gradD.p; }
     S4F_REQUIRE(c, X, "interpolate_to_points: field must be D or DD");
-    return s4f_interpolate_to_points(c, X, pointField);
+    return s4f_interpolate_to_points(c, X, mode == S4F_POINT_INTERP_GRAD ? G : nullptr, pointField);
 }
 
 int s4fgpu_update_total_fields(s4fgpu_handle c) {

@@ -175,6 +175,8 @@ struct s4fgpu_ctx {
     DevBuf<int> ptPtr, ptCol;                     // [nPoints+1], [nnzP]
     DevBuf<double> ptW, ptN;                      // [nnzP] normalised inverse-distance weights; [3*nPoints] constraint normal (0 = none)
     DevBuf<double> ptOut;                         // [3*nPoints]
+    DevBuf<int> pgPtr, pgCol;                     // gradient-extrapolated variant: every point from its pointCells
+    DevBuf<double> pgW, pgDelta;                  // [nnz] normalised weights, [3*nnz] point - cell centre
     bool histValid = false;
     int timeIndex = 0;                            // new_timestep() calls = runTime.timeIndex()
     DevBuf<double> gradD, gradDold;               // 9*ld
@@ -191,6 +193,12 @@ struct s4fgpu_ctx {
     // law history
     DevBuf<double> lawF, lawFold, lawJ, lawJold, bEbar, bEbarOld, sigmaY, sigmaYOld, DSigmaY, epsPEq, epsPEqOld,
         DEpsPEq, epsP, epsPOld, DEpsP, DEpsPprev, DLambda, plasticN, epsilon;
+    // ---- pressure smoothing (mechanicalLaw::updateSigmaHyd, solvePressureEqn) ----
+    DevBuf<double> sigmaHyd, pExp, pRatio;        // ld: sigmaHyd, explicit hydrostatic stress, impK/DEqnA
+    DevBuf<double> gradP;                         // 3*ld: grad(sigmaHyd)
+    DevBuf<double> eP;                            // [nEntries] rDAf magSf delta
+    DevBuf<double> pDiag, pRDiag, pX, pB;         // 3*ld each (the scalar system rides the fused 3-component PCG, components 1,2 idle)
+    s4fgpu_stats lastP{};
     // ---- fvMatrix ----
     DevBuf<double> diag0;             // ld: sum of laplacian coefficients + d2dt2
     DevBuf<double> diagC;             // 3*ld: per-component diagonal after addBoundaryDiag
@@ -240,6 +248,7 @@ int s4f_bc_evaluate(s4fgpu_ctx* c);
 int s4f_relax_and_residual(s4fgpu_ctx* c, int iCorr);
 int s4f_grad(s4fgpu_ctx* c);
 int s4f_kinematics(s4fgpu_ctx* c);
+int s4f_pressure_smooth(s4fgpu_ctx* c);              // updateSigmaHyd with the pressure equation; fixes sigma in place
 int s4f_make_m(s4fgpu_ctx* c);                       // lin-geom: M = sigma - gamma grad(D) when no law kernel produced it
 int s4f_update_totals(s4fgpu_ctx* c, bool disp, bool grad);
 int s4f_law_correct(s4fgpu_ctx* c);
@@ -261,5 +270,5 @@ void s4f_amg_destroy(s4fgpu_ctx* c);
 int s4f_amg_info(s4fgpu_ctx* c, int* nLevels, int* sizes, int maxLevels, double* bytesPerApply, double* setupSeconds);
 int s4f_download_upper(s4fgpu_ctx* c, double* hostUpper);           // lduMatrix upper() [F]
 int s4f_build_point_weights(s4fgpu_ctx* c, const double* points);   // vol->point CSR + weights (s4f_setup.cu)
-int s4f_interpolate_to_points(s4fgpu_ctx* c, const double* field3, double* hostOut);
+int s4f_interpolate_to_points(s4fgpu_ctx* c, const double* field3, const double* grad9 /* null: patch mode */, double* hostOut);
 int s4f_grad_calculated(s4fgpu_ctx* c, const double* X, double* gradOut);   // fvc::grad of a field with calculated patches

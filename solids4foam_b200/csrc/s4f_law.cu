@@ -86,13 +86,14 @@ struct S6 { double v[6]; };
 // the boundary slots
 __global__ void __launch_bounds__(S4F_BLOCK) k_law_linear_elastic(const double* __restrict__ gradD, double* __restrict__ sigma, int N,
                                                                   int bOff, int B, int ld, double mu, double K, S6 sigma0,
-                                                                  double* __restrict__ M, double gamma) {
+                                                                  double* __restrict__ M, double gamma, double* __restrict__ pExp) {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N + B; t += gridDim.x * blockDim.x) {
         const int i = field_index(t, N, bOff);
         double g[9], e[6], de[6], s[6];
         ld_soa<9>(gradD, ld, i, g);
         t_symm(g, e);
         const double sh = K * s_tr(e);
+        if (pExp) pExp[i] = sh;
         s_dev(e, de);
 #pragma unroll
         for (int q = 0; q < 6; q++) s[q] = 2.0 * mu * de[q] + sigma0.v[q];
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_law_linear_elastic(const double* 
 __global__ void __launch_bounds__(S4F_BLOCK) k_law_neo_hookean(const double* __restrict__ gradD, double* __restrict__ sigma,
                                                                double* __restrict__ Jout, int N, int bOff, int B, int ld, double mu, double K,
                                                                const double* __restrict__ Fold /* updated Lagrangian only */,
-                                                               double* __restrict__ Fout) {
+                                                               double* __restrict__ Fout, double* __restrict__ pExp) {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N + B; t += gridDim.x * blockDim.x) {
         const int i = field_index(t, N, bOff);
         double g[9], Fm[9], FT[9], FFT[9], b[6], s[6];
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_law_neo_hookean(const double* __r
         for (int q = 0; q < 6; q++) b[q] *= sc;
         s_dev(b, s);
         const double sh = 0.5 * K * (pow(J, 2.0) - 1.0);
+        if (pExp) pExp[i] = sh;
         const double rJ = 1.0 / J;
 #pragma unroll
         for (int q = 0; q < 6; q++) s[q] *= mu;
@@ -186,7 +188,7 @@ struct MisesPtrs {
     const double* gradD; const double* Fold; const double* Jold; const double* bEbarOld;
     const double* sigmaY; const double* epsPEq;
     double* F; double* J; double* bEbar; double* sigma; double* DSigmaY; double* DEpsPEq; double* DEpsP; double* DEpsPprev;
-    double* DLambda; double* plasticN;
+    double* DLambda; double* plasticN; double* pExp;
 };
 __global__ void __launch_bounds__(S4F_BLOCK) k_law_mises(MisesPtrs p, int N, int bOff, int B, int ld, double mu, double K, double Hp,
                                                          int consistent, double relax, HardeningTable T, OuterScalars* S,
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_law_mises(MisesPtrs p, int N, int
         for (int q = 0; q < 6; q++) be[q] = devB[q];
         be[0] += Ib; be[3] += Ib; be[5] += Ib;
         const double sh = 0.5 * K * (pow(J, 2.0) - 1.0);
+        if (p.pExp) p.pExp[i] = sh;
         s[0] += sh; s[3] += sh; s[5] += sh;
         const double rJ = 1.0 / J;
 #pragma unroll
@@ -272,7 +275,7 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_lin_mises_max_eps(const double* _
 struct LinMisesPtrs {
     const double* gradD; const double* epsPOld; const double* sigmaYOld; const double* epsPEqOld;
     double* epsilon; double* sigma; double* sigmaY; double* DSigmaY; double* epsPEq; double* DEpsPEq; double* epsP; double* DEpsP;
-    double* DEpsPprev; double* DLambda; double* plasticN;
+    double* DEpsPprev; double* DLambda; double* plasticN; double* pExp;
 };
 __global__ void __launch_bounds__(S4F_BLOCK) k_law_lin_mises(LinMisesPtrs p, int N, int bOff, int B, int ld, double mu, double K, double Hp,
                                                              HardeningTable T, OuterScalars* S, double* partials, unsigned int* ticket) {
@@ -310,6 +313,7 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_law_lin_mises(LinMisesPtrs p, int
 #pragma unroll
         for (int q = 0; q < 6; q++) { dep[q] = DLambda * pn[q]; ep[q] = epo[q] + dep[q]; s[q] = sT[q] - 2 * mu * dep[q]; }
         const double sh = K * s_tr(eps);
+        if (p.pExp) p.pExp[i] = sh;
         s[0] += sh; s[3] += sh; s[5] += sh;
         st_soa<6>(p.epsilon, ld, i, eps); st_soa<6>(p.sigma, ld, i, s); st_soa<6>(p.epsP, ld, i, ep);
         st_soa<6>(p.DEpsPprev, ld, i, prev); st_soa<6>(p.DEpsP, ld, i, dep); st_soa<6>(p.plasticN, ld, i, pn);
@@ -375,15 +379,21 @@ int s4f_law_correct(s4fgpu_ctx* c) {
     const s4fgpu_law& L = c->law;
     const int UL = c->UL() ? 1 : 0;
     const double* gD = UL ? c->gradD.p : c->gradForLaw();        // UL laws read grad(DD) (mechanicalLaw.C:1064-1072)
+    if (L.solvePressureEqn && c->pExp.n != (size_t)ld) {
+        S4F_CHECK_CUDA(c, c->pExp.alloc(ld)); S4F_CHECK_CUDA(c, c->sigmaHyd.alloc(ld)); S4F_CHECK_CUDA(c, c->pRatio.alloc(ld));
+        S4F_CHECK_CUDA(c, c->gradP.alloc(3 * (size_t)ld)); S4F_CHECK_CUDA(c, c->eP.alloc((size_t)c->nEntries));
+        for (DevBuf<double>* b : {&c->pDiag, &c->pRDiag, &c->pX, &c->pB}) S4F_CHECK_CUDA(c, b->alloc(3 * (size_t)ld));
+    }
+    double* pE = L.solvePressureEqn ? c->pExp.p : nullptr;
     if (L.kind == S4F_LAW_LINEAR_ELASTIC) {
         S6 s0; for (int q = 0; q < 6; q++) s0.v[q] = L.sigma0[q];
-        const bool emitM = c->fastRhs() && c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP;
-        k_law_linear_elastic<<<grid, S4F_BLOCK, 0, c->stream>>>(gD, c->sigma.p, N, bOff, B, ld, L.mu, L.K, s0, emitM ? c->T9.p : nullptr, c->gamma0());
+        const bool emitM = c->fastRhs() && c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP && !L.solvePressureEqn;
+        k_law_linear_elastic<<<grid, S4F_BLOCK, 0, c->stream>>>(gD, c->sigma.p, N, bOff, B, ld, L.mu, L.K, s0, emitM ? c->T9.p : nullptr, c->gamma0(), pE);
         c->launches++;
         if (emitM) { c->mValid = true; S4F_CHECK_CUDA(c, cudaGetLastError()); return s4f_halo_exchange(c, c->T9.p, 9); }
     } else if (L.kind == S4F_LAW_NEO_HOOKEAN_ELASTIC) {
         k_law_neo_hookean<<<grid, S4F_BLOCK, 0, c->stream>>>(gD, c->sigma.p, c->lawJ.p, N, bOff, B, ld, L.mu, L.K, UL ? c->lawFold.p : nullptr,
-                                                            c->lawF.p);
+                                                            c->lawF.p, pE);
         c->launches++;
     } else if (L.kind == S4F_LAW_NEO_HOOKEAN_MISES_PLASTIC) {
         HardeningTable T = make_table(L);
@@ -393,7 +403,7 @@ int s4f_law_correct(s4fgpu_ctx* c) {
             if (c->nRanks > 1) S4F_CHECK_NCCL(c, ncclAllReduce(&((OuterScalars*)c->outS.p)->maxMagBE, &((OuterScalars*)c->outS.p)->maxMagBE, 1, ncclDouble, ncclMax, c->comm, c->stream));
         }
         MisesPtrs p{gD, c->lawFold.p, c->lawJold.p, c->bEbarOld.p, c->sigmaY.p, c->epsPEq.p, c->lawF.p, c->lawJ.p, c->bEbar.p, c->sigma.p,
-                    c->DSigmaY.p, c->DEpsPEq.p, c->DEpsP.p, c->DEpsPprev.p, c->DLambda.p, c->plasticN.p};
+                    c->DSigmaY.p, c->DEpsPEq.p, c->DEpsP.p, c->DEpsPprev.p, c->DLambda.p, c->plasticN.p, pE};
         k_law_mises<<<grid, S4F_BLOCK, 0, c->stream>>>(p, N, bOff, B, ld, L.mu, L.K, c->Hp, L.updateBEbarConsistent, L.DEpsilonPRelax, T, c->outS.p,
                                                       c->partials.p, c->ticket.p, UL);
         c->launches++;
@@ -406,7 +416,7 @@ int s4f_law_correct(s4fgpu_ctx* c) {
             if (c->nRanks > 1) S4F_CHECK_NCCL(c, ncclAllReduce(&((OuterScalars*)c->outS.p)->maxMagBE, &((OuterScalars*)c->outS.p)->maxMagBE, 1, ncclDouble, ncclMax, c->comm, c->stream));
         }
         LinMisesPtrs p{gD, c->epsPOld.p, c->sigmaYOld.p, c->epsPEqOld.p, c->epsilon.p, c->sigma.p, c->sigmaY.p, c->DSigmaY.p, c->epsPEq.p,
-                       c->DEpsPEq.p, c->epsP.p, c->DEpsP.p, c->DEpsPprev.p, c->DLambda.p, c->plasticN.p};
+                       c->DEpsPEq.p, c->epsP.p, c->DEpsP.p, c->DEpsPprev.p, c->DLambda.p, c->plasticN.p, pE};
         k_law_lin_mises<<<grid, S4F_BLOCK, 0, c->stream>>>(p, N, bOff, B, ld, L.mu, L.K, c->Hp, T, c->outS.p, c->partials.p, c->ticket.p);
         c->launches++;
         if (c->nRanks > 1) S4F_CHECK_NCCL(c, ncclAllReduce(&((OuterScalars*)c->outS.p)->matNum, &((OuterScalars*)c->outS.p)->matNum, 2, ncclDouble, ncclMax, c->comm, c->stream));
@@ -414,6 +424,7 @@ int s4f_law_correct(s4fgpu_ctx* c) {
         c->err = "unknown mechanical law"; return 1;
     }
     S4F_CHECK_CUDA(c, cudaGetLastError());
+    if (L.solvePressureEqn) { int rp = s4f_pressure_smooth(c); if (rp) return rp; }
     if (c->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP) {
         // UL: relF = I + gradDD.T() takes the place of F: fvc::div(relJ*relFinv & sigma), nonLinGeomUpdatedLagSolid.C:188
         k_tl_flux_tensor<<<grid, S4F_BLOCK, 0, c->stream>>>(gD, c->sigma.p, c->T9.p, c->Finv.p, c->Jt.p, N, bOff, B, ld,

@@ -347,6 +347,22 @@ __global__ void k_vol_to_point(const int* __restrict__ ptPtr, const int* __restr
     const double na = n[0] * a[0] + n[1] * a[1] + n[2] * a[2];
     out[3 * (size_t)p] = a[0] - n[0] * na; out[3 * (size_t)p + 1] = a[1] - n[1] * na; out[3 * (size_t)p + 2] = a[2] - n[2] * na;
 }
+// interpolate(vf, gradVf, pf), enhancedVolPointInterpolate.C:351-418: pf = sum w (vf + delta & gradVf), w normalised
+__global__ void k_vol_to_point_grad(const int* __restrict__ ptr, const int* __restrict__ colc, const double* __restrict__ w,
+                                    const double* __restrict__ delta, const double* __restrict__ X, const double* __restrict__ G,
+                                    double* __restrict__ out, int nPoints, int ld, long long nnz) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nPoints) return;
+    double a[3] = {0, 0, 0};
+    for (int j = ptr[p]; j < ptr[p + 1]; j++) {
+        const int s = colc[j];
+        const double wj = w[j], d0 = delta[j], d1 = delta[nnz + j], d2 = delta[2 * nnz + j];
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+            a[q] += wj * (X[(size_t)q * ld + s] + d0 * G[(size_t)q * ld + s] + d1 * G[(size_t)(3 + q) * ld + s] + d2 * G[(size_t)(6 + q) * ld + s]);
+    }
+    out[3 * (size_t)p] = a[0]; out[3 * (size_t)p + 1] = a[1]; out[3 * (size_t)p + 2] = a[2];
+}
 }  // namespace
 
 int s4f_build_point_weights(s4fgpu_ctx* c, const double* points) {
@@ -376,6 +392,29 @@ int s4f_build_point_weights(s4fgpu_ctx* c, const double* points) {
                 for (int j = c->hFvPtr[F + b]; j < c->hFvPtr[F + b + 1]; j++) for (int q = 0; q < 3; q++) hN[3 * (size_t)c->hFv[j] + q] = n[q] / m;
             }
         }
+    }
+    {   // gradient-extrapolated variant: all points from their pointCells
+        std::vector<int> gptr(1, 0), gcol; std::vector<double> gw, gd[3];
+        for (int p = 0; p < nP; p++) {
+            const double* x = &points[3 * (size_t)p];
+            std::sort(pc[p].begin(), pc[p].end());
+            const size_t s0 = gw.size();
+            double sw = 0;
+            for (int cell : pc[p]) {
+                const double* cc = &c->hC[3 * (size_t)cell];
+                const double d[3] = {x[0] - cc[0], x[1] - cc[1], x[2] - cc[2]};
+                const double m = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                gcol.push_back(cell); gw.push_back(1.0 / m); sw += 1.0 / m;
+                for (int q = 0; q < 3; q++) gd[q].push_back(d[q]);
+            }
+            for (size_t j = s0; j < gw.size(); j++) gw[j] /= sw;
+            gptr.push_back((int)gw.size());
+        }
+        std::vector<double> gdel; gdel.reserve(3 * gw.size());
+        for (int q = 0; q < 3; q++) gdel.insert(gdel.end(), gd[q].begin(), gd[q].end());
+        if (gcol.empty()) { gcol.push_back(0); gw.push_back(0.0); gdel.assign(3, 0.0); }
+        S4F_CHECK_CUDA(c, c->pgPtr.upload(gptr)); S4F_CHECK_CUDA(c, c->pgCol.upload(gcol)); S4F_CHECK_CUDA(c, c->pgW.upload(gw));
+        S4F_CHECK_CUDA(c, c->pgDelta.upload(gdel));
     }
     std::vector<int> ptr(1, 0), col; std::vector<double> w;
     for (int p = 0; p < nP; p++) {
@@ -407,9 +446,10 @@ int s4f_build_point_weights(s4fgpu_ctx* c, const double* points) {
     return 0;
 }
 
-int s4f_interpolate_to_points(s4fgpu_ctx* c, const double* X, double* hostOut) {
+int s4f_interpolate_to_points(s4fgpu_ctx* c, const double* X, const double* G, double* hostOut) {
     const int nP = c->nPoints;
-    k_vol_to_point<<<(nP + 127) / 128, 128, 0, c->stream>>>(c->ptPtr.p, c->ptCol.p, c->ptW.p, c->ptN.p, X, c->ptOut.p, nP, c->ld);
+    if (G) k_vol_to_point_grad<<<(nP + 127) / 128, 128, 0, c->stream>>>(c->pgPtr.p, c->pgCol.p, c->pgW.p, c->pgDelta.p, X, G, c->ptOut.p, nP, c->ld, (long long)c->pgW.n);
+    else k_vol_to_point<<<(nP + 127) / 128, 128, 0, c->stream>>>(c->ptPtr.p, c->ptCol.p, c->ptW.p, c->ptN.p, X, c->ptOut.p, nP, c->ld);
     c->launches++;
     S4F_CHECK_CUDA(c, cudaGetLastError());
     S4F_CHECK_CUDA(c, cudaMemcpyAsync(hostOut, c->ptOut.p, 3 * (size_t)nP * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

@@ -119,14 +119,17 @@ class SolidModel:
         self._check(self.L.s4fgpu_evolve(self.h, C.byref(st)))
         return st.as_dict()
 
-    def interpolate_to_points(self, name: str = "D") -> np.ndarray:
-        """mechanicalModel::interpolate(D, pointD) (mechanicalModel.C:786-826): vol -> point interpolation on the device."""
+    def interpolate_to_points(self, name: str = "D", with_gradient: bool = False) -> np.ndarray:
+        """mechanicalModel::interpolate(D, pointD) (mechanicalModel.C:786-826) or, ``with_gradient``, interpolate(D, gradD,
+        pointD) (:829-877): vol -> point interpolation on the device."""
         out = np.empty((self.case.mesh.points.shape[0], 3))
-        self._check(self.L.s4fgpu_interpolate_to_points(self.h, K.FIELD[name], K._dptr(out)))
+        mode = K.POINT_INTERP_GRAD if with_gradient else K.POINT_INTERP_PATCH
+        self._check(self.L.s4fgpu_interpolate_to_points(self.h, K.FIELD[name], mode, K._dptr(out)))
         return out
 
     def pointD(self) -> np.ndarray:
-        return self.interpolate_to_points("D")
+        """pointD as the solid models update it after the loop, e.g. linGeomTotalDispSolid.C:212."""
+        return self.interpolate_to_points("D", with_gradient=True)
 
     def movingMesh(self) -> bool:
         """solidModel::movingMesh(): the updated-Lagrangian model moves the mesh at the end of every step."""

@@ -428,6 +428,12 @@ def test_vol_to_point_interpolation_matches_oracle():
     assert np.abs(pg - po).max() < 1e-15 + 1e-13 * np.abs(po).max()
     sym = np.abs(mesh.points[:, 2] - mesh.points[:, 2].max()) < 1e-12
     assert sym.any() and np.abs(pg[sym, 2]).max() < 1e-18
+    # interpolate(DD, gradDD, pointDD) (enhancedVolPointInterpolate.C:351-418), the variant the solid models call after the loop
+    gD = 1e-2 * rng.standard_normal((mesh.nCells, 9))
+    for s in (g, o):
+        s.set("gradDD", gD)
+    pg, po = g.interpolate_to_points("DD", with_gradient=True), o.interpolate_to_points("DD", with_gradient=True)
+    assert np.abs(pg - po).max() < 1e-15 + 1e-13 * np.abs(po).max()
 
 
 def test_updated_lagrangian_load_steps_match_oracle():
@@ -500,3 +506,37 @@ def test_beam_in_cross_flow_updated_lagrangian_backward_matches_oracle():
         g.updateTotalFields(); o.update_total_fields()
         assert np.abs(g.pointDD - o.pointDD).max() < SOLVE_TOL * np.abs(o.pointDD).max()
     assert o.get("D")[:, 0].max() > 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# pressure smoothing: mechanicalLaw::updateSigmaHyd with solvePressureEqn
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("law,model,case_kw", [
+    ("linearElastic", K.MODEL_LIN_GEOM_TOTAL_DISP, dict()),
+    ("linearElastic", K.MODEL_LIN_GEOM_TOTAL_DISP, dict(gradScheme=K.GRAD_GAUSS_LINEAR)),
+    ("neoHookeanElastic", K.MODEL_NONLIN_TL_TOTAL_DISP, dict(traction=(0.0, -4e8, 0.0))),
+])
+def test_pressure_smoothing_matches_oracle(law, model, case_kw):
+    """The pressure equation of mechanicalLaw.C:1374-1468 assembled and solved on the device (k_p_assemble, fused PCG,
+    k_grad_scalar) against the oracle's LDU restatement: converged D, sigma, sigmaHyd and grad(sigmaHyd)."""
+    from oracle.binding import OracleSolid
+    from solids4foam_b200.solid_model import SolidModel
+    kw = dict(nx=10, ny=5, nz=5, L=2.0, solidModel=model, nCorrectors=20000, fieldRelaxD=0.9, **TIGHT)
+    kw.update(case_kw)
+    pair = []
+    for pre in (K.PRECOND_GAMG, K.PRECOND_DIC):
+        c = cases.cantilever(preconditioner=pre, **kw)
+        c.law = K.mechanical_law(law, rho=7800.0, E=200e9, nu=0.3, solvePressureEqn=True, pressureSmoothingScaleFactor=100.0)
+        pair.append(c)
+    g, o = SolidModel(pair[0]), OracleSolid(pair[1])
+    sg, so = g.evolve(), o.evolve()
+    assert sg["converged"] and so["converged"], (sg, so)
+    assert rel_l2(g.get("D"), o.get("D")) < SOLVE_TOL
+    assert rel_l2(g.get("sigma"), o.get("sigma")) < SOLVE_TOL
+    assert rel_l2(g.get("sigmaHyd"), o.get("sigmaHyd")) < SOLVE_TOL
+    assert rel_l2(g.get("gradSigmaHyd"), o.get("gradSigmaHyd")) < 10 * SOLVE_TOL
+    # the smoothing is active: the solved hydrostatic stress differs from the explicit one
+    p = pair[1]
+    p.law.solvePressureEqn = 0
+    o2 = OracleSolid(p); o2.evolve()
+    assert rel_l2(o.get("sigma"), o2.get("sigma")) > 1e-3

@@ -57,6 +57,25 @@ def test_vol_to_point_interpolation_of_a_linear_field():
     assert np.allclose(pD[e], lin(m.points[e] + np.array([0.0, h / 4, h / 4])), atol=1e-14)
 
 
+def test_gradient_extrapolated_vol_to_point_interpolation_is_exact_for_linear_fields():
+    """interpolate(vf, gradVf, pf) (enhancedVolPointInterpolate.C:351-418): every donor is extrapolated to the point with its
+    own gradient, so a linear field is reproduced at ALL points, one-sided boundary points included, on a distorted mesh."""
+    case = cases.patch_test(n=5)
+    if case.mesh.points is None:
+        case = cases.neo_hookean_cantilever(6, 4, 4, general=True, solidModel=K.MODEL_NONLIN_TL_TOTAL_DISP, L=3.0, H=2.0, W=2.0)
+    o = OracleSolid(case)
+    m = case.mesh
+    G = np.array([[0.01, 0.02, -0.01], [0.0, 0.03, 0.01], [0.02, -0.01, 0.005]])
+    if m.solutionD[2] == 0:
+        G[2, :] = 0; G[:, 2] = 0
+    lin = lambda X: 0.1 + X @ G.T
+    F = m.nInternalFaces
+    o.set("D", lin(m.C)); o.set("D_b", lin(m.Cf[F:]))
+    o.set("gradD", np.tile(G.T.reshape(1, 9), (m.nCells, 1)))       # gradD_ij = d_i D_j
+    pD = o.interpolate_to_points("D", with_gradient=True)
+    assert np.abs(pD - lin(m.points)).max() < 1e-15 + 1e-13 * np.abs(pD).max()
+
+
 def test_homogeneous_deformation_in_two_updated_lagrangian_steps():
     """A prescribed affine motion x = A X in two increments: the first increment is exact (least-squares gradient, Gauss
     divergence of a constant flux tensor and the Rhie-Chow term all vanish identically for a linear field), F = A1; the
@@ -169,3 +188,54 @@ def test_beam_in_cross_flow_solid_side_runs_and_conserves_mass():
     assert np.abs(pD[sym, 2]).max() < 1e-15                                          # points stay in the symmetry plane
     assert np.abs(c.mesh.points[sym, 2] - 0.2).max() < 1e-12
     assert abs((c.mesh.V * o.get("rho")).sum() / m0 - 1) < 1e-3                       # rho V = rho0 V0 up to the vol->point error
+
+
+# ---------------------------------------------------------------------------------------------
+# pressure smoothing: mechanicalLaw::updateSigmaHyd with solvePressureEqn
+# ---------------------------------------------------------------------------------------------
+def _beam_with_pressure_eqn(n, solve, law="linearElastic", model=K.MODEL_LIN_GEOM_TOTAL_DISP, **kw):
+    tight = dict(solutionTolerance=1e-9, alternativeTolerance=1e-9, tolerance=1e-13, relTol=1e-3, nCorrectors=20000,
+                 preconditioner=K.PRECOND_DIC, solidModel=model)
+    tight.update(kw)
+    c = cases.cantilever(2 * n, n, n, L=2.0, **tight)
+    if law == "linearElastic":
+        c.law = K.mechanical_law(law, rho=7800.0, E=200e9, nu=0.3, solvePressureEqn=solve)
+    else:
+        c.law = K.mechanical_law(law, rho=7800.0, E=200e9, nu=0.3, solvePressureEqn=solve)
+    return c
+
+
+def test_pressure_equation_is_a_consistent_smoothing():
+    """mechanicalLaw.C:1442-1453: 'the fvm and fvc laplacian terms cancel at convergence and the laplacian - div(grad) term
+    produce a smoothing/diffusion': the converged fields with and without solvePressureEqn differ by a term that vanishes
+    under mesh refinement, tr(sigma)/3 is the solved sigmaHyd, and the hydrostatic stress field is smoother."""
+    diff = {}
+    for n in (4, 8):
+        res = {}
+        for solve in (False, True):
+            o = OracleSolid(_beam_with_pressure_eqn(n, solve))
+            st = o.evolve()
+            assert st["converged"]
+            res[solve] = o
+        sa, sb = res[False].get("sigma"), res[True].get("sigma")
+        tr = lambda s: (s[:, 0] + s[:, 3] + s[:, 5]) / 3.0
+        assert np.allclose(tr(sb), res[True].get("sigmaHyd"), rtol=0, atol=1e-9 * np.abs(sb).max())
+        rough = lambda s: np.std(np.diff(tr(s).reshape(n, n, 2 * n), axis=2))
+        assert rough(sb) < rough(sa)
+        diff[n] = rel_l2(res[True].get("D"), res[False].get("D"))
+    assert diff[8] < 0.25 * diff[4] and diff[8] < 0.05, diff
+
+
+def test_pressure_equation_with_zero_scale_factor_returns_the_explicit_cell_values():
+    """pressureSmoothingScaleFactor 0: rDAf = 0 and the equation degenerates to sigmaHyd = sigmaHydExplicit = K tr(epsilon) in
+    the cells (linearElastic.C:337); the patch values are zeroGradient (mechanicalLaw.C:452-458), not K tr(epsilon_b)."""
+    c = _beam_with_pressure_eqn(4, True)
+    c.law.pressureSmoothingScaleFactor = 0.0
+    o = OracleSolid(c)
+    assert o.evolve()["converged"]
+    g = o.get("gradD")
+    tr_eps = g[:, 0] + g[:, 4] + g[:, 8]
+    assert np.allclose(o.get("sigmaHyd"), c.law.K * tr_eps, rtol=1e-8, atol=1e-9 * np.abs(c.law.K * tr_eps).max())
+    sb = o.get("sigma_b")
+    trb = (sb[:, 0] + sb[:, 3] + sb[:, 5]) / 3.0
+    assert np.allclose(trb, o.get("sigmaHyd")[c.mesh.faceCells], rtol=1e-9, atol=1e-9 * np.abs(trb).max())
