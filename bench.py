@@ -47,8 +47,8 @@ def parse():
     ap.add_argument("--cells", default=None, help="nx,ny,nz (default 800,100,100)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precond", default="gamg", choices=["diagonal", "none", "chebyshev", "gamg", "gamg32"])
-    ap.add_argument("--gamg-degree", type=int, default=2)
-    ap.add_argument("--gamg-omega", type=float, default=1.8)
+    ap.add_argument("--gamg-degree", type=int, default=3)
+    ap.add_argument("--gamg-omega", type=float, default=2.2)
     ap.add_argument("--gamg-cycle", type=int, default=0)
     return ap.parse_args()
 

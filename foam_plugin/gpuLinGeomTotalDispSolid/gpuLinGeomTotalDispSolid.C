@@ -173,8 +173,8 @@ void gpuLinGeomTotalDispSolid::mirrorLawAndControls()
     const word pre(gpuDict.lookupOrDefault<word>("preconditioner", "GAMG"));
     c.preconditioner = (pre == "diagonal") ? S4F_PRECOND_DIAGONAL : (pre == "none") ? S4F_PRECOND_NONE : S4F_PRECOND_GAMG;
     c.gamgSinglePrecision = gpuDict.lookupOrDefault<Switch>("gamgSinglePrecision", false);
-    c.gamgOverCorrection = gpuDict.lookupOrDefault<scalar>("gamgOverCorrection", 1.8);
-    c.gamgSmootherDegree = gpuDict.lookupOrDefault<label>("gamgSmootherDegree", 2);
+    c.gamgOverCorrection = gpuDict.lookupOrDefault<scalar>("gamgOverCorrection", 2.2);
+    c.gamgSmootherDegree = gpuDict.lookupOrDefault<label>("gamgSmootherDegree", 3);
     c.tolerance = sol.lookupOrDefault<scalar>("tolerance", 1e-6);
     c.relTol = sol.lookupOrDefault<scalar>("relTol", 0);
     c.maxIter = sol.lookupOrDefault<label>("maxIter", 1000);

@@ -151,8 +151,8 @@ typedef struct {
     int chebyshevDegree;   /* S4F_PRECOND_CHEBYSHEV only */
     int checkEvery;        /* host polls the device-side convergence flags every n PCG iterations */
     int gamgSinglePrecision;   /* S4F_PRECOND_GAMG: 1 = V-cycle in fp32 (PCG itself stays fp64), 0 = fp64 */
-    double gamgOverCorrection; /* S4F_PRECOND_GAMG: fixed scaling of the coarse-grid correction (<= 0: 1.8) */
-    int gamgSmootherDegree;    /* S4F_PRECOND_GAMG: Chebyshev-Jacobi degree of the pre- and post-smoother (<= 0: 2) */
+    double gamgOverCorrection; /* S4F_PRECOND_GAMG: fixed scaling of the coarse-grid correction (<= 0: 2.2) */
+    int gamgSmootherDegree;    /* S4F_PRECOND_GAMG: Chebyshev-Jacobi degree of the pre- and post-smoother (<= 0: 3) */
     int gamgCycle;             /* S4F_PRECOND_GAMG: 0 = V-cycle, 1 = W-cycle */
 } s4fgpu_controls;
 

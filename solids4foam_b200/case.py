@@ -115,8 +115,8 @@ def default_controls(**kw) -> Controls:
     c.chebyshevDegree = 4
     c.checkEvery = 4
     c.gamgSinglePrecision = 0
-    c.gamgOverCorrection = 1.8
-    c.gamgSmootherDegree = 2
+    c.gamgOverCorrection = 2.2
+    c.gamgSmootherDegree = 3
     c.gamgCycle = 0
     for k, v in kw.items():
         if k == "g":

@@ -339,7 +339,7 @@ struct Hierarchy : S4fAmg {
     std::vector<std::unique_ptr<Level<T>>> lv;
     DevBuf<T> denseInv;                 // 3 * nC * nC
     int deg = 2, cycle = 0;
-    double omega = 1.8;
+    double omega = 2.2;
     double theta = 0, delta = 0;
     // multi-rank: level 0 is this rank's part of the mesh (ghost columns, halo exchange per SpMV); levels >= 1
     // are the GLOBAL coarse levels, replicated on every rank and fed by an all-gather of the restricted residual
@@ -573,9 +573,9 @@ int build(s4fgpu_ctx* c, std::vector<HostLevel>& H, const DistInfo& di) {
         S4F_CHECK_CUDA(c, A->grecv.alloc(3 * (size_t)std::max(di.maxLoc, 1) * c->nRanks));
         S4F_CHECK_CUDA(c, A->rankOff.upload(di.off)); S4F_CHECK_CUDA(c, A->rankCnt.upload(di.cnt));
     }
-    A->deg = c->ctl.gamgSmootherDegree > 0 ? c->ctl.gamgSmootherDegree : 2;
+    A->deg = c->ctl.gamgSmootherDegree > 0 ? c->ctl.gamgSmootherDegree : 3;
     A->cycle = c->ctl.gamgCycle;
-    A->omega = c->ctl.gamgOverCorrection > 0 ? c->ctl.gamgOverCorrection : 1.8;
+    A->omega = c->ctl.gamgOverCorrection > 0 ? c->ctl.gamgOverCorrection : 2.2;
     const double lmax = 2.0, lmin = 0.3 * lmax;      // Gershgorin bound of D^-1 A for the M-matrices of every level
     A->theta = 0.5 * (lmax + lmin); A->delta = 0.5 * (lmax - lmin);
     for (size_t l = 0; l < H.size(); l++) {

@@ -374,9 +374,9 @@ __global__ void __launch_bounds__(S4F_BLOCK, 3) k_source_m(
             for (int k = 0; k < G; k++) {
                 const bool ok = k0 + k < width;
                 const long long e = (long long)base + 32 * (ok ? k0 + k : k0) + lane;
-                cc[k] = col[e];
-                u0[k] = ok ? eU[e] : 0.0; u1[k] = ok ? eU1[e] : 0.0; u2[k] = ok ? eU2[e] : 0.0;
-                c0[k] = ok ? eC0[e] : 0.0;
+                cc[k] = __ldcs(col + e);            // streamed once: evict-first, keep L2 for the gathered M / D lines
+                u0[k] = ok ? __ldcs(eU + e) : 0.0; u1[k] = ok ? __ldcs(eU1 + e) : 0.0; u2[k] = ok ? __ldcs(eU2 + e) : 0.0;
+                c0[k] = ok ? __ldcs(eC0 + e) : 0.0;
             }
             double m[G][9], d[G][3];
 #pragma unroll
