@@ -164,10 +164,12 @@ struct Cheb { double c1, c2; };
 // x = d = (1/theta) rD b      (first smoothing step from a zero initial guess)
 template <class T, class TB>
 __global__ void __launch_bounds__(S4F_BLOCK) k_amg_first(const T* __restrict__ rD, const TB* __restrict__ b, T* __restrict__ x,
-                                                         T* __restrict__ d, int n, int ld, int ldb, T invTheta) {
+                                                         T* __restrict__ d, int n, int ld, int ldb, T invTheta, const int* __restrict__ act) {
+    const int a[3] = {act[0], act[1], act[2]};      // components whose PCG solve is still running (device-side flags)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 #pragma unroll
         for (int q = 0; q < 3; q++) {
+            if (!a[q]) continue;
             const T v = invTheta * rD[(size_t)q * ld + i] * (T)b[(size_t)q * ldb + i];
             x[(size_t)q * ld + i] = v; d[(size_t)q * ld + i] = v;
         }
@@ -183,7 +185,10 @@ template <class T, class TB, class TO, int MODE>
 __global__ void __launch_bounds__(S4F_AMG_BLOCK, 4) k_amg_step(const int* __restrict__ slicePtr, const int* __restrict__ col,
                                                                const T* __restrict__ a, const T* __restrict__ dg, const T* __restrict__ rD,
                                                                const TB* __restrict__ b, const T* __restrict__ x, T* __restrict__ d,
-                                                               TO* __restrict__ xo, int n, int ld, int ldb, int ldo, int nSlices, T c1, T c2) {
+                                                               TO* __restrict__ xo, int n, int ld, int ldb, int ldo, int nSlices, T c1, T c2,
+                                                               const int* __restrict__ act) {
+    // a converged component of the fused PCG skips its vector traffic; the matrix stream is shared by the others
+    const bool a0 = act[0] != 0, a1 = act[1] != 0, a2 = act[2] != 0;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nWarps = (gridDim.x * blockDim.x) >> 5;
@@ -201,12 +206,18 @@ __global__ void __launch_bounds__(S4F_AMG_BLOCK, 4) k_amg_step(const int* __rest
                 e[k] = ok ? a[idx] : (T)0;
             }
 #pragma unroll
-            for (int k = 0; k < 8; k++) { s0 += e[k] * x[cc[k]]; s1 += e[k] * x[cc[k] + ld]; s2 += e[k] * x[cc[k] + 2 * ld]; }
+            for (int k = 0; k < 8; k++) {
+                if (a0) s0 += e[k] * x[cc[k]];
+                if (a1) s1 += e[k] * x[cc[k] + ld];
+                if (a2) s2 += e[k] * x[cc[k] + 2 * ld];
+            }
         }
         if (row < n) {
             const T acc[3] = {s0, s1, s2};
+            const bool aq[3] = {a0, a1, a2};
 #pragma unroll
             for (int q = 0; q < 3; q++) {
+                if (!aq[q]) continue;
                 const int j = q * ld + row;
                 const T xv = x[j];
                 const T r = (T)b[(size_t)q * ldb + row] - (dg[j] * xv - acc[q]);
@@ -224,13 +235,16 @@ __global__ void __launch_bounds__(S4F_AMG_BLOCK, 4) k_amg_step(const int* __rest
 // b_c[I] = sum over the children of I of t[child]
 template <class T>
 __global__ void k_amg_restrict(const int* __restrict__ childPtr, const int* __restrict__ child, const T* __restrict__ t,
-                               T* __restrict__ bc, int nc, int ld, int ldc) {
+                               T* __restrict__ bc, int nc, int ld, int ldc, const int* __restrict__ act) {
     const int I = blockIdx.x * blockDim.x + threadIdx.x;
     if (I >= nc) return;
+    const bool a0 = act[0] != 0, a1 = act[1] != 0, a2 = act[2] != 0;
     T s0 = 0, s1 = 0, s2 = 0;
     for (int e = childPtr[I]; e < childPtr[I + 1]; e++) {
         const int i = child[e];
-        s0 += t[i]; s1 += t[(size_t)ld + i]; s2 += t[2 * (size_t)ld + i];
+        if (a0) s0 += t[i];
+        if (a1) s1 += t[(size_t)ld + i];
+        if (a2) s2 += t[2 * (size_t)ld + i];
     }
     bc[I] = s0; bc[(size_t)ldc + I] = s1; bc[2 * (size_t)ldc + I] = s2;
 }
@@ -238,11 +252,12 @@ __global__ void k_amg_restrict(const int* __restrict__ childPtr, const int* __re
 // x[i] += omega * e[parent[i]]
 template <class T>
 __global__ void __launch_bounds__(S4F_BLOCK) k_amg_prolong(const int* __restrict__ parent, const T* __restrict__ e, T* __restrict__ x,
-                                                           int n, int ld, int ldc, T omega) {
+                                                           int n, int ld, int ldc, T omega, const int* __restrict__ act) {
+    const int a[3] = {act[0], act[1], act[2]};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int I = parent[i];
 #pragma unroll
-        for (int q = 0; q < 3; q++) x[(size_t)q * ld + i] += omega * e[(size_t)q * ldc + I];
+        for (int q = 0; q < 3; q++) if (a[q]) x[(size_t)q * ld + i] += omega * e[(size_t)q * ldc + I];
     }
 }
 
@@ -324,8 +339,8 @@ struct Level {
 
 struct S4fAmg {
     virtual ~S4fAmg() {}
-    virtual int apply(s4fgpu_ctx* c, const double* r3, double* z3) = 0;
-    virtual int step0(s4fgpu_ctx* c, const double* r3) = 0;   // one fine-level smoothing step alone (timing)
+    virtual int apply(s4fgpu_ctx* c, const double* r3, double* z3, const int* act) = 0;
+    virtual int step0(s4fgpu_ctx* c, const double* r3, const int* act) = 0;   // one fine-level smoothing step alone (timing)
     double step0Bytes = 0;
     std::vector<int> sizes;
     double bytesPerApply = 0;
@@ -339,6 +354,7 @@ struct Hierarchy : S4fAmg {
     std::vector<std::unique_ptr<Level<T>>> lv;
     DevBuf<T> denseInv;                 // 3 * nC * nC
     int deg = 2, cycle = 0;
+    const int* act = nullptr;           // device int[3]: components to work on (the fused PCG's active flags, or all ones)
     double omega = 2.2;
     double theta = 0, delta = 0;
     // multi-rank: level 0 is this rank's part of the mesh (ghost columns, halo exchange per SpMV); levels >= 1
@@ -453,7 +469,7 @@ struct Hierarchy : S4fAmg {
         const int grid = step_grid(c, L);
         if (dist && &L == lv[0].get()) halo0(c, const_cast<T*>(xin));
         k_amg_step<T, TB, TO, 0><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, L.rD.p, b, xin, L.d.p, xout, L.n, L.ld, ldb, ldo,
-                                                                     L.nSlices, (T)c1, (T)c2);
+                                                                     L.nSlices, (T)c1, (T)c2, act);
         c->launches++;
     }
     // Chebyshev-Jacobi of degree `deg`; fromZero: x0 = 0.  Result ends in *xres (L.x or L.x2), or, when
@@ -466,7 +482,7 @@ struct Hierarchy : S4fAmg {
         int k0 = 0;
         if (fromZero) {
             const int grid = s4f_grid(c->numSMs, L.n);
-            k_amg_first<T, TB><<<grid, S4F_BLOCK, 0, c->stream>>>(L.rD.p, b, xcur, L.d.p, L.n, L.ld, ldb, (T)(1.0 / theta));
+            k_amg_first<T, TB><<<grid, S4F_BLOCK, 0, c->stream>>>(L.rD.p, b, xcur, L.d.p, L.n, L.ld, ldb, (T)(1.0 / theta), act);
             c->launches++;
             k0 = 1;
         }
@@ -491,15 +507,15 @@ struct Hierarchy : S4fAmg {
         const bool d0 = dist && l == 0;
         if (d0) { int rc = halo0(c, x); if (rc) return rc; }
         k_amg_step<T, TB, T, 1><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, L.rD.p, b, x, L.d.p, L.t.p, L.n, L.ld, ldb, L.ld,
-                                                                       L.nSlices, (T)0, (T)0);
+                                                                       L.nSlices, (T)0, (T)0, act);
         c->launches++;
         if (!d0) {
-            k_amg_restrict<T><<<(C.n + 127) / 128, 128, 0, c->stream>>>(C.childPtr.p, C.child.p, L.t.p, C.b.p, C.n, L.ld, C.ld);
+            k_amg_restrict<T><<<(C.n + 127) / 128, 128, 0, c->stream>>>(C.childPtr.p, C.child.p, L.t.p, C.b.p, C.n, L.ld, C.ld, act);
             c->launches++;
             return 0;
         }
         // this rank's aggregates -> packed [3][maxLoc]; all-gather over NVLink; scatter into the replicated vector
-        k_amg_restrict<T><<<(n1Local + 127) / 128, 128, 0, c->stream>>>(C.childPtr.p, C.child.p, L.t.p, gsend.p, n1Local, L.ld, maxLoc);
+        k_amg_restrict<T><<<(n1Local + 127) / 128, 128, 0, c->stream>>>(C.childPtr.p, C.child.p, L.t.p, gsend.p, n1Local, L.ld, maxLoc, act);
         S4F_CHECK_NCCL(c, ncclAllGather(gsend.p, grecv.p, 3 * (size_t)maxLoc, nccl_t(), c->comm, c->stream));
         dim3 g2((maxLoc + 255) / 256, c->nRanks);
         k_amg_scatter_gathered<T><<<g2, 256, 0, c->stream>>>(grecv.p, C.b.p, rankOff.p, rankCnt.p, c->nRanks, maxLoc, C.ld);
@@ -523,14 +539,14 @@ struct Hierarchy : S4fAmg {
         int rc = cycle_level<T>(c, l + 1, C.b.p, C.ld, nullptr, 0); if (rc) return rc;
         {
             const int grid = s4f_grid(c->numSMs, L.n);
-            k_amg_prolong<T><<<grid, S4F_BLOCK, 0, c->stream>>>(L.parent.p, C.x.p, x, L.n, L.ld, C.ld, (T)omega);
+            k_amg_prolong<T><<<grid, S4F_BLOCK, 0, c->stream>>>(L.parent.p, C.x.p, x, L.n, L.ld, C.ld, (T)omega, act);
             c->launches++;
         }
         if (cycle == 1 && l + 2 < lv.size()) {   // W-cycle: a second coarse correction on the updated residual
             rc = residual_restrict<TB>(c, l, b, ldb, x); if (rc) return rc;
             rc = cycle_level<T>(c, l + 1, C.b.p, C.ld, nullptr, 0); if (rc) return rc;
             const int gridp = s4f_grid(c->numSMs, L.n);
-            k_amg_prolong<T><<<gridp, S4F_BLOCK, 0, c->stream>>>(L.parent.p, C.x.p, x, L.n, L.ld, C.ld, (T)omega);
+            k_amg_prolong<T><<<gridp, S4F_BLOCK, 0, c->stream>>>(L.parent.p, C.x.p, x, L.n, L.ld, C.ld, (T)omega, act);
             c->launches++;
         }
         T* xr = smooth<TB>(c, L, b, ldb, false, x, out, ldo);                      // post-smoothing
@@ -541,17 +557,19 @@ struct Hierarchy : S4fAmg {
     }
 
     // the fine-level Chebyshev-Jacobi step kernel on its own (no halo): the dominant kernel of the V-cycle
-    int step0(s4fgpu_ctx* c, const double* r3) override {
+    int step0(s4fgpu_ctx* c, const double* r3, const int* actIn) override {
+        act = actIn;
         Level<T>& L = *lv[0];
         if (lv.size() < 2) return 0;
         const int grid = step_grid(c, L);
         k_amg_step<T, double, T, 0><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, L.rD.p, r3, L.x.p, L.d.p, L.x2.p, L.n, L.ld,
-                                                                            c->ld, L.ld, L.nSlices, (T)0.3, (T)0.5);
+                                                                            c->ld, L.ld, L.nSlices, (T)0.3, (T)0.5, act);
         c->launches++;
         return 0;
     }
 
-    int apply(s4fgpu_ctx* c, const double* r3, double* z3) override {
+    int apply(s4fgpu_ctx* c, const double* r3, double* z3, const int* actIn) override {
+        act = actIn;
         int rc = cycle_level<double>(c, 0, r3, c->ld, z3, c->ld);
         if (rc) return rc;
         S4F_CHECK_CUDA(c, cudaGetLastError());
@@ -810,10 +828,10 @@ int s4f_amg_info(s4fgpu_ctx* c, int* nLevels, int* sizes, int maxLevels, double*
 int s4f_amg_step0(s4fgpu_ctx* c, const double* r3, double* bytes) {
     if (!c->amg) { c->err = "GAMG hierarchy missing"; return 1; }
     if (bytes) *bytes = c->amg->step0Bytes;
-    return c->amg->step0(c, r3);
+    return c->amg->step0(c, r3, c->amgAct ? c->amgAct : c->ones3.p);
 }
 
 int s4f_amg_apply(s4fgpu_ctx* c, const double* r3, double* z3) {
     if (!c->amg) { c->err = "GAMG hierarchy missing"; return 1; }
-    return c->amg->apply(c, r3, z3);
+    return c->amg->apply(c, r3, z3, c->amgAct ? c->amgAct : c->ones3.p);
 }

@@ -220,6 +220,8 @@ struct s4fgpu_ctx {
     OuterScalars* hOutS = nullptr;
     double lambdaMax = 2.0;           // Chebyshev: bound of the Jacobi-scaled spectrum
     struct S4fAmg* amg = nullptr;     // GAMG hierarchy (s4f_amg.cu), rebuilt with the matrix
+    DevBuf<int> ones3;                // {1,1,1}
+    const int* amgAct = nullptr;      // device int[3] of components the V-cycle works on (null: all); the PCG passes its active flags
     bool amgValid = false;
 
     int iCorr = 0;

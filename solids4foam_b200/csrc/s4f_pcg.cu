@@ -299,7 +299,11 @@ __global__ void __launch_bounds__(S4F_BLOCK, 4) k_amul3(const int* __restrict__ 
                 e[k] = ok ? eA[idx] : 0.0;
             }
 #pragma unroll
-            for (int k = 0; k < 8; k++) { a0 += e[k] * p[cc[k]]; a1 += e[k] * p[cc[k] + ld]; a2 += e[k] * p[cc[k] + 2 * ld]; }
+            for (int k = 0; k < 8; k++) {          // a converged component skips its gathers (warp-uniform flags)
+                if (act[0]) a0 += e[k] * p[cc[k]];
+                if (act[1]) a1 += e[k] * p[cc[k] + ld];
+                if (act[2]) a2 += e[k] * p[cc[k] + 2 * ld];
+            }
         }
         if (row < N) {
             const double acc[3] = {a0, a1, a2};
@@ -663,7 +667,12 @@ static int solve_pbicgstab(s4fgpu_ctx* c, double* psi, PcgParams P, double nGlob
     const double* rD = (P.precond == S4F_PRECOND_NONE) ? nullptr : c->rDiagC.p;
     S4F_CHECK_CUDA(c, cudaMemcpyAsync(rA0, c->rA.p, 3 * (size_t)ld * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     auto precondition = [&](const double* in, double* out) -> int {
-        if (P.precond == S4F_PRECOND_GAMG) return s4f_amg_apply(c, in, out);
+        if (P.precond == S4F_PRECOND_GAMG) {
+            c->amgAct = &S->active[0];                      // converged components skip their share of the V-cycle
+            const int r = s4f_amg_apply(c, in, out);
+            c->amgAct = nullptr;
+            return r;
+        }
         return cheb_apply(c, P, in, out);
     };
     int rc, it = 0;
@@ -751,8 +760,11 @@ int s4f_solve_segregated(s4fgpu_ctx* c, double* psi, const double* source) {
                     k_pcg_p<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rDiagC.p, c->rA.p, c->pA.p, N, ld, S);
                 c->launches++;
             } else {
-                if (P.precond == S4F_PRECOND_GAMG) rc = s4f_amg_apply(c, c->rA.p, c->wA.p);
-                else rc = cheb_apply(c, P, c->rA.p, c->wA.p);
+                if (P.precond == S4F_PRECOND_GAMG) {
+                    c->amgAct = &S->active[0];              // converged components skip their share of the V-cycle
+                    rc = s4f_amg_apply(c, c->rA.p, c->wA.p);
+                    c->amgAct = nullptr;
+                } else rc = cheb_apply(c, P, c->rA.p, c->wA.p);
                 if (rc) return rc;
                 k_pcg_dot_zr<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->wA.p, c->rA.p, N, ld, S, P, nGlob, c->partials.p, c->ticket.p);
                 c->launches++;

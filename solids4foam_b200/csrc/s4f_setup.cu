@@ -263,6 +263,7 @@ int s4f_alloc_fields(s4fgpu_ctx* c) {
     S4F_CHECK_CUDA(c, A(c->pA, 3)); S4F_CHECK_CUDA(c, A(c->wA, 3)); S4F_CHECK_CUDA(c, A(c->rA, 3));
     S4F_CHECK_CUDA(c, c->pcgS.alloc(1)); S4F_CHECK_CUDA(c, c->outS.alloc(1));
     S4F_CHECK_CUDA(c, c->partials.alloc(32 * 4096)); S4F_CHECK_CUDA(c, c->ticket.alloc(8));
+    S4F_CHECK_CUDA(c, c->ones3.upload(std::vector<int>{1, 1, 1}));
     if (!c->hPcgS) S4F_CHECK_CUDA(c, cudaMallocHost((void**)&c->hPcgS, sizeof(PcgScalars)));
     if (!c->hOutS) S4F_CHECK_CUDA(c, cudaMallocHost((void**)&c->hOutS, sizeof(OuterScalars)));
     return 0;
