@@ -274,7 +274,7 @@ def main():
         return
     dom = "gamg_step0" if "gamg_step0" in kern else "spmv3"
     dom_name = {"gamg_step0": "k_amg_step (fine-level Chebyshev-Jacobi step of the GAMG V-cycle: 3-component SELL-32 SpMV + update; "
-                              "4 launches per PCG iteration, the largest share of the step)",
+                              f"{2 * args.gamg_degree} launches per PCG iteration, the largest share of the step)",
                 "spmv3": "k_amul3 (3-component SELL-32 SpMV + dot)"}[dom]
     traffic, traffic_src = (None, None)
     if world == 1:
@@ -291,7 +291,8 @@ def main():
                 ms_per_step=ms / K_, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
                 config=dict(workload=workload, cells_per_gpu=N, preconditioner=args.precond, solver="PCG relTol 0.1 tol 1e-9",
                             gradScheme="leastSquares", stabilisation="RhieChow 0.1", l2="working set >> L2 (inputs larger than L2)",
-                            pcg_inner_iterations_per_outer=inner_per_outer),
+                            pcg_inner_iterations_per_outer=inner_per_outer,
+                            pcg_iterations_per_component=[float(x) for x in np.mean(np.array(stats), axis=0)]),
                 clocks=clocks, gpu_launches=int(launches),
                 e2e=dict(value=e2e_val, unit="iter/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
                 roofline=roof, kernels=kern)
@@ -300,10 +301,10 @@ def main():
 
     if world == 1 and not args.no_cpu_baseline:
         sample = CPU_SAMPLE if nCellsFull > CPU_SAMPLE[0] * CPU_SAMPLE[1] * CPU_SAMPLE[2] else dims
-        ips, dt, inner, nS, cores = cpu_reference_run(sample, 4, 3, precond_dic=True)
+        ips, dt, inner, nS, cores = cpu_reference_run(sample, 12, 3, precond_dic=True)
         scale = nS / nCellsFull
         line["cpu_baseline"] = dict(value=ips * scale, unit="iter/s", cores=cores, kind="port",
-                                    sample=f"CPU oracle (LDU PCG+DIC, {cores} OpenMP threads) on {sample[0]}x{sample[1]}x{sample[2]} = {nS} cells, 4 outer "
+                                    sample=f"CPU oracle (LDU PCG+DIC, {cores} OpenMP threads) on {sample[0]}x{sample[1]}x{sample[2]} = {nS} cells, 12 outer "
                                            f"iterations after 3 warm-up in {dt:.1f} s, scaled by {scale:.4f} to the full workload")
     print(json.dumps(line))
     if world > 1:

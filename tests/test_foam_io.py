@@ -1,0 +1,142 @@
+"""On-disk formats: OpenFOAM dictionaries, polyMesh and vol-field files read / written by the host
+side, checked against the reference's own tutorial files where this container has them and by round trips otherwise."""
+import os
+
+import numpy as np
+import pytest
+
+from solids4foam_b200 import case as K
+from solids4foam_b200 import cases
+from solids4foam_b200 import foam_io as IO
+from solids4foam_b200 import mesh as M
+
+REF = "/root/reference/tutorials"
+needs_ref = pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree is only mounted in the build container")
+
+
+def test_dictionary_parser_handles_the_openfoam_syntax():
+    d = IO.parse_foam_dict('''
+        FoamFile { version 2.0; class dictionary; }
+        // comment
+        planeStress     no;   /* block
+        comment */
+        mechanical ( steel { type linearElastic; rho rho [1 -3 0 0 0 0 0] 7854; E E [1 -1 -2 0 0 0 0] 200e+9; nu nu [0 0 0 0 0 0 0] 0.3; } );
+        solvers { "D|DD" { solver PCG; preconditioner FDIC; tolerance 1e-09; relTol 0.1; } }
+        value uniform (0 1.5 -2);
+    ''')
+    assert d["planeStress"] == "no"
+    name, law = d["mechanical"][0]
+    assert name == "steel" and law["type"] == "linearElastic" and IO._scalar(law["E"]) == 200e9 and IO._scalar(law["rho"]) == 7854
+    assert IO._lookup(d["solvers"], "DD")["preconditioner"] == "FDIC" and IO._lookup(d["solvers"], "D")["relTol"] == 0.1
+    assert d["value"] == ["uniform", [0, 1.5, -2]]
+
+
+@needs_ref
+def test_plate_hole_tutorial_directory_gives_the_hand_built_case():
+    """tutorials/solids/linearElasticity/plateHole: constant/{solidProperties,mechanicalProperties}, system/{fvSchemes,
+    fvSolution}, 0/D read from the reference's own files reproduce cases.plate_hole() field by field."""
+    mesh = M.plate_hole()
+    c = IO.read_case(os.path.join(REF, "solids/linearElasticity/plateHole"), mesh=mesh)
+    ref = cases.plate_hole()
+    for f, _ in K.Law._fields_:
+        a, b = getattr(c.law, f), getattr(ref.law, f)
+        assert (list(a) == list(b)) if hasattr(a, "__len__") else (a == b), f
+    for f in ("solidModel", "gradScheme", "d2dt2Scheme", "stabilisation", "stabScaleFactor", "relaxationMethod", "fieldRelaxD", "solver",
+              "tolerance", "relTol", "nCorrectors", "solutionTolerance", "alternativeTolerance", "materialTolerance"):
+        assert getattr(c.controls, f) == getattr(ref.controls, f), f
+    assert c.controls.preconditioner == K.PRECOND_DIC              # FDIC in the tutorial
+    assert set(c.bcs) == set(ref.bcs)
+    for name in ref.bcs:
+        assert c.bcs[name].kind == ref.bcs[name].kind, name
+        if ref.bcs[name].value is not None:
+            p = mesh.patch(name)
+            assert np.allclose(np.broadcast_to(c.bcs[name].value, (p.size, 3)), np.broadcast_to(ref.bcs[name].value, (p.size, 3)), rtol=0, atol=1e-9)
+
+
+@needs_ref
+def test_beam_in_cross_flow_solid_dictionaries():
+    base = os.path.join(REF, "fluidSolidInteraction/beamInCrossFlow")
+    # the solid region keeps its files under constant/solid and system/solid: present them as a case directory
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "constant")); os.makedirs(os.path.join(tmp, "system"))
+        for sub, names in (("constant", ("solidProperties", "mechanicalProperties")), ("system", ("fvSchemes", "fvSolution"))):
+            for n in names:
+                os.symlink(os.path.join(base, sub, "solid", n), os.path.join(tmp, sub, n))
+        law = IO.read_mechanical_law(tmp)
+        ctl = IO.read_controls(tmp)
+    ref = cases.beam_in_cross_flow()
+    assert (law.kind, law.rho, law.mu, law.K) == (ref.law.kind, ref.law.rho, ref.law.mu, ref.law.K)
+    assert ctl.solidModel == K.MODEL_NONLIN_UL and ctl.d2dt2Scheme == K.D2DT2_BACKWARD and ctl.gradScheme == K.GRAD_LEAST_SQUARES
+    assert ctl.fieldRelaxD == ref.controls.fieldRelaxD == 0.9 and ctl.nCorrectors == ref.controls.nCorrectors == 1000
+    assert ctl.tolerance == 1e-9 and ctl.relTol == 0.1
+
+
+def test_poly_mesh_round_trip(tmp_path):
+    names = ("fixed", "loaded", "yMin", "yMax", "zMin", "zMax")
+    kinds = (M.PATCH, M.PATCH, M.PATCH, M.PATCH, M.SYMMETRY_PLANE, M.PATCH)
+    pmap = lambda p: p + 0.03 * np.sin(3.0 * p[:, [1, 2, 0]])              # a non-orthogonal mesh
+    mesh = M.hex_box_general(5, 4, 3, 2.0, 1.0, 1.0, names=names, kinds=kinds, point_map=pmap, cell_perm_seed=3)
+    IO.write_poly_mesh(str(tmp_path / "polyMesh"), mesh)
+    back = IO.read_poly_mesh(str(tmp_path / "polyMesh"))
+    assert back.nCells == mesh.nCells and np.array_equal(back.owner, mesh.owner) and np.array_equal(back.neighbour, mesh.neighbour)
+    assert [(p.name, p.kind, p.start, p.size) for p in back.patches] == [(p.name, p.kind, p.start, p.size) for p in mesh.patches]
+    for f in ("C", "V", "Sf", "magSf", "Cf", "weights", "nonOrthDeltaCoeffs", "nonOrthCorrVec", "CnbrB"):
+        assert np.allclose(getattr(back, f), getattr(mesh, f), rtol=1e-13, atol=1e-15), f
+    assert np.array_equal(back.faces, mesh.faces) and np.array_equal(back.points, mesh.points)
+    moved = M.move_points(back, back.points * 1.01)                          # a read mesh can be moved (updated Lagrangian)
+    assert np.allclose(moved.V, 1.01 ** 3 * mesh.V, rtol=1e-12)
+
+
+def test_polygon_geometry_matches_the_quad_routine():
+    mesh = M.hex_box_general(3, 3, 2, 1.0, 1.0, 1.0, point_map=lambda p: p + 0.05 * np.cos(2.0 * p[:, [2, 0, 1]]))
+    fptr = np.arange(0, 4 * mesh.faces.shape[0] + 1, 4)
+    c, a = IO.polygon_centres_and_areas(mesh.points, fptr, mesh.faces.reshape(-1).astype(np.int64))
+    c2, a2 = M.face_centres_and_areas(mesh.points, mesh.faces)
+    assert np.allclose(c, c2, atol=1e-15) and np.allclose(a, a2, atol=1e-15)
+    # a triangle: centroid and half cross product
+    pts = np.array([[0.0, 0, 0], [2, 0, 0], [0, 3, 0]])
+    c, a = IO.polygon_centres_and_areas(pts, np.array([0, 3]), np.array([0, 1, 2]))
+    assert np.allclose(c[0], pts.mean(axis=0)) and np.allclose(a[0], [0, 0, 3.0])
+
+
+def test_vol_field_round_trip(tmp_path):
+    mesh = M.hex_box_general(3, 2, 2)
+    rng = np.random.default_rng(0)
+    D = rng.standard_normal((mesh.nCells, 3)); Db = rng.standard_normal((mesh.nBoundaryFaces, 3))
+    sig = rng.standard_normal((mesh.nCells, 6))
+    IO.write_vol_field(str(tmp_path / "1"), "D", mesh, D, Db)
+    IO.write_vol_field(str(tmp_path / "1"), "sigma", mesh, sig, dimensions="[1 -1 -2 0 0 0 0]")
+    Di, Dbv = IO.read_vol_field(str(tmp_path / "1" / "D"), mesh)
+    assert np.array_equal(Di, D)
+    for p in mesh.patches:
+        assert np.array_equal(Dbv[p.name], Db[p.start:p.start + p.size])
+    si, _ = IO.read_vol_field(str(tmp_path / "1" / "sigma"), mesh)
+    assert np.array_equal(si, sig)
+    txt = open(tmp_path / "1" / "sigma").read()
+    assert "volSymmTensorField" in txt and "List<symmTensor>" in txt
+
+
+def test_case_directory_round_trip(tmp_path):
+    """write_case -> read_case gives back the law, the controls the dictionaries carry and the boundary data."""
+    c = cases.neo_hookean_cantilever(6, 3, 3, general=True, traction=(0.0, -2e3, 10.0), solidModel=K.MODEL_NONLIN_UL,
+                                     d2dt2Scheme=K.D2DT2_BACKWARD, deltaT=0.05, fieldRelaxD=0.9, g=(0.0, -9.81, 0.0), nCorrectors=123,
+                                     tolerance=1e-11, relTol=0.01, gradScheme=K.GRAD_GAUSS_LINEAR, preconditioner=K.PRECOND_GAMG)
+    c.law = K.mechanical_law("neoHookeanElasticMisesPlastic", rho=1000.0, E=3e6, nu=0.3, table=K.NECKING_BAR_TABLE, solvePressureEqn=True,
+                             pressureSmoothingScaleFactor=50.0)
+    IO.write_case(str(tmp_path), c)
+    r = IO.read_case(str(tmp_path))
+    for f in ("kind", "rho", "nTable", "solvePressureEqn", "pressureSmoothingScaleFactor"):
+        assert getattr(r.law, f) == getattr(c.law, f), f
+    assert np.isclose(r.law.mu, c.law.mu, rtol=1e-15) and np.isclose(r.law.K, c.law.K, rtol=1e-15)
+    assert list(r.law.tableSigY)[:8] == list(c.law.tableSigY)[:8]
+    for f in ("solidModel", "gradScheme", "d2dt2Scheme", "stabilisation", "stabScaleFactor", "fieldRelaxD", "solver", "preconditioner",
+              "tolerance", "relTol", "maxIter", "nCorrectors", "solutionTolerance", "alternativeTolerance", "deltaT"):
+        assert getattr(r.controls, f) == getattr(c.controls, f), f
+    assert list(r.controls.g) == [0.0, -9.81, 0.0]
+    assert np.allclose(r.mesh.V, c.mesh.V, rtol=1e-13)
+    for p in c.mesh.patches:
+        a, b = r.bcs[p.name], c.bcs[p.name]
+        assert a.kind == b.kind
+        if b.value is not None:
+            assert np.array_equal(np.broadcast_to(a.value, (p.size, 3)), np.broadcast_to(b.value, (p.size, 3)))

@@ -4,6 +4,8 @@ Tolerances: the path is fp64 on both sides; single operators agree to round-off 
 order: gather vs LDU scatter) -> 1e-12 relative; whole solves are compared at equal residual with the
 contract of BASELINE.json's north_star: relative L2 <= 1e-6 for D and sigma.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -540,3 +542,28 @@ def test_pressure_smoothing_matches_oracle(law, model, case_kw):
     p.law.solvePressureEqn = 0
     o2 = OracleSolid(p); o2.evolve()
     assert rel_l2(o.get("sigma"), o2.get("sigma")) > 1e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# standalone driver over an OpenFOAM case directory
+# ---------------------------------------------------------------------------------------------
+def test_standalone_driver_runs_a_case_directory(tmp_path):
+    """write_case -> run_case (read_case, SolidModel, evolve, updateTotalFields, time directories) reproduces the direct run, and
+    the written D / sigma files read back to the device fields."""
+    from solids4foam_b200 import foam_io as IO
+    from solids4foam_b200 import run_case
+    from solids4foam_b200.solid_model import SolidModel
+    kw = dict(nx=8, ny=4, nz=4, L=2.0, general=True, traction=(0.0, -4e3, 0.0), solidModel=K.MODEL_NONLIN_UL, fieldRelaxD=0.9,
+              nCorrectors=6000, preconditioner=K.PRECOND_GAMG, solutionTolerance=1e-10, alternativeTolerance=1e-10, tolerance=1e-13)
+    IO.write_case(str(tmp_path), cases.neo_hookean_cantilever(**kw), end_time=2.0)
+    solid, stats = run_case.run(str(tmp_path), log=lambda s: None)
+    assert len(stats) == 2 and all(s["converged"] for s in stats)
+    g = SolidModel(cases.neo_hookean_cantilever(**kw))
+    for _ in range(2):
+        g.new_timestep(1.0); g.evolve(); g.updateTotalFields()
+    assert rel_l2(solid.get("D"), g.get("D")) < SOLVE_TOL
+    Dfile, Db = IO.read_vol_field(str(tmp_path / "2" / "D"), solid.case.mesh)
+    assert np.array_equal(Dfile, solid.get("D"))
+    sfile, _ = IO.read_vol_field(str(tmp_path / "2" / "sigma"), solid.case.mesh)
+    assert np.array_equal(sfile, solid.get("sigma"))
+    assert os.path.exists(tmp_path / "1" / "D")
