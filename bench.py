@@ -125,15 +125,16 @@ def cpu_reference_run(dims, steps, warmup, precond_dic=True):
     c = cases.cantilever(*dims, preconditioner=pre)
     o = OracleSolid(c)
     cores = int(o.L.s4fo_set_threads(o.h, 0))     # all host cores; DIC becomes block-Jacobi over the thread ranges,
+    st0 = {"totalInnerIterations": 0}
     for _ in range(warmup):                        # as OpenFOAM's DIC is across MPI ranks
-        o.outer_iteration()
-    inner0 = 0
+        st0 = o.outer_iteration()
+    inner0 = o.outer_iteration()["totalInnerIterations"] if warmup == 0 else st0["totalInnerIterations"]
     t0 = time.perf_counter()
     st = None
     for _ in range(steps):
         st = o.outer_iteration()
     dt = time.perf_counter() - t0
-    inner = st["totalInnerIterations"] if st else 0
+    inner = (st["totalInnerIterations"] - inner0) / max(steps, 1) if st else 0      # PCG iterations per outer iteration (3 components)
     return steps / dt, dt, inner, c.mesh.nCells, cores
 
 
@@ -161,7 +162,7 @@ def main():
                     impl="reference", config=dict(workload=workload, preconditioner="DIC", solver="PCG relTol 0.1"),
                     cpu_baseline=dict(value=val, unit="iter/s", cores=cores, kind="port",
                                       sample=f"CPU oracle (LDU PCG+DIC, {cores} OpenMP threads), {sample[0]}x{sample[1]}x{sample[2]} = {nS} cells, "
-                                             f"{K_} outer iterations after {W_} warm-up, {dt:.1f} s; iter/s scaled by cells ratio "
+                                             f"{K_} outer iterations after {W_} warm-up, {dt:.1f} s, {inner:.0f} PCG iterations per outer iteration; iter/s scaled by cells ratio "
                                              f"{scale:.4f} to the {nCellsFull}-cell workload (optimistic for the CPU: inner iteration "
                                              "counts grow with mesh size)"),
                     e2e=dict(value=val, unit="iter/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -305,7 +306,9 @@ def main():
         scale = nS / nCellsFull
         line["cpu_baseline"] = dict(value=ips * scale, unit="iter/s", cores=cores, kind="port",
                                     sample=f"CPU oracle (LDU PCG+DIC, {cores} OpenMP threads) on {sample[0]}x{sample[1]}x{sample[2]} = {nS} cells, 12 outer "
-                                           f"iterations after 3 warm-up in {dt:.1f} s, scaled by {scale:.4f} to the full workload")
+                                           f"iterations after 3 warm-up in {dt:.1f} s, scaled by {scale:.4f} to the full workload; "
+                                           f"{inner:.0f} DIC-PCG iterations per outer iteration (3 components) on the sample against "
+                                           f"{inner_per_outer:.0f} GAMG-PCG iterations on the GPU at full size")
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

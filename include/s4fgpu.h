@@ -154,6 +154,7 @@ typedef struct {
     double gamgOverCorrection; /* S4F_PRECOND_GAMG: fixed scaling of the coarse-grid correction (<= 0: 2.2) */
     int gamgSmootherDegree;    /* S4F_PRECOND_GAMG: Chebyshev-Jacobi degree of the pre- and post-smoother (<= 0: 3) */
     int gamgCycle;             /* S4F_PRECOND_GAMG: 0 = V-cycle, 1 = W-cycle */
+    double gamgSmootherRatio;  /* S4F_PRECOND_GAMG: lower end of the Chebyshev interval as a fraction of the upper (<= 0: 0.3) */
 } s4fgpu_controls;
 
 /* result of one outer (momentum-correction) iteration / of evolve(); the numbers of the

@@ -74,7 +74,7 @@ class Controls(C.Structure):
                 ("g", C.c_double * 3), ("deltaT", C.c_double), ("deltaT0", C.c_double),
                 ("chebyshevDegree", C.c_int), ("checkEvery", C.c_int),
                 ("gamgSinglePrecision", C.c_int), ("gamgOverCorrection", C.c_double),
-                ("gamgSmootherDegree", C.c_int), ("gamgCycle", C.c_int)]
+                ("gamgSmootherDegree", C.c_int), ("gamgCycle", C.c_int), ("gamgSmootherRatio", C.c_double)]
 
 
 class Stats(C.Structure):
@@ -118,6 +118,7 @@ def default_controls(**kw) -> Controls:
     c.gamgOverCorrection = 2.2
     c.gamgSmootherDegree = 3
     c.gamgCycle = 0
+    c.gamgSmootherRatio = 0.3
     for k, v in kw.items():
         if k == "g":
             for i in range(3):

@@ -594,7 +594,8 @@ int build(s4fgpu_ctx* c, std::vector<HostLevel>& H, const DistInfo& di) {
     A->deg = c->ctl.gamgSmootherDegree > 0 ? c->ctl.gamgSmootherDegree : 3;
     A->cycle = c->ctl.gamgCycle;
     A->omega = c->ctl.gamgOverCorrection > 0 ? c->ctl.gamgOverCorrection : 2.2;
-    const double lmax = 2.0, lmin = 0.3 * lmax;      // Gershgorin bound of D^-1 A for the M-matrices of every level
+    const double ratio = c->ctl.gamgSmootherRatio > 0 ? c->ctl.gamgSmootherRatio : 0.3;
+    const double lmax = 2.0, lmin = ratio * lmax;    // Gershgorin bound of D^-1 A for the M-matrices of every level
     A->theta = 0.5 * (lmax + lmin); A->delta = 0.5 * (lmax - lmin);
     for (size_t l = 0; l < H.size(); l++) {
         A->lv.emplace_back(new Level<T>());
