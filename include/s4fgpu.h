@@ -65,7 +65,11 @@ enum {
 /* system/fvSchemes gradSchemes */
 enum {
     S4F_GRAD_LEAST_SQUARES = 0, /* 1/|d|^2-weighted LS: numerics/extendedLeastSquaresGrad/extendedLeastSquaresVectors.C:121-158,229-272 */
-    S4F_GRAD_GAUSS_LINEAR = 1   /* [OF-ext] gaussGrad + linear */
+    S4F_GRAD_GAUSS_LINEAR = 1,  /* [OF-ext] gaussGrad + linear */
+    S4F_GRAD_POINT_CELLS_LEAST_SQUARES = 2 /* [OF-ext] LeastSquaresGrad<centredCPCCellToCellStencilObject> ("pointCellsLeastSquares",
+                                   the scheme the tutorials use on OpenFOAM.com/.org, applications/scripts/solids4FoamScripts.sh:162-176):
+                                   1/|d|^2-weighted least squares over the cells sharing a point with the cell and the boundary faces
+                                   at its points; needs s4fgpu_set_points; single rank */
 };
 enum { S4F_D2DT2_STEADY_STATE = 0, S4F_D2DT2_EULER = 1, S4F_D2DT2_BACKWARD = 2 };
 enum { S4F_STAB_NONE = 0, S4F_STAB_RHIE_CHOW = 1 };        /* SM/solidModel/momentumStabilisation/momentumStabilisation.C:210-217 */

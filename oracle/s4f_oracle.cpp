@@ -146,6 +146,8 @@ struct s4f_oracle {
     // polyMesh points/faces for vol->point interpolation
     int nPoints = 0;
     dvec points; ivec fvPtr, fv, pcPtr, pcCells, pbPtr, pbFaces;
+    // pointCellsLeastSquares: per cell the stencil slots (cell index, or N + boundary face) and the least-squares vectors
+    ivec psPtr, psSlot; dvec psLs; bool psValid = false;
     int timeIndex = 0;             // number of new_timestep() calls (runTime.timeIndex())
     dvec impK, impKf;              // impK (N+B), impKf (F+B)
     dvec Ft, Finv, Jt;             // solver-level F, Finv, J of the TL models
@@ -361,11 +363,63 @@ void bcEvaluate(s4f_oracle& o) {
 // [OF-ext] Gauss linear; then gaussGrad::correctBoundaryConditions: grad_b = grad_P + n (snGrad_b - n & grad_P).
 // mechanicalModel::grad, mechanicalModel.C:571-582.
 // ------------------------------------------------------------------------------------------------
+// [OF-ext] LeastSquaresVectors<centredCPCCellToCellStencilObject>::calcLeastSquaresVectors ("pointCellsLeastSquares"):
+// stencil of cell i = the cells sharing a point with i and the boundary faces (non-empty, non-coupled) at i's points
+// (CPCCellToCellStencil); d_j = x_j - C_i (boundary faces: face centre); dd = dd0 + sum d d/|d|^2, dd0 = unit entries in the
+// empty directions; ls_j = (inv(dd) - dd0) & d_j/|d|^2; grad_i = sum_j ls_j (phi_j - phi_i).   Restated from the OpenFOAM
+// library (not vendored): consistent by construction (exact for linear fields), the weights are from the published source.
+void makePointCellsStencil(s4f_oracle& o) {
+    const int N = o.N, F = o.F, B = o.B;
+    std::vector<std::vector<int>> cellPts(N);
+    auto add = [](std::vector<int>& v, int x) { if (std::find(v.begin(), v.end(), x) == v.end()) v.push_back(x); };
+    for (int f = 0; f < F + B; f++) for (int j = o.fvPtr[f]; j < o.fvPtr[f + 1]; j++) {
+        add(cellPts[f < F ? o.own[f] : o.faceCells[f - F]], o.fv[j]);
+        if (f < F) add(cellPts[o.nei[f]], o.fv[j]);
+    }
+    o.psPtr.assign(1, 0); o.psSlot.clear(); o.psLs.clear();
+    for (int i = 0; i < N; i++) {
+        std::vector<int> st;
+        for (int p : cellPts[i]) {
+            for (int j = o.pcPtr[p]; j < o.pcPtr[p + 1]; j++) if (o.pcCells[j] != i) add(st, o.pcCells[j]);
+            for (int j = o.pbPtr[p]; j < o.pbPtr[p + 1]; j++) add(st, N + o.pbFaces[j]);
+        }
+        std::sort(st.begin(), st.end());
+        double dd[6] = {0, 0, 0, 0, 0, 0};
+        if (!o.solD[0]) dd[0] += 1; if (!o.solD[1]) dd[3] += 1; if (!o.solD[2]) dd[5] += 1;
+        std::vector<double> dl(3 * st.size());
+        for (size_t k = 0; k < st.size(); k++) {
+            const double* x = st[k] < N ? &o.C[3 * (size_t)st[k]] : &o.Cf[3 * (size_t)(F + st[k] - N)];
+            double d[3] = {x[0] - o.C[3 * (size_t)i], x[1] - o.C[3 * (size_t)i + 1], x[2] - o.C[3 * (size_t)i + 2]};
+            const double r = 1.0 / dot3(d, d);
+            dd[0] += r * d[0] * d[0]; dd[1] += r * d[0] * d[1]; dd[2] += r * d[0] * d[2];
+            dd[3] += r * d[1] * d[1]; dd[4] += r * d[1] * d[2]; dd[5] += r * d[2] * d[2];
+            for (int q = 0; q < 3; q++) dl[3 * k + q] = r * d[q];
+        }
+        double iv[6]; invS(dd, iv);
+        if (!o.solD[0]) iv[0] -= 1; if (!o.solD[1]) iv[3] -= 1; if (!o.solD[2]) iv[5] -= 1;
+        for (size_t k = 0; k < st.size(); k++) {
+            double a[3]; SvS(iv, &dl[3 * k], a);
+            o.psSlot.push_back(st[k]);
+            for (int q = 0; q < 3; q++) o.psLs.push_back(a[q]);
+        }
+        o.psPtr.push_back((int)o.psSlot.size());
+    }
+    o.psValid = true;
+}
+
 // cell values of fvc::grad(X) for a vol field X given as [internal | boundary] values
-void gradInterior(const s4f_oracle& o, const dvec& X, dvec& g) {
+void gradInterior(const s4f_oracle& oc, const dvec& X, dvec& g) {
+    s4f_oracle& o = const_cast<s4f_oracle&>(oc);
     const int N = o.N, F = o.F, B = o.B;
     g.assign(9 * (size_t)(N + B), 0.0);
-    if (o.ctl.gradScheme == S4F_GRAD_LEAST_SQUARES) {
+    if (o.ctl.gradScheme == S4F_GRAD_POINT_CELLS_LEAST_SQUARES) {
+        if (!o.psValid) makePointCellsStencil(o);
+        for (int i = 0; i < N; i++)
+            for (int k = o.psPtr[i]; k < o.psPtr[i + 1]; k++) {
+                const int s = o.psSlot[k];
+                for (int a = 0; a < 3; a++) for (int j = 0; j < 3; j++) g[9 * (size_t)i + 3 * a + j] += o.psLs[3 * (size_t)k + a] * (X[3 * (size_t)s + j] - X[3 * (size_t)i + j]);
+            }
+    } else if (o.ctl.gradScheme == S4F_GRAD_LEAST_SQUARES) {
         forAllInternalFaces(o, [&](int f) {
             int P = o.own[f], Nn = o.nei[f];
             double dv[3] = {X[3 * Nn] - X[3 * P], X[3 * Nn + 1] - X[3 * P + 1], X[3 * Nn + 2] - X[3 * P + 2]};
@@ -1341,6 +1395,7 @@ int s4fo_set_geometry(s4f_oracle* o, const double* C, const double* V, const dou
     o->Cf.assign(Cf, Cf + 3 * FB); o->w.assign(weights, weights + FB); o->nod.assign(nod, nod + FB);
     o->corr.assign(corr, corr + 3 * FB); o->CnbrB.assign(CnbrB, CnbrB + 3 * o->B);
     const bool again = !o->impK.empty() && (int)o->D.size() == 3 * o->NB();   // mesh motion: fields, BC data and history stay
+    o->psValid = false;
     makeLeastSquaresVectors(*o);
     allocFields(*o);
     if (again) setupImpK(*o);
@@ -1352,7 +1407,7 @@ int s4fo_set_geometry(s4f_oracle* o, const double* C, const double* V, const dou
 // (enhancedVolPointInterpolation.C:60-160: boundary faces of non-empty, non-coupled patches)
 int s4fo_set_points(s4f_oracle* o, int nPoints, const double* points, const int* faceVertsPtr, const int* faceVerts) {
     const int F = o->F, B = o->B;
-    o->nPoints = nPoints; o->points.assign(points, points + 3 * (size_t)nPoints);
+    o->nPoints = nPoints; o->points.assign(points, points + 3 * (size_t)nPoints); o->psValid = false;
     o->fvPtr.assign(faceVertsPtr, faceVertsPtr + F + B + 1); o->fv.assign(faceVerts, faceVerts + faceVertsPtr[F + B]);
     std::vector<std::vector<int>> pc(nPoints), pb(nPoints);
     auto add = [](std::vector<int>& v, int x) { if (std::find(v.begin(), v.end(), x) == v.end()) v.push_back(x); };

@@ -23,7 +23,7 @@ from .mesh import FvMesh, PROCESSOR
 BC_FIXED_DISPLACEMENT, BC_SOLID_TRACTION, BC_SOLID_SYMMETRY, BC_PROCESSOR = 0, 1, 2, 3
 MODEL_LIN_GEOM_TOTAL_DISP, MODEL_NONLIN_TL_TOTAL_DISP, MODEL_NONLIN_TL, MODEL_NONLIN_UL = 0, 1, 2, 3
 LAW_LINEAR_ELASTIC, LAW_NEO_HOOKEAN_ELASTIC, LAW_NEO_HOOKEAN_MISES_PLASTIC, LAW_LINEAR_ELASTIC_MISES_PLASTIC = 0, 1, 2, 3
-GRAD_LEAST_SQUARES, GRAD_GAUSS_LINEAR = 0, 1
+GRAD_LEAST_SQUARES, GRAD_GAUSS_LINEAR, GRAD_POINT_CELLS_LEAST_SQUARES = 0, 1, 2
 D2DT2_STEADY_STATE, D2DT2_EULER, D2DT2_BACKWARD = 0, 1, 2
 STAB_NONE, STAB_RHIE_CHOW = 0, 1
 RELAX_FIXED, RELAX_AITKEN = 0, 1

@@ -187,7 +187,7 @@ int s4fgpu_set_geometry(s4fgpu_handle c, const double* C, const double* V, const
     // host geometry copies are only needed to build the rows (cell centres stay for the vol->point weights)
     std::vector<double>().swap(c->hSf); std::vector<double>().swap(c->hCf); std::vector<double>().swap(c->hCorr);
     std::vector<double>().swap(c->hW); std::vector<double>().swap(c->hNod);
-    c->geomSet = true; c->matrixValid = false; c->amgValid = false; c->histValid = false; c->mValid = false;
+    c->geomSet = true; c->matrixValid = false; c->amgValid = false; c->histValid = false; c->mValid = false; c->gValid = false;
     if (c->lawSet && !again) { rc = s4f_setup_law(c); if (rc) return rc; }
     return 0;
 }
@@ -211,6 +211,7 @@ int s4fgpu_set_controls(s4fgpu_handle c, const s4fgpu_controls* ctl) {
                 "set_controls: nonLinearGeometryTotalLagrangian is available with the steadyState d2dt2 scheme");
     S4F_REQUIRE(c, ctl->solver == S4F_SOLVER_PCG || ctl->solver == S4F_SOLVER_PBICGSTAB, "set_controls: solver PCG or PBiCGStab");
     S4F_REQUIRE(c, ctl->d2dt2Scheme >= S4F_D2DT2_STEADY_STATE && ctl->d2dt2Scheme <= S4F_D2DT2_BACKWARD, "set_controls: unknown d2dt2 scheme");
+    S4F_REQUIRE(c, ctl->gradScheme >= S4F_GRAD_LEAST_SQUARES && ctl->gradScheme <= S4F_GRAD_POINT_CELLS_LEAST_SQUARES, "set_controls: unknown gradScheme");
     if (ctl->d2dt2Scheme == S4F_D2DT2_BACKWARD && ctl->deltaT0 > 0)     // backwardD2dt2Scheme.C:316-322
         S4F_REQUIRE(c, std::fabs(ctl->deltaT - ctl->deltaT0) <= 1e-15 + 1e-12 * ctl->deltaT, "set_controls: backwardD2dt2Scheme not implemented for variable time steps");
     c->ctl = *ctl; c->ctlSet = true; c->matrixValid = false; c->amgValid = false; c->histValid = false; c->mValid = false;
@@ -395,6 +396,8 @@ int s4fgpu_set_points(s4fgpu_handle c, int nPoints, const double* points, const 
     c->nPoints = nPoints;
     c->hFvPtr.assign(faceVertsPtr, faceVertsPtr + nF + 1);
     c->hFv.assign(faceVerts, faceVerts + faceVertsPtr[nF]);
+    c->hPoints.assign(points, points + 3 * (size_t)nPoints);
+    c->gValid = false;
     return s4f_build_point_weights(c, points);
 }
 

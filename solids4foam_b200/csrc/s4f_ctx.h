@@ -175,6 +175,9 @@ struct s4fgpu_ctx {
     DevBuf<int> ptPtr, ptCol;                     // [nPoints+1], [nnzP]
     DevBuf<double> ptW, ptN;                      // [nnzP] normalised inverse-distance weights; [3*nPoints] constraint normal (0 = none)
     DevBuf<double> ptOut;                         // [3*nPoints]
+    // pointCellsLeastSquares gradient: its own (wider) SELL-32 rows: cells sharing a point + boundary faces at the cell's points
+    DevBuf<int> gSlicePtr, gCol; DevBuf<double> gLs; long long gNE = 0; bool gValid = false;
+    std::vector<double> hPoints;
     DevBuf<int> pgPtr, pgCol;                     // gradient-extrapolated variant: every point from its pointCells
     DevBuf<double> pgW, pgDelta;                  // [nnz] normalised weights, [3*nnz] point - cell centre
     bool histValid = false;
@@ -230,6 +233,12 @@ struct s4fgpu_ctx {
 
     bool incremental() const { return ctl.solidModel == S4F_MODEL_NONLIN_TL || ctl.solidModel == S4F_MODEL_NONLIN_UL; }
     bool UL() const { return ctl.solidModel == S4F_MODEL_NONLIN_UL; }
+    bool pointCellsGrad() const { return ctl.gradScheme == S4F_GRAD_POINT_CELLS_LEAST_SQUARES; }
+    // rows the least-squares gradient kernels run over
+    const int* gradSlicePtr() const { return pointCellsGrad() ? gSlicePtr.p : slicePtr.p; }
+    const int* gradCol() const { return pointCellsGrad() ? gCol.p : col.p; }
+    const double* gradLs() const { return pointCellsGrad() ? gLs.p : eLs.p; }
+    long long gradNE() const { return pointCellsGrad() ? gNE : nEntries; }
     // orthogonal mesh + uniform Rhie-Chow coefficient: the right-hand side gathers ONE tensor per neighbour (k_source_m)
     bool fastRhs() const { return !nonOrth; }
     double gamma0() const { return ctl.stabilisation == S4F_STAB_RHIE_CHOW ? ctl.stabScaleFactor * impK0 : 0.0; }
@@ -271,6 +280,7 @@ int s4f_amg_step0(s4fgpu_ctx* c, const double* r3, double* bytes);
 void s4f_amg_destroy(s4fgpu_ctx* c);
 int s4f_amg_info(s4fgpu_ctx* c, int* nLevels, int* sizes, int maxLevels, double* bytesPerApply, double* setupSeconds);
 int s4f_download_upper(s4fgpu_ctx* c, double* hostUpper);           // lduMatrix upper() [F]
+int s4f_build_point_stencil(s4fgpu_ctx* c);                          // rows of the pointCellsLeastSquares gradient (s4f_setup.cu)
 int s4f_build_point_weights(s4fgpu_ctx* c, const double* points);   // vol->point CSR + weights (s4f_setup.cu)
 int s4f_interpolate_to_points(s4fgpu_ctx* c, const double* field3, const double* grad9 /* null: patch mode */, double* hostOut);
 int s4f_grad_calculated(s4fgpu_ctx* c, const double* X, double* gradOut);   // fvc::grad of a field with calculated patches

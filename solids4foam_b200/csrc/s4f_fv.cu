@@ -844,8 +844,10 @@ int s4f_grad(s4fgpu_ctx* c) {
     }
     if (c->ctl.gradScheme == S4F_GRAD_GAUSS_LINEAR)
         k_grad<true><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eSf.p, c->eW.p, c->D.p, c->rV.p, c->gradD.p, c->N, c->ld, c->nEntries, c->nSlices);
-    else
-        k_grad<false><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eLs.p, c->eW.p, c->D.p, c->rV.p, c->gradD.p, c->N, c->ld, c->nEntries, c->nSlices);
+    else {
+        if (c->pointCellsGrad() && !c->gValid) { int rc = s4f_build_point_stencil(c); if (rc) return rc; }
+        k_grad<false><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->gradSlicePtr(), c->gradCol(), c->gradLs(), c->eW.p, c->D.p, c->rV.p, c->gradD.p, c->N, c->ld, c->gradNE(), c->nSlices);
+    }
     c->launches++;
     if (c->B > 0) {
         k_grad_boundary<<<(c->B + 127) / 128, 128, 0, c->stream>>>(c->bFaceCell.p, c->bKind.p, c->bN.p, c->bSn.p, c->gradD.p, c->B, c->bOff(), c->ld);
@@ -875,8 +877,10 @@ int s4f_grad_calculated(s4fgpu_ctx* c, const double* X, double* gradOut) {
     }
     if (c->ctl.gradScheme == S4F_GRAD_GAUSS_LINEAR)
         k_grad<true><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eSf.p, c->eW.p, X, c->rV.p, gradOut, c->N, c->ld, c->nEntries, c->nSlices);
-    else
-        k_grad<false><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eLs.p, c->eW.p, X, c->rV.p, gradOut, c->N, c->ld, c->nEntries, c->nSlices);
+    else {
+        if (c->pointCellsGrad() && !c->gValid) { int rc = s4f_build_point_stencil(c); if (rc) return rc; }
+        k_grad<false><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->gradSlicePtr(), c->gradCol(), c->gradLs(), c->eW.p, X, c->rV.p, gradOut, c->N, c->ld, c->gradNE(), c->nSlices);
+    }
     c->launches++;
     if (c->B > 0) {
         k_grad_boundary<<<(c->B + 127) / 128, 128, 0, c->stream>>>(c->bFaceCell.p, c->bKind.p, c->bN.p, c->bSn.p, gradOut, c->B, c->bOff(), c->ld);

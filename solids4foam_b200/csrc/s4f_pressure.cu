@@ -162,8 +162,10 @@ int s4f_pressure_smooth(s4fgpu_ctx* c) {
     if ((rc = s4f_halo_exchange(c, c->sigmaHyd.p, 1))) return rc;
     if (c->ctl.gradScheme == S4F_GRAD_GAUSS_LINEAR)
         k_grad_scalar<true><<<gridR, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eSf.p, c->eW.p, c->sigmaHyd.p, c->rV.p, c->gradP.p, N, ld, c->nEntries, c->nSlices);
-    else
-        k_grad_scalar<false><<<gridR, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eLs.p, c->eW.p, c->sigmaHyd.p, c->rV.p, c->gradP.p, N, ld, c->nEntries, c->nSlices);
+    else {
+        if (c->pointCellsGrad() && !c->gValid) { int rcg = s4f_build_point_stencil(c); if (rcg) return rcg; }
+        k_grad_scalar<false><<<gridR, S4F_BLOCK, 0, c->stream>>>(c->gradSlicePtr(), c->gradCol(), c->gradLs(), c->eW.p, c->sigmaHyd.p, c->rV.p, c->gradP.p, N, ld, c->gradNE(), c->nSlices);
+    }
     c->launches++;
     if (B > 0) { k_grad_scalar_boundary<<<(B + 127) / 128, 128, 0, c->stream>>>(c->bFaceCell.p, c->bKind.p, c->bN.p, c->gradP.p, B, bOff, ld); c->launches++; }
     if ((rc = s4f_halo_exchange(c, c->gradP.p, 3))) return rc;

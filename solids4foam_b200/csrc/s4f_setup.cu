@@ -366,6 +366,90 @@ __global__ void k_vol_to_point_grad(const int* __restrict__ ptr, const int* __re
 }
 }  // namespace
 
+// [OF-ext] LeastSquaresVectors<centredCPCCellToCellStencilObject> ("pointCellsLeastSquares"): per cell the cells sharing a
+// point with it and the boundary faces at its points, 1/|d|^2 weights, ls = (inv(dd) - dd0) & d/|d|^2 -- see the oracle's
+// makePointCellsStencil for the restatement.  Laid out as SELL-32 rows of their own (about 26 entries per hex cell) that the
+// gradient kernels gather over exactly as they do over the face rows.
+int s4f_build_point_stencil(s4fgpu_ctx* c) {
+    const int N = c->N, F = c->F, B = c->B, nP = c->nPoints, bOff = c->bOff();
+    if (nP == 0) { c->err = "pointCellsLeastSquares needs the mesh points (s4fgpu_set_points)"; return 1; }
+    if (c->nRanks > 1) { c->err = "pointCellsLeastSquares is not available on decomposed meshes yet"; return 1; }
+    std::vector<std::vector<int>> pc(nP), pb(nP), cellPts(N);
+    auto add = [](std::vector<int>& v, int x) { if (std::find(v.begin(), v.end(), x) == v.end()) v.push_back(x); };
+    for (int f = 0; f < F + B; f++) for (int j = c->hFvPtr[f]; j < c->hFvPtr[f + 1]; j++) {
+        const int p = c->hFv[j];
+        const int o = f < F ? c->own[f] : c->faceCells[f - F];
+        add(pc[p], o); add(cellPts[o], p);
+        if (f < F) { add(pc[p], c->nei[f]); add(cellPts[c->nei[f]], p); }
+    }
+    for (int ip = 0; ip < c->nPatches; ip++) {
+        if (c->pKind[ip] == S4F_PATCH_PROCESSOR) continue;
+        for (int i = 0; i < c->pSize[ip]; i++) {
+            const int b = c->pStart[ip] + i;
+            for (int j = c->hFvPtr[F + b]; j < c->hFvPtr[F + b + 1]; j++) pb[c->hFv[j]].push_back(b);
+        }
+    }
+    std::vector<int> rowPtr(N + 1, 0), slot; std::vector<double> ls[3];
+    for (int i = 0; i < N; i++) {
+        std::vector<int> st;
+        for (int p : cellPts[i]) {
+            for (int cc : pc[p]) if (cc != i) add(st, cc);
+            for (int b : pb[p]) add(st, N + b);
+        }
+        std::sort(st.begin(), st.end());
+        double dd[6] = {0, 0, 0, 0, 0, 0};
+        if (!c->solD[0]) dd[0] += 1; if (!c->solD[1]) dd[3] += 1; if (!c->solD[2]) dd[5] += 1;
+        std::vector<double> dl(3 * st.size());
+        const double* Ci = &c->hC[3 * (size_t)i];
+        for (size_t k = 0; k < st.size(); k++) {
+            const double* x = st[k] < N ? &c->hC[3 * (size_t)st[k]] : &c->hCfB[3 * (size_t)(st[k] - N)];
+            const double d[3] = {x[0] - Ci[0], x[1] - Ci[1], x[2] - Ci[2]};
+            const double r = 1.0 / (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            dd[0] += r * d[0] * d[0]; dd[1] += r * d[0] * d[1]; dd[2] += r * d[0] * d[2];
+            dd[3] += r * d[1] * d[1]; dd[4] += r * d[1] * d[2]; dd[5] += r * d[2] * d[2];
+            for (int q = 0; q < 3; q++) dl[3 * k + q] = r * d[q];
+        }
+        double iv[6]; invSymm(dd, iv);
+        if (!c->solD[0]) iv[0] -= 1; if (!c->solD[1]) iv[3] -= 1; if (!c->solD[2]) iv[5] -= 1;
+        for (size_t k = 0; k < st.size(); k++) {
+            const double* d = &dl[3 * k];
+            slot.push_back(st[k] < N ? st[k] : bOff + (st[k] - N));
+            ls[0].push_back(iv[0] * d[0] + iv[1] * d[1] + iv[2] * d[2]);
+            ls[1].push_back(iv[1] * d[0] + iv[3] * d[1] + iv[4] * d[2]);
+            ls[2].push_back(iv[2] * d[0] + iv[4] * d[1] + iv[5] * d[2]);
+        }
+        rowPtr[i + 1] = (int)slot.size();
+    }
+    const int nSlices = c->nSlices;
+    std::vector<int> sp(nSlices + 1, 0);
+    for (int s = 0; s < nSlices; s++) {
+        int w = 0;
+        for (int r = s * 32; r < std::min(N, s * 32 + 32); r++) w = std::max(w, rowPtr[r + 1] - rowPtr[r]);
+        const long long next = (long long)sp[s] + 32LL * w;
+        if (next > 2147483647LL) { c->err = "mesh too large for int32 entry offsets (pointCellsLeastSquares rows)"; return 1; }
+        sp[s + 1] = (int)next;
+    }
+    const long long nE = sp[nSlices];
+    std::vector<int> hc((size_t)std::max<long long>(nE, 1), 0); std::vector<double> hl(3 * (size_t)std::max<long long>(nE, 1), 0.0);
+    for (int s = 0; s < nSlices; s++) {
+        const int w = (sp[s + 1] - sp[s]) / 32;
+        for (int lane = 0; lane < 32; lane++) {
+            const int P = s * 32 + lane;
+            for (int k = 0; k < w; k++) {
+                const size_t E = (size_t)sp[s] + 32 * (size_t)k + lane;
+                if (P >= N) { hc[E] = 0; continue; }
+                if (k >= rowPtr[P + 1] - rowPtr[P]) { hc[E] = P; continue; }           // padding: zero vector, own column
+                const size_t e = (size_t)rowPtr[P] + k;
+                hc[E] = slot[e];
+                for (int q = 0; q < 3; q++) hl[(size_t)q * nE + E] = ls[q][e];
+            }
+        }
+    }
+    S4F_CHECK_CUDA(c, c->gSlicePtr.upload(sp)); S4F_CHECK_CUDA(c, c->gCol.upload(hc)); S4F_CHECK_CUDA(c, c->gLs.upload(hl));
+    c->gNE = nE; c->gValid = true;
+    return 0;
+}
+
 int s4f_build_point_weights(s4fgpu_ctx* c, const double* points) {
     const int N = c->N, F = c->F, B = c->B, nP = c->nPoints, bOff = c->bOff();
     if (c->nRanks > 1) { c->err = "set_points: vol->point interpolation is not available on decomposed meshes yet"; return 1; }

@@ -188,7 +188,7 @@ def read_controls(case_dir: str, **overrides) -> K.Controls:
     kw["d2dt2Scheme"] = dict(steadyState=K.D2DT2_STEADY_STATE, Euler=K.D2DT2_EULER, backward=K.D2DT2_BACKWARD)[d2]
     grad = schemes.get("gradSchemes", {}).get("default", "leastSquares")
     grad = grad[0] if isinstance(grad, list) else grad
-    kw["gradScheme"] = K.GRAD_GAUSS_LINEAR if str(grad) == "Gauss" else K.GRAD_LEAST_SQUARES
+    kw["gradScheme"] = {"Gauss": K.GRAD_GAUSS_LINEAR, "pointCellsLeastSquares": K.GRAD_POINT_CELLS_LEAST_SQUARES}.get(str(grad), K.GRAD_LEAST_SQUARES)
     sol = read_foam_dict(os.path.join(case_dir, "system", "fvSolution"))
     field = "DD" if kw["solidModel"] in (K.MODEL_NONLIN_TL, K.MODEL_NONLIN_UL) else "D"
     sd = _lookup(sol.get("solvers", {}), field, {})
@@ -495,7 +495,7 @@ def write_case(case_dir: str, case: K.SolidCase, end_time: float = 1.0) -> None:
     _dict_file(os.path.join(case_dir, "constant", "g"), "g",
                f"dimensions      [0 1 -2 0 0 0 0];\nvalue           ({c.g[0]!r} {c.g[1]!r} {c.g[2]!r});", cls="uniformDimensionedVectorField")
     d2 = {K.D2DT2_STEADY_STATE: "steadyState", K.D2DT2_EULER: "Euler", K.D2DT2_BACKWARD: "backward"}[c.d2dt2Scheme]
-    grad = "Gauss linear" if c.gradScheme == K.GRAD_GAUSS_LINEAR else "leastSquares"
+    grad = {K.GRAD_GAUSS_LINEAR: "Gauss linear", K.GRAD_POINT_CELLS_LEAST_SQUARES: "pointCellsLeastSquares"}.get(c.gradScheme, "leastSquares")
     _dict_file(os.path.join(case_dir, "system", "fvSchemes"), "fvSchemes",
                f"d2dt2Schemes\n{{\n    default {d2};\n}}\nddtSchemes\n{{\n    default {d2};\n}}\ngradSchemes\n{{\n    default {grad};\n}}\n"
                "divSchemes\n{\n    default Gauss linear;\n}\nlaplacianSchemes\n{\n    default Gauss linear corrected;\n}\n"

@@ -239,3 +239,52 @@ def test_pressure_equation_with_zero_scale_factor_returns_the_explicit_cell_valu
     sb = o.get("sigma_b")
     trb = (sb[:, 0] + sb[:, 3] + sb[:, 5]) / 3.0
     assert np.allclose(trb, o.get("sigmaHyd")[c.mesh.faceCells], rtol=1e-9, atol=1e-9 * np.abs(trb).max())
+
+
+# ---------------------------------------------------------------------------------------------
+# pointCellsLeastSquares gradient (SURVEY 8f row f1, first half)
+# ---------------------------------------------------------------------------------------------
+def test_point_cells_least_squares_is_exact_for_linear_fields_and_passes_the_patch_test():
+    """[OF-ext] LeastSquaresGrad over the cell-point-cell stencil: exact for linear fields on distorted meshes (2-D with an
+    empty direction and 3-D); with it the patch test still returns the constant strain of patchTest/README.md:102-113."""
+    G = np.array([[0.01, 0.02, -0.01], [0.03, -0.01, 0.02], [0.005, 0.0, 0.01]])
+    pmap = lambda p: p + 0.04 * np.sin(3.0 * p[:, [1, 2, 0]])
+    c3 = cases.neo_hookean_cantilever(5, 4, 3, general=True, L=2.0, solidModel=K.MODEL_NONLIN_TL_TOTAL_DISP,
+                                      gradScheme=K.GRAD_POINT_CELLS_LEAST_SQUARES)
+    c3.mesh = M.hex_box_general(5, 4, 3, 2.0, 1.0, 1.0, names=("fixed", "loaded", "yMin", "yMax", "zMin", "zMax"), point_map=pmap)
+    for c, g in ((cases.patch_test(n=5, gradScheme=K.GRAD_POINT_CELLS_LEAST_SQUARES), G * np.array([[1, 1, 0], [1, 1, 0], [0, 0, 0]])), (c3, G)):
+        o = OracleSolid(c)
+        m = c.mesh
+        F = m.nInternalFaces
+        lin = lambda X: 0.1 + X @ g.T
+        o.set("D", lin(m.C)); o.set("D_b", lin(m.Cf[F:]))
+        o.op_grad()
+        assert np.abs(o.get("gradD").reshape(-1, 3, 3) - g.T).max() < 1e-15
+    o = OracleSolid(cases.patch_test(n=4, gradScheme=K.GRAD_POINT_CELLS_LEAST_SQUARES))
+    assert o.evolve()["converged"]
+    gD = o.get("gradD").reshape(-1, 3, 3)
+    eps = 0.5 * (gD + gD.transpose(0, 2, 1))
+    assert np.abs(eps[:, 0, 0] - 2e-6).max() < 1e-13 and np.abs(eps[:, 1, 1] - 6e-6).max() < 1e-13 and np.abs(eps[:, 0, 1] - 4e-6).max() < 1e-13
+
+
+def test_point_cells_stencil_size_and_plate_hole_accuracy():
+    """An interior hex cell sees 26 point neighbours; on the plate-hole case (C1) the scheme reaches the Kirsch solution at the
+    discretisation level the face-neighbour scheme does."""
+    c = cases.neo_hookean_cantilever(5, 5, 5, general=True, L=1.0, solidModel=K.MODEL_NONLIN_TL_TOTAL_DISP, gradScheme=K.GRAD_POINT_CELLS_LEAST_SQUARES)
+    o = OracleSolid(c)
+    # stencil size through the gradient of an indicator (the boundary values stay as they are: difference of two gradients)
+    centre = int(np.argmin(np.linalg.norm(c.mesh.C - 0.5, axis=1)))
+    D = np.zeros((c.mesh.nCells, 3))
+    o.set("D", D); o.op_grad(); g0 = o.get("gradD")
+    D[centre, 0] = 1.0
+    o.set("D", D); o.op_grad()
+    touched = np.nonzero(np.abs(o.get("gradD") - g0).sum(axis=1) > 0)[0]
+    assert len(touched) == 27                                   # the cell itself and its 26 point neighbours
+    errs = {}
+    for scheme in (K.GRAD_LEAST_SQUARES, K.GRAD_POINT_CELLS_LEAST_SQUARES):
+        cp = cases.plate_hole(gradScheme=scheme)
+        op = OracleSolid(cp)
+        assert op.evolve()["converged"]
+        sa = cases.kirsch_stress(cp.mesh.C)
+        errs[scheme] = rel_l2(op.get("sigma")[:, [0, 1, 3]], sa[:, [0, 1, 3]])
+    assert errs[K.GRAD_POINT_CELLS_LEAST_SQUARES] < 1.5 * errs[K.GRAD_LEAST_SQUARES] and errs[K.GRAD_POINT_CELLS_LEAST_SQUARES] < 0.1, errs
