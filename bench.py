@@ -32,7 +32,16 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+# stdout carries the one JSON line only: library chatter written to file descriptor 1 (NCCL's version banner) goes to stderr
+_STDOUT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_STDOUT_FD, (json.dumps(line) + "\n").encode())
 
 FULL = (800, 100, 100)      # 8.0 M cells: the configuration the metric is quoted on
 CPU_SAMPLE = (400, 50, 50)  # 1.0 M cells: bounded CPU sample of the same case
@@ -167,7 +176,7 @@ def main():
                                              "counts grow with mesh size)"),
                     e2e=dict(value=val, unit="iter/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                     note="the reference solids4Foam binary cannot be built here (needs OpenFOAM); this is the repo's CPU oracle")
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ---------------------------------------------------------------- our arm (CUDA)
@@ -309,7 +318,7 @@ def main():
                                            f"iterations after 3 warm-up in {dt:.1f} s, scaled by {scale:.4f} to the full workload; "
                                            f"{inner:.0f} DIC-PCG iterations per outer iteration (3 components) on the sample against "
                                            f"{inner_per_outer:.0f} GAMG-PCG iterations on the GPU at full size")
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
