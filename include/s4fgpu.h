@@ -51,7 +51,10 @@ enum {
     S4F_MODEL_LIN_GEOM_TOTAL_DISP = 0,   /* SM/linGeomTotalDispSolid/linGeomTotalDispSolid.C:111-232 */
     S4F_MODEL_NONLIN_TL_TOTAL_DISP = 1,  /* SM/nonLinGeomTotalLagTotalDispSolid/...C:173-281 */
     S4F_MODEL_NONLIN_TL = 2,             /* SM/nonLinGeomTotalLagSolid/nonLinGeomTotalLagSolid.C:125-260 (solves DD) */
-    S4F_MODEL_NONLIN_UL = 3              /* SM/nonLinGeomUpdatedLagSolid/...C:159-273 */
+    S4F_MODEL_NONLIN_UL = 3,             /* SM/nonLinGeomUpdatedLagSolid/...C:159-273 */
+    S4F_MODEL_UNS_LIN_GEOM = 4           /* SM/unsLinGeomSolid/unsLinGeomSolid.C:100-175 ("unsLinearGeometry"): face stresses from face
+                                            gradients built on the vertex displacements, fvc::div(mesh().Sf() & sigmaf);
+                                            linearElastic, needs s4fgpu_set_points, single rank */
 };
 
 /* mechanicalLaw (constant/mechanicalProperties "type") */
@@ -113,7 +116,9 @@ enum {
     S4F_FIELD_RHO = 23,          /* scalar [N]  density field of the updated-Lagrangian model (rho_ = rho_.oldTime()/relJ_) */
     S4F_FIELD_DD_B = 24,         /* vector [B]  boundary values of DD */
     S4F_FIELD_SIGMA_HYD = 25,    /* scalar [N]  hydrostatic stress of the law (mechanicalLaw::sigmaHyd()) */
-    S4F_FIELD_GRAD_SIGMA_HYD = 26 /* vector [N] */
+    S4F_FIELD_GRAD_SIGMA_HYD = 26, /* vector [N] */
+    S4F_FIELD_SIGMA_F = 27,      /* symmTensor [F+B]  face stress sigmaf of the uns* model (internal faces, then boundary faces) */
+    S4F_FIELD_GRAD_D_F = 28      /* tensor [F+B]      face gradient gradDf */
 };
 
 /* ---- parameter blocks ---------------------------------------------------------------------- */

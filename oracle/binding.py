@@ -40,6 +40,7 @@ def lib():
         L.s4fo_get_ls_vectors.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.s4fo_table_lookup.argtypes = [C.POINTER(K.Law), C.c_double]
         L.s4fo_table_lookup.restype = C.c_double
+        L.s4fo_uns_grad_from_points.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         _LIB = L
     return _LIB
 
@@ -140,6 +141,11 @@ class OracleSolid:
         st = K.Stats()
         self._check(self.L.s4fo_op_solve(self.h, K._dptr(psi), K._dptr(source), C.byref(st)))
         return psi, st.as_dict()
+
+    def uns_grad_from_points(self, pointD: np.ndarray) -> None:
+        """unsLinGeomSolid gradients (fvcGradf.C) from given vertex displacements, skipping the vol->point interpolation."""
+        pd = np.ascontiguousarray(pointD, dtype=np.float64)
+        self._check(self.L.s4fo_uns_grad_from_points(self.h, K._dptr(pd)))
 
     def ls_vectors(self):
         m = self.case.mesh

@@ -114,6 +114,7 @@ struct SolverPerf { double initRes, finalRes; int nIter; };
 }  // namespace
 struct s4f_oracle;
 namespace { void updateSigmaHydSmoothed(s4f_oracle& o, double impK); }
+extern "C" int s4fo_interpolate_to_points_impl(s4f_oracle* o, const std::vector<double>& X, double* out);
 
 struct s4f_oracle {
     std::string err;
@@ -142,6 +143,7 @@ struct s4f_oracle {
     // fvm::d2dt2(rho, DD) + fvc::d2dt2(rho, D.oldTime()) reach, and the density field with its old times
     dvec Dooooo, DDo, DDoo, DDooo, DDoooo, rho, rhoO, rhoOO;
     dvec gradSigmaHyd, sigmaHydExp;     // pressure smoothing (mechanicalLaw.C:1366-1476)
+    dvec pointD, gradDf, sigmaf;        // unsLinGeomSolid: vertex displacements [3 nPoints], face gradient [9 (F+B)], face stress [6 (F+B)]
     SolverPerf perfP{0, 0, 0};
     // polyMesh points/faces for vol->point interpolation
     int nPoints = 0;
@@ -175,6 +177,7 @@ struct s4f_oracle {
     int NB() const { return N + B; }
     bool incremental() const { return ctl.solidModel == S4F_MODEL_NONLIN_TL || ctl.solidModel == S4F_MODEL_NONLIN_UL; }
     bool UL() const { return ctl.solidModel == S4F_MODEL_NONLIN_UL; }
+    bool uns() const { return ctl.solidModel == S4F_MODEL_UNS_LIN_GEOM; }
     const dvec& gradForLaw() const { return incremental() ? gradDtot : gradD; }   // the registered "grad(D)"
 };
 
@@ -283,7 +286,15 @@ void tractionSnGrad(const s4f_oracle& o, int b, double* g) {
     const double impK = o.impK[N + b], rImpK = 1.0 / impK;
     const double* gD = &o.gradD[9 * (N + b)];
     const double* sg = &o.sigma[6 * (N + b)];
-    if (o.ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP) {
+    if (o.uns()) {
+        // unsLinGeomSolid::tractionBoundarySnGrad, unsLinGeomSolid.C:193-230: the same expression on the FACE fields
+        // sigmaf_ and gradDf_ of the patch
+        const double* gf = &o.gradDf[9 * (size_t)(o.F + b)];
+        double M[9]; S2T(&o.sigmaf[6 * (size_t)(o.F + b)], M);
+        for (int i = 0; i < 9; i++) M[i] -= impK * gf[i];
+        double nM[3]; vT(n, M, nM);
+        for (int i = 0; i < 3; i++) g[i] = ((t[i] - n[i] * p) - nM[i]) * rImpK;
+    } else if (o.ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP) {
         // ((traction - n*pressure) - (n & (pSigma - impK*pGradD)))*rImpK
         double M[9]; S2T(sg, M);
         for (int i = 0; i < 9; i++) M[i] -= impK * gD[i];
@@ -484,6 +495,141 @@ void gradCalculated(const s4f_oracle& o, const dvec& X, dvec& g) {
         for (int q = 0; q < 9; q++) gb[q] = g[9 * P + q];
         double ng[3]; vT(n, gb, ng);
         for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) gb[3 * i + j] += n[i] * (sn[j] - ng[j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// unsLinGeomSolid: gradients built on the vertex displacements (NUM/fvc/fvcGradf.C)
+// ------------------------------------------------------------------------------------------------
+// fsGrad, fvcGradf.C:170-232 (internal faces) / :236-298 (patch faces) / :359-440 (patch fGrad): the in-plane gradient of a
+// face from the edge-centre values, grad = (1/|Sf|) sum_edges Le fe, Le = (e - n (n & e)) ^ n, fe = (pf_start + pf_end)/2
+void unsFaceTangentialGrad(const s4f_oracle& o, int f, double* T) {
+    for (int q = 0; q < 9; q++) T[q] = 0;
+    const double mag = o.magSf[f];
+    double n[3] = {o.Sf[3 * (size_t)f] / mag, o.Sf[3 * (size_t)f + 1] / mag, o.Sf[3 * (size_t)f + 2] / mag};
+    const int a = o.fvPtr[f], m = o.fvPtr[f + 1] - a;
+    for (int i = 0; i < m; i++) {
+        const int v0 = o.fv[a + i], v1 = o.fv[a + (i + 1) % m];
+        const double* p0 = &o.points[3 * (size_t)v0]; const double* p1 = &o.points[3 * (size_t)v1];
+        double e[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+        const double ne = dot3(n, e);
+        for (int q = 0; q < 3; q++) e[q] -= n[q] * ne;
+        const double Le[3] = {e[1] * n[2] - e[2] * n[1], e[2] * n[0] - e[0] * n[2], e[0] * n[1] - e[1] * n[0]};
+        for (int j = 0; j < 3; j++) {
+            const double fe = 0.5 * (o.pointD[3 * (size_t)v0 + j] + o.pointD[3 * (size_t)v1 + j]);
+            for (int i2 = 0; i2 < 3; i2++) T[3 * i2 + j] += Le[i2] * fe;
+        }
+    }
+    for (int q = 0; q < 9; q++) T[q] /= mag;
+}
+
+// one face's contribution to fvc::grad(vf, pf), fvcGradf.C:497-566 (:603-668 on patches): triangles about the vertex average,
+// G = sum_t St ttcf (ttcf = (pf_a + pf_b + cf)/3), Vf = sum_t St & Ct; a triangular face is taken whole
+void unsFaceGauss(const s4f_oracle& o, int f, double* G, double& Vf) {
+    for (int q = 0; q < 9; q++) G[q] = 0;
+    Vf = 0;
+    const int a = o.fvPtr[f], m = o.fvPtr[f + 1] - a;
+    auto P = [&](int i) { return &o.points[3 * (size_t)o.fv[a + i]]; };
+    auto U = [&](int i) { return &o.pointD[3 * (size_t)o.fv[a + i]]; };
+    if (m == 3) {
+        const double e1[3] = {P(1)[0] - P(0)[0], P(1)[1] - P(0)[1], P(1)[2] - P(0)[2]}, e2[3] = {P(2)[0] - P(0)[0], P(2)[1] - P(0)[1], P(2)[2] - P(0)[2]};
+        const double S[3] = {0.5 * (e1[1] * e2[2] - e1[2] * e2[1]), 0.5 * (e1[2] * e2[0] - e1[0] * e2[2]), 0.5 * (e1[0] * e2[1] - e1[1] * e2[0])};
+        double c[3], u[3];
+        for (int q = 0; q < 3; q++) { c[q] = (P(0)[q] + P(1)[q] + P(2)[q]) / 3.0; u[q] = (U(0)[q] + U(1)[q] + U(2)[q]) / 3.0; }
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) G[3 * i + j] = S[i] * u[j];
+        Vf = dot3(S, c);
+        return;
+    }
+    double cp[3] = {0, 0, 0}, cf[3] = {0, 0, 0};
+    for (int i = 0; i < m; i++) for (int q = 0; q < 3; q++) { cp[q] += P(i)[q]; cf[q] += U(i)[q]; }
+    for (int q = 0; q < 3; q++) { cp[q] /= m; cf[q] /= m; }
+    for (int i = 0; i < m; i++) {
+        const double* pa = P(i); const double* pb = P((i + 1) % m);
+        const double* ua = U(i); const double* ub = U((i + 1) % m);
+        const double ra[3] = {pa[0] - cp[0], pa[1] - cp[1], pa[2] - cp[2]}, rb[3] = {pb[0] - cp[0], pb[1] - cp[1], pb[2] - cp[2]};
+        const double St[3] = {0.5 * (ra[1] * rb[2] - ra[2] * rb[1]), 0.5 * (ra[2] * rb[0] - ra[0] * rb[2]), 0.5 * (ra[0] * rb[1] - ra[1] * rb[0])};
+        double Ct[3], tt[3];
+        for (int q = 0; q < 3; q++) { Ct[q] = (cp[q] + pa[q] + pb[q]) / 3.0; tt[q] = (ua[q] + ub[q] + cf[q]) / 3.0; }
+        for (int i2 = 0; i2 < 3; i2++) for (int j = 0; j < 3; j++) G[3 * i2 + j] += St[i2] * tt[j];
+        Vf += dot3(St, Ct);
+    }
+}
+
+void gradInterior(const s4f_oracle& oc, const dvec& X, dvec& g);
+
+// mechanical().interpolate(D, pointD, false); mechanical().grad(D, pointD, gradD, gradDf)   (unsLinGeomSolid.C:146-150,
+// mechanicalModel.C:722-731): gradD = fvc::grad(D, pointD) (fvcGradf.C:442-800), gradDf = fvc::fGrad(D, pointD) =
+// fsGrad + n*fvc::snGrad(D) (fvcGradf.C:104-107; snGrad(D) corrected: the non-orthogonal part takes fvc::grad(D) of the gradScheme)
+void unsUpdateGradients(s4f_oracle& o, bool interpolate = true) {
+    const int N = o.N, F = o.F, B = o.B;
+    if (interpolate) {
+        o.pointD.assign(3 * (size_t)o.nPoints, 0.0);
+        s4fo_interpolate_to_points_impl(&o, o.D, o.pointD.data());
+    }
+    // ---- gradD = fvc::grad(D, pointD)
+    dvec g(9 * (size_t)(N + B), 0.0), V3(N, 0.0);
+    for (int f = 0; f < F + B; f++) {
+        double G[9], Vf; unsFaceGauss(o, f, G, Vf);
+        const int P = f < F ? o.own[f] : o.faceCells[f - F];
+        for (int q = 0; q < 9; q++) g[9 * (size_t)P + q] += G[q];
+        V3[P] += Vf;
+        if (f < F) { for (int q = 0; q < 9; q++) g[9 * (size_t)o.nei[f] + q] -= G[q]; V3[o.nei[f]] -= Vf; }
+    }
+    // the faces of empty patches are not mirrored (2-D cases): they are planar with normals along the empty direction, so
+    // their share of sum St & Ct is the cell volume (prismatic cells) and their share of the gradient sum cancels front to back
+    const int nEmpty = (o.solD[0] ? 0 : 1) + (o.solD[1] ? 0 : 1) + (o.solD[2] ? 0 : 1);
+    for (int c = 0; c < N; c++) V3[c] += nEmpty * o.V[c];
+    for (int c = 0; c < N; c++) for (int q = 0; q < 9; q++) g[9 * (size_t)c + q] /= (V3[c] / 3.0);
+    // patches: the in-plane gradient of the patch face (fGrad(polyPatch, ppf) :693-718), then the normal gradient of the
+    // boundary condition (:767-781; its snGrad() reads the registered grad(D), still the previous one)
+    for (int p = 0; p < o.nPatches; p++) for (int i = 0; i < o.pSize[p]; i++) {
+        const int b = o.pStart[p] + i;
+        double n[3], k[3], delta; patchGeom(o, b, n, k, delta);
+        double* gb = &g[9 * (size_t)(N + b)];
+        unsFaceTangentialGrad(o, F + b, gb);
+        double sn[3]; bcSnGrad(o, p, b, o.gradD, sn);
+        double ng[3]; vT(n, gb, ng);
+        for (int a = 0; a < 3; a++) for (int j = 0; j < 3; j++) gb[3 * a + j] += n[a] * (sn[j] - ng[j]);
+    }
+    o.gradD.swap(g);
+    // ---- gradDf = fsGrad(D, pointD) + n*snGrad(D)
+    dvec gLS;
+    if (o.nonOrth) gradInterior(o, o.D, gLS);
+    o.gradDf.assign(9 * (size_t)(F + B), 0.0);
+    for (int f = 0; f < F; f++) {
+        double* T = &o.gradDf[9 * (size_t)f];
+        unsFaceTangentialGrad(o, f, T);
+        const int P = o.own[f], Nn = o.nei[f];
+        const double mag = o.magSf[f];
+        double sn[3];
+        for (int j = 0; j < 3; j++) sn[j] = o.nod[f] * (o.D[3 * (size_t)Nn + j] - o.D[3 * (size_t)P + j]);
+        if (o.nonOrth) {
+            double gf[9]; for (int q = 0; q < 9; q++) gf[q] = o.w[f] * gLS[9 * (size_t)P + q] + (1 - o.w[f]) * gLS[9 * (size_t)Nn + q];
+            double cg[3]; vT(&o.corr[3 * (size_t)f], gf, cg);
+            for (int j = 0; j < 3; j++) sn[j] += cg[j];
+        }
+        for (int a = 0; a < 3; a++) for (int j = 0; j < 3; j++) T[3 * a + j] += (o.Sf[3 * (size_t)f + a] / mag) * sn[j];
+    }
+    for (int p = 0; p < o.nPatches; p++) for (int i = 0; i < o.pSize[p]; i++) {
+        const int b = o.pStart[p] + i;
+        double n[3], k[3], delta; patchGeom(o, b, n, k, delta);
+        double* T = &o.gradDf[9 * (size_t)(F + b)];
+        unsFaceTangentialGrad(o, F + b, T);
+        double sn[3]; bcSnGrad(o, p, b, o.gradD, sn);        // the patch snGrad() with the gradD just assigned
+        for (int a = 0; a < 3; a++) for (int j = 0; j < 3; j++) T[3 * a + j] += n[a] * sn[j];
+    }
+}
+
+// linearElastic::correct(surfaceSymmTensorField&), linearElastic.C:342-370: sigmaf = 2 mu epsilonf + lambda tr(epsilonf) I + sigma0f
+void unsLawFaces(s4f_oracle& o) {
+    const int nf = o.F + o.B;
+    o.sigmaf.assign(6 * (size_t)nf, 0.0);
+    for (int f = 0; f < nf; f++) {
+        double e[6]; symm(&o.gradDf[9 * (size_t)f], e);
+        const double tr = trS(e);
+        double* s = &o.sigmaf[6 * (size_t)f];
+        for (int q = 0; q < 6; q++) s[q] = 2.0 * o.law.mu * e[q] + o.law.sigma0[q];
+        s[0] += o.law.lambda * tr; s[3] += o.law.lambda * tr; s[5] += o.law.lambda * tr;
     }
 }
 
@@ -898,7 +1044,7 @@ void assembleMatrix(s4f_oracle& o) {
 
 void assembleSource(s4f_oracle& o) {
     const int N = o.N, F = o.F, B = o.B;
-    const bool TL = (o.ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP);
+    const bool TL = (o.ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP && !o.uns());
     o.source.assign(3 * N, 0.0);
     dvec& s = o.source;
     // d2dt2 old-time terms
@@ -932,6 +1078,15 @@ void assembleSource(s4f_oracle& o) {
         if (TL) { double t[9]; mulTT(&o.Finv[9 * c], sg, t); for (int q = 0; q < 9; q++) T[9 * c + q] = o.Jt[c] * t[q]; }
         else for (int q = 0; q < 9; q++) T[9 * c + q] = sg[q];
     }
+    if (o.uns()) {
+        // unsLinGeomSolid.C:129: fvc::div(mesh().Sf() & sigmaf_): the face stress itself, no interpolation
+        for (int f = 0; f < F + B; f++) {
+            double fl[3]; SvS(&o.sigmaf[6 * (size_t)f], &o.Sf[3 * (size_t)f], fl);      // Sf & sigmaf (symmetric)
+            const int P = f < F ? o.own[f] : o.faceCells[f - F];
+            for (int q = 0; q < 3; q++) s[3 * P + q] += fl[q];
+            if (f < F) for (int q = 0; q < 3; q++) s[3 * o.nei[f] + q] -= fl[q];
+        }
+    } else {
     forAllInternalFaces(o, [&](int f) {
         int P = o.own[f], Nn = o.nei[f];
         double wf = o.w[f], Tf[9];
@@ -943,12 +1098,13 @@ void assembleSource(s4f_oracle& o) {
         double fl[3]; vT(&o.Sf[3 * (F + b)], &T[9 * (N + b)], fl);
         for (int q = 0; q < 3; q++) s[3 * o.faceCells[b] + q] += fl[q];
     }
+    }
     // + V*rho*g  (updated Lagrangian: the rho_ field, already in hist)
     if (!o.UL()) for (int c = 0; c < N; c++) for (int q = 0; q < 3; q++) s[3 * c + q] += o.V[c] * o.law.rho * o.ctl.g[q];
     // + V*stabilisation: RhieChow, SM/solidModel/momentumStabilisation/momentumStabilisation.C:112-114
     // (gamma = scaleFactor*impK), :119 (linear interpolate), :198-206 (zero on non-coupled boundaries),
     // :210-217  fvc::laplacian(gammaf, D) - fvc::div(gammaf*(Sf & interpolate(gradD)))
-    if (o.ctl.stabilisation == S4F_STAB_RHIE_CHOW) {
+    if (o.ctl.stabilisation == S4F_STAB_RHIE_CHOW && !o.uns()) {      // the uns momentum equation has no stabilisation term (:124-131)
         const double sf = o.ctl.stabScaleFactor;
         forAllInternalFaces(o, [&](int f) {
             int P = o.own[f], Nn = o.nei[f];
@@ -1312,9 +1468,15 @@ void outerIteration(s4f_oracle& o, int iCorr) {
     bcEvaluate(o);                               // D.correctBoundaryConditions()
     relaxField(o, iCorr);
     updateTotals(o, true, false);
+    if (o.uns()) {                               // unsLinGeomSolid.C:146-157
+        unsUpdateGradients(o);                   // interpolate(D, pointD); grad(D, pointD, gradD, gradDf)
+        unsLawFaces(o);                          // mechanical().correct(sigmaf)
+        lawCorrect(o);                           // mechanical().correct(sigma)
+        return;
+    }
     calcGrad(o);                                 // mechanical().grad(D, gradD)
     updateTotals(o, false, true);
-    if (o.ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP) updateKinematics(o);
+    if (o.ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP && !o.uns()) updateKinematics(o);
     lawCorrect(o);                               // mechanical().correct(sigma)
 }
 
@@ -1324,6 +1486,7 @@ void allocFields(s4f_oracle& o) {
     z(o.D, 3); z(o.Dprev, 3); z(o.Dold, 3); z(o.DoldOld, 3); z(o.gradD, 9); z(o.gradDold, 9); z(o.sigma, 6); z(o.sigmaOld, 6);
     z(o.Dtot, 3); z(o.gradDtot, 9);
     z(o.epsilon, 6); z(o.sigmaHyd, 1);
+    if ((int)o.sigmaf.size() != 6 * (o.F + o.B)) { o.sigmaf.assign(6 * (size_t)(o.F + o.B), 0.0); o.gradDf.assign(9 * (size_t)(o.F + o.B), 0.0); }
     z(o.Dooo, 3); z(o.Doooo, 3); z(o.Dooooo, 3); z(o.DDo, 3); z(o.DDoo, 3); z(o.DDooo, 3); z(o.DDoooo, 3);
     if ((int)o.rho.size() != n) { o.rho.assign(n, o.law.rho); o.rhoO = o.rho; o.rhoOO = o.rho; }
     if ((int)o.Ft.size() != 9 * n) {
@@ -1396,6 +1559,8 @@ int s4fo_set_geometry(s4f_oracle* o, const double* C, const double* V, const dou
     o->corr.assign(corr, corr + 3 * FB); o->CnbrB.assign(CnbrB, CnbrB + 3 * o->B);
     const bool again = !o->impK.empty() && (int)o->D.size() == 3 * o->NB();   // mesh motion: fields, BC data and history stay
     o->psValid = false;
+    o->nonOrth = false;
+    for (size_t i = 0; i < o->corr.size(); i++) if (std::fabs(o->corr[i]) > 1e-12) { o->nonOrth = true; break; }
     makeLeastSquaresVectors(*o);
     allocFields(*o);
     if (again) setupImpK(*o);
@@ -1437,6 +1602,18 @@ int s4fo_set_points(s4f_oracle* o, int nPoints, const double* points, const int*
 // inverse-distance weights of enhancedVolPointInterpolation.C:165-198 for points off the patches, interpolateBoundaryField
 // :262-330 with the weights of :201-245 from the boundary-face values for patch points, then pointConstraints::constrain
 // ([OF-ext]: symmetryPlane points lose their normal component, transform(I - nn, pf)).
+int s4fo_interpolate_to_points(s4f_oracle* o, int field, int mode, double* out);
+int s4fo_interpolate_to_points_impl(s4f_oracle* o, const dvec& Xf, double* out) {
+    // PATCH mode on an explicit field (used by the uns model every outer iteration)
+    dvec save; const bool inc = o->incremental();
+    (void)inc;
+    dvec& slot = o->incremental() ? o->Dtot : o->D;
+    const bool same = (&Xf == &slot);
+    if (!same) { save = slot; slot = Xf; }
+    const int rc = s4fo_interpolate_to_points(o, S4F_FIELD_D, S4F_POINT_INTERP_PATCH, out);
+    if (!same) slot = save;
+    return rc;
+}
 int s4fo_interpolate_to_points(s4f_oracle* o, int field, int mode, double* out) {
     if (o->nPoints == 0) { o->err = "interpolate_to_points: call set_points first"; return 1; }
     const dvec* X = nullptr; const dvec* G = nullptr;
@@ -1544,6 +1721,8 @@ static dvec* fieldPtr(s4f_oracle* o, int field, int& ncomp, int& off, int& count
         case S4F_FIELD_TRACTION_GRADIENT_B: ncomp = 3; count = B; return &o->tracGrad;
         case S4F_FIELD_RHO: ncomp = 1; return &o->rho;
         case S4F_FIELD_SIGMA_HYD: ncomp = 1; return &o->sigmaHyd;
+        case S4F_FIELD_SIGMA_F: ncomp = 6; count = F + B; return &o->sigmaf;
+        case S4F_FIELD_GRAD_D_F: ncomp = 9; count = F + B; return &o->gradDf;
         case S4F_FIELD_GRAD_SIGMA_HYD: ncomp = 3; return &o->gradSigmaHyd;
         case S4F_FIELD_DD_B: ncomp = 3; off = N; count = B; return o->incremental() ? &o->D : nullptr;
     }
@@ -1567,6 +1746,12 @@ int s4fo_initialise(s4f_oracle* o) {
     bcUpdateCoeffs(*o);
     bcEvaluate(*o);
     o->Dprev = o->D;
+    if (o->uns()) {       // unsLinGeomSolid.C:86-89
+        if (o->nPoints == 0) { o->err = "unsLinearGeometry needs the mesh points (set_points)"; return 1; }
+        unsUpdateGradients(*o);
+        assembleMatrix(*o);
+        return 0;
+    }
     calcGrad(*o);
     updateTotals(*o, false, true);
     if (o->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP) updateKinematics(*o);
@@ -1638,7 +1823,7 @@ int s4fo_update_total_fields(s4f_oracle* o) {
     return 0;
 }
 
-int s4fo_op_grad(s4f_oracle* o) { calcGrad(*o); updateTotals(*o, false, true); if (o->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP) updateKinematics(*o); return 0; }
+int s4fo_op_grad(s4f_oracle* o) { if (o->uns()) { unsUpdateGradients(*o); unsLawFaces(*o); return 0; } calcGrad(*o); updateTotals(*o, false, true); if (o->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP) updateKinematics(*o); return 0; }
 int s4fo_op_correct(s4f_oracle* o) { lawCorrect(*o); return 0; }
 int s4fo_op_assemble(s4f_oracle* o) { bcUpdateCoeffs(*o); assembleMatrix(*o); assembleSource(*o); return 0; }
 int s4fo_op_amul(s4f_oracle* o, int cmpt, const double* x, double* y) {
@@ -1650,6 +1835,12 @@ int s4fo_op_solve(s4f_oracle* o, double* psi, const double* source, s4fgpu_stats
     if (!o->matrixValid) assembleMatrix(*o);
     solveSegregated(*o, psi, source);
     if (st) for (int q = 0; q < 3; q++) { st->initialResidual[q] = o->perf[q].initRes; st->finalResidual[q] = o->perf[q].finalRes; st->nIterations[q] = o->perf[q].nIter; }
+    return 0;
+}
+// unsLinGeomSolid gradients from GIVEN vertex displacements (tests: the gradient formulas of fvcGradf.C on their own)
+int s4fo_uns_grad_from_points(s4f_oracle* o, const double* pointD) {
+    o->pointD.assign(pointD, pointD + 3 * (size_t)o->nPoints);
+    unsUpdateGradients(*o, false); unsLawFaces(*o);
     return 0;
 }
 // least-squares vectors for inspection (lsP [3(F+B)], lsN [3F])

@@ -21,7 +21,7 @@ from .mesh import FvMesh, PROCESSOR
 
 # ---- enums (include/s4fgpu.h) ---------------------------------------------------------------
 BC_FIXED_DISPLACEMENT, BC_SOLID_TRACTION, BC_SOLID_SYMMETRY, BC_PROCESSOR = 0, 1, 2, 3
-MODEL_LIN_GEOM_TOTAL_DISP, MODEL_NONLIN_TL_TOTAL_DISP, MODEL_NONLIN_TL, MODEL_NONLIN_UL = 0, 1, 2, 3
+MODEL_LIN_GEOM_TOTAL_DISP, MODEL_NONLIN_TL_TOTAL_DISP, MODEL_NONLIN_TL, MODEL_NONLIN_UL, MODEL_UNS_LIN_GEOM = 0, 1, 2, 3, 4
 LAW_LINEAR_ELASTIC, LAW_NEO_HOOKEAN_ELASTIC, LAW_NEO_HOOKEAN_MISES_PLASTIC, LAW_LINEAR_ELASTIC_MISES_PLASTIC = 0, 1, 2, 3
 GRAD_LEAST_SQUARES, GRAD_GAUSS_LINEAR, GRAD_POINT_CELLS_LEAST_SQUARES = 0, 1, 2
 D2DT2_STEADY_STATE, D2DT2_EULER, D2DT2_BACKWARD = 0, 1, 2
@@ -33,13 +33,13 @@ POINT_INTERP_PATCH, POINT_INTERP_GRAD = 0, 1
 
 FIELD = dict(D=0, D_old=1, D_oldOld=2, gradD=3, sigma=4, D_b=5, gradD_b=6, sigma_b=7, source=8, diag=9,
              upper=10, epsilonPEq=11, sigmaY=12, bEbar=13, DLambda=14, J=15, F=16, gradD_old=17,
-             DEpsilonP=18, tractionGradient_b=19, epsilonP=20, DD=21, gradDD=22, rho=23, DD_b=24, sigmaHyd=25, gradSigmaHyd=26)
+             DEpsilonP=18, tractionGradient_b=19, epsilonP=20, DD=21, gradDD=22, rho=23, DD_b=24, sigmaHyd=25, gradSigmaHyd=26, sigmaf=27, gradDf=28)
 # (ncomp, 'N' | 'B' | 'F')
 FIELD_SHAPE = dict(D=(3, "N"), D_old=(3, "N"), D_oldOld=(3, "N"), gradD=(9, "N"), sigma=(6, "N"), D_b=(3, "B"),
                    gradD_b=(9, "B"), sigma_b=(6, "B"), source=(3, "N"), diag=(3, "N"), upper=(1, "F"),
                    epsilonPEq=(1, "N"), sigmaY=(1, "N"), bEbar=(6, "N"), DLambda=(1, "N"), J=(1, "N"), F=(9, "N"),
                    gradD_old=(9, "N"), DEpsilonP=(6, "N"), tractionGradient_b=(3, "B"), epsilonP=(6, "N"),
-                   DD=(3, "N"), gradDD=(9, "N"), rho=(1, "N"), DD_b=(3, "B"), sigmaHyd=(1, "N"), gradSigmaHyd=(3, "N"))
+                   DD=(3, "N"), gradDD=(9, "N"), rho=(1, "N"), DD_b=(3, "B"), sigmaHyd=(1, "N"), gradSigmaHyd=(3, "N"), sigmaf=(6, "FB"), gradDf=(9, "FB"))
 
 MODEL_NAMES = {
     # reference TypeName -> (gpu TypeName registered by the plugin, enum)
@@ -47,6 +47,7 @@ MODEL_NAMES = {
     "nonLinearGeometryTotalLagrangianTotalDisplacement": MODEL_NONLIN_TL_TOTAL_DISP,
     "nonLinearGeometryTotalLagrangian": MODEL_NONLIN_TL,
     "nonLinearGeometryUpdatedLagrangian": MODEL_NONLIN_UL,
+    "unsLinearGeometry": MODEL_UNS_LIN_GEOM,
 }
 LAW_NAMES = {
     "linearElastic": LAW_LINEAR_ELASTIC,
@@ -321,7 +322,7 @@ def move_mesh(lib, prefix: str, handle, case: "SolidCase", pointDD: np.ndarray, 
 
 def field_size(mesh: FvMesh, name: str) -> tuple:
     nc, where = FIELD_SHAPE[name]
-    n = dict(N=mesh.nCells, B=mesh.nBoundaryFaces, F=mesh.nInternalFaces)[where]
+    n = dict(N=mesh.nCells, B=mesh.nBoundaryFaces, F=mesh.nInternalFaces, FB=mesh.nInternalFaces + mesh.nBoundaryFaces)[where]
     return (n, nc) if nc > 1 else (n,)
 
 

@@ -123,6 +123,7 @@ int s4fgpu_destroy(s4fgpu_handle c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     s4f_amg_destroy(c);
+    s4f_uns_destroy(c);
     if (c->comm) ncclCommDestroy(c->comm);
     if (c->hPcgS) cudaFreeHost(c->hPcgS);
     if (c->hOutS) cudaFreeHost(c->hOutS);
@@ -187,7 +188,7 @@ int s4fgpu_set_geometry(s4fgpu_handle c, const double* C, const double* V, const
     // host geometry copies are only needed to build the rows (cell centres stay for the vol->point weights)
     std::vector<double>().swap(c->hSf); std::vector<double>().swap(c->hCf); std::vector<double>().swap(c->hCorr);
     std::vector<double>().swap(c->hW); std::vector<double>().swap(c->hNod);
-    c->geomSet = true; c->matrixValid = false; c->amgValid = false; c->histValid = false; c->mValid = false; c->gValid = false;
+    c->geomSet = true; c->matrixValid = false; c->amgValid = false; c->histValid = false; c->mValid = false; c->gValid = false; c->unsValid = false;
     if (c->lawSet && !again) { rc = s4f_setup_law(c); if (rc) return rc; }
     return 0;
 }
@@ -198,7 +199,7 @@ int s4fgpu_set_law(s4fgpu_handle c, const s4fgpu_law* law) {
     S4F_REQUIRE(c, law->nTable >= 0 && law->nTable <= 64, "set_law: table too long");
     if (law->kind == S4F_LAW_NEO_HOOKEAN_MISES_PLASTIC || law->kind == S4F_LAW_LINEAR_ELASTIC_MISES_PLASTIC)
         S4F_REQUIRE(c, law->nTable >= 1, "set_law: plasticity law needs the (epsilonP sigmaY) table");
-    c->law = *law; c->lawSet = true; c->histValid = false;
+    c->law = *law; c->lawSet = true; c->histValid = false; c->unsValid = false;
     if (c->geomSet) return s4f_setup_law(c);
     return 0;
 }
@@ -206,7 +207,7 @@ int s4fgpu_set_law(s4fgpu_handle c, const s4fgpu_law* law) {
 int s4fgpu_set_controls(s4fgpu_handle c, const s4fgpu_controls* ctl) {
     S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
     S4F_REQUIRE(c, ctl, "set_controls: null");
-    S4F_REQUIRE(c, ctl->solidModel >= S4F_MODEL_LIN_GEOM_TOTAL_DISP && ctl->solidModel <= S4F_MODEL_NONLIN_UL, "set_controls: unknown solidModel");
+    S4F_REQUIRE(c, ctl->solidModel >= S4F_MODEL_LIN_GEOM_TOTAL_DISP && ctl->solidModel <= S4F_MODEL_UNS_LIN_GEOM, "set_controls: unknown solidModel");
     S4F_REQUIRE(c, ctl->solidModel != S4F_MODEL_NONLIN_TL || ctl->d2dt2Scheme == S4F_D2DT2_STEADY_STATE,
                 "set_controls: nonLinearGeometryTotalLagrangian is available with the steadyState d2dt2 scheme");
     S4F_REQUIRE(c, ctl->solver == S4F_SOLVER_PCG || ctl->solver == S4F_SOLVER_PBICGSTAB, "set_controls: solver PCG or PBiCGStab");
@@ -214,6 +215,7 @@ int s4fgpu_set_controls(s4fgpu_handle c, const s4fgpu_controls* ctl) {
     S4F_REQUIRE(c, ctl->gradScheme >= S4F_GRAD_LEAST_SQUARES && ctl->gradScheme <= S4F_GRAD_POINT_CELLS_LEAST_SQUARES, "set_controls: unknown gradScheme");
     if (ctl->d2dt2Scheme == S4F_D2DT2_BACKWARD && ctl->deltaT0 > 0)     // backwardD2dt2Scheme.C:316-322
         S4F_REQUIRE(c, std::fabs(ctl->deltaT - ctl->deltaT0) <= 1e-15 + 1e-12 * ctl->deltaT, "set_controls: backwardD2dt2Scheme not implemented for variable time steps");
+    c->unsValid = false;
     c->ctl = *ctl; c->ctlSet = true; c->matrixValid = false; c->amgValid = false; c->histValid = false; c->mValid = false;
     if (c->geomSet) return s4f_alloc_model_fields(c);
     return 0;
@@ -289,6 +291,7 @@ int s4fgpu_download(s4fgpu_handle c, int field, double* host) {
         if (!c->matrixValid) { int rc = s4f_assemble_matrix(c); if (rc) return rc; }
         return s4f_download_upper(c, host);
     }
+    if (field == S4F_FIELD_SIGMA_F || field == S4F_FIELD_GRAD_D_F) return s4f_uns_download(c, field, host);
     if (field == S4F_FIELD_TRACTION_GRADIENT_B) {
         std::vector<double> t(3 * (size_t)c->B);
         S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -397,7 +400,7 @@ int s4fgpu_set_points(s4fgpu_handle c, int nPoints, const double* points, const 
     c->hFvPtr.assign(faceVertsPtr, faceVertsPtr + nF + 1);
     c->hFv.assign(faceVerts, faceVerts + faceVertsPtr[nF]);
     c->hPoints.assign(points, points + 3 * (size_t)nPoints);
-    c->gValid = false;
+    c->gValid = false; c->unsValid = false;
     return s4f_build_point_weights(c, points);
 }
 

@@ -223,6 +223,8 @@ struct s4fgpu_ctx {
     OuterScalars* hOutS = nullptr;
     double lambdaMax = 2.0;           // Chebyshev: bound of the Jacobi-scaled spectrum
     struct S4fAmg* amg = nullptr;     // GAMG hierarchy (s4f_amg.cu), rebuilt with the matrix
+    struct S4fUns* uns = nullptr;     // face-based data of the unsLinearGeometry model (s4f_uns.cu)
+    bool unsValid = false;
     DevBuf<int> ones3;                // {1,1,1}
     const int* amgAct = nullptr;      // device int[3] of components the V-cycle works on (null: all); the PCG passes its active flags
     bool amgValid = false;
@@ -233,6 +235,8 @@ struct s4fgpu_ctx {
 
     bool incremental() const { return ctl.solidModel == S4F_MODEL_NONLIN_TL || ctl.solidModel == S4F_MODEL_NONLIN_UL; }
     bool UL() const { return ctl.solidModel == S4F_MODEL_NONLIN_UL; }
+    bool unsModel() const { return ctl.solidModel == S4F_MODEL_UNS_LIN_GEOM; }
+    bool finiteStrain() const { return ctl.solidModel == S4F_MODEL_NONLIN_TL_TOTAL_DISP || ctl.solidModel == S4F_MODEL_NONLIN_TL || ctl.solidModel == S4F_MODEL_NONLIN_UL; }
     bool pointCellsGrad() const { return ctl.gradScheme == S4F_GRAD_POINT_CELLS_LEAST_SQUARES; }
     // rows the least-squares gradient kernels run over
     const int* gradSlicePtr() const { return pointCellsGrad() ? gSlicePtr.p : slicePtr.p; }
@@ -260,6 +264,14 @@ int s4f_relax_and_residual(s4fgpu_ctx* c, int iCorr);
 int s4f_grad(s4fgpu_ctx* c);
 int s4f_kinematics(s4fgpu_ctx* c);
 int s4f_pressure_smooth(s4fgpu_ctx* c);              // updateSigmaHyd with the pressure equation; fixes sigma in place
+int s4f_uns_setup(s4fgpu_ctx* c);                    // s4f_uns.cu: the face-stress ("uns") discretisation
+int s4f_uns_gradients(s4fgpu_ctx* c);
+int s4f_uns_bc_update(s4fgpu_ctx* c);
+int s4f_uns_source(s4fgpu_ctx* c);
+int s4f_uns_download(s4fgpu_ctx* c, int field, double* host);
+void s4f_uns_destroy(s4fgpu_ctx* c);
+int s4f_bc_sngrad_store(s4fgpu_ctx* c);              // snGrad() of every boundary face into bSn
+int s4f_grad_calculated_interior(s4fgpu_ctx* c, const double* X, double* gradOut);   // cell values of fvc::grad(X) only
 int s4f_make_m(s4fgpu_ctx* c);                       // lin-geom: M = sigma - gamma grad(D) when no law kernel produced it
 int s4f_update_totals(s4fgpu_ctx* c, bool disp, bool grad);
 int s4f_law_correct(s4fgpu_ctx* c);

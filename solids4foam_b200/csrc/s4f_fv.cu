@@ -763,7 +763,8 @@ int s4f_assemble_matrix(s4fgpu_ctx* c) {
 
 int s4f_bc_update_coeffs(s4fgpu_ctx* c) {
     if (c->B == 0) return 0;
-    const int TL = c->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP;
+    if (c->unsModel()) return s4f_uns_bc_update(c);
+    const int TL = c->finiteStrain() ? 1 : 0;
     k_bc_update<<<(c->B + 127) / 128, 128, 0, c->stream>>>(c->bKind.p, c->bN.p, c->bcValue.p, c->bcPressure.p, c->impK.p, c->sigma.p, c->gradD.p,
                                                           c->Finv.p, c->tracGrad.p, c->D.p, c->incremental() ? c->Dold.p : nullptr, c->B,
                                                           c->bOff(), c->ld, TL);
@@ -807,9 +808,19 @@ int s4f_make_m(s4fgpu_ctx* c) {
     return s4f_halo_exchange(c, c->T9.p, 9);
 }
 
+int s4f_bc_sngrad_store(s4fgpu_ctx* c) {
+    if (c->B == 0) return 0;
+    k_bc_sngrad_store<<<(c->B + 127) / 128, 128, 0, c->stream>>>(c->bFaceCell.p, c->bKind.p, c->bN.p, c->bK.p, c->bDelta.p, c->tracGrad.p, c->D.p,
+                                                                c->gradD.p, c->bSn.p, c->B, c->bOff(), c->ld);
+    c->launches++;
+    return 0;
+}
+
 int s4f_assemble_source(s4fgpu_ctx* c) {
     int rh = s4f_d2dt2_history(c); if (rh) return rh;
-    if (c->fastRhs()) {
+    if (c->unsModel()) {          // unsLinGeomSolid.C:124-131: no stabilisation term, the divergence of the face stress
+        int rc = s4f_uns_source(c); if (rc) return rc;
+    } else if (c->fastRhs()) {
         if (!c->mValid) {
             int rc = (c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP) ? s4f_make_m(c) : s4f_kinematics(c);
             if (rc) return rc;
@@ -836,6 +847,7 @@ int s4f_assemble_source(s4fgpu_ctx* c) {
 }
 
 int s4f_grad(s4fgpu_ctx* c) {
+    if (c->unsModel()) return s4f_uns_gradients(c);
     const int gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32, 3);
     if (c->B > 0) {
         k_bc_sngrad_store<<<(c->B + 127) / 128, 128, 0, c->stream>>>(c->bFaceCell.p, c->bKind.p, c->bN.p, c->bK.p, c->bDelta.p, c->tracGrad.p, c->D.p,
@@ -869,6 +881,19 @@ __global__ void k_sngrad_calculated(const int* __restrict__ bFaceCell, const int
     for (int c = 0; c < 3; c++) bSn[(size_t)c * B + b] = bDelta[b] * (X[(size_t)c * ld + bOff + b] - X[(size_t)c * ld + P]);
 }
 }  // namespace
+int s4f_grad_calculated_interior(s4fgpu_ctx* c, const double* X, double* gradOut) {
+    const int gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32, 3);
+    if (c->ctl.gradScheme == S4F_GRAD_GAUSS_LINEAR)
+        k_grad<true><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eSf.p, c->eW.p, X, c->rV.p, gradOut, c->N, c->ld, c->nEntries, c->nSlices);
+    else {
+        if (c->pointCellsGrad() && !c->gValid) { int rc = s4f_build_point_stencil(c); if (rc) return rc; }
+        k_grad<false><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->gradSlicePtr(), c->gradCol(), c->gradLs(), c->eW.p, X, c->rV.p, gradOut, c->N, c->ld, c->gradNE(), c->nSlices);
+    }
+    c->launches++;
+    S4F_CHECK_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
 int s4f_grad_calculated(s4fgpu_ctx* c, const double* X, double* gradOut) {
     const int gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32, 3);
     if (c->B > 0) {

@@ -425,7 +425,7 @@ int s4f_law_correct(s4fgpu_ctx* c) {
     }
     S4F_CHECK_CUDA(c, cudaGetLastError());
     if (L.solvePressureEqn) { int rp = s4f_pressure_smooth(c); if (rp) return rp; }
-    if (c->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP) {
+    if (c->finiteStrain()) {
         // UL: relF = I + gradDD.T() takes the place of F: fvc::div(relJ*relFinv & sigma), nonLinGeomUpdatedLagSolid.C:188
         k_tl_flux_tensor<<<grid, S4F_BLOCK, 0, c->stream>>>(gD, c->sigma.p, c->T9.p, c->Finv.p, c->Jt.p, N, bOff, B, ld,
                                                             c->fastRhs() ? c->gradD.p : nullptr, c->gamma0());
@@ -440,7 +440,7 @@ int s4f_law_correct(s4fgpu_ctx* c) {
 // Solver-level kinematics of the total-Lagrangian models: F = I + gradD.T(), Finv, J and the flux tensor
 // J Finv & sigma (nonLinGeomTotalLagTotalDispSolid.C:225-232) from the current gradD and sigma.
 int s4f_kinematics(s4fgpu_ctx* c) {
-    if (c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP) return 0;
+    if (!c->finiteStrain()) return 0;
     const int grid = s4f_grid(c->numSMs, c->N + c->B);
     k_tl_flux_tensor<<<grid, S4F_BLOCK, 0, c->stream>>>(c->UL() ? c->gradD.p : c->gradForLaw(), c->sigma.p, c->T9.p, c->Finv.p, c->Jt.p, c->N, c->bOff(), c->B, c->ld,
                                                         c->fastRhs() ? c->gradD.p : nullptr, c->gamma0());

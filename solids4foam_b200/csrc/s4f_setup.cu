@@ -272,7 +272,7 @@ int s4f_alloc_fields(s4fgpu_ctx* c) {
 // fields that only finite-strain models / plastic laws need; called from set_law / set_controls
 int s4f_alloc_model_fields(s4fgpu_ctx* c) {
     const size_t ld = c->ld;
-    const bool TL = c->ctlSet && c->ctl.solidModel != S4F_MODEL_LIN_GEOM_TOTAL_DISP;
+    const bool TL = c->ctlSet && c->finiteStrain();
     const int kind = c->law.kind;
     auto A = [&](DevBuf<double>& b, int nc) { return (b.n == nc * ld) ? cudaSuccess : b.alloc(nc * ld); };
     auto fillI = [&](DevBuf<double>& b, int nc, const int* diagIdx, int nd) {

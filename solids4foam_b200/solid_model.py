@@ -30,6 +30,8 @@ class SolidModel:
         "nonLinearGeometryTotalLagrangianTotalDisplacement": K.MODEL_NONLIN_TL_TOTAL_DISP,
         "gpuNonLinearGeometryTotalLagrangian": K.MODEL_NONLIN_TL,
         "nonLinearGeometryTotalLagrangian": K.MODEL_NONLIN_TL,
+        "gpuUnsLinearGeometry": K.MODEL_UNS_LIN_GEOM,
+        "unsLinearGeometry": K.MODEL_UNS_LIN_GEOM,
         "gpuNonLinearGeometryUpdatedLagrangian": K.MODEL_NONLIN_UL,
         "nonLinearGeometryUpdatedLagrangian": K.MODEL_NONLIN_UL,
     }

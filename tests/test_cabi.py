@@ -92,7 +92,7 @@ def test_enum_values_match_the_header():
                "S4F_FIELD_D_LAMBDA": "S4F_FIELD_DLAMBDA", "S4F_FIELD_D_EPSILON_P": "S4F_FIELD_DEPSILON_P",
                "S4F_FIELD_TRACTION_GRADIENT_B": "S4F_FIELD_TRACTION_GRADIENT_B",
                "S4F_FIELD_D_D": "S4F_FIELD_DD", "S4F_FIELD_GRAD_D_D": "S4F_FIELD_GRAD_DD",
-               "S4F_FIELD_D_D_B": "S4F_FIELD_DD_B"}.get(key, key)
+               "S4F_FIELD_D_D_B": "S4F_FIELD_DD_B", "S4F_FIELD_SIGMAF": "S4F_FIELD_SIGMA_F", "S4F_FIELD_GRAD_DF": "S4F_FIELD_GRAD_D_F"}.get(key, key)
         assert vals[key] == idx, (name, key)
 
 

@@ -598,3 +598,47 @@ def test_point_cells_least_squares_evolve_matches_oracle():
     assert sg["converged"] and so["converged"]
     assert rel_l2(g.get("D"), o.get("D")) < SOLVE_TOL
     assert rel_l2(g.get("sigma"), o.get("sigma")) < SOLVE_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# unsLinGeomSolid: face stresses (second half)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case_fn,kw", [
+    (cases.plate_hole, dict()),
+    (cases.plate_hole, dict(cell_perm_seed=2, gradScheme=K.GRAD_GAUSS_LINEAR)),
+    (cases.cantilever, dict(nx=9, ny=5, nz=4, general=True)),
+    (cases.patch_test, dict(n=5)),
+])
+def test_uns_face_gradients_and_stress_match_oracle(case_fn, kw):
+    """k_vol_to_point + k_uns_face_pre / k_uns_cell_grad / k_uns_face_stress against the oracle's restatement of fvcGradf.C and
+    linearElastic::correct(surfaceSymmTensorField&): vertex-based cell gradient, face gradient, face stress, and the assembled
+    right-hand side fvc::div(Sf & sigmaf)."""
+    g, o, mesh = _pair(case_fn, solidModel=K.MODEL_UNS_LIN_GEOM, **kw)
+    D = _analytic_D(mesh)
+    if mesh.solutionD[2] == 0:
+        D[:, 2] = 0.0
+    for s in (g, o):
+        s.set("D", D)
+        s.op_grad()
+    assert rel_l2(g.get("gradD"), o.get("gradD")) < OP_TOL
+    assert rel_l2(g.get("gradD_b"), o.get("gradD_b")) < 10 * OP_TOL
+    assert rel_l2(g.get("gradDf"), o.get("gradDf")) < OP_TOL
+    assert rel_l2(g.get("sigmaf"), o.get("sigmaf")) < OP_TOL
+    for s in (g, o):
+        s.op_assemble()
+    assert np.abs(g.get("source") - o.get("source")).max() / np.abs(o.get("source")).max() < 1e-11
+    assert rel_l2(g.get("tractionGradient_b"), o.get("tractionGradient_b")) < 1e-11
+
+
+@pytest.mark.parametrize("case_fn,kw", [(cases.plate_hole, dict()), (cases.cantilever, dict(nx=8, ny=4, nz=4, L=2.0, general=True))])
+def test_uns_model_evolve_matches_oracle(case_fn, kw):
+    from oracle.binding import OracleSolid
+    from solids4foam_b200.solid_model import SolidModel
+    tight = dict(TIGHT, nCorrectors=20000)
+    g = SolidModel.New(case_fn(preconditioner=K.PRECOND_GAMG, **kw, **tight), "gpuUnsLinearGeometry")
+    o = OracleSolid(case_fn(preconditioner=K.PRECOND_DIC, solidModel=K.MODEL_UNS_LIN_GEOM, **kw, **tight))
+    sg, so = g.evolve(), o.evolve()
+    assert sg["converged"] and so["converged"], (sg, so)
+    assert rel_l2(g.get("D"), o.get("D")) < SOLVE_TOL
+    assert rel_l2(g.get("sigma"), o.get("sigma")) < SOLVE_TOL
+    assert rel_l2(g.get("sigmaf"), o.get("sigmaf")) < SOLVE_TOL
