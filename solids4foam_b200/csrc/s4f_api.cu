@@ -124,6 +124,7 @@ int s4fgpu_destroy(s4fgpu_handle c) {
     cudaStreamSynchronize(c->stream);
     s4f_amg_destroy(c);
     s4f_uns_destroy(c);
+    s4f_dic_destroy(c);
     if (c->comm) ncclCommDestroy(c->comm);
     if (c->hPcgS) cudaFreeHost(c->hPcgS);
     if (c->hOutS) cudaFreeHost(c->hOutS);

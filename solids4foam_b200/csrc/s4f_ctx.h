@@ -223,6 +223,8 @@ struct s4fgpu_ctx {
     OuterScalars* hOutS = nullptr;
     double lambdaMax = 2.0;           // Chebyshev: bound of the Jacobi-scaled spectrum
     struct S4fAmg* amg = nullptr;     // GAMG hierarchy (s4f_amg.cu), rebuilt with the matrix
+    struct S4fDic* dic = nullptr;     // level-scheduled DIC (s4f_dic.cu), rebuilt with the matrix
+    bool dicValid = false;
     struct S4fUns* uns = nullptr;     // face-based data of the unsLinearGeometry model (s4f_uns.cu)
     bool unsValid = false;
     DevBuf<int> ones3;                // {1,1,1}
@@ -264,6 +266,9 @@ int s4f_relax_and_residual(s4fgpu_ctx* c, int iCorr);
 int s4f_grad(s4fgpu_ctx* c);
 int s4f_kinematics(s4fgpu_ctx* c);
 int s4f_pressure_smooth(s4fgpu_ctx* c);              // updateSigmaHyd with the pressure equation; fixes sigma in place
+int s4f_dic_setup(s4fgpu_ctx* c);                    // s4f_dic.cu: exact DIC / FDIC by level scheduling
+int s4f_dic_apply(s4fgpu_ctx* c, const double* r3, double* z3);
+void s4f_dic_destroy(s4fgpu_ctx* c);
 int s4f_uns_setup(s4fgpu_ctx* c);                    // s4f_uns.cu: the face-stress ("uns") discretisation
 int s4f_uns_gradients(s4fgpu_ctx* c);
 int s4f_uns_bc_update(s4fgpu_ctx* c);

@@ -756,7 +756,7 @@ int s4f_assemble_matrix(s4fgpu_ctx* c) {
     k_diag_recip<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->diagC.p, c->rDiagC.p, c->N, c->ld);
     c->launches++;
     c->matrixValid = true;
-    c->amgValid = false;
+    c->amgValid = false; c->dicValid = false;
     S4F_CHECK_CUDA(c, cudaGetLastError());
     return 0;
 }

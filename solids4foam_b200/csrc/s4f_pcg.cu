@@ -656,7 +656,7 @@ static int cheb_apply(s4fgpu_ctx* c, const PcgParams& P, const double* r, double
 
 // [OF-ext] PBiCGStab::scalarSolve for the three components at once (set-up of rA, normFactor, initial residual
 // already done by k_pcg_sum / k_pcg_init).  M^-1 is the diagonal (or nothing), the Chebyshev polynomial or the
-// GAMG V-cycle; DIC is stood in for by the diagonal as in the PCG path.
+// GAMG V-cycle, or the exact level-scheduled DIC (s4f_dic.cu; for the symmetric matrix DILU coincides with it).
 static int solve_pbicgstab(s4fgpu_ctx* c, double* psi, PcgParams P, double nGlob) {
     const int N = c->N, ld = c->ld;
     const int gridV = s4f_grid(c->numSMs, N);
@@ -673,6 +673,7 @@ static int solve_pbicgstab(s4fgpu_ctx* c, double* psi, PcgParams P, double nGlob
             c->amgAct = nullptr;
             return r;
         }
+        if (P.precond == S4F_PRECOND_DIC) return s4f_dic_apply(c, in, out);
         return cheb_apply(c, P, in, out);
     };
     int rc, it = 0;
@@ -713,8 +714,7 @@ int s4f_solve_segregated(s4fgpu_ctx* c, double* psi, const double* source) {
     const double nGlob = global_cells(c);
     const int gridV = s4f_grid(c->numSMs, N), gridV2 = s4f_grid(c->numSMs, (N + 1) / 2), gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
     PcgScalars* S = c->pcgS.p;
-    const bool fusedJacobi = (P.precond == S4F_PRECOND_DIAGONAL || P.precond == S4F_PRECOND_NONE || P.precond == S4F_PRECOND_DIC);
-    if (P.precond == S4F_PRECOND_DIC) P.precond = S4F_PRECOND_DIAGONAL;   // GPU stand-in, reported
+    const bool fusedJacobi = (P.precond == S4F_PRECOND_DIAGONAL || P.precond == S4F_PRECOND_NONE);
     if (P.precond == S4F_PRECOND_CHEBYSHEV && c->cheb0.n != 3 * (size_t)ld) {
         S4F_CHECK_CUDA(c, c->cheb0.alloc(3 * (size_t)ld)); S4F_CHECK_CUDA(c, c->cheb1.alloc(3 * (size_t)ld));
     }
@@ -764,7 +764,8 @@ int s4f_solve_segregated(s4fgpu_ctx* c, double* psi, const double* source) {
                     c->amgAct = &S->active[0];              // converged components skip their share of the V-cycle
                     rc = s4f_amg_apply(c, c->rA.p, c->wA.p);
                     c->amgAct = nullptr;
-                } else rc = cheb_apply(c, P, c->rA.p, c->wA.p);
+                } else if (P.precond == S4F_PRECOND_DIC) rc = s4f_dic_apply(c, c->rA.p, c->wA.p);      // exact DIC / FDIC, level scheduled
+                else rc = cheb_apply(c, P, c->rA.p, c->wA.p);
                 if (rc) return rc;
                 k_pcg_dot_zr<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->wA.p, c->rA.p, N, ld, S, P, nGlob, c->partials.p, c->ticket.p);
                 c->launches++;

@@ -22,8 +22,10 @@ def run(case_dir: str, steps: int | None = None, device: int = 0, precond: str |
     if precond:
         over["preconditioner"] = getattr(K, "PRECOND_" + precond.upper())
     case = IO.read_case(case_dir, **over)
-    if case.controls.preconditioner == K.PRECOND_DIC:
-        case.controls.preconditioner = K.PRECOND_GAMG          # DIC/FDIC in fvSolution -> the GPU preconditioner family
+    if case.controls.preconditioner == K.PRECOND_DIC and precond is None:
+        # DIC/FDIC in fvSolution: the device has it exactly (level scheduled, iteration counts of the CPU solver) but GAMG is the
+        # fast preconditioner on a GPU; --precond DIC keeps the case's own choice
+        case.controls.preconditioner = K.PRECOND_GAMG
     cd = IO.read_foam_dict(os.path.join(case_dir, "system", "controlDict"))
     dt = float(cd.get("deltaT", 1.0))
     n = steps if steps is not None else max(1, int(round((float(cd.get("endTime", dt)) - float(cd.get("startTime", 0.0))) / dt)))
@@ -50,7 +52,7 @@ def main():
     ap.add_argument("case_dir")
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--device", type=int, default=0)
-    ap.add_argument("--precond", default=None, choices=["GAMG", "DIAGONAL", "CHEBYSHEV", "NONE"])
+    ap.add_argument("--precond", default=None, choices=["GAMG", "DIC", "DIAGONAL", "CHEBYSHEV", "NONE"])
     a = ap.parse_args()
     run(a.case_dir, a.steps, a.device, a.precond)
 

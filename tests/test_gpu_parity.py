@@ -78,7 +78,7 @@ def test_operators(case_fn, kw):
     assert rel_l2(psi_g, psi_o) < 1e-9
 
 
-@pytest.mark.parametrize("pre", [K.PRECOND_DIAGONAL, K.PRECOND_NONE])
+@pytest.mark.parametrize("pre", [K.PRECOND_DIAGONAL, K.PRECOND_NONE, K.PRECOND_DIC])
 def test_outer_iterations_track_oracle(pre):
     """Iteration-by-iteration tracking.  The first outer iteration must agree to round-off.  Later ones are
     compared loosely: a relTol-0.1 PCG solve of the ill-conditioned bending component amplifies 1e-15
@@ -642,3 +642,44 @@ def test_uns_model_evolve_matches_oracle(case_fn, kw):
     assert rel_l2(g.get("D"), o.get("D")) < SOLVE_TOL
     assert rel_l2(g.get("sigma"), o.get("sigma")) < SOLVE_TOL
     assert rel_l2(g.get("sigmaf"), o.get("sigmaf")) < SOLVE_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# [OF-ext] DIC / FDIC, the reference's default preconditioner, exactly (level-scheduled sweeps)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case_fn,kw", [
+    (cases.cantilever, dict(nx=14, ny=5, nz=4)),
+    (cases.plate_hole, dict(cell_perm_seed=4)),
+    (cases.notched_bar, dict(nx=12, ny=4, nz=4)),
+])
+def test_dic_pcg_takes_the_iteration_counts_of_the_cpu_solver(case_fn, kw):
+    """s4f_dic.cu evaluates the sequential DIC face sweeps level by level: the preconditioned residuals equal the oracle's up to
+    the summation order inside a cell, so PCG stops after the same number of iterations with the same residuals."""
+    rng = np.random.default_rng(3)
+    for relTol, tol in ((0.1, 1e-9), (0.0, 1e-12)):
+        g, o, mesh = _pair(case_fn, preconditioner=K.PRECOND_DIC, relTol=relTol, tolerance=tol, **kw)
+        b = rng.standard_normal((mesh.nCells, 3))
+        if mesh.solutionD[2] == 0:
+            b[:, 2] = 0.0
+        x0 = np.zeros((mesh.nCells, 3))
+        psi_g, st_g = g.op_solve(x0, b)
+        psi_o, st_o = o.op_solve(x0, b)
+        assert st_g["nIterations"] == st_o["nIterations"], (st_g, st_o)
+        assert np.allclose(st_g["initialResidual"], st_o["initialResidual"], rtol=1e-12)
+        # a deep solve (1e-12) amplifies the summation-order round-off to ~1e-5 of the final residual
+        assert np.allclose(st_g["finalResidual"], st_o["finalResidual"], rtol=1e-6 if relTol > 0 else 1e-3, atol=1e-300)
+        assert rel_l2(psi_g, psi_o) < 1e-9
+
+
+def test_plate_hole_with_dic_follows_the_cpu_run():
+    """Config C1 with the tutorial's own solver settings (PCG + FDIC, relTol 0.1): same corrector count, same inner iteration
+    counts over the first correctors, fields to round-off amplification level."""
+    g, o, mesh = _pair(cases.plate_hole, preconditioner=K.PRECOND_DIC)
+    for it in range(4):
+        sg, so = g.outer_iteration(), o.outer_iteration()
+        assert sg["nIterations"] == so["nIterations"], (it, sg, so)
+        assert rel_l2(g.get("D"), o.get("D")) < 1e-9
+    g2, o2, _ = _pair(cases.plate_hole, preconditioner=K.PRECOND_DIC)
+    sg, so = g2.evolve(), o2.evolve()
+    assert sg["converged"] and so["converged"] and abs(sg["nCorr"] - so["nCorr"]) <= 1
+    assert rel_l2(g2.get("D"), o2.get("D")) < 1e-6 and rel_l2(g2.get("sigma"), o2.get("sigma")) < 1e-6
