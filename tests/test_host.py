@@ -87,7 +87,7 @@ def test_notched_bar_mesh_is_non_orthogonal_but_valid():
     assert not c.mesh.is_orthogonal()
 
 
-@pytest.mark.parametrize("nRanks", [2, 3, 4])
+@pytest.mark.parametrize("nRanks", [2, 3, 4, 8])
 def test_slab_decomposition_matches_whole_mesh(nRanks):
     nx, ny, nz = 10, 3, 2
     whole = M.hex_box(nx, ny, nz, 8.0, 1.0, 1.0)
