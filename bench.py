@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--precond", default="gamg", choices=["diagonal", "none", "chebyshev", "gamg", "gamg32"])
     ap.add_argument("--gamg-degree", type=int, default=3)
     ap.add_argument("--gamg-omega", type=float, default=2.2)
-    ap.add_argument("--gamg-cycle", type=int, default=0)
+    ap.add_argument("--gamg-cycle", type=int, default=2)
     return ap.parse_args()
 
 

@@ -175,6 +175,7 @@ void gpuLinGeomTotalDispSolid::mirrorLawAndControls()
     c.gamgSinglePrecision = gpuDict.lookupOrDefault<Switch>("gamgSinglePrecision", false);
     c.gamgOverCorrection = gpuDict.lookupOrDefault<scalar>("gamgOverCorrection", 2.2);
     c.gamgSmootherDegree = gpuDict.lookupOrDefault<label>("gamgSmootherDegree", 3);
+    c.gamgCycle = gpuDict.lookupOrDefault<label>("gamgCycle", 2);          // K-cycle on level 1
     c.tolerance = sol.lookupOrDefault<scalar>("tolerance", 1e-6);
     c.relTol = sol.lookupOrDefault<scalar>("relTol", 0);
     c.maxIter = sol.lookupOrDefault<label>("maxIter", 1000);

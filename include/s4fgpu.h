@@ -162,7 +162,7 @@ typedef struct {
     int gamgSinglePrecision;   /* S4F_PRECOND_GAMG: 1 = V-cycle in fp32 (PCG itself stays fp64), 0 = fp64 */
     double gamgOverCorrection; /* S4F_PRECOND_GAMG: fixed scaling of the coarse-grid correction (<= 0: 2.2) */
     int gamgSmootherDegree;    /* S4F_PRECOND_GAMG: Chebyshev-Jacobi degree of the pre- and post-smoother (<= 0: 3) */
-    int gamgCycle;             /* S4F_PRECOND_GAMG: 0 = V-cycle, 1 = W-cycle */
+    int gamgCycle;             /* S4F_PRECOND_GAMG: 0 = V-cycle, 1 = W-cycle, 2 = K-cycle on level 1 (two flexible-CG steps; single rank) */
     double gamgSmootherRatio;  /* S4F_PRECOND_GAMG: lower end of the Chebyshev interval as a fraction of the upper (<= 0: 0.3) */
 } s4fgpu_controls;
 

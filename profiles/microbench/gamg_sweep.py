@@ -29,6 +29,9 @@ def main():
     if len(sys.argv) > 2:
         configs = [eval("dict(" + a + ")") for a in sys.argv[2:]]
     for cfg in configs:
+        cfg = dict(cfg)
+        if "omegaK" in cfg:          # K-cycle tuning aid: scaling of the fine-level correction (read by the library at set-up)
+            os.environ["S4F_GAMG_OMEGA_K"] = str(cfg.pop("omegaK"))
         ctl = K.default_controls(preconditioner=K.PRECOND_GAMG, **cfg)
         g.set_controls(ctl)
         g.set("D", zero); g.set("sigma", np.zeros((case.mesh.nCells, 6)))

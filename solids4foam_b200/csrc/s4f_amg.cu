@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -321,6 +322,100 @@ __global__ void k_gather_upper(const int* __restrict__ faceEntry, const double* 
     if (f < F) upper[f] = -eA[faceEntry[f]];
 }
 
+
+// ---- K-cycle on level 1 (gamgCycle 2): two flexible-CG steps on the coarse problem A_1 x = b, each preconditioned by the
+// V-cycle from level 1 down (Notay's aggregation multigrid): the coarse correction is scaled by the Krylov step instead of a
+// fixed factor.  Per component q:  c1 = V(b), v1 = A c1, rho1 = c1.v1, alpha1 = c1.b;  r = b - (alpha1/rho1) v1;
+// c2 = V(r), v2 = A c2, gamma = c2.v1, beta = c2.v2, alpha2 = c2.r, rho2 = beta - gamma^2/rho1;
+// x = (alpha1/rho1 - gamma alpha2/(rho1 rho2)) c1 + (alpha2/rho2) c2.
+struct KcScalars { double rho1[3], alpha1[3], gamma[3], beta[3], alpha2[3]; };
+
+// v = A c (row gather over the level's SELL rows) with the dot products the step needs, accumulated by atomics:
+// STEP 1: rho1 += c.v, alpha1 += c.b;   STEP 2: gamma += c.v1, beta += c.v, alpha2 += c.r
+template <class T, int STEP>
+__global__ void __launch_bounds__(S4F_AMG_BLOCK, 4) k_kc_amul(const int* __restrict__ slicePtr, const int* __restrict__ col,
+                                                              const T* __restrict__ a, const T* __restrict__ dg, const T* __restrict__ cvec,
+                                                              const T* __restrict__ bvec /* b (step 1) or r (step 2) */,
+                                                              const T* __restrict__ v1, T* __restrict__ v, int n, int ld, int nSlices,
+                                                              KcScalars* S, const int* __restrict__ act) {
+    const bool aq[3] = {act[0] != 0, act[1] != 0, act[2] != 0};
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    double d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0}, d2[3] = {0, 0, 0};
+    for (int s = warp; s < nSlices; s += nWarps) {
+        const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
+        const int row = s * 32 + lane;
+        T acc[3] = {0, 0, 0};
+        for (int k = 0; k < width; k++) {
+            const int idx = base + 32 * k + lane;
+            const int cc = col[idx];
+            const T e = a[idx];
+#pragma unroll
+            for (int q = 0; q < 3; q++) if (aq[q]) acc[q] += e * cvec[cc + q * ld];
+        }
+        if (row < n) {
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                if (!aq[q]) continue;
+                const int j = q * ld + row;
+                const T cv = cvec[j];
+                const T vv = dg[j] * cv - acc[q];
+                v[j] = vv;
+                d0[q] += (double)cv * (double)vv;
+                d1[q] += (double)cv * (double)bvec[j];
+                if (STEP == 2) d2[q] += (double)cv * (double)v1[j];
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        if (!aq[q]) continue;
+        double x0 = d0[q], x1 = d1[q], x2 = d2[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { x0 += __shfl_xor_sync(0xffffffffu, x0, o); x1 += __shfl_xor_sync(0xffffffffu, x1, o); x2 += __shfl_xor_sync(0xffffffffu, x2, o); }
+        if (lane == 0) {
+            if (STEP == 1) { atomicAdd(&S->rho1[q], x0); atomicAdd(&S->alpha1[q], x1); }
+            else { atomicAdd(&S->beta[q], x0); atomicAdd(&S->alpha2[q], x1); atomicAdd(&S->gamma[q], x2); }
+        }
+    }
+}
+
+// r = b - (alpha1/rho1) v1
+template <class T>
+__global__ void k_kc_resid(const T* __restrict__ b, const T* __restrict__ v1, T* __restrict__ r, int n, int ld, const KcScalars* S,
+                           const int* __restrict__ act) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        if (!act[q]) continue;
+        const double rho = S->rho1[q];
+        const T sc = (T)(fabs(rho) > 1e-300 ? S->alpha1[q] / rho : 0.0);
+        r[q * ld + i] = b[q * ld + i] - sc * v1[q * ld + i];
+    }
+}
+
+// x = (alpha1/rho1 - gamma alpha2/(rho1 rho2)) c1 + (alpha2/rho2) c2
+template <class T>
+__global__ void k_kc_final(const T* __restrict__ c1, const T* __restrict__ c2, T* __restrict__ x, int n, int ld, const KcScalars* S,
+                           const int* __restrict__ act) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        if (!act[q]) continue;
+        const double rho1 = S->rho1[q];
+        double k1 = 0, k2 = 0;
+        if (fabs(rho1) > 1e-300) {
+            k1 = S->alpha1[q] / rho1;
+            const double rho2 = S->beta[q] - S->gamma[q] * S->gamma[q] / rho1;
+            if (fabs(rho2) > 1e-300 * fabs(S->beta[q]) && fabs(rho2) > 1e-300) { k2 = S->alpha2[q] / rho2; k1 -= S->gamma[q] * k2 / rho1; }
+        }
+        x[q * ld + i] = (T)k1 * c1[q * ld + i] + (T)k2 * c2[q * ld + i];
+    }
+}
+
 // ================================================================================================
 // hierarchy
 // ================================================================================================
@@ -354,6 +449,9 @@ struct Hierarchy : S4fAmg {
     std::vector<std::unique_ptr<Level<T>>> lv;
     DevBuf<T> denseInv;                 // 3 * nC * nC
     int deg = 2, cycle = 0;
+    DevBuf<T> kc1, kv1, kr, kc2;        // K-cycle work vectors on level 1 (3*ld each)
+    DevBuf<KcScalars> kS;
+    double omegaK = 1.0;                // scaling of the K-cycle's coarse correction on the fine level
     const int* act = nullptr;           // device int[3]: components to work on (the fused PCG's active flags, or all ones)
     double omega = 2.2;
     double theta = 0, delta = 0;
@@ -445,19 +543,26 @@ struct Hierarchy : S4fAmg {
     // algorithmic bytes of one application (for the roofline report): every array read / written once
     double bytes_per_apply(int fineLdUnused) const {
         (void)fineLdUnused;
-        double tot = 0;
+        double tot = 0, below1 = 0;
         const double sT = sizeof(T);
         for (size_t l = 0; l + 1 < lv.size(); l++) {
             const Level<T>& L = *lv[l];
             const double n = L.n, nz = nnz[l], sB = (l == 0) ? 8.0 : sT, sO = (l == 0) ? 8.0 : sT, nc = lv[l + 1]->n;
             const double mat = nz * (4 + sT) + n * 0.125;
-            tot += 3 * n * (sT + sB + 2 * sT);                                         // first
-            tot += (deg - 1) * (mat + 3 * n * (sB + 5 * sT + sT));                      // pre steps
-            tot += mat + 3 * n * (sB + 3 * sT);                                        // residual
-            tot += 3 * n * sT + 3 * nc * sT + 4 * n;                                   // restrict
-            tot += 4 * n + 6 * n * sT + 3 * nc * sT;                                   // prolong
-            tot += mat + 3 * n * (sB + 4 * sT + sT);                                   // post step 0 (no d read)
-            tot += (deg - 1) * (mat + 3 * n * (sB + 5 * sT)) + (deg > 1 ? 3 * n * sO : 0);   // post steps
+            double t = 0;
+            t += 3 * n * (sT + sB + 2 * sT);                                         // first
+            t += (deg - 1) * (mat + 3 * n * (sB + 5 * sT + sT));                      // pre steps
+            t += mat + 3 * n * (sB + 3 * sT);                                        // residual
+            t += 3 * n * sT + 3 * nc * sT + 4 * n;                                   // restrict
+            t += 4 * n + 6 * n * sT + 3 * nc * sT;                                   // prolong
+            t += mat + 3 * n * (sB + 4 * sT + sT);                                   // post step 0 (no d read)
+            t += (deg - 1) * (mat + 3 * n * (sB + 5 * sT)) + (deg > 1 ? 3 * n * sO : 0);   // post steps
+            tot += t;
+            if (l >= 1) below1 += t;
+        }
+        if (cycle == 2 && lv.size() > 2 && !dist) {      // K-cycle: a second V-cycle from level 1, two A_1 products with their dots, r, x, two copies
+            const double n1 = lv[1]->n, mat1 = nnz[1] * (4 + sT) + n1 * 0.125;
+            tot += below1 + 2 * (mat1 + 3 * n1 * 4 * sT) + 3 * n1 * 3 * sT + 3 * n1 * 3 * sT + 2 * 3 * n1 * 2 * sT;
         }
         return tot;
     }
@@ -536,10 +641,13 @@ struct Hierarchy : S4fAmg {
         Level<T>& C = *lv[l + 1];
         T* x = smooth<TB>(c, L, b, ldb, true, L.x.p, nullptr, 0);                 // pre-smoothing from zero
         { int rr = residual_restrict<TB>(c, l, b, ldb, x); if (rr) return rr; }
-        int rc = cycle_level<T>(c, l + 1, C.b.p, C.ld, nullptr, 0); if (rc) return rc;
+        int rc;
+        const bool kcycle = (cycle == 2 && l == 0 && lv.size() > 2 && !dist);
+        if (kcycle) { rc = kcycle_level1(c); if (rc) return rc; }
+        else { rc = cycle_level<T>(c, l + 1, C.b.p, C.ld, nullptr, 0); if (rc) return rc; }
         {
             const int grid = s4f_grid(c->numSMs, L.n);
-            k_amg_prolong<T><<<grid, S4F_BLOCK, 0, c->stream>>>(L.parent.p, C.x.p, x, L.n, L.ld, C.ld, (T)omega, act);
+            k_amg_prolong<T><<<grid, S4F_BLOCK, 0, c->stream>>>(L.parent.p, C.x.p, x, L.n, L.ld, C.ld, (T)(kcycle ? omegaK : omega), act);
             c->launches++;
         }
         if (cycle == 1 && l + 2 < lv.size()) {   // W-cycle: a second coarse correction on the updated residual
@@ -553,6 +661,29 @@ struct Hierarchy : S4fAmg {
         if (!out && xr != L.x.p) {   // callers read the level result from L.x
             S4F_CHECK_CUDA(c, cudaMemcpyAsync(L.x.p, xr, 3 * (size_t)L.ld * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
         }
+        return 0;
+    }
+
+    // two FCG steps on A_1 x = C.b preconditioned by the V-cycle from level 1; result in lv[1]->x
+    int kcycle_level1(s4fgpu_ctx* c) {
+        Level<T>& C = *lv[1];
+        const size_t m = 3 * (size_t)C.ld;
+        if (kc1.n != m) {
+            S4F_CHECK_CUDA(c, kc1.alloc(m)); S4F_CHECK_CUDA(c, kv1.alloc(m)); S4F_CHECK_CUDA(c, kr.alloc(m)); S4F_CHECK_CUDA(c, kc2.alloc(m));
+            S4F_CHECK_CUDA(c, kS.alloc(1));
+        }
+        const int grid = step_grid(c, C), gv = (C.n + 255) / 256;
+        S4F_CHECK_CUDA(c, cudaMemsetAsync(kS.p, 0, sizeof(KcScalars), c->stream));
+        int rc = cycle_level<T>(c, 1, C.b.p, C.ld, nullptr, 0); if (rc) return rc;                       // c1 = V(b)
+        S4F_CHECK_CUDA(c, cudaMemcpyAsync(kc1.p, C.x.p, m * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
+        k_kc_amul<T, 1><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(C.slicePtr, C.col, C.a, C.dg.p, kc1.p, C.b.p, nullptr, kv1.p, C.n, C.ld, C.nSlices, kS.p, act);
+        k_kc_resid<T><<<gv, 256, 0, c->stream>>>(C.b.p, kv1.p, kr.p, C.n, C.ld, kS.p, act);
+        c->launches += 2;
+        rc = cycle_level<T>(c, 1, kr.p, C.ld, nullptr, 0); if (rc) return rc;                            // c2 = V(r)
+        S4F_CHECK_CUDA(c, cudaMemcpyAsync(kc2.p, C.x.p, m * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
+        k_kc_amul<T, 2><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(C.slicePtr, C.col, C.a, C.dg.p, kc2.p, kr.p, kv1.p, C.t.p, C.n, C.ld, C.nSlices, kS.p, act);
+        k_kc_final<T><<<gv, 256, 0, c->stream>>>(kc1.p, kc2.p, C.x.p, C.n, C.ld, kS.p, act);
+        c->launches += 2;
         return 0;
     }
 
@@ -594,6 +725,8 @@ int build(s4fgpu_ctx* c, std::vector<HostLevel>& H, const DistInfo& di) {
     A->deg = c->ctl.gamgSmootherDegree > 0 ? c->ctl.gamgSmootherDegree : 3;
     A->cycle = c->ctl.gamgCycle;
     A->omega = c->ctl.gamgOverCorrection > 0 ? c->ctl.gamgOverCorrection : 2.2;
+    A->omegaK = A->omega;            // sweep: 1.0 -> 19.0, 1.5 -> 15.5, 2.2 -> 13.4, 2.6 -> 16.2 ms per outer iteration at 8 M cells
+    if (const char* e = getenv("S4F_GAMG_OMEGA_K")) A->omegaK = atof(e);      // tuning aid (profiles/microbench/gamg_sweep.py)
     const double ratio = c->ctl.gamgSmootherRatio > 0 ? c->ctl.gamgSmootherRatio : 0.3;
     const double lmax = 2.0, lmin = ratio * lmax;    // Gershgorin bound of D^-1 A for the M-matrices of every level
     A->theta = 0.5 * (lmax + lmin); A->delta = 0.5 * (lmax - lmin);
