@@ -157,8 +157,9 @@ def read_mechanical_law(case_dir: str) -> K.Law:
         kw["solvePressureEqn"] = str(ld["solvePressureEqn"]).lower() in ("yes", "true", "on")
     if "pressureSmoothingScaleFactor" in ld:
         kw["pressureSmoothingScaleFactor"] = _scalar(ld["pressureSmoothingScaleFactor"])
-    if "fileName" in ld:        # plasticity: the (epsilonP sigmaY) table file, neoHookeanElasticMisesPlastic.C:868-930
-        path = str(ld["fileName"]).strip('"').replace("$FOAM_CASE", case_dir)
+    fname = _lookup(ld, "fileName") or _lookup(ld, "file")      # the tutorials write the key as "file|fileName"
+    if fname is not None:       # plasticity: the (epsilonP sigmaY) table file, neoHookeanElasticMisesPlastic.C:868-930
+        path = str(fname).strip('"').replace("$FOAM_CASE", case_dir)
         with open(path) as f:
             tbl = _Parser(_tokenize(f.read())).parse_value()
         kw["table"] = [(float(a), float(b)) for a, b in tbl]

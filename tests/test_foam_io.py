@@ -72,6 +72,20 @@ def test_beam_in_cross_flow_solid_dictionaries():
     assert ctl.tolerance == 1e-9 and ctl.relTol == 0.1
 
 
+@needs_ref
+def test_necking_bar_tutorial_law_and_table():
+    """tutorials/solids/elastoplasticity/neckingBar: neoHookeanElasticMisesPlastic with the hardening table read through the
+    "file|fileName" key and $FOAM_CASE; updated-Lagrangian solid model."""
+    base = os.path.join(REF, "solids/elastoplasticity/neckingBar")
+    law = IO.read_mechanical_law(base)
+    ref = K.mechanical_law("neoHookeanElasticMisesPlastic", rho=7833.0, E=200e9, nu=0.3, table=K.NECKING_BAR_TABLE)
+    assert law.kind == K.LAW_NEO_HOOKEAN_MISES_PLASTIC and law.nTable == 8
+    assert (law.rho, law.mu, law.K) == (ref.rho, ref.mu, ref.K)
+    assert list(law.tableEps)[:8] == list(ref.tableEps)[:8] and list(law.tableSigY)[:8] == list(ref.tableSigY)[:8]
+    sp = IO.read_foam_dict(os.path.join(base, "constant", "solidProperties"))
+    assert K.MODEL_NAMES[str(sp["solidModel"])] == K.MODEL_NONLIN_UL
+
+
 def test_poly_mesh_round_trip(tmp_path):
     names = ("fixed", "loaded", "yMin", "yMax", "zMin", "zMax")
     kinds = (M.PATCH, M.PATCH, M.PATCH, M.PATCH, M.SYMMETRY_PLANE, M.PATCH)
