@@ -336,3 +336,132 @@ def test_uns_model_reaches_the_kirsch_solution_and_agrees_with_the_cell_centred_
         assert o.evolve()["converged"]
         ratio[n] = np.abs(o.get("D")[:, 1]).max() / 1.28e-3
     assert 0.35 < ratio[4] < ratio[8] < 1.0 and (1 - ratio[8]) < 0.55 * (1 - ratio[4]), ratio
+
+
+# ---------------------------------------------------------------------------------------------
+# independent numpy restatements (plain loops on small meshes) of the point-based operators, on RANDOM fields
+# ---------------------------------------------------------------------------------------------
+def _point_cells(mesh):
+    pc = [set() for _ in range(mesh.points.shape[0])]
+    F = mesh.nInternalFaces
+    cells = np.concatenate([mesh.owner, mesh.faceCells])
+    for f, verts in enumerate(mesh.faces):
+        for v in verts:
+            pc[v].add(int(cells[f]))
+            if f < F:
+                pc[v].add(int(mesh.neighbour[f]))
+    return pc
+
+
+def test_vol_to_point_weights_against_a_numpy_restatement():
+    """enhancedVolPointInterpolation.C:165-245 restated with python loops: w = 1/|x_p - C| over pointCells for points off the
+    patches, w = 1/|x_p - Cf| over the patch faces at the point otherwise (random cell and patch values, distorted mesh)."""
+    pmap = lambda p: p + 0.03 * np.sin(4.0 * p[:, [2, 0, 1]])
+    c = cases.cantilever(4, 3, 3, L=2.0, general=True)
+    c.mesh = M.hex_box_general(4, 3, 3, 2.0, 1.0, 1.0, names=("fixed", "loaded", "yMin", "yMax", "zMin", "zMax"), point_map=pmap)
+    o = OracleSolid(c)
+    m = c.mesh
+    F = m.nInternalFaces
+    rng = np.random.default_rng(2)
+    D, Db = rng.standard_normal((m.nCells, 3)), rng.standard_normal((m.nBoundaryFaces, 3))
+    o.set("D", D); o.set("D_b", Db)
+    got = o.interpolate_to_points("D")
+    pc = _point_cells(m)
+    pb = [[] for _ in range(m.points.shape[0])]
+    for b in range(m.nBoundaryFaces):
+        for v in m.faces[F + b]:
+            pb[v].append(b)
+    ref = np.zeros_like(got)
+    for p, x in enumerate(m.points):
+        if pb[p]:
+            w = np.array([1.0 / np.linalg.norm(x - m.Cf[F + b]) for b in pb[p]])
+            ref[p] = (w[:, None] * Db[pb[p]]).sum(axis=0) / w.sum()
+        else:
+            cl = sorted(pc[p])
+            w = np.array([1.0 / np.linalg.norm(x - m.C[i]) for i in cl])
+            ref[p] = (w[:, None] * D[cl]).sum(axis=0) / w.sum()
+    assert np.abs(got - ref).max() < 1e-13
+
+
+def test_point_cells_least_squares_against_a_numpy_restatement():
+    """LeastSquaresVectors over the cell-point-cell stencil restated with python loops (stencil: cells sharing a point, boundary
+    faces at the cell's points; dd = sum d d/|d|^2; ls = inv(dd) d/|d|^2) on a random field."""
+    pmap = lambda p: p + 0.03 * np.sin(4.0 * p[:, [2, 0, 1]])
+    c = cases.cantilever(4, 3, 3, L=2.0, general=True, gradScheme=K.GRAD_POINT_CELLS_LEAST_SQUARES)
+    c.mesh = M.hex_box_general(4, 3, 3, 2.0, 1.0, 1.0, names=("fixed", "loaded", "yMin", "yMax", "zMin", "zMax"), point_map=pmap)
+    o = OracleSolid(c)
+    m = c.mesh
+    F = m.nInternalFaces
+    rng = np.random.default_rng(4)
+    D, Db = rng.standard_normal((m.nCells, 3)), rng.standard_normal((m.nBoundaryFaces, 3))
+    o.set("D", D); o.set("D_b", Db)
+    o.op_grad()
+    got = o.get("gradD").reshape(-1, 3, 3)
+    pc = _point_cells(m)
+    cell_pts = [set() for _ in range(m.nCells)]
+    for p, cl in enumerate(pc):
+        for i in cl:
+            cell_pts[i].add(p)
+    pb = [[] for _ in range(m.points.shape[0])]
+    for b in range(m.nBoundaryFaces):
+        for v in m.faces[F + b]:
+            pb[v].append(b)
+    for i in range(m.nCells):
+        nb_cells = sorted({j for p in cell_pts[i] for j in pc[p]} - {i})
+        nb_faces = sorted({b for p in cell_pts[i] for b in pb[p]})
+        X = np.concatenate([m.C[nb_cells], m.Cf[F:][nb_faces]]) if nb_faces else m.C[nb_cells]
+        U = np.concatenate([D[nb_cells], Db[nb_faces]]) if nb_faces else D[nb_cells]
+        d = X - m.C[i]
+        r2 = (d * d).sum(axis=1)
+        dd = np.einsum("ka,kb->ab", d / r2[:, None], d)
+        ls = (np.linalg.inv(dd) @ (d / r2[:, None]).T).T            # [k,3]
+        g = np.einsum("ka,kj->aj", ls, U - D[i])                    # grad_aj = d_a D_j
+        assert np.abs(got[i] - g).max() < 1e-10 * max(1.0, np.abs(g).max()), i
+
+
+def test_uns_gradients_against_a_numpy_restatement():
+    """fvcGradf.C restated with python loops on random vertex values: the in-plane face gradient (edge loop), the Gauss cell
+    gradient (triangle fans, volume from the same fans) and gradDf = fsGrad + n snGrad on internal faces."""
+    pmap = lambda p: p + 0.03 * np.sin(4.0 * p[:, [2, 0, 1]])
+    c = cases.cantilever(3, 3, 2, L=1.5, general=True, solidModel=K.MODEL_UNS_LIN_GEOM)
+    c.mesh = M.hex_box_general(3, 3, 2, 1.5, 1.0, 1.0, names=("fixed", "loaded", "yMin", "yMax", "zMin", "zMax"), point_map=pmap)
+    o = OracleSolid(c)
+    m = c.mesh
+    F, nF = m.nInternalFaces, m.nInternalFaces + m.nBoundaryFaces
+    rng = np.random.default_rng(6)
+    D, pD = rng.standard_normal((m.nCells, 3)), rng.standard_normal((m.points.shape[0], 3))
+    o.set("D", D)
+    o.uns_grad_from_points(pD)
+    gD, gDf = o.get("gradD").reshape(-1, 3, 3), o.get("gradDf").reshape(-1, 3, 3)
+    cells = np.concatenate([m.owner, m.faceCells])
+    G = np.zeros((m.nCells, 3, 3)); V3 = np.zeros(m.nCells)
+    # non-orthogonal part of snGrad(D) needs fvc::grad(D) of the gradScheme (least squares): take it from a second oracle
+    o2 = OracleSolid(cases.cantilever(3, 3, 2, L=1.5, general=True))
+    o2.case.mesh = m
+    for f in range(nF):
+        verts = m.faces[f]
+        P = m.points[verts]; U = pD[verts]
+        n = m.Sf[f] / m.magSf[f]
+        T = np.zeros((3, 3))
+        cp, cf = P.mean(axis=0), U.mean(axis=0)
+        Gf = np.zeros((3, 3)); Vf = 0.0
+        for i in range(4):
+            p0, p1, u0, u1 = P[i], P[(i + 1) % 4], U[i], U[(i + 1) % 4]
+            e = p1 - p0
+            e = e - n * (n @ e)
+            T += np.outer(np.cross(e, n), 0.5 * (u0 + u1))
+            St = 0.5 * np.cross(p0 - cp, p1 - cp)
+            Gf += np.outer(St, (u0 + u1 + cf) / 3.0)
+            Vf += St @ ((cp + p0 + p1) / 3.0)
+        T /= m.magSf[f]
+        G[cells[f]] += Gf; V3[cells[f]] += Vf
+        if f < F:
+            G[m.neighbour[f]] -= Gf; V3[m.neighbour[f]] -= Vf
+            # orthogonal part of the corrected snGrad; the correction-vector part is checked through exactness elsewhere
+            sn = m.nonOrthDeltaCoeffs[f] * (D[m.neighbour[f]] - D[m.owner[f]])
+            resid = gDf[f] - T - np.outer(n, sn)
+            # what is left must be n (x) (corr & grad_f): normal in its first index
+            assert np.abs(resid - np.outer(n, n @ resid)).max() < 1e-10
+    ref = G / (V3 / 3.0)[:, None, None]
+    assert np.abs(gD - ref).max() < 1e-11 * max(1.0, np.abs(ref).max())
+    assert np.allclose(V3 / 3.0, m.V, rtol=2e-2)          # the fan volume is the cell volume up to face warpage
