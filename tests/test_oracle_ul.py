@@ -465,3 +465,46 @@ def test_uns_gradients_against_a_numpy_restatement():
     ref = G / (V3 / 3.0)[:, None, None]
     assert np.abs(gD - ref).max() < 1e-11 * max(1.0, np.abs(ref).max())
     assert np.allclose(V3 / 3.0, m.V, rtol=2e-2)          # the fan volume is the cell volume up to face warpage
+
+
+def test_updated_lagrangian_inertia_is_exact_for_quadratic_rigid_motion():
+    """fvm::d2dt2(rho, DD) + fvc::d2dt2(rho, D.oldTime()) (nonLinGeomUpdatedLagSolid.C:173-176) with the backward scheme is
+    backward ddt applied twice to D = D.old + DD: exact for D(t) = a t^2 once every old-time level of both chains holds the
+    quadratic (DD.o .. DD.oooo, D.o .. D.ooooo: from the seventh step), A DD - source = rho V 2a for a traction-free body that
+    is translated rigidly, with the mesh moved after every step.  Euler: first order, the same identity with an O(dt) defect
+    only in the start-up."""
+    import scipy.sparse as sp
+    dt, a = 1e-3, np.array([3.0, -2.0, 0.5])
+    for scheme in (K.D2DT2_BACKWARD, K.D2DT2_EULER):
+        mesh = M.hex_box_general(4, 3, 3, 2.0, 1.0, 1.0, names=("a", "b", "c", "d", "e", "f"))
+        bcs = {p.name: K.solidTraction((0.0, 0.0, 0.0)) for p in mesh.patches}
+        law = K.mechanical_law("neoHookeanElastic", rho=1000.0, E=3e6, nu=0.3)
+        c = K.SolidCase(mesh, bcs, law, K.default_controls(solidModel=K.MODEL_NONLIN_UL, d2dt2Scheme=scheme, deltaT=dt, deltaT0=dt,
+                                                           stabilisation=K.STAB_NONE))
+        o = OracleSolid(c)
+        N = mesh.nCells
+        rigid = lambda t: np.tile(a * t * t, (N, 1))
+        ok_steps = 0
+        for step in range(1, 10):
+            o.new_timestep(dt)
+            o.set("DD", rigid(step * dt) - rigid((step - 1) * dt))
+            o.set("D", rigid(step * dt))
+            o.initialise()                     # boundary values and gradient of the rigid increment (zero strain)
+            o.op_assemble()
+            m = c.mesh
+            src, diag, upper = o.get("source"), o.get("diag"), o.get("upper")
+            DD = o.get("DD")
+            res = np.zeros((N, 3))
+            for q in range(3):
+                A = sp.coo_matrix((np.concatenate([diag[:, q], upper, upper]),
+                                   (np.concatenate([np.arange(N), m.owner, m.neighbour]), np.concatenate([np.arange(N), m.neighbour, m.owner]))),
+                                  shape=(N, N)).tocsr()
+                res[:, q] = A @ DD[:, q] - src[:, q]
+            exact = 1000.0 * m.V[:, None] * 2.0 * a[None, :]
+            if step >= 7 or (scheme == K.D2DT2_EULER and step >= 4):
+                assert np.abs(res - exact).max() < 1e-6 * np.abs(exact).max(), (scheme, step)
+                ok_steps += 1
+            o.update_total_fields()            # rho / relJ (relJ = 1) and the rigid mesh motion
+            assert np.allclose(o.get("rho"), 1000.0, rtol=1e-12)
+        assert ok_steps >= 3
+        assert np.allclose(c.mesh.C - mesh.C, a * (9 * dt) ** 2, atol=1e-12)       # the mesh followed the body
