@@ -508,3 +508,43 @@ def test_updated_lagrangian_inertia_is_exact_for_quadratic_rigid_motion():
             assert np.allclose(o.get("rho"), 1000.0, rtol=1e-12)
         assert ok_steps >= 3
         assert np.allclose(c.mesh.C - mesh.C, a * (9 * dt) ** 2, atol=1e-12)       # the mesh followed the body
+
+
+def test_pressure_equation_against_a_scipy_restatement():
+    """The first pressure solve (grad(sigmaHyd) still zero) restated with scipy: (V + sum a) p_P - sum a p_N = V p_explicit with
+    a = scale * interpolate(impK/DEqnA) magSf nonOrthDeltaCoeffs, DEqnA = component-averaged diagonal / V (mechanicalLaw.C:1432-1453),
+    solved directly; then grad(sigmaHyd) of that field is the gradScheme's gradient with zero-gradient patches."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    c = _beam_with_pressure_eqn(4, True, tolerance=1e-14, relTol=0.0)
+    o = OracleSolid(c)
+    m = c.mesh
+    N, F = m.nCells, m.nInternalFaces
+    rng = np.random.default_rng(8)
+    g = 1e-4 * rng.standard_normal((N, 9))
+    o.set("gradD", g)
+    o.op_assemble()                                   # the momentum diagonal DEqnA is built from
+    diag = o.get("diag")
+    o.op_correct()
+    p = o.get("sigmaHyd")
+    pExp = c.law.K * (g[:, 0] + g[:, 4] + g[:, 8])
+    impK = 2 * c.law.mu + c.law.lambda_
+    r = impK / (diag.mean(axis=1) / m.V)
+    w = m.weights[:F]
+    a = c.law.pressureSmoothingScaleFactor * (w * r[m.owner] + (1 - w) * r[m.neighbour]) * m.magSf[:F] * m.nonOrthDeltaCoeffs[:F]
+    d = m.V + np.bincount(m.owner, weights=a, minlength=N) + np.bincount(m.neighbour, weights=a, minlength=N)
+    A = sp.coo_matrix((np.concatenate([d, -a, -a]), (np.concatenate([np.arange(N), m.owner, m.neighbour]),
+                                                    np.concatenate([np.arange(N), m.neighbour, m.owner]))), shape=(N, N)).tocsc()
+    ref = spla.spsolve(A, m.V * pExp)
+    assert rel_l2(p, ref) < 1e-10
+    # sigma carries the solved hydrostatic stress; the smoothing is active
+    s = o.get("sigma")
+    assert np.allclose((s[:, 0] + s[:, 3] + s[:, 5]) / 3.0, p, rtol=0, atol=1e-9 * np.abs(p).max())
+    assert rel_l2(p, pExp) > 1e-2
+    # grad(sigmaHyd): least squares with zero-gradient patch values (p_b = p_P)
+    lsP, lsN = o.ls_vectors()
+    gp = np.zeros((N, 3))
+    dp = p[m.neighbour] - p[m.owner]
+    for q in range(3):
+        gp[:, q] = np.bincount(m.owner, weights=lsP[:F, q] * dp, minlength=N) - np.bincount(m.neighbour, weights=lsN[:, q] * dp, minlength=N)
+    assert rel_l2(o.get("gradSigmaHyd"), gp) < 1e-10
