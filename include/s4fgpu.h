@@ -158,11 +158,12 @@ typedef struct {
     double g[3];           /* constant/g */
     double deltaT, deltaT0;
     int chebyshevDegree;   /* S4F_PRECOND_CHEBYSHEV only */
-    int checkEvery;        /* host polls the device-side convergence flags every n PCG iterations */
+    int checkEvery;        /* stream-launched solves (DIC, Chebyshev, PBiCGStab): host polls the device-side convergence flags every n iterations;
+                              PCG with the diagonal / GAMG preconditioner runs as one CUDA graph with a device-side loop instead */
     int gamgSinglePrecision;   /* S4F_PRECOND_GAMG: 1 = V-cycle in fp32 (PCG itself stays fp64), 0 = fp64 */
     double gamgOverCorrection; /* S4F_PRECOND_GAMG: fixed scaling of the coarse-grid correction (<= 0: 2.2) */
     int gamgSmootherDegree;    /* S4F_PRECOND_GAMG: Chebyshev-Jacobi degree of the pre- and post-smoother (<= 0: 3) */
-    int gamgCycle;             /* S4F_PRECOND_GAMG: 0 = V-cycle, 1 = W-cycle, 2 = K-cycle on level 1 (two flexible-CG steps; single rank) */
+    int gamgCycle;             /* S4F_PRECOND_GAMG: 0 = V-cycle, 1 = W-cycle, 2 = K-cycle on level 1 (two flexible-CG steps) */
     double gamgSmootherRatio;  /* S4F_PRECOND_GAMG: lower end of the Chebyshev interval as a fraction of the upper (<= 0: 0.3) */
 } s4fgpu_controls;
 
@@ -187,9 +188,11 @@ int s4fgpu_destroy(s4fgpu_handle h);
 const char* s4fgpu_last_error(s4fgpu_handle h);   /* h may be NULL: last creation error */
 int s4fgpu_version(void);
 
-/* Parallel runs ([OF-ext] Pstream / processor patches -> NCCL over NVLink).  Rank 0
- * obtains an id, the host broadcasts it (Pstream in the plugin, torch.distributed in the python
- * harness), every rank calls comm_init.  Without comm_init the handle is a serial run. */
+/* Parallel runs ([OF-ext] Pstream / processor patches).  Rank 0 obtains an id, the host
+ * broadcasts it (Pstream in the plugin, torch.distributed in the python harness), every rank calls
+ * comm_init (collective).  Without comm_init the handle is a serial run.  NCCL carries the set-up
+ * traffic only; halos, reductions and the coarse-level gather of the iteration run over cudaIpc-mapped
+ * peer memory (NVLink), so every GPU of the run must be peer-accessible from every other one. */
 int s4fgpu_get_unique_id(char id[128]);
 int s4fgpu_comm_init(s4fgpu_handle h, int nRanks, int rank, const char id[128]);
 
@@ -310,6 +313,10 @@ int s4fgpu_time_kernel(s4fgpu_handle h, int kernel, int reps, int flushL2,
  * (sizes[maxLevels]), algorithmic bytes of one V-cycle and the host set-up time. */
 int s4fgpu_gamg_info(s4fgpu_handle h, int* nLevels, int* sizes, int maxLevels, double* bytesPerApply,
                      double* setupSeconds);
+/* decomposed runs: how many levels (from the finest) are distributed, one part per rank with halo exchanges
+ * ([OF-ext] GAMG processor interfaces); the levels below are gathered and replicated.  sizes[] of
+ * s4fgpu_gamg_info holds this rank's part on the distributed levels. */
+int s4fgpu_gamg_distributed_levels(s4fgpu_handle h);
 
 /* CUDA-event timer on the library's own stream (torch.cuda.Event only sees torch's stream), and a
  * stream synchronise.  timer_stop returns the device time in milliseconds since timer_start. */

@@ -15,8 +15,11 @@
 //     global dot products per level; a constant keeps the preconditioner linear and costs nothing);
 //   * coarsest level (<= 512 cells): dense inverse applied by one small kernel;
 //   * optional fp32 V-cycle: the preconditioner only has to be an SPD approximation, PCG stays fp64.
-// Multi-rank: the hierarchy is rank-local (couplings across processor patches are dropped in the
-// preconditioner only, i.e. block-Jacobi over ranks, like DIC in OpenFOAM); Amul in PCG is exact.
+// Multi-rank (OpenFOAM: GAMG over processor interfaces + processorAgglomeration): every rank agglomerates its own cells;
+// the couplings across processor patches are kept on every level as interface entries with ghost columns, so levels
+// stay DISTRIBUTED (each rank smooths its own aggregates, one peer-memory halo exchange per smoothing step,
+// s4f_comm.cu) until the global level size falls below `replicateBelow` cells; from there the level is gathered to all
+// ranks and the rest of the hierarchy is replicated (identical arithmetic on every rank, no communication).
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -24,7 +27,7 @@
 #include <cstring>
 #include <memory>
 
-#include "s4f_ctx.h"
+#include "s4f_comm.h"
 #include "s4f_dev.cuh"
 
 namespace {
@@ -32,12 +35,17 @@ namespace {
 // ================================================================================================
 // host: agglomeration
 // ================================================================================================
+// couplings of this rank's cells to cells of one neighbour rank, in an order both sides agree on
+struct Iface { int rank = -1; std::vector<int> cell, remote; std::vector<double> a; };
 struct HostLevel {
     int n = 0;
     std::vector<int> own, nei;          // faces, upper-triangular order
     std::vector<double> a;              // positive face coefficient (= -upper)
     std::vector<double> diag[3];
-    std::vector<int> parent;            // aggregate of each cell in the next (coarser) level
+    std::vector<int> parent;            // aggregate of each cell in the next (coarser) level: its index in that level's vectors
+    bool dist = false;                  // one part per rank (n = this rank's cells); false: the whole level on every rank
+    std::vector<Iface> ifc;             // dist: couplings across rank boundaries
+    int childOff = 0, childCnt = 0;     // the range of the next level's cells that this rank's cells feed
 };
 
 // one pair-wise pass: greedy matching of every still-unmatched cell with its strongest unmatched
@@ -276,32 +284,6 @@ __global__ void k_amg_dense(const T* __restrict__ inv, const TB* __restrict__ b,
     if (lane == 0) x[(size_t)q * ldo + i] = (TO)s;
 }
 
-// halo of a level-0 work vector (type T): boundary-cell values -> staging, staging -> ghost slots [N, N+G)
-template <class T>
-__global__ void k_amg_pack(const T* __restrict__ f, const int* __restrict__ sendCells, T* __restrict__ buf, int G, int ld) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 3 * G) return;
-    const int q = i / G, g = i % G;
-    buf[i] = f[(size_t)q * ld + sendCells[g]];
-}
-template <class T>
-__global__ void k_amg_unpack(T* __restrict__ f, const T* __restrict__ buf, int G, int N, int ld) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 3 * G) return;
-    const int q = i / G, g = i % G;
-    f[(size_t)q * ld + N + g] = buf[i];
-}
-// all-gathered level-1 right-hand sides ([rank][3][maxLoc]) -> the replicated level-1 vector
-template <class T>
-__global__ void k_amg_scatter_gathered(const T* __restrict__ recv, T* __restrict__ b, const int* __restrict__ off, const int* __restrict__ cnt,
-                                       int world, int maxLoc, int ldc) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
-    if (r >= world || i >= cnt[r]) return;
-#pragma unroll
-    for (int q = 0; q < 3; q++) b[(size_t)q * ldc + off[r] + i] = recv[((size_t)r * 3 + q) * maxLoc + i];
-}
-
 template <class T>
 __global__ void k_amg_convert(const double* __restrict__ in, T* __restrict__ out, long long n) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -330,19 +312,35 @@ __global__ void k_gather_upper(const int* __restrict__ faceEntry, const double* 
 // x = (alpha1/rho1 - gamma alpha2/(rho1 rho2)) c1 + (alpha2/rho2) c2.
 struct KcScalars { double rho1[3], alpha1[3], gamma[3], beta[3], alpha2[3]; };
 
-// v = A c (row gather over the level's SELL rows) with the dot products the step needs, accumulated by atomics:
-// STEP 1: rho1 += c.v, alpha1 += c.b;   STEP 2: gamma += c.v1, beta += c.v, alpha2 += c.r
+template <int STEP>
+struct FinKc {
+    KcScalars* S;
+    __device__ void operator()(const double* tot) const {
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            if (STEP == 1) { S->rho1[q] = tot[q]; S->alpha1[q] = tot[3 + q]; }
+            else { S->beta[q] = tot[q]; S->alpha2[q] = tot[3 + q]; S->gamma[q] = tot[6 + q]; }
+        }
+    }
+};
+
+// v = A c (row gather over the level's SELL rows) with the dot products the step needs (deterministic grid reduction,
+// all-reduced over the ranks when the level is distributed):
+// STEP 1: rho1 = c.v, alpha1 = c.b;   STEP 2: beta = c.v, alpha2 = c.r, gamma = c.v1
 template <class T, int STEP>
 __global__ void __launch_bounds__(S4F_AMG_BLOCK, 4) k_kc_amul(const int* __restrict__ slicePtr, const int* __restrict__ col,
                                                               const T* __restrict__ a, const T* __restrict__ dg, const T* __restrict__ cvec,
                                                               const T* __restrict__ bvec /* b (step 1) or r (step 2) */,
                                                               const T* __restrict__ v1, T* __restrict__ v, int n, int ld, int nSlices,
-                                                              KcScalars* S, const int* __restrict__ act) {
+                                                              KcScalars* S, const int* __restrict__ act, RedCtx red) {
     const bool aq[3] = {act[0] != 0, act[1] != 0, act[2] != 0};
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nWarps = (gridDim.x * blockDim.x) >> 5;
-    double d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0}, d2[3] = {0, 0, 0};
+    constexpr int NV = (STEP == 1) ? 6 : 9;
+    double d[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) d[i] = 0;
     for (int s = warp; s < nSlices; s += nWarps) {
         const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
         const int row = s * 32 + lane;
@@ -362,23 +360,13 @@ __global__ void __launch_bounds__(S4F_AMG_BLOCK, 4) k_kc_amul(const int* __restr
                 const T cv = cvec[j];
                 const T vv = dg[j] * cv - acc[q];
                 v[j] = vv;
-                d0[q] += (double)cv * (double)vv;
-                d1[q] += (double)cv * (double)bvec[j];
-                if (STEP == 2) d2[q] += (double)cv * (double)v1[j];
+                d[q] += (double)cv * (double)vv;
+                d[3 + q] += (double)cv * (double)bvec[j];
+                if constexpr (STEP == 2) d[6 + q] += (double)cv * (double)v1[j];
             }
         }
     }
-#pragma unroll
-    for (int q = 0; q < 3; q++) {
-        if (!aq[q]) continue;
-        double x0 = d0[q], x1 = d1[q], x2 = d2[q];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { x0 += __shfl_xor_sync(0xffffffffu, x0, o); x1 += __shfl_xor_sync(0xffffffffu, x1, o); x2 += __shfl_xor_sync(0xffffffffu, x2, o); }
-        if (lane == 0) {
-            if (STEP == 1) { atomicAdd(&S->rho1[q], x0); atomicAdd(&S->alpha1[q], x1); }
-            else { atomicAdd(&S->beta[q], x0); atomicAdd(&S->alpha2[q], x1); atomicAdd(&S->gamma[q], x2); }
-        }
-    }
+    grid_reduce<NV, OpSum>(d, red, FinKc<STEP>{S});
 }
 
 // r = b - (alpha1/rho1) v1
@@ -416,18 +404,34 @@ __global__ void k_kc_final(const T* __restrict__ c1, const T* __restrict__ c2, T
     }
 }
 
+// device copy of the active components (a kernel, not a memcpy node: the cycle is replayed inside a CUDA graph loop)
+template <class T>
+__global__ void __launch_bounds__(S4F_BLOCK) k_amg_copy(const T* __restrict__ src, T* __restrict__ dst, int n, int ld, const int* __restrict__ act) {
+    const int a[3] = {act[0], act[1], act[2]};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+#pragma unroll
+        for (int q = 0; q < 3; q++) if (a[q]) dst[(size_t)q * ld + i] = src[(size_t)q * ld + i];
+}
+
 // ================================================================================================
 // hierarchy
 // ================================================================================================
 template <class T>
 struct Level {
-    int n = 0, ld = 0, nSlices = 0;
+    int n = 0, nGhost = 0, ld = 0, nSlices = 0;
     const int* slicePtr = nullptr; const int* col = nullptr; const T* a = nullptr;   // level 0 aliases the fine rows
     DevBuf<int> slicePtrB, colB; DevBuf<T> aB;
     DevBuf<T> dg, rD;                   // 3*ld
-    DevBuf<int> parent;                 // [n] -> next level
+    DevBuf<int> parent;                 // [n] -> index in the next level's vectors
     DevBuf<int> childPtr, child;        // children lists of THIS level's cells in the finer level
     DevBuf<T> b, x, x2, d, t;           // 3*ld work vectors
+    bool dist = false;                  // one part per rank; ghost columns [n, n+nGhost) filled by `halo`
+    S4fHaloPlan* halo = nullptr; bool ownHalo = false;
+    // transition to the replicated part of the hierarchy: this (distributed) level restricts into `gsend`, which is
+    // gathered to every rank as the right-hand side of the next level
+    S4fGatherPlan* gather = nullptr; DevBuf<T> gsend; int gLocal = 0, gStride = 0;
+    double nnz = 0;
+    ~Level() { if (ownHalo) s4f_halo_plan_destroy(halo); s4f_gather_plan_destroy(gather); }
 };
 
 }  // namespace
@@ -438,6 +442,7 @@ struct S4fAmg {
     virtual int step0(s4fgpu_ctx* c, const double* r3, const int* act) = 0;   // one fine-level smoothing step alone (timing)
     double step0Bytes = 0;
     std::vector<int> sizes;
+    std::vector<int> distributed;       // per level: 1 = one part per rank (sizes[] is then this rank's part)
     double bytesPerApply = 0;
     double setupSeconds = 0;
 };
@@ -455,36 +460,38 @@ struct Hierarchy : S4fAmg {
     const int* act = nullptr;           // device int[3]: components to work on (the fused PCG's active flags, or all ones)
     double omega = 2.2;
     double theta = 0, delta = 0;
-    // multi-rank: level 0 is this rank's part of the mesh (ghost columns, halo exchange per SpMV); levels >= 1
-    // are the GLOBAL coarse levels, replicated on every rank and fed by an all-gather of the restricted residual
-    bool dist = false;
-    int n1Local = 0, n1Off = 0, maxLoc = 0;
-    DevBuf<T> hsend, hrecv, gsend, grecv;
-    DevBuf<int> rankOff, rankCnt;
 
-    static ncclDataType_t nccl_t() { return sizeof(T) == 4 ? ncclFloat : ncclDouble; }
-    int halo0(s4fgpu_ctx* c, T* x) {
-        if (!dist || c->G == 0) return 0;
-        const int G = c->G;
-        k_amg_pack<T><<<(3 * G + 255) / 256, 256, 0, c->stream>>>(x, c->sendCells.p, hsend.p, G, c->ld);
-        S4F_CHECK_NCCL(c, ncclGroupStart());
-        for (const auto& nb : c->nbrs)
-            for (int q = 0; q < 3; q++) {
-                S4F_CHECK_NCCL(c, ncclSend(hsend.p + (size_t)q * G + nb.sendOff, nb.count, nccl_t(), nb.rank, c->comm, c->stream));
-                S4F_CHECK_NCCL(c, ncclRecv(hrecv.p + (size_t)q * G + nb.sendOff, nb.count, nccl_t(), nb.rank, c->comm, c->stream));
-            }
-        S4F_CHECK_NCCL(c, ncclGroupEnd());
-        k_amg_unpack<T><<<(3 * G + 255) / 256, 256, 0, c->stream>>>(x, hrecv.p, G, c->N, c->ld);
-        c->launches += 2;
-        return 0;
+    int halo(s4fgpu_ctx* c, Level<T>& L, T* x) {
+        if (!L.dist || !L.halo) return 0;
+        return s4f_halo_run<T>(c, L.halo, x, L.ld, 3, L.n);
     }
 
+    // rows of a coarse level: interior neighbours (lower, upper), then the couplings across rank boundaries (ghost columns)
     int build_level_rows(s4fgpu_ctx* c, Level<T>& L, const HostLevel& H) {
         const int n = H.n;
-        L.n = n; L.ld = ((n + 31) / 32) * 32; L.nSlices = (n + 31) / 32;
+        L.n = n; L.nSlices = (n + 31) / 32; L.dist = H.dist;
+        // ghosts: per neighbour the distinct remote cells in ascending order; send list: the distinct local cells
+        std::vector<int> nbrRank, nbrCount, sendCells;
+        std::vector<std::vector<int>> ghostIds(H.ifc.size());
+        int nGhost = 0;
+        std::vector<int> ghostBase(H.ifc.size(), 0);
+        for (size_t k = 0; k < H.ifc.size(); k++) {
+            const Iface& I = H.ifc[k];
+            std::vector<int> g(I.remote), sc(I.cell);
+            std::sort(g.begin(), g.end()); g.erase(std::unique(g.begin(), g.end()), g.end());
+            std::sort(sc.begin(), sc.end()); sc.erase(std::unique(sc.begin(), sc.end()), sc.end());
+            ghostIds[k] = g; ghostBase[k] = nGhost; nGhost += (int)g.size();
+            // what I send to this neighbour are my distinct cells; what I receive are its distinct cells: both sides sort
+            // by the owner's local index, so the orders agree (the two counts differ in general)
+            nbrRank.push_back(I.rank); nbrCount.push_back((int)sc.size());
+            sendCells.insert(sendCells.end(), sc.begin(), sc.end());
+        }
+        L.nGhost = nGhost;
+        L.ld = ((n + nGhost + 31) / 32) * 32; if (L.ld == 0) L.ld = 32;
         std::vector<int> cnt(n, 0);
         const size_t F = H.own.size();
         for (size_t f = 0; f < F; f++) { cnt[H.own[f]]++; cnt[H.nei[f]]++; }
+        for (const Iface& I : H.ifc) for (int cl : I.cell) cnt[cl]++;
         std::vector<long long> rowPtr(n + 1, 0);
         for (int i = 0; i < n; i++) rowPtr[i + 1] = rowPtr[i] + cnt[i];
         std::vector<int> rc(rowPtr[n]); std::vector<double> rv(rowPtr[n]);
@@ -492,6 +499,13 @@ struct Hierarchy : S4fAmg {
             std::vector<long long> cur(rowPtr.begin(), rowPtr.end() - 1);
             for (size_t f = 0; f < F; f++) { long long e = cur[H.nei[f]]++; rc[e] = H.own[f]; rv[e] = H.a[f]; }
             for (size_t f = 0; f < F; f++) { long long e = cur[H.own[f]]++; rc[e] = H.nei[f]; rv[e] = H.a[f]; }
+            for (size_t k = 0; k < H.ifc.size(); k++) {
+                const Iface& I = H.ifc[k];
+                for (size_t f = 0; f < I.cell.size(); f++) {
+                    const int g = (int)(std::lower_bound(ghostIds[k].begin(), ghostIds[k].end(), I.remote[f]) - ghostIds[k].begin());
+                    long long e = cur[I.cell[f]]++; rc[e] = n + ghostBase[k] + g; rv[e] = I.a[f];
+                }
+            }
         }
         std::vector<int> sp(L.nSlices + 1, 0);
         for (int s = 0; s < L.nSlices; s++) {
@@ -513,11 +527,20 @@ struct Hierarchy : S4fAmg {
                 }
             }
         }
+        L.nnz = (double)rowPtr[n];
         S4F_CHECK_CUDA(c, L.slicePtrB.upload(sp)); S4F_CHECK_CUDA(c, L.colB.upload(hc)); S4F_CHECK_CUDA(c, L.aB.upload(ha));
         L.slicePtr = L.slicePtrB.p; L.col = L.colB.p; L.a = L.aB.p;
         std::vector<T> hd(3 * (size_t)L.ld, (T)1), hr(3 * (size_t)L.ld, (T)1);
         for (int q = 0; q < 3; q++) for (int i = 0; i < n; i++) { hd[(size_t)q * L.ld + i] = (T)H.diag[q][i]; hr[(size_t)q * L.ld + i] = (T)(1.0 / H.diag[q][i]); }
         S4F_CHECK_CUDA(c, L.dg.upload(hd)); S4F_CHECK_CUDA(c, L.rD.upload(hr));
+        if (H.dist) {
+            // receive counts = distinct remote cells per neighbour; the plan moves nbrCount values out and expects the same
+            // number in: the two sides' lists are mirror images (my send list to r = r's ghost list of me)
+            std::vector<int> recvCount;
+            for (size_t k = 0; k < H.ifc.size(); k++) recvCount.push_back((int)ghostIds[k].size());
+            int rcx = s4f_halo_plan_create_asym(c, nbrRank, nbrCount, recvCount, sendCells, 3, &L.halo); if (rcx) return rcx;
+            L.ownHalo = true;
+        }
         return 0;
     }
     int alloc_work(s4fgpu_ctx* c, Level<T>& L) {
@@ -526,11 +549,11 @@ struct Hierarchy : S4fAmg {
         S4F_CHECK_CUDA(c, L.d.alloc(m)); S4F_CHECK_CUDA(c, L.t.alloc(m));
         return 0;
     }
-    // parent[i] = coarse cell of fine cell i (global numbering); the children lists cover the coarse cells
-    // [off, off+nc) that this rank's fine cells feed (off = 0, nc = all on replicated / serial levels)
-    int set_transfer(s4fgpu_ctx* c, Level<T>& fine, Level<T>& coarse, const std::vector<int>& parent, int nc, int off = 0) {
-        S4F_CHECK_CUDA(c, fine.parent.upload(parent));
-        std::vector<int> ptr(nc + 1, 0), ch(parent.size());
+    // parent[i] = index of the coarse cell of fine cell i in the next level's vectors; the children lists cover the coarse
+    // cells [off, off+nc) that this rank's fine cells feed (all of them on replicated / serial levels)
+    int set_transfer(s4fgpu_ctx* c, Level<T>& fine, Level<T>& coarse, const std::vector<int>& parent, int nc, int off) {
+        S4F_CHECK_CUDA(c, fine.parent.upload(parent.empty() ? std::vector<int>(1, 0) : parent));
+        std::vector<int> ptr(nc + 1, 0), ch(std::max<size_t>(parent.size(), 1), 0);
         for (size_t i = 0; i < parent.size(); i++) ptr[parent[i] - off + 1]++;
         for (int i = 0; i < nc; i++) ptr[i + 1] += ptr[i];
         std::vector<int> cur(ptr.begin(), ptr.end() - 1);
@@ -540,14 +563,13 @@ struct Hierarchy : S4fAmg {
     }
 
     static int step_grid(const s4fgpu_ctx* c, const Level<T>& L) { return s4f_grid(c->numSMs, (long long)L.nSlices * 32, 4); }
-    // algorithmic bytes of one application (for the roofline report): every array read / written once
-    double bytes_per_apply(int fineLdUnused) const {
-        (void)fineLdUnused;
+    // algorithmic bytes of one application on this rank (for the roofline report): every array read / written once
+    double bytes_per_apply() const {
         double tot = 0, below1 = 0;
         const double sT = sizeof(T);
         for (size_t l = 0; l + 1 < lv.size(); l++) {
             const Level<T>& L = *lv[l];
-            const double n = L.n, nz = nnz[l], sB = (l == 0) ? 8.0 : sT, sO = (l == 0) ? 8.0 : sT, nc = lv[l + 1]->n;
+            const double n = L.n, nz = L.nnz, sB = (l == 0) ? 8.0 : sT, sO = (l == 0) ? 8.0 : sT, nc = lv[l + 1]->n;
             const double mat = nz * (4 + sT) + n * 0.125;
             double t = 0;
             t += 3 * n * (sT + sB + 2 * sT);                                         // first
@@ -560,31 +582,31 @@ struct Hierarchy : S4fAmg {
             tot += t;
             if (l >= 1) below1 += t;
         }
-        if (cycle == 2 && lv.size() > 2 && !dist) {      // K-cycle: a second V-cycle from level 1, two A_1 products with their dots, r, x, two copies
-            const double n1 = lv[1]->n, mat1 = nnz[1] * (4 + sT) + n1 * 0.125;
+        if (cycle == 2 && lv.size() > 2) {      // K-cycle: a second V-cycle from level 1, two A_1 products with their dots, r, x, two copies
+            const double n1 = lv[1]->n, mat1 = lv[1]->nnz * (4 + sT) + n1 * 0.125;
             tot += below1 + 2 * (mat1 + 3 * n1 * 4 * sT) + 3 * n1 * 3 * sT + 3 * n1 * 3 * sT + 2 * 3 * n1 * 2 * sT;
         }
         return tot;
     }
-    std::vector<double> nnz;
 
     // ---- smoothing on one level ---------------------------------------------------------------
     template <class TB, class TO>
-    void step(s4fgpu_ctx* c, Level<T>& L, const TB* b, int ldb, const T* xin, TO* xout, int ldo, double c1, double c2) {
+    int step(s4fgpu_ctx* c, Level<T>& L, const TB* b, int ldb, const T* xin, TO* xout, int ldo, double c1, double c2) {
         const int grid = step_grid(c, L);
-        if (dist && &L == lv[0].get()) halo0(c, const_cast<T*>(xin));
+        int rc = halo(c, L, const_cast<T*>(xin)); if (rc) return rc;
         k_amg_step<T, TB, TO, 0><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, L.rD.p, b, xin, L.d.p, xout, L.n, L.ld, ldb, ldo,
                                                                      L.nSlices, (T)c1, (T)c2, act);
         c->launches++;
+        return 0;
     }
     // Chebyshev-Jacobi of degree `deg`; fromZero: x0 = 0.  Result ends in *xres (L.x or L.x2), or, when
     // `out` is given (level 0), the last step writes the fp64 output directly.
     template <class TB>
-    T* smooth(s4fgpu_ctx* c, Level<T>& L, const TB* b, int ldb, bool fromZero, T* xcur, double* out, int ldo) {
+    int smooth(s4fgpu_ctx* c, Level<T>& L, const TB* b, int ldb, bool fromZero, T* xcur, double* out, int ldo, T** xres) {
         const double sigma = theta / delta;
         double rho = 1.0 / sigma;
         T* other = (xcur == L.x.p) ? L.x2.p : L.x.p;
-        int k0 = 0;
+        int k0 = 0, rc;
         if (fromZero) {
             const int grid = s4f_grid(c->numSMs, L.n);
             k_amg_first<T, TB><<<grid, S4F_BLOCK, 0, c->stream>>>(L.rD.p, b, xcur, L.d.p, L.n, L.ld, ldb, (T)(1.0 / theta), act);
@@ -596,11 +618,12 @@ struct Hierarchy : S4fAmg {
             if (k == 0) { c1 = 0.0; c2 = 1.0 / theta; }
             else { const double rhon = 1.0 / (2.0 * sigma - rho); c1 = rhon * rho; c2 = 2.0 * rhon / delta; rho = rhon; }
             const bool last = (k == deg - 1);
-            if (last && out) { step<TB, double>(c, L, b, ldb, xcur, out, ldo, c1, c2); return nullptr; }
-            step<TB, T>(c, L, b, ldb, xcur, other, L.ld, c1, c2);
+            if (last && out) { if ((rc = step<TB, double>(c, L, b, ldb, xcur, out, ldo, c1, c2))) return rc; *xres = nullptr; return 0; }
+            if ((rc = step<TB, T>(c, L, b, ldb, xcur, other, L.ld, c1, c2))) return rc;
             std::swap(xcur, other);
         }
-        return xcur;
+        *xres = xcur;
+        return 0;
     }
 
     // t = b - A x on level l, restricted into the right-hand side of level l+1
@@ -609,22 +632,24 @@ struct Hierarchy : S4fAmg {
         Level<T>& L = *lv[l];
         Level<T>& C = *lv[l + 1];
         const int grid = step_grid(c, L);
-        const bool d0 = dist && l == 0;
-        if (d0) { int rc = halo0(c, x); if (rc) return rc; }
+        int rc = halo(c, L, x); if (rc) return rc;
         k_amg_step<T, TB, T, 1><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, L.rD.p, b, x, L.d.p, L.t.p, L.n, L.ld, ldb, L.ld,
                                                                        L.nSlices, (T)0, (T)0, act);
         c->launches++;
-        if (!d0) {
+        if (!L.gather) {
             k_amg_restrict<T><<<(C.n + 127) / 128, 128, 0, c->stream>>>(C.childPtr.p, C.child.p, L.t.p, C.b.p, C.n, L.ld, C.ld, act);
             c->launches++;
             return 0;
         }
-        // this rank's aggregates -> packed [3][maxLoc]; all-gather over NVLink; scatter into the replicated vector
-        k_amg_restrict<T><<<(n1Local + 127) / 128, 128, 0, c->stream>>>(C.childPtr.p, C.child.p, L.t.p, gsend.p, n1Local, L.ld, maxLoc, act);
-        S4F_CHECK_NCCL(c, ncclAllGather(gsend.p, grecv.p, 3 * (size_t)maxLoc, nccl_t(), c->comm, c->stream));
-        dim3 g2((maxLoc + 255) / 256, c->nRanks);
-        k_amg_scatter_gathered<T><<<g2, 256, 0, c->stream>>>(grecv.p, C.b.p, rankOff.p, rankCnt.p, c->nRanks, maxLoc, C.ld);
-        c->launches += 2;
+        // this rank's aggregates -> packed [3][gStride]; pushed to every rank over NVLink into the replicated right-hand side
+        k_amg_restrict<T><<<(L.gLocal + 127) / 128, 128, 0, c->stream>>>(C.childPtr.p, C.child.p, L.t.p, L.gsend.p, L.gLocal, L.ld, L.gStride, act);
+        c->launches++;
+        return s4f_gather_run<T>(c, L.gather, L.gsend.p, L.gStride, C.b.p, C.ld, act);
+    }
+
+    int copy(s4fgpu_ctx* c, Level<T>& L, const T* src, T* dst) {
+        k_amg_copy<T><<<s4f_grid(c->numSMs, L.n), S4F_BLOCK, 0, c->stream>>>(src, dst, L.n, L.ld, act);
+        c->launches++;
         return 0;
     }
 
@@ -639,10 +664,11 @@ struct Hierarchy : S4fAmg {
             return 0;
         }
         Level<T>& C = *lv[l + 1];
-        T* x = smooth<TB>(c, L, b, ldb, true, L.x.p, nullptr, 0);                 // pre-smoothing from zero
-        { int rr = residual_restrict<TB>(c, l, b, ldb, x); if (rr) return rr; }
         int rc;
-        const bool kcycle = (cycle == 2 && l == 0 && lv.size() > 2 && !dist);
+        T* x = nullptr;
+        if ((rc = smooth<TB>(c, L, b, ldb, true, L.x.p, nullptr, 0, &x))) return rc;       // pre-smoothing from zero
+        if ((rc = residual_restrict<TB>(c, l, b, ldb, x))) return rc;
+        const bool kcycle = (cycle == 2 && l == 0 && lv.size() > 2);
         if (kcycle) { rc = kcycle_level1(c); if (rc) return rc; }
         else { rc = cycle_level<T>(c, l + 1, C.b.p, C.ld, nullptr, 0); if (rc) return rc; }
         {
@@ -657,31 +683,28 @@ struct Hierarchy : S4fAmg {
             k_amg_prolong<T><<<gridp, S4F_BLOCK, 0, c->stream>>>(L.parent.p, C.x.p, x, L.n, L.ld, C.ld, (T)omega, act);
             c->launches++;
         }
-        T* xr = smooth<TB>(c, L, b, ldb, false, x, out, ldo);                      // post-smoothing
-        if (!out && xr != L.x.p) {   // callers read the level result from L.x
-            S4F_CHECK_CUDA(c, cudaMemcpyAsync(L.x.p, xr, 3 * (size_t)L.ld * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
-        }
+        T* xr = nullptr;
+        if ((rc = smooth<TB>(c, L, b, ldb, false, x, out, ldo, &xr))) return rc;           // post-smoothing
+        if (!out && xr != L.x.p) copy(c, L, xr, L.x.p);   // callers read the level result from L.x
         return 0;
     }
 
     // two FCG steps on A_1 x = C.b preconditioned by the V-cycle from level 1; result in lv[1]->x
     int kcycle_level1(s4fgpu_ctx* c) {
         Level<T>& C = *lv[1];
-        const size_t m = 3 * (size_t)C.ld;
-        if (kc1.n != m) {
-            S4F_CHECK_CUDA(c, kc1.alloc(m)); S4F_CHECK_CUDA(c, kv1.alloc(m)); S4F_CHECK_CUDA(c, kr.alloc(m)); S4F_CHECK_CUDA(c, kc2.alloc(m));
-            S4F_CHECK_CUDA(c, kS.alloc(1));
-        }
         const int grid = step_grid(c, C), gv = (C.n + 255) / 256;
-        S4F_CHECK_CUDA(c, cudaMemsetAsync(kS.p, 0, sizeof(KcScalars), c->stream));
+        // a distributed level 1 all-reduces its dot products; on a replicated one every rank computes the same sums
+        const RedCtx red = C.dist ? c->red() : RedCtx{c->partials.p, c->ticket.p, nullptr};
         int rc = cycle_level<T>(c, 1, C.b.p, C.ld, nullptr, 0); if (rc) return rc;                       // c1 = V(b)
-        S4F_CHECK_CUDA(c, cudaMemcpyAsync(kc1.p, C.x.p, m * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
-        k_kc_amul<T, 1><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(C.slicePtr, C.col, C.a, C.dg.p, kc1.p, C.b.p, nullptr, kv1.p, C.n, C.ld, C.nSlices, kS.p, act);
+        copy(c, C, C.x.p, kc1.p);
+        if ((rc = halo(c, C, kc1.p))) return rc;
+        k_kc_amul<T, 1><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(C.slicePtr, C.col, C.a, C.dg.p, kc1.p, C.b.p, nullptr, kv1.p, C.n, C.ld, C.nSlices, kS.p, act, red);
         k_kc_resid<T><<<gv, 256, 0, c->stream>>>(C.b.p, kv1.p, kr.p, C.n, C.ld, kS.p, act);
         c->launches += 2;
         rc = cycle_level<T>(c, 1, kr.p, C.ld, nullptr, 0); if (rc) return rc;                            // c2 = V(r)
-        S4F_CHECK_CUDA(c, cudaMemcpyAsync(kc2.p, C.x.p, m * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
-        k_kc_amul<T, 2><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(C.slicePtr, C.col, C.a, C.dg.p, kc2.p, kr.p, kv1.p, C.t.p, C.n, C.ld, C.nSlices, kS.p, act);
+        copy(c, C, C.x.p, kc2.p);
+        if ((rc = halo(c, C, kc2.p))) return rc;
+        k_kc_amul<T, 2><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(C.slicePtr, C.col, C.a, C.dg.p, kc2.p, kr.p, kv1.p, C.t.p, C.n, C.ld, C.nSlices, kS.p, act, red);
         k_kc_final<T><<<gv, 256, 0, c->stream>>>(kc1.p, kc2.p, C.x.p, C.n, C.ld, kS.p, act);
         c->launches += 2;
         return 0;
@@ -708,20 +731,10 @@ struct Hierarchy : S4fAmg {
     }
 };
 
-struct DistInfo { bool on = false; int n1Local = 0, n1Off = 0, maxLoc = 0; std::vector<int> off, cnt; };
-
 template <class T>
-int build(s4fgpu_ctx* c, std::vector<HostLevel>& H, const DistInfo& di) {
+int build(s4fgpu_ctx* c, std::vector<HostLevel>& H) {
     auto* A = new Hierarchy<T>();
     std::unique_ptr<S4fAmg> guard(A);
-    A->dist = di.on; A->n1Local = di.n1Local; A->n1Off = di.n1Off; A->maxLoc = di.maxLoc;
-    if (di.on) {
-        const size_t G = std::max(c->G, 1);
-        S4F_CHECK_CUDA(c, A->hsend.alloc(3 * G)); S4F_CHECK_CUDA(c, A->hrecv.alloc(3 * G));
-        S4F_CHECK_CUDA(c, A->gsend.alloc(3 * (size_t)std::max(di.maxLoc, 1)));
-        S4F_CHECK_CUDA(c, A->grecv.alloc(3 * (size_t)std::max(di.maxLoc, 1) * c->nRanks));
-        S4F_CHECK_CUDA(c, A->rankOff.upload(di.off)); S4F_CHECK_CUDA(c, A->rankCnt.upload(di.cnt));
-    }
     A->deg = c->ctl.gamgSmootherDegree > 0 ? c->ctl.gamgSmootherDegree : 3;
     A->cycle = c->ctl.gamgCycle;
     A->omega = c->ctl.gamgOverCorrection > 0 ? c->ctl.gamgOverCorrection : 2.2;
@@ -735,7 +748,7 @@ int build(s4fgpu_ctx* c, std::vector<HostLevel>& H, const DistInfo& di) {
         Level<T>& L = *A->lv.back();
         int rc;
         if (l == 0) {
-            L.n = c->N; L.ld = c->ld; L.nSlices = c->nSlices;
+            L.n = c->N; L.nGhost = c->G; L.ld = c->ld; L.nSlices = c->nSlices; L.dist = H[0].dist; L.halo = c->halo0; L.nnz = (double)c->nnzOff;
             L.slicePtr = c->slicePtr.p; L.col = c->col.p;
             if (sizeof(T) == sizeof(double)) L.a = reinterpret_cast<const T*>(c->eA.p);
             else {
@@ -750,13 +763,30 @@ int build(s4fgpu_ctx* c, std::vector<HostLevel>& H, const DistInfo& di) {
             if ((rc = A->build_level_rows(c, L, H[l]))) return rc;
         }
         if ((rc = A->alloc_work(c, L))) return rc;
-        if (l == 1 && di.on) { if ((rc = A->set_transfer(c, *A->lv[0], L, H[0].parent, di.n1Local, di.n1Off))) return rc; }
-        else if (l > 0) { if ((rc = A->set_transfer(c, *A->lv[l - 1], L, H[l - 1].parent, H[l].n))) return rc; }
+        if (l > 0) {
+            Level<T>& Fn = *A->lv[l - 1];
+            const HostLevel& HF = H[l - 1];
+            if ((rc = A->set_transfer(c, Fn, L, HF.parent, HF.childCnt, HF.childOff))) return rc;
+            if (HF.dist && !H[l].dist) {        // the distributed part ends here: gather to all ranks
+                std::vector<int> cnt(c->nRanks);
+                if ((rc = s4f_allgather_host(c, &HF.childCnt, sizeof(int), cnt.data()))) return rc;
+                int mx = 1; for (int v : cnt) mx = std::max(mx, v);
+                Fn.gLocal = HF.childCnt; Fn.gStride = ((mx + 31) / 32) * 32;
+                S4F_CHECK_CUDA(c, Fn.gsend.alloc(3 * (size_t)Fn.gStride));
+                if ((rc = s4f_gather_plan_create(c, cnt, &Fn.gather))) return rc;
+            }
+        }
         A->sizes.push_back(H[l].n);
-        A->nnz.push_back(l == 0 ? (double)c->nnzOff : 2.0 * (double)H[l].own.size());
+        A->distributed.push_back(H[l].dist ? 1 : 0);
+    }
+    if (A->lv.size() > 1) {      // K-cycle work vectors on level 1
+        const size_t m = 3 * (size_t)A->lv[1]->ld;
+        S4F_CHECK_CUDA(c, A->kc1.alloc(m)); S4F_CHECK_CUDA(c, A->kv1.alloc(m)); S4F_CHECK_CUDA(c, A->kr.alloc(m)); S4F_CHECK_CUDA(c, A->kc2.alloc(m));
+        S4F_CHECK_CUDA(c, A->kS.alloc(1));
     }
     // dense inverse on the coarsest level
     const HostLevel& HC = H.back();
+    if (HC.dist) { c->err = "GAMG: the coarsest level must be replicated"; return 1; }
     std::vector<T> inv(3 * (size_t)HC.n * HC.n);
     for (int q = 0; q < 3; q++) {
         std::vector<double> iq;
@@ -765,8 +795,8 @@ int build(s4fgpu_ctx* c, std::vector<HostLevel>& H, const DistInfo& di) {
     }
     S4F_CHECK_CUDA(c, A->denseInv.upload(inv));
     S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
-    A->bytesPerApply = A->bytes_per_apply(c->ld);
-    A->step0Bytes = A->nnz[0] * (4 + sizeof(T)) + 0.125 * c->N + 3.0 * c->N * (8 + 5 * sizeof(T) + sizeof(T));   // col,a | b(fp64) x d dg rD in, d x' out
+    A->bytesPerApply = A->bytes_per_apply();
+    A->step0Bytes = A->lv[0]->nnz * (4 + sizeof(T)) + 0.125 * c->N + 3.0 * c->N * (8 + 5 * sizeof(T) + sizeof(T));   // col,a | b(fp64) x d dg rD in, d x' out
     c->amg = guard.release();
     return 0;
 }
@@ -785,6 +815,7 @@ int s4f_download_upper(s4fgpu_ctx* c, double* hostUpper) {
 }
 
 void s4f_amg_destroy(s4fgpu_ctx* c) {
+    if (c->amg) c->graphSerial++;           // captured solves hold pointers into the hierarchy
     delete c->amg;
     c->amg = nullptr;
 }
@@ -811,62 +842,15 @@ int coarsen3(const HostLevel& srcIn, int stopBelow, std::vector<int>& total, Hos
     return nc;
 }
 
-// equal-sized host blocks, all-gathered through device staging (set-up only)
-int allgather_host(s4fgpu_ctx* c, const void* send, size_t bytes, void* recv) {
-    DevBuf<char> ds, dr;
-    S4F_CHECK_CUDA(c, ds.alloc(std::max<size_t>(bytes, 1), false)); S4F_CHECK_CUDA(c, dr.alloc(std::max<size_t>(bytes, 1) * c->nRanks, false));
-    if (bytes) S4F_CHECK_CUDA(c, cudaMemcpyAsync(ds.p, send, bytes, cudaMemcpyHostToDevice, c->stream));
-    S4F_CHECK_NCCL(c, ncclAllGather(ds.p, dr.p, std::max<size_t>(bytes, 1), ncclChar, c->comm, c->stream));
-    S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (bytes) S4F_CHECK_CUDA(c, cudaMemcpy(recv, dr.p, bytes * c->nRanks, cudaMemcpyDeviceToHost));
-    return 0;
-}
-
-// one int per processor-patch face, sent to / received from the rank across the face (patch order)
-int exchange_ghost_ints(s4fgpu_ctx* c, const std::vector<int>& send, std::vector<int>& recv) {
-    const int G = c->G;
-    recv.assign(G, 0);
-    if (G == 0) return 0;
-    DevBuf<int> ds, dr;
-    S4F_CHECK_CUDA(c, ds.upload(send)); S4F_CHECK_CUDA(c, dr.alloc(G));
-    S4F_CHECK_NCCL(c, ncclGroupStart());
-    for (const auto& nb : c->nbrs) {
-        S4F_CHECK_NCCL(c, ncclSend(ds.p + nb.sendOff, nb.count, ncclInt, nb.rank, c->comm, c->stream));
-        S4F_CHECK_NCCL(c, ncclRecv(dr.p + nb.sendOff, nb.count, ncclInt, nb.rank, c->comm, c->stream));
-    }
-    S4F_CHECK_NCCL(c, ncclGroupEnd());
-    S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
-    S4F_CHECK_CUDA(c, cudaMemcpy(recv.data(), dr.p, G * sizeof(int), cudaMemcpyDeviceToHost));
-    return 0;
-}
-
 __global__ void k_gather_entries(const int* __restrict__ idx, const double* __restrict__ eA, double* __restrict__ out, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = eA[idx[i]];
 }
 
-// Multi-rank: aggregate this rank's cells, learn the aggregates of the ghost cells, form this rank's rows of
-// the global level-1 matrix (incl. the couplings across processor patches) and all-gather the pieces, so that
-// every rank holds the same global level 1 and continues the coarsening identically.
-int build_global_level1(s4fgpu_ctx* c, HostLevel& L0, HostLevel& H1, DistInfo& di) {
-    const int N = c->N, G = c->G, world = c->nRanks, rank = c->rank;
-    std::vector<int> parentLoc; HostLevel dummy;
-    const int n1Local = coarsen3(L0, 0, parentLoc, dummy);
-    std::vector<int> cnt(world);
-    int rc = allgather_host(c, &n1Local, sizeof(int), cnt.data()); if (rc) return rc;
-    std::vector<int> off(world + 1, 0);
-    for (int r = 0; r < world; r++) off[r + 1] = off[r] + cnt[r];
-    const int n1Global = off[world], myOff = off[rank];
-    // aggregates of the ghost cells + coefficients of the processor faces
-    std::vector<int> sendP(std::max(G, 1), 0), ghostParent, sendCellsH(std::max(G, 1), 0), entryH(std::max(G, 1), 0);
-    for (const auto& nb : c->nbrs)
-        for (int i = 0; i < nb.count; i++) {
-            const int cell = c->faceCells[c->pStart[nb.patch] + i];
-            sendCellsH[nb.sendOff + i] = cell;
-            sendP[nb.sendOff + i] = myOff + parentLoc[cell];
-        }
-    sendP.resize(G); 
-    if ((rc = exchange_ghost_ints(c, sendP, ghostParent))) return rc;
+// the fine level's couplings across processor patches: cell = faceCells (patch order, which both sides share), remote =
+// the neighbour's cell behind the same face, a = the assembled face coefficient
+int fine_interfaces(s4fgpu_ctx* c, HostLevel& L0) {
+    const int G = c->G;
     std::vector<double> aPf(std::max(G, 1), 0.0);
     if (G > 0) {
         DevBuf<double> d; S4F_CHECK_CUDA(c, d.alloc(G));
@@ -875,41 +859,86 @@ int build_global_level1(s4fgpu_ctx* c, HostLevel& L0, HostLevel& H1, DistInfo& d
         S4F_CHECK_CUDA(c, cudaMemcpyAsync(aPf.data(), d.p, G * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
     }
-    // augmented level: local cells + ghost cells, internal faces + processor faces
-    HostLevel aug; aug.n = N + G;
-    aug.own = L0.own; aug.nei = L0.nei; aug.a = L0.a;
-    for (int g = 0; g < G; g++) { aug.own.push_back(sendCellsH[g]); aug.nei.push_back(N + g); aug.a.push_back(aPf[g]); }
-    for (int q = 0; q < 3; q++) { aug.diag[q] = L0.diag[q]; aug.diag[q].resize(N + G, 0.0); }
-    std::vector<int> agg(N + G);
-    for (int i = 0; i < N; i++) agg[i] = myOff + parentLoc[i];
-    for (int g = 0; g < G; g++) agg[N + g] = ghostParent[g];
-    HostLevel part; galerkin(aug, agg, n1Global, part);
-    // the faces this rank contributes: owner (lower id) among its own aggregates
-    std::vector<int> fo, fn; std::vector<double> fa;
-    for (size_t f = 0; f < part.own.size(); f++)
-        if (part.own[f] >= myOff && part.own[f] < myOff + n1Local) { fo.push_back(part.own[f]); fn.push_back(part.nei[f]); fa.push_back(part.a[f]); }
-    int nF = (int)fo.size();
-    std::vector<int> nFs(world);
-    if ((rc = allgather_host(c, &nF, sizeof(int), nFs.data()))) return rc;
-    int maxF = 1, maxLoc = 1;
-    for (int r = 0; r < world; r++) { maxF = std::max(maxF, nFs[r]); maxLoc = std::max(maxLoc, cnt[r]); }
-    std::vector<int> si(2 * (size_t)maxF, 0), ri(2 * (size_t)maxF * world);
-    std::vector<double> sd((size_t)maxF + 3 * (size_t)maxLoc, 0.0), rd(((size_t)maxF + 3 * (size_t)maxLoc) * world);
-    for (int f = 0; f < nF; f++) { si[f] = fo[f]; si[maxF + f] = fn[f]; sd[f] = fa[f]; }
-    for (int q = 0; q < 3; q++) for (int i = 0; i < n1Local; i++) sd[(size_t)maxF + (size_t)q * maxLoc + i] = part.diag[q][myOff + i];
-    if ((rc = allgather_host(c, si.data(), si.size() * sizeof(int), ri.data()))) return rc;
-    if ((rc = allgather_host(c, sd.data(), sd.size() * sizeof(double), rd.data()))) return rc;
-    H1 = HostLevel(); H1.n = n1Global;
-    for (int q = 0; q < 3; q++) H1.diag[q].assign(n1Global, 0.0);
-    for (int r = 0; r < world; r++) {
-        const int* pi = ri.data() + (size_t)r * 2 * maxF;
-        const double* pd = rd.data() + (size_t)r * ((size_t)maxF + 3 * (size_t)maxLoc);
-        for (int f = 0; f < nFs[r]; f++) { H1.own.push_back(pi[f]); H1.nei.push_back(pi[maxF + f]); H1.a.push_back(pd[f]); }
-        for (int q = 0; q < 3; q++) for (int i = 0; i < cnt[r]; i++) H1.diag[q][off[r] + i] = pd[(size_t)maxF + (size_t)q * maxLoc + i];
+    std::vector<int> nbrRank; std::vector<std::vector<int>> send, recv;
+    for (const auto& nb : c->nbrs) {
+        Iface I; I.rank = nb.rank;
+        for (int i = 0; i < nb.count; i++) { I.cell.push_back(c->faceCells[c->pStart[nb.patch] + i]); I.a.push_back(aPf[nb.sendOff + i]); }
+        nbrRank.push_back(nb.rank); send.push_back(I.cell);
+        L0.ifc.push_back(std::move(I));
     }
-    L0.parent.assign(agg.begin(), agg.begin() + N);
-    di.on = true; di.n1Local = n1Local; di.n1Off = myOff; di.maxLoc = maxLoc;
-    di.off.assign(off.begin(), off.begin() + world); di.cnt = cnt;
+    int rc = s4f_exchange_nbr_ints(c, nbrRank, send, recv); if (rc) return rc;
+    for (size_t k = 0; k < L0.ifc.size(); k++) L0.ifc[k].remote = recv[k];
+    return 0;
+}
+
+// Coarsen one distributed level: every rank agglomerates its own cells (couplings across ranks never join an aggregate),
+// learns the aggregates behind its interface faces and sums the interface coefficients per (own aggregate, remote
+// aggregate) pair, in an order both sides reproduce (sorted by the pair as seen from the lower rank).
+int coarsen_distributed(s4fgpu_ctx* c, HostLevel& L, HostLevel& C) {
+    std::vector<int> parentLoc;
+    const int nc = coarsen3(L, 0, parentLoc, C);
+    C.dist = true;
+    std::vector<int> nbrRank; std::vector<std::vector<int>> send, recv;
+    for (const Iface& I : L.ifc) {
+        nbrRank.push_back(I.rank);
+        std::vector<int> s(I.cell.size());
+        for (size_t f = 0; f < I.cell.size(); f++) s[f] = parentLoc[I.cell[f]];
+        send.push_back(std::move(s));
+    }
+    int rc = s4f_exchange_nbr_ints(c, nbrRank, send, recv); if (rc) return rc;
+    C.ifc.clear();
+    for (size_t k = 0; k < L.ifc.size(); k++) {
+        const Iface& I = L.ifc[k];
+        const bool lower = c->rank < I.rank;
+        struct E { int p, r; double a; };
+        std::vector<E> es(I.cell.size());
+        for (size_t f = 0; f < I.cell.size(); f++) es[f] = E{send[k][f], recv[k][f], I.a[f]};
+        std::stable_sort(es.begin(), es.end(), [lower](const E& x, const E& y) {
+            const int x0 = lower ? x.p : x.r, x1 = lower ? x.r : x.p, y0 = lower ? y.p : y.r, y1 = lower ? y.r : y.p;
+            return x0 != y0 ? x0 < y0 : x1 < y1;
+        });
+        Iface J; J.rank = I.rank;
+        for (size_t f = 0; f < es.size();) {
+            size_t m = f; double s = 0;
+            while (m < es.size() && es[m].p == es[f].p && es[m].r == es[f].r) s += es[m++].a;
+            J.cell.push_back(es[f].p); J.remote.push_back(es[f].r); J.a.push_back(s);
+            f = m;
+        }
+        C.ifc.push_back(std::move(J));
+    }
+    L.parent = parentLoc; L.childOff = 0; L.childCnt = nc;
+    return 0;
+}
+
+// Gather a distributed level to every rank: global cell = offset of the owning rank + local cell; interior faces of all
+// ranks, then every interface face once (from its lower rank).  The fine level's parents become global indices.
+int gather_level(s4fgpu_ctx* c, HostLevel& fine, const HostLevel& part, HostLevel& glob) {
+    const int R = c->nRanks, me = c->rank;
+    std::vector<int> cnt(R), off(R + 1, 0);
+    int rc = s4f_allgather_host(c, &part.n, sizeof(int), cnt.data()); if (rc) return rc;
+    for (int r = 0; r < R; r++) off[r + 1] = off[r] + cnt[r];
+    std::vector<int> fi; std::vector<double> fd;
+    for (size_t f = 0; f < part.own.size(); f++) { fi.push_back(off[me] + part.own[f]); fi.push_back(off[me] + part.nei[f]); fd.push_back(part.a[f]); }
+    for (const Iface& I : part.ifc)
+        if (me < I.rank)
+            for (size_t f = 0; f < I.cell.size(); f++) { fi.push_back(off[me] + I.cell[f]); fi.push_back(off[I.rank] + I.remote[f]); fd.push_back(I.a[f]); }
+    const size_t nF = fd.size();
+    for (int q = 0; q < 3; q++) fd.insert(fd.end(), part.diag[q].begin(), part.diag[q].end());
+    std::vector<std::vector<char>> ri, rd;
+    if ((rc = s4f_allgatherv_host(c, fi.data(), fi.size() * sizeof(int), ri))) return rc;
+    if ((rc = s4f_allgatherv_host(c, fd.data(), fd.size() * sizeof(double), rd))) return rc;
+    (void)nF;
+    glob = HostLevel(); glob.n = off[R]; glob.dist = false;
+    for (int q = 0; q < 3; q++) glob.diag[q].assign(glob.n, 0.0);
+    for (int r = 0; r < R; r++) {
+        const int* pi = reinterpret_cast<const int*>(ri[r].data());
+        const double* pd = reinterpret_cast<const double*>(rd[r].data());
+        const size_t nf = ri[r].size() / (2 * sizeof(int));
+        for (size_t f = 0; f < nf; f++) { glob.own.push_back(pi[2 * f]); glob.nei.push_back(pi[2 * f + 1]); glob.a.push_back(pd[f]); }
+        for (int q = 0; q < 3; q++) for (int i = 0; i < cnt[r]; i++) glob.diag[q][off[r] + i] = pd[nf + (size_t)q * cnt[r] + i];
+    }
+    for (int& p : fine.parent) p += off[me];
+    fine.childOff = off[me]; fine.childCnt = cnt[me];
     return 0;
 }
 
@@ -921,33 +950,49 @@ int s4f_amg_setup(s4fgpu_ctx* c) {
     const auto t0 = std::chrono::steady_clock::now();
     const int N = c->N, F = c->F;
     std::vector<HostLevel> H(1);
+    int rc;
     {
         HostLevel& L0 = H[0];
         L0.n = N; L0.own = c->own; L0.nei = c->nei; L0.a.resize(F);
-        int rc = s4f_download_upper(c, L0.a.data()); if (rc) return rc;
+        rc = s4f_download_upper(c, L0.a.data()); if (rc) return rc;
         for (int f = 0; f < F; f++) L0.a[f] = -L0.a[f];
         std::vector<double> d(3 * (size_t)c->ld);
         S4F_CHECK_CUDA(c, cudaMemcpy(d.data(), c->diagC.p, d.size() * sizeof(double), cudaMemcpyDeviceToHost));
         for (int q = 0; q < 3; q++) L0.diag[q].assign(d.begin() + (size_t)q * c->ld, d.begin() + (size_t)q * c->ld + N);
+        if (c->nRanks > 1) { L0.dist = true; if ((rc = fine_interfaces(c, L0))) return rc; }
     }
     const int coarsest = 512;
-    DistInfo di;
-    if (c->nRanks > 1) {
-        HostLevel H1;
-        int rc = build_global_level1(c, H[0], H1, di); if (rc) return rc;
-        H.push_back(std::move(H1));
+    long long replicateBelow = 150000;          // global cells: below this a level costs less replicated than distributed
+    if (const char* e = getenv("S4F_GAMG_REPLICATE_BELOW")) replicateBelow = atoll(e);
+    while (H.back().dist) {
+        HostLevel part;
+        if ((rc = coarsen_distributed(c, H.back(), part))) return rc;
+        std::vector<int> cnt(c->nRanks);
+        if ((rc = s4f_allgather_host(c, &part.n, sizeof(int), cnt.data()))) return rc;
+        long long nGlobal = 0, fineGlobal = 0;
+        for (int v : cnt) nGlobal += v;
+        std::vector<int> cntF(c->nRanks);
+        if ((rc = s4f_allgather_host(c, &H.back().n, sizeof(int), cntF.data()))) return rc;
+        for (int v : cntF) fineGlobal += v;
+        const bool stalled = nGlobal * 10 > fineGlobal * 9;
+        if (nGlobal <= replicateBelow || stalled || H.size() >= 6) {
+            HostLevel glob;
+            if ((rc = gather_level(c, H.back(), part, glob))) return rc;
+            H.push_back(std::move(glob));
+        } else H.push_back(std::move(part));
     }
     while (H.back().n > coarsest && H.size() < 12) {
         std::vector<int> total; HostLevel next;
         const int nc = coarsen3(H.back(), coarsest / 4, total, next);
         if (nc >= H.back().n) break;        // no coarsening possible (no faces)
-        H.back().parent = total;
+        H.back().parent = total; H.back().childOff = 0; H.back().childCnt = nc;
         H.push_back(std::move(next));
     }
-    int rc;
-    if (c->ctl.gamgSinglePrecision) rc = build<float>(c, H, di);
-    else rc = build<double>(c, H, di);
+    if (H.back().n > 4096) { c->err = "GAMG: agglomeration stalled above the size of the dense coarsest solve"; return 1; }
+    if (c->ctl.gamgSinglePrecision) rc = build<float>(c, H);
+    else rc = build<double>(c, H);
     if (!rc) c->amg->setupSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    c->graphSerial++;
     return rc;
 }
 
@@ -957,6 +1002,12 @@ int s4f_amg_info(s4fgpu_ctx* c, int* nLevels, int* sizes, int maxLevels, double*
     for (int i = 0; i < *nLevels && i < maxLevels; i++) sizes[i] = c->amg->sizes[i];
     *bytesPerApply = c->amg->bytesPerApply; *setupSeconds = c->amg->setupSeconds;
     return 0;
+}
+
+int s4f_amg_distributed_levels(s4fgpu_ctx* c) {
+    int n = 0;
+    if (c->amg) for (int v : c->amg->distributed) n += v;
+    return n;
 }
 
 int s4f_amg_step0(s4fgpu_ctx* c, const double* r3, double* bytes) {

@@ -6,7 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "s4f_ctx.h"
+#include "s4f_comm.h"
 
 int s4f_update_total_fields_impl(s4fgpu_ctx* c);
 
@@ -55,7 +55,7 @@ int s4f_outer_iteration(s4fgpu_ctx* c, int iCorr) {
     if ((rc = s4f_bc_update_coeffs(c))) return rc;                               // fvMatrix ctor -> updateCoeffs()
     if (!c->matrixValid && (rc = s4f_assemble_matrix(c))) return rc;             // fvm::laplacian(impKf, D): constant while impKf is
     if ((rc = s4f_assemble_source(c))) return rc;                                // explicit terms
-    if ((rc = s4f_solve_segregated(c, c->D.p, c->source.p))) return rc;          // DEqn.solve()
+    if ((rc = s4f_solve_segregated(c, c->D.p, c->source.p, true))) return rc;    // DEqn.solve(); statistics read with the residuals
     if ((rc = s4f_bc_evaluate(c))) return rc;                                    // D.correctBoundaryConditions()
     if ((rc = s4f_relax_and_residual(c, iCorr))) return rc;                      // relaxField + residual reductions
     if ((rc = s4f_update_totals(c, true, false))) return rc;                     // incremental: D = D.oldTime() + DD
@@ -68,7 +68,8 @@ int s4f_outer_iteration(s4fgpu_ctx* c, int iCorr) {
 // converged(): solidModelTemplates.C:27-188, evaluated from the device-side reductions
 int s4f_read_outer_scalars(s4fgpu_ctx* c, s4fgpu_stats* st, bool* converged, int iCorr) {
     S4F_CHECK_CUDA(c, cudaMemcpyAsync(c->hOutS, c->outS.p, sizeof(OuterScalars), cudaMemcpyDeviceToHost, c->stream));
-    S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+    S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));      // the one host synchronisation of an outer iteration
+    { int rf = s4f_finish_solve(c); if (rf) return rf; }
     const OuterScalars& o = *c->hOutS;
     const bool incremental = (c->ctl.solidModel == S4F_MODEL_NONLIN_TL || c->ctl.solidModel == S4F_MODEL_NONLIN_UL);
     double denom = incremental ? o.maxMag : o.maxIncr;
@@ -113,7 +114,10 @@ int s4fgpu_create(s4fgpu_handle* out, int device) {
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_createError = cudaGetErrorString(e); delete c; return 2; }
     c->numSMs = prop.multiProcessorCount;
-    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { g_createError = cudaGetErrorString(e); delete c; return 2; }
+    // A BLOCKING stream: DevBuf::alloc / upload and s4fgpu_set_bc use cudaMemset / cudaMemcpy on the legacy default stream,
+    // which is ordered against blocking streams only.  With cudaStreamNonBlocking a fresh buffer's zero fill could still be
+    // running when the first kernel on c->stream wrote into it (latent at test sizes, real at 8 M cells).
+    if ((e = cudaStreamCreate(&c->stream)) != cudaSuccess) { g_createError = cudaGetErrorString(e); delete c; return 2; }
     *out = c;
     return 0;
 }
@@ -125,6 +129,9 @@ int s4fgpu_destroy(s4fgpu_handle c) {
     s4f_amg_destroy(c);
     s4f_uns_destroy(c);
     s4f_dic_destroy(c);
+    s4f_solve_graphs_destroy(c);
+    s4f_halo_plan_destroy(c->halo0); c->halo0 = nullptr;
+    s4f_comm_destroy(c);
     if (c->comm) ncclCommDestroy(c->comm);
     if (c->hPcgS) cudaFreeHost(c->hPcgS);
     if (c->hOutS) cudaFreeHost(c->hOutS);
@@ -148,7 +155,7 @@ int s4fgpu_comm_init(s4fgpu_handle c, int nRanks, int rank, const char id[128]) 
     ncclUniqueId u; std::memcpy(&u, id, 128);
     S4F_CHECK_NCCL(c, ncclCommInitRank(&c->comm, nRanks, u, rank));
     c->nRanks = nRanks; c->rank = rank; c->nGlobalCells = -1;
-    return 0;
+    return s4f_comm_setup(c);           // all-reduce mailboxes over peer memory (collective)
 }
 
 int s4fgpu_set_mesh(s4fgpu_handle c, int nCells, int nInternalFaces, const int* owner, const int* neighbour, int nPatches,
@@ -493,6 +500,8 @@ int s4fgpu_gamg_info(s4fgpu_handle c, int* nLevels, int* sizes, int maxLevels, d
     if (!c->amgValid) { int rc = s4f_amg_setup(c); if (rc) return rc; c->amgValid = true; }
     return s4f_amg_info(c, nLevels, sizes, maxLevels, bytesPerApply, setupSeconds);
 }
+
+int s4fgpu_gamg_distributed_levels(s4fgpu_handle c) { return c ? s4f_amg_distributed_levels(c) : 0; }
 
 int s4fgpu_timer_start(s4fgpu_handle c) {
     S4F_CHECK_CUDA(c, cudaSetDevice(c->device));

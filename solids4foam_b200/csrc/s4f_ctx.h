@@ -69,6 +69,20 @@ struct DevBuf {
     }
 };
 
+#define S4F_MAX_RANKS 16
+#define S4F_MAX_NBRS 16
+#define S4F_RED_MAX 16
+
+// all-reduce mailboxes of one context (device memory; null pointer = single rank)
+struct PeerRed {
+    int nRanks, rank;
+    double* box[S4F_MAX_RANKS];          // box[r]: rank r's mailbox  [2 parities][nRanks][S4F_RED_MAX]
+    unsigned int* flag[S4F_MAX_RANKS];   // flag[r]: rank r's flags   [2 parities][nRanks]
+    unsigned int seq;                    // reductions completed so far
+};
+
+struct RedCtx { double* partials; unsigned int* ticket; PeerRed* peer; };
+
 // scalar block of the fused 3-component PCG, one per solve, in device memory.
 // All per-component quantities are [3].
 struct PcgScalars {
@@ -108,9 +122,14 @@ struct s4fgpu_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     // ---- parallel ----
-    ncclComm_t comm = nullptr;
+    ncclComm_t comm = nullptr;            // set-up collectives only (IPC handles, agglomeration tables)
     int nRanks = 1, rank = 0;
     double nGlobalCells = -1;
+    DevBuf<char> redArena;                // this rank's all-reduce mailbox (peers write into it over NVLink)
+    DevBuf<PeerRed> redDev;               // device descriptor with every rank's mailbox pointers (s4f_comm.cu)
+    std::vector<void*> ipcOpened;
+    struct S4fHaloPlan* halo0 = nullptr;  // processor-patch halo of the fine mesh
+    long long graphSerial = 0;            // bumped whenever anything a captured solve points at is rebuilt
 
     // ---- host copy of the mesh description ----
     int N = 0, F = 0, B = 0, G = 0, nPatches = 0;
@@ -157,7 +176,6 @@ struct s4fgpu_ctx {
     struct Nbr { int rank; int patch; int count; int sendOff; int ghostOff; };
     std::vector<Nbr> nbrs;
     DevBuf<int> sendCells;            // [G] local cells adjacent to processor faces, in patch order
-    DevBuf<double> sendBuf, recvBuf;  // [9*G] staging
 
     // ---- fields (SoA, ld per component) ----
     DevBuf<double> D, Dprev, Dold, DoldOld;       // 3*ld
@@ -210,6 +228,10 @@ struct s4fgpu_ctx {
     bool matrixValid = false;
     // ---- PCG work vectors ----
     DevBuf<double> pA, wA, rA;        // 3*ld each
+    DevBuf<double> zA;                // 3*ld: M^-1 rA of the non-local preconditioners
+    struct S4fSolveGraphs* solveGraphs = nullptr;   // captured solves (s4f_pcg.cu)
+    bool solvePending = false;        // a solve's statistics are still on their way to hPcgS
+    long long pendingPre = 0, pendingBody = 0;
     DevBuf<double> cheb0, cheb1;      // 3*ld polynomial-preconditioner work
     DevBuf<double> bi[6];             // 3*ld each: PBiCGStab rA0, yA, AyA, sA, zA, tA
     DevBuf<double> aitRes, aitResPrev, aitAlpha;  // Aitken relaxation state (solidModel.C:842-897)
@@ -249,6 +271,7 @@ struct s4fgpu_ctx {
     bool fastRhs() const { return !nonOrth; }
     double gamma0() const { return ctl.stabilisation == S4F_STAB_RHIE_CHOW ? ctl.stabScaleFactor * impK0 : 0.0; }
     const double* gradForLaw() const { return incremental() ? gradDtot.p : gradD.p; }   // the registered "grad(D)"
+    RedCtx red() const { return RedCtx{partials.p, ticket.p, nRanks > 1 ? redDev.p : nullptr}; }
     int NT() const { return N + G + B; }
     int bOff() const { return N + G; }
 };
@@ -280,8 +303,10 @@ int s4f_grad_calculated_interior(s4fgpu_ctx* c, const double* X, double* gradOut
 int s4f_make_m(s4fgpu_ctx* c);                       // lin-geom: M = sigma - gamma grad(D) when no law kernel produced it
 int s4f_update_totals(s4fgpu_ctx* c, bool disp, bool grad);
 int s4f_law_correct(s4fgpu_ctx* c);
-int s4f_solve_segregated(s4fgpu_ctx* c, double* psi, const double* source);   // device SoA pointers
+int s4f_solve_segregated(s4fgpu_ctx* c, double* psi, const double* source, bool defer = false);   // device SoA pointers
+int s4f_finish_solve(s4fgpu_ctx* c);
 int s4f_halo_exchange(s4fgpu_ctx* c, double* field, int ncomp);
+void s4f_solve_graphs_destroy(s4fgpu_ctx* c);       // captured PCG solves (s4f_pcg.cu)
 int s4f_outer_iteration(s4fgpu_ctx* c, int iCorr);
 int s4f_read_outer_scalars(s4fgpu_ctx* c, s4fgpu_stats* st, bool* converged, int iCorr);
 int s4f_aos_to_soa(s4fgpu_ctx* c, const double* hostAoS, double* devSoA, int count, int ncomp, int offset);
@@ -295,6 +320,7 @@ int s4f_amg_setup(s4fgpu_ctx* c);                                   // after s4f
 int s4f_amg_apply(s4fgpu_ctx* c, const double* r3, double* z3);     // z = M^-1 r, 3 components, stride ld
 int s4f_amg_step0(s4fgpu_ctx* c, const double* r3, double* bytes);
 void s4f_amg_destroy(s4fgpu_ctx* c);
+int s4f_amg_distributed_levels(s4fgpu_ctx* c);
 int s4f_amg_info(s4fgpu_ctx* c, int* nLevels, int* sizes, int maxLevels, double* bytesPerApply, double* setupSeconds);
 int s4f_download_upper(s4fgpu_ctx* c, double* hostUpper);           // lduMatrix upper() [F]
 int s4f_build_point_stencil(s4fgpu_ctx* c);                          // rows of the pointCellsLeastSquares gradient (s4f_setup.cu)

@@ -47,10 +47,30 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV]) {
     __syncthreads();
 }
 
+// ---- multi-GPU: reductions and halos over cudaIpc-mapped peer memory (NVLink), no NCCL in the iteration ----------
+// Every rank owns a mailbox that its peers write into with plain stores followed by a system-scope release of a flag
+// word; messages carry a sequence number kept in device memory (CUDA-graph replays need no host-side argument), and
+// slots alternate by parity: in a symmetric exchange a rank sends message k+1 only after it has seen the peer's message
+// k, which the peer sent after consuming message k-1, so the slot of k-1 is free.  (s4f_comm.cu sets the pointers up.)
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // Grid reduce: every block deposits its NV partials; the last block to arrive (ticket) combines
-// them in a fixed order (deterministic for a fixed grid) and calls fin(tot) from thread 0.
+// them in a fixed order (deterministic for a fixed grid), all-reduces the totals with the other ranks through the
+// peer mailboxes (summed in rank order on every rank: bit-identical results everywhere, so all ranks take the same
+// branches) and calls fin(tot) from thread 0.  This replaces gSum/gMax + Pstream reductions ([OF-ext]) and the
+// separate ncclAllReduce + scalar-step launches of round 1.
 template <int NV, class Op, class Fin>
-__device__ __forceinline__ void grid_reduce(double (&v)[NV], double* partials, unsigned int* ticket, Fin fin) {
+__device__ __forceinline__ void grid_reduce(double (&v)[NV], const RedCtx& rc, Fin fin) {
+    static_assert(NV <= S4F_RED_MAX, "reduction wider than the mailbox");
+    double* partials = rc.partials;
+    unsigned int* ticket = rc.ticket;
     block_reduce<NV, Op>(v);
     __shared__ bool isLast;
     if (threadIdx.x == 0) {
@@ -71,9 +91,55 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double* partials, u
             tot[i] = a;
         }
         block_reduce<NV, Op>(tot);
+        PeerRed* pr = rc.peer;
+        if (pr) {
+            __shared__ double shTot[NV];
+            const int R = pr->nRanks, me = pr->rank;
+            const unsigned int k = pr->seq + 1u, par = k & 1u;
+            if (threadIdx.x == 0) {
+#pragma unroll
+                for (int i = 0; i < NV; i++) shTot[i] = tot[i];
+            }
+            __syncthreads();
+            for (int t = threadIdx.x; t < R * NV; t += blockDim.x) {
+                const int r = t / NV, i = t - r * NV;
+                pr->box[r][((size_t)par * R + me) * S4F_RED_MAX + i] = shTot[i];
+            }
+            __threadfence_system();
+            __syncthreads();
+            if ((int)threadIdx.x < R) {
+                st_release_sys(pr->flag[threadIdx.x] + par * R + me, k);
+                const unsigned int* mine = pr->flag[me] + par * R + threadIdx.x;
+                while (ld_acquire_sys(mine) != k) {}
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const double* mb = pr->box[me] + (size_t)par * R * S4F_RED_MAX;
+#pragma unroll
+                for (int i = 0; i < NV; i++) {
+                    double a = __ldcv(mb + i);
+                    for (int r = 1; r < R; r++) a = Op::f(a, __ldcv(mb + (size_t)r * S4F_RED_MAX + i));
+                    tot[i] = a;
+                }
+                pr->seq = k;
+            }
+        }
         if (threadIdx.x == 0) { *ticket = 0u; fin(tot); }
     }
 }
+
+// halo exchange of one plan (HaloPlan in s4f_comm.cu), passed to the exchange kernel by value
+struct HaloDev {
+    int nNbr, maxComp;
+    int scount[S4F_MAX_NBRS], soff[S4F_MAX_NBRS]; // values per component sent to neighbour n; prefix sums (into sendCells)
+    int rcount[S4F_MAX_NBRS], roff[S4F_MAX_NBRS]; // values per component received from neighbour n; prefix sums (ghost order)
+    char* peerBox[S4F_MAX_NBRS];                  // remote: where my message to neighbour n goes, [2][maxComp * count] of 8 bytes
+    unsigned int* peerFlag[S4F_MAX_NBRS];         // remote: [2]
+    char* myBox[S4F_MAX_NBRS];                    // local: messages of neighbour n
+    unsigned int* myFlag[S4F_MAX_NBRS];
+    const int* sendCells;                         // [sum count] local cells whose values go out, neighbour by neighbour
+    unsigned int* seq;                            // exchanges completed; [1] and [2] are the two block tickets
+};
 
 // ---- tensor algebra: tensor 9 row-major, symmTensor 6 = XX XY XZ YY YZ ZZ ----------------------
 __device__ __forceinline__ void t_symm(const double* T, double* S) {

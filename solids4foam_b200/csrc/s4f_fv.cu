@@ -547,7 +547,7 @@ struct FinOuter {
 };
 __global__ void __launch_bounds__(S4F_BLOCK) k_relax_residual(double* __restrict__ D, const double* __restrict__ Dprev,
                                                               const double* __restrict__ Dold, int N, int bOff, int B, int ld,
-                                                              double alpha, OuterScalars* S, double* partials, unsigned int* ticket) {
+                                                              double alpha, OuterScalars* S, RedCtx red) {
     double v[3] = {0, 0, 0};
     const int total = N + B;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
@@ -567,15 +567,14 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_relax_residual(double* __restrict
             v[0] = fmax(v[0], a); v[1] = fmax(v[1], bb); v[2] = fmax(v[2], m);
         }
     }
-    grid_reduce<3, OpMax>(v, partials, ticket, FinOuter{S});
+    grid_reduce<3, OpMax>(v, red, FinOuter{S});
 }
 
 // Aitken relaxation (solidModel.C:842-897): cell-wise alpha, incl. boundary values
 __global__ void __launch_bounds__(S4F_BLOCK) k_relax_aitken(double* __restrict__ D, const double* __restrict__ Dprev,
                                                             const double* __restrict__ Dold, double* __restrict__ res,
                                                             double* __restrict__ resPrev, double* __restrict__ aAlpha, int N, int bOff,
-                                                            int B, int ld, int first, double alpha0, OuterScalars* S, double* partials,
-                                                            unsigned int* ticket) {
+                                                            int B, int ld, int first, double alpha0, OuterScalars* S, RedCtx red) {
     double v[3] = {0, 0, 0};
     const int total = N + B;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
@@ -610,7 +609,7 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_relax_aitken(double* __restrict__
             v[0] = fmax(v[0], x); v[1] = fmax(v[1], bb); v[2] = fmax(v[2], m);
         }
     }
-    grid_reduce<3, OpMax>(v, partials, ticket, FinOuter{S});
+    grid_reduce<3, OpMax>(v, red, FinOuter{S});
 }
 
 }  // namespace
@@ -938,13 +937,12 @@ int s4f_relax_and_residual(s4fgpu_ctx* c, int iCorr) {
         const size_t ld = c->ld;
         if (c->aitRes.n != 3 * ld) { S4F_CHECK_CUDA(c, c->aitRes.alloc(3 * ld)); S4F_CHECK_CUDA(c, c->aitResPrev.alloc(3 * ld)); S4F_CHECK_CUDA(c, c->aitAlpha.alloc(ld)); }
         k_relax_aitken<<<grid, S4F_BLOCK, 0, c->stream>>>(c->D.p, c->Dprev.p, c->Dold.p, c->aitRes.p, c->aitResPrev.p, c->aitAlpha.p, c->N, c->bOff(), c->B,
-                                                         c->ld, iCorr == 0, c->ctl.fieldRelaxD, c->outS.p, c->partials.p, c->ticket.p);
+                                                         c->ld, iCorr == 0, c->ctl.fieldRelaxD, c->outS.p, c->red());
     } else {
         k_relax_residual<<<grid, S4F_BLOCK, 0, c->stream>>>(c->D.p, c->Dprev.p, c->Dold.p, c->N, c->bOff(), c->B, c->ld, c->ctl.fieldRelaxD,
-                                                           c->outS.p, c->partials.p, c->ticket.p);
+                                                           c->outS.p, c->red());
     }
     c->launches++;
-    if (c->nRanks > 1) S4F_CHECK_NCCL(c, ncclAllReduce((double*)c->outS.p, (double*)c->outS.p, 3, ncclDouble, ncclMax, c->comm, c->stream));
     S4F_CHECK_CUDA(c, cudaGetLastError());
     return s4f_halo_exchange(c, c->D.p, 3);
 }

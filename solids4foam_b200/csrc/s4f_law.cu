@@ -172,14 +172,14 @@ __device__ __forceinline__ void mises_trial(const double* __restrict__ gradD, co
 struct FinMaxBE { OuterScalars* S; __device__ void operator()(const double* tot) const { S->maxMagBE = tot[0]; } };
 __global__ void __launch_bounds__(S4F_BLOCK) k_mises_max_be(const double* __restrict__ gradD, const double* __restrict__ Fold,
                                                             const double* __restrict__ Jold, const double* __restrict__ bEbarOld, int N, int ld,
-                                                            OuterScalars* S, double* partials, unsigned int* ticket, int UL) {
+                                                            OuterScalars* S, RedCtx red, int UL) {
     double v[1] = {0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {   // gMax over the internal field :1030
         double Fm[9], J, bt[6];
         mises_trial(gradD, Fold, Jold, bEbarOld, ld, i, Fm, J, bt, UL);
         v[0] = fmax(v[0], sqrt(s_magSqr(bt)));
     }
-    grid_reduce<1, OpMax>(v, partials, ticket, FinMaxBE{S});
+    grid_reduce<1, OpMax>(v, red, FinMaxBE{S});
 }
 
 struct FinMat { OuterScalars* S; __device__ void operator()(const double* tot) const { S->matNum = tot[0]; S->matDen = tot[1]; } };
@@ -192,7 +192,7 @@ struct MisesPtrs {
 };
 __global__ void __launch_bounds__(S4F_BLOCK) k_law_mises(MisesPtrs p, int N, int bOff, int B, int ld, double mu, double K, double Hp,
                                                          int consistent, double relax, HardeningTable T, OuterScalars* S,
-                                                         double* partials, unsigned int* ticket, int UL) {
+                                                         RedCtx red, int UL) {
     const bool nonLinearPlasticity = T.n > 2;
     const double magHp = fabs(Hp);
     const double maxMagBE = fmax(S->maxMagBE, S4F_SMALL);
@@ -258,19 +258,19 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_law_mises(MisesPtrs p, int N, int
             v[1] = fmax(v[1], S4F_SMALL + sqrt(s_magSqr(prev)));
         }
     }
-    grid_reduce<2, OpMax>(v, partials, ticket, FinMat{S});
+    grid_reduce<2, OpMax>(v, red, FinMat{S});
 }
 
 // ---- linearElasticMisesPlastic ----------------------------------------------------------------------
 __global__ void __launch_bounds__(S4F_BLOCK) k_lin_mises_max_eps(const double* __restrict__ gradD, int N, int ld, OuterScalars* S,
-                                                                 double* partials, unsigned int* ticket) {
+                                                                 RedCtx red) {
     double v[1] = {0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
         double g[9], e[6];
         ld_soa<9>(gradD, ld, i, g); t_symm(g, e);
         v[0] = fmax(v[0], sqrt(s_magSqr(e)));
     }
-    grid_reduce<1, OpMax>(v, partials, ticket, FinMaxBE{S});
+    grid_reduce<1, OpMax>(v, red, FinMaxBE{S});
 }
 struct LinMisesPtrs {
     const double* gradD; const double* epsPOld; const double* sigmaYOld; const double* epsPEqOld;
@@ -278,7 +278,7 @@ struct LinMisesPtrs {
     double* DEpsPprev; double* DLambda; double* plasticN; double* pExp;
 };
 __global__ void __launch_bounds__(S4F_BLOCK) k_law_lin_mises(LinMisesPtrs p, int N, int bOff, int B, int ld, double mu, double K, double Hp,
-                                                             HardeningTable T, OuterScalars* S, double* partials, unsigned int* ticket) {
+                                                             HardeningTable T, OuterScalars* S, RedCtx red) {
     const bool nonLinearPlasticity = T.n > 2;
     const double maxMagBE = fmax(S->maxMagBE, S4F_SMALL);
     double v[2] = {0, 0};
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_law_lin_mises(LinMisesPtrs p, int
             v[1] = fmax(v[1], S4F_SMALL + sqrt(s_magSqr(prev)));
         }
     }
-    grid_reduce<2, OpMax>(v, partials, ticket, FinMat{S});
+    grid_reduce<2, OpMax>(v, red, FinMat{S});
 }
 
 // ---- total-Lagrangian flux tensor: F = I + gradD.T(); Finv; J; T = J Finv & sigma ------------------
@@ -398,28 +398,24 @@ int s4f_law_correct(s4fgpu_ctx* c) {
     } else if (L.kind == S4F_LAW_NEO_HOOKEAN_MISES_PLASTIC) {
         HardeningTable T = make_table(L);
         if (T.n > 2) {
-            k_mises_max_be<<<gridN, S4F_BLOCK, 0, c->stream>>>(gD, c->lawFold.p, c->lawJold.p, c->bEbarOld.p, N, ld, c->outS.p, c->partials.p, c->ticket.p, UL);
+            k_mises_max_be<<<gridN, S4F_BLOCK, 0, c->stream>>>(gD, c->lawFold.p, c->lawJold.p, c->bEbarOld.p, N, ld, c->outS.p, c->red(), UL);
             c->launches++;
-            if (c->nRanks > 1) S4F_CHECK_NCCL(c, ncclAllReduce(&((OuterScalars*)c->outS.p)->maxMagBE, &((OuterScalars*)c->outS.p)->maxMagBE, 1, ncclDouble, ncclMax, c->comm, c->stream));
         }
         MisesPtrs p{gD, c->lawFold.p, c->lawJold.p, c->bEbarOld.p, c->sigmaY.p, c->epsPEq.p, c->lawF.p, c->lawJ.p, c->bEbar.p, c->sigma.p,
                     c->DSigmaY.p, c->DEpsPEq.p, c->DEpsP.p, c->DEpsPprev.p, c->DLambda.p, c->plasticN.p, pE};
         k_law_mises<<<grid, S4F_BLOCK, 0, c->stream>>>(p, N, bOff, B, ld, L.mu, L.K, c->Hp, L.updateBEbarConsistent, L.DEpsilonPRelax, T, c->outS.p,
-                                                      c->partials.p, c->ticket.p, UL);
+                                                      c->red(), UL);
         c->launches++;
-        if (c->nRanks > 1) S4F_CHECK_NCCL(c, ncclAllReduce(&((OuterScalars*)c->outS.p)->matNum, &((OuterScalars*)c->outS.p)->matNum, 2, ncclDouble, ncclMax, c->comm, c->stream));
     } else if (L.kind == S4F_LAW_LINEAR_ELASTIC_MISES_PLASTIC) {
         HardeningTable T = make_table(L);
         if (T.n > 2) {
-            k_lin_mises_max_eps<<<gridN, S4F_BLOCK, 0, c->stream>>>(gD, N, ld, c->outS.p, c->partials.p, c->ticket.p);
+            k_lin_mises_max_eps<<<gridN, S4F_BLOCK, 0, c->stream>>>(gD, N, ld, c->outS.p, c->red());
             c->launches++;
-            if (c->nRanks > 1) S4F_CHECK_NCCL(c, ncclAllReduce(&((OuterScalars*)c->outS.p)->maxMagBE, &((OuterScalars*)c->outS.p)->maxMagBE, 1, ncclDouble, ncclMax, c->comm, c->stream));
         }
         LinMisesPtrs p{gD, c->epsPOld.p, c->sigmaYOld.p, c->epsPEqOld.p, c->epsilon.p, c->sigma.p, c->sigmaY.p, c->DSigmaY.p, c->epsPEq.p,
                        c->DEpsPEq.p, c->epsP.p, c->DEpsP.p, c->DEpsPprev.p, c->DLambda.p, c->plasticN.p, pE};
-        k_law_lin_mises<<<grid, S4F_BLOCK, 0, c->stream>>>(p, N, bOff, B, ld, L.mu, L.K, c->Hp, T, c->outS.p, c->partials.p, c->ticket.p);
+        k_law_lin_mises<<<grid, S4F_BLOCK, 0, c->stream>>>(p, N, bOff, B, ld, L.mu, L.K, c->Hp, T, c->outS.p, c->red());
         c->launches++;
-        if (c->nRanks > 1) S4F_CHECK_NCCL(c, ncclAllReduce(&((OuterScalars*)c->outS.p)->matNum, &((OuterScalars*)c->outS.p)->matNum, 2, ncclDouble, ncclMax, c->comm, c->stream));
     } else {
         c->err = "unknown mechanical law"; return 1;
     }

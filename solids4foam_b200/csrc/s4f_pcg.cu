@@ -21,9 +21,12 @@
 // fvSolution "solver PBiCGStab" ([OF-ext] PBiCGStab.C) runs through the same kernels with its own vector updates
 // (solve_pbicgstab below): two preconditioner applications and two SpMVs per iteration, the half-step exit on sA.
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
 
-#include "s4f_ctx.h"
+#include "s4f_comm.h"
 #include "s4f_dev.cuh"
 
 namespace {
@@ -32,9 +35,12 @@ struct PcgParams {
     double tolerance, relTol;
     int maxIter;
     int solD[3];
-    int defer;       // 1: multi-rank, totals are all-reduced before the scalar step
     int precond;
+    int flexible;    // Polak-Ribiere beta = z_new.(r_new - r_old)/(z_old.r_old): the preconditioner changes between iterations (K-cycle, fp32 cycle)
 };
+
+// loop condition of the captured solve (a CUDA-graph conditional WHILE node); off when the host drives the iterations
+struct Cond { cudaGraphConditionalHandle h = 0; int on = 0; };
 
 enum { PH_AVG = 0, PH_INIT = 1, PH_AMUL = 2, PH_XR = 3, PH_DOT = 4, PH_BI_RHO = 5, PH_BI_ALPHA = 6, PH_BI_S = 7, PH_BI_OMEGA = 8, PH_BI_XR = 9 };
 
@@ -119,38 +125,33 @@ __device__ void pcg_scalar_step(int phase, PcgScalars* S, const double* tot, con
             any |= S->active[c];
         }
         S->anyActive = any;
-    } else if (phase == PH_DOT) {   // generic preconditioner path: rho = wA.rA
+    } else if (phase == PH_DOT) {   // generic preconditioner path: rho = z.rA
         for (int c = 0; c < 3; c++) if (S->active[c]) {   // rhoOld was saved by PH_XR
             S->rho[c] = tot[c];
-            S->beta[c] = (S->nIter[c] > 0) ? S->rho[c] / S->rhoOld[c] : 0.0;
+            if (S->nIter[c] == 0) S->beta[c] = 0.0;
+            // flexible: z.(r_new - r_old) = -alpha z.(A p_old); equal to z.r_new for a fixed symmetric preconditioner
+            else S->beta[c] = P.flexible ? -S->alpha[c] * tot[3 + c] / S->rhoOld[c] : S->rho[c] / S->rhoOld[c];
         }
     }
 }
 
+// finisher of every reducing kernel: tot holds the GLOBAL sums (grid_reduce all-reduces them across the ranks)
 struct Fin {
-    int phase; PcgScalars* S; PcgParams P; double nGlob; int nv;
+    int phase; PcgScalars* S; PcgParams P; double nGlob; int nv; Cond cond;
     __device__ void operator()(const double* tot) const {
-        if (P.defer) { for (int i = 0; i < nv; i++) S->part[i] = tot[i]; }
-        else pcg_scalar_step(phase, S, tot, P, nGlob);
+        pcg_scalar_step(phase, S, tot, P, nGlob);
+        if (cond.on) cudaGraphSetConditional(cond.h, S->anyActive ? 1u : 0u);
     }
 };
 
-__global__ void k_pcg_scalar_step(int phase, PcgScalars* S, PcgParams P, double nGlob) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double tot[16];
-        for (int i = 0; i < 16; i++) tot[i] = S->part[i];
-        pcg_scalar_step(phase, S, tot, P, nGlob);
-    }
-}
-
 // gAverage(psi) numerator
 __global__ void __launch_bounds__(S4F_BLOCK) k_pcg_sum(const double* __restrict__ x, int N, int ld, PcgScalars* S, PcgParams P,
-                                                       double nGlob, double* partials, unsigned int* ticket) {
+                                                       double nGlob, RedCtx red) {
     double v[3] = {0, 0, 0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
         v[0] += x[i]; v[1] += x[(size_t)ld + i]; v[2] += x[2 * (size_t)ld + i];
     }
-    grid_reduce<3, OpSum>(v, partials, ticket, Fin{PH_AVG, S, P, nGlob, 3});
+    grid_reduce<3, OpSum>(v, red, Fin{PH_AVG, S, P, nGlob, 3, Cond{}});
 }
 
 // wA = A psi ; rA = b - wA ; sums |rA|, |wA - sumA*avg| + |b - sumA*avg|, rA.rA/diag
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_pcg_init(const int* __restrict__ 
                                                         const double* __restrict__ rDiag, const double* __restrict__ x,
                                                         const double* __restrict__ b, double* __restrict__ r, int N, int ld,
                                                         int nSlices, PcgScalars* S,
-                                                        PcgParams P, double nGlob, double* partials, unsigned int* ticket) {
+                                                        PcgParams P, double nGlob, RedCtx red, Cond cond) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nWarps = (gridDim.x * blockDim.x) >> 5;
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_pcg_init(const int* __restrict__ 
             }
         }
     }
-    grid_reduce<9, OpSum>(v, partials, ticket, Fin{PH_INIT, S, P, nGlob, 9});
+    grid_reduce<9, OpSum>(v, red, Fin{PH_INIT, S, P, nGlob, 9, cond});
 }
 
 // ---- streaming vector kernels: two cells per thread (128-bit loads), all loads of a component issued
@@ -268,8 +269,7 @@ template <int DOT>
 __global__ void __launch_bounds__(S4F_BLOCK, 4) k_amul3(const int* __restrict__ slicePtr, const int* __restrict__ col,
                                                         const double* __restrict__ eA, const double* __restrict__ diagC,
                                                         const double* __restrict__ p, double* __restrict__ w, int N, int ld,
-                                                        int nSlices, PcgScalars* S, PcgParams P, double nGlob, double* partials,
-                                                        unsigned int* ticket, int cmptMask, const double* __restrict__ dotv, int phase) {
+                                                        int nSlices, PcgScalars* S, PcgParams P, double nGlob, RedCtx red, int cmptMask, const double* __restrict__ dotv, int phase) {
     int act[3];
     if (DOT) {
         if (!S->anyActive) return;
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(S4F_BLOCK, 4) k_amul3(const int* __restrict__ 
             }
         }
     }
-    if constexpr (DOT != 0) grid_reduce<(DOT == 2 ? 6 : 3), OpSum>(v, partials, ticket, Fin{phase, S, P, nGlob, DOT == 2 ? 6 : 3});
+    if constexpr (DOT != 0) grid_reduce<(DOT == 2 ? 6 : 3), OpSum>(v, red, Fin{phase, S, P, nGlob, DOT == 2 ? 6 : 3, Cond{}});
 }
 
 // scalar (single-vector) Amul, for the roofline number the metric quotes
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_amul1(const int* __restrict__ sli
 // psi += alpha pA; rA -= alpha wA; sums |rA| and (rD rA).rA (the next wArA for the diagonal preconditioner)
 __global__ void __launch_bounds__(S4F_BLOCK) k_pcg_xr(const double* __restrict__ rD, double* __restrict__ x, double* __restrict__ r,
                                                       const double* __restrict__ p, const double* __restrict__ w, int N, int ld,
-                                                      PcgScalars* S, PcgParams P, double nGlob, double* partials, unsigned int* ticket) {
+                                                      PcgScalars* S, PcgParams P, double nGlob, RedCtx red, Cond cond) {
     if (!S->anyActive) return;
     int act[3]; double alpha[3];
 #pragma unroll
@@ -381,22 +381,28 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_pcg_xr(const double* __restrict__
             else if (P.precond == S4F_PRECOND_NONE) v[3 + c] += rr * rr;
         }
     }
-    grid_reduce<6, OpSum>(v, partials, ticket, Fin{PH_XR, S, P, nGlob, 6});
+    grid_reduce<6, OpSum>(v, red, Fin{PH_XR, S, P, nGlob, 6, cond});
 }
 
-// rho = wA.rA for preconditioners whose result is not local (Chebyshev)
-__global__ void __launch_bounds__(S4F_BLOCK) k_pcg_dot_zr(const double* __restrict__ z, const double* __restrict__ r, int N, int ld,
-                                                          PcgScalars* S, PcgParams P, double nGlob, double* partials, unsigned int* ticket) {
+// rho = z.rA for preconditioners whose result is not local (GAMG, DIC, Chebyshev); with w (= A pA of the previous iteration)
+// also z.w for the flexible beta
+__global__ void __launch_bounds__(S4F_BLOCK) k_pcg_dot_zr(const double* __restrict__ z, const double* __restrict__ r, const double* __restrict__ w,
+                                                          int N, int ld, PcgScalars* S, PcgParams P, double nGlob, RedCtx red) {
     if (!S->anyActive) return;
     int act[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) act[c] = S->active[c];
-    double v[3] = {0, 0, 0};
+    double v[6] = {0, 0, 0, 0, 0, 0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) if (act[c]) { const size_t j = (size_t)c * ld + i; v[c] += z[j] * r[j]; }
+        for (int c = 0; c < 3; c++) if (act[c]) {
+            const size_t j = (size_t)c * ld + i;
+            const double zz = z[j];
+            v[c] += zz * r[j];
+            if (w) v[3 + c] += zz * w[j];
+        }
     }
-    grid_reduce<3, OpSum>(v, partials, ticket, Fin{PH_DOT, S, P, nGlob, 3});
+    grid_reduce<6, OpSum>(v, red, Fin{PH_DOT, S, P, nGlob, 6, Cond{}});
 }
 
 // Chebyshev polynomial preconditioner on the Jacobi-scaled operator D^-1 A, spectrum in
@@ -451,7 +457,7 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_cheb_step(const int* __restrict__
 // ---- PBiCGStab vector kernels ([OF-ext] PBiCGStab.C), three components with their own flags ----------
 // rA0.rA
 __global__ void __launch_bounds__(S4F_BLOCK) k_bi_rho(const double* __restrict__ r0, const double* __restrict__ r, int N, int ld, PcgScalars* S,
-                                                      PcgParams P, double nGlob, double* partials, unsigned int* ticket) {
+                                                      PcgParams P, double nGlob, RedCtx red) {
     if (!S->anyActive) return;
     int act[3];
 #pragma unroll
@@ -461,7 +467,7 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_bi_rho(const double* __restrict__
 #pragma unroll
         for (int c = 0; c < 3; c++) if (act[c]) { const size_t j = (size_t)c * ld + i; v[c] += r0[j] * r[j]; }
     }
-    grid_reduce<3, OpSum>(v, partials, ticket, Fin{PH_BI_RHO, S, P, nGlob, 3});
+    grid_reduce<3, OpSum>(v, red, Fin{PH_BI_RHO, S, P, nGlob, 3, Cond{}});
 }
 
 // pA = rA + beta (pA - omega AyA)  (first iteration: pA = rA);  yA = M^-1 pA for the local preconditioners
@@ -488,7 +494,7 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_bi_p(const double* __restrict__ r
 // sA = rA - alpha AyA ; sums |sA| ;  zA = M^-1 sA for the local preconditioners
 __global__ void __launch_bounds__(S4F_BLOCK) k_bi_s(const double* __restrict__ r, const double* __restrict__ AyA, const double* __restrict__ rD,
                                                     double* __restrict__ sA, double* __restrict__ z, int N, int ld, PcgScalars* S, PcgParams P,
-                                                    double nGlob, double* partials, unsigned int* ticket) {
+                                                    double nGlob, RedCtx red) {
     if (!S->anyActive) return;
     int act[3]; double alpha[3];
 #pragma unroll
@@ -505,15 +511,14 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_bi_s(const double* __restrict__ r
             v[c] += fabs(ss);
         }
     }
-    grid_reduce<3, OpSum>(v, partials, ticket, Fin{PH_BI_S, S, P, nGlob, 3});
+    grid_reduce<3, OpSum>(v, red, Fin{PH_BI_S, S, P, nGlob, 3, Cond{}});
 }
 
 // psi += alpha yA + omega zA ; rA = sA - omega tA ; sums |rA|.   Components that converged on the half step
 // only take psi += alpha yA.
 __global__ void __launch_bounds__(S4F_BLOCK) k_bi_xr(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ y,
                                                      const double* __restrict__ z, const double* __restrict__ sA, const double* __restrict__ tA,
-                                                     int N, int ld, PcgScalars* S, PcgParams P, double nGlob, double* partials,
-                                                     unsigned int* ticket) {
+                                                     int N, int ld, PcgScalars* S, PcgParams P, double nGlob, RedCtx red) {
     if (!S->anyActive) return;
     int act[3], half[3]; double alpha[3], omega[3];
 #pragma unroll
@@ -531,62 +536,27 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_bi_xr(double* __restrict__ x, dou
             } else if (half[c]) x[j] += alpha[c] * y[j];
         }
     }
-    grid_reduce<3, OpSum>(v, partials, ticket, Fin{PH_BI_XR, S, P, nGlob, 3});
-}
-
-// pack boundary-cell values of an ncomp-component SoA field into the send buffer
-__global__ void k_pack(const double* __restrict__ f, const int* __restrict__ sendCells, double* __restrict__ buf, int G, int ld, int ncomp) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= G * ncomp) return;
-    int q = i / G, g = i % G;
-    buf[i] = f[(size_t)q * ld + sendCells[g]];
-}
-__global__ void k_unpack(double* __restrict__ f, const double* __restrict__ buf, int G, int N, int ld, int ncomp) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= G * ncomp) return;
-    int q = i / G, g = i % G;
-    f[(size_t)q * ld + N + g] = buf[i];
+    grid_reduce<3, OpSum>(v, red, Fin{PH_BI_XR, S, P, nGlob, 3, Cond{}});
 }
 
 PcgParams make_params(const s4fgpu_ctx* c) {
     PcgParams P;
     P.tolerance = c->ctl.tolerance; P.relTol = c->ctl.relTol; P.maxIter = c->ctl.maxIter;
     for (int i = 0; i < 3; i++) P.solD[i] = c->solD[i];
-    P.defer = (c->nRanks > 1) ? 1 : 0;
     P.precond = c->ctl.preconditioner;
+    // the K-cycle (two inner Krylov steps) and the fp32 cycle are not fixed linear operators: use the flexible recurrence
+    P.flexible = (P.precond == S4F_PRECOND_GAMG && (c->ctl.gamgCycle == 2 || c->ctl.gamgSinglePrecision)) ? 1 : 0;
     return P;
 }
 
 }  // namespace
 
-// Halo exchange of an ncomp-component SoA field: pack boundary-cell values, one grouped
-// ncclSend/ncclRecv per neighbour, unpack into the ghost range [N, N+G).   Replaces the
-// processor-patch initEvaluate/evaluate (and initMatrixInterfaces/updateMatrixInterfaces in Amul).
+// Halo exchange of an ncomp-component SoA field: the boundary-cell values go into the neighbours' ghost range [N, N+G)
+// in one kernel over peer memory (s4f_comm.cu).  Replaces the processor-patch initEvaluate/evaluate (and
+// initMatrixInterfaces/updateMatrixInterfaces in Amul).
 int s4f_halo_exchange(s4fgpu_ctx* c, double* field, int ncomp) {
-    if (c->nRanks <= 1 || c->G == 0) return 0;
-    const int G = c->G;
-    if (c->sendBuf.n < (size_t)ncomp * G) { S4F_CHECK_CUDA(c, c->sendBuf.alloc((size_t)ncomp * G)); S4F_CHECK_CUDA(c, c->recvBuf.alloc((size_t)ncomp * G)); }
-    k_pack<<<(G * ncomp + 255) / 256, 256, 0, c->stream>>>(field, c->sendCells.p, c->sendBuf.p, G, c->ld, ncomp);
-    c->launches++;
-    // buffers are component-major over all G ghosts: per neighbour send one strided piece per component
-    S4F_CHECK_NCCL(c, ncclGroupStart());
-    for (const auto& nb : c->nbrs)
-        for (int q = 0; q < ncomp; q++) {
-            S4F_CHECK_NCCL(c, ncclSend(c->sendBuf.p + (size_t)q * G + nb.sendOff, nb.count, ncclDouble, nb.rank, c->comm, c->stream));
-            S4F_CHECK_NCCL(c, ncclRecv(c->recvBuf.p + (size_t)q * G + nb.sendOff, nb.count, ncclDouble, nb.rank, c->comm, c->stream));
-        }
-    S4F_CHECK_NCCL(c, ncclGroupEnd());
-    k_unpack<<<(G * ncomp + 255) / 256, 256, 0, c->stream>>>(field, c->recvBuf.p, G, c->N, c->ld, ncomp);
-    c->launches++;
-    return 0;
-}
-
-static int allreduce_part(s4fgpu_ctx* c, int n, int phase, const PcgParams& P, double nGlob) {
     if (c->nRanks <= 1) return 0;
-    S4F_CHECK_NCCL(c, ncclAllReduce((double*)c->pcgS.p, (double*)c->pcgS.p, n, ncclDouble, ncclSum, c->comm, c->stream));
-    k_pcg_scalar_step<<<1, 32, 0, c->stream>>>(phase, c->pcgS.p, P, nGlob);
-    c->launches++;
-    return 0;
+    return s4f_halo_run<double>(c, c->halo0, field, c->ld, ncomp, c->N);
 }
 
 static int amul3(s4fgpu_ctx* c, const double* p, double* w, bool dot, const PcgParams& P, double nGlob, int mask,
@@ -594,7 +564,7 @@ static int amul3(s4fgpu_ctx* c, const double* p, double* w, bool dot, const PcgP
     const int grid = s4f_grid(c->numSMs, (long long)c->nSlices * 32, 4);
 #define S4F_AMUL3(DOT)                                                                                                              \
     k_amul3<DOT><<<grid, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, p, w, c->N, c->ld, c->nSlices, c->pcgS.p, \
-                                                    P, nGlob, c->partials.p, c->ticket.p, mask, dotv ? dotv : p, phase)
+                                                    P, nGlob, c->red(), mask, dotv ? dotv : p, phase)
     if (!dot) S4F_AMUL3(0);
     else if (twoDots) S4F_AMUL3(2);
     else S4F_AMUL3(1);
@@ -683,111 +653,221 @@ static int solve_pbicgstab(s4fgpu_ctx* c, double* psi, PcgParams P, double nGlob
         if (!c->hPcgS->anyActive || it >= P.maxIter) break;
         const int burst = local ? (c->ctl.checkEvery > 0 ? c->ctl.checkEvery : 4) : 1;
         for (int k = 0; k < burst; k++, it++) {
-            k_bi_rho<<<gridV, S4F_BLOCK, 0, c->stream>>>(rA0, c->rA.p, N, ld, S, P, nGlob, c->partials.p, c->ticket.p);
+            k_bi_rho<<<gridV, S4F_BLOCK, 0, c->stream>>>(rA0, c->rA.p, N, ld, S, P, nGlob, c->red());
             c->launches++;
-            if ((rc = allreduce_part(c, 3, PH_BI_RHO, P, nGlob))) return rc;
             k_bi_p<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->rA.p, AyA, rD, c->pA.p, local ? yA : nullptr, N, ld, S);
             c->launches++;
             if (!local && (rc = precondition(c->pA.p, yA))) return rc;
             if ((rc = s4f_halo_exchange(c, yA, 3))) return rc;
             if ((rc = amul3(c, yA, AyA, true, P, nGlob, 7, rA0, PH_BI_ALPHA))) return rc;
-            if ((rc = allreduce_part(c, 3, PH_BI_ALPHA, P, nGlob))) return rc;
-            k_bi_s<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->rA.p, AyA, rD, sA, local ? zA : nullptr, N, ld, S, P, nGlob, c->partials.p, c->ticket.p);
+            k_bi_s<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->rA.p, AyA, rD, sA, local ? zA : nullptr, N, ld, S, P, nGlob, c->red());
             c->launches++;
-            if ((rc = allreduce_part(c, 3, PH_BI_S, P, nGlob))) return rc;
             if (!local && (rc = precondition(sA, zA))) return rc;
             if ((rc = s4f_halo_exchange(c, zA, 3))) return rc;
             if ((rc = amul3(c, zA, tA, true, P, nGlob, 7, sA, PH_BI_OMEGA, true))) return rc;
-            if ((rc = allreduce_part(c, 6, PH_BI_OMEGA, P, nGlob))) return rc;
-            k_bi_xr<<<gridV, S4F_BLOCK, 0, c->stream>>>(psi, c->rA.p, yA, zA, sA, tA, N, ld, S, P, nGlob, c->partials.p, c->ticket.p);
+            k_bi_xr<<<gridV, S4F_BLOCK, 0, c->stream>>>(psi, c->rA.p, yA, zA, sA, tA, N, ld, S, P, nGlob, c->red());
             c->launches++;
-            if ((rc = allreduce_part(c, 3, PH_BI_XR, P, nGlob))) return rc;
         }
     }
     return 0;
 }
 
-// fvMatrix<vector>::solveSegregated for device SoA psi (3*ld, ghosts/boundary slots untouched) and source
-int s4f_solve_segregated(s4fgpu_ctx* c, double* psi, const double* source) {
+// ---- one PCG iteration / the set-up of a solve as launch sequences (run directly on the stream, or captured) ----------
+struct SolveArgs { double* psi; const double* source; PcgParams P; double nGlob; Cond cond; };
+
+static int enqueue_init(s4fgpu_ctx* c, const SolveArgs& a) {
     const int N = c->N, ld = c->ld;
-    PcgParams P = make_params(c);
-    const double nGlob = global_cells(c);
-    const int gridV = s4f_grid(c->numSMs, N), gridV2 = s4f_grid(c->numSMs, (N + 1) / 2), gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
+    const int gridV = s4f_grid(c->numSMs, N), gridM = s4f_grid(c->numSMs, (long long)c->nSlices * 32);
     PcgScalars* S = c->pcgS.p;
-    const bool fusedJacobi = (P.precond == S4F_PRECOND_DIAGONAL || P.precond == S4F_PRECOND_NONE);
-    if (P.precond == S4F_PRECOND_CHEBYSHEV && c->cheb0.n != 3 * (size_t)ld) {
-        S4F_CHECK_CUDA(c, c->cheb0.alloc(3 * (size_t)ld)); S4F_CHECK_CUDA(c, c->cheb1.alloc(3 * (size_t)ld));
-    }
-    if (P.precond == S4F_PRECOND_GAMG && !c->amgValid) {
-        int rca = s4f_amg_setup(c); if (rca) return rca;
-        c->amgValid = true;
-    }
-
-    k_pcg_sum<<<gridV, S4F_BLOCK, 0, c->stream>>>(psi, N, ld, S, P, nGlob, c->partials.p, c->ticket.p);
+    k_pcg_sum<<<gridV, S4F_BLOCK, 0, c->stream>>>(a.psi, N, ld, S, a.P, a.nGlob, c->red());
     c->launches++;
-    int rc = allreduce_part(c, 3, PH_AVG, P, nGlob); if (rc) return rc;
-    rc = s4f_halo_exchange(c, psi, 3); if (rc) return rc;
-    k_pcg_init<<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, c->rDiagC.p, psi, source, c->rA.p, N, ld, c->nSlices,
-                                                   S, P, nGlob, c->partials.p, c->ticket.p);
+    int rc = s4f_halo_exchange(c, a.psi, 3); if (rc) return rc;
+    k_pcg_init<<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eA.p, c->diagC.p, c->rDiagC.p, a.psi, a.source, c->rA.p, N, ld, c->nSlices,
+                                                   S, a.P, a.nGlob, c->red(), a.cond);
     c->launches++;
-    rc = allreduce_part(c, 9, PH_INIT, P, nGlob); if (rc) return rc;
+    return 0;
+}
 
-    if (c->ctl.solver == S4F_SOLVER_PBICGSTAB) {
-        rc = solve_pbicgstab(c, psi, P, nGlob); if (rc) return rc;
-        for (int q = 0; q < 3; q++) {
-            c->last.initialResidual[q] = c->hPcgS->initRes[q];
-            c->last.finalResidual[q] = c->hPcgS->finalRes[q];
-            c->last.nIterations[q] = c->hPcgS->nIter[q];
-            c->totalInner += c->hPcgS->nIter[q];
-        }
-        S4F_CHECK_CUDA(c, cudaGetLastError());
-        return 0;
+static int enqueue_iteration(s4fgpu_ctx* c, const SolveArgs& a) {
+    const int N = c->N, ld = c->ld;
+    const int gridV = s4f_grid(c->numSMs, N), gridV2 = s4f_grid(c->numSMs, (N + 1) / 2);
+    PcgScalars* S = c->pcgS.p;
+    const PcgParams& P = a.P;
+    int rc = 0;
+    if (P.precond == S4F_PRECOND_DIAGONAL || P.precond == S4F_PRECOND_NONE) {
+        if (P.precond == S4F_PRECOND_NONE) k_pcg_p_generic<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rA.p, c->pA.p, N, ld, S);
+        else k_pcg_p<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rDiagC.p, c->rA.p, c->pA.p, N, ld, S);
+        c->launches++;
+    } else {
+        // z = M^-1 rA goes to its own vector: wA still holds A pA of the previous iteration, which the flexible beta needs
+        if (P.precond == S4F_PRECOND_GAMG) {
+            c->amgAct = &S->active[0];              // converged components skip their share of the cycle
+            rc = s4f_amg_apply(c, c->rA.p, c->zA.p);
+            c->amgAct = nullptr;
+        } else if (P.precond == S4F_PRECOND_DIC) rc = s4f_dic_apply(c, c->rA.p, c->zA.p);      // exact DIC / FDIC, level scheduled
+        else rc = cheb_apply(c, P, c->rA.p, c->zA.p);
+        if (rc) return rc;
+        k_pcg_dot_zr<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->zA.p, c->rA.p, P.flexible ? c->wA.p : nullptr, N, ld, S, P, a.nGlob, c->red());
+        c->launches++;
+        k_pcg_p_generic<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->zA.p, c->pA.p, N, ld, S);
+        c->launches++;
     }
+    rc = s4f_halo_exchange(c, c->pA.p, 3); if (rc) return rc;
+    rc = amul3(c, c->pA.p, c->wA.p, true, P, a.nGlob, 7); if (rc) return rc;
+    k_pcg_xr<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rDiagC.p, a.psi, c->rA.p, c->pA.p, c->wA.p, N, ld, S, P, a.nGlob, c->red(), a.cond);
+    c->launches++;
+    return 0;
+}
 
-    // the host polls the device-side flags every checkEvery iterations (an idle iteration costs three early-exit
-    // launches); a multigrid / polynomial application is far dearer than a poll, so those poll every iteration
-    const int checkEvery = fusedJacobi ? (c->ctl.checkEvery > 0 ? c->ctl.checkEvery : 4) : 1;
-    int it = 0;
-    for (;;) {
-        S4F_CHECK_CUDA(c, cudaMemcpyAsync(c->hPcgS, S, sizeof(PcgScalars), cudaMemcpyDeviceToHost, c->stream));
-        S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (!c->hPcgS->anyActive || it >= P.maxIter) break;
-        for (int k = 0; k < checkEvery; k++, it++) {
-            if (fusedJacobi) {
-                if (c->ctl.preconditioner == S4F_PRECOND_NONE)
-                    k_pcg_p_generic<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rA.p, c->pA.p, N, ld, S);
-                else
-                    k_pcg_p<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rDiagC.p, c->rA.p, c->pA.p, N, ld, S);
-                c->launches++;
-            } else {
-                if (P.precond == S4F_PRECOND_GAMG) {
-                    c->amgAct = &S->active[0];              // converged components skip their share of the V-cycle
-                    rc = s4f_amg_apply(c, c->rA.p, c->wA.p);
-                    c->amgAct = nullptr;
-                } else if (P.precond == S4F_PRECOND_DIC) rc = s4f_dic_apply(c, c->rA.p, c->wA.p);      // exact DIC / FDIC, level scheduled
-                else rc = cheb_apply(c, P, c->rA.p, c->wA.p);
-                if (rc) return rc;
-                k_pcg_dot_zr<<<gridV, S4F_BLOCK, 0, c->stream>>>(c->wA.p, c->rA.p, N, ld, S, P, nGlob, c->partials.p, c->ticket.p);
-                c->launches++;
-                rc = allreduce_part(c, 3, PH_DOT, P, nGlob); if (rc) return rc;
-                k_pcg_p_generic<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->wA.p, c->pA.p, N, ld, S);
-                c->launches++;
-            }
-            rc = s4f_halo_exchange(c, c->pA.p, 3); if (rc) return rc;
-            rc = amul3(c, c->pA.p, c->wA.p, true, P, nGlob, 7); if (rc) return rc;
-            rc = allreduce_part(c, 3, PH_AMUL, P, nGlob); if (rc) return rc;
-            k_pcg_xr<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rDiagC.p, psi, c->rA.p, c->pA.p, c->wA.p, N, ld, S, P, nGlob, c->partials.p, c->ticket.p);
-            c->launches++;
-            rc = allreduce_part(c, 6, PH_XR, P, nGlob); if (rc) return rc;
-        }
+// ---- the whole solve as ONE CUDA graph: set-up kernels, then a conditional WHILE node whose body is one PCG iteration.
+// The loop condition is the device-side `anyActive` flag, written by the finisher of the residual reduction
+// (cudaGraphSetConditional in Fin): no host round trip per iteration, no launch gaps between the ~100 small kernels of a
+// multigrid cycle.  All ranks of a decomposed run execute the same number of iterations because the reductions give
+// bit-identical results everywhere.
+struct SolveGraph {
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    const void* key[8] = {}; long long serial = -1; PcgParams P{}; double nGlob = 0; int N = 0;
+    long long preLaunches = 0, bodyLaunches = 0;
+    ~SolveGraph() { if (exec) cudaGraphExecDestroy(exec); if (graph) cudaGraphDestroy(graph); }
+};
+struct S4fSolveGraphs { std::vector<std::unique_ptr<SolveGraph>> g; bool unsupported = false; };
+
+void s4f_solve_graphs_destroy(s4fgpu_ctx* c) { delete c->solveGraphs; c->solveGraphs = nullptr; }
+
+static bool same_params(const PcgParams& a, const PcgParams& b) {
+    return a.tolerance == b.tolerance && a.relTol == b.relTol && a.maxIter == b.maxIter && a.precond == b.precond && a.flexible == b.flexible &&
+           a.solD[0] == b.solD[0] && a.solD[1] == b.solD[1] && a.solD[2] == b.solD[2];
+}
+
+static int capture_solve(s4fgpu_ctx* c, SolveArgs a, SolveGraph& G) {
+#define S4F_CAP(call)                                                                                                 \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { c->err = std::string(#call) + ": " + cudaGetErrorString(e_); \
+         cudaStreamCaptureStatus st_; if (cudaStreamIsCapturing(c->stream, &st_) == cudaSuccess && st_ != cudaStreamCaptureStatusNone) { cudaGraph_t g_; cudaStreamEndCapture(c->stream, &g_); } \
+         cudaGetLastError(); return 2; } } while (0)
+    S4F_CAP(cudaGraphCreate(&G.graph, 0));
+    cudaGraphConditionalHandle h;
+    S4F_CAP(cudaGraphConditionalHandleCreate(&h, G.graph, 0, cudaGraphCondAssignDefault));
+    a.cond.h = h; a.cond.on = 1;
+    const long long l0 = c->launches;
+    S4F_CAP(cudaStreamBeginCaptureToGraph(c->stream, G.graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_init(c, a);
+    cudaStreamCaptureStatus st; const cudaGraphNode_t* deps = nullptr; size_t nDeps = 0;
+    if (!rc) S4F_CAP(cudaStreamGetCaptureInfo(c->stream, &st, nullptr, nullptr, &deps, &nDeps));
+    std::vector<cudaGraphNode_t> last(deps, deps + nDeps);
+    cudaGraph_t g2;
+    S4F_CAP(cudaStreamEndCapture(c->stream, &g2));
+    if (rc) return rc;
+    G.preLaunches = c->launches - l0;
+    cudaGraphNodeParams cp = {};
+    cp.type = cudaGraphNodeTypeConditional;
+    cp.conditional.handle = h; cp.conditional.type = cudaGraphCondTypeWhile; cp.conditional.size = 1;
+    cudaGraphNode_t node;
+    S4F_CAP(cudaGraphAddNode(&node, G.graph, last.data(), last.size(), &cp));
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    const long long l1 = c->launches;
+    S4F_CAP(cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_iteration(c, a);
+    S4F_CAP(cudaStreamEndCapture(c->stream, &g2));
+    if (rc) return rc;
+    G.bodyLaunches = c->launches - l1;
+    c->launches = l0;                               // nothing ran yet
+    S4F_CAP(cudaGraphInstantiate(&G.exec, G.graph, 0));
+#undef S4F_CAP
+    return 0;
+}
+
+static SolveGraph* find_or_capture(s4fgpu_ctx* c, const SolveArgs& a) {
+    if (!c->solveGraphs) c->solveGraphs = new S4fSolveGraphs();
+    S4fSolveGraphs& SG = *c->solveGraphs;
+    if (SG.unsupported) return nullptr;
+    const void* key[8] = {a.psi, a.source, c->eA.p, c->diagC.p, c->rDiagC.p, c->slicePtr.p, c->col.p, c->rA.p};
+    for (auto it = SG.g.begin(); it != SG.g.end();) {
+        SolveGraph& G = **it;
+        if (G.serial != c->graphSerial) { it = SG.g.erase(it); continue; }
+        if (!std::memcmp(G.key, key, sizeof(key)) && same_params(G.P, a.P) && G.nGlob == a.nGlob && G.N == c->N) return &G;
+        ++it;
     }
+    std::unique_ptr<SolveGraph> G(new SolveGraph());
+    std::memcpy(G->key, key, sizeof(key)); G->serial = c->graphSerial; G->P = a.P; G->nGlob = a.nGlob; G->N = c->N;
+    if (capture_solve(c, a, *G)) {
+        SG.unsupported = true;
+        fprintf(stderr, "libs4fgpu: CUDA-graph capture of the PCG solve failed (%s); using stream launches with host polling\n", c->err.c_str());
+        c->err.clear();
+        return nullptr;
+    }
+    if (SG.g.size() >= 4) SG.g.erase(SG.g.begin());
+    SG.g.push_back(std::move(G));
+    return SG.g.back().get();
+}
+
+// read the finished solve's scalars (one synchronisation; the outer loop shares it with its own residual read-back)
+int s4f_finish_solve(s4fgpu_ctx* c) {
+    if (!c->solvePending) return 0;
+    S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->solvePending = false;
+    int loops = 0;
     for (int q = 0; q < 3; q++) {
         c->last.initialResidual[q] = c->hPcgS->initRes[q];
         c->last.finalResidual[q] = c->hPcgS->finalRes[q];
         c->last.nIterations[q] = c->hPcgS->nIter[q];
         c->totalInner += c->hPcgS->nIter[q];
+        loops = std::max(loops, c->hPcgS->nIter[q]);
     }
+    c->launches += c->pendingPre + c->pendingBody * loops;
+    c->pendingPre = c->pendingBody = 0;
     S4F_CHECK_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+// fvMatrix<vector>::solveSegregated for device SoA psi (3*ld, ghosts/boundary slots untouched) and source.
+// defer: leave the read-back of the solver statistics to s4f_finish_solve (the caller synchronises later anyway).
+int s4f_solve_segregated(s4fgpu_ctx* c, double* psi, const double* source, bool defer) {
+    const int ld = c->ld;
+    int rc = s4f_finish_solve(c); if (rc) return rc;
+    PcgParams P = make_params(c);
+    const double nGlob = global_cells(c);
+    PcgScalars* S = c->pcgS.p;
+    const bool local = (P.precond == S4F_PRECOND_DIAGONAL || P.precond == S4F_PRECOND_NONE);
+    if (P.precond == S4F_PRECOND_CHEBYSHEV && c->cheb0.n != 3 * (size_t)ld) {
+        S4F_CHECK_CUDA(c, c->cheb0.alloc(3 * (size_t)ld)); S4F_CHECK_CUDA(c, c->cheb1.alloc(3 * (size_t)ld));
+    }
+    if (!local && c->zA.n != 3 * (size_t)ld) { S4F_CHECK_CUDA(c, c->zA.alloc(3 * (size_t)ld)); c->graphSerial++; }
+    if (P.precond == S4F_PRECOND_GAMG && !c->amgValid) {
+        int rca = s4f_amg_setup(c); if (rca) return rca;
+        c->amgValid = true;
+    }
+    SolveArgs a{psi, source, P, nGlob, Cond{}};
+
+    if (c->ctl.solver == S4F_SOLVER_PBICGSTAB) {
+        if ((rc = enqueue_init(c, a))) return rc;
+        if ((rc = solve_pbicgstab(c, psi, P, nGlob))) return rc;
+        c->solvePending = true;
+        return s4f_finish_solve(c);
+    }
+
+    // graph path: everything but the level-scheduled DIC (thousands of tiny launches per application) and the polynomial
+    static const bool noGraph = getenv("S4F_NO_GRAPH") != nullptr;
+    SolveGraph* G = (!noGraph && (local || P.precond == S4F_PRECOND_GAMG)) ? find_or_capture(c, a) : nullptr;
+    if (G) {
+        S4F_CHECK_CUDA(c, cudaGraphLaunch(G->exec, c->stream));
+        c->pendingPre = G->preLaunches; c->pendingBody = G->bodyLaunches;
+    } else {
+        // stream path: the host polls the device-side flags every checkEvery iterations (an idle iteration costs three
+        // early-exit launches); a DIC / polynomial application is far dearer than a poll, so those poll every iteration
+        if ((rc = enqueue_init(c, a))) return rc;
+        const int checkEvery = local ? (c->ctl.checkEvery > 0 ? c->ctl.checkEvery : 4) : 1;
+        int it = 0;
+        for (;;) {
+            S4F_CHECK_CUDA(c, cudaMemcpyAsync(c->hPcgS, S, sizeof(PcgScalars), cudaMemcpyDeviceToHost, c->stream));
+            S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+            if (!c->hPcgS->anyActive || it >= P.maxIter) break;
+            for (int k = 0; k < checkEvery; k++, it++)
+                if ((rc = enqueue_iteration(c, a))) return rc;
+        }
+    }
+    S4F_CHECK_CUDA(c, cudaMemcpyAsync(c->hPcgS, S, sizeof(PcgScalars), cudaMemcpyDeviceToHost, c->stream));
+    c->solvePending = true;
+    if (!defer) return s4f_finish_solve(c);
     return 0;
 }
 
@@ -815,7 +895,7 @@ int s4f_time_pcg_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, doubl
     PcgScalars h; memset(&h, 0, sizeof(h));
     for (int q = 0; q < 3; q++) { h.active[q] = 1; h.alpha[q] = 1e-3; h.beta[q] = 0.5; h.nIter[q] = 1; h.rho[q] = 1; h.rhoOld[q] = 1; h.normFactor[q] = 1; h.initRes[q] = 1; }
     h.anyActive = 1;
-    PcgParams Pn = P; Pn.maxIter = 1 << 30; Pn.tolerance = 0; Pn.relTol = 0; Pn.defer = 0;
+    PcgParams Pn = P; Pn.maxIter = 1 << 30; Pn.tolerance = 0; Pn.relTol = 0;
     if (flushL2 && c->flushBuf.n == 0) S4F_CHECK_CUDA(c, c->flushBuf.alloc((size_t)48 * 1024 * 1024));   // 384 MB > 126 MB L2
     cudaEvent_t e0, e1;
     S4F_CHECK_CUDA(c, cudaEventCreate(&e0)); S4F_CHECK_CUDA(c, cudaEventCreate(&e1));
@@ -833,13 +913,13 @@ int s4f_time_pcg_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, doubl
             k_pcg_p<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rDiagC.p, c->rA.p, c->pA.p, N, ld, c->pcgS.p);
             c->launches++;
         } else if (kernel == S4F_KERNEL_PCG_XR) {
-            k_pcg_xr<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rDiagC.p, c->source.p, c->rA.p, c->pA.p, c->wA.p, N, ld, c->pcgS.p, Pn, 1.0, c->partials.p, c->ticket.p);
+            k_pcg_xr<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rDiagC.p, c->source.p, c->rA.p, c->pA.p, c->wA.p, N, ld, c->pcgS.p, Pn, 1.0, c->red(), Cond{});
             c->launches++;
         } else {
             k_pcg_p<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rDiagC.p, c->rA.p, c->pA.p, N, ld, c->pcgS.p);
             c->launches++;
             amul3(c, c->pA.p, c->wA.p, true, Pn, 1.0, 7);
-            k_pcg_xr<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rDiagC.p, c->source.p, c->rA.p, c->pA.p, c->wA.p, N, ld, c->pcgS.p, Pn, 1.0, c->partials.p, c->ticket.p);
+            k_pcg_xr<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rDiagC.p, c->source.p, c->rA.p, c->pA.p, c->wA.p, N, ld, c->pcgS.p, Pn, 1.0, c->red(), Cond{});
             c->launches++;
         }
         S4F_CHECK_CUDA(c, cudaEventRecord(e1, c->stream));

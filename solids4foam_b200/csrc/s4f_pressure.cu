@@ -147,11 +147,17 @@ int s4f_pressure_smooth(s4fgpu_ctx* c) {
     S4F_CHECK_CUDA(c, cudaMemcpyAsync(c->pX.p, c->sigmaHyd.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     {   // sigmaHydEqn.solve(): the fused solver on the pressure matrix (Jacobi-preconditioned PCG; the momentum GAMG hierarchy
         // belongs to another matrix)
+        if ((rc = s4f_finish_solve(c))) return rc;      // the momentum solve's statistics are read before they are set aside
         const s4fgpu_stats keep = c->last; const long long keepInner = c->totalInner;
         const int pre = c->ctl.preconditioner, sol = c->ctl.solver;
         std::swap(c->eA.p, c->eP.p); std::swap(c->diagC.p, c->pDiag.p); std::swap(c->rDiagC.p, c->pRDiag.p);
         c->ctl.preconditioner = S4F_PRECOND_DIAGONAL; c->ctl.solver = S4F_SOLVER_PCG;
+        // the scalar equation rides component 0 whatever the mesh's empty directions are (a 2-D case whose empty direction
+        // is x would otherwise skip it)
+        const int keepD[3] = {c->solD[0], c->solD[1], c->solD[2]};
+        c->solD[0] = 1; c->solD[1] = 0; c->solD[2] = 0;
         rc = s4f_solve_segregated(c, c->pX.p, c->pB.p);
+        for (int q = 0; q < 3; q++) c->solD[q] = keepD[q];
         c->ctl.preconditioner = pre; c->ctl.solver = sol;
         std::swap(c->eA.p, c->eP.p); std::swap(c->diagC.p, c->pDiag.p); std::swap(c->rDiagC.p, c->pRDiag.p);
         c->lastP = c->last; c->last = keep; c->totalInner = keepInner;

@@ -10,7 +10,7 @@
 #include <cmath>
 #include <cstring>
 
-#include "s4f_ctx.h"
+#include "s4f_comm.h"
 #include "s4f_dev.cuh"
 
 namespace {
@@ -244,9 +244,13 @@ int s4f_build_rows(s4fgpu_ctx* c) {
         S4F_CHECK_CUDA(c, c->bcCells.upload(cells)); S4F_CHECK_CUDA(c, c->bcPtr.upload(ptr)); S4F_CHECK_CUDA(c, c->bcFaces.upload(faces));
     }
     // halo
-    if (G > 0) {
-        S4F_CHECK_CUDA(c, c->sendCells.upload(sendCells));
-        S4F_CHECK_CUDA(c, c->sendBuf.alloc(9 * (size_t)G)); S4F_CHECK_CUDA(c, c->recvBuf.alloc(9 * (size_t)G));
+    if (G > 0) S4F_CHECK_CUDA(c, c->sendCells.upload(sendCells));
+    if (c->nRanks > 1) {       // collective: every rank (also one without processor patches) builds its plan here
+        s4f_halo_plan_destroy(c->halo0); c->halo0 = nullptr;
+        std::vector<int> nbrRank, nbrCount;
+        for (const auto& nb : c->nbrs) { nbrRank.push_back(nb.rank); nbrCount.push_back(nb.count); }
+        int rc = s4f_halo_plan_create(c, nbrRank, nbrCount, sendCells, 9, &c->halo0); if (rc) return rc;
+        c->graphSerial++;
     }
     return 0;
 }

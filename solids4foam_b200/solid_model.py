@@ -201,7 +201,8 @@ class SolidModel:
     def gamg_info(self) -> dict:
         n, sizes, by, st = C.c_int(), (C.c_int * 16)(), C.c_double(), C.c_double()
         self._check(self.L.s4fgpu_gamg_info(self.h, C.byref(n), sizes, 16, C.byref(by), C.byref(st)))
-        return dict(levels=[sizes[i] for i in range(n.value)], bytes_per_vcycle=by.value, setup_seconds=st.value)
+        return dict(levels=[sizes[i] for i in range(n.value)], bytes_per_vcycle=by.value, setup_seconds=st.value,
+                    distributed_levels=int(self.L.s4fgpu_gamg_distributed_levels(self.h)))
 
     def launch_count(self) -> int:
         return int(self.L.s4fgpu_launch_count(self.h))
