@@ -1,18 +1,10 @@
 /*---------------------------------------------------------------------------*\
   See gpuNonLinGeomUpdatedLagSolid.H.  Source only: needs OpenFOAM + solids4foam to compile.
-  The mesh / boundary-condition mirroring is the one of gpuLinGeomTotalDispSolid.C (same C-ABI
-  calls); only what differs for the updated-Lagrangian model is spelled out here.
 \*---------------------------------------------------------------------------*/
 #include "gpuNonLinGeomUpdatedLagSolid.H"
 #include "addToRunTimeSelectionTable.H"
 #include "fvc.H"
 #include "fvm.H"
-#include "emptyPolyPatch.H"
-#include "symmetryPolyPatch.H"
-#include "processorFvPatch.H"
-#include "solidTractionFvPatchVectorField.H"
-#include "fixedDisplacementFvPatchVectorField.H"
-#include "solidSymmetryFvPatchVectorField.H"
 
 namespace Foam
 {
@@ -23,64 +15,16 @@ defineTypeNameAndDebug(gpuNonLinGeomUpdatedLagSolid, 0);
 addToRunTimeSelectionTable(solidModel, gpuNonLinGeomUpdatedLagSolid, dictionary);   // nonLinGeomUpdatedLagSolid.C:40-43
 
 
-void gpuNonLinGeomUpdatedLagSolid::check(const int rc, const char* where) const
-{
-    if (rc != 0)
-    {
-        FatalErrorIn(where) << "libs4fgpu: " << s4fgpu_last_error(gpu_) << abort(FatalError);
-    }
-}
-
-
-// mirrorMesh(), mirrorBoundaryConditions(): identical to gpuLinGeomTotalDispSolid.C (s4fgpu_set_mesh / s4fgpu_set_bc)
-// with DD().boundaryField() in place of D().boundaryField(): the fixedDisplacement patches hand over the TOTAL
-// displacement, the device subtracts D.oldTime() (fixedDisplacementFvPatchVectorField.C:279-287).
-
-
-void gpuNonLinGeomUpdatedLagSolid::mirrorGeometry()
-{
-    // ... the nine geometry arrays exactly as gpuLinGeomTotalDispSolid::mirrorGeometry() builds them, then:
-    // check(s4fgpu_set_geometry(gpu_, C, V, Sf, magSf, Cf, w, nod, corr, CnbrB), "mirrorGeometry()");
-
-    // points() and faces() for the vol->point interpolation (enhancedVolPointInterpolation): CSR of the fv faces
-    const fvMesh& m = mesh();
-    const faceList& fs = m.faces();
-    labelList ptr(1, 0), verts;
-    DynamicList<label> v;
-    for (label faceI = 0; faceI < m.nFaces(); faceI++)
-    {
-        if (faceI >= m.nInternalFaces() && isA<emptyPolyPatch>(m.boundaryMesh()[m.boundaryMesh().whichPatch(faceI)])) continue;
-        forAll(fs[faceI], fp) v.append(fs[faceI][fp]);
-        ptr.append(v.size());
-    }
-    verts.transfer(v);
-    check
-    (
-        s4fgpu_set_points
-        (
-            gpu_, m.nPoints(), reinterpret_cast<const double*>(m.points().cdata()), ptr.begin(), verts.begin()
-        ),
-        "mirrorGeometry()"
-    );
-}
-
-
-void gpuNonLinGeomUpdatedLagSolid::mirrorLawAndControls()
-{
-    // as gpuLinGeomTotalDispSolid::mirrorLawAndControls() with
-    //   law.kind = S4F_LAW_NEO_HOOKEAN_ELASTIC (or S4F_LAW_NEO_HOOKEAN_MISES_PLASTIC + the hardening table),
-    //   mu, K from neoHookeanElastic.C:51-85,  law.solvePressureEqn / pressureSmoothingScaleFactor from the law dict,
-    //   c.solidModel = S4F_MODEL_NONLIN_UL,  c.d2dt2Scheme from d2dt2Schemes (steadyState | Euler | backward),
-    //   c.fieldRelaxD = fieldRelaxationFactor("DD"),  solver controls from solverDict("DD").
-}
-
-
 void gpuNonLinGeomUpdatedLagSolid::downloadState()
 {
-    // D, DD, gradD, gradDD, sigma (+ boundary values) as in gpuLinGeomTotalDispSolid::downloadState(), and
-    check(s4fgpu_download(gpu_, S4F_FIELD_F, reinterpret_cast<double*>(F_.primitiveFieldRef().data())), "downloadState()");
-    check(s4fgpu_download(gpu_, S4F_FIELD_J, J_.primitiveFieldRef().data()), "downloadState()");
-    check(s4fgpu_download(gpu_, S4F_FIELD_RHO, rho_.primitiveFieldRef().data()), "downloadState()");
+    gpu_.downloadVector(D(), S4F_FIELD_D, S4F_FIELD_D_B);
+    gpu_.downloadVector(DD(), S4F_FIELD_DD, S4F_FIELD_DD_B);
+    gpu_.downloadTensor(gradD(), S4F_FIELD_GRAD_D, S4F_FIELD_GRAD_D_B);
+    gpu_.downloadTensor(gradDD(), S4F_FIELD_GRAD_DD, -1);
+    gpu_.downloadSymmTensor(sigma(), S4F_FIELD_SIGMA, S4F_FIELD_SIGMA_B);
+    gpu_.downloadTensor(F_, S4F_FIELD_F, -1);
+    gpu_.download(S4F_FIELD_J, J_.primitiveFieldRef().data(), "downloadState()");
+    gpu_.download(S4F_FIELD_RHO, rho_.primitiveFieldRef().data(), "downloadState()");
 }
 
 
@@ -92,33 +36,30 @@ gpuNonLinGeomUpdatedLagSolid::gpuNonLinGeomUpdatedLagSolid(Time& runTime, const 
     rho_(IOobject("rho", runTime.timeName(), mesh(), IOobject::READ_IF_PRESENT, IOobject::AUTO_WRITE), mechanical().rho()),
     impK_(mechanical().impK()),
     rImpK_(1.0/impK_),
-    gpu_(NULL),
-    patchStart_()
+    gpu_(mesh(), solidModelDict().subOrEmptyDict("gpu"))
 {
     DDisRequired();
     fvm::d2dt2(rho_, DD());                     // old-time levels on the host, as the CPU model (:143-145)
     fvc::d2dt2(rho_, D().oldTime());
 
-    if (s4fgpu_create(&gpu_, Pstream::parRun() ? Pstream::myProcNo() % 8 : 0) != 0)
-    {
-        FatalErrorIn("gpuNonLinGeomUpdatedLagSolid::gpuNonLinGeomUpdatedLagSolid(...)")
-            << s4fgpu_last_error(NULL) << abort(FatalError);
-    }
-    mirrorMesh();
-    mirrorGeometry();
-    mirrorLawAndControls();
-    mirrorBoundaryConditions();
-    check(s4fgpu_upload(gpu_, S4F_FIELD_D, reinterpret_cast<const double*>(D().internalField().cdata())), "ctor");
-    check(s4fgpu_upload(gpu_, S4F_FIELD_D_OLD, reinterpret_cast<const double*>(D().oldTime().internalField().cdata())), "ctor");
-    check(s4fgpu_upload(gpu_, S4F_FIELD_F, reinterpret_cast<const double*>(F_.internalField().cdata())), "ctor");
-    check(s4fgpu_initialise(gpu_), "ctor");
+    gpu_.mirrorMesh();
+    gpu_.mirrorGeometry(true);                  // with points()/faces(): vol->point interpolation runs on the device
+    gpu_.mirrorLaw(mechanical());               // gpuNeoHookeanElastic | gpuNeoHookeanElasticMisesPlastic
+    gpuSolidBridge::loopControls lc = {nCorr(), solutionTol(), alternativeTol(), materialTol()};
+    gpu_.mirrorControls(S4F_MODEL_NONLIN_UL, "DD", solidModelDict(), lc, g().value());
+    // the fixedDisplacement patches hand over the TOTAL displacement, the device subtracts D.oldTime()
+    // (fixedDisplacementFvPatchVectorField.C:279-287)
+    gpu_.mirrorBoundaryConditions(DD());
+
+    gpu_.upload(S4F_FIELD_D, reinterpret_cast<const double*>(D().internalField().cdata()), "ctor");
+    gpu_.upload(S4F_FIELD_D_OLD, reinterpret_cast<const double*>(D().oldTime().internalField().cdata()), "ctor");
+    gpu_.upload(S4F_FIELD_F, reinterpret_cast<const double*>(F_.internalField().cdata()), "ctor");
+    gpu_.check(s4fgpu_initialise(gpu_.handle()), "gpuNonLinGeomUpdatedLagSolid::gpuNonLinGeomUpdatedLagSolid(...)");
 }
 
 
 gpuNonLinGeomUpdatedLagSolid::~gpuNonLinGeomUpdatedLagSolid()
-{
-    s4fgpu_destroy(gpu_);
-}
+{}
 
 
 bool gpuNonLinGeomUpdatedLagSolid::evolve()
@@ -126,20 +67,25 @@ bool gpuNonLinGeomUpdatedLagSolid::evolve()
     Info<< "Evolving solid solver on the GPU" << nl
         << "Solving the updated Lagrangian form of the momentum equation for DD" << endl;
 
-    check(s4fgpu_new_timestep(gpu_, runTime().deltaTValue()), "evolve()");
-    mirrorBoundaryConditions();
+    gpu_.newTimeStepIfNeeded();                 // once per time index, not once per evolve()
+    gpu_.mirrorBoundaryConditions(DD());
 
     s4fgpu_stats st;
-    check(s4fgpu_evolve(gpu_, &st), "evolve()");      // the do-while loop nonLinGeomUpdatedLagSolid.C:166-240
+    gpu_.check(s4fgpu_evolve(gpu_.handle(), &st), "evolve()");      // the do-while loop nonLinGeomUpdatedLagSolid.C:166-240
+
+    Info<< "    Corr, res, relRes, matRes, iters" << nl
+        << "    " << st.nCorr << ", " << st.solverPerfInitRes << ", " << st.relResidual << ", "
+        << st.materialResidual << ", " << st.nIterations[0] + st.nIterations[1] + st.nIterations[2]
+        << nl << endl;
 
     downloadState();
 
     // mechanical().interpolate(DD(), gradDD(), pointDD()) (:249), on the device
-    check
+    gpu_.check
     (
         s4fgpu_interpolate_to_points
         (
-            gpu_, S4F_FIELD_DD, S4F_POINT_INTERP_GRAD, reinterpret_cast<double*>(pointDD().primitiveFieldRef().data())
+            gpu_.handle(), S4F_FIELD_DD, S4F_POINT_INTERP_GRAD, reinterpret_cast<double*>(pointDD().primitiveFieldRef().data())
         ),
         "evolve()"
     );
@@ -173,17 +119,17 @@ void gpuNonLinGeomUpdatedLagSolid::updateTotalFields()
 {
     // moveMesh(oldPoints, DD(), pointDD()) (solidModel.C:2008-2148): the interpolation it starts with runs on the device
     pointVectorField& pDD = pointDD();
-    check
+    gpu_.check
     (
         s4fgpu_interpolate_to_points
         (
-            gpu_, S4F_FIELD_DD, S4F_POINT_INTERP_PATCH, reinterpret_cast<double*>(pDD.primitiveFieldRef().data())
+            gpu_.handle(), S4F_FIELD_DD, S4F_POINT_INTERP_PATCH, reinterpret_cast<double*>(pDD.primitiveFieldRef().data())
         ),
         "updateTotalFields()"
     );
 
     // rho_ = rho_.oldTime()/relJ_, gradD = fvc::grad(D.oldTime() + DD), law history: on the device
-    check(s4fgpu_update_total_fields(gpu_), "updateTotalFields()");
+    gpu_.check(s4fgpu_update_total_fields(gpu_.handle()), "updateTotalFields()");
 
     // symmetry-plane / empty corrections and mesh().movePoints(newPoints): the reference's own host code.  Note that
     // solidModel::moveMesh starts by interpolating DD to the points again on the host (solidModel.C:2020); the device
@@ -192,7 +138,7 @@ void gpuNonLinGeomUpdatedLagSolid::updateTotalFields()
     moveMesh(oldPoints, DD(), pDD);
 
     // the moved geometry goes back to the device; fields, boundary data and history are kept
-    mirrorGeometry();
+    gpu_.mirrorGeometry(true);
 
     solidModel::updateTotalFields();
 }

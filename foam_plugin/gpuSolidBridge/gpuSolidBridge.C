@@ -305,7 +305,7 @@ void gpuSolidBridge::mirrorControls
 }
 
 
-void gpuSolidBridge::mirrorBoundaryConditions(const volVectorField& Dsolved)
+void gpuSolidBridge::mirrorBoundaryConditions(volVectorField& Dsolved)
 {
     forAll(Dsolved.boundaryField(), patchI)
     {
@@ -325,10 +325,16 @@ void gpuSolidBridge::mirrorBoundaryConditions(const volVectorField& Dsolved)
         }
         else if (isA<fixedDisplacementFvPatchVectorField>(pf))
         {
-            // updateCoeffs() has evaluated the time series on the host (fixedDisplacement...C:258-294): for a DD field the
-            // patch holds the TOTAL displacement minus D.oldTime(); the device wants the total and subtracts itself
-            const fixedDisplacementFvPatchVectorField& fd = refCast<const fixedDisplacementFvPatchVectorField>(pf);
-            const vectorField total(fd.totalDisp());
+            // updateCoeffs() evaluates the displacement time series on the host (fixedDisplacement...C:258-294); for a DD field
+            // the patch then holds the TOTAL displacement minus D.oldTime(): the device wants the total and subtracts itself
+            fixedDisplacementFvPatchVectorField& fd =
+                refCast<fixedDisplacementFvPatchVectorField>(Dsolved.boundaryFieldRef()[patchI]);
+            fd.updateCoeffs();
+            vectorField total(fd);
+            if (Dsolved.name() == "DD")
+            {
+                total += mesh_.lookupObject<volVectorField>("D").oldTime().boundaryField()[patchI];
+            }
             check
             (
                 s4fgpu_set_bc(gpu_, patchI, S4F_BC_FIXED_DISPLACEMENT, reinterpret_cast<const double*>(total.cdata()), NULL),

@@ -32,6 +32,27 @@ __global__ void k_xchg(const double* __restrict__ src, double* __restrict__ dst,
     if (threadIdx.x == 0) { unsigned t = atomicAdd(ticket + 1, 1u); if (t == gridDim.x - 1) { ticket[0] = 0; ticket[1] = 0; *seq = k; } }
 }
 
+// LL variant (after NCCL's low-latency protocol): every double travels as two 8-byte words {lo32, flag}, {hi32, flag}; an
+// 8-byte store is atomic, so the receiver needs no fence and no separate flag message: it spins on each element until both
+// flags carry the sequence number.  Any grid size, no block-level synchronisation on the critical path.
+__global__ void k_xchg_ll(const double* __restrict__ src, double* __restrict__ dst, uint2* peerBox, uint2* myBox, unsigned* seq, int n) {
+    const unsigned k = seq[0] + 1, par = k & 1;
+    uint2* out = peerBox + (size_t)par * 2 * n;
+    const volatile uint2* in = myBox + (size_t)par * 2 * n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long v = __double_as_longlong(src[i]);
+        out[2 * i] = make_uint2((unsigned)v, k);
+        out[2 * i + 1] = make_uint2((unsigned)(v >> 32), k);
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint2 a, b;
+        do { a.x = in[2 * i].x; a.y = in[2 * i].y; b.x = in[2 * i + 1].x; b.y = in[2 * i + 1].y; } while (a.y != k || b.y != k);
+        dst[i] = __longlong_as_double(((unsigned long long)b.x << 32) | a.x);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned t = atomicAdd(seq + 1, 1u); if (t == gridDim.x - 1) { seq[1] = 0; __threadfence(); seq[0] = k; } }
+}
+
 int main(int argc, char** argv) {
     const int R = argc > 1 ? atoi(argv[1]) : 2;
     const int n = argc > 2 ? atoi(argv[2]) : 30000;
@@ -90,6 +111,42 @@ int main(int argc, char** argv) {
     float msg; CK(cudaEventElapsedTime(&msg, e0, e1));
     printf("rank %d: %d doubles per exchange, stream launches %.2f us, in a graph %.2f us per exchange, data %s\n", rank, n,
            1e3 * ms / reps, 1e3 * msg / 1000, ok ? "ok" : "WRONG");
+    // ---- LL protocol ----
+    {
+        char* llbox; CK(cudaMalloc(&llbox, 2 * (size_t)n * 16)); CK(cudaMemset(llbox, 0, 2 * (size_t)n * 16));
+        unsigned* seq2; CK(cudaMalloc(&seq2, 8)); CK(cudaMemset(seq2, 0, 8));
+        CK(cudaDeviceSynchronize());
+        CK(cudaIpcGetMemHandle(&sh->h[rank], llbox));
+        __sync_synchronize();
+        // second barrier set: reuse counters beyond the first four
+        __sync_fetch_and_add(&sh->arrived[3], 1); while (sh->arrived[3] < 2 * R) usleep(100);
+        char* peerLL; CK(cudaIpcOpenMemHandle((void**)&peerLL, sh->h[peer], cudaIpcMemLazyEnablePeerAccess));
+        __sync_fetch_and_add(&sh->arrived[2], 1); while (sh->arrived[2] < 2 * R) usleep(100);
+        const int blocksLL = n >= 8192 ? 32 : (n >= 1024 ? 4 : 1);
+        auto launchLL = [&]() { k_xchg_ll<<<blocksLL, 256, 0, s>>>(src, dst, (uint2*)peerLL, (uint2*)llbox, seq2, n); };
+        CK(cudaMemset(dst, 0, n * 8));
+        for (int i = 0; i < 20; i++) launchLL();
+        CK(cudaStreamSynchronize(s));
+        __sync_fetch_and_add(&sh->arrived[1], 1); while (sh->arrived[1] < 2 * R) usleep(100);
+        CK(cudaEventRecord(e0, s));
+        for (int i = 0; i < reps; i++) launchLL();
+        CK(cudaEventRecord(e1, s)); CK(cudaEventSynchronize(e1));
+        float msl; CK(cudaEventElapsedTime(&msl, e0, e1));
+        CK(cudaMemcpy(hs, dst, n * 8, cudaMemcpyDeviceToHost));
+        const bool okl = hs[0] == prev * 1000000.0 && hs[n - 1] == prev * 1000000.0 + n - 1;
+        cudaGraph_t g2; cudaGraphExec_t ex2;
+        CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        for (int i = 0; i < 50; i++) launchLL();
+        CK(cudaStreamEndCapture(s, &g2)); CK(cudaGraphInstantiate(&ex2, g2, 0));
+        __sync_fetch_and_add(&sh->arrived[0], 1); while (sh->arrived[0] < 2 * R) usleep(100);
+        CK(cudaGraphLaunch(ex2, s)); CK(cudaStreamSynchronize(s));
+        CK(cudaEventRecord(e0, s));
+        for (int i = 0; i < 20; i++) CK(cudaGraphLaunch(ex2, s));
+        CK(cudaEventRecord(e1, s)); CK(cudaEventSynchronize(e1));
+        float msgl; CK(cudaEventElapsedTime(&msgl, e0, e1));
+        printf("rank %d: LL protocol (%d blocks): stream launches %.2f us, in a graph %.2f us per exchange, data %s\n", rank, blocksLL,
+               1e3 * msl / reps, 1e3 * msgl / 1000, okl ? "ok" : "WRONG");
+    }
     if (rank == 0) { int st; while (wait(&st) > 0) {} }
     return 0;
 }

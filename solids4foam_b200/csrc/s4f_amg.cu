@@ -170,32 +170,34 @@ bool dense_inverse(const HostLevel& L, int q, std::vector<double>& inv) {
 // ================================================================================================
 struct Cheb { double c1, c2; };
 
-// x = d = (1/theta) rD b      (first smoothing step from a zero initial guess)
+// x = (1/theta) b/diag      (first smoothing step from a zero initial guess)
 template <class T, class TB>
-__global__ void __launch_bounds__(S4F_BLOCK) k_amg_first(const T* __restrict__ rD, const TB* __restrict__ b, T* __restrict__ x,
-                                                         T* __restrict__ d, int n, int ld, int ldb, T invTheta, const int* __restrict__ act) {
+__global__ void __launch_bounds__(S4F_BLOCK) k_amg_first(const T* __restrict__ dg, const TB* __restrict__ b, T* __restrict__ x,
+                                                         int n, int ld, int ldb, T invTheta, const int* __restrict__ act) {
     const int a[3] = {act[0], act[1], act[2]};      // components whose PCG solve is still running (device-side flags)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 #pragma unroll
         for (int q = 0; q < 3; q++) {
             if (!a[q]) continue;
-            const T v = invTheta * rD[(size_t)q * ld + i] * (T)b[(size_t)q * ldb + i];
-            x[(size_t)q * ld + i] = v; d[(size_t)q * ld + i] = v;
+            x[(size_t)q * ld + i] = invTheta * (T)b[(size_t)q * ldb + i] / dg[(size_t)q * ld + i];
         }
     }
 }
 
-// one Chebyshev-Jacobi step:  r = b - A x;  d' = c1 d + c2 rD r;  x' = x + d'   (out of place in x)
-// MODE 0: as written; MODE 1: residual only (xo = r, nothing else written).
+// one Chebyshev-Jacobi step in its three-term form:  r = b - A x;  x' = x + c1 (x - xprev) + c2 r/diag   (out of place)
+// Per component the step reads b, x, xprev, diag and writes x' (40 B per row in fp64; the direction-vector form of round 1
+// read and wrote a fourth vector and a stored 1/diag: 56 B).  PREV 0: no previous iterate (c1 = 0, first post-smoothing
+// step); 1: xprev given; 2: the previous iterate is the zero initial guess (second pre-smoothing step).
+// MODE 0: as written; MODE 1: residual only (xo = r).
 // Row per thread, entries in groups of eight with all index/coefficient loads issued before the gathers
 // (the mapping of the PCG SpMV k_amul3, see there).
 #define S4F_AMG_BLOCK 256
 template <class T, class TB, class TO, int MODE>
 __global__ void __launch_bounds__(S4F_AMG_BLOCK, 4) k_amg_step(const int* __restrict__ slicePtr, const int* __restrict__ col,
-                                                               const T* __restrict__ a, const T* __restrict__ dg, const T* __restrict__ rD,
-                                                               const TB* __restrict__ b, const T* __restrict__ x, T* __restrict__ d,
+                                                               const T* __restrict__ a, const T* __restrict__ dg,
+                                                               const TB* __restrict__ b, const T* __restrict__ x, const T* __restrict__ xprev,
                                                                TO* __restrict__ xo, int n, int ld, int ldb, int ldo, int nSlices, T c1, T c2,
-                                                               const int* __restrict__ act) {
+                                                               int prevMode, const int* __restrict__ act) {
     // a converged component of the fused PCG skips its vector traffic; the matrix stream is shared by the others
     const bool a0 = act[0] != 0, a1 = act[1] != 0, a2 = act[2] != 0;
     const int lane = threadIdx.x & 31;
@@ -228,13 +230,14 @@ __global__ void __launch_bounds__(S4F_AMG_BLOCK, 4) k_amg_step(const int* __rest
             for (int q = 0; q < 3; q++) {
                 if (!aq[q]) continue;
                 const int j = q * ld + row;
-                const T xv = x[j];
-                const T r = (T)b[(size_t)q * ldb + row] - (dg[j] * xv - acc[q]);
+                const T xv = x[j], d = dg[j];
+                const T r = (T)b[(size_t)q * ldb + row] - (d * xv - acc[q]);
                 if (MODE == 1) { xo[(size_t)q * ldo + row] = (TO)r; }
                 else {
-                    const T dn = (c1 != (T)0 ? c1 * d[j] : (T)0) + c2 * rD[j] * r;
-                    d[j] = dn;
-                    xo[(size_t)q * ldo + row] = (TO)(xv + dn);
+                    T xn = xv + c2 * r / d;
+                    if (prevMode == 1) xn += c1 * (xv - xprev[j]);
+                    else if (prevMode == 2) xn += c1 * xv;
+                    xo[(size_t)q * ldo + row] = (TO)xn;
                 }
             }
         }
@@ -290,14 +293,11 @@ __global__ void k_amg_convert(const double* __restrict__ in, T* __restrict__ out
     if (i < n) out[i] = (T)in[i];
 }
 template <class T>
-__global__ void k_amg_diag(const double* __restrict__ diagC, T* __restrict__ dg, T* __restrict__ rD, int n, int ldIn, int ld) {
+__global__ void k_amg_diag(const double* __restrict__ diagC, T* __restrict__ dg, int n, int ldIn, int ld) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
 #pragma unroll
-    for (int q = 0; q < 3; q++) {
-        const double v = diagC[(size_t)q * ldIn + i];
-        dg[(size_t)q * ld + i] = (T)v; rD[(size_t)q * ld + i] = (T)(1.0 / v);
-    }
+    for (int q = 0; q < 3; q++) dg[(size_t)q * ld + i] = (T)diagC[(size_t)q * ldIn + i];
 }
 __global__ void k_gather_upper(const int* __restrict__ faceEntry, const double* __restrict__ eA, double* __restrict__ upper, int F) {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -421,10 +421,10 @@ struct Level {
     int n = 0, nGhost = 0, ld = 0, nSlices = 0;
     const int* slicePtr = nullptr; const int* col = nullptr; const T* a = nullptr;   // level 0 aliases the fine rows
     DevBuf<int> slicePtrB, colB; DevBuf<T> aB;
-    DevBuf<T> dg, rD;                   // 3*ld
+    DevBuf<T> dg;                       // 3*ld: per-component diagonal
     DevBuf<int> parent;                 // [n] -> index in the next level's vectors
     DevBuf<int> childPtr, child;        // children lists of THIS level's cells in the finer level
-    DevBuf<T> b, x, x2, d, t;           // 3*ld work vectors
+    DevBuf<T> b, x, x2, x3, t;          // 3*ld work vectors (x, x2, x3: the three rotating iterates of the smoother)
     bool dist = false;                  // one part per rank; ghost columns [n, n+nGhost) filled by `halo`
     S4fHaloPlan* halo = nullptr; bool ownHalo = false;
     // transition to the replicated part of the hierarchy: this (distributed) level restricts into `gsend`, which is
@@ -530,9 +530,9 @@ struct Hierarchy : S4fAmg {
         L.nnz = (double)rowPtr[n];
         S4F_CHECK_CUDA(c, L.slicePtrB.upload(sp)); S4F_CHECK_CUDA(c, L.colB.upload(hc)); S4F_CHECK_CUDA(c, L.aB.upload(ha));
         L.slicePtr = L.slicePtrB.p; L.col = L.colB.p; L.a = L.aB.p;
-        std::vector<T> hd(3 * (size_t)L.ld, (T)1), hr(3 * (size_t)L.ld, (T)1);
-        for (int q = 0; q < 3; q++) for (int i = 0; i < n; i++) { hd[(size_t)q * L.ld + i] = (T)H.diag[q][i]; hr[(size_t)q * L.ld + i] = (T)(1.0 / H.diag[q][i]); }
-        S4F_CHECK_CUDA(c, L.dg.upload(hd)); S4F_CHECK_CUDA(c, L.rD.upload(hr));
+        std::vector<T> hd(3 * (size_t)L.ld, (T)1);
+        for (int q = 0; q < 3; q++) for (int i = 0; i < n; i++) hd[(size_t)q * L.ld + i] = (T)H.diag[q][i];
+        S4F_CHECK_CUDA(c, L.dg.upload(hd));
         if (H.dist) {
             // receive counts = distinct remote cells per neighbour; the plan moves nbrCount values out and expects the same
             // number in: the two sides' lists are mirror images (my send list to r = r's ghost list of me)
@@ -546,7 +546,7 @@ struct Hierarchy : S4fAmg {
     int alloc_work(s4fgpu_ctx* c, Level<T>& L) {
         const size_t m = 3 * (size_t)L.ld;
         S4F_CHECK_CUDA(c, L.b.alloc(m)); S4F_CHECK_CUDA(c, L.x.alloc(m)); S4F_CHECK_CUDA(c, L.x2.alloc(m));
-        S4F_CHECK_CUDA(c, L.d.alloc(m)); S4F_CHECK_CUDA(c, L.t.alloc(m));
+        S4F_CHECK_CUDA(c, L.x3.alloc(m)); S4F_CHECK_CUDA(c, L.t.alloc(m));
         return 0;
     }
     // parent[i] = index of the coarse cell of fine cell i in the next level's vectors; the children lists cover the coarse
@@ -572,13 +572,14 @@ struct Hierarchy : S4fAmg {
             const double n = L.n, nz = L.nnz, sB = (l == 0) ? 8.0 : sT, sO = (l == 0) ? 8.0 : sT, nc = lv[l + 1]->n;
             const double mat = nz * (4 + sT) + n * 0.125;
             double t = 0;
-            t += 3 * n * (sT + sB + 2 * sT);                                         // first
-            t += (deg - 1) * (mat + 3 * n * (sB + 5 * sT + sT));                      // pre steps
-            t += mat + 3 * n * (sB + 3 * sT);                                        // residual
+            t += 3 * n * (sT + sB + sT);                                             // first: diag, b in, x out
+            t += mat + 3 * n * (sB + 2 * sT + sT);                                   // second pre step (previous iterate = 0)
+            t += (deg > 2 ? deg - 2 : 0) * (mat + 3 * n * (sB + 3 * sT + sT));                      // further pre steps
+            t += mat + 3 * n * (sB + 2 * sT + sT);                                   // residual
             t += 3 * n * sT + 3 * nc * sT + 4 * n;                                   // restrict
             t += 4 * n + 6 * n * sT + 3 * nc * sT;                                   // prolong
-            t += mat + 3 * n * (sB + 4 * sT + sT);                                   // post step 0 (no d read)
-            t += (deg - 1) * (mat + 3 * n * (sB + 5 * sT)) + (deg > 1 ? 3 * n * sO : 0);   // post steps
+            t += mat + 3 * n * (sB + 2 * sT + sT);                                   // post step 0 (no previous iterate)
+            t += (deg - 1) * (mat + 3 * n * (sB + 3 * sT + sT)) + (deg > 1 && l == 0 ? 3 * n * (sO - sT) : 0);   // post steps
             tot += t;
             if (l >= 1) below1 += t;
         }
@@ -590,39 +591,51 @@ struct Hierarchy : S4fAmg {
     }
 
     // ---- smoothing on one level ---------------------------------------------------------------
+    // The iterates rotate through the level's three vectors x, x2, x3.  `Rot` tracks where the current and the previous
+    // iterate live; the starting slot is chosen so that the result of the whole cycle on the level ends in L.x.
+    struct Rot { T* buf[3]; int cur; int prev; };     // prev: -1 none, -2 the zero initial guess, else a slot
+    Rot rot_start(Level<T>& L) const {
+        Rot r; r.buf[0] = L.x.p; r.buf[1] = L.x2.p; r.buf[2] = L.x3.p;
+        // pre-smoothing writes deg slots, post-smoothing deg more (W-cycle: the extra prolongation is in place)
+        int s = (1 - 2 * deg) % 3; if (s < 0) s += 3;
+        r.cur = s; r.prev = -1;
+        return r;
+    }
     template <class TB, class TO>
-    int step(s4fgpu_ctx* c, Level<T>& L, const TB* b, int ldb, const T* xin, TO* xout, int ldo, double c1, double c2) {
+    int step(s4fgpu_ctx* c, Level<T>& L, const TB* b, int ldb, const T* xin, const T* xprev, int prevMode, TO* xout, int ldo, double c1, double c2) {
         const int grid = step_grid(c, L);
         int rc = halo(c, L, const_cast<T*>(xin)); if (rc) return rc;
-        k_amg_step<T, TB, TO, 0><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, L.rD.p, b, xin, L.d.p, xout, L.n, L.ld, ldb, ldo,
-                                                                     L.nSlices, (T)c1, (T)c2, act);
+        k_amg_step<T, TB, TO, 0><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, b, xin, xprev, xout, L.n, L.ld, ldb, ldo,
+                                                                     L.nSlices, (T)c1, (T)c2, prevMode, act);
         c->launches++;
         return 0;
     }
-    // Chebyshev-Jacobi of degree `deg`; fromZero: x0 = 0.  Result ends in *xres (L.x or L.x2), or, when
-    // `out` is given (level 0), the last step writes the fp64 output directly.
+    // Chebyshev-Jacobi of degree `deg`; fromZero: x0 = 0.  The result is R.buf[R.cur], or, when `out` is given (level 0),
+    // the last step writes the fp64 output directly.
     template <class TB>
-    int smooth(s4fgpu_ctx* c, Level<T>& L, const TB* b, int ldb, bool fromZero, T* xcur, double* out, int ldo, T** xres) {
+    int smooth(s4fgpu_ctx* c, Level<T>& L, const TB* b, int ldb, bool fromZero, Rot& R, double* out, int ldo) {
         const double sigma = theta / delta;
         double rho = 1.0 / sigma;
-        T* other = (xcur == L.x.p) ? L.x2.p : L.x.p;
         int k0 = 0, rc;
         if (fromZero) {
             const int grid = s4f_grid(c->numSMs, L.n);
-            k_amg_first<T, TB><<<grid, S4F_BLOCK, 0, c->stream>>>(L.rD.p, b, xcur, L.d.p, L.n, L.ld, ldb, (T)(1.0 / theta), act);
+            k_amg_first<T, TB><<<grid, S4F_BLOCK, 0, c->stream>>>(L.dg.p, b, R.buf[R.cur], L.n, L.ld, ldb, (T)(1.0 / theta), act);
             c->launches++;
+            R.prev = -2;
             k0 = 1;
-        }
+        } else R.prev = -1;
         for (int k = k0; k < deg; k++) {
             double c1, c2;
             if (k == 0) { c1 = 0.0; c2 = 1.0 / theta; }
             else { const double rhon = 1.0 / (2.0 * sigma - rho); c1 = rhon * rho; c2 = 2.0 * rhon / delta; rho = rhon; }
             const bool last = (k == deg - 1);
-            if (last && out) { if ((rc = step<TB, double>(c, L, b, ldb, xcur, out, ldo, c1, c2))) return rc; *xres = nullptr; return 0; }
-            if ((rc = step<TB, T>(c, L, b, ldb, xcur, other, L.ld, c1, c2))) return rc;
-            std::swap(xcur, other);
+            const T* xprev = R.prev >= 0 ? R.buf[R.prev] : nullptr;
+            const int prevMode = (k == 0) ? 0 : (R.prev >= 0 ? 1 : (R.prev == -2 ? 2 : 0));
+            if (last && out) return step<TB, double>(c, L, b, ldb, R.buf[R.cur], xprev, prevMode, out, ldo, c1, c2);
+            const int nxt = (R.cur + 1) % 3;          // never the previous iterate's slot (that is cur - 1)
+            if ((rc = step<TB, T>(c, L, b, ldb, R.buf[R.cur], xprev, prevMode, R.buf[nxt], L.ld, c1, c2))) return rc;
+            R.prev = R.cur; R.cur = nxt;
         }
-        *xres = xcur;
         return 0;
     }
 
@@ -633,8 +646,8 @@ struct Hierarchy : S4fAmg {
         Level<T>& C = *lv[l + 1];
         const int grid = step_grid(c, L);
         int rc = halo(c, L, x); if (rc) return rc;
-        k_amg_step<T, TB, T, 1><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, L.rD.p, b, x, L.d.p, L.t.p, L.n, L.ld, ldb, L.ld,
-                                                                       L.nSlices, (T)0, (T)0, act);
+        k_amg_step<T, TB, T, 1><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, b, x, nullptr, L.t.p, L.n, L.ld, ldb, L.ld,
+                                                                       L.nSlices, (T)0, (T)0, 0, act);
         c->launches++;
         if (!L.gather) {
             k_amg_restrict<T><<<(C.n + 127) / 128, 128, 0, c->stream>>>(C.childPtr.p, C.child.p, L.t.p, C.b.p, C.n, L.ld, C.ld, act);
@@ -665,8 +678,9 @@ struct Hierarchy : S4fAmg {
         }
         Level<T>& C = *lv[l + 1];
         int rc;
-        T* x = nullptr;
-        if ((rc = smooth<TB>(c, L, b, ldb, true, L.x.p, nullptr, 0, &x))) return rc;       // pre-smoothing from zero
+        Rot R = rot_start(L);
+        if ((rc = smooth<TB>(c, L, b, ldb, true, R, nullptr, 0))) return rc;               // pre-smoothing from zero
+        T* x = R.buf[R.cur];
         if ((rc = residual_restrict<TB>(c, l, b, ldb, x))) return rc;
         const bool kcycle = (cycle == 2 && l == 0 && lv.size() > 2);
         if (kcycle) { rc = kcycle_level1(c); if (rc) return rc; }
@@ -683,9 +697,8 @@ struct Hierarchy : S4fAmg {
             k_amg_prolong<T><<<gridp, S4F_BLOCK, 0, c->stream>>>(L.parent.p, C.x.p, x, L.n, L.ld, C.ld, (T)omega, act);
             c->launches++;
         }
-        T* xr = nullptr;
-        if ((rc = smooth<TB>(c, L, b, ldb, false, x, out, ldo, &xr))) return rc;           // post-smoothing
-        if (!out && xr != L.x.p) copy(c, L, xr, L.x.p);   // callers read the level result from L.x
+        if ((rc = smooth<TB>(c, L, b, ldb, false, R, out, ldo))) return rc;                // post-smoothing
+        if (!out && R.buf[R.cur] != L.x.p) copy(c, L, R.buf[R.cur], L.x.p);   // callers read the level result from L.x (deg 1 only)
         return 0;
     }
 
@@ -716,8 +729,8 @@ struct Hierarchy : S4fAmg {
         Level<T>& L = *lv[0];
         if (lv.size() < 2) return 0;
         const int grid = step_grid(c, L);
-        k_amg_step<T, double, T, 0><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, L.rD.p, r3, L.x.p, L.d.p, L.x2.p, L.n, L.ld,
-                                                                            c->ld, L.ld, L.nSlices, (T)0.3, (T)0.5, act);
+        k_amg_step<T, double, T, 0><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, r3, L.x.p, L.x3.p, L.x2.p, L.n, L.ld,
+                                                                            c->ld, L.ld, L.nSlices, (T)0.3, (T)0.5, 1, act);
         c->launches++;
         return 0;
     }
@@ -756,8 +769,8 @@ int build(s4fgpu_ctx* c, std::vector<HostLevel>& H) {
                 k_amg_convert<T><<<(unsigned)((c->nEntries + 255) / 256), 256, 0, c->stream>>>(c->eA.p, L.aB.p, c->nEntries);
                 L.a = L.aB.p;
             }
-            S4F_CHECK_CUDA(c, L.dg.alloc(3 * (size_t)L.ld)); S4F_CHECK_CUDA(c, L.rD.alloc(3 * (size_t)L.ld));
-            k_amg_diag<T><<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->diagC.p, L.dg.p, L.rD.p, c->N, c->ld, L.ld);
+            S4F_CHECK_CUDA(c, L.dg.alloc(3 * (size_t)L.ld));
+            k_amg_diag<T><<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->diagC.p, L.dg.p, c->N, c->ld, L.ld);
             c->launches += 2;
         } else {
             if ((rc = A->build_level_rows(c, L, H[l]))) return rc;
@@ -796,7 +809,7 @@ int build(s4fgpu_ctx* c, std::vector<HostLevel>& H) {
     S4F_CHECK_CUDA(c, A->denseInv.upload(inv));
     S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
     A->bytesPerApply = A->bytes_per_apply();
-    A->step0Bytes = A->lv[0]->nnz * (4 + sizeof(T)) + 0.125 * c->N + 3.0 * c->N * (8 + 5 * sizeof(T) + sizeof(T));   // col,a | b(fp64) x d dg rD in, d x' out
+    A->step0Bytes = A->lv[0]->nnz * (4 + sizeof(T)) + 0.125 * c->N + 3.0 * c->N * (8 + 3 * sizeof(T) + sizeof(T));   // col,a | b(fp64) x xprev diag in, x' out
     c->amg = guard.release();
     return 0;
 }

@@ -6,9 +6,11 @@
 // Amul / smoothing sweep), and Pstream::gSum / gMax ([OF-ext]).  Round 1 did both with NCCL (pack kernel,
 // one ncclSend/ncclRecv per neighbour and component, unpack kernel: ~90 us per exchange; ncclAllReduce plus a one-thread
 // kernel per reduction).  Here:
-//   * a halo exchange is ONE kernel: every block writes its share of the boundary-cell values straight into the
-//     neighbour's mailbox (peer stores over NVLink), the last block to finish releases a flag word at system scope, then
-//     the blocks wait for the neighbour's flag and copy the received values into the ghost slots [n, n+G) of the field;
+//   * a halo exchange is ONE kernel: every thread writes its share of the boundary-cell values straight into the
+//     neighbour's mailbox (peer stores over NVLink) as LL words {payload32, sequence number} -- an 8-byte store is atomic, so
+//     no fence and no flag message are needed --, then polls its share of the incoming words and copies the values into
+//     the ghost slots [n, n+G) of the field: 5 us per exchange inside a CUDA graph against 14 us for data + fence + flag
+//     (profiles/r2_p2p_exchange_latency.log) and ~90 us for round 1's pack / NCCL group / unpack;
 //   * a reduction needs no kernel of its own: the last block of the reducing kernel exchanges the partial sums with
 //     all ranks (s4f_dev.cuh, grid_reduce) and finishes the scalar step;
 //   * the gather that feeds the replicated coarse GAMG levels is the same push + flag scheme to all ranks.
@@ -104,8 +106,8 @@ int s4f_comm_setup(s4fgpu_ctx* c) {
     if (c->nRanks <= 1) return 0;
     if (c->nRanks > S4F_MAX_RANKS) { c->err = "more ranks than S4F_MAX_RANKS"; return 1; }
     const int R = c->nRanks;
-    const size_t boxBytes = 2 * (size_t)R * S4F_RED_MAX * sizeof(double), flagBytes = 2 * (size_t)R * sizeof(unsigned int);
-    S4F_CHECK_CUDA(c, c->redArena.alloc(boxBytes + flagBytes));          // zero-filled
+    const size_t boxBytes = 2 * (size_t)R * 2 * S4F_RED_MAX * sizeof(unsigned long long);
+    S4F_CHECK_CUDA(c, c->redArena.alloc(boxBytes));          // zero-filled: sequence number 0 = nothing received
     S4F_CHECK_CUDA(c, cudaDeviceSynchronize());
     std::vector<IpcRecord> all;
     int rc = ipc_publish(c, c->redArena.p, nullptr, 0, all); if (rc) return rc;
@@ -114,8 +116,7 @@ int s4f_comm_setup(s4fgpu_ctx* c) {
     for (int r = 0; r < R; r++) {
         void* base = c->redArena.p;
         if (r != c->rank) { rc = ipc_open(c, all[r], &base, c->ipcOpened); if (rc) return rc; }
-        h.box[r] = (double*)base;
-        h.flag[r] = (unsigned int*)((char*)base + boxBytes);
+        h.box[r] = (unsigned long long*)base;
     }
     S4F_CHECK_CUDA(c, c->redDev.alloc(1));
     S4F_CHECK_CUDA(c, cudaMemcpy(c->redDev.p, &h, sizeof(h), cudaMemcpyHostToDevice));
@@ -142,44 +143,36 @@ struct S4fHaloPlan {
 
 namespace {
 
-// the whole exchange in one kernel; the grid is small (<= 64 blocks), so every block is resident while it waits
+// the whole exchange in one kernel: push my boundary-cell values as LL words, poll the neighbours' words into the ghost slots
 template <class T>
 __global__ void __launch_bounds__(256) k_halo_xchg(HaloDev h, T* __restrict__ f, int ld, int ncomp, int ghostBase) {
+    constexpr int W = sizeof(T) / 4;                 // LL words per value
     const unsigned int k = h.seq[0] + 1u, par = k & 1u;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (int n = 0; n < h.nNbr; n++) {
         const int cnt = h.scount[n];
-        T* box = reinterpret_cast<T*>(h.peerBox[n] + (size_t)par * h.maxComp * cnt * 8);
+        unsigned long long* box = h.peerBox[n] + (size_t)par * 2 * h.maxComp * cnt;
         const int* sc = h.sendCells + h.soff[n];
         for (int i = tid; i < cnt * ncomp; i += nth) {
             const int q = i / cnt, g = i - q * cnt;
-            box[i] = f[(size_t)q * ld + sc[g]];
+            ll_put(box, (size_t)i, f[(size_t)q * ld + sc[g]], k);
         }
+        (void)W;
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int t = atomicAdd(h.seq + 1, 1u);
-        if (t == gridDim.x - 1) {
-            __threadfence_system();
-            for (int n = 0; n < h.nNbr; n++) st_release_sys(h.peerFlag[n] + par, k);
-        }
-    }
-    if ((int)threadIdx.x < h.nNbr) { while (ld_acquire_sys(h.myFlag[threadIdx.x] + par) != k) {} }
-    __syncthreads();
     for (int n = 0; n < h.nNbr; n++) {
         const int cnt = h.rcount[n];
-        const T* box = reinterpret_cast<const T*>(h.myBox[n] + (size_t)par * h.maxComp * cnt * 8);
+        const unsigned long long* box = h.myBox[n] + (size_t)par * 2 * h.maxComp * cnt;
         T* dst = f + ghostBase + h.roff[n];
         for (int i = tid; i < cnt * ncomp; i += nth) {
             const int q = i / cnt, g = i - q * cnt;
-            dst[(size_t)q * ld + g] = __ldcv(box + i);
+            T v; ll_get(box, (size_t)i, k, v);
+            dst[(size_t)q * ld + g] = v;
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int t = atomicAdd(h.seq + 2, 1u);
-        if (t == gridDim.x - 1) { h.seq[1] = 0u; h.seq[2] = 0u; __threadfence(); h.seq[0] = k; }
+    if (threadIdx.x == 0) {       // every block has read seq[0] by now: the last one out publishes the new sequence number
+        const unsigned int t = atomicAdd(h.seq + 1, 1u);
+        if (t == gridDim.x - 1) { h.seq[1] = 0u; __threadfence(); h.seq[0] = k; }
     }
 }
 
@@ -199,7 +192,7 @@ int s4f_halo_plan_create_asym(s4fgpu_ctx* c, const std::vector<int>& nbrRank, co
     std::unique_ptr<S4fHaloPlan> guard(P);
     HaloDev& d = P->d;
     d.nNbr = nn; d.maxComp = maxComp;
-    // my arena: per neighbour [2][maxComp*count] of 8 bytes, then the flags [nn][2]
+    // my arena: per neighbour [2 parities][2 * maxComp * count] LL words (a double is two words)
     unsigned long long extra[2 + 2 * S4F_MAX_NBRS]; std::memset(extra, 0, sizeof(extra));
     size_t off = 0; int tot = 0, rtot = 0;
     for (int n = 0; n < nn; n++) {
@@ -207,13 +200,12 @@ int s4f_halo_plan_create_asym(s4fgpu_ctx* c, const std::vector<int>& nbrRank, co
         d.rcount[n] = recvCount[n]; d.roff[n] = rtot; rtot += recvCount[n];
         extra[2 + 2 * n] = (unsigned long long)nbrRank[n];
         extra[2 + 2 * n + 1] = off;
-        off += 2 * (size_t)maxComp * recvCount[n] * 8;
+        off += 2 * (size_t)2 * maxComp * recvCount[n] * sizeof(unsigned long long);
         off = (off + 255) / 256 * 256;
     }
-    const size_t flagOff = off;
-    extra[0] = (unsigned long long)nn; extra[1] = flagOff;
+    extra[0] = (unsigned long long)nn; extra[1] = 0;
     P->total = std::max(tot, rtot);
-    S4F_CHECK_CUDA(c, P->arena.alloc(flagOff + 2 * sizeof(unsigned int) * std::max(nn, 1) + 256));
+    S4F_CHECK_CUDA(c, P->arena.alloc(off + 256));
     S4F_CHECK_CUDA(c, P->seq.alloc(4));
     S4F_CHECK_CUDA(c, P->sendCells.upload(sendCells.empty() ? std::vector<int>(1, 0) : sendCells));
     S4F_CHECK_CUDA(c, cudaDeviceSynchronize());
@@ -232,10 +224,8 @@ int s4f_halo_plan_create_asym(s4fgpu_ctx* c, const std::vector<int>& nbrRank, co
         for (int j = 0; j < (int)rec.extra[0]; j++)
             if ((int)rec.extra[2 + 2 * j] == c->rank) { if (seen == kth) { found = j; break; } seen++; }
         if (found < 0) { c->err = "halo plan: the neighbour rank does not list this rank"; return 1; }
-        d.peerBox[n] = (char*)base[r] + rec.extra[2 + 2 * found + 1];
-        d.peerFlag[n] = (unsigned int*)((char*)base[r] + rec.extra[1]) + 2 * found;
-        d.myBox[n] = P->arena.p + extra[2 + 2 * n + 1];
-        d.myFlag[n] = (unsigned int*)(P->arena.p + flagOff) + 2 * n;
+        d.peerBox[n] = (unsigned long long*)((char*)base[r] + rec.extra[2 + 2 * found + 1]);
+        d.myBox[n] = (unsigned long long*)(P->arena.p + extra[2 + 2 * n + 1]);
     }
     d.sendCells = P->sendCells.p;
     d.seq = P->seq.p;
@@ -256,7 +246,7 @@ int s4f_halo_run(s4fgpu_ctx* c, S4fHaloPlan* P, T* field, int ld, int ncomp, int
     if (!P || P->d.nNbr == 0) return 0;
     if (ncomp > P->d.maxComp) { c->err = "halo exchange wider than the plan's mailbox"; return 1; }
     long long work = (long long)P->total * ncomp;
-    int grid = (int)std::min<long long>(64, (work + 1023) / 1024);
+    int grid = (int)std::min<long long>(64, (work + 767) / 768);
     if (grid < 1) grid = 1;
     k_halo_xchg<T><<<grid, 256, 0, c->stream>>>(P->d, field, ld, ncomp, ghostBase);
     c->launches++;
@@ -269,8 +259,7 @@ template int s4f_halo_run<float>(s4fgpu_ctx*, S4fHaloPlan*, float*, int, int, in
 struct GatherDev {
     int nRanks, rank, ldG;                 // ldG: leading dimension of the gathered [3][ldG] vector
     int off[S4F_MAX_RANKS], cnt[S4F_MAX_RANKS];
-    char* box[S4F_MAX_RANKS];              // rank r's buffer [2][3*ldG] of 8 bytes
-    unsigned int* flag[S4F_MAX_RANKS];     // rank r's flags [2][nRanks]
+    unsigned long long* box[S4F_MAX_RANKS];   // rank r's buffer [2 parities][2 * 3 * ldG] LL words
     unsigned int* seq;
 };
 struct S4fGatherPlan {
@@ -289,34 +278,24 @@ __global__ void __launch_bounds__(256) k_gather_xchg(GatherDev g, const T* __res
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const int R = g.nRanks, me = g.rank, nLoc = g.cnt[me], myOff = g.off[me];
     const bool a[3] = {act[0] != 0, act[1] != 0, act[2] != 0};
-    for (int r = 0; r < R; r++) {
-        T* box = reinterpret_cast<T*>(g.box[(me + r) % R] + (size_t)par * 3 * g.ldG * 8);
+    const size_t slot = (size_t)par * 2 * 3 * g.ldG;
+    for (int r = 0; r < R; r++) {          // my piece to every rank (staggered start), as LL words
+        unsigned long long* box = g.box[(me + r) % R] + slot;
         for (int i = tid; i < 3 * nLoc; i += nth) {
             const int q = i / nLoc, j = i - q * nLoc;
-            if (a[q]) box[(size_t)q * g.ldG + myOff + j] = src[(size_t)q * lds + j];
+            if (a[q]) ll_put(box, (size_t)q * g.ldG + myOff + j, src[(size_t)q * lds + j], k);
         }
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int t = atomicAdd(g.seq + 1, 1u);
-        if (t == gridDim.x - 1) {
-            __threadfence_system();
-            for (int r = 0; r < R; r++) st_release_sys(g.flag[r] + par * R + me, k);
-        }
-    }
-    if ((int)threadIdx.x < R) { while (ld_acquire_sys(g.flag[me] + par * R + threadIdx.x) != k) {} }
-    __syncthreads();
-    const T* box = reinterpret_cast<const T*>(g.box[me] + (size_t)par * 3 * g.ldG * 8);
+    const unsigned long long* mine = g.box[me] + slot;
     const int nG = g.off[R - 1] + g.cnt[R - 1];
     for (int i = tid; i < 3 * nG; i += nth) {
         const int q = i / nG, j = i - q * nG;
-        if (a[q]) dst[(size_t)q * ldd + j] = __ldcv(box + (size_t)q * g.ldG + j);
+        if (a[q]) { T v; ll_get(mine, (size_t)q * g.ldG + j, k, v); dst[(size_t)q * ldd + j] = v; }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int t = atomicAdd(g.seq + 2, 1u);
-        if (t == gridDim.x - 1) { g.seq[1] = 0u; g.seq[2] = 0u; __threadfence(); g.seq[0] = k; }
+        const unsigned int t = atomicAdd(g.seq + 1, 1u);
+        if (t == gridDim.x - 1) { g.seq[1] = 0u; __threadfence(); g.seq[0] = k; }
     }
 }
 }  // namespace
@@ -332,8 +311,8 @@ int s4f_gather_plan_create(s4fgpu_ctx* c, const std::vector<int>& cntPerRank, S4
     for (int r = 0; r < R; r++) { d.off[r] = tot; d.cnt[r] = cntPerRank[r]; tot += cntPerRank[r]; }
     P->nGlobal = tot;
     d.ldG = ((tot + 31) / 32) * 32;
-    const size_t boxBytes = 2 * (size_t)3 * d.ldG * 8, flagBytes = 2 * (size_t)R * sizeof(unsigned int);
-    S4F_CHECK_CUDA(c, P->arena.alloc(boxBytes + flagBytes));
+    const size_t boxBytes = 2 * (size_t)2 * 3 * d.ldG * sizeof(unsigned long long);
+    S4F_CHECK_CUDA(c, P->arena.alloc(boxBytes));
     S4F_CHECK_CUDA(c, P->seq.alloc(4));
     S4F_CHECK_CUDA(c, cudaDeviceSynchronize());
     std::vector<IpcRecord> all;
@@ -341,8 +320,7 @@ int s4f_gather_plan_create(s4fgpu_ctx* c, const std::vector<int>& cntPerRank, S4
     for (int r = 0; r < R; r++) {
         void* base = P->arena.p;
         if (r != c->rank) { rc = ipc_open(c, all[r], &base, P->opened); if (rc) return rc; }
-        d.box[r] = (char*)base;
-        d.flag[r] = (unsigned int*)((char*)base + boxBytes);
+        d.box[r] = (unsigned long long*)base;
     }
     d.seq = P->seq.p;
     int one = 1; std::vector<int> ones(R);

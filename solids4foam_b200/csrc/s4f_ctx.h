@@ -76,8 +76,7 @@ struct DevBuf {
 // all-reduce mailboxes of one context (device memory; null pointer = single rank)
 struct PeerRed {
     int nRanks, rank;
-    double* box[S4F_MAX_RANKS];          // box[r]: rank r's mailbox  [2 parities][nRanks][S4F_RED_MAX]
-    unsigned int* flag[S4F_MAX_RANKS];   // flag[r]: rank r's flags   [2 parities][nRanks]
+    unsigned long long* box[S4F_MAX_RANKS];   // box[r]: rank r's mailbox of LL words  [2 parities][nRanks][2 * S4F_RED_MAX]
     unsigned int seq;                    // reductions completed so far
 };
 

@@ -52,6 +52,28 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV]) {
 // word; messages carry a sequence number kept in device memory (CUDA-graph replays need no host-side argument), and
 // slots alternate by parity: in a symmetric exchange a rank sends message k+1 only after it has seen the peer's message
 // k, which the peer sent after consuming message k-1, so the slot of k-1 is free.  (s4f_comm.cu sets the pointers up.)
+// LL words (after NCCL's low-latency protocol): a message travels as 8-byte words {payload32, sequence number}.  An 8-byte
+// store is atomic, so the receiver needs neither a fence nor a separate flag message: it polls every word until the
+// sequence number matches.  A double is two words (low / high half), a float one.
+__device__ __forceinline__ void ll_store(unsigned long long* p, unsigned int payload, unsigned int k) {
+    *reinterpret_cast<volatile unsigned long long*>(p) = ((unsigned long long)k << 32) | payload;
+}
+__device__ __forceinline__ unsigned int ll_wait(const unsigned long long* p, unsigned int k) {
+    unsigned long long w;
+    do { w = *reinterpret_cast<const volatile unsigned long long*>(p); } while ((unsigned int)(w >> 32) != k);
+    return (unsigned int)w;
+}
+__device__ __forceinline__ void ll_put(unsigned long long* box, size_t i, double v, unsigned int k) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    ll_store(box + 2 * i, (unsigned int)b, k); ll_store(box + 2 * i + 1, (unsigned int)(b >> 32), k);
+}
+__device__ __forceinline__ void ll_put(unsigned long long* box, size_t i, float v, unsigned int k) { ll_store(box + i, __float_as_uint(v), k); }
+__device__ __forceinline__ void ll_get(const unsigned long long* box, size_t i, unsigned int k, double& v) {
+    const unsigned int lo = ll_wait(box + 2 * i, k), hi = ll_wait(box + 2 * i + 1, k);
+    v = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+}
+__device__ __forceinline__ void ll_get(const unsigned long long* box, size_t i, unsigned int k, float& v) { v = __uint_as_float(ll_wait(box + i, k)); }
+
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -94,6 +116,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], const RedCtx& rc, F
         PeerRed* pr = rc.peer;
         if (pr) {
             __shared__ double shTot[NV];
+            __shared__ double shIn[S4F_MAX_RANKS][NV];
             const int R = pr->nRanks, me = pr->rank;
             const unsigned int k = pr->seq + 1u, par = k & 1u;
             if (threadIdx.x == 0) {
@@ -101,24 +124,23 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], const RedCtx& rc, F
                 for (int i = 0; i < NV; i++) shTot[i] = tot[i];
             }
             __syncthreads();
+            // my partial sums go to every rank's mailbox (slot `me`), then I collect the R contributions in mine
             for (int t = threadIdx.x; t < R * NV; t += blockDim.x) {
                 const int r = t / NV, i = t - r * NV;
-                pr->box[r][((size_t)par * R + me) * S4F_RED_MAX + i] = shTot[i];
+                ll_put(pr->box[r] + ((size_t)par * R + me) * 2 * S4F_RED_MAX, (size_t)i, shTot[i], k);
             }
-            __threadfence_system();
-            __syncthreads();
-            if ((int)threadIdx.x < R) {
-                st_release_sys(pr->flag[threadIdx.x] + par * R + me, k);
-                const unsigned int* mine = pr->flag[me] + par * R + threadIdx.x;
-                while (ld_acquire_sys(mine) != k) {}
+            for (int t = threadIdx.x; t < R * NV; t += blockDim.x) {
+                const int r = t / NV, i = t - r * NV;
+                double v;
+                ll_get(pr->box[me] + ((size_t)par * R + r) * 2 * S4F_RED_MAX, (size_t)i, k, v);
+                shIn[r][i] = v;
             }
             __syncthreads();
             if (threadIdx.x == 0) {
-                const double* mb = pr->box[me] + (size_t)par * R * S4F_RED_MAX;
 #pragma unroll
                 for (int i = 0; i < NV; i++) {
-                    double a = __ldcv(mb + i);
-                    for (int r = 1; r < R; r++) a = Op::f(a, __ldcv(mb + (size_t)r * S4F_RED_MAX + i));
+                    double a = shIn[0][i];
+                    for (int r = 1; r < R; r++) a = Op::f(a, shIn[r][i]);
                     tot[i] = a;
                 }
                 pr->seq = k;
@@ -133,12 +155,10 @@ struct HaloDev {
     int nNbr, maxComp;
     int scount[S4F_MAX_NBRS], soff[S4F_MAX_NBRS]; // values per component sent to neighbour n; prefix sums (into sendCells)
     int rcount[S4F_MAX_NBRS], roff[S4F_MAX_NBRS]; // values per component received from neighbour n; prefix sums (ghost order)
-    char* peerBox[S4F_MAX_NBRS];                  // remote: where my message to neighbour n goes, [2][maxComp * count] of 8 bytes
-    unsigned int* peerFlag[S4F_MAX_NBRS];         // remote: [2]
-    char* myBox[S4F_MAX_NBRS];                    // local: messages of neighbour n
-    unsigned int* myFlag[S4F_MAX_NBRS];
+    unsigned long long* peerBox[S4F_MAX_NBRS];    // remote: where my message to neighbour n goes, [2 parities][2 * maxComp * scount] LL words
+    unsigned long long* myBox[S4F_MAX_NBRS];      // local: messages of neighbour n, [2][2 * maxComp * rcount]
     const int* sendCells;                         // [sum count] local cells whose values go out, neighbour by neighbour
-    unsigned int* seq;                            // exchanges completed; [1] and [2] are the two block tickets
+    unsigned int* seq;                            // exchanges completed; [1] is the block ticket of the kernel's tail
 };
 
 // ---- tensor algebra: tensor 9 row-major, symmTensor 6 = XX XY XZ YY YZ ZZ ----------------------
