@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--cells", default=None, help="nx,ny,nz (default 800,100,100)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the decomposed-run-vs-oracle parity check after the timed region")
+    ap.add_argument("--workload", default="cantilever", choices=["cantilever", "notched_bar", "neo_hookean"],
+                    help="cantilever: BASELINE.json configs[1] (the headline); notched_bar: configs[3] (neoHookeanElasticMisesPlastic, "
+                         "non-orthogonal mesh, total Lagrangian); neo_hookean: configs[2] (neoHookeanElastic, total Lagrangian)")
     ap.add_argument("--precond", default="gamg", choices=["diagonal", "none", "chebyshev", "gamg", "gamg32"])
     ap.add_argument("--gamg-degree", type=int, default=3)
     ap.add_argument("--gamg-omega", type=float, default=2.2)
@@ -217,7 +220,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dims = tuple(int(x) for x in args.cells.split(",")) if args.cells else FULL
     nCellsFull = dims[0] * dims[1] * dims[2]
-    workload = f"hex cantilever {dims[0]}x{dims[1]}x{dims[2]} ({nCellsFull / 1e6:.2f}M cells), linearElastic, linearGeometryTotalDisplacement"
+    workload = {"cantilever": f"hex cantilever {dims[0]}x{dims[1]}x{dims[2]} ({nCellsFull / 1e6:.2f}M cells), linearElastic, linearGeometryTotalDisplacement",
+                "notched_bar": f"notched bar {dims[0]}x{dims[1]}x{dims[2]} ({nCellsFull / 1e6:.2f}M cells, non-orthogonal), neoHookeanElasticMisesPlastic, "
+                               "nonLinearGeometryTotalLagrangianTotalDisplacement",
+                "neo_hookean": f"hex cantilever {dims[0]}x{dims[1]}x{dims[2]} ({nCellsFull / 1e6:.2f}M cells), neoHookeanElastic, "
+                               "nonLinearGeometryTotalLagrangianTotalDisplacement"}[args.workload]
 
     # ---------------------------------------------------------------- reference arm (CPU oracle)
     if args.impl == "reference":
@@ -269,9 +276,16 @@ def main():
     comm = new_comm()
     pre = dict(diagonal=K.PRECOND_DIAGONAL, none=K.PRECOND_NONE, chebyshev=K.PRECOND_CHEBYSHEV, gamg=K.PRECOND_GAMG,
                gamg32=K.PRECOND_GAMG)[args.precond]
-    case = cases.cantilever(*dims, rank=rank, nRanks=world, preconditioner=pre,
-                            gamgSinglePrecision=1 if args.precond == "gamg32" else 0, gamgSmootherDegree=args.gamg_degree,
-                            gamgOverCorrection=args.gamg_omega, gamgCycle=args.gamg_cycle)
+    ctl = dict(preconditioner=pre, gamgSinglePrecision=1 if args.precond == "gamg32" else 0, gamgSmootherDegree=args.gamg_degree,
+               gamgOverCorrection=args.gamg_omega, gamgCycle=args.gamg_cycle)
+    if args.workload == "cantilever":
+        case = cases.cantilever(*dims, rank=rank, nRanks=world, **ctl)
+    elif args.workload == "notched_bar":
+        case = cases.notched_bar(*dims, rank=rank, nRanks=world, **ctl)
+    else:
+        if world > 1:
+            raise SystemExit("--workload neo_hookean is a single-GPU kernel benchmark")
+        case = cases.neo_hookean_cantilever(*dims, **ctl)
     mesh = case.mesh
     g = SolidModel(case, device=local_rank, comm=comm)
 
@@ -313,7 +327,7 @@ def main():
     hD[:] = g.get("D")
     loaded = [p for p in mesh.patches if p.name == "loaded"]
     trac = None
-    if loaded:
+    if loaded and args.workload == "cantilever":
         trac = torch.zeros((loaded[0].size, 3), dtype=torch.float64).pin_memory().numpy()
         trac[:, 1] = -1e6
     for name, buf in zip(("D", "gradD", "sigma"), hOut):    # first use sizes the library's staging buffer and touches the host pages
@@ -356,7 +370,7 @@ def main():
         kern[name] = dict(ms=ms_k, algo_bytes=by, gbs=by / (ms_k * 1e-3) / 1e9, frac=by / (ms_k * 1e-3) / 1e9 / peak)
     barrier()
     g.close()
-    parity = None if args.no_parity else multi_gpu_parity(rank, world, local_rank, new_comm)
+    parity = None if (args.no_parity or args.workload != "cantilever") else multi_gpu_parity(rank, world, local_rank, new_comm)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -390,7 +404,7 @@ def main():
     if parity is not None:
         line["parity"] = parity
 
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "cantilever":
         # bounded sample of the SAME workload: two outer iterations of the full-size case after one warm-up (~30 s of CPU work)
         ips, dt, inner, nS, cores = cpu_reference_run(dims, 2, 1, precond_dic=True)
         line["cpu_baseline"] = dict(value=ips, unit="iter/s", cores=cores, kind="port",

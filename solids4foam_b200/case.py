@@ -209,6 +209,37 @@ class BC:
     kind: int
     value: Optional[np.ndarray] = None      # [size,3] displacement / traction (None = zero)
     pressure: Optional[np.ndarray] = None   # [size]
+    # time series of the reference's patch fields: displacementSeries (fixedDisplacement...C:258-294), tractionSeries /
+    # pressureSeries (solidTraction...C:120-170): s4f's interpolationTable, piece-wise linear, outOfBounds clamp.
+    # [(t, (x y z))] / [(t, p)]; at(t) gives the BC of that time (the driver calls set_bc with it every time step)
+    value_series: Optional[list] = None
+    pressure_series: Optional[list] = None
+
+    def at(self, t: float) -> "BC":
+        if self.value_series is None and self.pressure_series is None:
+            return self
+        v, pr = self.value, self.pressure
+        if self.value_series is not None:
+            v = np.asarray(interpolate_series(self.value_series, t), dtype=np.float64)
+        if self.pressure_series is not None:
+            pr = np.asarray(float(interpolate_series(self.pressure_series, t)), dtype=np.float64)
+        return BC(self.kind, v, pr)
+
+
+def interpolate_series(series, t: float):
+    """numerics/interpolationTable/interpolationTable.C:493-632 with outOfBounds clamp: first / last ordinate outside the
+    abscissa range, linear in between."""
+    ts = [float(a) for a, _ in series]
+    ys = [np.asarray(b, dtype=np.float64) for _, b in series]
+    if t <= ts[0]:
+        return ys[0]
+    if t >= ts[-1]:
+        return ys[-1]
+    for i in range(len(ts) - 1):
+        if ts[i] <= t <= ts[i + 1]:
+            w = (t - ts[i]) / (ts[i + 1] - ts[i])
+            return (1.0 - w) * ys[i] + w * ys[i + 1]
+    return ys[-1]
 
 
 def fixedDisplacement(value=(0.0, 0.0, 0.0)) -> BC:

@@ -157,8 +157,8 @@ struct s4fgpu_ctx {
     DevBuf<double> eCorr;             // [3*nEntries] magSf*nonOrthCorrectionVector, outward sense (only if nonOrth)
     DevBuf<double> eA;                // laplacian coefficient impKf*magSf*delta  (= -upper)
     DevBuf<double> eGam;              // RhieChow gamma_f
-    DevBuf<double> eU, eC0, eVc;      // factored RHS coefficients (k_source_f): (1-w) Sf [3*nE], gamma magSf delta - a, gamma (1-w) corr [3*nE]
-    DevBuf<double> rowK;              // [6*ld] per-row sums U (3), Vv (3) of the factored RHS
+    DevBuf<double> eU, eC0, eVc;      // factored RHS coefficients (k_source_g / k_source_m): (1-w) Sf [3*nE], gamma magSf delta - a, gamma (1-w) corr [3*nE]
+    DevBuf<double> rowK;              // [6*ld] per-row sums U = sum w Sf (3), Vc = sum gamma w corr (3) of the factored RHS
     DevBuf<double> V, rV;             // cell volumes [ld]
     DevBuf<int> faceEntry;            // [F] entry index of internal face f in its owner's row (-> lduMatrix upper())
     DevBuf<int> procEntry;            // [G] entry index of processor-patch face g (ghost order) in its cell's row
@@ -205,8 +205,8 @@ struct s4fgpu_ctx {
     DevBuf<double> Dtot, gradDtot;                // 3*ld, 9*ld (incremental models only)
     DevBuf<double> sigma, sigmaOld;               // 6*ld
     DevBuf<double> impK;                          // ld
-    DevBuf<double> T9;                            // 9*ld: J*Finv & sigma (TL)  [cells + boundary]; on orthogonal meshes the combined
-                                                  // tensor M = T - gamma grad(D) of the factored right-hand side (k_source_m)
+    DevBuf<double> T9;                            // 9*ld: the combined tensor M = T - gamma grad(D) of the factored right-hand side, T = sigma or
+                                                  // J Finv & sigma / relJ relFinv & sigma  [cells + ghosts + boundary slots: M_b = T_b]
     bool mValid = false;                          // T9 holds M of the current sigma / grad(D)
     double impK0 = 0;                             // the (uniform) implicit stiffness
     DevBuf<double> Finv, Jt;                      // 9*ld, ld (TL solver kinematics)
@@ -266,8 +266,6 @@ struct s4fgpu_ctx {
     const int* gradCol() const { return pointCellsGrad() ? gCol.p : col.p; }
     const double* gradLs() const { return pointCellsGrad() ? gLs.p : eLs.p; }
     long long gradNE() const { return pointCellsGrad() ? gNE : nEntries; }
-    // orthogonal mesh + uniform Rhie-Chow coefficient: the right-hand side gathers ONE tensor per neighbour (k_source_m)
-    bool fastRhs() const { return !nonOrth; }
     double gamma0() const { return ctl.stabilisation == S4F_STAB_RHIE_CHOW ? ctl.stabScaleFactor * impK0 : 0.0; }
     const double* gradForLaw() const { return incremental() ? gradDtot.p : gradD.p; }   // the registered "grad(D)"
     RedCtx red() const { return RedCtx{partials.p, ticket.p, nRanks > 1 ? redDev.p : nullptr}; }
@@ -302,6 +300,7 @@ int s4f_grad_calculated_interior(s4fgpu_ctx* c, const double* X, double* gradOut
 int s4f_make_m(s4fgpu_ctx* c);                       // lin-geom: M = sigma - gamma grad(D) when no law kernel produced it
 int s4f_update_totals(s4fgpu_ctx* c, bool disp, bool grad);
 int s4f_law_correct(s4fgpu_ctx* c);
+double s4f_law_bytes(const s4fgpu_ctx* c);           // algorithmic bytes of one s4f_law_correct (roofline report)
 int s4f_solve_segregated(s4fgpu_ctx* c, double* psi, const double* source, bool defer = false);   // device SoA pointers
 int s4f_finish_solve(s4fgpu_ctx* c);
 int s4f_halo_exchange(s4fgpu_ctx* c, double* field, int ncomp);

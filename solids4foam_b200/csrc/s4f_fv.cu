@@ -7,6 +7,7 @@
 // Reference lines are cited at each kernel; the CPU restatement of the same operators in the
 // reference's own LDU face-loop form is oracle/s4f_oracle.cpp.
 #include <cmath>
+#include <cstdlib>
 
 #include "s4f_ctx.h"
 #include "s4f_dev.cuh"
@@ -49,9 +50,9 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_assemble_laplacian(
                 if (fabs(kP - kN) > S4F_SMALL) gf = 0.01 * 0.5 * (kP + kN);   // material interface
             }
             eGam[e] = gf;
-            // factored right-hand-side coefficients (see k_source_f): the neighbour value of T enters with
-            // u = (1-w) Sf, of D with c0 = gamma_f magSf delta - a, of grad(D) with -gamma (1-w) Sf (+ vc);
-            // the row's own values with the sums U, Vv, C0 over its entries.
+            // factored right-hand-side coefficients (see k_source_g): the neighbour value of M = T - gamma grad(D) enters
+            // with u = (1-w) Sf, of D with c0 = gamma_f magSf delta - a, of grad(D) with vc = gamma (1-w) corr (non-orthogonal
+            // meshes); the row's own values with the sums U = sum w Sf and Vc = sum gamma w corr over its entries.
             const double c0 = gf * dn - a;
             eC0[e] = c0;
 #pragma unroll
@@ -59,13 +60,11 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_assemble_laplacian(
                 const double Sq = eSf[(size_t)q * nE + e];
                 eU[(size_t)q * nE + e] = w1 * Sq;
                 sU[q] += w * Sq;
-                double m = -Sq;
                 if (eCorr) {
                     const double cq = eCorr[(size_t)q * nE + e];
-                    m += cq;
                     eVc[(size_t)q * nE + e] = gf * w1 * cq;
+                    sV[q] += gf * w * cq;
                 }
-                sV[q] += gf * w * m;
             }
         }
         if (row < N) {
@@ -258,98 +257,102 @@ __global__ void k_bc_evaluate(const int* __restrict__ bFaceCell, const int* __re
 // ------------------------------------------------------------------------------------------------
 // Explicit right-hand side, one gather per cell over its faces:
 //   - V fvc::laplacian(impKf,D) [compact part; the non-orthogonal parts of fvm and fvc cancel]
-//   + V fvc::div(sigma)        [OF-ext] gaussDivScheme + linear:  Sf & (w T_P + (1-w) T_N); boundary Sf_b & T_b
+//   + V fvc::div(T)            [OF-ext] gaussDivScheme + linear:  Sf & (w T_P + (1-w) T_N); boundary Sf_b & T_b
 //   + V rho g + d2dt2 old-time terms
 //   + V RhieChow = sum_f gamma_f [ magSf (delta (D_N-D_P) + corr & gradD_f) - Sf & gradD_f ]   (momentumStabilisation.C:210-217)
-// T is sigma (6 comps, TENSOR9=false) or J Finv & sigma (9 comps, total-Lagrangian, TENSOR9=true).
+// T is sigma (linear geometry) or J Finv & sigma / relJ relFinv & sigma (total / updated Lagrangian).
 //
-// Factored form.  With m = corr - Sf and the face values w X_P + (1-w) X_N the sum over the faces of a cell
-// separates into a part that only needs the NEIGHBOUR values and per-entry coefficients fixed at assembly,
-//      sum_e [ u_e & T_N(:,q) + c0_e (D_N,q - D_P,q) - gamma_e (u_e & gradD_N(:,q)) + vc_e & gradD_N(:,q) ],
-//      u = (1-w) Sf,  c0 = gamma magSf delta - a,  vc = gamma (1-w) corr  (non-orthogonal meshes only),
-// and a part in the cell's OWN values with per-row sums U = sum w Sf, Vv = sum gamma w m:
-//      U & T_P(:,q) + Vv & gradD_P(:,q).
-// Per entry that is 6 streamed doubles + 7 gathered values + 7 FMAs per component, no face interpolation in
-// the loop.  Mapping: three consecutive warps share a slice and produce one displacement component each
-// (a thread gathers only the column of T and grad(D) its component needs); entries are taken in pairs with
-// the streamed loads issued ahead of the gathers.
+// Factored form.  With linear face interpolation w X_P + (1-w) X_N and the uniform Rhie-Chow coefficient gamma of a
+// single-law case, the kernel that produces the stress also writes ONE combined tensor per cell,
+//      M = T - gamma grad(D)   (cells, ghost cells);   M_b = T_b on boundary slots (gamma_f = 0 there),
+// and the sum over the faces of a cell separates into a part that only needs NEIGHBOUR values and per-entry
+// coefficients fixed at assembly, and a part in the cell's own values with per-row sums:
+//      rhs_q(P) = sum_e [ u_e & M_N(:,q) + vc_e & gradD_N(:,q) + c0_e (D_N,q - D_P,q) ]
+//                 + U & M_P(:,q) + Vc & gradD_P(:,q) + V (rho g_q + hist_q),
+//      u = (1-w) Sf,  vc = gamma (1-w) corr,  c0 = gamma magSf delta - a,  U = sum w Sf,  Vc = sum gamma w corr.
+// k_source_g is the general kernel (non-orthogonal meshes: plateHole, the notched bar, every moved updated-Lagrangian
+// mesh): it streams col, u, vc, c0 (60 B per entry) and gathers M, grad(D), D (21 values).  Round 1's version gave every
+// displacement component its own warp (each re-streaming the coefficients and gathering T, grad(D) and gamma_f
+// separately: 0.41 of the HBM peak); here one lane owns a row for all three components, as in k_source_m.
+// On orthogonal meshes vc = Vc = 0 and the gather of grad(D) disappears: k_source_m below.
 // ------------------------------------------------------------------------------------------------
-#define S4F_SRC_BLOCK 192
-template <bool TENSOR9, bool STAB, bool NONORTH>
-__global__ void __launch_bounds__(S4F_SRC_BLOCK, 4) k_source_f(
-    const int* __restrict__ slicePtr, const int* __restrict__ col, const double* __restrict__ eU, const double* __restrict__ eC0,
-    const double* __restrict__ eGam, const double* __restrict__ eVc, const double* __restrict__ rowK, const double* __restrict__ D,
-    const double* __restrict__ T, const double* __restrict__ gradD, const double* __restrict__ V,
-    const double* __restrict__ hist /* old-time d2dt2 terms per unit volume, null for steadyState */, double* __restrict__ source, int N,
+template <int MINB>
+__global__ void __launch_bounds__(S4F_BLOCK, MINB) k_source_g(
+    const int* __restrict__ slicePtr, const int* __restrict__ col, const double* __restrict__ eU, const double* __restrict__ eVc,
+    const double* __restrict__ eC0, const double* __restrict__ rowK, const double* __restrict__ D, const double* __restrict__ M,
+    const double* __restrict__ gradD, const double* __restrict__ V, const double* __restrict__ hist, double* __restrict__ source, int N,
     int ld, long long nE, int nSlices, double rhoGx, double rhoGy, double rhoGz) {
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int q = wib % 3, sub = wib / 3;
-    constexpr int SPB = S4F_SRC_BLOCK / 96;
-    int t0, t1, t2;
-    if (TENSOR9) { t0 = q; t1 = 3 + q; t2 = 6 + q; }
-    else { t0 = q; t1 = (q == 0) ? 1 : (q == 1 ? 3 : 4); t2 = (q == 0) ? 2 : (q == 1 ? 4 : 5); }   // column q of a symmTensor
-    const double* __restrict__ Dq = D + (size_t)q * ld;
-    const double* __restrict__ T0 = T + (size_t)t0 * ld;
-    const double* __restrict__ T1 = T + (size_t)t1 * ld;
-    const double* __restrict__ T2 = T + (size_t)t2 * ld;
-    const double* __restrict__ G0 = gradD + (size_t)q * ld;
-    const double* __restrict__ G1 = gradD + (size_t)(3 + q) * ld;
-    const double* __restrict__ G2 = gradD + (size_t)(6 + q) * ld;
-    const double* __restrict__ eU0 = eU;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
     const double* __restrict__ eU1 = eU + nE;
     const double* __restrict__ eU2 = eU + 2 * nE;
-    const double rg = (q == 0) ? rhoGx : (q == 1 ? rhoGy : rhoGz);
-    constexpr int G = 2;
-    for (int s = blockIdx.x * SPB + sub; s < nSlices; s += gridDim.x * SPB) {
+    const double* __restrict__ eV1 = eVc + nE;
+    const double* __restrict__ eV2 = eVc + 2 * nE;
+    for (int s = warp; s < nSlices; s += nWarps) {
         const int base = slicePtr[s], width = (slicePtr[s + 1] - base) >> 5;
         const int row = s * 32 + lane;
-        const double DP = Dq[row < N ? row : 0];      // the laplacian keeps its difference form c0 (D_N - D_P): no cancellation
-        double acc = 0;
-        for (int k0 = 0; k0 < width; k0 += G) {
-            int cc[G]; double u0[G], u1[G], u2[G], c0[G], gm[G], v0[G], v1[G], v2[G];
+        const int r = (row < N) ? row : 0;
+        const double DP[3] = {D[r], D[(size_t)ld + r], D[2 * (size_t)ld + r]};
+        double acc[3] = {0, 0, 0};
+        // software pipeline over the entries: the streamed coefficients of entry k+1 are loaded while entry k's 21 gathers fly
+        int cc = __ldcs(col + base + lane);
+        double u0 = 0, u1 = 0, u2 = 0, v0 = 0, v1 = 0, v2 = 0, c0 = 0;
+        if (width > 0) {
+            const long long e = (long long)base + lane;
+            u0 = __ldcs(eU + e); u1 = __ldcs(eU1 + e); u2 = __ldcs(eU2 + e);
+            v0 = __ldcs(eVc + e); v1 = __ldcs(eV1 + e); v2 = __ldcs(eV2 + e); c0 = __ldcs(eC0 + e);
+        }
+        for (int k = 0; k < width; k++) {
+            const int n = cc;
+            const double a0 = u0, a1 = u1, a2 = u2, b0 = v0, b1 = v1, b2 = v2, cz = c0;
+            double m[9], g[9], d[3];
+            // faces without a correction vector (the orthogonal part of a hex-dominant mesh) need no grad(D): warp-uniform skip
+            const bool needG = __any_sync(0xffffffffu, (b0 != 0.0) | (b1 != 0.0) | (b2 != 0.0));
 #pragma unroll
-            for (int k = 0; k < G; k++) {
-                const bool ok = k0 + k < width;
-                const long long e = (long long)base + 32 * (ok ? k0 + k : k0) + lane;
-                cc[k] = col[e];
-                u0[k] = ok ? eU0[e] : 0.0; u1[k] = ok ? eU1[e] : 0.0; u2[k] = ok ? eU2[e] : 0.0;
-                c0[k] = ok ? eC0[e] : 0.0;
-                if (STAB) gm[k] = ok ? eGam[e] : 0.0;
-                if (STAB && NONORTH) { v0[k] = ok ? eVc[e] : 0.0; v1[k] = ok ? eVc[nE + e] : 0.0; v2[k] = ok ? eVc[2 * nE + e] : 0.0; }
+            for (int q = 0; q < 9; q++) m[q] = M[(size_t)q * ld + n];
+            if (needG) {
+#pragma unroll
+                for (int q = 0; q < 9; q++) g[q] = gradD[(size_t)q * ld + n];
+            } else {
+#pragma unroll
+                for (int q = 0; q < 9; q++) g[q] = 0.0;
             }
 #pragma unroll
-            for (int k = 0; k < G; k++) {
-                const int n = cc[k];
-                double t = u0[k] * T0[n] + u1[k] * T1[n] + u2[k] * T2[n] + c0[k] * (Dq[n] - DP);
-                if (STAB) {
-                    const double g0 = G0[n], g1 = G1[n], g2 = G2[n];
-                    t -= gm[k] * (u0[k] * g0 + u1[k] * g1 + u2[k] * g2);
-                    if (NONORTH) t += v0[k] * g0 + v1[k] * g1 + v2[k] * g2;
-                }
-                acc += t;
+            for (int q = 0; q < 3; q++) d[q] = D[(size_t)q * ld + n];
+            if (k + 1 < width) {
+                const long long e = (long long)base + 32 * (k + 1) + lane;
+                cc = __ldcs(col + e);
+                u0 = __ldcs(eU + e); u1 = __ldcs(eU1 + e); u2 = __ldcs(eU2 + e);
+                v0 = __ldcs(eVc + e); v1 = __ldcs(eV1 + e); v2 = __ldcs(eV2 + e); c0 = __ldcs(eC0 + e);
             }
+#pragma unroll
+            for (int q = 0; q < 3; q++)
+                acc[q] += a0 * m[q] + a1 * m[3 + q] + a2 * m[6 + q] + b0 * g[q] + b1 * g[3 + q] + b2 * g[6 + q] + cz * (d[q] - DP[q]);
         }
         if (row < N) {
-            double sv = acc + rowK[row] * T0[row] + rowK[(size_t)ld + row] * T1[row] + rowK[2 * (size_t)ld + row] * T2[row];
-            if (STAB) sv += rowK[3 * (size_t)ld + row] * G0[row] + rowK[4 * (size_t)ld + row] * G1[row] + rowK[5 * (size_t)ld + row] * G2[row];
-            const double v = V[row];
-            sv += v * rg;
-            if (hist) sv += v * hist[(size_t)q * ld + row];
-            source[(size_t)q * ld + row] = sv;
+            const double U0 = rowK[row], U1 = rowK[(size_t)ld + row], U2 = rowK[2 * (size_t)ld + row], v = V[row];
+            const double W0 = rowK[3 * (size_t)ld + row], W1 = rowK[4 * (size_t)ld + row], W2 = rowK[5 * (size_t)ld + row];
+            const double rg[3] = {rhoGx, rhoGy, rhoGz};
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                double sv = acc[q] + U0 * M[(size_t)q * ld + row] + U1 * M[(size_t)(3 + q) * ld + row] + U2 * M[(size_t)(6 + q) * ld + row]
+                          + W0 * gradD[(size_t)q * ld + row] + W1 * gradD[(size_t)(3 + q) * ld + row] + W2 * gradD[(size_t)(6 + q) * ld + row];
+                sv += v * rg[q];
+                if (hist) sv += v * hist[(size_t)q * ld + row];
+                source[(size_t)q * ld + row] = sv;
+            }
         }
     }
 }
 
 
 // ------------------------------------------------------------------------------------------------
-// Right-hand side on ORTHOGONAL meshes (no correction vectors) with the uniform Rhie-Chow coefficient gamma of a
-// single-law case: the neighbour part of the factored form above collapses to ONE gathered tensor per neighbour,
-//      M = T - gamma grad(D)   (cells, ghost cells);   M_b = T_b on boundary slots (gamma_f = 0 there),
-//      rhs_q(P) = sum_e [ u_e & M_N(:,q) + c0_e (D_N,q - D_P,q) ] + U & M_P(:,q) + V (rho g_q + hist_q),
-// because Vv = sum gamma w (corr - Sf) = -gamma U when corr = 0.  M is written by the kernel that produces the stress
-// (law kernels / the flux-tensor kernel), so the right-hand side streams 5 values per entry (col, u, c0) and gathers
-// 12 (M, D) instead of 6 + 18 (eGam; D, T, grad(D)).  One row per lane, a slice per warp, entries in pairs with the
-// streamed loads issued ahead of the gathers.
+// Right-hand side on ORTHOGONAL meshes (no correction vectors): the factored form above without the grad(D) terms,
+//      rhs_q(P) = sum_e [ u_e & M_N(:,q) + c0_e (D_N,q - D_P,q) ] + U & M_P(:,q) + V (rho g_q + hist_q).
+// M is written by the kernel that produces the stress (law kernels / the flux-tensor kernel), so the right-hand side
+// streams 5 values per entry (col, u, c0) and gathers 12 (M, D).  One row per lane, a slice per warp, entries in pairs
+// with the streamed loads issued ahead of the gathers.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(S4F_BLOCK, 3) k_source_m(
     const int* __restrict__ slicePtr, const int* __restrict__ col, const double* __restrict__ eU, const double* __restrict__ eC0,
@@ -779,26 +782,6 @@ int s4f_bc_evaluate(s4fgpu_ctx* c) {
     return 0;
 }
 
-template <bool T9>
-static void launch_source(s4fgpu_ctx* c, const double* T) {
-    const bool stab = c->ctl.stabilisation == S4F_STAB_RHIE_CHOW;
-    const double rs = c->UL() ? 0.0 : c->law.rho;          // updated Lagrangian: rho_*g() of the density field is part of d2Hist
-    const double rg[3] = {rs * c->ctl.g[0], rs * c->ctl.g[1], rs * c->ctl.g[2]};
-    long long need = ((long long)c->nSlices + 1) / 2, g = (long long)c->numSMs * 8;
-    if (need < g) g = need;
-    const int grid = (int)(g < 1 ? 1 : g);
-    const double* hist = (c->ctl.d2dt2Scheme == S4F_D2DT2_STEADY_STATE && !c->UL()) ? nullptr : c->d2Hist.p;
-#define S4F_LAUNCH_SRC(STAB, NO)                                                                                                      \
-    k_source_f<T9, STAB, NO><<<grid, S4F_SRC_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eU.p, c->eC0.p, c->eGam.p, c->eVc.p,   \
-                                                                    c->rowK.p, c->D.p, T, c->gradD.p, c->V.p, hist, c->source.p, c->N, \
-                                                                    c->ld, c->nEntries, c->nSlices, rg[0], rg[1], rg[2])
-    if (stab && c->nonOrth) S4F_LAUNCH_SRC(true, true);
-    else if (stab) S4F_LAUNCH_SRC(true, false);
-    else S4F_LAUNCH_SRC(false, false);
-#undef S4F_LAUNCH_SRC
-    c->launches++;
-}
-
 int s4f_make_m(s4fgpu_ctx* c) {
     k_make_m<<<s4f_grid(c->numSMs, c->N + c->B), S4F_BLOCK, 0, c->stream>>>(c->sigma.p, c->gradD.p, c->T9.p, c->N, c->bOff(), c->B, c->ld, c->gamma0());
     c->launches++;
@@ -819,21 +802,30 @@ int s4f_assemble_source(s4fgpu_ctx* c) {
     int rh = s4f_d2dt2_history(c); if (rh) return rh;
     if (c->unsModel()) {          // unsLinGeomSolid.C:124-131: no stabilisation term, the divergence of the face stress
         int rc = s4f_uns_source(c); if (rc) return rc;
-    } else if (c->fastRhs()) {
-        if (!c->mValid) {
+    } else {
+        if (!c->mValid) {      // M = T - gamma grad(D) was not left behind by a law kernel (uploaded / initial fields)
             int rc = (c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP) ? s4f_make_m(c) : s4f_kinematics(c);
             if (rc) return rc;
         }
-        const double rs = c->UL() ? 0.0 : c->law.rho;
+        const double rs = c->UL() ? 0.0 : c->law.rho;          // updated Lagrangian: rho_*g() of the density field is part of d2Hist
         const double* hist = (c->ctl.d2dt2Scheme == S4F_D2DT2_STEADY_STATE && !c->UL()) ? nullptr : c->d2Hist.p;
-        k_source_m<<<s4f_grid(c->numSMs, (long long)c->nSlices * 32, 6), S4F_BLOCK, 0, c->stream>>>(
-            c->slicePtr.p, c->col.p, c->eU.p, c->eC0.p, c->rowK.p, c->D.p, c->T9.p, c->V.p, hist, c->source.p, c->N, c->ld, c->nEntries,
-            c->nSlices, rs * c->ctl.g[0], rs * c->ctl.g[1], rs * c->ctl.g[2]);
+        if (!c->nonOrth)
+            k_source_m<<<s4f_grid(c->numSMs, (long long)c->nSlices * 32, 6), S4F_BLOCK, 0, c->stream>>>(
+                c->slicePtr.p, c->col.p, c->eU.p, c->eC0.p, c->rowK.p, c->D.p, c->T9.p, c->V.p, hist, c->source.p, c->N, c->ld, c->nEntries,
+                c->nSlices, rs * c->ctl.g[0], rs * c->ctl.g[1], rs * c->ctl.g[2]);
+        else {
+            const char* ev = getenv("S4F_SRCG_MINB");      // tuning aid: 2 = 98 registers, no spill; 3 = 80 registers; 6 = 80 registers, finer grid
+            const int minb = ev ? atoi(ev) : 2;
+            if (minb == 2)
+                k_source_g<2><<<s4f_grid(c->numSMs, (long long)c->nSlices * 32, 2), S4F_BLOCK, 0, c->stream>>>(
+                    c->slicePtr.p, c->col.p, c->eU.p, c->eVc.p, c->eC0.p, c->rowK.p, c->D.p, c->T9.p, c->gradD.p, c->V.p, hist, c->source.p, c->N,
+                    c->ld, c->nEntries, c->nSlices, rs * c->ctl.g[0], rs * c->ctl.g[1], rs * c->ctl.g[2]);
+            else
+                k_source_g<3><<<s4f_grid(c->numSMs, (long long)c->nSlices * 32, minb == 3 ? 3 : 6), S4F_BLOCK, 0, c->stream>>>(
+                    c->slicePtr.p, c->col.p, c->eU.p, c->eVc.p, c->eC0.p, c->rowK.p, c->D.p, c->T9.p, c->gradD.p, c->V.p, hist, c->source.p, c->N,
+                    c->ld, c->nEntries, c->nSlices, rs * c->ctl.g[0], rs * c->ctl.g[1], rs * c->ctl.g[2]);
+        }
         c->launches++;
-    } else if (c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP) launch_source<false>(c, c->sigma.p);
-    else {
-        if (!c->mValid) { int rc = s4f_kinematics(c); if (rc) return rc; }     // T9 held M of an orthogonal mesh before the mesh moved
-        launch_source<true>(c, c->T9.p);
     }
     if (c->nBCells > 0) {
         k_source_boundary<<<(c->nBCells + 127) / 128, 128, 0, c->stream>>>(c->bcCells.p, c->bcPtr.p, c->bcFaces.p, c->bKind.p, c->bN.p, c->bK.p,
@@ -976,10 +968,10 @@ int s4f_time_fv_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, double
     *msOut = total / reps;
     const double N = c->N, nnz = (double)c->nnzOff + (c->B - c->G);   // row entries incl. boundary faces
     if (kernel == S4F_KERNEL_GRAD) *bytesOut = 24 * N + nnz * (4 + 24) + 72 * N + 0.125 * N;                 // D, (col, ls), gradD out
-    else if (kernel == S4F_KERNEL_LAW) *bytesOut = (72 + 48 + (c->fastRhs() ? 72 : 0)) * N;                    // gradD in, sigma out (Hooke) [+ M out]
+    else if (kernel == S4F_KERNEL_LAW) *bytesOut = s4f_law_bytes(c);
     else if (kernel == S4F_KERNEL_GAMG_STEP0) { int rc = s4f_amg_step0(c, c->rA.p, bytesOut); if (rc) return rc; }
     else if (kernel == S4F_KERNEL_GAMG_VCYCLE) { int nl, sz[16]; double st; int rc = s4f_amg_info(c, &nl, sz, 16, bytesOut, &st); if (rc) return rc; }
-    else if (c->fastRhs()) *bytesOut = (24 + 72) * N + nnz * (4 + 24 + 8) + (24 + 8 + 24 + 0.125) * N;          // D, M | col,u,c0 | U, V, out
-    else *bytesOut = (24 + 48 + 72) * N + nnz * (4 + 24 + 8 + 8) + (48 + 8 + 24 + 0.125) * N;                   // D,sigma,gradD | col,u,c0,gamma | rowK, V, out
+    else if (!c->nonOrth) *bytesOut = (24 + 72) * N + nnz * (4 + 24 + 8) + (24 + 8 + 24 + 0.125) * N;          // D, M | col,u,c0 | U, V, out
+    else *bytesOut = (24 + 72 + 72) * N + nnz * (4 + 24 + 24 + 8) + (48 + 8 + 24 + 0.125) * N;                  // D, M, gradD | col,u,vc,c0 | U,Vc, V, out
     return 0;
 }

@@ -387,7 +387,7 @@ int s4f_law_correct(s4fgpu_ctx* c) {
     double* pE = L.solvePressureEqn ? c->pExp.p : nullptr;
     if (L.kind == S4F_LAW_LINEAR_ELASTIC) {
         S6 s0; for (int q = 0; q < 6; q++) s0.v[q] = L.sigma0[q];
-        const bool emitM = c->fastRhs() && c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP && !L.solvePressureEqn;
+        const bool emitM = c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP && !L.solvePressureEqn;
         k_law_linear_elastic<<<grid, S4F_BLOCK, 0, c->stream>>>(gD, c->sigma.p, N, bOff, B, ld, L.mu, L.K, s0, emitM ? c->T9.p : nullptr, c->gamma0(), pE);
         c->launches++;
         if (emitM) { c->mValid = true; S4F_CHECK_CUDA(c, cudaGetLastError()); return s4f_halo_exchange(c, c->T9.p, 9); }
@@ -424,7 +424,7 @@ int s4f_law_correct(s4fgpu_ctx* c) {
     if (c->finiteStrain()) {
         // UL: relF = I + gradDD.T() takes the place of F: fvc::div(relJ*relFinv & sigma), nonLinGeomUpdatedLagSolid.C:188
         k_tl_flux_tensor<<<grid, S4F_BLOCK, 0, c->stream>>>(gD, c->sigma.p, c->T9.p, c->Finv.p, c->Jt.p, N, bOff, B, ld,
-                                                            c->fastRhs() ? c->gradD.p : nullptr, c->gamma0());
+                                                            c->gradD.p, c->gamma0());
         c->launches++;
         c->mValid = true;
         return s4f_halo_exchange(c, c->T9.p, 9);
@@ -433,13 +433,34 @@ int s4f_law_correct(s4fgpu_ctx* c) {
     return s4f_halo_exchange(c, c->sigma.p, 6);
 }
 
+// Algorithmic bytes of one s4f_law_correct (every field read / written once per cell, fp64), for the roofline report:
+//   linearElastic              grad(D) in | sigma, M out                                             72 + 48 + 72
+//   neoHookeanElastic          grad(D) [, F.old] in | [F,] J, sigma out  (F only for the updated-Lagrangian model)  72 [+72 +72] + 8 + 48
+//   neoHookeanElasticMisesPlastic  k_mises_max_be (table > 2 points): grad(D), F.old, J.old, bEbar.old  200
+//                              k_law_mises: those + sigmaY, plasticN, DLambda, DSigmaY, epsPEq, DEpsP in  328
+//                                           F, J, bEbar, sigma, DEpsP.prevIter, DEpsP, plasticN, DLambda, DSigmaY, DEpsPEq out  344
+//   linearElasticMisesPlastic  grad(D), epsP.old, sigmaY.old, epsPEq.old, DEpsP, DLambda, plasticN in | epsilon, sigma, sigmaY,
+//                              DSigmaY, epsPEq, DEpsPEq, epsP, DEpsP, DEpsP.prevIter, DLambda, plasticN out  (+ 72 for the max-epsilon pass)
+//   finite-strain models       + k_tl_flux_tensor: grad(D), sigma [, grad(DD)] in | M, J out           72 + 48 [+72] + 72 + 8
+double s4f_law_bytes(const s4fgpu_ctx* c) {
+    const double n = (double)c->N + c->B;
+    const s4fgpu_law& L = c->law;
+    double b = 0;
+    if (L.kind == S4F_LAW_LINEAR_ELASTIC) b = 72 + 48 + ((c->ctl.solidModel == S4F_MODEL_LIN_GEOM_TOTAL_DISP && !L.solvePressureEqn) ? 72 : 0);
+    else if (L.kind == S4F_LAW_NEO_HOOKEAN_ELASTIC) b = 72 + (c->UL() ? 72 + 72 : 0) + 8 + 48;
+    else if (L.kind == S4F_LAW_NEO_HOOKEAN_MISES_PLASTIC) b = (L.nTable > 2 ? 200.0 * c->N / n : 0) + 328 + 344;
+    else b = (L.nTable > 2 ? 72.0 * c->N / n : 0) + (72 + 48 + 8 + 8 + 48 + 8 + 48) + (48 + 48 + 8 + 8 + 8 + 8 + 48 + 48 + 48 + 8 + 48);
+    if (c->finiteStrain()) b += 72 + 48 + (c->incremental() ? 72 : 0) + 72 + 8;      // Finv is written on the boundary slots only
+    return b * n;
+}
+
 // Solver-level kinematics of the total-Lagrangian models: F = I + gradD.T(), Finv, J and the flux tensor
 // J Finv & sigma (nonLinGeomTotalLagTotalDispSolid.C:225-232) from the current gradD and sigma.
 int s4f_kinematics(s4fgpu_ctx* c) {
     if (!c->finiteStrain()) return 0;
     const int grid = s4f_grid(c->numSMs, c->N + c->B);
     k_tl_flux_tensor<<<grid, S4F_BLOCK, 0, c->stream>>>(c->UL() ? c->gradD.p : c->gradForLaw(), c->sigma.p, c->T9.p, c->Finv.p, c->Jt.p, c->N, c->bOff(), c->B, c->ld,
-                                                        c->fastRhs() ? c->gradD.p : nullptr, c->gamma0());
+                                                        c->gradD.p, c->gamma0());
     c->launches++;
     c->mValid = true;
     S4F_CHECK_CUDA(c, cudaGetLastError());

@@ -172,7 +172,13 @@ int s4f_build_rows(s4fgpu_ctx* c) {
                 for (int q = 0; q < 3; q++) hSf[(size_t)q * nE + E] = sg * c->hSf[3 * (size_t)f + q];
                 if (!bnd) {
                     hDn[E] = c->hMagSf[f] * c->hNod[f];
-                    if (nonOrth) for (int q = 0; q < 3; q++) hCorr[(size_t)q * nE + E] = sg * c->hMagSf[f] * c->hCorr[3 * (size_t)f + q];
+                    if (nonOrth) {
+                        // correction vectors at round-off level (|corr| < 1e-13 of a unit vector) are orthogonal faces: exactly
+                        // zero lets the right-hand side skip their grad(D) gather (k_source_g)
+                        const double* cv = &c->hCorr[3 * (size_t)f];
+                        const bool tiny = std::fabs(cv[0]) < 1e-13 && std::fabs(cv[1]) < 1e-13 && std::fabs(cv[2]) < 1e-13;
+                        for (int q = 0; q < 3; q++) hCorr[(size_t)q * nE + E] = tiny ? 0.0 : sg * c->hMagSf[f] * cv[q];
+                    }
                 }
                 double d[3]; otherPoint(e, P, d);
                 const double r = 1.0 / (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);

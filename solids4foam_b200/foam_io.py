@@ -179,7 +179,10 @@ def read_controls(case_dir: str, **overrides) -> K.Controls:
             kw[dst] = type(getattr(K.default_controls(), dst))(coeffs[src])
     stab = coeffs.get("stabilisation", {})
     if stab:
-        kw["stabilisation"] = K.STAB_NONE if str(stab.get("type", "RhieChow")) == "none" else K.STAB_RHIE_CHOW
+        st = str(stab.get("type", "RhieChow"))
+        if st not in ("none", "RhieChow"):      # momentumStabilisation.C:43-81 also knows JamesonSchmidtTurkel and Laplacian
+            raise ValueError(f"stabilisation type {st} is not available on the GPU path (RhieChow, none)")
+        kw["stabilisation"] = K.STAB_NONE if st == "none" else K.STAB_RHIE_CHOW
         if "scaleFactor" in stab:
             kw["stabScaleFactor"] = float(stab["scaleFactor"])
     if str(coeffs.get("relaxationMethod", "fixed")) == "Aitken":
@@ -207,6 +210,14 @@ def read_controls(case_dir: str, **overrides) -> K.Controls:
     rf = _lookup(sol.get("relaxationFactors", {}).get("fields", {}), field)
     if rf is not None:
         kw["fieldRelaxD"] = float(rf)
+    re_ = _lookup(sol.get("relaxationFactors", {}).get("equations", {}), field)
+    if re_ is not None and abs(float(re_) - 1.0) > 1e-12:      # DEqn.relax() with a factor != 1 changes the matrix diagonal
+        raise ValueError(f"relaxationFactors equations {field} {re_}: equation relaxation is not available on the GPU path")
+    known_pre = dict(DIC=K.PRECOND_DIC, FDIC=K.PRECOND_DIC, DILU=K.PRECOND_DIC, diagonal=K.PRECOND_DIAGONAL, none=K.PRECOND_NONE, GAMG=K.PRECOND_GAMG)
+    if "preconditioner" in sd and not isinstance(sd["preconditioner"], dict) and str(sd["preconditioner"]) not in known_pre:
+        raise ValueError(f"preconditioner {sd['preconditioner']} is not available on the GPU path ({', '.join(known_pre)})")
+    if str(sd.get("solver", "PCG")) not in ("PCG", "PBiCGStab", "PBiCG", "GAMG"):
+        raise ValueError(f"solver {sd.get('solver')} is not available on the GPU path (PCG, PBiCGStab, GAMG)")
     gpath = os.path.join(case_dir, "constant", "g")
     if os.path.exists(gpath):
         gv = read_foam_dict(gpath).get("value")
@@ -231,6 +242,44 @@ def _uniform_or_list(v, n: int, ncomp: int) -> np.ndarray:
     raise ValueError(f"cannot read field entry {v!r}")
 
 
+def _read_series(sub, case_dir: str):
+    """A <name>Series sub-dictionary of a patch field: s4f's interpolationTable read from "file|fileName" (list of
+    (t value) tuples); only outOfBounds clamp is on this path."""
+    oob = str(sub.get("outOfBounds", "clamp"))
+    if oob != "clamp":
+        raise ValueError(f"time series with outOfBounds {oob}: only clamp is available on the GPU path")
+    fname = _lookup(sub, "fileName") or _lookup(sub, "file")
+    if fname is None:
+        raise ValueError("time series without file / fileName")
+    path = str(fname).strip('"').replace("$FOAM_CASE", case_dir)
+    with open(path) as f:
+        tbl = _Parser(_tokenize(f.read())).parse_value()
+    return [(float(a), b) for a, b in tbl]
+
+
+# what each patch-field type may carry; anything else is refused rather than silently ignored (a case with e.g.
+# "secondOrder yes" would otherwise run and report a converged but different answer)
+_BC_KEYS = {
+    "fixedDisplacement": {"type", "value", "displacementSeries", "patchType"},
+    "solidTraction": {"type", "value", "traction", "pressure", "tractionSeries", "pressureSeries", "gradient", "patchType",
+                      "secondOrder", "setEffectiveTraction", "relaxationFactor", "limitCoeff"},
+}
+_BC_NEUTRAL = {"secondOrder": ("no", "false", "off"), "setEffectiveTraction": ("no", "false", "off"), "relaxationFactor": ("1", "1.0"),
+               "limitCoeff": None}
+
+
+def _check_bc_keys(patch: str, t: str, pd) -> None:
+    allowed = _BC_KEYS.get(t)
+    if allowed is None:
+        return
+    for k, v in pd.items():
+        if k not in allowed:
+            raise ValueError(f"patch {patch}: entry {k} of {t} is not available on the GPU path")
+        neutral = _BC_NEUTRAL.get(k, ())
+        if neutral and str(v).lower() not in neutral:
+            raise ValueError(f"patch {patch}: {t} with {k} {v} is not available on the GPU path")
+
+
 def read_boundary_conditions(case_dir: str, mesh: M.FvMesh, field: str = "D", time: str = "0") -> Dict[str, K.BC]:
     d = read_foam_dict(os.path.join(case_dir, time, field))
     out: Dict[str, K.BC] = {}
@@ -242,10 +291,24 @@ def read_boundary_conditions(case_dir: str, mesh: M.FvMesh, field: str = "D", ti
         if pd is None:
             raise KeyError(f"patch {p.name} missing in {time}/{field}")
         t = str(pd["type"])
+        _check_bc_keys(p.name, t, pd)
         if t == "fixedDisplacement":
-            out[p.name] = K.fixedDisplacement(_uniform_or_list(pd["value"], p.size, 3))
+            bc = K.fixedDisplacement(_uniform_or_list(pd["value"], p.size, 3))
+            if "displacementSeries" in pd:         # fixedDisplacementFvPatchVectorField.C:258-294: disp = dispSeries_(time)
+                bc.value_series = _read_series(pd["displacementSeries"], case_dir)
+            out[p.name] = bc
         elif t == "solidTraction":
-            out[p.name] = K.solidTraction(_uniform_or_list(pd["traction"], p.size, 3), _uniform_or_list(pd["pressure"], p.size, 1))
+            if ("traction" in pd) == ("tractionSeries" in pd) or ("pressure" in pd) == ("pressureSeries" in pd):
+                raise ValueError(f"patch {p.name}: exactly one of traction / tractionSeries and of pressure / pressureSeries "
+                                 "must be given (solidTractionFvPatchVectorField.C:104-170; tractionField / pressureField are not on the GPU path)")
+            tr = _uniform_or_list(pd["traction"], p.size, 3) if "traction" in pd else np.zeros((p.size, 3))
+            pr = _uniform_or_list(pd["pressure"], p.size, 1) if "pressure" in pd else np.zeros(p.size)
+            bc = K.solidTraction(tr, pr)
+            if "tractionSeries" in pd:
+                bc.value_series = _read_series(pd["tractionSeries"], case_dir)
+            if "pressureSeries" in pd:
+                bc.pressure_series = _read_series(pd["pressureSeries"], case_dir)
+            out[p.name] = bc
         elif t in ("solidSymmetry", "symmetryPlane", "symmetry"):
             out[p.name] = K.solidSymmetry()
         elif t == "analyticalPlateHoleTraction":

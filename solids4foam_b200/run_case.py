@@ -26,15 +26,20 @@ def run(case_dir: str, steps: int | None = None, device: int = 0, precond: str |
         # DIC/FDIC in fvSolution: the device has it exactly (level scheduled, iteration counts of the CPU solver) but GAMG is the
         # fast preconditioner on a GPU; --precond DIC keeps the case's own choice
         case.controls.preconditioner = K.PRECOND_GAMG
+        log("fvSolution asks for the DIC/FDIC preconditioner; running PCG with the GAMG preconditioner instead "
+            "(same converged solution, fewer inner iterations; --precond DIC keeps the case's own choice)")
     cd = IO.read_foam_dict(os.path.join(case_dir, "system", "controlDict"))
     dt = float(cd.get("deltaT", 1.0))
     n = steps if steps is not None else max(1, int(round((float(cd.get("endTime", dt)) - float(cd.get("startTime", 0.0))) / dt)))
     solid = SolidModel(case, device=device)
     t = float(cd.get("startTime", 0.0))
     stats = []
+    timed = {name: bc for name, bc in case.bcs.items() if bc.value_series is not None or bc.pressure_series is not None}
     for _ in range(n):
         t += dt
         solid.new_timestep(dt)
+        for name, bc in timed.items():          # displacementSeries / tractionSeries / pressureSeries at the new time
+            solid.set_bc(name, bc.at(t))
         st = solid.evolve()
         solid.updateTotalFields()
         stats.append(st)

@@ -154,3 +154,71 @@ def test_case_directory_round_trip(tmp_path):
         assert a.kind == b.kind
         if b.value is not None:
             assert np.array_equal(np.broadcast_to(a.value, (p.size, 3)), np.broadcast_to(b.value, (p.size, 3)))
+
+
+# ---- time series and refused entries (a case must not run with a silently different set-up) ----------------------------
+@needs_ref
+def test_necking_bar_displacement_series_is_read_and_interpolated():
+    """neckingBar/0/DD: the "loading" patch is a fixedDisplacement driven by displacementSeries (constant/timeVsDisp:
+    (0 (0 0 0)) (1 (0.007 0 0)), clamp) -- fixedDisplacementFvPatchVectorField.C:258-294 evaluates it at every time."""
+    base = os.path.join(REF, "solids/elastoplasticity/neckingBar")
+    d = IO.read_foam_dict(os.path.join(base, "0", "DD"))
+    sub = IO._lookup(d["boundaryField"], "loading")
+    series = IO._read_series(sub["displacementSeries"], base)
+    assert series[0][0] == 0.0 and series[-1][0] == 1.0 and list(series[-1][1]) == [0.007, 0, 0]
+    bc = K.fixedDisplacement((0.0, 0.0, 0.0))
+    bc.value_series = series
+    assert np.allclose(bc.at(0.25).value, [0.00175, 0.0, 0.0]) and np.allclose(bc.at(7.0).value, [0.007, 0.0, 0.0])      # clamp
+    assert np.allclose(bc.at(-1.0).value, 0.0)
+
+
+def _write_min_case(tmp_path, patch_entries: str, stab="RhieChow", extra_relax=""):
+    mesh = M.hex_box_general(3, 2, 2, 1.0, 1.0, 1.0, names=("fixed", "loaded", "yMin", "yMax", "zMin", "zMax"))
+    c = cases.cantilever(3, 2, 2, general=True)
+    IO.write_case(str(tmp_path), c)
+    p = tmp_path / "0" / "D"
+    txt = p.read_text()
+    import re
+    txt = re.sub(r"loaded\s*\{[^}]*\}", "loaded { " + patch_entries + " }", txt, count=1)
+    p.write_text(txt)
+    if stab != "RhieChow":
+        sp = tmp_path / "constant" / "solidProperties"
+        sp.write_text(sp.read_text().replace("RhieChow", stab))
+    if extra_relax:
+        fs = tmp_path / "system" / "fvSolution"
+        fs.write_text(fs.read_text().replace("relaxationFactors\n{", "relaxationFactors\n{\n    equations { D " + extra_relax + "; }"))
+    return mesh
+
+
+def test_traction_series_runs_through_the_case_reader(tmp_path):
+    (tmp_path / "constant").mkdir(parents=True, exist_ok=True)
+    _write_min_case(tmp_path, 'type solidTraction; tractionSeries { file "$FOAM_CASE/constant/timeVsTraction"; outOfBounds clamp; } '
+                              'pressure uniform 0; value uniform (0 0 0);')
+    (tmp_path / "constant" / "timeVsTraction").write_text("( (0 (0 0 0)) (2 (0 -2e6 0)) )\n")
+    c = IO.read_case(str(tmp_path))
+    bc = c.bcs["loaded"]
+    assert bc.value_series is not None and np.allclose(bc.at(1.0).value, [0.0, -1e6, 0.0]) and np.allclose(bc.at(5.0).value, [0.0, -2e6, 0.0])
+
+
+@pytest.mark.parametrize("entries,msg", [
+    ("type solidTraction; traction uniform (0 -1e6 0); pressure uniform 0; secondOrder yes; value uniform (0 0 0);", "secondOrder"),
+    ("type solidTraction; traction uniform (0 -1e6 0); pressure uniform 0; setEffectiveTraction yes; value uniform (0 0 0);", "setEffectiveTraction"),
+    ("type solidTraction; tractionField sigmaTrac; pressure uniform 0; value uniform (0 0 0);", "tractionField"),
+    ('type solidTraction; traction uniform (0 0 0); tractionSeries { file "x"; } pressure uniform 0; value uniform (0 0 0);', "exactly one"),
+])
+def test_unsupported_patch_entries_are_refused(tmp_path, entries, msg):
+    _write_min_case(tmp_path, entries)
+    with pytest.raises(ValueError, match=msg):
+        IO.read_case(str(tmp_path))
+
+
+def test_unsupported_stabilisation_and_equation_relaxation_are_refused(tmp_path):
+    d1, d2 = tmp_path / "a", tmp_path / "b"
+    d1.mkdir(); d2.mkdir()
+    ok = 'type solidTraction; traction uniform (0 -1e6 0); pressure uniform 0; value uniform (0 0 0);'
+    _write_min_case(d1, ok, stab="JamesonSchmidtTurkel")
+    with pytest.raises(ValueError, match="stabilisation type"):
+        IO.read_case(str(d1))
+    _write_min_case(d2, ok, extra_relax="0.9")
+    with pytest.raises(ValueError, match="equation relaxation"):
+        IO.read_case(str(d2))

@@ -337,6 +337,70 @@ def test_linear_elastic_mises_plastic_law_matches_oracle():
     assert rel_l2(g.get("epsilonPEq"), o.get("epsilonPEq")) < 1e-9
 
 
+# ---------------------------------------------------------------------------------------------
+# J2 hardening branches: 2-point table = linear hardening (Hp), 1-point table = perfect plasticity
+# (neoHookeanElasticMisesPlastic.C:909-930, :1107-1115; linearElasticMisesPlastic.C:58-131)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("law", ["neoHookeanElasticMisesPlastic", "linearElasticMisesPlastic"])
+@pytest.mark.parametrize("table", [[(0.0, 0.451e9), (0.5, 0.777e9)], [(0.0, 0.451e9)]], ids=["linearHardening", "perfectPlasticity"])
+def test_j2_linear_and_perfect_plasticity_branches(law, table):
+    finite = law.startswith("neoHookean")
+
+    def case_fn():
+        c = cases.notched_bar(nx=16, ny=4, nz=4) if finite else cases.cantilever(nx=12, ny=4, nz=4)
+        c.law = K.mechanical_law(law, rho=7800.0, E=200e9, nu=0.3, table=table)
+        return c
+    g, o, mesh = _pair(case_fn)
+    D = _finite_strain_D(mesh, 0.02 if finite else 0.03)
+    for s in (g, o):
+        s.set("D", D)
+        s.initialise()
+        s.op_correct()
+    dl = o.get("DLambda")
+    assert (dl > 0).mean() > 0.05                                   # a real plastic zone
+    assert np.abs(g.get("DLambda") - dl).max() < 1e-9 * dl.max()
+    assert rel_l2(g.get("sigma"), o.get("sigma")) < 1e-11
+    assert rel_l2(g.get("sigma_b"), o.get("sigma_b")) < 1e-11
+    assert rel_l2(g.get("DEpsilonP"), o.get("DEpsilonP")) < 1e-9
+    # history commit, then a second evaluation from the committed state
+    for s in (g, o):
+        s.update_total_fields()
+    assert rel_l2(g.get("epsilonPEq"), o.get("epsilonPEq")) < 1e-9
+    assert rel_l2(g.get("sigmaY"), o.get("sigmaY")) < 1e-12
+    for s in (g, o):
+        s.new_timestep(1.0)
+        s.set("D", 1.3 * D)
+        s.initialise()
+        s.op_correct()
+    assert rel_l2(g.get("sigma"), o.get("sigma")) < 1e-11
+    assert np.abs(g.get("DLambda") - o.get("DLambda")).max() < 1e-9 * max(o.get("DLambda").max(), 1e-30)
+
+
+def test_linear_elastic_mises_plastic_evolve_and_history_commit():
+    """linearElasticMisesPlastic under linearGeometryTotalDisplacement through two load steps: evolve to convergence, commit the
+    plastic history (updateTotalFields), load further -- the small-strain counterpart of the notched-bar test."""
+    def case_fn(**kw):
+        c = cases.cantilever(nx=12, ny=4, nz=4, L=2.0, fieldRelaxD=1.0, nCorrectors=20000, **kw)
+        c.law = K.mechanical_law("linearElasticMisesPlastic", rho=7800.0, E=200e9, nu=0.3, table=K.NECKING_BAR_TABLE)
+        return c
+    g, o, mesh = _pair(case_fn, preconditioner=K.PRECOND_GAMG, **TIGHT)
+    n = mesh.patch("loaded").size
+    for step, t in enumerate((-6.0e7, -7.0e7)):
+        tr = np.zeros((n, 3)); tr[:, 1] = t
+        for s in (g, o):
+            s.new_timestep(1.0)
+            s.set_bc("loaded", K.solidTraction(tr))
+        sg, so = g.evolve(), o.evolve()
+        assert sg["converged"] and so["converged"], (step, sg, so)
+        assert rel_l2(g.get("D"), o.get("D")) < SOLVE_TOL
+        assert rel_l2(g.get("sigma"), o.get("sigma")) < 5 * SOLVE_TOL
+        for s in (g, o):
+            s.update_total_fields()
+        ep_o = o.get("epsilonPEq")
+        assert np.abs(g.get("epsilonPEq") - ep_o).max() < 1e-6 * max(ep_o.max(), 1e-30) + 1e-12
+    assert ep_o.max() > 1e-5
+
+
 def test_incremental_tl_model_two_load_steps_match_oracle():
     """nonLinearGeometryTotalLagrangian: the DD solver (nonLinGeomTotalLagSolid.C:125-260) over two load steps."""
     kw = dict(nx=8, ny=4, nz=4, L=2.0, traction=(0.0, 0.0, 0.0), fieldRelaxD=0.9, nCorrectors=8000,
@@ -562,6 +626,14 @@ def test_standalone_driver_runs_a_case_directory(tmp_path):
     for _ in range(2):
         g.new_timestep(1.0); g.evolve(); g.updateTotalFields()
     assert rel_l2(solid.get("D"), g.get("D")) < SOLVE_TOL
+    # ... and the oracle's run of the same two steps (the file round trip is checked against an independent solver)
+    from oracle.binding import OracleSolid
+    kwo = dict(kw); kwo["preconditioner"] = K.PRECOND_DIC
+    o = OracleSolid(cases.neo_hookean_cantilever(**kwo))
+    for _ in range(2):
+        o.new_timestep(1.0); o.evolve(); o.update_total_fields()
+    assert rel_l2(solid.get("D"), o.get("D")) < SOLVE_TOL
+    assert rel_l2(solid.get("sigma"), o.get("sigma")) < SOLVE_TOL
     Dfile, Db = IO.read_vol_field(str(tmp_path / "2" / "D"), solid.case.mesh)
     assert np.array_equal(Dfile, solid.get("D"))
     sfile, _ = IO.read_vol_field(str(tmp_path / "2" / "sigma"), solid.case.mesh)
