@@ -239,6 +239,16 @@ int s4fgpu_set_points(s4fgpu_handle h, int nPoints, const double* points, const 
 enum { S4F_POINT_INTERP_PATCH = 0, S4F_POINT_INTERP_GRAD = 1 };
 int s4fgpu_interpolate_to_points(s4fgpu_handle h, int field, int mode, double* pointField);
 
+/* solidModel::moveMesh (SM/solidModel/solidModel.C:2008-2148; called from nonLinGeomUpdatedLagSolid::updateTotalFields,
+ * ...C:360-374) with everything fvMesh::movePoints invalidates, ON THE DEVICE: newPoints = points + pointDD (the points
+ * of an axis-aligned symmetry plane keep their plane), then face centres / areas, cell centres / volumes, interpolation
+ * weights, delta coefficients, correction vectors, least-squares vectors, patch correction vectors and the vol->point
+ * weights are recomputed from the new points; fields, boundary data and law history stay, the GAMG hierarchy keeps its
+ * aggregates and re-sums its coefficients.  pointDD: host [3*nPoints], or NULL = the point field the last
+ * s4fgpu_interpolate_to_points left on the device (no host round trip).  Needs s4fgpu_set_points; meshes with empty
+ * patches (2-D cases) are refused: mirror their moved geometry with set_geometry / set_points instead. */
+int s4fgpu_move_points(s4fgpu_handle h, const double* pointDD);
+
 /* ---- models ---------------------------------------------------------------------------------- */
 
 int s4fgpu_set_law(s4fgpu_handle h, const s4fgpu_law* law);

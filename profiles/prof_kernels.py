@@ -1,11 +1,12 @@
 #!/usr/bin/env python
-"""Short driver for ncu: builds the hex-cantilever case and launches every hot kernel a few times
-through the C-ABI timing entry (s4fgpu_time_kernel), plus a few outer iterations.
+"""Short driver for ncu: builds a case and launches every hot kernel a few times through the C-ABI timing entry
+(s4fgpu_time_kernel).
 
-    ncu --set full --clock-control none --import-source on -k regex:'k_amul3|k_source|k_grad|k_pcg' \
-        -c 12 -o gpurun_out/prof python profiles/prof_kernels.py 800,100,100
+    S4F_NO_GRAPH=1 ncu --set full --clock-control none --import-source on -k regex:'k_amg|k_kc|k_amul3|k_source|k_grad|k_pcg|k_law|k_tl' \
+        -c 260 -o gpurun_out/prof python profiles/prof_kernels.py 800,100,100 cantilever GAMG
 
-Numbers printed under ncu are NOT bench values."""
+workload: cantilever (linearElastic, orthogonal) | notched_bar (neoHookeanElasticMisesPlastic, non-orthogonal, total Lagrangian) |
+neo_hookean.  Numbers printed under ncu are NOT bench values."""
 import os
 import sys
 
@@ -19,16 +20,17 @@ from solids4foam_b200.solid_model import SolidModel  # noqa: E402
 
 def main():
     dims = tuple(int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "800,100,100").split(","))
-    outer = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-    pre = getattr(K, "PRECOND_" + (sys.argv[3] if len(sys.argv) > 3 else "DIAGONAL"))
-    g = SolidModel(cases.cantilever(*dims, preconditioner=pre, maxIter=20 if outer else 1000))
-    for _ in range(outer):
-        g.outer_iteration()
-    names = ["spmv3", "spmv1", "pcg_p", "pcg_xr", "pcg_iter", "grad", "rhs", "law"]
-    if pre == K.PRECOND_GAMG:
-        names += ["gamg_vcycle", "gamg_step0"]
+    workload = sys.argv[2] if len(sys.argv) > 2 else "cantilever"
+    pre = getattr(K, "PRECOND_" + (sys.argv[3] if len(sys.argv) > 3 else "GAMG"))
+    fn = dict(cantilever=cases.cantilever, notched_bar=cases.notched_bar, neo_hookean=cases.neo_hookean_cantilever)[workload]
+    g = SolidModel(fn(*dims, preconditioner=pre))
+    names = ["grad", "rhs", "law"]
+    if workload == "cantilever":
+        names = ["spmv3", "spmv1", "pcg_p", "pcg_xr"] + names
+        if pre == K.PRECOND_GAMG:
+            names += ["gamg_vcycle"]
     for name in names:
-        ms, by = g.time_kernel(name, reps=2, flush_l2=False)
+        ms, by = g.time_kernel(name, reps=1, flush_l2=False)
         print(f"{name:9s} {ms:8.4f} ms  {by / ms / 1e6:8.1f} GB/s (under a profiler: not a bench value)")
 
 

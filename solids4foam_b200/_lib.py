@@ -21,7 +21,7 @@ EXPORTS = ["s4fgpu_create", "s4fgpu_destroy", "s4fgpu_last_error", "s4fgpu_versi
            "s4fgpu_outer_iteration", "s4fgpu_evolve", "s4fgpu_update_total_fields", "s4fgpu_op_grad",
            "s4fgpu_op_correct", "s4fgpu_op_assemble", "s4fgpu_op_amul", "s4fgpu_op_solve", "s4fgpu_time_kernel",
            "s4fgpu_launch_count", "s4fgpu_gamg_info", "s4fgpu_timer_start", "s4fgpu_timer_stop", "s4fgpu_synchronize",
-           "s4fgpu_set_points", "s4fgpu_interpolate_to_points", "s4fgpu_gamg_distributed_levels"]
+           "s4fgpu_set_points", "s4fgpu_interpolate_to_points", "s4fgpu_gamg_distributed_levels", "s4fgpu_move_points"]
 
 
 def _preload_nccl():
@@ -71,6 +71,7 @@ def lib():
     L.s4fgpu_launch_count.restype = C.c_longlong
     L.s4fgpu_gamg_info.argtypes = [H, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.s4fgpu_gamg_distributed_levels.argtypes = [H]
+    L.s4fgpu_move_points.argtypes = [H, C.POINTER(C.c_double)]
     K.declare_api(L, "s4fgpu_", H)
     _LIB = L
     return L

@@ -323,7 +323,7 @@ def set_points(lib, prefix: str, handle, m: FvMesh, check) -> None:
     check(getattr(lib, prefix + "set_points")(handle, pts.shape[0], _dptr(pts), _iptr(ptr), _iptr(fv)))
 
 
-def move_mesh(lib, prefix: str, handle, case: "SolidCase", pointDD: np.ndarray, check) -> None:
+def move_mesh(lib, prefix: str, handle, case: "SolidCase", pointDD: np.ndarray, check, mirror: bool = True) -> None:
     """solidModel::moveMesh (SM/solidModel/solidModel.C:2008-2148) on the host side of the boundary: symmetryPlane
     points keep their plane (:2040-2080), newPoints = oldPoints + pointDD, mesh.movePoints(newPoints); the new geometry
     is mirrored again (set_geometry keeps fields, boundary data and history; set_points refreshes the weights)."""
@@ -347,8 +347,9 @@ def move_mesh(lib, prefix: str, handle, case: "SolidCase", pointDD: np.ndarray, 
                 pdd[mp, ax] = 0.0
                 break
     case.mesh = M.move_points(m, m.points + pdd)
-    set_geometry(lib, prefix, handle, case.mesh, check)
-    set_points(lib, prefix, handle, case.mesh, check)
+    if mirror:          # mirror=False: the device has moved its own copy (s4fgpu_move_points); only the host polyMesh follows
+        set_geometry(lib, prefix, handle, case.mesh, check)
+        set_points(lib, prefix, handle, case.mesh, check)
 
 
 def field_size(mesh: FvMesh, name: str) -> tuple:

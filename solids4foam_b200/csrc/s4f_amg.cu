@@ -305,6 +305,45 @@ __global__ void k_gather_upper(const int* __restrict__ faceEntry, const double* 
 }
 
 
+// Galerkin sums of one coarse level from the (new) coefficients of the finer one, aggregates unchanged: coarse row I collects, over
+// its children i and their entries (i, j, a), a into the coarse entry of J = parent[j], or -- J = I -- out of the diagonal:
+// diag_c[I] = sum_i diag[i] - sum_{j in I} a_ij.  One thread per coarse row; set-up work, not on the iteration path.
+#define S4F_AMG_MAXW 64
+template <class T>
+__global__ void k_amg_galerkin(const int* __restrict__ spF, const int* __restrict__ colF, const T* __restrict__ aF, const T* __restrict__ dgF,
+                               const int* __restrict__ parent, int nFine, int ldF, const int* __restrict__ spC, const int* __restrict__ colC,
+                               T* __restrict__ aC, T* __restrict__ dgC, const int* __restrict__ childPtr, const int* __restrict__ child, int nC,
+                               int ldC, int* __restrict__ fail) {
+    const int I = blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= nC) return;
+    const int sC = I >> 5, lC = I & 31, baseC = spC[sC], wC = (spC[sC + 1] - baseC) >> 5;
+    if (wC > S4F_AMG_MAXW) { *fail = 1; return; }
+    int cc[S4F_AMG_MAXW]; double acc[S4F_AMG_MAXW];
+    for (int k = 0; k < wC; k++) { cc[k] = colC[baseC + 32 * k + lC]; acc[k] = 0.0; }
+    double dsub = 0, dsum[3] = {0, 0, 0};
+    for (int ce = childPtr[I]; ce < childPtr[I + 1]; ce++) {
+        const int i = child[ce];
+        const int sF = i >> 5, lF = i & 31, baseF = spF[sF], wF = (spF[sF + 1] - baseF) >> 5;
+#pragma unroll
+        for (int q = 0; q < 3; q++) dsum[q] += (double)dgF[(size_t)q * ldF + i];
+        for (int k = 0; k < wF; k++) {
+            const double a = (double)aF[baseF + 32 * k + lF];
+            if (a == 0.0) continue;
+            const int j = colF[baseF + 32 * k + lF];
+            if (j >= nFine) continue;
+            const int J = parent[j];
+            if (J == I) { dsub += a; continue; }
+            int k2 = 0;
+            while (k2 < wC && cc[k2] != J) k2++;
+            if (k2 == wC) { *fail = 2; return; }
+            acc[k2] += a;
+        }
+    }
+    for (int k = 0; k < wC; k++) aC[baseC + 32 * k + lC] = (T)acc[k];
+#pragma unroll
+    for (int q = 0; q < 3; q++) dgC[(size_t)q * ldC + I] = (T)(dsum[q] - dsub);
+}
+
 // ---- K-cycle on level 1 (gamgCycle 2): two flexible-CG steps on the coarse problem A_1 x = b, each preconditioned by the
 // V-cycle from level 1 down (Notay's aggregation multigrid): the coarse correction is scaled by the Krylov step instead of a
 // fixed factor.  Per component q:  c1 = V(b), v1 = A c1, rho1 = c1.v1, alpha1 = c1.b;  r = b - (alpha1/rho1) v1;
@@ -440,11 +479,13 @@ struct S4fAmg {
     virtual ~S4fAmg() {}
     virtual int apply(s4fgpu_ctx* c, const double* r3, double* z3, const int* act) = 0;
     virtual int step0(s4fgpu_ctx* c, const double* r3, const int* act) = 0;   // one fine-level smoothing step alone (timing)
+    virtual int refresh(s4fgpu_ctx* c) = 0;   // new fine-matrix coefficients, same aggregates
     double step0Bytes = 0;
     std::vector<int> sizes;
     std::vector<int> distributed;       // per level: 1 = one part per rank (sizes[] is then this rank's part)
     double bytesPerApply = 0;
     double setupSeconds = 0;
+    double refreshSeconds = 0;
 };
 
 namespace {
@@ -720,6 +761,58 @@ struct Hierarchy : S4fAmg {
         k_kc_amul<T, 2><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(C.slicePtr, C.col, C.a, C.dg.p, kc2.p, kr.p, kv1.p, C.t.p, C.n, C.ld, C.nSlices, kS.p, act, red);
         k_kc_final<T><<<gv, 256, 0, c->stream>>>(kc1.p, kc2.p, C.x.p, C.n, C.ld, kS.p, act);
         c->launches += 2;
+        return 0;
+    }
+
+    // The fine matrix changed its coefficients but not its graph (mesh motion): keep the aggregates, re-sum every coarse
+    // level on the device, invert the coarsest matrix again.  Single rank (the gathered levels of a decomposed run would
+    // need the other ranks' sums: those runs rebuild the hierarchy).
+    int refresh(s4fgpu_ctx* c) override {
+        Level<T>& L0 = *lv[0];
+        if (sizeof(T) != sizeof(double)) {
+            k_amg_convert<T><<<(unsigned)((c->nEntries + 255) / 256), 256, 0, c->stream>>>(c->eA.p, L0.aB.p, c->nEntries);
+            c->launches++;
+        }
+        k_amg_diag<T><<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->diagC.p, L0.dg.p, c->N, c->ld, L0.ld);
+        c->launches++;
+        DevBuf<int> fail;
+        S4F_CHECK_CUDA(c, fail.alloc(1));
+        for (size_t l = 1; l < lv.size(); l++) {
+            Level<T>& Fn = *lv[l - 1];
+            Level<T>& C = *lv[l];
+            k_amg_galerkin<T><<<(C.n + 127) / 128, 128, 0, c->stream>>>(Fn.slicePtr, Fn.col, Fn.a, Fn.dg.p, Fn.parent.p, Fn.n, Fn.ld, C.slicePtrB.p,
+                                                                       C.colB.p, C.aB.p, C.dg.p, C.childPtr.p, C.child.p, C.n, C.ld, fail.p);
+            c->launches++;
+        }
+        int hf = 0;
+        S4F_CHECK_CUDA(c, cudaMemcpyAsync(&hf, fail.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (hf) { c->err = "GAMG refresh: coarse rows wider than expected"; return 1; }
+        // coarsest level: dense inverse again (<= 512 cells)
+        Level<T>& LC = *lv.back();
+        const int n = LC.n;
+        std::vector<int> sp(LC.nSlices + 1);
+        S4F_CHECK_CUDA(c, cudaMemcpy(sp.data(), LC.slicePtrB.p, sp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        std::vector<int> hc(std::max(sp.back(), 1)); std::vector<T> ha(std::max(sp.back(), 1)), hd(3 * (size_t)LC.ld);
+        S4F_CHECK_CUDA(c, cudaMemcpy(hc.data(), LC.colB.p, sp.back() * sizeof(int), cudaMemcpyDeviceToHost));
+        S4F_CHECK_CUDA(c, cudaMemcpy(ha.data(), LC.aB.p, sp.back() * sizeof(T), cudaMemcpyDeviceToHost));
+        S4F_CHECK_CUDA(c, cudaMemcpy(hd.data(), LC.dg.p, hd.size() * sizeof(T), cudaMemcpyDeviceToHost));
+        HostLevel HC; HC.n = n;
+        for (int q = 0; q < 3; q++) { HC.diag[q].resize(n); for (int i = 0; i < n; i++) HC.diag[q][i] = (double)hd[(size_t)q * LC.ld + i]; }
+        for (int i = 0; i < n; i++) {
+            const int sI = i >> 5, lane = i & 31, w = (sp[sI + 1] - sp[sI]) / 32;
+            for (int k = 0; k < w; k++) {
+                const int j = hc[sp[sI] + 32 * k + lane]; const double a = (double)ha[sp[sI] + 32 * k + lane];
+                if (j > i && j < n && a != 0.0) { HC.own.push_back(i); HC.nei.push_back(j); HC.a.push_back(a); }
+            }
+        }
+        std::vector<T> inv(3 * (size_t)n * n);
+        for (int q = 0; q < 3; q++) {
+            std::vector<double> iq;
+            if (!dense_inverse(HC, q, iq)) { c->err = "GAMG refresh: coarsest-level matrix is not positive definite"; return 1; }
+            for (size_t i = 0; i < iq.size(); i++) inv[(size_t)q * n * n + i] = (T)iq[i];
+        }
+        S4F_CHECK_CUDA(c, denseInv.upload(inv));
         return 0;
     }
 
@@ -1007,6 +1100,16 @@ int s4f_amg_setup(s4fgpu_ctx* c) {
     if (!rc) c->amg->setupSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     c->graphSerial++;
     return rc;
+}
+
+// after mesh motion: same aggregates, new coefficients.  Falls back to a full set-up when there is nothing to refresh.
+int s4f_amg_refresh(s4fgpu_ctx* c) {
+    if (!c->amg || c->nRanks > 1) return s4f_amg_setup(c);
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = c->amg->refresh(c);
+    if (rc) { c->err.clear(); return s4f_amg_setup(c); }
+    c->amg->refreshSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
 }
 
 int s4f_amg_info(s4fgpu_ctx* c, int* nLevels, int* sizes, int maxLevels, double* bytesPerApply, double* setupSeconds) {

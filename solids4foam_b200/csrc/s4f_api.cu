@@ -176,6 +176,7 @@ int s4fgpu_set_mesh(s4fgpu_handle c, int nCells, int nInternalFaces, const int* 
         S4F_REQUIRE(c, owner[f] >= 0 && owner[f] < neighbour[f] && neighbour[f] < nCells, "set_mesh: lduAddressing must be upper-triangular (owner < neighbour)");
     for (int b = 0; b < B; b++) S4F_REQUIRE(c, faceCells[b] >= 0 && faceCells[b] < nCells, "set_mesh: faceCells out of range");
     c->bcKind.assign(nPatches, S4F_BC_SOLID_TRACTION);
+    s4f_amg_destroy(c); c->amgRefresh = false;          // another graph: the aggregates go with it
     c->meshSet = true; c->geomSet = false; c->matrixValid = false; c->nGlobalCells = -1;
     return 0;
 }
@@ -196,6 +197,7 @@ int s4fgpu_set_geometry(s4fgpu_handle c, const double* C, const double* V, const
     // host geometry copies are only needed to build the rows (cell centres stay for the vol->point weights)
     std::vector<double>().swap(c->hSf); std::vector<double>().swap(c->hCf); std::vector<double>().swap(c->hCorr);
     std::vector<double>().swap(c->hW); std::vector<double>().swap(c->hNod);
+    c->hostGeomStale = false;
     c->geomSet = true; c->matrixValid = false; c->amgValid = false; c->histValid = false; c->mValid = false; c->gValid = false; c->unsValid = false;
     if (c->lawSet && !again) { rc = s4f_setup_law(c); if (rc) return rc; }
     return 0;
@@ -224,6 +226,9 @@ int s4fgpu_set_controls(s4fgpu_handle c, const s4fgpu_controls* ctl) {
     if (ctl->d2dt2Scheme == S4F_D2DT2_BACKWARD && ctl->deltaT0 > 0)     // backwardD2dt2Scheme.C:316-322
         S4F_REQUIRE(c, std::fabs(ctl->deltaT - ctl->deltaT0) <= 1e-15 + 1e-12 * ctl->deltaT, "set_controls: backwardD2dt2Scheme not implemented for variable time steps");
     c->unsValid = false;
+    if (c->ctlSet && (ctl->gamgSinglePrecision != c->ctl.gamgSinglePrecision || ctl->gamgSmootherDegree != c->ctl.gamgSmootherDegree ||
+                      ctl->gamgCycle != c->ctl.gamgCycle || ctl->gamgOverCorrection != c->ctl.gamgOverCorrection ||
+                      ctl->gamgSmootherRatio != c->ctl.gamgSmootherRatio)) { s4f_amg_destroy(c); c->amgRefresh = false; }
     c->ctl = *ctl; c->ctlSet = true; c->matrixValid = false; c->amgValid = false; c->histValid = false; c->mValid = false;
     if (c->geomSet) return s4f_alloc_model_fields(c);
     return 0;
@@ -423,6 +428,12 @@ int s4fgpu_interpolate_to_points(s4fgpu_handle c, int field, int mode, double* p
     return s4f_interpolate_to_points(c, X, mode == S4F_POINT_INTERP_GRAD ? G : nullptr, pointField);
 }
 
+int s4fgpu_move_points(s4fgpu_handle c, const double* pointDD) {
+    S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
+    S4F_REQUIRE(c, c->geomSet, "move_points: call set_geometry first");
+    return s4f_move_points_device(c, pointDD);
+}
+
 int s4fgpu_update_total_fields(s4fgpu_handle c) {
     S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
     return s4f_update_total_fields_impl(c);
@@ -497,7 +508,7 @@ long long s4fgpu_launch_count(s4fgpu_handle c) { return c ? c->launches : 0; }
 int s4fgpu_gamg_info(s4fgpu_handle c, int* nLevels, int* sizes, int maxLevels, double* bytesPerApply, double* setupSeconds) {
     S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
     S4F_REQUIRE(c, c->geomSet && c->matrixValid, "gamg_info: initialise first");
-    if (!c->amgValid) { int rc = s4f_amg_setup(c); if (rc) return rc; c->amgValid = true; }
+    if (!c->amgValid) { int rc = c->amgRefresh ? s4f_amg_refresh(c) : s4f_amg_setup(c); if (rc) return rc; c->amgValid = true; c->amgRefresh = false; }
     return s4f_amg_info(c, nLevels, sizes, maxLevels, bytesPerApply, setupSeconds);
 }
 

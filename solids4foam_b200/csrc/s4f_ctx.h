@@ -189,6 +189,12 @@ struct s4fgpu_ctx {
     std::vector<double> hBSfHost;                 // [3B] boundary area vectors (patch normals of the point constraints)
     bool rhoInit = false;
     std::vector<double> hCfB;                     // [3B] boundary face centres of the last set_geometry (hC is kept too)
+    // device mesh motion (s4f_geom.cu): points, face -> vertex CSR, signed face of every row entry, face / cell geometry
+    DevBuf<double> dPoints;                       // [3*nPoints] AoS
+    DevBuf<int> dFvPtr, dFv, eFaceS, ptFixAxis;   // [F+B+1], [sum verts], [nEntries] +-(face+1) (0 = padding), [nPoints] axis a symmetry plane fixes (-1: none)
+    DevBuf<double> fCtr, fSf, Cc;                 // [3*(F+B)] SoA, [3*(F+B)] SoA, [3*ld] cell centres (ghosts by halo exchange)
+    bool amgRefresh = false;                      // the hierarchy's aggregates are still good: re-sum the coefficients only
+    bool hostGeomStale = false;                   // the mesh moved on the device: hC / hCfB / hPoints are those of the last host call
     DevBuf<int> ptPtr, ptCol;                     // [nPoints+1], [nnzP]
     DevBuf<double> ptW, ptN;                      // [nnzP] normalised inverse-distance weights; [3*nPoints] constraint normal (0 = none)
     DevBuf<double> ptOut;                         // [3*nPoints]
@@ -315,6 +321,9 @@ int s4f_amul_device(s4fgpu_ctx* c, const double* x3, double* w3, int mask);
 int s4f_alloc_model_fields(s4fgpu_ctx* c);
 int s4f_upload_bc(s4fgpu_ctx* c);
 int s4f_amg_setup(s4fgpu_ctx* c);                                   // after s4f_assemble_matrix
+int s4f_amg_refresh(s4fgpu_ctx* c);                                 // same aggregates, Galerkin sums of the new fine matrix (device)
+int s4f_move_points_device(s4fgpu_ctx* c, const double* hostPointDD);   // s4f_geom.cu
+int s4f_refresh_host_geometry(s4fgpu_ctx* c);
 int s4f_amg_apply(s4fgpu_ctx* c, const double* r3, double* z3);     // z = M^-1 r, 3 components, stride ld
 int s4f_amg_step0(s4fgpu_ctx* c, const double* r3, double* bytes);
 void s4f_amg_destroy(s4fgpu_ctx* c);

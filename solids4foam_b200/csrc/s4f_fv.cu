@@ -758,6 +758,8 @@ int s4f_assemble_matrix(s4fgpu_ctx* c) {
     k_diag_recip<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->diagC.p, c->rDiagC.p, c->N, c->ld);
     c->launches++;
     c->matrixValid = true;
+    // new coefficients on the same graph: an existing GAMG hierarchy keeps its aggregates and re-sums its levels on the device
+    c->amgRefresh = (c->amg != nullptr && c->nRanks == 1);
     c->amgValid = false; c->dicValid = false;
     S4F_CHECK_CUDA(c, cudaGetLastError());
     return 0;
@@ -942,8 +944,8 @@ int s4f_relax_and_residual(s4fgpu_ctx* c, int iCorr) {
 // ---- timing of the face-loop kernels (bench.py roofline) ----------------------------------------
 int s4f_time_fv_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, double* msOut, double* bytesOut) {
     if ((kernel == S4F_KERNEL_GAMG_VCYCLE || kernel == S4F_KERNEL_GAMG_STEP0) && !c->amgValid) {
-        int rc = s4f_amg_setup(c); if (rc) return rc;
-        c->amgValid = true;
+        int rc = c->amgRefresh ? s4f_amg_refresh(c) : s4f_amg_setup(c); if (rc) return rc;
+        c->amgValid = true; c->amgRefresh = false;
     }
     if (flushL2 && c->flushBuf.n < (size_t)48 * 1024 * 1024) S4F_CHECK_CUDA(c, c->flushBuf.alloc((size_t)48 * 1024 * 1024));
     cudaEvent_t e0, e1;

@@ -833,7 +833,8 @@ int s4f_solve_segregated(s4fgpu_ctx* c, double* psi, const double* source, bool 
     }
     if (!local && c->zA.n != 3 * (size_t)ld) { S4F_CHECK_CUDA(c, c->zA.alloc(3 * (size_t)ld)); c->graphSerial++; }
     if (P.precond == S4F_PRECOND_GAMG && !c->amgValid) {
-        int rca = s4f_amg_setup(c); if (rca) return rca;
+        int rca = c->amgRefresh ? s4f_amg_refresh(c) : s4f_amg_setup(c); if (rca) return rca;
+        c->amgRefresh = false;
         c->amgValid = true;
     }
     SolveArgs a{psi, source, P, nGlob, Cond{}};

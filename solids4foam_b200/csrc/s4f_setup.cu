@@ -383,6 +383,7 @@ __global__ void k_vol_to_point_grad(const int* __restrict__ ptr, const int* __re
 int s4f_build_point_stencil(s4fgpu_ctx* c) {
     const int N = c->N, F = c->F, B = c->B, nP = c->nPoints, bOff = c->bOff();
     if (nP == 0) { c->err = "pointCellsLeastSquares needs the mesh points (s4fgpu_set_points)"; return 1; }
+    if (c->hostGeomStale) { int rg = s4f_refresh_host_geometry(c); if (rg) return rg; }
     if (c->nRanks > 1) { c->err = "pointCellsLeastSquares is not available on decomposed meshes yet"; return 1; }
     std::vector<std::vector<int>> pc(nP), pb(nP), cellPts(N);
     auto add = [](std::vector<int>& v, int x) { if (std::find(v.begin(), v.end(), x) == v.end()) v.push_back(x); };
@@ -462,6 +463,7 @@ int s4f_build_point_stencil(s4fgpu_ctx* c) {
 
 int s4f_build_point_weights(s4fgpu_ctx* c, const double* points) {
     const int N = c->N, F = c->F, B = c->B, nP = c->nPoints, bOff = c->bOff();
+    if (c->hostGeomStale) { int rg = s4f_refresh_host_geometry(c); if (rg) return rg; }
     if (c->nRanks > 1) { c->err = "set_points: vol->point interpolation is not available on decomposed meshes yet"; return 1; }
     std::vector<std::vector<int>> pc(nP), pb(nP);
     auto add = [](std::vector<int>& v, int x) { if (std::find(v.begin(), v.end(), x) == v.end()) v.push_back(x); };
@@ -472,6 +474,7 @@ int s4f_build_point_weights(s4fgpu_ctx* c, const double* points) {
         if (f < F) add(pc[p], c->nei[f]);
     }
     std::vector<double> hN(3 * (size_t)std::max(nP, 1), 0.0);
+    std::vector<int> fixAxis(std::max(nP, 1), -1);
     for (int ip = 0; ip < c->nPatches; ip++) {
         if (c->pKind[ip] == S4F_PATCH_PROCESSOR) continue;
         double n[3] = {0, 0, 0};
@@ -486,6 +489,27 @@ int s4f_build_point_weights(s4fgpu_ctx* c, const double* points) {
                 const int b = c->pStart[ip] + i;
                 for (int j = c->hFvPtr[F + b]; j < c->hFvPtr[F + b + 1]; j++) for (int q = 0; q < 3; q++) hN[3 * (size_t)c->hFv[j] + q] = n[q] / m;
             }
+            // solidModel::moveMesh (solidModel.C:2040-2080): the points of a symmetry plane aligned with a coordinate axis keep
+            // that coordinate.  Average of the point normals (each the normalised sum of the unit normals of its patch faces).
+            std::vector<double> pn(3 * (size_t)nP, 0.0); std::vector<char> on(nP, 0);
+            for (int i = 0; i < c->pSize[ip]; i++) {
+                const int b = c->pStart[ip] + i;
+                const double* sf = &c->hBSfHost[3 * (size_t)b];
+                const double ms = std::sqrt(sf[0] * sf[0] + sf[1] * sf[1] + sf[2] * sf[2]);
+                for (int j = c->hFvPtr[F + b]; j < c->hFvPtr[F + b + 1]; j++) {
+                    const int p = c->hFv[j]; on[p] = 1;
+                    for (int q = 0; q < 3; q++) pn[3 * (size_t)p + q] += sf[q] / ms;
+                }
+            }
+            double avg[3] = {0, 0, 0}; int cntP = 0;
+            for (int p = 0; p < nP; p++) if (on[p]) {
+                const double* v = &pn[3 * (size_t)p];
+                const double mv = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+                for (int q = 0; q < 3; q++) avg[q] += v[q] / mv;
+                cntP++;
+            }
+            for (int ax = 0; ax < 3; ax++)
+                if (std::fabs(avg[ax] / cntP) > 0.95) { for (int p = 0; p < nP; p++) if (on[p]) fixAxis[p] = ax; break; }
         }
     }
     {   // gradient-extrapolated variant: all points from their pointCells
@@ -538,6 +562,10 @@ int s4f_build_point_weights(s4fgpu_ctx* c, const double* points) {
     S4F_CHECK_CUDA(c, c->ptPtr.upload(ptr)); S4F_CHECK_CUDA(c, c->ptCol.upload(col)); S4F_CHECK_CUDA(c, c->ptW.upload(w));
     S4F_CHECK_CUDA(c, c->ptN.upload(hN));
     if (c->ptOut.n != 3 * (size_t)std::max(nP, 1)) S4F_CHECK_CUDA(c, c->ptOut.alloc(3 * (size_t)std::max(nP, 1)));
+    // what the device-side mesh motion needs (s4f_geom.cu): the points, the face -> vertex CSR, the symmetry-plane constraint
+    S4F_CHECK_CUDA(c, c->ptFixAxis.upload(fixAxis));
+    S4F_CHECK_CUDA(c, c->dPoints.upload(std::vector<double>(points, points + 3 * (size_t)nP)));
+    S4F_CHECK_CUDA(c, c->dFvPtr.upload(c->hFvPtr)); S4F_CHECK_CUDA(c, c->dFv.upload(c->hFv.empty() ? std::vector<int>(1, 0) : c->hFv));
     return 0;
 }
 

@@ -356,8 +356,10 @@ def _read_list_file(path: str):
     return n, body
 
 
-def read_poly_mesh(poly_dir: str) -> M.FvMesh:
-    """[OF-ext] polyMesh ASCII files -> fvMesh with the geometry primitiveMesh / surfaceInterpolation would compute."""
+def read_poly_mesh(poly_dir: str, rank: int = 0, nRanks: int = 1, exchange=None) -> M.FvMesh:
+    """[OF-ext] polyMesh ASCII files -> fvMesh with the geometry primitiveMesh / surfaceInterpolation would compute.
+    ``processorN/constant/polyMesh`` of a decomposed case: pass rank, nRanks and exchange (see fv_mesh_from_poly); the
+    global cell numbers come from ``cellProcAddressing`` when decomposePar wrote it."""
     _, pts = _read_list_file(os.path.join(poly_dir, "points"))
     points = np.asarray(pts, dtype=np.float64).reshape(-1, 3)
     nF, fl = _read_list_file(os.path.join(poly_dir, "faces"))
@@ -374,7 +376,11 @@ def read_poly_mesh(poly_dir: str) -> M.FvMesh:
     neighbour = np.asarray(nei, dtype=np.int64)
     _, bl = _read_list_file(os.path.join(poly_dir, "boundary"))
     patches_raw = [(name, d) for name, d in bl]
-    return fv_mesh_from_poly(points, faces, owner, neighbour, patches_raw)
+    cellGlobal = None
+    cpa = os.path.join(poly_dir, "cellProcAddressing")
+    if os.path.exists(cpa):
+        cellGlobal = np.asarray(_read_list_file(cpa)[1], dtype=np.int64)
+    return fv_mesh_from_poly(points, faces, owner, neighbour, patches_raw, rank=rank, nRanks=nRanks, exchange=exchange, cellGlobal=cellGlobal)
 
 
 def polygon_centres_and_areas(points: np.ndarray, fptr: np.ndarray, fflat: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
@@ -400,7 +406,11 @@ def polygon_centres_and_areas(points: np.ndarray, fptr: np.ndarray, fflat: np.nd
     return ctr, 0.5 * sumN
 
 
-def fv_mesh_from_poly(points, faces, owner, neighbour, patches_raw) -> M.FvMesh:
+def fv_mesh_from_poly(points, faces, owner, neighbour, patches_raw, rank: int = 0, nRanks: int = 1, exchange=None,
+                      cellGlobal=None) -> M.FvMesh:
+    """polyMesh arrays -> fvMesh.  On a decomposed mesh (``processor`` patches) the interpolation geometry of the cut faces
+    needs the cell centres across the cut: ``exchange({nbr_rank: C[faceCells of the patch]}) -> {nbr_rank: their centres}``
+    supplies them (torch.distributed in run_case, an in-memory swap in the tests)."""
     nI = neighbour.size
     nCells = int(owner.max()) + 1
     fptr = np.zeros(len(faces) + 1, dtype=np.int64)
@@ -429,8 +439,19 @@ def fv_mesh_from_poly(points, faces, owner, neighbour, patches_raw) -> M.FvMesh:
     kb = np.concatenate(keep) if keep else np.zeros(0, dtype=np.int64)
     Sf = np.concatenate([fAreas[:nI], fAreas[kb]])
     Cf = np.concatenate([fCtrs[:nI], fCtrs[kb]])
-    mesh = M._finish_mesh(nCells, owner[:nI], neighbour, owner[kb], patches, C, V, Sf, Cf, None, solutionD,
-                          cellGlobal=np.arange(nCells, dtype=np.int64))
+    CnbrB_proc = None
+    procs = [p for p in patches if p.kind == M.PROCESSOR]
+    if procs:
+        if exchange is None:
+            raise ValueError("a mesh with processor patches needs the neighbour cell centres: pass exchange=")
+        fcB = owner[kb]
+        got = exchange({p.nbr_rank: C[fcB[p.start:p.start + p.size]] for p in procs})
+        CnbrB_proc = Cf[nI:].copy()
+        for p in procs:
+            CnbrB_proc[p.start:p.start + p.size] = got[p.nbr_rank]
+    mesh = M._finish_mesh(nCells, owner[:nI], neighbour, owner[kb], patches, C, V, Sf, Cf, CnbrB_proc, solutionD,
+                          cellGlobal=np.arange(nCells, dtype=np.int64) if cellGlobal is None else np.asarray(cellGlobal, dtype=np.int64),
+                          rank=rank, nRanks=nRanks)
     mesh.points = points.copy()
     kept = list(range(nI)) + [int(i) for i in kb]
     if all(len(f) == 4 for f in faces):          # quads: the mesh can be moved (mesh.move_points) and its points interpolated to
@@ -466,6 +487,73 @@ def write_poly_mesh(poly_dir: str, mesh: M.FvMesh) -> None:
         items.append(f"    {p.name}\n    {{\n        type            {tname[p.kind]};\n        nFaces          {p.size};\n"
                      f"        startFace       {F + p.start};\n{extra}    }}")
     wr("boundary", "polyBoundaryMesh", f"{len(items)}\n(\n" + "\n".join(items) + "\n)")
+
+
+def write_raw_poly_mesh(poly_dir: str, points, faces, owner, neighbour, patches_raw, rank: int = 0, cellGlobal=None) -> None:
+    """points / faces / owner / neighbour / boundary (+ cellProcAddressing) from raw polyMesh arrays."""
+    os.makedirs(poly_dir, exist_ok=True)
+
+    def wr(name, cls, body):
+        with open(os.path.join(poly_dir, name), "w") as f:
+            f.write(_HEADER.format(cls=cls, loc="constant/polyMesh", obj=name))
+            f.write(body)
+            f.write("\n\n// ************************************************************************* //\n")
+    wr("points", "vectorField", f"{len(points)}\n(\n" + "\n".join(f"({p[0]!r} {p[1]!r} {p[2]!r})" for p in np.asarray(points).tolist()) + "\n)")
+    wr("faces", "faceList", f"{len(faces)}\n(\n" + "\n".join(f"{len(fc)}({' '.join(str(int(v)) for v in fc)})" for fc in faces) + "\n)")
+    wr("owner", "labelList", f"{len(owner)}\n(\n" + "\n".join(str(int(v)) for v in owner) + "\n)")
+    wr("neighbour", "labelList", f"{len(neighbour)}\n(\n" + "\n".join(str(int(v)) for v in neighbour) + "\n)")
+    items = []
+    for name, d in patches_raw:
+        body = "".join(f"        {k:<15} {v};\n" for k, v in d.items())
+        items.append(f"    {name}\n    {{\n{body}    }}")
+    wr("boundary", "polyBoundaryMesh", f"{len(items)}\n(\n" + "\n".join(items) + "\n)")
+    if cellGlobal is not None:
+        wr("cellProcAddressing", "labelList", f"{len(cellGlobal)}\n(\n" + "\n".join(str(int(v)) for v in cellGlobal) + "\n)")
+
+
+def decompose_case(case_dir: str, nRanks: int, cell_rank=None) -> None:
+    """``decomposePar`` for a solid case directory (constant/polyMesh, 0/D): writes ``processorN/constant/polyMesh`` (with
+    cellProcAddressing) and ``processorN/0/D``.  Default cell -> processor map: ``method simple`` with ``n (P 1 1)``, equal
+    slabs of cells along x (system/decomposeParDict of the plateHole tutorial); the initial D field must be uniform."""
+    case = read_case(case_dir)
+    mesh = case.mesh
+    meta = mesh.meta["poly"]
+    if cell_rank is None:
+        order = np.argsort(mesh.C[:, 0], kind="stable")
+        cell_rank = np.empty(mesh.nCells, dtype=np.int64)
+        cell_rank[order] = (np.arange(mesh.nCells) * nRanks) // mesh.nCells
+    parts = M.decompose_poly(mesh.points, meta["faces"], np.asarray(meta["owner"]), np.asarray(meta["neighbour"]), meta["patches_raw"], cell_rank)
+    kind_of = dict(patch=M.PATCH, wall=M.PATCH, empty=M.EMPTY, symmetryPlane=M.SYMMETRY_PLANE, symmetry=M.SYMMETRY_PLANE, processor=M.PROCESSOR)
+    for r, part in enumerate(parts):
+        pdir = os.path.join(case_dir, f"processor{r}")
+        write_raw_poly_mesh(os.path.join(pdir, "constant", "polyMesh"), part["points"], part["faces"], part["owner"], part["neighbour"],
+                            part["patches_raw"], rank=r, cellGlobal=part["cellGlobal"])
+        patches, bcs = [], {}
+        for name, d in part["patches_raw"]:
+            kind = kind_of.get(str(d["type"]), M.PATCH)
+            if kind == M.EMPTY:
+                continue
+            patches.append(M.PatchInfo(name, kind, 0, int(d["nFaces"]), nbr_rank=int(d.get("neighbProcNo", -1))))
+            if kind == M.PROCESSOR:
+                continue
+            bc, sel = case.bcs[name], part["patchSel"][name]
+            n0 = mesh.patch(name).size
+            val = None if bc.value is None else np.broadcast_to(np.asarray(bc.value, dtype=np.float64), (n0, 3))[sel]
+            pr = None if bc.pressure is None else np.broadcast_to(np.asarray(bc.pressure, dtype=np.float64), (n0,))[sel]
+            bcs[name] = K.BC(bc.kind, val, pr)
+        write_D_file(os.path.join(pdir, "0"), patches, bcs)
+
+
+def read_decomposed_case(case_dir: str, rank: int, nRanks: int, exchange, **overrides) -> K.SolidCase:
+    """One processor's part of a decomposed case: processor<rank>/constant/polyMesh and processor<rank>/0/<field>; the
+    dictionaries under constant/ and system/ are shared."""
+    pdir = os.path.join(case_dir, f"processor{rank}")
+    mesh = read_poly_mesh(os.path.join(pdir, "constant", "polyMesh"), rank=rank, nRanks=nRanks, exchange=exchange)
+    law = read_mechanical_law(case_dir)
+    ctl = read_controls(case_dir, **overrides)
+    field = "DD" if ctl.solidModel in (K.MODEL_NONLIN_TL, K.MODEL_NONLIN_UL) and os.path.exists(os.path.join(pdir, "0", "DD")) else "D"
+    bcs = read_boundary_conditions(pdir, mesh, field)
+    return K.SolidCase(mesh, bcs, law, ctl, name=os.path.basename(os.path.normpath(case_dir)) + f"/processor{rank}")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -534,6 +622,27 @@ def _dict_file(path: str, obj: str, body: str, cls: str = "dictionary") -> None:
         f.write(body + "\n")
 
 
+def write_D_file(zero_dir: str, patches, bcs) -> None:
+    """0/D with the patch entries the reference reads (fixedDisplacement value, solidTraction traction / pressure, solidSymmetry)."""
+    rows = []
+    for p in patches:
+        if p.kind == M.PROCESSOR:
+            rows.append(f"    {p.name}\n    {{\n        type            processor;\n        value           uniform (0 0 0);\n    }}")
+            continue
+        bc = bcs[p.name]
+        vec = lambda a: "nonuniform List<vector>\n" + f"{p.size}\n(\n" + _fmt_rows(np.broadcast_to(np.asarray(a, dtype=np.float64), (p.size, 3))) + "\n)\n"
+        if bc.kind == K.BC_FIXED_DISPLACEMENT:
+            rows.append(f"    {p.name}\n    {{\n        type            fixedDisplacement;\n        value           {vec(bc.value)};\n    }}")
+        elif bc.kind == K.BC_SOLID_TRACTION:
+            pr = np.broadcast_to(np.zeros(1) if bc.pressure is None else np.asarray(bc.pressure, dtype=np.float64), (p.size,))
+            rows.append(f"    {p.name}\n    {{\n        type            solidTraction;\n        traction        {vec(bc.value)};\n"
+                        f"        pressure        nonuniform List<scalar>\n{p.size}\n(\n{_fmt_rows(pr)}\n)\n;\n        value           uniform (0 0 0);\n    }}")
+        else:
+            rows.append(f"    {p.name}\n    {{\n        type            solidSymmetry;\n        patchType       symmetryPlane;\n        value           uniform (0 0 0);\n    }}")
+    _dict_file(os.path.join(zero_dir, "D"), "D",
+               "dimensions      [0 1 0 0 0 0 0];\n\ninternalField   uniform (0 0 0);\n\nboundaryField\n{\n" + "\n".join(rows) + "\n}", cls="volVectorField")
+
+
 def write_case(case_dir: str, case: K.SolidCase, end_time: float = 1.0) -> None:
     """constant/{polyMesh, solidProperties, mechanicalProperties, g}, system/{controlDict, fvSchemes, fvSolution}, 0/D with the
     keys the reference reads (see the module header)."""
@@ -573,20 +682,4 @@ def write_case(case_dir: str, case: K.SolidCase, end_time: float = 1.0) -> None:
     _dict_file(os.path.join(case_dir, "system", "controlDict"), "controlDict",
                f"application     solids4Foam;\nstartTime       0;\nendTime         {end_time!r};\ndeltaT          {c.deltaT!r};\n"
                "writeControl    timeStep;\nwriteInterval   1;")
-    rows = []
-    for p in m.patches:
-        if p.kind == M.PROCESSOR:
-            rows.append(f"    {p.name}\n    {{\n        type            processor;\n    }}")
-            continue
-        bc = case.bcs[p.name]
-        vec = lambda a: "nonuniform List<vector>\n" + f"{p.size}\n(\n" + _fmt_rows(np.broadcast_to(np.asarray(a, dtype=np.float64), (p.size, 3))) + "\n)\n"
-        if bc.kind == K.BC_FIXED_DISPLACEMENT:
-            rows.append(f"    {p.name}\n    {{\n        type            fixedDisplacement;\n        value           {vec(bc.value)};\n    }}")
-        elif bc.kind == K.BC_SOLID_TRACTION:
-            pr = np.broadcast_to(np.zeros(1) if bc.pressure is None else np.asarray(bc.pressure, dtype=np.float64), (p.size,))
-            rows.append(f"    {p.name}\n    {{\n        type            solidTraction;\n        traction        {vec(bc.value)};\n"
-                        f"        pressure        nonuniform List<scalar>\n{p.size}\n(\n{_fmt_rows(pr)}\n)\n;\n        value           uniform (0 0 0);\n    }}")
-        else:
-            rows.append(f"    {p.name}\n    {{\n        type            solidSymmetry;\n        patchType       symmetryPlane;\n        value           uniform (0 0 0);\n    }}")
-    _dict_file(os.path.join(case_dir, "0", "D"), "D",
-               "dimensions      [0 1 0 0 0 0 0];\n\ninternalField   uniform (0 0 0);\n\nboundaryField\n{\n" + "\n".join(rows) + "\n}", cls="volVectorField")
+    write_D_file(os.path.join(case_dir, "0"), m.patches, case.bcs)

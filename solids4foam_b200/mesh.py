@@ -724,3 +724,73 @@ def hex_box_general(nx, ny, nz, L=1.0, H=1.0, W=1.0, point_map=None, cell_perm_s
     if cell_perm_seed is not None:
         perm = np.random.default_rng(cell_perm_seed).permutation(hexes.shape[0])
     return poly_mesh_from_hexes(points, hexes, classify, list(zip(names, kinds)), cell_perm=perm)
+
+
+# ----------------------------------------------------------------------------
+# decomposePar restated: a serial polyMesh -> one polyMesh per processor
+# ----------------------------------------------------------------------------
+def decompose_poly(points: np.ndarray, faces: Sequence[Sequence[int]], owner: np.ndarray, neighbour: np.ndarray,
+                   patches_raw: Sequence[Tuple[str, Dict]], cell_rank: np.ndarray) -> List[Dict]:
+    """What ``decomposePar`` writes under ``processorN/constant/polyMesh`` ([OF-ext] domainDecomposition), for a given
+    cell -> processor map (``method manual`` / the result of ``simple``): per processor
+
+    * cells in ascending global order (``cellProcAddressing``), points in ascending global order,
+    * internal faces = global internal faces with both cells on the processor, in the upper-triangular order of the local
+      numbering; the original patches, each with its faces on this processor in global order; then one ``processor`` patch
+      per neighbour processor (ascending), its faces in global face order on BOTH sides, which is what makes the two sides
+      match face by face; the side that holds the global neighbour cell stores the face reversed (normal out of its cell).
+
+    Returns per rank: points, faces (list of vertex lists), owner, neighbour, patches_raw [(name, dict)], cellGlobal,
+    pointGlobal, faceGlobal (signed: -(f+1) for a reversed face), patchSel {patch: positions of its faces in the serial patch}."""
+    owner = np.asarray(owner, dtype=np.int64); neighbour = np.asarray(neighbour, dtype=np.int64)
+    cell_rank = np.asarray(cell_rank, dtype=np.int64)
+    nI = neighbour.size
+    nRanks = int(cell_rank.max()) + 1
+    out = []
+    for r in range(nRanks):
+        cells = np.nonzero(cell_rank == r)[0]
+        loc = -np.ones(cell_rank.size, dtype=np.int64); loc[cells] = np.arange(cells.size)
+        ro, rn = cell_rank[owner[:nI]], cell_rank[neighbour]
+        # internal faces of this processor, sorted by (local owner, local neighbour)
+        fi = np.nonzero((ro == r) & (rn == r))[0]
+        lo, ln = loc[owner[fi]], loc[neighbour[fi]]
+        flip_i = lo > ln                       # local numbering keeps the global order here (ascending), so never true; kept for safety
+        a, b = np.where(flip_i, ln, lo), np.where(flip_i, lo, ln)
+        order = np.lexsort((b, a))
+        face_ids = [fi[order]]; face_flip = [flip_i[order]]
+        f_owner = [a[order]]; f_neigh = b[order]
+        praw = []
+        patch_sel = {}
+        start = fi.size
+        for name, d in patches_raw:
+            s0, n0 = int(d["startFace"]), int(d["nFaces"])
+            pf = np.arange(s0, s0 + n0)
+            pf = pf[cell_rank[owner[pf]] == r]
+            patch_sel[name] = pf - s0
+            dd = dict(d); dd["nFaces"] = int(pf.size); dd["startFace"] = int(start)
+            praw.append((name, dd))
+            face_ids.append(pf); face_flip.append(np.zeros(pf.size, dtype=bool)); f_owner.append(loc[owner[pf]])
+            start += pf.size
+        # processor patches: cut faces, per neighbour processor, in global face order
+        cut_o = np.nonzero((ro == r) & (rn != r))[0]       # I hold the owner: keep orientation
+        cut_n = np.nonzero((rn == r) & (ro != r))[0]       # I hold the neighbour: reversed
+        other = np.concatenate([rn[cut_o], ro[cut_n]])
+        cutf = np.concatenate([cut_o, cut_n])
+        mine = np.concatenate([loc[owner[cut_o]], loc[neighbour[cut_n]]])
+        flipc = np.concatenate([np.zeros(cut_o.size, dtype=bool), np.ones(cut_n.size, dtype=bool)])
+        for q in sorted(set(int(x) for x in other)):
+            sel = np.nonzero(other == q)[0]
+            sel = sel[np.argsort(cutf[sel], kind="stable")]
+            praw.append((f"procBoundary{r}to{q}", dict(type="processor", nFaces=int(sel.size), startFace=int(start), myProcNo=r, neighbProcNo=q)))
+            face_ids.append(cutf[sel]); face_flip.append(flipc[sel]); f_owner.append(mine[sel])
+            start += sel.size
+        gids = np.concatenate(face_ids); gflip = np.concatenate(face_flip)
+        used = np.unique(np.fromiter((v for f in gids for v in faces[int(f)]), dtype=np.int64))
+        ploc = -np.ones(points.shape[0], dtype=np.int64); ploc[used] = np.arange(used.size)
+        lfaces = []
+        for f, fl in zip(gids, gflip):
+            vs = [int(ploc[v]) for v in faces[int(f)]]
+            lfaces.append([vs[0]] + vs[:0:-1] if fl else vs)      # reversed face keeps its first vertex ([OF-ext] face::reverseFace)
+        out.append(dict(points=points[used].copy(), faces=lfaces, owner=np.concatenate(f_owner), neighbour=f_neigh, patches_raw=praw,
+                        cellGlobal=cells, pointGlobal=used, faceGlobal=np.where(gflip, -(gids + 1), gids + 1), patchSel=patch_sel))
+    return out

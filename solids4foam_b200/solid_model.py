@@ -56,6 +56,9 @@ class SolidModel:
             self._check(self.L.s4fgpu_comm_init(self.h, nRanks, rank, uid))
         K.apply_case(self.L, "s4fgpu_", self.h, case, self._check)
         self._check(self.L.s4fgpu_initialise(self.h))
+        # mesh motion of the updated-Lagrangian model on the device (s4fgpu_move_points); 2-D meshes (empty patches) keep the
+        # host route: set_geometry / set_points with the geometry the host recomputed
+        self.device_mesh_motion = bool(np.all(np.asarray(case.mesh.solutionD) != 0))
 
     # ---- plumbing ----
     def _check(self, rc: int) -> None:
@@ -141,9 +144,13 @@ class SolidModel:
         """solidModel::updateTotalFields; for the updated-Lagrangian model nonLinGeomUpdatedLagSolid::updateTotalFields
         (nonLinGeomUpdatedLagSolid.C:360-374): density update, moveMesh(oldPoints, DD, pointDD), law history."""
         if self.movingMesh():
-            pointDD = self.interpolate_to_points("DD")
+            pointDD = self.interpolate_to_points("DD")          # stays on the device as well
             self._check(self.L.s4fgpu_update_total_fields(self.h))
-            K.move_mesh(self.L, "s4fgpu_", self.h, self.case, pointDD, self._check)
+            if self.device_mesh_motion:
+                self._check(self.L.s4fgpu_move_points(self.h, None))      # points, geometry, weights, GAMG coefficients: all on the device
+                K.move_mesh(self.L, "s4fgpu_", self.h, self.case, pointDD, self._check, mirror=False)   # the host's own polyMesh follows
+            else:
+                K.move_mesh(self.L, "s4fgpu_", self.h, self.case, pointDD, self._check)
             self.pointDD = pointDD
             return
         self._check(self.L.s4fgpu_update_total_fields(self.h))

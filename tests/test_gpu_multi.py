@@ -18,3 +18,15 @@ def test_two_gpu_slab_decomposition_matches_oracle(precond, dims):
            "--master-port", "29517", os.path.join(HERE, "dist_gpu_check.py")] + dims.split() + [precond]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_decomposed_case_directory_runs_on_two_gpus(tmp_path):
+    """processorN/ directories (foam_io.decompose_case = decomposePar simple (2 1 1)) read rank by rank and run by the
+    standalone driver, against the single-domain oracle run of the serial case."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29518", os.path.join(HERE, "dist_case_check.py"), str(tmp_path / "case")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
