@@ -54,7 +54,15 @@ Foam::gpuLinearElastic::gpuLinearElastic
         K_ = dimensionedScalar(dict.lookup("K"));
         const scalar E = 9.0*K_.value()*mu_.value()/(3.0*K_.value() + mu_.value());
         const scalar nu = (3.0*K_.value() - 2.0*mu_.value())/(2.0*(3.0*K_.value() + mu_.value()));
-        lambda_.value() = nu*E/((1.0 + nu)*(1.0 - 2.0*nu));
+        if (planeStress())             // linearElastic.C:107-113: lambda and K are reset for plane stress
+        {
+            lambda_.value() = nu*E/((1.0 + nu)*(1.0 - nu));
+            K_.value() = E/(3.0*(1.0 - nu));
+        }
+        else
+        {
+            lambda_.value() = nu*E/((1.0 + nu)*(1.0 - 2.0*nu));
+        }
     }
     else
     {
@@ -69,6 +77,15 @@ Foam::gpuLinearElastic::gpuLinearElastic
     pod_.updateBEbarConsistent = 1; pod_.DEpsilonPRelax = 1.0;
     pod_.solvePressureEqn = dict.lookupOrDefault<Switch>("solvePressureEqn", false);               // mechanicalLaw.C:1525-1532
     pod_.pressureSmoothingScaleFactor = dict.lookupOrDefault<scalar>("pressureSmoothingScaleFactor", 100.0);
+    if (pod_.solvePressureEqn)
+    {
+        // sigmaHydEqn.solve(); sigmaHyd.relax()  (mechanicalLaw.C:1455-1459): fvSolution solvers / relaxationFactors "sigmaHyd"
+        const dictionary& sd = mesh.solverDict("sigmaHyd");
+        pod_.sigmaHydTolerance = sd.lookupOrDefault<scalar>("tolerance", 1e-6);
+        pod_.sigmaHydRelTol = sd.lookupOrDefault<scalar>("relTol", 0);
+        pod_.sigmaHydMaxIter = sd.lookupOrDefault<label>("maxIter", 1000);
+        pod_.sigmaHydRelax = mesh.relaxField("sigmaHyd") ? mesh.fieldRelaxationFactor("sigmaHyd") : 1.0;
+    }
 }
 
 

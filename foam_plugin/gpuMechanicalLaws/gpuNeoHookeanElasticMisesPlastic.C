@@ -64,6 +64,15 @@ Foam::gpuNeoHookeanElasticMisesPlastic::gpuNeoHookeanElasticMisesPlastic
     pod_.DEpsilonPRelax = mesh.relaxField("DEpsilonP") ? mesh.fieldRelaxationFactor("DEpsilonP") : 1.0;
     pod_.solvePressureEqn = dict.lookupOrDefault<Switch>("solvePressureEqn", false);               // mechanicalLaw.C:1525-1532
     pod_.pressureSmoothingScaleFactor = dict.lookupOrDefault<scalar>("pressureSmoothingScaleFactor", 100.0);
+    if (pod_.solvePressureEqn)
+    {
+        // sigmaHydEqn.solve(); sigmaHyd.relax()  (mechanicalLaw.C:1455-1459): fvSolution solvers / relaxationFactors "sigmaHyd"
+        const dictionary& sd = mesh.solverDict("sigmaHyd");
+        pod_.sigmaHydTolerance = sd.lookupOrDefault<scalar>("tolerance", 1e-6);
+        pod_.sigmaHydRelTol = sd.lookupOrDefault<scalar>("relTol", 0);
+        pod_.sigmaHydMaxIter = sd.lookupOrDefault<label>("maxIter", 1000);
+        pod_.sigmaHydRelax = mesh.relaxField("sigmaHyd") ? mesh.fieldRelaxationFactor("sigmaHyd") : 1.0;
+    }
 }
 
 

@@ -137,6 +137,12 @@ typedef struct {
     double DEpsilonPRelax;     /* fvSolution relaxationFactors fields DEpsilonP (1 = none) */
     int solvePressureEqn;      /* mechanicalLaw.C:1525-1528: smooth sigmaHyd with the pressure Poisson equation :1374-1468 */
     double pressureSmoothingScaleFactor; /* :1529-1532, default 100 */
+    /* fvSolution "solvers sigmaHyd" and "relaxationFactors fields sigmaHyd" of the pressure equation (sigmaHydEqn.solve();
+     * sigmaHyd.relax(); mechanicalLaw.C:1455-1459).  tolerance <= 0: the D solver's tolerance / relTol / maxIter;
+     * relax <= 0 or 1: no relaxation */
+    double sigmaHydTolerance, sigmaHydRelTol;
+    int sigmaHydMaxIter;
+    double sigmaHydRelax;
 } s4fgpu_law;
 
 /* solidProperties <model>Coeffs + fvSchemes + fvSolution entries used on the path */

@@ -1368,10 +1368,16 @@ void updateSigmaHydSmoothed(s4f_oracle& o, double /*impK: uniform, o.impK holds 
     }
     dvec x(o.sigmaHyd.begin(), o.sigmaHyd.begin() + N);
     o.upper.swap(up);
-    o.perfP = solvePCG(o, dg.data(), x.data(), src.data());
+    {   // sigmaHydEqn.solve() with the fvSolution "sigmaHyd" entry when the case has one (mechanicalLaw.C:1455)
+        const s4fgpu_controls keep = o.ctl;
+        if (o.law.sigmaHydTolerance > 0) { o.ctl.tolerance = o.law.sigmaHydTolerance; o.ctl.relTol = o.law.sigmaHydRelTol; if (o.law.sigmaHydMaxIter > 0) o.ctl.maxIter = o.law.sigmaHydMaxIter; }
+        o.perfP = solvePCG(o, dg.data(), x.data(), src.data());
+        o.ctl = keep;
+    }
     o.upper.swap(up);
-    for (int c = 0; c < N; c++) o.sigmaHyd[c] = x[c];
-    for (int b = 0; b < B; b++) o.sigmaHyd[N + b] = x[o.faceCells[b]];                  // zeroGradient
+    const double al = o.law.sigmaHydRelax > 0 ? o.law.sigmaHydRelax : 1.0;                 // sigmaHyd.relax() :1459
+    for (int c = 0; c < N; c++) o.sigmaHyd[c] = (al == 1.0) ? x[c] : o.sigmaHyd[c] + al * (x[c] - o.sigmaHyd[c]);
+    for (int b = 0; b < B; b++) o.sigmaHyd[N + b] = o.sigmaHyd[o.faceCells[b]];         // zeroGradient
     // grad(sigmaHyd) = fvc::grad(sigmaHyd): scalar gradient through the vector machinery (component 0)
     dvec X(3 * (size_t)(N + B), 0.0), g;
     for (int c = 0; c < N + B; c++) X[3 * c] = o.sigmaHyd[c];

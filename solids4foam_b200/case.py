@@ -62,7 +62,9 @@ class Law(C.Structure):
                 ("lambda_", C.c_double), ("sigma0", C.c_double * 6), ("nTable", C.c_int),
                 ("tableEps", C.c_double * 64), ("tableSigY", C.c_double * 64),
                 ("updateBEbarConsistent", C.c_int), ("DEpsilonPRelax", C.c_double),
-                ("solvePressureEqn", C.c_int), ("pressureSmoothingScaleFactor", C.c_double)]
+                ("solvePressureEqn", C.c_int), ("pressureSmoothingScaleFactor", C.c_double),
+                ("sigmaHydTolerance", C.c_double), ("sigmaHydRelTol", C.c_double), ("sigmaHydMaxIter", C.c_int),
+                ("sigmaHydRelax", C.c_double)]
 
 
 class Controls(C.Structure):
@@ -137,7 +139,8 @@ def mechanical_law(type: str, rho: float = 0.0, E: Optional[float] = None, nu: O
                    mu: Optional[float] = None, K: Optional[float] = None, planeStress: bool = False,
                    sigma0: Optional[Sequence[float]] = None, table: Optional[Sequence[Sequence[float]]] = None,
                    updateBEbarConsistent: bool = True, DEpsilonPRelax: float = 1.0, solvePressureEqn: bool = False,
-                   pressureSmoothingScaleFactor: float = 100.0) -> Law:
+                   pressureSmoothingScaleFactor: float = 100.0, sigmaHydTolerance: float = 0.0, sigmaHydRelTol: float = 0.0,
+                   sigmaHydMaxIter: int = 0, sigmaHydRelax: float = 1.0) -> Law:
     """The mechanicalProperties entry -> POD parameters, with the reference constructors' formulas:
     linearElastic.C:62-133, neoHookeanElastic.C:51-85, neoHookeanElasticMisesPlastic.C:868-930,
     linearElasticMisesPlastic (same E,nu -> mu,K as linearElastic)."""
@@ -146,6 +149,8 @@ def mechanical_law(type: str, rho: float = 0.0, E: Optional[float] = None, nu: O
     L.kind = kind
     L.rho = rho
     lam = 0.0
+    if solvePressureEqn and planeStress and kind in (LAW_LINEAR_ELASTIC, LAW_LINEAR_ELASTIC_MISES_PLASTIC):
+        raise ValueError("planeStress must be 'off' when solvePressureEqn is enabled")       # linearElastic.C:112-119
     if kind in (LAW_LINEAR_ELASTIC, LAW_LINEAR_ELASTIC_MISES_PLASTIC):
         if E is not None and nu is not None:
             if nu < -1.0 or nu > 0.5:
@@ -164,7 +169,13 @@ def mechanical_law(type: str, rho: float = 0.0, E: Optional[float] = None, nu: O
             mu_, K_ = mu, K
             E_ = 9.0 * K_ * mu_ / (3.0 * K_ + mu_)
             nu_ = (3.0 * K_ - 2.0 * mu_) / (2.0 * (3.0 * K_ + mu_))
-            lam = nu_ * E_ / ((1.0 + nu_) * (1.0 - 2.0 * nu_))
+            if nu_ >= 0.5:
+                lam = K_ = 1e15
+            elif planeStress:          # linearElastic.C:107-113: lambda AND K are reset for plane stress
+                lam = nu_ * E_ / ((1.0 + nu_) * (1.0 - nu_))
+                K_ = E_ / (3.0 * (1.0 - nu_))
+            else:
+                lam = nu_ * E_ / ((1.0 + nu_) * (1.0 - 2.0 * nu_))
         else:
             raise ValueError("Either E and nu or mu and K elastic parameters should be specified")
     else:
@@ -196,6 +207,7 @@ def mechanical_law(type: str, rho: float = 0.0, E: Optional[float] = None, nu: O
     L.DEpsilonPRelax = DEpsilonPRelax
     L.solvePressureEqn = 1 if solvePressureEqn else 0        # mechanicalLaw.C:1525-1532
     L.pressureSmoothingScaleFactor = pressureSmoothingScaleFactor
+    L.sigmaHydTolerance, L.sigmaHydRelTol, L.sigmaHydMaxIter, L.sigmaHydRelax = sigmaHydTolerance, sigmaHydRelTol, sigmaHydMaxIter, sigmaHydRelax
     return L
 
 
@@ -291,7 +303,7 @@ def apply_case(lib, prefix: str, handle, case: SolidCase, check) -> None:
     arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in
             (m.C, m.V, m.Sf, m.magSf, m.Cf, m.weights, m.nonOrthDeltaCoeffs, m.nonOrthCorrVec, m.CnbrB)]
     check(f("set_geometry")(handle, *[_dptr(a) for a in arrs]))
-    if m.points is not None:
+    if m.points is not None and m.nRanks == 1:      # the point-based operators are single-rank (no point sync across processor patches yet)
         set_points(lib, prefix, handle, m, check)
     check(f("set_controls")(handle, C.byref(case.controls)))
     check(f("set_law")(handle, C.byref(case.law)))

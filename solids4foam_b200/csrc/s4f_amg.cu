@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -783,6 +784,7 @@ struct Hierarchy : S4fAmg {
             k_amg_galerkin<T><<<(C.n + 127) / 128, 128, 0, c->stream>>>(Fn.slicePtr, Fn.col, Fn.a, Fn.dg.p, Fn.parent.p, Fn.n, Fn.ld, C.slicePtrB.p,
                                                                        C.colB.p, C.aB.p, C.dg.p, C.childPtr.p, C.child.p, C.n, C.ld, fail.p);
             c->launches++;
+            S4F_CHECK_CUDA(c, cudaGetLastError());
         }
         int hf = 0;
         S4F_CHECK_CUDA(c, cudaMemcpyAsync(&hf, fail.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -792,10 +794,11 @@ struct Hierarchy : S4fAmg {
         Level<T>& LC = *lv.back();
         const int n = LC.n;
         std::vector<int> sp(LC.nSlices + 1);
-        S4F_CHECK_CUDA(c, cudaMemcpy(sp.data(), LC.slicePtrB.p, sp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        // (a mesh of <= 512 cells has the fine level as its only, dense level: its rows are the fine rows)
+        S4F_CHECK_CUDA(c, cudaMemcpy(sp.data(), LC.slicePtr, sp.size() * sizeof(int), cudaMemcpyDeviceToHost));
         std::vector<int> hc(std::max(sp.back(), 1)); std::vector<T> ha(std::max(sp.back(), 1)), hd(3 * (size_t)LC.ld);
-        S4F_CHECK_CUDA(c, cudaMemcpy(hc.data(), LC.colB.p, sp.back() * sizeof(int), cudaMemcpyDeviceToHost));
-        S4F_CHECK_CUDA(c, cudaMemcpy(ha.data(), LC.aB.p, sp.back() * sizeof(T), cudaMemcpyDeviceToHost));
+        S4F_CHECK_CUDA(c, cudaMemcpy(hc.data(), LC.col, sp.back() * sizeof(int), cudaMemcpyDeviceToHost));
+        S4F_CHECK_CUDA(c, cudaMemcpy(ha.data(), LC.a, sp.back() * sizeof(T), cudaMemcpyDeviceToHost));
         S4F_CHECK_CUDA(c, cudaMemcpy(hd.data(), LC.dg.p, hd.size() * sizeof(T), cudaMemcpyDeviceToHost));
         HostLevel HC; HC.n = n;
         for (int q = 0; q < 3; q++) { HC.diag[q].resize(n); for (int i = 0; i < n; i++) HC.diag[q][i] = (double)hd[(size_t)q * LC.ld + i]; }
@@ -1107,7 +1110,12 @@ int s4f_amg_refresh(s4fgpu_ctx* c) {
     if (!c->amg || c->nRanks > 1) return s4f_amg_setup(c);
     const auto t0 = std::chrono::steady_clock::now();
     int rc = c->amg->refresh(c);
-    if (rc) { c->err.clear(); return s4f_amg_setup(c); }
+    if (rc) {
+        fprintf(stderr, "libs4fgpu: GAMG coefficient refresh not possible (%s); rebuilding the hierarchy\n", c->err.c_str());
+        c->err.clear();
+        cudaGetLastError();
+        return s4f_amg_setup(c);
+    }
     c->amg->refreshSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return 0;
 }

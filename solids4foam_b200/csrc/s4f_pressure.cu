@@ -127,6 +127,11 @@ __global__ void k_sigma_hyd_fix(double* __restrict__ sigma, const double* __rest
     sigma[i] += d; sigma[(size_t)3 * ld + i] += d; sigma[(size_t)5 * ld + i] += d;
 }
 
+__global__ void k_p_relax(double* __restrict__ p, const double* __restrict__ x, double alpha, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) p[i] = (alpha == 1.0) ? x[i] : p[i] + alpha * (x[i] - p[i]);
+}
+
 }  // namespace
 
 int s4f_pressure_smooth(s4fgpu_ctx* c) {
@@ -152,6 +157,9 @@ int s4f_pressure_smooth(s4fgpu_ctx* c) {
         const int pre = c->ctl.preconditioner, sol = c->ctl.solver;
         std::swap(c->eA.p, c->eP.p); std::swap(c->diagC.p, c->pDiag.p); std::swap(c->rDiagC.p, c->pRDiag.p);
         c->ctl.preconditioner = S4F_PRECOND_DIAGONAL; c->ctl.solver = S4F_SOLVER_PCG;
+        // fvSolution "solvers sigmaHyd": its own tolerances when the case gives them
+        const double keepTol = c->ctl.tolerance, keepRel = c->ctl.relTol; const int keepMax = c->ctl.maxIter;
+        if (c->law.sigmaHydTolerance > 0) { c->ctl.tolerance = c->law.sigmaHydTolerance; c->ctl.relTol = c->law.sigmaHydRelTol; if (c->law.sigmaHydMaxIter > 0) c->ctl.maxIter = c->law.sigmaHydMaxIter; }
         // the scalar equation rides component 0 whatever the mesh's empty directions are (a 2-D case whose empty direction
         // is x would otherwise skip it)
         const int keepD[3] = {c->solD[0], c->solD[1], c->solD[2]};
@@ -159,11 +167,16 @@ int s4f_pressure_smooth(s4fgpu_ctx* c) {
         rc = s4f_solve_segregated(c, c->pX.p, c->pB.p);
         for (int q = 0; q < 3; q++) c->solD[q] = keepD[q];
         c->ctl.preconditioner = pre; c->ctl.solver = sol;
+        c->ctl.tolerance = keepTol; c->ctl.relTol = keepRel; c->ctl.maxIter = keepMax;
         std::swap(c->eA.p, c->eP.p); std::swap(c->diagC.p, c->pDiag.p); std::swap(c->rDiagC.p, c->pRDiag.p);
         c->lastP = c->last; c->last = keep; c->totalInner = keepInner;
         if (rc) return rc;
     }
-    S4F_CHECK_CUDA(c, cudaMemcpyAsync(c->sigmaHyd.p, c->pX.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    {   // sigmaHyd.relax(): sigmaHyd = sigmaHyd.prevIter + alpha (solution - sigmaHyd.prevIter); alpha = 1 is a copy
+        const double al = (c->law.sigmaHydRelax > 0) ? c->law.sigmaHydRelax : 1.0;
+        k_p_relax<<<(N + 255) / 256, 256, 0, c->stream>>>(c->sigmaHyd.p, c->pX.p, al, N);
+        c->launches++;
+    }
     if (B > 0) { k_p_boundary<<<(B + 127) / 128, 128, 0, c->stream>>>(c->bFaceCell.p, c->bKind.p, c->sigmaHyd.p, B, bOff); c->launches++; }
     if ((rc = s4f_halo_exchange(c, c->sigmaHyd.p, 1))) return rc;
     if (c->ctl.gradScheme == S4F_GRAD_GAUSS_LINEAR)

@@ -157,6 +157,18 @@ def read_mechanical_law(case_dir: str) -> K.Law:
         kw["solvePressureEqn"] = str(ld["solvePressureEqn"]).lower() in ("yes", "true", "on")
     if "pressureSmoothingScaleFactor" in ld:
         kw["pressureSmoothingScaleFactor"] = _scalar(ld["pressureSmoothingScaleFactor"])
+    if kw.get("solvePressureEqn"):          # fvSolution solvers sigmaHyd / relaxationFactors fields sigmaHyd (mechanicalLaw.C:1455-1459)
+        fs = os.path.join(case_dir, "system", "fvSolution")
+        if os.path.exists(fs):
+            sol = read_foam_dict(fs)
+            sd = _lookup(sol.get("solvers", {}), "sigmaHyd", {})
+            if "tolerance" in sd:
+                kw["sigmaHydTolerance"] = float(sd["tolerance"])
+                kw["sigmaHydRelTol"] = float(sd.get("relTol", 0.0))
+                kw["sigmaHydMaxIter"] = int(sd.get("maxIter", 1000))
+            rf = _lookup(sol.get("relaxationFactors", {}).get("fields", {}), "sigmaHyd")
+            if rf is not None:
+                kw["sigmaHydRelax"] = float(rf)
     fname = _lookup(ld, "fileName") or _lookup(ld, "file")      # the tutorials write the key as "file|fileName"
     if fname is not None:       # plasticity: the (epsilonP sigmaY) table file, neoHookeanElasticMisesPlastic.C:868-930
         path = str(fname).strip('"').replace("$FOAM_CASE", case_dir)

@@ -543,7 +543,7 @@ def test_device_mesh_motion_matches_the_host_route(which):
                   preconditioner=K.PRECOND_GAMG, **TIGHT)
         mk = lambda: cases.neo_hookean_cantilever(**kw)
     else:                                   # a symmetry plane: its points keep their plane
-        mk = lambda: cases.beam_in_cross_flow(refine=1, pressure=40.0, d2dt2Scheme=K.D2DT2_STEADY_STATE, preconditioner=K.PRECOND_GAMG, **TIGHT)
+        mk = lambda: cases.beam_in_cross_flow(refine=1, pressure=40.0, d2dt2Scheme=K.D2DT2_STEADY_STATE, preconditioner=K.PRECOND_GAMG, nCorrectors=20000, **TIGHT)
     gd, gh = SolidModel(mk()), SolidModel(mk())
     assert gd.device_mesh_motion
     gh.device_mesh_motion = False
@@ -575,6 +575,34 @@ def test_device_mesh_motion_matches_the_host_route(which):
         g.new_timestep(1.0)
         assert g.evolve()["converged"]
     assert rel_l2(gd.get("D"), gh.get("D")) < SOLVE_TOL and rel_l2(gd.get("sigma"), gh.get("sigma")) < SOLVE_TOL
+
+
+def test_gamg_coefficient_refresh_equals_a_rebuilt_hierarchy(monkeypatch):
+    """A re-assembled matrix on the same mesh graph (here: the Euler d2dt2 diagonal of another time step size) keeps the GAMG
+    aggregates and re-sums the Galerkin coefficients on the device (k_amg_galerkin, three levels at 13.8 k cells).  The
+    refreshed hierarchy must precondition exactly like one rebuilt from scratch with the same aggregates would: the rebuilt
+    one re-agglomerates from slightly different coefficients, so the check is iteration counts within one and equal solutions."""
+    from solids4foam_b200.solid_model import SolidModel
+    kw = dict(nx=48, ny=17, nz=17, L=2.0, d2dt2Scheme=K.D2DT2_EULER, deltaT=1e-3, deltaT0=1e-3, g=(0.0, -9.81, 0.0),
+              preconditioner=K.PRECOND_GAMG, tolerance=1e-11, relTol=0.0, maxIter=200)
+    res = {}
+    for mode in ("refresh", "rebuild"):
+        if mode == "rebuild":
+            monkeypatch.setenv("S4F_NO_AMG_REFRESH", "1")
+        g = SolidModel(cases.cantilever(**kw))
+        assert len(g.gamg_info()["levels"]) >= 3
+        g.new_timestep(1e-3)
+        g.outer_iteration()                      # builds the hierarchy for this matrix
+        g.new_timestep(2.5e-4)                   # another diagonal: the matrix is re-assembled
+        st = g.outer_iteration()
+        rng = np.random.default_rng(3)
+        src = rng.standard_normal((g.case.mesh.nCells, 3))
+        psi, sst = g.op_solve(np.zeros_like(src), src)
+        res[mode] = (st, psi, sst, g.gamg_info())
+    (st_a, psi_a, ss_a, ia), (st_b, psi_b, ss_b, ib) = res["refresh"], res["rebuild"]
+    assert ia["levels"] == ib["levels"]
+    assert max(abs(a - b) for a, b in zip(ss_a["nIterations"], ss_b["nIterations"])) <= 1, (ss_a, ss_b)
+    assert rel_l2(psi_a, psi_b) < 1e-8
 
 
 def test_updated_lagrangian_first_iterates_match_oracle_to_round_off():
@@ -652,6 +680,26 @@ def test_pressure_smoothing_matches_oracle(law, model, case_kw):
     p.law.solvePressureEqn = 0
     o2 = OracleSolid(p); o2.evolve()
     assert rel_l2(o.get("sigma"), o2.get("sigma")) > 1e-3
+
+
+def test_pressure_equation_own_solver_controls_and_relaxation():
+    """fvSolution "solvers sigmaHyd" (its own tolerance / relTol) and "relaxationFactors fields sigmaHyd" (sigmaHyd.relax(),
+    mechanicalLaw.C:1455-1459) on both sides: the converged fields still agree."""
+    from oracle.binding import OracleSolid
+    from solids4foam_b200.solid_model import SolidModel
+    kw = dict(nx=10, ny=5, nz=5, L=2.0, nCorrectors=20000, fieldRelaxD=0.9, **TIGHT)
+    pair = []
+    for pre in (K.PRECOND_GAMG, K.PRECOND_DIC):
+        c = cases.cantilever(preconditioner=pre, **kw)
+        c.law = K.mechanical_law("linearElastic", rho=7800.0, E=200e9, nu=0.3, solvePressureEqn=True, pressureSmoothingScaleFactor=100.0,
+                                 sigmaHydTolerance=1e-12, sigmaHydRelTol=0.01, sigmaHydMaxIter=500, sigmaHydRelax=0.8)
+        pair.append(c)
+    g, o = SolidModel(pair[0]), OracleSolid(pair[1])
+    sg, so = g.evolve(), o.evolve()
+    assert sg["converged"] and so["converged"], (sg, so)
+    assert rel_l2(g.get("D"), o.get("D")) < SOLVE_TOL
+    assert rel_l2(g.get("sigma"), o.get("sigma")) < SOLVE_TOL
+    assert rel_l2(g.get("sigmaHyd"), o.get("sigmaHyd")) < SOLVE_TOL
 
 
 # ---------------------------------------------------------------------------------------------
