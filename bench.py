@@ -8,15 +8,20 @@ synthetic hex cantilever: explicit RHS assembly, the f
 solve (relTol 0.1), boundary-condition evaluation, relaxation + residual reductions, least-squares
 gradient and the linearElastic stress update.  Default workload: 800x100x100 = 8.0 M cells; with N>1
 ranks the same mesh is cut into N x-slabs (decomposePar simple (N 1 1)) -> strong scaling.
+--workload notched_bar | neo_hookean: the finite-strain configurations (kernel rooflines of the J2 / neo-Hookean laws,
+the flux tensor and the non-orthogonal right-hand side at 8 M cells).
 
 value      outer iterations/s with all state resident in HBM (device-timed, max over ranks)
 e2e        the same metric through the host-facing call sequence with HOST buffers: state upload
            (D, D_old) from pinned memory, per step a traction upload + the residual read-back, and the
            download of D, gradD, sigma at the end (what the OpenFOAM plugin's evolve() does).
-roofline   dominant kernel = the 3-component fused SpMV (k_amul3) timed alone, inputs >> L2.
+roofline   dominant kernel = k_amg_step, the fine-level Chebyshev-Jacobi step of the GAMG K-cycle (a 3-component
+           SELL-32 SpMV + update, six launches per PCG iteration), timed alone, inputs >> L2; kernels.* holds every
+           other kernel of the step (spmv3 = k_amul3, the PCG's own SpMV: BASELINE.json's "SpMV HBM GB/s vs peak").
+parity     (every N) the decomposed run against the single-domain CPU oracle on a small beam, outside the timed region.
 cpu_baseline / --impl reference: the CPU oracle (oracle/, a restatement of the reference algorithm in
-           its own LDU face-loop form, PCG + DIC) -- the reference itself needs OpenFOAM, which is not
-           installable here.
+           its own LDU face-loop form, PCG + DIC) on the SAME workload and all host cores, measured, never
+           scaled -- the reference itself needs OpenFOAM, which is not installable here.
 """
 from __future__ import annotations
 
@@ -67,8 +72,8 @@ def parse():
 
 def ncu_traffic(kernel_prefix, n_cells):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the fine-level launch of a kernel, from the
-    committed ncu --set full capture (profiles/r1c_ncu_dram_traffic.json); None when the capture is of another workload."""
-    p = os.path.join(ROOT, "profiles", "r1c_ncu_dram_traffic.json")
+    committed ncu --set full capture (profiles/r2_ncu_dram_traffic.json); None when the capture is of another workload."""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_dram_traffic.json")
     try:
         with open(p) as f:
             t = json.load(f)
@@ -76,7 +81,7 @@ def ncu_traffic(kernel_prefix, n_cells):
             return None, None
         for name, launches in t["kernels"].items():
             if name.startswith(kernel_prefix):
-                return float(launches[0]["dram_bytes"]), "profiles/r1c_ncu_dram_traffic.json (" + name + ", launch %d)" % launches[0]["launch"]
+                return float(launches[0]["dram_bytes"]), "profiles/r2_ncu_dram_traffic.json (" + name + ", launch %d)" % launches[0]["launch"]
     except Exception:
         pass
     return None, None
@@ -360,7 +365,9 @@ def main():
     # face-loop kernels and the multi-rank V-cycle end in halo exchanges / all-gathers.
     peak, peak_src = peaks()
     kern = {}
-    names = ["spmv3", "spmv1", "pcg_p", "pcg_xr", "pcg_iter", "grad", "rhs", "law"]
+    names = ["spmv3", "spmv1", "pcg_p", "pcg_xr", "pcg_iter", "grad", "rhs", "law", "dot_reduce"]
+    if world > 1:
+        names.append("halo3")          # one processor-patch exchange of a 3-component field over peer memory
     gamg = None
     if args.precond.startswith("gamg"):
         names += ["gamg_vcycle", "gamg_step0"]
@@ -369,6 +376,23 @@ def main():
         ms_k, by = g.time_kernel(name, reps=20, flush_l2=False)
         kern[name] = dict(ms=ms_k, algo_bytes=by, gbs=by / (ms_k * 1e-3) / 1e9, frac=by / (ms_k * 1e-3) / 1e9 / peak)
     barrier()
+    # ---- not the headline: the same window with the fp32 preconditioner cycle (PCG recurrence, residuals and fields stay fp64;
+    # reported so that the cost of keeping the GAMG cycle in fp64 is on record)
+    mixed = None
+    if world == 1 and args.precond == "gamg" and args.workload == "cantilever":
+        ctl32 = K.Controls.from_buffer_copy(case.controls)
+        ctl32.gamgSinglePrecision = 1
+        g.set_controls(ctl32)
+        g.set("D", np.zeros((mesh.nCells, 3))); g.set("sigma", np.zeros((mesh.nCells, 6)))
+        g.initialise()
+        for _ in range(W_):
+            g.outer_iteration()
+        g.timer_start()
+        st32 = [g.outer_iteration()["nIterations"] for _ in range(K_)]
+        ms32 = g.timer_stop()
+        mixed = dict(value=K_ / (ms32 * 1e-3), unit="iter/s", ms_per_step=ms32 / K_,
+                     pcg_iterations_per_component=[float(x) for x in np.mean(np.array(st32), axis=0)],
+                     note="GAMG cycle in fp32 (gamgSinglePrecision), flexible PCG in fp64: same converged solution, not the headline number")
     g.close()
     parity = None if (args.no_parity or args.workload != "cantilever") else multi_gpu_parity(rank, world, local_rank, new_comm)
     if rank != 0:
@@ -403,6 +427,8 @@ def main():
         line["config"]["gamg"] = gamg
     if parity is not None:
         line["parity"] = parity
+    if mixed is not None:
+        line["fp32_preconditioner"] = mixed
 
     if world == 1 and not args.no_cpu_baseline and args.workload == "cantilever":
         # bounded sample of the SAME workload: two outer iterations of the full-size case after one warm-up (~30 s of CPU work)

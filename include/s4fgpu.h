@@ -320,7 +320,9 @@ enum {
     S4F_KERNEL_PCG_P = 6,      /* pA = rD rA + beta pA */
     S4F_KERNEL_PCG_XR = 7,     /* psi += alpha pA; rA -= alpha wA; residual sums */
     S4F_KERNEL_GAMG_VCYCLE = 8,/* one application of the GAMG preconditioner (all levels) */
-    S4F_KERNEL_GAMG_STEP0 = 9  /* the fine-level Chebyshev-Jacobi smoothing step of the V-cycle, alone */
+    S4F_KERNEL_GAMG_STEP0 = 9, /* the fine-level Chebyshev-Jacobi smoothing step of the V-cycle, alone */
+    S4F_KERNEL_HALO3 = 10,     /* one processor-patch halo exchange of a 3-component field (decomposed runs; peer memory) */
+    S4F_KERNEL_DOT_REDUCE = 11 /* a reducing kernel (z.r of the PCG) with the all-reduce fused into its last block */
 };
 int s4fgpu_time_kernel(s4fgpu_handle h, int kernel, int reps, int flushL2,
                        double* msPerLaunch, double* algoBytesPerLaunch);

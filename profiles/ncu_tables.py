@@ -3,8 +3,7 @@
 
     python profiles/ncu_tables.py gpurun_out/prof_r2.ncu-rep profiles/r2_ncu_full_table.md profiles/r2_ncu_dram_traffic.json "title" [cells]
 
-Reads `ncu -i <rep> --page raw --csv`; one row per profiled launch (last launch of every (kernel, grid) pair is kept:
-the earlier ones are the warm-up launches of s4fgpu_time_kernel)."""
+Reads `ncu -i <rep> --page raw --csv` (or that CSV itself); one row per profiled launch."""
 import csv
 import io
 import json
@@ -28,7 +27,11 @@ def to_float(x):
 def main():
     rep, md, js, title = sys.argv[1:5]
     cells = int(sys.argv[5]) if len(sys.argv) > 5 else None
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):          # already exported on the GPU box (the .ncu-rep files are too large to bring back)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    raw = raw[raw.index('"ID"'):] if '"ID"' in raw else raw
     rows = list(csv.reader(io.StringIO(raw)))
     head, units, body = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(head)}
@@ -45,17 +48,13 @@ def main():
         for key, _, _ in COLS:
             vals[key] = to_float(r[idx[key]]) * (unit_scale(key) if ("bytes" in key or "time" in key) else 1.0) if key in idx else float("nan")
         launches.append((name, grid, vals))
-    # keep the last launch of every (kernel, grid)
-    last = {}
-    for i, (name, grid, vals) in enumerate(launches):
-        last[(name, grid)] = i
-    keep = sorted(last.values())
+    keep = list(range(len(launches)))
     with open(md, "w") as f:
         f.write(f"# {title}\n\nReplayed, cold-cache launches under `ncu --set full --clock-control none`: counters and shares, not bench times.  Source report: {rep}.\n\n")
         f.write("| # | kernel | grid | " + " | ".join(c[1] for c in COLS) + " |\n|---|---|---|" + "---|" * len(COLS) + "\n")
         for i in keep:
             name, grid, v = launches[i]
-            short = name.split("(")[0]
+            short = name.split("(")[0].replace("void ", "").replace("<unnamed>::", "")
             cellsv = []
             for key, _, _ in COLS:
                 x = v[key]
@@ -69,7 +68,7 @@ def main():
     out = {"source": f"{rep}: {title}", "cells": cells, "kernels": {}}
     for i in keep:
         name, grid, v = launches[i]
-        short = name.split("(")[0]
+        short = name.split("(")[0].replace("void ", "").replace("<unnamed>::", "")
         out["kernels"].setdefault(short, []).append(dict(launch=i, grid=grid, time_ms=v["gpu__time_duration.sum"] * 1e-6,
                                                           dram_bytes=v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"]))
     with open(js, "w") as f:

@@ -2,8 +2,9 @@
 """Short driver for ncu: builds a case and launches every hot kernel a few times through the C-ABI timing entry
 (s4fgpu_time_kernel).
 
-    S4F_NO_GRAPH=1 ncu --set full --clock-control none --import-source on -k regex:'k_amg|k_kc|k_amul3|k_source|k_grad|k_pcg|k_law|k_tl' \
-        -c 260 -o gpurun_out/prof python profiles/prof_kernels.py 800,100,100 cantilever GAMG
+    S4F_NO_GRAPH=1 S4F_TIME_WARMUP=0 ncu --set full --clock-control none -k regex:'k_amg|k_kc|k_amul|k_source|k_grad|k_pcg|k_law|k_tl' \
+        -c 48 -o /tmp/prof python profiles/prof_kernels.py 800,100,100 cantilever GAMG
+    (S4F_TIME_WARMUP=0: one launch per kernel; the K-cycle comes last, its first ~35 launches are the two finest levels)
 
 workload: cantilever (linearElastic, orthogonal) | notched_bar (neoHookeanElasticMisesPlastic, non-orthogonal, total Lagrangian) |
 neo_hookean.  Numbers printed under ncu are NOT bench values."""

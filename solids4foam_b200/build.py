@@ -8,8 +8,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libs4fgpu.so")
-SOURCES = ["s4f_api.cu", "s4f_comm.cu", "s4f_geom.cu", "s4f_setup.cu", "s4f_pcg.cu", "s4f_fv.cu", "s4f_law.cu", "s4f_amg.cu", "s4f_pressure.cu", "s4f_uns.cu", "s4f_dic.cu"]
-HEADERS = ["s4f_ctx.h", "s4f_comm.h", "s4f_dev.cuh", os.path.join("..", "..", "include", "s4fgpu.h")]
+SOURCES = ["s4f_api.cu", "s4f_comm.cu", "s4f_geom.cu", "s4f_amg_setup.cu", "s4f_setup.cu", "s4f_pcg.cu", "s4f_fv.cu", "s4f_law.cu", "s4f_amg.cu", "s4f_pressure.cu", "s4f_uns.cu", "s4f_dic.cu"]
+HEADERS = ["s4f_ctx.h", "s4f_comm.h", "s4f_amg_setup.h", "s4f_dev.cuh", os.path.join("..", "..", "include", "s4fgpu.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=true",
          "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]

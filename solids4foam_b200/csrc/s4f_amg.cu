@@ -28,6 +28,7 @@
 #include <cstring>
 #include <memory>
 
+#include "s4f_amg_setup.h"
 #include "s4f_comm.h"
 #include "s4f_dev.cuh"
 
@@ -790,7 +791,11 @@ struct Hierarchy : S4fAmg {
         S4F_CHECK_CUDA(c, cudaMemcpyAsync(&hf, fail.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
         if (hf) { c->err = "GAMG refresh: coarse rows wider than expected"; return 1; }
-        // coarsest level: dense inverse again (<= 512 cells)
+        return invert_coarsest(c);
+    }
+
+    // dense inverse of the coarsest matrix from its device rows (<= 512 cells; host Cholesky)
+    int invert_coarsest(s4fgpu_ctx* c) {
         Level<T>& LC = *lv.back();
         const int n = LC.n;
         std::vector<int> sp(LC.nSlices + 1);
@@ -906,6 +911,71 @@ int build(s4fgpu_ctx* c, std::vector<HostLevel>& H) {
     S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
     A->bytesPerApply = A->bytes_per_apply();
     A->step0Bytes = A->lv[0]->nnz * (4 + sizeof(T)) + 0.125 * c->N + 3.0 * c->N * (8 + 3 * sizeof(T) + sizeof(T));   // col,a | b(fp64) x xprev diag in, x' out
+    c->amg = guard.release();
+    return 0;
+}
+
+// the hierarchy from levels built on the device (s4f_amg_setup.cu): rows are adopted (fp64) or converted (fp32)
+template <class T>
+int build_from_device(s4fgpu_ctx* c, std::vector<std::unique_ptr<AmgDevLevel>>& D) {
+    auto* A = new Hierarchy<T>();
+    std::unique_ptr<S4fAmg> guard(A);
+    A->deg = c->ctl.gamgSmootherDegree > 0 ? c->ctl.gamgSmootherDegree : 3;
+    A->cycle = c->ctl.gamgCycle;
+    A->omega = c->ctl.gamgOverCorrection > 0 ? c->ctl.gamgOverCorrection : 2.2;
+    A->omegaK = A->omega;
+    if (const char* e = getenv("S4F_GAMG_OMEGA_K")) A->omegaK = atof(e);
+    const double ratio = c->ctl.gamgSmootherRatio > 0 ? c->ctl.gamgSmootherRatio : 0.3;
+    const double lmax = 2.0, lmin = ratio * lmax;
+    A->theta = 0.5 * (lmax + lmin); A->delta = 0.5 * (lmax - lmin);
+    for (size_t l = 0; l < D.size(); l++) {
+        A->lv.emplace_back(new Level<T>());
+        Level<T>& L = *A->lv.back();
+        AmgDevLevel& S = *D[l];
+        int rc;
+        L.n = S.n; L.nGhost = 0; L.ld = S.ld; L.nSlices = S.nSlices; L.dist = false; L.nnz = (double)S.nnz;
+        if (l == 0) {
+            L.slicePtr = c->slicePtr.p; L.col = c->col.p;
+            if (sizeof(T) == sizeof(double)) L.a = reinterpret_cast<const T*>(c->eA.p);
+            else {
+                S4F_CHECK_CUDA(c, L.aB.alloc((size_t)c->nEntries, false));
+                k_amg_convert<T><<<(unsigned)((c->nEntries + 255) / 256), 256, 0, c->stream>>>(c->eA.p, L.aB.p, c->nEntries);
+                L.a = L.aB.p;
+            }
+            S4F_CHECK_CUDA(c, L.dg.alloc(3 * (size_t)L.ld));
+            k_amg_diag<T><<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->diagC.p, L.dg.p, c->N, c->ld, L.ld);
+            c->launches += 2;
+        } else {
+            L.slicePtrB.swap(S.slicePtr); L.colB.swap(S.col);
+            const size_t nE = S.a.n;
+            if (sizeof(T) == sizeof(double)) {
+                reinterpret_cast<DevBuf<double>&>(L.aB).swap(S.a);
+                reinterpret_cast<DevBuf<double>&>(L.dg).swap(S.dg);
+            } else {
+                S4F_CHECK_CUDA(c, L.aB.alloc(nE, false)); S4F_CHECK_CUDA(c, L.dg.alloc(3 * (size_t)L.ld, false));
+                k_amg_convert<T><<<(unsigned)((nE + 255) / 256), 256, 0, c->stream>>>(S.a.p, L.aB.p, (long long)nE);
+                k_amg_convert<T><<<(unsigned)((3 * (size_t)L.ld + 255) / 256), 256, 0, c->stream>>>(S.dg.p, L.dg.p, 3 * (long long)L.ld);
+                c->launches += 2;
+                S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+            }
+            L.slicePtr = L.slicePtrB.p; L.col = L.colB.p; L.a = L.aB.p;
+            L.childPtr.swap(S.childPtr); L.child.swap(S.child);
+        }
+        if (S.parent.n) L.parent.swap(S.parent);
+        if ((rc = A->alloc_work(c, L))) return rc;
+        A->sizes.push_back(L.n);
+        A->distributed.push_back(0);
+    }
+    if (A->lv.size() > 1) {
+        const size_t m = 3 * (size_t)A->lv[1]->ld;
+        S4F_CHECK_CUDA(c, A->kc1.alloc(m)); S4F_CHECK_CUDA(c, A->kv1.alloc(m)); S4F_CHECK_CUDA(c, A->kr.alloc(m)); S4F_CHECK_CUDA(c, A->kc2.alloc(m));
+        S4F_CHECK_CUDA(c, A->kS.alloc(1));
+    }
+    if (A->lv.back()->n > 4096) { c->err = "GAMG: agglomeration stalled above the size of the dense coarsest solve"; return 1; }
+    S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+    int rc = A->invert_coarsest(c); if (rc) return rc;
+    A->bytesPerApply = A->bytes_per_apply();
+    A->step0Bytes = A->lv[0]->nnz * (4 + sizeof(T)) + 0.125 * c->N + 3.0 * c->N * (8 + 3 * sizeof(T) + sizeof(T));
     c->amg = guard.release();
     return 0;
 }
@@ -1057,6 +1127,21 @@ int gather_level(s4fgpu_ctx* c, HostLevel& fine, const HostLevel& part, HostLeve
 int s4f_amg_setup(s4fgpu_ctx* c) {
     s4f_amg_destroy(c);
     const auto t0 = std::chrono::steady_clock::now();
+    // single rank: agglomeration and Galerkin products on the device (s4f_amg_setup.cu); S4F_AMG_HOST_SETUP=1 keeps the
+    // sequential host agglomeration (the one decomposed runs use per rank), for A/B comparison in the tests
+    if (c->nRanks == 1 && !getenv("S4F_AMG_HOST_SETUP")) {
+        std::vector<std::unique_ptr<AmgDevLevel>> D;
+        int rcd = s4f_amg_device_levels(c, D, 512, 3);
+        if (!rcd) rcd = c->ctl.gamgSinglePrecision ? build_from_device<float>(c, D) : build_from_device<double>(c, D);
+        if (!rcd) {
+            c->amg->setupSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            c->graphSerial++;
+            return 0;
+        }
+        fprintf(stderr, "libs4fgpu: GAMG device set-up not possible (%s); agglomerating on the host\n", c->err.c_str());
+        c->err.clear(); cudaGetLastError();
+        s4f_amg_destroy(c);
+    }
     const int N = c->N, F = c->F;
     std::vector<HostLevel> H(1);
     int rc;

@@ -498,7 +498,7 @@ int s4fgpu_time_kernel(s4fgpu_handle c, int kernel, int reps, int flushL2, doubl
     S4F_REQUIRE(c, c->geomSet && c->matrixValid, "time_kernel: initialise first");
     S4F_REQUIRE(c, reps > 0, "time_kernel: reps");
     if (kernel == S4F_KERNEL_SPMV1 || kernel == S4F_KERNEL_SPMV3 || kernel == S4F_KERNEL_PCG_ITER || kernel == S4F_KERNEL_PCG_P ||
-        kernel == S4F_KERNEL_PCG_XR)
+        kernel == S4F_KERNEL_PCG_XR || kernel == S4F_KERNEL_HALO3 || kernel == S4F_KERNEL_DOT_REDUCE)
         return s4f_time_pcg_kernels(c, kernel, reps, flushL2, msPerLaunch, algoBytesPerLaunch);
     return s4f_time_fv_kernels(c, kernel, reps, flushL2, msPerLaunch, algoBytesPerLaunch);
 }

@@ -53,6 +53,7 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr; n = 0;
     }
+    void swap(DevBuf& o) { T* tp = p; p = o.p; o.p = tp; size_t tn = n; n = o.n; o.n = tn; }
     cudaError_t alloc(size_t count, bool zero = true) {
         if (count == n && p) { return zero ? cudaMemset(p, 0, n * sizeof(T)) : cudaSuccess; }
         release();

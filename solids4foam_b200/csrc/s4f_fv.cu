@@ -951,7 +951,8 @@ int s4f_time_fv_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, double
     cudaEvent_t e0, e1;
     S4F_CHECK_CUDA(c, cudaEventCreate(&e0)); S4F_CHECK_CUDA(c, cudaEventCreate(&e1));
     double total = 0;
-    for (int r = -3; r < reps; r++) {
+    const int warm = getenv("S4F_TIME_WARMUP") ? atoi(getenv("S4F_TIME_WARMUP")) : 3;      // ncu runs set 0: one launch per kernel
+    for (int r = -warm; r < reps; r++) {
         if (flushL2) S4F_CHECK_CUDA(c, cudaMemsetAsync(c->flushBuf.p, 0, c->flushBuf.n * sizeof(double), c->stream));
         S4F_CHECK_CUDA(c, cudaEventRecord(e0, c->stream));
         int rc = 0;

@@ -901,7 +901,8 @@ int s4f_time_pcg_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, doubl
     cudaEvent_t e0, e1;
     S4F_CHECK_CUDA(c, cudaEventCreate(&e0)); S4F_CHECK_CUDA(c, cudaEventCreate(&e1));
     double total = 0;
-    for (int r = -3; r < reps; r++) {
+    const int warm = getenv("S4F_TIME_WARMUP") ? atoi(getenv("S4F_TIME_WARMUP")) : 3;      // ncu runs set 0: one launch per kernel
+    for (int r = -warm; r < reps; r++) {
         S4F_CHECK_CUDA(c, cudaMemcpyAsync(c->pcgS.p, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
         if (flushL2) S4F_CHECK_CUDA(c, cudaMemsetAsync(c->flushBuf.p, 0, c->flushBuf.n * sizeof(double), c->stream));
         S4F_CHECK_CUDA(c, cudaEventRecord(e0, c->stream));
@@ -910,6 +911,11 @@ int s4f_time_pcg_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, doubl
             c->launches++;
         } else if (kernel == S4F_KERNEL_SPMV3) {
             amul3(c, c->pA.p, c->wA.p, true, Pn, 1.0, 7);
+        } else if (kernel == S4F_KERNEL_HALO3) {
+            int rh = s4f_halo_exchange(c, c->pA.p, 3); if (rh) return rh;
+        } else if (kernel == S4F_KERNEL_DOT_REDUCE) {
+            k_pcg_dot_zr<<<s4f_grid(c->numSMs, N), S4F_BLOCK, 0, c->stream>>>(c->pA.p, c->rA.p, nullptr, N, ld, c->pcgS.p, Pn, 1.0, c->red());
+            c->launches++;
         } else if (kernel == S4F_KERNEL_PCG_P) {
             k_pcg_p<<<gridV2, S4F_BLOCK, 0, c->stream>>>(c->rDiagC.p, c->rA.p, c->pA.p, N, ld, c->pcgS.p);
             c->launches++;
@@ -935,7 +941,9 @@ int s4f_time_pcg_kernels(s4fgpu_ctx* c, int kernel, int reps, int flushL2, doubl
     const double spmv3 = 12.0 * nnz + (24 + 24 + 24 + 0.125) * N;             // a,col | diag, p, w, slicePtr
     const double pk = (24 + 24 + 24 + 24.0) * N;                             // r, rD, p in | p out
     const double xr = (24 * 5 + 24 * 2.0) * N;                               // x, r, p, w, rD in | x, r out
-    if (kernel == S4F_KERNEL_SPMV1) *bytesOut = 12.0 * nnz + (8 + 8 + 8 + 0.125) * N;
+    if (kernel == S4F_KERNEL_HALO3) *bytesOut = 2.0 * 3 * 8 * c->G;                  // values sent + received
+    else if (kernel == S4F_KERNEL_DOT_REDUCE) *bytesOut = 2.0 * 24 * N;
+    else if (kernel == S4F_KERNEL_SPMV1) *bytesOut = 12.0 * nnz + (8 + 8 + 8 + 0.125) * N;
     else if (kernel == S4F_KERNEL_SPMV3) *bytesOut = spmv3;
     else if (kernel == S4F_KERNEL_PCG_P) *bytesOut = pk;
     else if (kernel == S4F_KERNEL_PCG_XR) *bytesOut = xr;

@@ -17,7 +17,7 @@ import numpy as np
 from . import case as K
 from ._lib import lib
 
-KERNELS = dict(spmv1=0, spmv3=1, pcg_iter=2, grad=3, law=4, rhs=5, pcg_p=6, pcg_xr=7, gamg_vcycle=8, gamg_step0=9)
+KERNELS = dict(spmv1=0, spmv3=1, pcg_iter=2, grad=3, law=4, rhs=5, pcg_p=6, pcg_xr=7, gamg_vcycle=8, gamg_step0=9, halo3=10, dot_reduce=11)
 
 
 class SolidModel:
