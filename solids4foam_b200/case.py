@@ -302,8 +302,11 @@ def apply_case(lib, prefix: str, handle, case: SolidCase, check) -> None:
                         _iptr(pSize), _iptr(pKind), _iptr(pNbr), _iptr(fc), _iptr(solD)))
     arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in
             (m.C, m.V, m.Sf, m.magSf, m.Cf, m.weights, m.nonOrthDeltaCoeffs, m.nonOrthCorrVec, m.CnbrB)]
+    has_points = m.points is not None and m.faces is not None
+    if has_points and m.nRanks > 1:      # decomposed: the points first -- set_geometry lays out the point-neighbour ghosts with the rows
+        set_points(lib, prefix, handle, m, check)
     check(f("set_geometry")(handle, *[_dptr(a) for a in arrs]))
-    if m.points is not None and m.nRanks == 1:      # the point-based operators are single-rank (no point sync across processor patches yet)
+    if has_points and m.nRanks == 1:
         set_points(lib, prefix, handle, m, check)
     check(f("set_controls")(handle, C.byref(case.controls)))
     check(f("set_law")(handle, C.byref(case.law)))

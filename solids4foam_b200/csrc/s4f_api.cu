@@ -131,6 +131,7 @@ int s4fgpu_destroy(s4fgpu_handle c) {
     s4f_dic_destroy(c);
     s4f_solve_graphs_destroy(c);
     s4f_halo_plan_destroy(c->halo0); c->halo0 = nullptr;
+    s4f_halo_plan_destroy(c->haloX); c->haloX = nullptr;
     s4f_comm_destroy(c);
     if (c->comm) ncclCommDestroy(c->comm);
     if (c->hPcgS) cudaFreeHost(c->hPcgS);
@@ -177,6 +178,7 @@ int s4fgpu_set_mesh(s4fgpu_handle c, int nCells, int nInternalFaces, const int* 
     for (int b = 0; b < B; b++) S4F_REQUIRE(c, faceCells[b] >= 0 && faceCells[b] < nCells, "set_mesh: faceCells out of range");
     c->bcKind.assign(nPatches, S4F_BC_SOLID_TRACTION);
     s4f_amg_destroy(c); c->amgRefresh = false;          // another graph: the aggregates go with it
+    c->nPoints = 0; c->X = 0; c->extPtr.clear();          // another mesh: its points arrive with the next set_points
     c->meshSet = true; c->geomSet = false; c->matrixValid = false; c->nGlobalCells = -1;
     return 0;
 }
@@ -192,8 +194,13 @@ int s4fgpu_set_geometry(s4fgpu_handle c, const double* C, const double* V, const
     // a second call on the same mesh is a geometry refresh after mesh motion (nonLinGeomUpdatedLagSolid.C:360-374 ->
     // solidModel::moveMesh): fields, boundary data and the law history stay, everything derived from geometry is rebuilt
     const bool again = c->geomSet;
-    int rc = s4f_build_rows(c); if (rc) return rc;
+    int rc = 0;
+    // decomposed mesh with points: the values of other ranks' cells and boundary faces at shared points get slots of their
+    // own in the field index space, so they must be known before the rows fix the leading dimension
+    if (c->nRanks > 1 && c->nPoints > 0 && (rc = s4f_build_point_ghosts(c))) return rc;
+    rc = s4f_build_rows(c); if (rc) return rc;
     rc = s4f_alloc_fields(c); if (rc) return rc;
+    if (c->nRanks > 1 && c->nPoints > 0 && (rc = s4f_build_point_weights(c, c->hPoints.data()))) return rc;
     // host geometry copies are only needed to build the rows (cell centres stay for the vol->point weights)
     std::vector<double>().swap(c->hSf); std::vector<double>().swap(c->hCf); std::vector<double>().swap(c->hCorr);
     std::vector<double>().swap(c->hW); std::vector<double>().swap(c->hNod);
@@ -406,14 +413,19 @@ int s4fgpu_evolve(s4fgpu_handle c, s4fgpu_stats* st) {
 
 int s4fgpu_set_points(s4fgpu_handle c, int nPoints, const double* points, const int* faceVertsPtr, const int* faceVerts) {
     S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
-    S4F_REQUIRE(c, c->geomSet, "set_points: call set_geometry first");
+    S4F_REQUIRE(c, c->meshSet, "set_points: call set_mesh first");
     S4F_REQUIRE(c, nPoints > 0 && points && faceVertsPtr && faceVerts, "set_points: bad arguments");
+    // single rank: after set_geometry (the weights are built here).  Decomposed: BEFORE set_geometry, which then lays out
+    // the point-neighbour ghosts with the rows and builds the weights (s4f_build_point_ghosts)
+    S4F_REQUIRE(c, c->nRanks > 1 ? (!c->geomSet || nPoints == c->nPoints) : c->geomSet,
+                c->nRanks > 1 ? "set_points: on a decomposed mesh call set_points before set_geometry" : "set_points: call set_geometry first");
     const int nF = c->F + c->B;
     c->nPoints = nPoints;
     c->hFvPtr.assign(faceVertsPtr, faceVertsPtr + nF + 1);
     c->hFv.assign(faceVerts, faceVerts + faceVertsPtr[nF]);
     c->hPoints.assign(points, points + 3 * (size_t)nPoints);
     c->gValid = false; c->unsValid = false;
+    if (c->nRanks > 1) return 0;
     return s4f_build_point_weights(c, points);
 }
 

@@ -129,10 +129,18 @@ struct s4fgpu_ctx {
     DevBuf<PeerRed> redDev;               // device descriptor with every rank's mailbox pointers (s4f_comm.cu)
     std::vector<void*> ipcOpened;
     struct S4fHaloPlan* halo0 = nullptr;  // processor-patch halo of the fine mesh
+    struct S4fHaloPlan* haloX = nullptr;  // point-neighbour ghosts (cells and boundary faces of other ranks at shared points)
     long long graphSerial = 0;            // bumped whenever anything a captured solve points at is rebuilt
 
     // ---- host copy of the mesh description ----
     int N = 0, F = 0, B = 0, G = 0, nPatches = 0;
+    // decomposed meshes with points: X slots after the boundary slots hold the values of the cells and boundary faces of
+    // OTHER ranks that share a point with this rank's cells (s4f_build_point_ghosts); filled by haloX before every
+    // operator with a point stencil.  extPtr/extSlot/extCtr/extIsB: per local point those slots, their centres, cell or face.
+    int X = 0;
+    int xOff() const { return N + G + B; }
+    std::vector<int> extPtr, extSlot; std::vector<double> extCtr; std::vector<char> extIsB;
+    std::vector<double> extSymN; std::vector<int> extFixAxis;      // per point: a symmetry-plane normal / fixed axis known to another rank only
     int ld = 0;                       // leading dimension of vol-field component arrays (>= N+G+B)
     std::vector<int> own, nei, faceCells, pStart, pSize, pKind, pNbr, bcKind;
     int solD[3] = {1, 1, 1};
@@ -331,7 +339,9 @@ void s4f_amg_destroy(s4fgpu_ctx* c);
 int s4f_amg_distributed_levels(s4fgpu_ctx* c);
 int s4f_amg_info(s4fgpu_ctx* c, int* nLevels, int* sizes, int maxLevels, double* bytesPerApply, double* setupSeconds);
 int s4f_download_upper(s4fgpu_ctx* c, double* hostUpper);           // lduMatrix upper() [F]
-int s4f_build_point_stencil(s4fgpu_ctx* c);                          // rows of the pointCellsLeastSquares gradient (s4f_setup.cu)
+int s4f_build_point_stencil(s4fgpu_ctx* c);                         // rows of the pointCellsLeastSquares gradient (s4f_setup.cu)
+int s4f_build_point_ghosts(s4fgpu_ctx* c);                          // decomposed meshes: collective, from set_geometry
+int s4f_point_ghost_exchange(s4fgpu_ctx* c, double* field, int ncomp);
 int s4f_build_point_weights(s4fgpu_ctx* c, const double* points);   // vol->point CSR + weights (s4f_setup.cu)
 int s4f_interpolate_to_points(s4fgpu_ctx* c, const double* field3, const double* grad9 /* null: patch mode */, double* hostOut);
 int s4f_grad_calculated(s4fgpu_ctx* c, const double* X, double* gradOut);   // fvc::grad of a field with calculated patches

@@ -851,6 +851,7 @@ int s4f_grad(s4fgpu_ctx* c) {
         k_grad<true><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eSf.p, c->eW.p, c->D.p, c->rV.p, c->gradD.p, c->N, c->ld, c->nEntries, c->nSlices);
     else {
         if (c->pointCellsGrad() && !c->gValid) { int rc = s4f_build_point_stencil(c); if (rc) return rc; }
+        if (c->pointCellsGrad()) { int rc = s4f_point_ghost_exchange(c, c->D.p, 3); if (rc) return rc; }
         k_grad<false><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->gradSlicePtr(), c->gradCol(), c->gradLs(), c->eW.p, c->D.p, c->rV.p, c->gradD.p, c->N, c->ld, c->gradNE(), c->nSlices);
     }
     c->launches++;
@@ -880,6 +881,7 @@ int s4f_grad_calculated_interior(s4fgpu_ctx* c, const double* X, double* gradOut
         k_grad<true><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eSf.p, c->eW.p, X, c->rV.p, gradOut, c->N, c->ld, c->nEntries, c->nSlices);
     else {
         if (c->pointCellsGrad() && !c->gValid) { int rc = s4f_build_point_stencil(c); if (rc) return rc; }
+        if (c->pointCellsGrad()) { int rc = s4f_point_ghost_exchange(c, const_cast<double*>(X), 3); if (rc) return rc; }
         k_grad<false><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->gradSlicePtr(), c->gradCol(), c->gradLs(), c->eW.p, X, c->rV.p, gradOut, c->N, c->ld, c->gradNE(), c->nSlices);
     }
     c->launches++;
@@ -897,6 +899,7 @@ int s4f_grad_calculated(s4fgpu_ctx* c, const double* X, double* gradOut) {
         k_grad<true><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eSf.p, c->eW.p, X, c->rV.p, gradOut, c->N, c->ld, c->nEntries, c->nSlices);
     else {
         if (c->pointCellsGrad() && !c->gValid) { int rc = s4f_build_point_stencil(c); if (rc) return rc; }
+        if (c->pointCellsGrad()) { int rc = s4f_point_ghost_exchange(c, const_cast<double*>(X), 3); if (rc) return rc; }
         k_grad<false><<<gridM, S4F_BLOCK, 0, c->stream>>>(c->gradSlicePtr(), c->gradCol(), c->gradLs(), c->eW.p, X, c->rV.p, gradOut, c->N, c->ld, c->gradNE(), c->nSlices);
     }
     c->launches++;

@@ -283,6 +283,7 @@ int s4f_refresh_host_geometry(s4fgpu_ctx* c) {
 int s4f_move_points_device(s4fgpu_ctx* c, const double* hostPointDD) {
     const int N = c->N, F = c->F, B = c->B, nF = F + B, nP = c->nPoints, ld = c->ld;
     if (nP == 0) { c->err = "move_points: call set_points first"; return 1; }
+    if (c->nRanks > 1) { c->err = "move_points: decomposed meshes move on the host (set_points, then set_geometry, on every rank)"; return 1; }
     for (int p = 0; p < c->nPatches; p++)
         if (c->pKind[p] == S4F_PATCH_EMPTY) { c->err = "move_points: meshes with empty patches (2-D cases) move on the host (set_geometry / set_points)"; return 1; }
     if (c->eFaceS.n != (size_t)std::max<long long>(c->nEntries, 1)) { int rc = build_entry_faces(c); if (rc) return rc; }

@@ -183,6 +183,7 @@ int s4f_pressure_smooth(s4fgpu_ctx* c) {
         k_grad_scalar<true><<<gridR, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eSf.p, c->eW.p, c->sigmaHyd.p, c->rV.p, c->gradP.p, N, ld, c->nEntries, c->nSlices);
     else {
         if (c->pointCellsGrad() && !c->gValid) { int rcg = s4f_build_point_stencil(c); if (rcg) return rcg; }
+        if (c->pointCellsGrad() && (rc = s4f_point_ghost_exchange(c, c->sigmaHyd.p, 1))) return rc;
         k_grad_scalar<false><<<gridR, S4F_BLOCK, 0, c->stream>>>(c->gradSlicePtr(), c->gradCol(), c->gradLs(), c->eW.p, c->sigmaHyd.p, c->rV.p, c->gradP.p, N, ld, c->gradNE(), c->nSlices);
     }
     c->launches++;

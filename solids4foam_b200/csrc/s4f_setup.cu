@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
 
 #include "s4f_comm.h"
 #include "s4f_dev.cuh"
@@ -64,6 +65,199 @@ int s4f_soa_to_aos(s4fgpu_ctx* c, const double* devSoA, double* hostAoS, int cou
     return 0;
 }
 
+// symmetry-plane data of the points (shared by the point-ghost builder and the vol->point weights): hN = the plane normal
+// at the points of a symmetryPlane patch (symmetryPlanePolyPatch::n(): the normalised sum of the patch's face areas), fixAxis
+// = the coordinate such a plane fixes when it is aligned with an axis (solidModel::moveMesh, solidModel.C:2040-2080).
+static void point_symmetry(const s4fgpu_ctx* c, const double* bSf, std::vector<double>& hN, std::vector<int>& fixAxis) {
+    const int F = c->F, nP = c->nPoints;
+    hN.assign(3 * (size_t)std::max(nP, 1), 0.0);
+    fixAxis.assign(std::max(nP, 1), -1);
+    for (int ip = 0; ip < c->nPatches; ip++) {
+        if (c->pKind[ip] != S4F_PATCH_SYMMETRY || c->pSize[ip] == 0) continue;
+        double n[3] = {0, 0, 0};
+        for (int i = 0; i < c->pSize[ip]; i++) for (int q = 0; q < 3; q++) n[q] += bSf[3 * (size_t)(c->pStart[ip] + i) + q];
+        const double m = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        std::vector<double> pn(3 * (size_t)nP, 0.0); std::vector<char> on(nP, 0);
+        for (int i = 0; i < c->pSize[ip]; i++) {
+            const int b = c->pStart[ip] + i;
+            const double* sf = &bSf[3 * (size_t)b];
+            const double ms = std::sqrt(sf[0] * sf[0] + sf[1] * sf[1] + sf[2] * sf[2]);
+            for (int j = c->hFvPtr[F + b]; j < c->hFvPtr[F + b + 1]; j++) {
+                const int p = c->hFv[j]; on[p] = 1;
+                for (int q = 0; q < 3; q++) { hN[3 * (size_t)p + q] = n[q] / m; pn[3 * (size_t)p + q] += sf[q] / ms; }
+            }
+        }
+        // the average of the point normals (each the normalised sum of the unit normals of its patch faces)
+        double avg[3] = {0, 0, 0}; int cntP = 0;
+        for (int p = 0; p < nP; p++) if (on[p]) {
+            const double* v = &pn[3 * (size_t)p];
+            const double mv = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+            for (int q = 0; q < 3; q++) avg[q] += v[q] / mv;
+            cntP++;
+        }
+        for (int ax = 0; ax < 3; ax++)
+            if (std::fabs(avg[ax] / cntP) > 0.95) { for (int p = 0; p < nP; p++) if (on[p]) fixAxis[p] = ax; break; }
+    }
+}
+
+// Decomposed meshes: the operators with a point stencil (pointCellsLeastSquares gradient, vol->point interpolation, the
+// uns face gradients) need, at the points of the processor patches, the cells and the boundary faces of the OTHER ranks
+// around the same point -- also of ranks that touch this one only along an edge or at a corner.  OpenFOAM does this with
+// globalMeshData / syncTools point synchronisation of partial sums; here every rank holds those remote values in X
+// extra slots behind its boundary slots (one peer-memory exchange, haloX, fills them) and evaluates the complete stencil
+// itself: no partial sums, the same summation on every rank that shares the point.
+//   1. every rank publishes, per processor-patch point: coordinates, the local cells around it with their centres, the
+//      local (non-processor) boundary faces around it with their centres, its symmetry-plane data;
+//   2. points are identified across ranks by their coordinates, bit for bit (processor patches are written from one set
+//      of points; a mismatch is an error, not a tolerance);
+//   3. requests go back (which of your cells / boundary slots I need), giving the send lists of the exchange plan.
+// Collective; called from set_geometry, before the rows are laid out, because X enters the leading dimension.
+int s4f_build_point_ghosts(s4fgpu_ctx* c) {
+    const int N = c->N, F = c->F, B = c->B, nP = c->nPoints;
+    s4f_halo_plan_destroy(c->haloX); c->haloX = nullptr;
+    c->X = 0; c->extPtr.assign(nP + 1, 0); c->extSlot.clear(); c->extCtr.clear(); c->extIsB.clear();
+    c->extSymN.assign(3 * (size_t)std::max(nP, 1), 0.0); c->extFixAxis.assign(std::max(nP, 1), -1);
+    if (c->nRanks <= 1 || nP == 0) return 0;
+    int G = 0;
+    for (int ip = 0; ip < c->nPatches; ip++) if (c->pKind[ip] == S4F_PATCH_PROCESSOR) G += c->pSize[ip];
+    const int bOff = N + G, xOff = N + G + B;
+    // local point -> cells / boundary faces, for the processor-patch points only
+    std::vector<char> isProc(nP, 0);
+    for (int ip = 0; ip < c->nPatches; ip++) {
+        if (c->pKind[ip] != S4F_PATCH_PROCESSOR) continue;
+        for (int i = 0; i < c->pSize[ip]; i++) {
+            const int b = c->pStart[ip] + i;
+            for (int j = c->hFvPtr[F + b]; j < c->hFvPtr[F + b + 1]; j++) isProc[c->hFv[j]] = 1;
+        }
+    }
+    std::vector<int> procPts, procIdx(nP, -1);
+    for (int p = 0; p < nP; p++) if (isProc[p]) { procIdx[p] = (int)procPts.size(); procPts.push_back(p); }
+    std::vector<std::vector<int>> pc(procPts.size()), pb(procPts.size());
+    auto add = [](std::vector<int>& v, int x) { if (std::find(v.begin(), v.end(), x) == v.end()) v.push_back(x); };
+    for (int f = 0; f < F + B; f++) for (int j = c->hFvPtr[f]; j < c->hFvPtr[f + 1]; j++) {
+        const int k = procIdx[c->hFv[j]];
+        if (k < 0) continue;
+        add(pc[k], f < F ? c->own[f] : c->faceCells[f - F]);
+        if (f < F) add(pc[k], c->nei[f]);
+    }
+    for (int ip = 0; ip < c->nPatches; ip++) {
+        if (c->pKind[ip] == S4F_PATCH_PROCESSOR) continue;
+        for (int i = 0; i < c->pSize[ip]; i++) {
+            const int b = c->pStart[ip] + i;
+            for (int j = c->hFvPtr[F + b]; j < c->hFvPtr[F + b + 1]; j++) { const int k = procIdx[c->hFv[j]]; if (k >= 0) pb[k].push_back(b); }
+        }
+    }
+    std::vector<double> symN; std::vector<int> fixAxis;
+    point_symmetry(c, c->hSf.data() + 3 * (size_t)F, symN, fixAxis);
+    // 1. publish
+    std::vector<double> rec;
+    for (size_t k = 0; k < procPts.size(); k++) {
+        const int p = procPts[k];
+        for (int q = 0; q < 3; q++) rec.push_back(c->hPoints[3 * (size_t)p + q] + 0.0);        // + 0.0: -0 -> +0
+        rec.push_back((double)pc[k].size()); rec.push_back((double)pb[k].size());
+        for (int q = 0; q < 3; q++) rec.push_back(symN[3 * (size_t)p + q]);
+        rec.push_back((double)fixAxis[p]);
+        for (int cell : pc[k]) { rec.push_back((double)cell); for (int q = 0; q < 3; q++) rec.push_back(c->hC[3 * (size_t)cell + q]); }
+        for (int b : pb[k]) { rec.push_back((double)b); for (int q = 0; q < 3; q++) rec.push_back(c->hCf[3 * (size_t)(F + b) + q]); }
+    }
+    std::vector<std::vector<char>> all;
+    int rc = s4f_allgatherv_host(c, rec.data(), rec.size() * sizeof(double), all); if (rc) return rc;
+    // 2. match by coordinates
+    struct Key { unsigned long long a, b, d; bool operator<(const Key& o) const { return a != o.a ? a < o.a : (b != o.b ? b < o.b : d < o.d); } };
+    auto keyOf = [](const double* x) { Key k; std::memcpy(&k.a, x, 8); std::memcpy(&k.b, x + 1, 8); std::memcpy(&k.d, x + 2, 8); return k; };
+    std::map<Key, int> mine;
+    for (size_t k = 0; k < procPts.size(); k++) {
+        const double x[3] = {c->hPoints[3 * (size_t)procPts[k]] + 0.0, c->hPoints[3 * (size_t)procPts[k] + 1] + 0.0, c->hPoints[3 * (size_t)procPts[k] + 2] + 0.0};
+        mine[keyOf(x)] = (int)k;
+    }
+    struct Ext { int rank, id; bool isB; double ctr[3]; };
+    std::vector<std::vector<Ext>> ext(procPts.size());
+    for (int r = 0; r < c->nRanks; r++) {
+        if (r == c->rank) continue;
+        const double* d = (const double*)all[r].data();
+        const size_t nd = all[r].size() / sizeof(double);
+        for (size_t i = 0; i < nd;) {
+            const int nC = (int)d[i + 3], nB = (int)d[i + 4];
+            auto it = mine.find(keyOf(d + i));
+            if (it != mine.end()) {
+                const int k = it->second, p = procPts[k];
+                if (d[i + 5] != 0 || d[i + 6] != 0 || d[i + 7] != 0) for (int q = 0; q < 3; q++) c->extSymN[3 * (size_t)p + q] = d[i + 5 + q];
+                if ((int)d[i + 8] >= 0) c->extFixAxis[p] = (int)d[i + 8];
+                for (int j = 0; j < nC + nB; j++) {
+                    const double* e = d + i + 9 + 4 * (size_t)j;
+                    Ext x; x.rank = r; x.id = (int)e[0]; x.isB = j >= nC; x.ctr[0] = e[1]; x.ctr[1] = e[2]; x.ctr[2] = e[3];
+                    ext[k].push_back(x);
+                }
+            }
+            i += 9 + 4 * (size_t)(nC + nB);
+        }
+    }
+    for (size_t k = 0; k < procPts.size(); k++)
+        if (ext[k].empty()) { c->err = "point ghosts: a processor-patch point has no counterpart on any other rank (the points of processor patches must coincide bit for bit)"; return 1; }
+    // 3. slots: per source rank its cells (ascending), then its boundary faces (ascending)
+    std::vector<std::vector<int>> needC(c->nRanks), needB(c->nRanks);
+    for (auto& v : ext) for (auto& x : v) (x.isB ? needB : needC)[x.rank].push_back(x.id);
+    std::vector<int> baseC(c->nRanks, 0), baseB(c->nRanks, 0);
+    int X = 0;
+    std::vector<int> req;                                   // [dest, nC, nB, ids...] per source rank
+    for (int r = 0; r < c->nRanks; r++) {
+        for (auto* v : {&needC[r], &needB[r]}) { std::sort(v->begin(), v->end()); v->erase(std::unique(v->begin(), v->end()), v->end()); }
+        baseC[r] = X; X += (int)needC[r].size();
+        baseB[r] = X; X += (int)needB[r].size();
+        if (needC[r].empty() && needB[r].empty()) continue;
+        req.push_back(r); req.push_back((int)needC[r].size()); req.push_back((int)needB[r].size());
+        req.insert(req.end(), needC[r].begin(), needC[r].end()); req.insert(req.end(), needB[r].begin(), needB[r].end());
+    }
+    std::vector<std::vector<char>> allReq;
+    rc = s4f_allgatherv_host(c, req.data(), req.size() * sizeof(int), allReq); if (rc) return rc;
+    std::vector<std::vector<int>> sendTo(c->nRanks);         // index-space positions of what rank r wants from me
+    for (int r = 0; r < c->nRanks; r++) {
+        if (r == c->rank) continue;
+        const int* q = (const int*)allReq[r].data();
+        const size_t nq = allReq[r].size() / sizeof(int);
+        for (size_t i = 0; i < nq;) {
+            const int dest = q[i], nC = q[i + 1], nB = q[i + 2];
+            if (dest == c->rank) {
+                for (int j = 0; j < nC; j++) {
+                    if (q[i + 3 + j] < 0 || q[i + 3 + j] >= N) { c->err = "point ghosts: a requested cell is out of range"; return 1; }
+                    sendTo[r].push_back(q[i + 3 + j]);
+                }
+                for (int j = 0; j < nB; j++) {
+                    if (q[i + 3 + nC + j] < 0 || q[i + 3 + nC + j] >= B) { c->err = "point ghosts: a requested boundary face is out of range"; return 1; }
+                    sendTo[r].push_back(bOff + q[i + 3 + nC + j]);
+                }
+            }
+            i += 3 + (size_t)nC + nB;
+        }
+    }
+    std::vector<int> nbrRank, sendCount, recvCount, sendCells;
+    for (int r = 0; r < c->nRanks; r++) {
+        const int nr = (int)(needC[r].size() + needB[r].size()), ns = (int)sendTo[r].size();
+        if (nr == 0 && ns == 0) continue;
+        nbrRank.push_back(r); sendCount.push_back(ns); recvCount.push_back(nr);
+        sendCells.insert(sendCells.end(), sendTo[r].begin(), sendTo[r].end());
+    }
+    rc = s4f_halo_plan_create_asym(c, nbrRank, sendCount, recvCount, sendCells, 9, &c->haloX); if (rc) return rc;
+    // per local point: the slots of its remote cells / faces
+    c->X = X;
+    for (int p = 0; p < nP; p++) {
+        c->extPtr[p] = (int)c->extSlot.size();
+        const int k = procIdx[p];
+        if (k < 0) continue;
+        for (const Ext& x : ext[k]) {
+            const std::vector<int>& v = x.isB ? needB[x.rank] : needC[x.rank];
+            const int pos = (int)(std::lower_bound(v.begin(), v.end(), x.id) - v.begin());
+            const int slot = xOff + (x.isB ? baseB : baseC)[x.rank] + pos;
+            if (std::find(c->extSlot.begin() + c->extPtr[p], c->extSlot.end(), slot) != c->extSlot.end()) continue;
+            c->extSlot.push_back(slot); c->extIsB.push_back(x.isB ? 1 : 0);
+            for (int q = 0; q < 3; q++) c->extCtr.push_back(x.ctr[q]);
+        }
+    }
+    c->extPtr[nP] = (int)c->extSlot.size();
+    c->graphSerial++;
+    return 0;
+}
+
 int s4f_build_rows(s4fgpu_ctx* c) {
     const int N = c->N, F = c->F, B = c->B;
     // ---- ghosts: one per processor-patch face, in patch order ----
@@ -85,7 +279,7 @@ int s4f_build_rows(s4fgpu_ctx* c) {
     }
     c->G = G;
     const int bOff = N + G;
-    c->ld = ((N + G + B + 31) / 32) * 32;
+    c->ld = ((N + G + B + c->X + 31) / 32) * 32;           // X: point-neighbour ghosts of a decomposed mesh (s4f_build_point_ghosts)
     if (c->ld == 0) c->ld = 32;
 
     // ---- rows: lower neighbours, upper neighbours, boundary/processor faces ----
@@ -384,7 +578,13 @@ int s4f_build_point_stencil(s4fgpu_ctx* c) {
     const int N = c->N, F = c->F, B = c->B, nP = c->nPoints, bOff = c->bOff();
     if (nP == 0) { c->err = "pointCellsLeastSquares needs the mesh points (s4fgpu_set_points)"; return 1; }
     if (c->hostGeomStale) { int rg = s4f_refresh_host_geometry(c); if (rg) return rg; }
-    if (c->nRanks > 1) { c->err = "pointCellsLeastSquares is not available on decomposed meshes yet"; return 1; }
+    if (c->nRanks > 1 && c->extPtr.size() != (size_t)nP + 1) {
+        c->err = "pointCellsLeastSquares on a decomposed mesh: call s4fgpu_set_points before s4fgpu_set_geometry (the point-neighbour ghosts are laid out with the rows)";
+        return 1;
+    }
+    const int xOff = c->xOff();
+    const bool ext = c->nRanks > 1;
+    // stencil entries are positions in the field index space: cell < N, boundary slot bOff + b, remote cell/face >= xOff
     std::vector<std::vector<int>> pc(nP), pb(nP), cellPts(N);
     auto add = [](std::vector<int>& v, int x) { if (std::find(v.begin(), v.end(), x) == v.end()) v.push_back(x); };
     for (int f = 0; f < F + B; f++) for (int j = c->hFvPtr[f]; j < c->hFvPtr[f + 1]; j++) {
@@ -397,15 +597,21 @@ int s4f_build_point_stencil(s4fgpu_ctx* c) {
         if (c->pKind[ip] == S4F_PATCH_PROCESSOR) continue;
         for (int i = 0; i < c->pSize[ip]; i++) {
             const int b = c->pStart[ip] + i;
-            for (int j = c->hFvPtr[F + b]; j < c->hFvPtr[F + b + 1]; j++) pb[c->hFv[j]].push_back(b);
+            for (int j = c->hFvPtr[F + b]; j < c->hFvPtr[F + b + 1]; j++) pb[c->hFv[j]].push_back(bOff + b);
         }
+    }
+    std::vector<double> xCtr;                       // centre of every extra slot (a slot may be listed at several points)
+    if (ext) {
+        xCtr.assign(3 * (size_t)std::max(c->X, 1), 0.0);
+        for (size_t e = 0; e < c->extSlot.size(); e++) for (int q = 0; q < 3; q++) xCtr[3 * (size_t)(c->extSlot[e] - xOff) + q] = c->extCtr[3 * e + q];
     }
     std::vector<int> rowPtr(N + 1, 0), slot; std::vector<double> ls[3];
     for (int i = 0; i < N; i++) {
         std::vector<int> st;
         for (int p : cellPts[i]) {
             for (int cc : pc[p]) if (cc != i) add(st, cc);
-            for (int b : pb[p]) add(st, N + b);
+            for (int b : pb[p]) add(st, b);
+            if (ext) for (int e = c->extPtr[p]; e < c->extPtr[p + 1]; e++) add(st, c->extSlot[e]);
         }
         std::sort(st.begin(), st.end());
         double dd[6] = {0, 0, 0, 0, 0, 0};
@@ -413,7 +619,7 @@ int s4f_build_point_stencil(s4fgpu_ctx* c) {
         std::vector<double> dl(3 * st.size());
         const double* Ci = &c->hC[3 * (size_t)i];
         for (size_t k = 0; k < st.size(); k++) {
-            const double* x = st[k] < N ? &c->hC[3 * (size_t)st[k]] : &c->hCfB[3 * (size_t)(st[k] - N)];
+            const double* x = st[k] < N ? &c->hC[3 * (size_t)st[k]] : (st[k] >= xOff ? &xCtr[3 * (size_t)(st[k] - xOff)] : &c->hCfB[3 * (size_t)(st[k] - bOff)]);
             const double d[3] = {x[0] - Ci[0], x[1] - Ci[1], x[2] - Ci[2]};
             const double r = 1.0 / (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
             dd[0] += r * d[0] * d[0]; dd[1] += r * d[0] * d[1]; dd[2] += r * d[0] * d[2];
@@ -424,7 +630,7 @@ int s4f_build_point_stencil(s4fgpu_ctx* c) {
         if (!c->solD[0]) iv[0] -= 1; if (!c->solD[1]) iv[3] -= 1; if (!c->solD[2]) iv[5] -= 1;
         for (size_t k = 0; k < st.size(); k++) {
             const double* d = &dl[3 * k];
-            slot.push_back(st[k] < N ? st[k] : bOff + (st[k] - N));
+            slot.push_back(st[k]);
             ls[0].push_back(iv[0] * d[0] + iv[1] * d[1] + iv[2] * d[2]);
             ls[1].push_back(iv[1] * d[0] + iv[3] * d[1] + iv[4] * d[2]);
             ls[2].push_back(iv[2] * d[0] + iv[4] * d[1] + iv[5] * d[2]);
@@ -462,9 +668,13 @@ int s4f_build_point_stencil(s4fgpu_ctx* c) {
 }
 
 int s4f_build_point_weights(s4fgpu_ctx* c, const double* points) {
-    const int N = c->N, F = c->F, B = c->B, nP = c->nPoints, bOff = c->bOff();
+    const int N = c->N, F = c->F, B = c->B, nP = c->nPoints, bOff = c->bOff(), xOff = c->xOff();
     if (c->hostGeomStale) { int rg = s4f_refresh_host_geometry(c); if (rg) return rg; }
-    if (c->nRanks > 1) { c->err = "set_points: vol->point interpolation is not available on decomposed meshes yet"; return 1; }
+    const bool ext = c->nRanks > 1;
+    if (ext && c->extPtr.size() != (size_t)nP + 1) {
+        c->err = "set_points on a decomposed mesh: call s4fgpu_set_points before s4fgpu_set_geometry (the point-neighbour ghosts are laid out with the rows)";
+        return 1;
+    }
     std::vector<std::vector<int>> pc(nP), pb(nP);
     auto add = [](std::vector<int>& v, int x) { if (std::find(v.begin(), v.end(), x) == v.end()) v.push_back(x); };
     for (int f = 0; f < F + B; f++) for (int j = c->hFvPtr[f]; j < c->hFvPtr[f + 1]; j++) {
@@ -473,45 +683,29 @@ int s4f_build_point_weights(s4fgpu_ctx* c, const double* points) {
         add(pc[p], f < F ? c->own[f] : c->faceCells[f - F]);
         if (f < F) add(pc[p], c->nei[f]);
     }
-    std::vector<double> hN(3 * (size_t)std::max(nP, 1), 0.0);
-    std::vector<int> fixAxis(std::max(nP, 1), -1);
     for (int ip = 0; ip < c->nPatches; ip++) {
         if (c->pKind[ip] == S4F_PATCH_PROCESSOR) continue;
-        double n[3] = {0, 0, 0};
         for (int i = 0; i < c->pSize[ip]; i++) {
             const int b = c->pStart[ip] + i;
-            for (int j = c->hFvPtr[F + b]; j < c->hFvPtr[F + b + 1]; j++) pb[c->hFv[j]].push_back(b);
-            for (int q = 0; q < 3; q++) n[q] += c->hBSfHost[3 * (size_t)b + q];
-        }
-        if (c->pKind[ip] == S4F_PATCH_SYMMETRY && c->pSize[ip] > 0) {       // symmetryPlanePolyPatch::n()
-            const double m = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-            for (int i = 0; i < c->pSize[ip]; i++) {
-                const int b = c->pStart[ip] + i;
-                for (int j = c->hFvPtr[F + b]; j < c->hFvPtr[F + b + 1]; j++) for (int q = 0; q < 3; q++) hN[3 * (size_t)c->hFv[j] + q] = n[q] / m;
-            }
-            // solidModel::moveMesh (solidModel.C:2040-2080): the points of a symmetry plane aligned with a coordinate axis keep
-            // that coordinate.  Average of the point normals (each the normalised sum of the unit normals of its patch faces).
-            std::vector<double> pn(3 * (size_t)nP, 0.0); std::vector<char> on(nP, 0);
-            for (int i = 0; i < c->pSize[ip]; i++) {
-                const int b = c->pStart[ip] + i;
-                const double* sf = &c->hBSfHost[3 * (size_t)b];
-                const double ms = std::sqrt(sf[0] * sf[0] + sf[1] * sf[1] + sf[2] * sf[2]);
-                for (int j = c->hFvPtr[F + b]; j < c->hFvPtr[F + b + 1]; j++) {
-                    const int p = c->hFv[j]; on[p] = 1;
-                    for (int q = 0; q < 3; q++) pn[3 * (size_t)p + q] += sf[q] / ms;
-                }
-            }
-            double avg[3] = {0, 0, 0}; int cntP = 0;
-            for (int p = 0; p < nP; p++) if (on[p]) {
-                const double* v = &pn[3 * (size_t)p];
-                const double mv = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-                for (int q = 0; q < 3; q++) avg[q] += v[q] / mv;
-                cntP++;
-            }
-            for (int ax = 0; ax < 3; ax++)
-                if (std::fabs(avg[ax] / cntP) > 0.95) { for (int p = 0; p < nP; p++) if (on[p]) fixAxis[p] = ax; break; }
+            for (int j = c->hFvPtr[F + b]; j < c->hFvPtr[F + b + 1]; j++) pb[c->hFv[j]].push_back(bOff + b);
         }
     }
+    std::vector<double> hN; std::vector<int> fixAxis;
+    point_symmetry(c, c->hBSfHost.data(), hN, fixAxis);
+    std::vector<double> xCtr;                       // centre of every extra slot
+    if (ext) {
+        xCtr.assign(3 * (size_t)std::max(c->X, 1), 0.0);
+        for (size_t e = 0; e < c->extSlot.size(); e++) for (int q = 0; q < 3; q++) xCtr[3 * (size_t)(c->extSlot[e] - xOff) + q] = c->extCtr[3 * e + q];
+        for (int p = 0; p < nP; p++) {              // cells and boundary faces of the other ranks around the same point
+            for (int e = c->extPtr[p]; e < c->extPtr[p + 1]; e++) (c->extIsB[e] ? pb : pc)[p].push_back(c->extSlot[e]);
+            const double* n = &c->extSymN[3 * (size_t)p];
+            if (hN[3 * (size_t)p] == 0 && hN[3 * (size_t)p + 1] == 0 && hN[3 * (size_t)p + 2] == 0) for (int q = 0; q < 3; q++) hN[3 * (size_t)p + q] = n[q];
+            if (fixAxis[p] < 0) fixAxis[p] = c->extFixAxis[p];
+        }
+    }
+    auto centre = [&](int slot) -> const double* {
+        return slot < N ? &c->hC[3 * (size_t)slot] : (slot >= xOff ? &xCtr[3 * (size_t)(slot - xOff)] : &c->hCfB[3 * (size_t)(slot - bOff)]);
+    };
     {   // gradient-extrapolated variant: all points from their pointCells
         std::vector<int> gptr(1, 0), gcol; std::vector<double> gw, gd[3];
         for (int p = 0; p < nP; p++) {
@@ -520,7 +714,7 @@ int s4f_build_point_weights(s4fgpu_ctx* c, const double* points) {
             const size_t s0 = gw.size();
             double sw = 0;
             for (int cell : pc[p]) {
-                const double* cc = &c->hC[3 * (size_t)cell];
+                const double* cc = centre(cell);
                 const double d[3] = {x[0] - cc[0], x[1] - cc[1], x[2] - cc[2]};
                 const double m = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
                 gcol.push_back(cell); gw.push_back(1.0 / m); sw += 1.0 / m;
@@ -535,29 +729,23 @@ int s4f_build_point_weights(s4fgpu_ctx* c, const double* points) {
         S4F_CHECK_CUDA(c, c->pgPtr.upload(gptr)); S4F_CHECK_CUDA(c, c->pgCol.upload(gcol)); S4F_CHECK_CUDA(c, c->pgW.upload(gw));
         S4F_CHECK_CUDA(c, c->pgDelta.upload(gdel));
     }
+    // volPointInterpolation as the solid models use it: a point of a (non-empty, non-processor) patch takes the patch face
+    // values around it, any other point the cell values around it; normalised inverse-distance weights
     std::vector<int> ptr(1, 0), col; std::vector<double> w;
     for (int p = 0; p < nP; p++) {
         const double* x = &points[3 * (size_t)p];
         const size_t s0 = w.size();
         double sw = 0;
-        if (!pb[p].empty()) {
-            for (int b : pb[p]) {
-                const double* cf = &c->hCfB[3 * (size_t)b];
-                const double d = std::sqrt((x[0] - cf[0]) * (x[0] - cf[0]) + (x[1] - cf[1]) * (x[1] - cf[1]) + (x[2] - cf[2]) * (x[2] - cf[2]));
-                col.push_back(bOff + b); w.push_back(1.0 / d); sw += 1.0 / d;
-            }
-        } else {
-            std::sort(pc[p].begin(), pc[p].end());
-            for (int cell : pc[p]) {
-                const double* cc = &c->hC[3 * (size_t)cell];
-                const double d = std::sqrt((x[0] - cc[0]) * (x[0] - cc[0]) + (x[1] - cc[1]) * (x[1] - cc[1]) + (x[2] - cc[2]) * (x[2] - cc[2]));
-                col.push_back(cell); w.push_back(1.0 / d); sw += 1.0 / d;
-            }
+        std::vector<int>& src = pb[p].empty() ? pc[p] : pb[p];
+        std::sort(src.begin(), src.end());
+        for (int sl : src) {
+            const double* cc = centre(sl);
+            const double d = std::sqrt((x[0] - cc[0]) * (x[0] - cc[0]) + (x[1] - cc[1]) * (x[1] - cc[1]) + (x[2] - cc[2]) * (x[2] - cc[2]));
+            col.push_back(sl); w.push_back(1.0 / d); sw += 1.0 / d;
         }
         for (size_t j = s0; j < w.size(); j++) w[j] /= sw;
         ptr.push_back((int)w.size());
     }
-    (void)N;
     if (col.empty()) { col.push_back(0); w.push_back(0.0); }
     S4F_CHECK_CUDA(c, c->ptPtr.upload(ptr)); S4F_CHECK_CUDA(c, c->ptCol.upload(col)); S4F_CHECK_CUDA(c, c->ptW.upload(w));
     S4F_CHECK_CUDA(c, c->ptN.upload(hN));
@@ -569,8 +757,16 @@ int s4f_build_point_weights(s4fgpu_ctx* c, const double* points) {
     return 0;
 }
 
+// decomposed meshes: the values of the other ranks' cells and boundary faces at shared points (slots >= xOff)
+int s4f_point_ghost_exchange(s4fgpu_ctx* c, double* field, int ncomp) {
+    if (c->nRanks <= 1 || !c->haloX) return 0;
+    return s4f_halo_run(c, c->haloX, field, c->ld, ncomp, c->xOff());
+}
+
 int s4f_interpolate_to_points(s4fgpu_ctx* c, const double* X, const double* G, double* hostOut) {
     const int nP = c->nPoints;
+    int rx = s4f_point_ghost_exchange(c, const_cast<double*>(X), 3); if (rx) return rx;
+    if (G && (rx = s4f_point_ghost_exchange(c, const_cast<double*>(G), 9))) return rx;
     if (G) k_vol_to_point_grad<<<(nP + 127) / 128, 128, 0, c->stream>>>(c->pgPtr.p, c->pgCol.p, c->pgW.p, c->pgDelta.p, X, G, c->ptOut.p, nP, c->ld, (long long)c->pgW.n);
     else k_vol_to_point<<<(nP + 127) / 128, 128, 0, c->stream>>>(c->ptPtr.p, c->ptCol.p, c->ptW.p, c->ptN.p, X, c->ptOut.p, nP, c->ld);
     c->launches++;

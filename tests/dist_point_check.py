@@ -1,0 +1,130 @@
+#!/usr/bin/env python
+"""The operators with a point stencil on a decomposed mesh (pointCellsLeastSquares gradient, vol->point
+interpolation), one rank per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 \
+        tests/dist_point_check.py <emptyDir> [checker|slab]
+
+Rank 0 writes a serial cantilever case with ``gradSchemes default pointCellsLeastSquares`` on a general (points + faces)
+mesh and decomposes it like decomposePar with a manual cell -> processor map: ``checker`` cuts the beam into 2 x 2 blocks in
+x and y and deals them out like a chess board, so the processor boundary has corners and edges where four blocks meet --
+the points there see cells and boundary faces of the other rank that no processor FACE connects them to.  Every rank reads its
+processorN directory, and the checks against the single-domain CPU oracle on the serial mesh are
+
+* grad(D) of an analytic (cubic) displacement field: the complete pointCells stencil incl. remote cells / boundary faces;
+* both vol->point interpolations of that field (patch mode and gradient-extrapolated), point by point;
+* the converged solution of the case (D, sigma) to north_star's 1e-6."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def field(C):
+    x, y, z = C[:, 0], C[:, 1], C[:, 2]
+    return 1e-3 * np.stack([x * y + 0.3 * z * z * x, np.sin(0.7 * x) + y * z, 0.2 * x * x * y - z ** 3], axis=1)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from solids4foam_b200 import case as K
+    from solids4foam_b200 import cases
+    from solids4foam_b200 import foam_io as IO
+    from solids4foam_b200 import run_case
+    from solids4foam_b200.solid_model import SolidModel, nccl_unique_id
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    case_dir = sys.argv[1]
+    mode = sys.argv[2] if len(sys.argv) > 2 else "checker"
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nx, ny, nz = 12, 6, 4
+    kw = dict(L=2.0, fieldRelaxD=0.9, nCorrectors=6000, solutionTolerance=1e-11, alternativeTolerance=1e-11, tolerance=1e-13,
+              preconditioner=K.PRECOND_GAMG, general=True, gradScheme=K.GRAD_POINT_CELLS_LEAST_SQUARES)
+    if rank == 0:
+        serial = cases.cantilever(nx, ny, nz, **kw)
+        # a non-uniform prescribed displacement on the clamped end: the boundary points there take boundary-face values, some
+        # of them faces of the other rank
+        pf = serial.mesh.patch("fixed")
+        F = serial.mesh.nInternalFaces
+        serial.bcs["fixed"].value = 1e-2 * field(serial.mesh.Cf[F + pf.start:F + pf.start + pf.size])
+        IO.write_case(case_dir, serial, end_time=1.0)
+        C = serial.mesh.C
+        if mode == "checker":
+            bx = (C[:, 0] > 0.5 * C[:, 0].max() + 1e-9).astype(np.int64)
+            by = (C[:, 1] > 0.5 * (C[:, 1].max() + C[:, 1].min())).astype(np.int64)
+            cell_rank = ((bx + by) % 2) if world == 2 else (bx + 2 * by) % world
+        else:
+            cell_rank = None
+        IO.decompose_case(case_dir, world, cell_rank=cell_rank)
+    dist.barrier()
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.tensor(list(nccl_unique_id()), dtype=torch.uint8, device="cuda")
+    dist.broadcast(uid, 0)
+    case = IO.read_decomposed_case(case_dir, rank, world, run_case.dist_exchange(rank), preconditioner=K.PRECOND_GAMG)
+    solid = SolidModel(case, device=local, comm=(world, rank, bytes(uid.cpu().tolist())))
+    m = case.mesh
+    # operators on an analytic field, fresh model
+    solid.set("D", field(m.C))
+    solid.op_grad()
+    g = solid.get("gradD")
+    pP = solid.interpolate_to_points("D", with_gradient=False)
+    pG = solid.interpolate_to_points("D", with_gradient=True)
+    # the case itself
+    solid.set("D", np.zeros((m.nCells, 3)))
+    solid.op_grad()
+    solid.new_timestep(1.0)
+    st = solid.evolve()
+    Dsol, Ssol = solid.get("D"), solid.get("sigma")
+    out = [None] * world
+    dist.all_gather_object(out, (m.cellGlobal, Dsol, Ssol, g, m.points, pP, pG))
+    ok = True
+    if rank == 0:
+        from oracle.binding import OracleSolid
+        serial = IO.read_case(case_dir, preconditioner=K.PRECOND_DIC)
+        o = OracleSolid(serial)
+        N = serial.mesh.nCells
+        o.set("D", field(serial.mesh.C))
+        o.op_grad()
+        Go = o.get("gradD")
+        oP = o.interpolate_to_points("D", with_gradient=False)
+        oG = o.interpolate_to_points("D", with_gradient=True)
+        o.set("D", np.zeros((N, 3)))
+        o.op_grad()
+        o.new_timestep(1.0)
+        so = o.evolve()
+        D = np.zeros((N, 3)); S = np.zeros((N, 6)); G = np.zeros((N, 9))
+        for cg, d, s_, gg, *_ in out:
+            D[cg] = d; S[cg] = s_; G[cg] = gg
+        eD = np.linalg.norm(D - o.get("D")) / np.linalg.norm(o.get("D"))
+        eS = np.linalg.norm(S - o.get("sigma")) / np.linalg.norm(o.get("sigma"))
+        eG = np.abs(G - Go).max() / np.abs(Go).max()
+        key = {tuple(x): i for i, x in enumerate(np.round(serial.mesh.points, 12).tolist())}
+        eP = eGp = 0.0
+        shared = {}
+        for r, (_, _, _, _, pts, pP_r, pG_r) in enumerate(out):
+            ids = np.array([key[tuple(x)] for x in np.round(pts, 12).tolist()])
+            eP = max(eP, np.abs(pP_r - oP[ids]).max() / np.abs(oP).max())
+            eGp = max(eGp, np.abs(pG_r - oG[ids]).max() / np.abs(oG).max())
+            for i, v in zip(ids.tolist(), pP_r.tolist()):
+                shared.setdefault(i, []).append(v)
+        nShared = sum(1 for v in shared.values() if len(v) > 1)
+        # a point held by several ranks gets the same value on each of them (no partial sums to synchronise)
+        spread = max((np.ptp(np.array(v), axis=0).max() for v in shared.values() if len(v) > 1), default=0.0) / np.abs(oP).max()
+        print(f"point stencils on {world} GPUs ({mode}): pointCells grad max rel err {eG:.2e}; vol->point patch {eP:.2e} grad-extrapolated {eGp:.2e}; "
+              f"{nShared} shared points, spread between ranks {spread:.2e}; converged gpu {st['converged']} ({st['nCorr']}) "
+              f"oracle {so['converged']} ({so['nCorr']}); relL2 D {eD:.2e} sigma {eS:.2e}", flush=True)
+        ok = bool(st["converged"] and so["converged"] and eD < 1e-6 and eS < 1e-6 and eG < 1e-11 and eP < 1e-12 and eGp < 1e-11
+                  and spread < 1e-13 and nShared > 0)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
