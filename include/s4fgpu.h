@@ -54,7 +54,8 @@ enum {
     S4F_MODEL_NONLIN_UL = 3,             /* SM/nonLinGeomUpdatedLagSolid/...C:159-273 */
     S4F_MODEL_UNS_LIN_GEOM = 4           /* SM/unsLinGeomSolid/unsLinGeomSolid.C:100-175 ("unsLinearGeometry"): face stresses from face
                                             gradients built on the vertex displacements, fvc::div(mesh().Sf() & sigmaf);
-                                            linearElastic, needs s4fgpu_set_points, single rank */
+                                            linearElastic, needs s4fgpu_set_points; decomposed meshes: processor faces take the
+                                            corrected snGrad of an internal face, vertex values see the other ranks' cells */
 };
 
 /* mechanicalLaw (constant/mechanicalProperties "type") */
@@ -72,7 +73,8 @@ enum {
     S4F_GRAD_POINT_CELLS_LEAST_SQUARES = 2 /* [OF-ext] LeastSquaresGrad<centredCPCCellToCellStencilObject> ("pointCellsLeastSquares",
                                    the scheme the tutorials use on OpenFOAM.com/.org, applications/scripts/solids4FoamScripts.sh:162-176):
                                    1/|d|^2-weighted least squares over the cells sharing a point with the cell and the boundary faces
-                                   at its points; needs s4fgpu_set_points; single rank */
+                                   at its points; needs s4fgpu_set_points; on decomposed meshes the stencil includes the cells and
+                                   boundary faces of other ranks at shared points (see s4fgpu_set_points) */
 };
 enum { S4F_D2DT2_STEADY_STATE = 0, S4F_D2DT2_EULER = 1, S4F_D2DT2_BACKWARD = 2 };
 enum { S4F_STAB_NONE = 0, S4F_STAB_RHIE_CHOW = 1 };        /* SM/solidModel/momentumStabilisation/momentumStabilisation.C:210-217 */
@@ -227,6 +229,14 @@ int s4fgpu_set_geometry(s4fgpu_handle h, const double* C, const double* V, const
  * faces in patch order; faceVertsPtr [F+B+1] CSR offsets into faceVerts).  Builds pointCells and the
  * boundary pointFaces addressing that volPointInterpolation needs.  Re-callable with moved points (same
  * topology): the inverse-distance weights are recomputed from the geometry of the last set_geometry.
+ * Decomposed meshes (s4fgpu_comm_init, processor patches): call this BEFORE s4fgpu_set_geometry.  set_geometry then
+ * identifies the points of the processor patches across ranks by their coordinates (bit for bit -- decomposePar writes
+ * them from one set of points), and reserves, behind the boundary slots of the field index space, one slot per cell and
+ * per boundary face of ANOTHER rank that shares a point with this rank's cells ("point-neighbour ghosts"; also ranks that
+ * touch this one only along an edge or at a corner).  One peer-memory exchange fills them before every operator with a
+ * point stencil (pointCellsLeastSquares gradient, vol->point interpolation, the uns face gradients), which each rank then
+ * evaluates completely by itself: where OpenFOAM synchronises partial sums over globalMeshData's shared points
+ * ([OF-ext] volPointInterpolation / syncTools), every rank here holds the same point value by construction.
  * Reference: mesh().points()/faces() as used by enhancedVolPointInterpolation.C:60-250
  * (src/blockCoupledSolids4FoamTools/enhancedVolPointInterpolation) and solidModel::moveMesh
  * (SM/solidModel/solidModel.C:2008-2148). */

@@ -23,6 +23,7 @@ struct S4fUns {
     DevBuf<double> fT, fG;               // [9*ldF] in-plane gradient, Gauss sum of a face
     DevBuf<double> gradDf, sigmaf;       // [9*ldF], [6*ldF]
     DevBuf<double> gLS;                  // [9*ld] fvc::grad(D) of the gradScheme (non-orthogonal part of snGrad(D))
+    DevBuf<int> procFace;                // [G] boundary face of each processor-patch ghost (decomposed meshes)
 };
 
 namespace {
@@ -195,6 +196,38 @@ __global__ void k_uns_face_stress(const int* __restrict__ fOwn, const int* __res
     for (int q = 0; q < 6; q++) sigmaf[(size_t)q * ldF + f] = s[q];
 }
 
+// processor-patch faces: the corrected snGrad(D) of an internal face, with the cell across the cut in its ghost slot
+// (what the coupled patch field's snGrad() + the processor patch's interpolate(fvc::grad(D)) give in OpenFOAM); both ranks
+// evaluate the same expression with n and (D_N - D_P) reversed, so the face stress is the same on either side
+__global__ void k_uns_proc_sngrad(const int* __restrict__ procFace, const int* __restrict__ procEntry, const int* __restrict__ bFaceCell,
+                                  const double* __restrict__ eSf, const double* __restrict__ eDn, const double* __restrict__ eW,
+                                  const double* __restrict__ eCorr /* null when orthogonal */, const double* __restrict__ D,
+                                  const double* __restrict__ gLS, double* __restrict__ bSn, int G, int N, int B, int ld, long long nE) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const int b = procFace[g], P = bFaceCell[b], Nn = N + g;
+    const long long e = procEntry[g];
+    const double S[3] = {eSf[e], eSf[nE + e], eSf[2 * nE + e]};
+    const double mag = sqrt(S[0] * S[0] + S[1] * S[1] + S[2] * S[2]);
+    const double nod = eDn[e] / mag;
+    double sn[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) sn[j] = nod * (D[(size_t)j * ld + Nn] - D[(size_t)j * ld + P]);
+    if (eCorr) {
+        const double w = eW[e], w1 = 1.0 - w;
+        const double c[3] = {eCorr[e] / mag, eCorr[nE + e] / mag, eCorr[2 * nE + e] / mag};
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double t = 0;
+#pragma unroll
+            for (int i = 0; i < 3; i++) t += c[i] * (w * gLS[(size_t)(3 * i + j) * ld + P] + w1 * gLS[(size_t)(3 * i + j) * ld + Nn]);
+            sn[j] += t;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++) bSn[(size_t)j * B + b] = sn[j];
+}
+
 // traction patches: unsLinGeomSolid::tractionBoundarySnGrad (unsLinGeomSolid.C:193-230) on the face fields
 __global__ void k_bc_update_uns(const int* __restrict__ bKind, const double* __restrict__ bN, const double* __restrict__ bcValue,
                                 const double* __restrict__ bcPressure, const double* __restrict__ impK, const double* __restrict__ sigmaf,
@@ -285,7 +318,10 @@ void s4f_uns_destroy(s4fgpu_ctx* c) { delete c->uns; c->uns = nullptr; }
 // face->vertex CSR, owner/neighbour, the face of every row entry, and 3/sum(St & Ct) per cell (geometry only)
 int s4f_uns_setup(s4fgpu_ctx* c) {
     if (c->nPoints == 0) { c->err = "unsLinearGeometry needs the mesh points (s4fgpu_set_points)"; return 1; }
-    if (c->nRanks > 1) { c->err = "unsLinearGeometry is not available on decomposed meshes yet"; return 1; }
+    if (c->nRanks > 1 && c->extPtr.size() != (size_t)c->nPoints + 1) {
+        c->err = "unsLinearGeometry on a decomposed mesh: call s4fgpu_set_points before s4fgpu_set_geometry";
+        return 1;
+    }
     if (c->law.kind != S4F_LAW_LINEAR_ELASTIC) { c->err = "unsLinearGeometry: linearElastic is the law available on the faces"; return 1; }
     const int N = c->N, F = c->F, B = c->B;
     if (!c->uns) c->uns = new S4fUns();
@@ -296,6 +332,11 @@ int s4f_uns_setup(s4fgpu_ctx* c) {
     for (int f = 0; f < F; f++) { own[f] = c->own[f]; nei[f] = c->nei[f]; }
     S4F_CHECK_CUDA(c, u.fOwn.upload(own)); S4F_CHECK_CUDA(c, u.fNei.upload(nei));
     S4F_CHECK_CUDA(c, u.pts.upload(c->hPoints));
+    {
+        std::vector<int> pf(std::max(c->G, 1), 0);
+        for (int b = 0; b < B; b++) if (c->ghostOfFace[b] >= 0) pf[c->ghostOfFace[b] - N] = b;
+        S4F_CHECK_CUDA(c, u.procFace.upload(pf));
+    }
     // rows in the order of s4f_build_rows: lower neighbours, upper neighbours, boundary faces
     std::vector<int> cnt(N, 0);
     for (int f = 0; f < F; f++) { cnt[c->own[f]]++; cnt[c->nei[f]]++; }
@@ -370,6 +411,7 @@ int s4f_uns_gradients(s4fgpu_ctx* c) {
     S4fUns& u = *c->uns;
     const int N = c->N, F = c->F, B = c->B, bOff = c->bOff(), ld = c->ld, nF = F + B;
     const int gridR = s4f_grid(c->numSMs, (long long)c->nSlices * 32, 4);
+    { int rx = s4f_point_ghost_exchange(c, c->D.p, 3); if (rx) return rx; }       // decomposed: the other ranks' values at shared points
     k_vol_to_point_dev<<<(c->nPoints + 127) / 128, 128, 0, c->stream>>>(c->ptPtr.p, c->ptCol.p, c->ptW.p, c->ptN.p, c->D.p, c->ptOut.p, c->nPoints, ld);
     k_uns_face_pre<<<(nF + 127) / 128, 128, 0, c->stream>>>(u.fPtr.p, u.fVerts.p, u.pts.p, c->ptOut.p, c->faceEntry.p, c->eSf.p, c->bSf.p, u.fT.p,
                                                            u.fG.p, F, B, u.ldF, c->nEntries);
@@ -384,14 +426,23 @@ int s4f_uns_gradients(s4fgpu_ctx* c) {
         c->launches++;
         int rc = s4f_bc_sngrad_store(c); if (rc) return rc;            // again, with the gradD just assigned: fvc::snGrad(D) on the patches
     }
-    if (c->nonOrth) { int rc = s4f_grad_calculated_interior(c, c->D.p, u.gLS.p); if (rc) return rc; }
+    if (c->nonOrth) {
+        int rc = s4f_grad_calculated_interior(c, c->D.p, u.gLS.p); if (rc) return rc;
+        if ((rc = s4f_halo_exchange(c, u.gLS.p, 9))) return rc;
+    }
+    if (c->G > 0) {
+        k_uns_proc_sngrad<<<(c->G + 127) / 128, 128, 0, c->stream>>>(u.procFace.p, c->procEntry.p, c->bFaceCell.p, c->eSf.p, c->eDn.p, c->eW.p,
+                                                                    c->nonOrth ? c->eCorr.p : nullptr, c->D.p, u.gLS.p, c->bSn.p, c->G, N, B, ld,
+                                                                    c->nEntries);
+        c->launches++;
+    }
     S6u s0; for (int q = 0; q < 6; q++) s0.v[q] = c->law.sigma0[q];
     k_uns_face_stress<<<(nF + 127) / 128, 128, 0, c->stream>>>(u.fOwn.p, u.fNei.p, c->faceEntry.p, c->eSf.p, c->eDn.p, c->eW.p,
                                                               c->nonOrth ? c->eCorr.p : nullptr, c->bN.p, c->bSn.p, c->D.p, u.gLS.p, u.fT.p,
                                                               u.gradDf.p, u.sigmaf.p, F, B, ld, u.ldF, c->nEntries, c->law.mu, c->law.lambda, s0);
     c->launches++;
     S4F_CHECK_CUDA(c, cudaGetLastError());
-    return 0;
+    return s4f_halo_exchange(c, c->gradD.p, 9);
 }
 
 int s4f_uns_bc_update(s4fgpu_ctx* c) {

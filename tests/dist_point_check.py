@@ -3,7 +3,7 @@
 interpolation), one rank per GPU:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 \
-        tests/dist_point_check.py <emptyDir> [checker|slab]
+        tests/dist_point_check.py <emptyDir> [checker|slab] [pointCells|uns] [box|warped]
 
 Rank 0 writes a serial cantilever case with ``gradSchemes default pointCellsLeastSquares`` on a general (points + faces)
 mesh and decomposes it like decomposePar with a manual cell -> processor map: ``checker`` cuts the beam into 2 x 2 blocks in
@@ -13,7 +13,11 @@ processorN directory, and the checks against the single-domain CPU oracle on the
 
 * grad(D) of an analytic (cubic) displacement field: the complete pointCells stencil incl. remote cells / boundary faces;
 * both vol->point interpolations of that field (patch mode and gradient-extrapolated), point by point;
-* the converged solution of the case (D, sigma) to north_star's 1e-6."""
+* the converged solution of the case (D, sigma) to north_star's 1e-6.
+
+``uns`` runs the unsLinearGeometry model instead (vertex values from vol->point, face gradients and face stress; the processor
+faces take the corrected snGrad of an internal face with the cell across the cut); ``warped`` distorts the mesh so that the
+non-orthogonal correction (and its ghost gradients) is exercised."""
 import os
 import sys
 
@@ -39,13 +43,29 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     case_dir = sys.argv[1]
     mode = sys.argv[2] if len(sys.argv) > 2 else "checker"
+    model = sys.argv[3] if len(sys.argv) > 3 else "pointCells"
+    shape = sys.argv[4] if len(sys.argv) > 4 else "box"
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nx, ny, nz = 12, 6, 4
     kw = dict(L=2.0, fieldRelaxD=0.9, nCorrectors=6000, solutionTolerance=1e-11, alternativeTolerance=1e-11, tolerance=1e-13,
-              preconditioner=K.PRECOND_GAMG, general=True, gradScheme=K.GRAD_POINT_CELLS_LEAST_SQUARES)
+              preconditioner=K.PRECOND_GAMG, general=True)
+    if model == "uns":
+        kw["solidModel"] = K.MODEL_UNS_LIN_GEOM
+    else:
+        kw["gradScheme"] = K.GRAD_POINT_CELLS_LEAST_SQUARES
     if rank == 0:
         serial = cases.cantilever(nx, ny, nz, **kw)
+        if shape == "warped":
+            from solids4foam_b200 import mesh as M
+
+            def warp(p):
+                q = p.copy()
+                q[:, 0] += 0.04 * np.sin(2.1 * p[:, 1] + 1.3 * p[:, 2])
+                q[:, 1] += 0.03 * np.sin(1.7 * p[:, 0]) * (1 + 0.5 * p[:, 2])
+                q[:, 2] += 0.03 * np.cos(1.1 * p[:, 0] + 0.9 * p[:, 1])
+                return q
+            serial.mesh = M.hex_box_general(nx, ny, nz, 2.0, 1.0, 1.0, point_map=warp, names=("fixed", "loaded", "yMin", "yMax", "zMin", "zMax"))
         # a non-uniform prescribed displacement on the clamped end: the boundary points there take boundary-face values, some
         # of them faces of the other rank
         pf = serial.mesh.patch("fixed")
@@ -54,8 +74,10 @@ def main():
         IO.write_case(case_dir, serial, end_time=1.0)
         C = serial.mesh.C
         if mode == "checker":
-            bx = (C[:, 0] > 0.5 * C[:, 0].max() + 1e-9).astype(np.int64)
-            by = (C[:, 1] > 0.5 * (C[:, 1].max() + C[:, 1].min())).astype(np.int64)
+            # blocks from the cell numbering (x fastest), not from the (possibly warped) centres
+            idx = np.arange(serial.mesh.nCells)
+            bx = ((idx % nx) >= nx // 2).astype(np.int64)
+            by = (((idx // nx) % ny) >= ny // 2).astype(np.int64)
             cell_rank = ((bx + by) % 2) if world == 2 else (bx + 2 * by) % world
         else:
             cell_rank = None
@@ -115,7 +137,7 @@ def main():
         nShared = sum(1 for v in shared.values() if len(v) > 1)
         # a point held by several ranks gets the same value on each of them (no partial sums to synchronise)
         spread = max((np.ptp(np.array(v), axis=0).max() for v in shared.values() if len(v) > 1), default=0.0) / np.abs(oP).max()
-        print(f"point stencils on {world} GPUs ({mode}): pointCells grad max rel err {eG:.2e}; vol->point patch {eP:.2e} grad-extrapolated {eGp:.2e}; "
+        print(f"point stencils on {world} GPUs ({mode}, {model}, {shape}): grad(D) max rel err {eG:.2e}; vol->point patch {eP:.2e} grad-extrapolated {eGp:.2e}; "
               f"{nShared} shared points, spread between ranks {spread:.2e}; converged gpu {st['converged']} ({st['nCorr']}) "
               f"oracle {so['converged']} ({so['nCorr']}); relL2 D {eD:.2e} sigma {eS:.2e}", flush=True)
         ok = bool(st["converged"] and so["converged"] and eD < 1e-6 and eS < 1e-6 and eG < 1e-11 and eP < 1e-12 and eGp < 1e-11

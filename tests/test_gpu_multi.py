@@ -32,15 +32,17 @@ def test_decomposed_case_directory_runs_on_two_gpus(tmp_path):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-@pytest.mark.parametrize("mode", ["checker", "slab"])
-def test_point_stencils_on_a_decomposed_mesh(tmp_path, mode):
-    """pointCellsLeastSquares gradient and vol->point interpolation across processor patches (point-neighbour ghosts,
-    s4f_build_point_ghosts): operators on an analytic field and the converged case against the single-domain oracle."""
+@pytest.mark.parametrize("mode,model,shape", [("checker", "pointCells", "box"), ("slab", "pointCells", "warped"),
+                                              ("checker", "uns", "box"), ("checker", "uns", "warped")])
+def test_point_stencils_on_a_decomposed_mesh(tmp_path, mode, model, shape):
+    """pointCellsLeastSquares gradient, vol->point interpolation and the unsLinearGeometry model across processor patches
+    (point-neighbour ghosts, s4f_build_point_ghosts): operators on an analytic field and the converged case against the
+    single-domain oracle."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29519", os.path.join(HERE, "dist_point_check.py"), str(tmp_path / "case"), mode]
+           "--master-port", "29519", os.path.join(HERE, "dist_point_check.py"), str(tmp_path / "case"), mode, model, shape]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
     print(r.stdout[-1500:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
