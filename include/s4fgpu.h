@@ -52,10 +52,16 @@ enum {
     S4F_MODEL_NONLIN_TL_TOTAL_DISP = 1,  /* SM/nonLinGeomTotalLagTotalDispSolid/...C:173-281 */
     S4F_MODEL_NONLIN_TL = 2,             /* SM/nonLinGeomTotalLagSolid/nonLinGeomTotalLagSolid.C:125-260 (solves DD) */
     S4F_MODEL_NONLIN_UL = 3,             /* SM/nonLinGeomUpdatedLagSolid/...C:159-273 */
-    S4F_MODEL_UNS_LIN_GEOM = 4           /* SM/unsLinGeomSolid/unsLinGeomSolid.C:100-175 ("unsLinearGeometry"): face stresses from face
+    S4F_MODEL_UNS_LIN_GEOM = 4,          /* SM/unsLinGeomSolid/unsLinGeomSolid.C:100-175 ("unsLinearGeometry"): face stresses from face
                                             gradients built on the vertex displacements, fvc::div(mesh().Sf() & sigmaf);
                                             linearElastic, needs s4fgpu_set_points; decomposed meshes: processor faces take the
                                             corrected snGrad of an internal face, vertex values see the other ranks' cells */
+    S4F_MODEL_UNS_NONLIN_TL = 5          /* SM/unsNonLinGeomTotalLagSolid/unsNonLinGeomTotalLagSolid.C:218-405
+                                            ("unsNonLinearGeometryTotalLagrangian"): the same face gradients, Ff = I + gradDf.T()
+                                            on the faces, neoHookeanElastic::correct(surfaceSymmTensorField&)
+                                            (neoHookeanElastic.C:306-352), fvc::div((Jf Finvf.T() & Sf) & sigmaf); its own
+                                            convergence criterion (:49-76, :333-378); neoHookeanElastic; the enforceLinear
+                                            fall-back of the reference is not implemented */
 };
 
 /* mechanicalLaw (constant/mechanicalProperties "type") */

@@ -177,7 +177,9 @@ struct s4f_oracle {
     int NB() const { return N + B; }
     bool incremental() const { return ctl.solidModel == S4F_MODEL_NONLIN_TL || ctl.solidModel == S4F_MODEL_NONLIN_UL; }
     bool UL() const { return ctl.solidModel == S4F_MODEL_NONLIN_UL; }
-    bool uns() const { return ctl.solidModel == S4F_MODEL_UNS_LIN_GEOM; }
+    bool uns() const { return ctl.solidModel == S4F_MODEL_UNS_LIN_GEOM || ctl.solidModel == S4F_MODEL_UNS_NONLIN_TL; }
+    bool unsTL() const { return ctl.solidModel == S4F_MODEL_UNS_NONLIN_TL; }
+    double unsMaxRes = 0;          // unsNonLinGeomTotalLagSolid::evolve: the largest relative residual of this time step
     const dvec& gradForLaw() const { return incremental() ? gradDtot : gradD; }   // the registered "grad(D)"
 };
 
@@ -286,7 +288,19 @@ void tractionSnGrad(const s4f_oracle& o, int b, double* g) {
     const double impK = o.impK[N + b], rImpK = 1.0 / impK;
     const double* gD = &o.gradD[9 * (N + b)];
     const double* sg = &o.sigma[6 * (N + b)];
-    if (o.uns()) {
+    if (o.unsTL()) {
+        // unsNonLinGeomTotalLagSolid::tractionBoundarySnGrad, unsNonLinGeomTotalLagSolid.C:420-488 (enforceLinear off):
+        // nCurrent = Jf Finvf.T() & n (not normalised); ((t - nCurrent p) - (nCurrent & sigmaf) + (n & (impK gradDf))) rImpK
+        const double* gf = &o.gradDf[9 * (size_t)(o.F + b)];
+        double Ff[9]; transposeT(gf, Ff); Ff[0] += 1; Ff[4] += 1; Ff[8] += 1;
+        const double J = detT(Ff);
+        double Fi[9], FiT[9]; invT(Ff, Fi); transposeT(Fi, FiT);
+        double nc[3];
+        for (int i = 0; i < 3; i++) nc[i] = J * (FiT[3 * i] * n[0] + FiT[3 * i + 1] * n[1] + FiT[3 * i + 2] * n[2]);
+        double ns[3]; SvS(&o.sigmaf[6 * (size_t)(o.F + b)], nc, ns);
+        double ng[3]; vT(n, gf, ng);
+        for (int i = 0; i < 3; i++) g[i] = ((t[i] - nc[i] * p) - ns[i] + impK * ng[i]) * rImpK;
+    } else if (o.uns()) {
         // unsLinGeomSolid::tractionBoundarySnGrad, unsLinGeomSolid.C:193-230: the same expression on the FACE fields
         // sigmaf_ and gradDf_ of the patch
         const double* gf = &o.gradDf[9 * (size_t)(o.F + b)];
@@ -624,6 +638,26 @@ void unsUpdateGradients(s4f_oracle& o, bool interpolate = true) {
 void unsLawFaces(s4f_oracle& o) {
     const int nf = o.F + o.B;
     o.sigmaf.assign(6 * (size_t)nf, 0.0);
+    if (o.unsTL()) {
+        // unsNonLinGeomTotalLagSolid.C:312-330: Ff = I + gradDf.T(); then neoHookeanElastic::correct(surfaceSymmTensorField&)
+        // -> correctF (neoHookeanElastic.C:306-352): J = det F; bEbar = J^(-2/3) symm(F & F.T()); s = mu dev(bEbar);
+        // sigma = (1/J) (0.5 K (J^2 - 1) I + s)
+        for (int f = 0; f < nf; f++) {
+            double Ff[9]; transposeT(&o.gradDf[9 * (size_t)f], Ff); Ff[0] += 1; Ff[4] += 1; Ff[8] += 1;
+            const double J = detT(Ff);
+            double FT[9], FFT[9], b[6];
+            transposeT(Ff, FT); mulTT(Ff, FT, FFT); symm(FFT, b);
+            const double sc = std::pow(J, -2.0 / 3.0);
+            for (int q = 0; q < 6; q++) b[q] *= sc;
+            double dv[6]; devS(b, dv);
+            const double sh = 0.5 * o.law.K * (std::pow(J, 2.0) - 1.0);
+            double* sg = &o.sigmaf[6 * (size_t)f];
+            for (int q = 0; q < 6; q++) sg[q] = o.law.mu * dv[q];
+            sg[0] += sh; sg[3] += sh; sg[5] += sh;
+            for (int q = 0; q < 6; q++) sg[q] *= 1.0 / J;
+        }
+        return;
+    }
     for (int f = 0; f < nf; f++) {
         double e[6]; symm(&o.gradDf[9 * (size_t)f], e);
         const double tr = trS(e);
@@ -1081,7 +1115,17 @@ void assembleSource(s4f_oracle& o) {
     if (o.uns()) {
         // unsLinGeomSolid.C:129: fvc::div(mesh().Sf() & sigmaf_): the face stress itself, no interpolation
         for (int f = 0; f < F + B; f++) {
-            double fl[3]; SvS(&o.sigmaf[6 * (size_t)f], &o.Sf[3 * (size_t)f], fl);      // Sf & sigmaf (symmetric)
+            double fl[3];
+            if (o.unsTL()) {      // unsNonLinGeomTotalLagSolid.C:273: fvc::div((Jf Finvf.T() & Sf) & sigmaf)
+                double Ff[9]; transposeT(&o.gradDf[9 * (size_t)f], Ff); Ff[0] += 1; Ff[4] += 1; Ff[8] += 1;
+                const double J = detT(Ff);
+                double Fi[9], FiT[9]; invT(Ff, Fi); transposeT(Fi, FiT);
+                const double* S = &o.Sf[3 * (size_t)f];
+                double a[3];
+                for (int i = 0; i < 3; i++) a[i] = J * (FiT[3 * i] * S[0] + FiT[3 * i + 1] * S[1] + FiT[3 * i + 2] * S[2]);
+                SvS(&o.sigmaf[6 * (size_t)f], a, fl);
+            } else
+            SvS(&o.sigmaf[6 * (size_t)f], &o.Sf[3 * (size_t)f], fl);      // Sf & sigmaf (symmetric)
             const int P = f < F ? o.own[f] : o.faceCells[f - F];
             for (int q = 0; q < 3; q++) s[3 * P + q] += fl[q];
             if (f < F) for (int q = 0; q < 3; q++) s[3 * o.nei[f] + q] -= fl[q];
@@ -1430,6 +1474,29 @@ void relaxField(s4f_oracle& o, int iCorr) {
 // for the total-displacement models)
 bool convergedCheck(s4f_oracle& o, int iCorr, s4fgpu_stats* st) {
     const int N = o.N;
+    if (o.unsTL()) {
+        // unsNonLinGeomTotalLagSolid.C:49-76 (residual) and :333-378: res = max|D - D.prevIter| / max(max|D - D.oldTime|, SMALL);
+        // tolerance = max(maxRes * relativeTol_, solutionTol) with relativeTol_ read from "solutionTolerance" as well (:206-213);
+        // the first iteration never converges ("force at least one iteration")
+        double num = 0, den = 0;
+        for (int c = 0; c < N; c++) {
+            double a[3], r[3];
+            for (int q = 0; q < 3; q++) { a[q] = o.D[3 * c + q] - o.Dold[3 * c + q]; r[q] = o.D[3 * c + q] - o.Dprev[3 * c + q]; }
+            num = std::max(num, mag3(r)); den = std::max(den, mag3(a));
+        }
+        const double res = num / std::max(den, SMALL);
+        if (iCorr == 0) o.unsMaxRes = 0;
+        o.unsMaxRes = std::max(o.unsMaxRes, res);
+        const double tol = std::max(o.unsMaxRes * o.ctl.solutionTolerance, o.ctl.solutionTolerance);
+        const bool conv = iCorr > 0 && !(res > tol);
+        if (st) {
+            for (int q = 0; q < 3; q++) { st->initialResidual[q] = o.perf[q].initRes; st->finalResidual[q] = o.perf[q].finalRes; st->nIterations[q] = o.perf[q].nIter; }
+            const double ir[3] = {o.perf[0].initRes, o.perf[1].initRes, o.perf[2].initRes};
+            st->solverPerfInitRes = mag3(ir); st->relResidual = res; st->materialResidual = 0; st->converged = conv;
+            st->totalInnerIterations = o.totalInner;
+        }
+        return conv;
+    }
     double denom = 0, dmax = 0, res = 0;
     const bool incremental = (o.ctl.solidModel == S4F_MODEL_NONLIN_TL || o.ctl.solidModel == S4F_MODEL_NONLIN_UL);
     for (int c = 0; c < N; c++) {

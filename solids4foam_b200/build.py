@@ -41,7 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         fail |= p.returncode != 0
     if fail:
         raise RuntimeError("nvcc failed")
-    cmd = [NVCC, "-shared", "-o", SO] + objs + ["-lnccl", "-lcudart", "-ccbin", "/usr/bin/g++"]
+    cmd = [NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", SO] + objs + ["-lnccl", "-lcudart", "-ccbin", "/usr/bin/g++"]
     subprocess.check_call(cmd)
     return SO
 

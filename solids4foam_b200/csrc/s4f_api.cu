@@ -71,6 +71,21 @@ int s4f_read_outer_scalars(s4fgpu_ctx* c, s4fgpu_stats* st, bool* converged, int
     S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));      // the one host synchronisation of an outer iteration
     { int rf = s4f_finish_solve(c); if (rf) return rf; }
     const OuterScalars& o = *c->hOutS;
+    if (c->unsTL()) {
+        // unsNonLinGeomTotalLagSolid.C:49-76, :333-378: res = max|D - D.prevIter| / max(max|D - D.oldTime|, SMALL), tolerance
+        // max(maxRes * relativeTol_, solutionTol) with relativeTol_ = solutionTolerance (:206-213); never on the first iteration
+        const double res = o.maxDelta / std::max(o.maxIncr, 1e-15);
+        if (iCorr == 0) c->unsMaxRes = 0;
+        c->unsMaxRes = std::max(c->unsMaxRes, res);
+        const double tol = std::max(c->unsMaxRes * c->ctl.solutionTolerance, c->ctl.solutionTolerance);
+        const bool conv = iCorr > 0 && !(res > tol);
+        const double* ir = c->last.initialResidual;
+        c->last.solverPerfInitRes = std::sqrt(ir[0] * ir[0] + ir[1] * ir[1] + ir[2] * ir[2]); c->last.relResidual = res;
+        c->last.materialResidual = 0; c->last.converged = conv ? 1 : 0; c->last.totalInnerIterations = c->totalInner;
+        if (st) *st = c->last;
+        *converged = conv;
+        return 0;
+    }
     const bool incremental = (c->ctl.solidModel == S4F_MODEL_NONLIN_TL || c->ctl.solidModel == S4F_MODEL_NONLIN_UL);
     double denom = incremental ? o.maxMag : o.maxIncr;
     if (denom < 1e-15) denom = std::max(o.maxMag, 1e-15);
@@ -224,7 +239,7 @@ int s4fgpu_set_law(s4fgpu_handle c, const s4fgpu_law* law) {
 int s4fgpu_set_controls(s4fgpu_handle c, const s4fgpu_controls* ctl) {
     S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
     S4F_REQUIRE(c, ctl, "set_controls: null");
-    S4F_REQUIRE(c, ctl->solidModel >= S4F_MODEL_LIN_GEOM_TOTAL_DISP && ctl->solidModel <= S4F_MODEL_UNS_LIN_GEOM, "set_controls: unknown solidModel");
+    S4F_REQUIRE(c, ctl->solidModel >= S4F_MODEL_LIN_GEOM_TOTAL_DISP && ctl->solidModel <= S4F_MODEL_UNS_NONLIN_TL, "set_controls: unknown solidModel");
     S4F_REQUIRE(c, ctl->solidModel != S4F_MODEL_NONLIN_TL || ctl->d2dt2Scheme == S4F_D2DT2_STEADY_STATE,
                 "set_controls: nonLinearGeometryTotalLagrangian is available with the steadyState d2dt2 scheme");
     S4F_REQUIRE(c, ctl->solver == S4F_SOLVER_PCG || ctl->solver == S4F_SOLVER_PBICGSTAB, "set_controls: solver PCG or PBiCGStab");

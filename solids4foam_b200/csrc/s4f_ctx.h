@@ -273,7 +273,9 @@ struct s4fgpu_ctx {
 
     bool incremental() const { return ctl.solidModel == S4F_MODEL_NONLIN_TL || ctl.solidModel == S4F_MODEL_NONLIN_UL; }
     bool UL() const { return ctl.solidModel == S4F_MODEL_NONLIN_UL; }
-    bool unsModel() const { return ctl.solidModel == S4F_MODEL_UNS_LIN_GEOM; }
+    bool unsModel() const { return ctl.solidModel == S4F_MODEL_UNS_LIN_GEOM || ctl.solidModel == S4F_MODEL_UNS_NONLIN_TL; }
+    bool unsTL() const { return ctl.solidModel == S4F_MODEL_UNS_NONLIN_TL; }
+    double unsMaxRes = 0;                 // unsNonLinGeomTotalLagSolid::evolve: largest relative residual of the time step
     bool finiteStrain() const { return ctl.solidModel == S4F_MODEL_NONLIN_TL_TOTAL_DISP || ctl.solidModel == S4F_MODEL_NONLIN_TL || ctl.solidModel == S4F_MODEL_NONLIN_UL; }
     bool pointCellsGrad() const { return ctl.gradScheme == S4F_GRAD_POINT_CELLS_LEAST_SQUARES; }
     // rows the least-squares gradient kernels run over

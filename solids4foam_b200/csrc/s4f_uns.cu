@@ -5,6 +5,10 @@
 //   gradDf  = fvc::fGrad(D, pointD)     fvcGradf.C:44-112: fsGrad (:123-232, in-plane gradient from the edge-centre values)
 //                                       + n*fvc::snGrad(D) (corrected snGrad; patch faces: the boundary condition's snGrad())
 //   sigmaf  = 2 mu symm(gradDf) + lambda tr I + sigma0f             linearElastic.C:342-370
+// unsNonLinGeomTotalLagSolid (SM/unsNonLinGeomTotalLagSolid/unsNonLinGeomTotalLagSolid.C:218-405) uses the same gradients at
+// finite strain: Ff = I + gradDf.T() (:312), sigmaf = neoHookeanElastic::correct(surfaceSymmTensorField&)
+// (neoHookeanElastic.C:306-352), and the divergence of (Jf Finvf.T() & Sf) & sigmaf (:273) -- formed per face as one
+// traction vector in k_uns_face_stress, summed by k_source_uns.
 // One thread per face for the face quantities (vertex gathers through the face->vertex CSR), the usual atomic-free row
 // gathers for the cell gradient and the divergence.  CPU restatement: oracle/s4f_oracle.cpp (unsUpdateGradients, unsLawFaces).
 #include <algorithm>
@@ -24,6 +28,7 @@ struct S4fUns {
     DevBuf<double> gradDf, sigmaf;       // [9*ldF], [6*ldF]
     DevBuf<double> gLS;                  // [9*ld] fvc::grad(D) of the gradScheme (non-orthogonal part of snGrad(D))
     DevBuf<int> procFace;                // [G] boundary face of each processor-patch ghost (decomposed meshes)
+    DevBuf<double> faceT;                // [3*ldF] total-Lagrangian model: (Jf Finvf.T() & Sf) & sigmaf, owner orientation
 };
 
 namespace {
@@ -147,13 +152,15 @@ __global__ void k_uns_face_stress(const int* __restrict__ fOwn, const int* __res
                                   const double* __restrict__ eCorr /* null when orthogonal */, const double* __restrict__ bN,
                                   const double* __restrict__ bSn, const double* __restrict__ D, const double* __restrict__ gLS,
                                   const double* __restrict__ fT, double* __restrict__ gradDf, double* __restrict__ sigmaf, int F, int B,
-                                  int ld, int ldF, long long nE, double mu, double lambda, S6u s0) {
+                                  int ld, int ldF, long long nE, double mu, double lambda, S6u s0,
+                                  const double* __restrict__ bSf, double* __restrict__ faceT /* null: linear geometry */, double K) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F + B) return;
-    double n[3], sn[3];
+    double n[3], sn[3], Sv[3];
     if (f < F) {
         const long long e = faceEntry[f];
         const double S[3] = {eSf[e], eSf[nE + e], eSf[2 * nE + e]};
+        Sv[0] = S[0]; Sv[1] = S[1]; Sv[2] = S[2];
         const double mag = sqrt(S[0] * S[0] + S[1] * S[1] + S[2] * S[2]);
 #pragma unroll
         for (int q = 0; q < 3; q++) n[q] = S[q] / mag;
@@ -175,7 +182,7 @@ __global__ void k_uns_face_stress(const int* __restrict__ fOwn, const int* __res
     } else {
         const int b = f - F;
 #pragma unroll
-        for (int q = 0; q < 3; q++) { n[q] = bN[(size_t)q * B + b]; sn[q] = bSn[(size_t)q * B + b]; }
+        for (int q = 0; q < 3; q++) { n[q] = bN[(size_t)q * B + b]; sn[q] = bSn[(size_t)q * B + b]; Sv[q] = bSf[(size_t)q * B + b]; }
     }
     double g[9];
 #pragma unroll
@@ -184,12 +191,39 @@ __global__ void k_uns_face_stress(const int* __restrict__ fOwn, const int* __res
     for (int i = 0; i < 3; i++)
 #pragma unroll
         for (int j = 0; j < 3; j++) g[3 * i + j] += n[i] * sn[j];
-    double e6[6], s[6];
-    t_symm(g, e6);
-    const double tr = s_tr(e6);
+    double s[6];
+    if (faceT) {
+        // Ff = I + gradDf.T(); neoHookeanElastic::correctF: bEbar = J^(-2/3) symm(F & F.T()), sigma = (0.5 K (J^2 - 1) I + mu dev(bEbar)) / J
+        double Fm[9], FT[9], FFT[9], b6[6], Fi[9];
+        t_transpose(g, Fm); Fm[0] += 1; Fm[4] += 1; Fm[8] += 1;
+        const double J = t_det(Fm);
+        t_transpose(Fm, FT); t_mul(Fm, FT, FFT); t_symm(FFT, b6);
+        const double sc = pow(J, -2.0 / 3.0);
 #pragma unroll
-    for (int q = 0; q < 6; q++) s[q] = 2.0 * mu * e6[q] + s0.v[q];
-    s[0] += lambda * tr; s[3] += lambda * tr; s[5] += lambda * tr;
+        for (int q = 0; q < 6; q++) b6[q] *= sc;
+        s_dev(b6, s);
+        const double sh = 0.5 * K * (pow(J, 2.0) - 1.0), rJ = 1.0 / J;
+#pragma unroll
+        for (int q = 0; q < 6; q++) s[q] *= mu;
+        s[0] += sh; s[3] += sh; s[5] += sh;
+#pragma unroll
+        for (int q = 0; q < 6; q++) s[q] *= rJ;
+        // (Jf Finvf.T() & Sf) & sigmaf
+        t_inv(Fm, Fi);
+        double a[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) a[i] = J * (Fi[i] * Sv[0] + Fi[3 + i] * Sv[1] + Fi[6 + i] * Sv[2]);      // Finv.T()_ij = Finv_ji
+        faceT[f] = a[0] * s[0] + a[1] * s[1] + a[2] * s[2];
+        faceT[(size_t)ldF + f] = a[0] * s[1] + a[1] * s[3] + a[2] * s[4];
+        faceT[2 * (size_t)ldF + f] = a[0] * s[2] + a[1] * s[4] + a[2] * s[5];
+    } else {
+        double e6[6];
+        t_symm(g, e6);
+        const double tr = s_tr(e6);
+#pragma unroll
+        for (int q = 0; q < 6; q++) s[q] = 2.0 * mu * e6[q] + s0.v[q];
+        s[0] += lambda * tr; s[3] += lambda * tr; s[5] += lambda * tr;
+    }
 #pragma unroll
     for (int q = 0; q < 9; q++) gradDf[(size_t)q * ldF + f] = g[q];
 #pragma unroll
@@ -232,7 +266,7 @@ __global__ void k_uns_proc_sngrad(const int* __restrict__ procFace, const int* _
 __global__ void k_bc_update_uns(const int* __restrict__ bKind, const double* __restrict__ bN, const double* __restrict__ bcValue,
                                 const double* __restrict__ bcPressure, const double* __restrict__ impK, const double* __restrict__ sigmaf,
                                 const double* __restrict__ gradDf, double* __restrict__ tracGrad, double* __restrict__ D, int F, int B,
-                                int bOff, int ld, int ldF) {
+                                int bOff, int ld, int ldF, int TL) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int kind = bKind[b];
@@ -249,6 +283,23 @@ __global__ void k_bc_update_uns(const int* __restrict__ bKind, const double* __r
         for (int q = 0; q < 6; q++) s[q] = sigmaf[(size_t)q * ldF + F + b];
         const double p = bcPressure[b], k = impK[bOff + b];
         s_to_t(s, M);
+        if (TL) {
+            // unsNonLinGeomTotalLagSolid::tractionBoundarySnGrad (:420-488): nCurrent = Jf Finvf.T() & n (not normalised);
+            // ((t - nCurrent p) - (nCurrent & sigmaf) + (n & (impK gradDf))) / impK
+            double Fm[9], Fi[9], nc[3];
+            t_transpose(g, Fm); Fm[0] += 1; Fm[4] += 1; Fm[8] += 1;
+            const double J = t_det(Fm);
+            t_inv(Fm, Fi);
+#pragma unroll
+            for (int i = 0; i < 3; i++) nc[i] = J * (Fi[i] * n[0] + Fi[3 + i] * n[1] + Fi[6 + i] * n[2]);
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const double ns = nc[0] * M[c] + nc[1] * M[3 + c] + nc[2] * M[6 + c];
+                const double ng = n[0] * g[c] + n[1] * g[3 + c] + n[2] * g[6 + c];
+                tracGrad[(size_t)c * B + b] = ((t[c] - nc[c] * p) - ns + k * ng) / k;
+            }
+            return;
+        }
 #pragma unroll
         for (int q = 0; q < 9; q++) M[q] -= k * g[q];
 #pragma unroll
@@ -265,7 +316,8 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_source_uns(const int* __restrict_
                                                          const double* __restrict__ eA, const double* __restrict__ D,
                                                          const double* __restrict__ sigmaf, const double* __restrict__ V,
                                                          const double* __restrict__ hist, double* __restrict__ source, int N, int ld,
-                                                         int ldF, long long nE, int nSlices, double rgx, double rgy, double rgz) {
+                                                         int ldF, long long nE, int nSlices, double rgx, double rgy, double rgz,
+                                                         const double* __restrict__ faceT /* null: Sf & sigmaf */) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nWarps = (gridDim.x * blockDim.x) >> 5;
@@ -280,7 +332,15 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_source_uns(const int* __restrict_
             const int ef = eFace[e];
             if (ef == 0) continue;
             const int f = (ef > 0 ? ef : -ef) - 1, cc = col[e];
-            const double S[3] = {eSf[e], eSf[nE + e], eSf[2 * nE + e]}, a = eA[e];
+            const double a = eA[e];
+            if (faceT) {        // total-Lagrangian: the face traction vector, owner orientation
+                const double sgn = ef > 0 ? 1.0 : -1.0;
+                acc[0] += sgn * faceT[f] - a * (D[cc] - DP[0]);
+                acc[1] += sgn * faceT[(size_t)ldF + f] - a * (D[(size_t)ld + cc] - DP[1]);
+                acc[2] += sgn * faceT[2 * (size_t)ldF + f] - a * (D[2 * (size_t)ld + cc] - DP[2]);
+                continue;
+            }
+            const double S[3] = {eSf[e], eSf[nE + e], eSf[2 * nE + e]};
             double sg[6];
 #pragma unroll
             for (int q = 0; q < 6; q++) sg[q] = sigmaf[(size_t)q * ldF + f];
@@ -322,7 +382,10 @@ int s4f_uns_setup(s4fgpu_ctx* c) {
         c->err = "unsLinearGeometry on a decomposed mesh: call s4fgpu_set_points before s4fgpu_set_geometry";
         return 1;
     }
-    if (c->law.kind != S4F_LAW_LINEAR_ELASTIC) { c->err = "unsLinearGeometry: linearElastic is the law available on the faces"; return 1; }
+    if (!c->unsTL() && c->law.kind != S4F_LAW_LINEAR_ELASTIC) { c->err = "unsLinearGeometry: linearElastic is the law available on the faces"; return 1; }
+    if (c->unsTL() && c->law.kind != S4F_LAW_NEO_HOOKEAN_ELASTIC) {
+        c->err = "unsNonLinearGeometryTotalLagrangian: neoHookeanElastic is the law available on the faces"; return 1;
+    }
     const int N = c->N, F = c->F, B = c->B;
     if (!c->uns) c->uns = new S4fUns();
     S4fUns& u = *c->uns;
@@ -401,6 +464,7 @@ int s4f_uns_setup(s4fgpu_ctx* c) {
         S4F_CHECK_CUDA(c, u.gradDf.alloc(9 * lf)); S4F_CHECK_CUDA(c, u.sigmaf.alloc(6 * lf));
     }
     if (c->nonOrth && u.gLS.n != 9 * (size_t)c->ld) S4F_CHECK_CUDA(c, u.gLS.alloc(9 * (size_t)c->ld));
+    if (c->unsTL()) { if (u.faceT.n != 3 * lf) S4F_CHECK_CUDA(c, u.faceT.alloc(3 * lf)); } else u.faceT.release();
     c->unsValid = true;
     return 0;
 }
@@ -439,7 +503,8 @@ int s4f_uns_gradients(s4fgpu_ctx* c) {
     S6u s0; for (int q = 0; q < 6; q++) s0.v[q] = c->law.sigma0[q];
     k_uns_face_stress<<<(nF + 127) / 128, 128, 0, c->stream>>>(u.fOwn.p, u.fNei.p, c->faceEntry.p, c->eSf.p, c->eDn.p, c->eW.p,
                                                               c->nonOrth ? c->eCorr.p : nullptr, c->bN.p, c->bSn.p, c->D.p, u.gLS.p, u.fT.p,
-                                                              u.gradDf.p, u.sigmaf.p, F, B, ld, u.ldF, c->nEntries, c->law.mu, c->law.lambda, s0);
+                                                              u.gradDf.p, u.sigmaf.p, F, B, ld, u.ldF, c->nEntries, c->law.mu, c->law.lambda, s0,
+                                                              c->bSf.p, c->unsTL() ? u.faceT.p : nullptr, c->law.K);
     c->launches++;
     S4F_CHECK_CUDA(c, cudaGetLastError());
     return s4f_halo_exchange(c, c->gradD.p, 9);
@@ -450,7 +515,7 @@ int s4f_uns_bc_update(s4fgpu_ctx* c) {
     S4fUns& u = *c->uns;
     if (c->B == 0) return 0;
     k_bc_update_uns<<<(c->B + 127) / 128, 128, 0, c->stream>>>(c->bKind.p, c->bN.p, c->bcValue.p, c->bcPressure.p, c->impK.p, u.sigmaf.p, u.gradDf.p,
-                                                              c->tracGrad.p, c->D.p, c->F, c->B, c->bOff(), c->ld, u.ldF);
+                                                              c->tracGrad.p, c->D.p, c->F, c->B, c->bOff(), c->ld, u.ldF, c->unsTL() ? 1 : 0);
     c->launches++;
     return 0;
 }
@@ -462,7 +527,7 @@ int s4f_uns_source(s4fgpu_ctx* c) {
     const double rs = c->law.rho;
     k_source_uns<<<s4f_grid(c->numSMs, (long long)c->nSlices * 32, 4), S4F_BLOCK, 0, c->stream>>>(
         c->slicePtr.p, c->col.p, u.eFace.p, c->eSf.p, c->eA.p, c->D.p, u.sigmaf.p, c->V.p, hist, c->source.p, c->N, c->ld, u.ldF, c->nEntries,
-        c->nSlices, rs * c->ctl.g[0], rs * c->ctl.g[1], rs * c->ctl.g[2]);
+        c->nSlices, rs * c->ctl.g[0], rs * c->ctl.g[1], rs * c->ctl.g[2], c->unsTL() ? u.faceT.p : nullptr);
     c->launches++;
     return 0;
 }

@@ -20,6 +20,12 @@ from ._lib import lib
 KERNELS = dict(spmv1=0, spmv3=1, pcg_iter=2, grad=3, law=4, rhs=5, pcg_p=6, pcg_xr=7, gamg_vcycle=8, gamg_step0=9, halo3=10, dot_reduce=11)
 
 
+def _euler_d2dt2(vf, vf_o, vf_oo, dt: float, dt0: float):
+    """[OF-ext] EulerD2dt2Scheme::fvcD2dt2 on a fixed mesh: rDeltaT2 (c vf - (c + c00) vf.o + c00 vf.oo)."""
+    c, c00 = (dt + dt0) / (2.0 * dt), (dt + dt0) / (2.0 * dt0)
+    return 4.0 / (dt + dt0) ** 2 * (c * vf - (c + c00) * vf_o + c00 * vf_oo)
+
+
 class SolidModel:
     # run-time selection table: solidProperties "solidModel" -> enum behind the C-ABI.  The plugin
     # registers the same names with the prefix "gpu" (foam_plugin/).
@@ -32,6 +38,8 @@ class SolidModel:
         "nonLinearGeometryTotalLagrangian": K.MODEL_NONLIN_TL,
         "gpuUnsLinearGeometry": K.MODEL_UNS_LIN_GEOM,
         "unsLinearGeometry": K.MODEL_UNS_LIN_GEOM,
+        "gpuUnsNonLinearGeometryTotalLagrangian": K.MODEL_UNS_NONLIN_TL,
+        "unsNonLinearGeometryTotalLagrangian": K.MODEL_UNS_NONLIN_TL,
         "gpuNonLinearGeometryUpdatedLagrangian": K.MODEL_NONLIN_UL,
         "nonLinearGeometryUpdatedLagrangian": K.MODEL_NONLIN_UL,
     }
@@ -104,14 +112,79 @@ class SolidModel:
                                          None if pr is None else K._dptr(pr)))
 
     # ---- reference-named interface ----
+    def _traction_patch(self, patch_name: str) -> K.BC:
+        bc = self.case.bcs.get(patch_name)
+        if bc is None or bc.kind != K.BC_SOLID_TRACTION:      # the FatalError of solidModel.C:1784-1800
+            raise RuntimeError(f"Boundary condition of patch {patch_name} should instead be type solidTraction")
+        return bc
+
     def setTraction(self, patch_name: str, traction, pressure=None) -> None:
-        """solidModel::setTraction (solidModel.C:1752-1817): new traction on a solidTraction patch."""
-        self.set_bc(patch_name, K.solidTraction(traction, pressure))
+        """solidModel::setTraction (solidModel.C:1752-1817): new traction on a solidTraction patch (the pressure is kept
+        unless given)."""
+        bc = self._traction_patch(patch_name)
+        new = K.solidTraction(traction, bc.pressure if pressure is None else pressure)
+        self.case.bcs[patch_name] = new
+        self.set_bc(patch_name, new)
+
+    def setPressure(self, patch_name: str, pressure) -> None:
+        """solidModel::setPressure (solidModel.C:1820-1890): new pressure on a solidTraction patch, the traction is kept."""
+        bc = self._traction_patch(patch_name)
+        new = K.solidTraction(bc.value if bc.value is not None else (0.0, 0.0, 0.0), pressure)
+        self.case.bcs[patch_name] = new
+        self.set_bc(patch_name, new)
+
+    # -- what the FSI coupler reads (fluidSolidInterface::updateDisplacement / AitkenCouplingInterface.C:67-136) --
+    def enable_interface_fields(self) -> None:
+        """Keep pointD.oldTime() and the boundary values of D at the two old time levels: what faceZonePointDisplacementOld
+        and faceZoneAcceleration need.  Costs one vol->point interpolation and one boundary download per time step."""
+        if getattr(self, "_iface", None) is None:
+            Db = self.get("D_b")
+            self._iface = dict(pointD_old=self.pointD(), Db_o=Db.copy(), Db_oo=Db.copy(), dt=None, dt0=None)
+
+    def patchMeshPoints(self, patch_name: str) -> np.ndarray:
+        """PrimitivePatch::meshPoints() of a patch: its points in the order the faces meet them."""
+        m = self.case.mesh
+        sl = m.patch_slice(patch_name)
+        verts = np.asarray(m.faces)[m.nInternalFaces + sl.start:m.nInternalFaces + sl.stop].ravel()
+        _, first = np.unique(verts, return_index=True)
+        return verts[np.sort(first)]
+
+    def faceZonePointDisplacementIncrement(self, patch_name: str) -> np.ndarray:
+        """solidModel::faceZonePointDisplacementIncrement (solidModel.C:1579-1593): pointDD at the interface's meshPoints."""
+        self.enable_interface_fields()
+        ids = self.patchMeshPoints(patch_name)
+        if self.case.controls.solidModel in (K.MODEL_NONLIN_TL, K.MODEL_NONLIN_UL):
+            return self.interpolate_to_points("DD", with_gradient=True)[ids]
+        return (self.pointD() - self._iface["pointD_old"])[ids]
+
+    def faceZonePointDisplacementOld(self, patch_name: str) -> np.ndarray:
+        """solidModel::faceZonePointDisplacementOld (solidModel.C:1596-1610): pointD.oldTime() at the interface's meshPoints."""
+        self.enable_interface_fields()
+        return self._iface["pointD_old"][self.patchMeshPoints(patch_name)]
+
+    def faceZoneAcceleration(self, patch_name: str) -> np.ndarray:
+        """solidModel::faceZoneAcceleration (solidModel.C:1613-1625): the patch field of fvc::d2dt2(D) with the case's d2dt2
+        scheme (Euler: EulerD2dt2Scheme, variable step; steadyState: zero)."""
+        self.enable_interface_fields()
+        sl = self.case.mesh.patch_slice(patch_name)
+        it, sch = self._iface, self.case.controls.d2dt2Scheme
+        Db = self.get("D_b")[sl]
+        if sch == K.D2DT2_STEADY_STATE or it["dt"] is None:
+            return np.zeros_like(Db)
+        if sch != K.D2DT2_EULER:
+            raise RuntimeError("faceZoneAcceleration: available with the Euler and steadyState d2dt2 schemes")
+        dt, dt0 = it["dt"], it["dt0"] if it["dt0"] else it["dt"]
+        return _euler_d2dt2(Db, it["Db_o"][sl], it["Db_oo"][sl], dt, dt0)
 
     def initialise(self) -> None:
         self._check(self.L.s4fgpu_initialise(self.h))
 
     def new_timestep(self, deltaT: float = 1.0) -> None:
+        it = getattr(self, "_iface", None)
+        if it is not None:          # oldTime() of the interface fields, before the device shifts its own time levels
+            it["pointD_old"] = self.pointD()
+            it["Db_oo"], it["Db_o"] = it["Db_o"], self.get("D_b")
+            it["dt0"], it["dt"] = it["dt"], float(deltaT)
         self._check(self.L.s4fgpu_new_timestep(self.h, deltaT))
 
     def outer_iteration(self) -> dict:

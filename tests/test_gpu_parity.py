@@ -11,6 +11,7 @@ import pytest
 
 from solids4foam_b200 import case as K
 from solids4foam_b200 import cases
+from solids4foam_b200 import mesh as M
 from s4f_testutil import rel_l2
 
 pytestmark = pytest.mark.gpu
@@ -883,3 +884,98 @@ def test_plate_hole_with_dic_follows_the_cpu_run():
     sg, so = g2.evolve(), o2.evolve()
     assert sg["converged"] and so["converged"] and abs(sg["nCorr"] - so["nCorr"]) <= 1
     assert rel_l2(g2.get("D"), o2.get("D")) < 1e-6 and rel_l2(g2.get("sigma"), o2.get("sigma")) < 1e-6
+
+
+def test_fsi_interface_accessors_against_oracle():
+    """What the FSI coupler calls on the solid (solidModel.C:1579-1625, :1752-1890): setTraction /
+    setPressure on the interface patch, then after evolve() the point displacement increment, the old point displacement and
+    the acceleration on the interface.  A dynamic (Euler) cantilever driven through three steps of a changing interface load;
+    the expected values are formed from the CPU oracle's fields with the definitions of the reference."""
+    from oracle.binding import OracleSolid
+    from solids4foam_b200.solid_model import SolidModel, _euler_d2dt2
+    kw = dict(nx=8, ny=4, nz=4, L=2.0, general=True, d2dt2Scheme=K.D2DT2_EULER, deltaT=2e-4, nCorrectors=4000, solutionTolerance=1e-10,
+              alternativeTolerance=1e-10, tolerance=1e-12, preconditioner=K.PRECOND_DIC)
+    g, o = SolidModel(cases.cantilever(**kw)), OracleSolid(cases.cantilever(**kw))
+    mesh = g.case.mesh
+    g.enable_interface_fields()
+    ids = g.patchMeshPoints("loaded")
+    sl = mesh.patch_slice("loaded")
+    quads = np.asarray(mesh.faces)[mesh.nInternalFaces + sl.start:mesh.nInternalFaces + sl.stop]
+    assert set(ids.tolist()) == set(quads.ravel().tolist()) and ids.size == (kw["ny"] + 1) * (kw["nz"] + 1) and ids[0] == quads[0, 0]
+    with pytest.raises(RuntimeError, match="solidTraction"):
+        g.setTraction("fixed", (0.0, 1.0, 0.0))
+    oP_old = o.interpolate_to_points("D", with_gradient=True)
+    Db_o = o.get("D_b").copy(); Db_oo = Db_o.copy()
+    dts = [2e-4, 2e-4, 3e-4]                      # the last step changes deltaT: EulerD2dt2Scheme's variable-step coefficients
+    for step, dt in enumerate(dts):
+        for s in (g, o):
+            s.new_timestep(dt)
+        trac = (0.0, -2e5 * (step + 1), 5e4 * step)
+        pres = 1e4 * step
+        g.setTraction("loaded", trac)
+        g.setPressure("loaded", pres)             # keeps the traction just set
+        o.set_bc("loaded", K.solidTraction(trac, pres))
+        sg, so = g.evolve(), o.evolve()
+        assert sg["converged"] and so["converged"]
+        oP = o.interpolate_to_points("D", with_gradient=True)
+        scale = np.abs(oP - oP_old).max()
+        assert np.abs(g.faceZonePointDisplacementIncrement("loaded") - (oP - oP_old)[ids]).max() < 1e-6 * scale
+        assert np.abs(g.faceZonePointDisplacementOld("loaded") - oP_old[ids]).max() <= 1e-6 * max(np.abs(oP_old).max(), scale)
+        dt0 = dts[step - 1] if step > 0 else dt
+        acc = _euler_d2dt2(o.get("D_b")[sl], Db_o[sl], Db_oo[sl], dt, dt0)
+        assert np.abs(g.faceZoneAcceleration("loaded") - acc).max() < 1e-3 * np.abs(acc).max()
+        oP_old = oP
+        Db_oo, Db_o = Db_o, o.get("D_b").copy()
+
+
+# ---------------------------------------------------------------------------------------------
+# unsNonLinGeomTotalLagSolid: finite-strain face stresses (SURVEY 8f row f1, neoHookeanElastic.C:306-352)
+# ---------------------------------------------------------------------------------------------
+def _uns_tl_case(warped: bool, **kw):
+    c = cases.neo_hookean_cantilever(8, 4, 4, general=True, L=2.0, solidModel=K.MODEL_UNS_NONLIN_TL, **kw)
+    if warped:
+        pmap = lambda p: p + 0.04 * np.sin(3.0 * p[:, [1, 2, 0]])
+        c.mesh = M.hex_box_general(8, 4, 4, 2.0, 1.0, 1.0, names=("fixed", "loaded", "yMin", "yMax", "zMin", "zMax"), point_map=pmap)
+    return c
+
+
+@pytest.mark.parametrize("warped", [False, True])
+def test_uns_total_lagrangian_face_stress_and_source_match_oracle(warped):
+    """k_uns_face_stress (Ff = I + gradDf.T(), neo-Hookean Cauchy stress on the faces, the face traction (Jf Finvf.T() & Sf) &
+    sigmaf), k_bc_update_uns with the deformed normal and k_source_uns against the oracle at a finite-strain state."""
+    from oracle.binding import OracleSolid
+    from solids4foam_b200.solid_model import SolidModel
+    g, o = SolidModel(_uns_tl_case(warped)), OracleSolid(_uns_tl_case(warped))
+    mesh = g.case.mesh
+    D = _finite_strain_D(mesh, 0.4)
+    for s in (g, o):
+        s.set("D", D)
+        s.op_grad()
+    assert rel_l2(g.get("gradDf"), o.get("gradDf")) < OP_TOL
+    assert rel_l2(g.get("sigmaf"), o.get("sigmaf")) < 1e-11
+    J = np.linalg.det(np.eye(3) + o.get("gradDf").reshape(-1, 3, 3).transpose(0, 2, 1))
+    assert J.min() < 0.9 and J.max() > 1.1                    # really a finite-strain state
+    for s in (g, o):
+        s.op_assemble()
+    assert rel_l2(g.get("tractionGradient_b"), o.get("tractionGradient_b")) < 1e-11
+    assert np.abs(g.get("source") - o.get("source")).max() / np.abs(o.get("source")).max() < 1e-11
+
+
+@pytest.mark.parametrize("warped", [False, True])
+def test_uns_total_lagrangian_evolve_matches_oracle(warped):
+    """The whole unsNonLinGeomTotalLagSolid::evolve loop with its own convergence criterion (max |D - D.prevIter| relative to
+    the increment of the step, never on the first iteration): same number of outer iterations, same solution."""
+    from oracle.binding import OracleSolid
+    from solids4foam_b200.solid_model import SolidModel
+    kw = dict(traction=(0.0, -2e4, 0.0), nCorrectors=8000, solutionTolerance=1e-9, tolerance=1e-11, relTol=0.01)
+    g = SolidModel.New(_uns_tl_case(warped, preconditioner=K.PRECOND_GAMG, **kw), "gpuUnsNonLinearGeometryTotalLagrangian")
+    o = OracleSolid(_uns_tl_case(warped, preconditioner=K.PRECOND_DIC, **kw))
+    for s in (g, o):
+        s.new_timestep(1.0)
+    sg, so = g.evolve(), o.evolve()
+    assert sg["converged"] and so["converged"], (sg, so)
+    assert abs(sg["nCorr"] - so["nCorr"]) <= max(3, so["nCorr"] // 50), (sg, so)
+    assert np.abs(o.get("D")[:, 1]).max() > 0.1                # a tenth of the beam height: geometrically non-linear
+    assert rel_l2(g.get("D"), o.get("D")) < SOLVE_TOL
+    assert rel_l2(g.get("sigmaf"), o.get("sigmaf")) < SOLVE_TOL
+    assert rel_l2(g.get("sigma"), o.get("sigma")) < SOLVE_TOL

@@ -548,3 +548,54 @@ def test_pressure_equation_against_a_scipy_restatement():
     for q in range(3):
         gp[:, q] = np.bincount(m.owner, weights=lsP[:F, q] * dp, minlength=N) - np.bincount(m.neighbour, weights=lsN[:, q] * dp, minlength=N)
     assert rel_l2(o.get("gradSigmaHyd"), gp) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------
+# unsNonLinGeomTotalLagSolid (finite-strain face stresses)
+# ---------------------------------------------------------------------------------------------
+def test_uns_total_lagrangian_face_stress_is_exact_for_a_uniform_deformation_gradient():
+    """With exact vertex values of a linear displacement field on a distorted mesh the face gradient is the exact gradient
+    (fvcGradf.C), so Ff = I + gradDf.T() is uniform and sigmaf must equal the closed-form compressible neo-Hookean Cauchy stress
+    (neoHookeanElastic.C:338-352) of that F on every internal face."""
+    G = np.array([[0.05, 0.02, -0.01], [0.03, -0.04, 0.02], [0.01, 0.02, 0.06]])
+    pmap = lambda p: p + 0.04 * np.sin(3.0 * p[:, [1, 2, 0]])
+    c = cases.neo_hookean_cantilever(5, 4, 3, general=True, L=2.0, solidModel=K.MODEL_UNS_NONLIN_TL)
+    c.mesh = M.hex_box_general(5, 4, 3, 2.0, 1.0, 1.0, names=("fixed", "loaded", "yMin", "yMax", "zMin", "zMax"), point_map=pmap)
+    o = OracleSolid(c)
+    m = c.mesh
+    F = m.nInternalFaces
+    lin = lambda X: 0.1 + X @ G.T
+    o.set("D", lin(m.C)); o.set("D_b", lin(m.Cf[F:]))
+    o.uns_grad_from_points(lin(m.points))
+    assert np.abs(o.get("gradDf").reshape(-1, 3, 3)[:F] - G.T).max() < 1e-14
+    Fm = np.eye(3) + G                                  # F = I + gradD.T(), gradD = G.T
+    J = np.linalg.det(Fm)
+    b = J ** (-2.0 / 3.0) * (Fm @ Fm.T)
+    sig = (0.5 * c.law.K * (J * J - 1.0) * np.eye(3) + c.law.mu * (b - np.trace(b) / 3.0 * np.eye(3))) / J
+    ref = np.array([sig[0, 0], sig[0, 1], sig[0, 2], sig[1, 1], sig[1, 2], sig[2, 2]])
+    assert np.abs(o.get("sigmaf")[:F] - ref).max() < 1e-12 * np.abs(ref).max()
+
+
+def test_uns_total_lagrangian_model_reduces_to_the_linear_uns_model_at_small_strain():
+    """unsNonLinGeomTotalLagSolid with neoHookeanElastic under a vanishing load against unsLinGeomSolid with linearElastic
+    (same E, nu): the neo-Hookean law linearises to Hooke's, J Finv.T() -> I, so the two discretisations must agree to O(strain);
+    this pins the finite-strain face path on the (independently pinned) linear one.  Under a large load it still converges,
+    with its own criterion, to a visibly non-linear state."""
+    kw = dict(general=True, L=2.0, E=3e6, nu=0.3, nCorrectors=5000, tolerance=1e-12, relTol=0.01, preconditioner=K.PRECOND_DIC)
+    a = OracleSolid(cases.cantilever(8, 4, 4, traction=(0.0, -1e-3, 0.0), solidModel=K.MODEL_UNS_LIN_GEOM, solutionTolerance=1e-10,
+                                     alternativeTolerance=1e-10, **kw))
+    b = OracleSolid(cases.neo_hookean_cantilever(8, 4, 4, traction=(0.0, -1e-3, 0.0), solidModel=K.MODEL_UNS_NONLIN_TL,
+                                                 solutionTolerance=1e-8, **kw))
+    for o in (a, b):
+        o.new_timestep(1.0)
+    sa, sb = a.evolve(), b.evolve()
+    assert sa["converged"] and sb["converged"]
+    assert rel_l2(b.get("D"), a.get("D")) < 1e-6
+    big = OracleSolid(cases.neo_hookean_cantilever(8, 4, 4, traction=(0.0, -2e4, 0.0), solidModel=K.MODEL_UNS_NONLIN_TL,
+                                                   solutionTolerance=1e-9, **kw))
+    big.new_timestep(1.0)
+    st = big.evolve()
+    assert st["converged"] and st["nCorr"] > 1 and st["relResidual"] <= 1e-9
+    lin = a.get("D") * (2e4 / 1e-3)                              # the linear answer scaled to the large load
+    assert big.get("D")[:, 1].min() < -0.1
+    assert 2e-3 < rel_l2(big.get("D"), lin) < 0.1                # close to, but not, the linear extrapolation
