@@ -56,12 +56,17 @@ enum {
                                             gradients built on the vertex displacements, fvc::div(mesh().Sf() & sigmaf);
                                             linearElastic, needs s4fgpu_set_points; decomposed meshes: processor faces take the
                                             corrected snGrad of an internal face, vertex values see the other ranks' cells */
-    S4F_MODEL_UNS_NONLIN_TL = 5          /* SM/unsNonLinGeomTotalLagSolid/unsNonLinGeomTotalLagSolid.C:218-405
+    S4F_MODEL_UNS_NONLIN_TL = 5,         /* SM/unsNonLinGeomTotalLagSolid/unsNonLinGeomTotalLagSolid.C:218-405
                                             ("unsNonLinearGeometryTotalLagrangian"): the same face gradients, Ff = I + gradDf.T()
                                             on the faces, neoHookeanElastic::correct(surfaceSymmTensorField&)
                                             (neoHookeanElastic.C:306-352), fvc::div((Jf Finvf.T() & Sf) & sigmaf); its own
                                             convergence criterion (:49-76, :333-378); neoHookeanElastic; the enforceLinear
                                             fall-back of the reference is not implemented */
+    S4F_MODEL_UNS_NONLIN_UL = 6          /* SM/unsNonLinGeomUpdatedLagSolid/unsNonLinGeomUpdatedLagSolid.C:247-345
+                                            ("unsNonLinearGeometryUpdatedLagrangian"): solves DD on the updated configuration;
+                                            relFf = I + gradDDf.T(), Ff = relFf & Ff.oldTime() on the faces,
+                                            fvc::div((relJf relFinvf.T() & Sf) & sigmaf), the updated-Lagrangian inertia terms,
+                                            solidModel::converged; mesh motion as S4F_MODEL_NONLIN_UL; neoHookeanElastic */
 };
 
 /* mechanicalLaw (constant/mechanicalProperties "type") */

@@ -110,7 +110,7 @@ class OracleSolid:
         return out
 
     def update_total_fields(self):
-        if self.case.controls.solidModel == K.MODEL_NONLIN_UL:
+        if self.case.controls.solidModel in K.MOVING_MESH_MODELS:
             pointDD = self.interpolate_to_points("DD")
             self._check(self.L.s4fo_update_total_fields(self.h))
             K.move_mesh(self.L, "s4fo_", self.h, self.case, pointDD, self._check)

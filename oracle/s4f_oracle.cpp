@@ -175,10 +175,13 @@ struct s4f_oracle {
     ivec cellStart, faceStart, crossFaces;
 
     int NB() const { return N + B; }
-    bool incremental() const { return ctl.solidModel == S4F_MODEL_NONLIN_TL || ctl.solidModel == S4F_MODEL_NONLIN_UL; }
-    bool UL() const { return ctl.solidModel == S4F_MODEL_NONLIN_UL; }
-    bool uns() const { return ctl.solidModel == S4F_MODEL_UNS_LIN_GEOM || ctl.solidModel == S4F_MODEL_UNS_NONLIN_TL; }
+    bool incremental() const { return ctl.solidModel == S4F_MODEL_NONLIN_TL || ctl.solidModel == S4F_MODEL_NONLIN_UL || ctl.solidModel == S4F_MODEL_UNS_NONLIN_UL; }
+    bool UL() const { return ctl.solidModel == S4F_MODEL_NONLIN_UL || ctl.solidModel == S4F_MODEL_UNS_NONLIN_UL; }
+    bool uns() const { return ctl.solidModel == S4F_MODEL_UNS_LIN_GEOM || ctl.solidModel == S4F_MODEL_UNS_NONLIN_TL || ctl.solidModel == S4F_MODEL_UNS_NONLIN_UL; }
     bool unsTL() const { return ctl.solidModel == S4F_MODEL_UNS_NONLIN_TL; }
+    bool unsUL() const { return ctl.solidModel == S4F_MODEL_UNS_NONLIN_UL; }
+    bool unsFinite() const { return unsTL() || unsUL(); }
+    dvec Ff, FfOld;                // unsNonLinGeomUpdatedLagSolid: total deformation gradient on the faces and its oldTime() [9 (F+B)]
     double unsMaxRes = 0;          // unsNonLinGeomTotalLagSolid::evolve: the largest relative residual of this time step
     const dvec& gradForLaw() const { return incremental() ? gradDtot : gradD; }   // the registered "grad(D)"
 };
@@ -288,7 +291,19 @@ void tractionSnGrad(const s4f_oracle& o, int b, double* g) {
     const double impK = o.impK[N + b], rImpK = 1.0 / impK;
     const double* gD = &o.gradD[9 * (N + b)];
     const double* sg = &o.sigma[6 * (N + b)];
-    if (o.unsTL()) {
+    if (o.unsUL()) {
+        // unsNonLinGeomUpdatedLagSolid::tractionBoundarySnGrad, unsNonLinGeomUpdatedLagSolid.C:373-419: nCurrent = relJf relFinvf.T() & n
+        // on the stress term only -- the pressure acts along n: ((t - n p) - (nCurrent & sigmaf) + (n & (impK gradDDf))) rImpK
+        const double* gf = &o.gradDf[9 * (size_t)(o.F + b)];
+        double rF[9]; transposeT(gf, rF); rF[0] += 1; rF[4] += 1; rF[8] += 1;
+        const double rJ = detT(rF);
+        double Fi[9], FiT[9]; invT(rF, Fi); transposeT(Fi, FiT);
+        double nc[3];
+        for (int i = 0; i < 3; i++) nc[i] = rJ * (FiT[3 * i] * n[0] + FiT[3 * i + 1] * n[1] + FiT[3 * i + 2] * n[2]);
+        double ns[3]; SvS(&o.sigmaf[6 * (size_t)(o.F + b)], nc, ns);
+        double ng[3]; vT(n, gf, ng);
+        for (int i = 0; i < 3; i++) g[i] = ((t[i] - n[i] * p) - ns[i] + impK * ng[i]) * rImpK;
+    } else if (o.unsTL()) {
         // unsNonLinGeomTotalLagSolid::tractionBoundarySnGrad, unsNonLinGeomTotalLagSolid.C:420-488 (enforceLinear off):
         // nCurrent = Jf Finvf.T() & n (not normalised); ((t - nCurrent p) - (nCurrent & sigmaf) + (n & (impK gradDf))) rImpK
         const double* gf = &o.gradDf[9 * (size_t)(o.F + b)];
@@ -337,7 +352,7 @@ void bcUpdateCoeffs(s4f_oracle& o) {
         else if (o.bcKind[p] == S4F_BC_FIXED_DISPLACEMENT) {
             for (int c = 0; c < 3; c++) {
                 double v = o.bcValue[3 * b + c];
-                if (o.ctl.solidModel == S4F_MODEL_NONLIN_TL || o.ctl.solidModel == S4F_MODEL_NONLIN_UL)
+                if (o.incremental())
                     v -= o.Dold[3 * (o.N + b) + c];        // DD field: disp -= Dold  (:279-287)
                 o.D[3 * (o.N + b) + c] = v;
             }
@@ -638,12 +653,19 @@ void unsUpdateGradients(s4f_oracle& o, bool interpolate = true) {
 void unsLawFaces(s4f_oracle& o) {
     const int nf = o.F + o.B;
     o.sigmaf.assign(6 * (size_t)nf, 0.0);
-    if (o.unsTL()) {
+    if (o.unsFinite()) {
         // unsNonLinGeomTotalLagSolid.C:312-330: Ff = I + gradDf.T(); then neoHookeanElastic::correct(surfaceSymmTensorField&)
         // -> correctF (neoHookeanElastic.C:306-352): J = det F; bEbar = J^(-2/3) symm(F & F.T()); s = mu dev(bEbar);
-        // sigma = (1/J) (0.5 K (J^2 - 1) I + s)
+        // sigma = (1/J) (0.5 K (J^2 - 1) I + s).
+        // unsNonLinGeomUpdatedLagSolid.C:283-301: relFf = I + gradDDf.T(); Ff = relFf & Ff.oldTime() (the field the law's
+        // updateF(surface) forms as well, mechanicalLaw.C updated-Lagrangian branch)
+        if ((int)o.FfOld.size() != 9 * nf) { o.FfOld.assign(9 * (size_t)nf, 0.0); for (int f = 0; f < nf; f++) for (int d = 0; d < 3; d++) o.FfOld[9 * (size_t)f + 4 * d] = 1; }
+        o.Ff.resize(9 * (size_t)nf);
         for (int f = 0; f < nf; f++) {
-            double Ff[9]; transposeT(&o.gradDf[9 * (size_t)f], Ff); Ff[0] += 1; Ff[4] += 1; Ff[8] += 1;
+            double rF[9]; transposeT(&o.gradDf[9 * (size_t)f], rF); rF[0] += 1; rF[4] += 1; rF[8] += 1;
+            double Ff[9];
+            if (o.unsUL()) mulTT(rF, &o.FfOld[9 * (size_t)f], Ff); else for (int q = 0; q < 9; q++) Ff[q] = rF[q];
+            for (int q = 0; q < 9; q++) o.Ff[9 * (size_t)f + q] = Ff[q];
             const double J = detT(Ff);
             double FT[9], FFT[9], b[6];
             transposeT(Ff, FT); mulTT(Ff, FT, FFT); symm(FFT, b);
@@ -1000,7 +1022,8 @@ D2dt2Coeffs d2dt2Coeffs(const s4fgpu_controls& ctl, double rho, int timeIndex) {
 double ulD2dt2(const s4f_oracle& o, dvec& hist) {
     const int N = o.N;
     hist.assign(3 * (size_t)N, 0.0);
-    for (int c = 0; c < N; c++) for (int q = 0; q < 3; q++) hist[3 * c + q] = o.rho[c] * o.ctl.g[q];     // rho_*g()
+    // rho_*g() (nonLinGeomUpdatedLagSolid.C:190); the uns model writes rho()*g(), the reference density (unsNonLinGeomUpdatedLagSolid.C:263)
+    for (int c = 0; c < N; c++) for (int q = 0; q < 3; q++) hist[3 * c + q] = (o.unsUL() ? o.law.rho : o.rho[c]) * o.ctl.g[q];
     if (o.ctl.d2dt2Scheme == S4F_D2DT2_STEADY_STATE) return 0.0;
     const double dt = o.ctl.deltaT, dt0 = o.ctl.deltaT0 > 0 ? o.ctl.deltaT0 : dt;
     if (o.ctl.d2dt2Scheme == S4F_D2DT2_EULER) {
@@ -1116,7 +1139,8 @@ void assembleSource(s4f_oracle& o) {
         // unsLinGeomSolid.C:129: fvc::div(mesh().Sf() & sigmaf_): the face stress itself, no interpolation
         for (int f = 0; f < F + B; f++) {
             double fl[3];
-            if (o.unsTL()) {      // unsNonLinGeomTotalLagSolid.C:273: fvc::div((Jf Finvf.T() & Sf) & sigmaf)
+            if (o.unsFinite()) {  // unsNonLinGeomTotalLagSolid.C:273: fvc::div((Jf Finvf.T() & Sf) & sigmaf); updated Lagrangian
+                                  // (unsNonLinGeomUpdatedLagSolid.C:262) the same with relJf, relFinvf: gradDf is grad(DD)f there
                 double Ff[9]; transposeT(&o.gradDf[9 * (size_t)f], Ff); Ff[0] += 1; Ff[4] += 1; Ff[8] += 1;
                 const double J = detT(Ff);
                 double Fi[9], FiT[9]; invT(Ff, Fi); transposeT(Fi, FiT);
@@ -1498,7 +1522,7 @@ bool convergedCheck(s4f_oracle& o, int iCorr, s4fgpu_stats* st) {
         return conv;
     }
     double denom = 0, dmax = 0, res = 0;
-    const bool incremental = (o.ctl.solidModel == S4F_MODEL_NONLIN_TL || o.ctl.solidModel == S4F_MODEL_NONLIN_UL);
+    const bool incremental = o.incremental();
     for (int c = 0; c < N; c++) {
         double a[3], m[3], r[3];
         for (int q = 0; q < 3; q++) { a[q] = o.D[3 * c + q] - o.Dold[3 * c + q]; m[q] = o.D[3 * c + q]; r[q] = o.D[3 * c + q] - o.Dprev[3 * c + q]; }
@@ -1544,6 +1568,7 @@ void outerIteration(s4f_oracle& o, int iCorr) {
     if (o.uns()) {                               // unsLinGeomSolid.C:146-157
         unsUpdateGradients(o);                   // interpolate(D, pointD); grad(D, pointD, gradD, gradDf)
         unsLawFaces(o);                          // mechanical().correct(sigmaf)
+        if (o.unsUL()) updateKinematics(o);      // after the loop (:318-330): relF, relFinv, relJ of the cells (density update)
         lawCorrect(o);                           // mechanical().correct(sigma)
         return;
     }
@@ -1855,6 +1880,7 @@ int s4fo_new_timestep(s4f_oracle* o, double deltaT) {
     else { o->Dold = o->D; o->gradDold = o->gradD; }
     o->sigmaOld = o->sigma;
     o->lawFold = o->lawF; o->lawJold = o->lawJ; o->bEbarOld = o->bEbar;
+    if (o->unsUL() && !o->Ff.empty()) o->FfOld = o->Ff;
     o->epsPOld = o->epsP; o->epsPEqOld = o->epsPEq; o->sigmaYOld = o->sigmaY;
     if (o->ctl.d2dt2Scheme != S4F_D2DT2_STEADY_STATE) o->matrixValid = false;
     return 0;

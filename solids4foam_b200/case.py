@@ -21,7 +21,7 @@ from .mesh import FvMesh, PROCESSOR
 
 # ---- enums (include/s4fgpu.h) ---------------------------------------------------------------
 BC_FIXED_DISPLACEMENT, BC_SOLID_TRACTION, BC_SOLID_SYMMETRY, BC_PROCESSOR = 0, 1, 2, 3
-MODEL_LIN_GEOM_TOTAL_DISP, MODEL_NONLIN_TL_TOTAL_DISP, MODEL_NONLIN_TL, MODEL_NONLIN_UL, MODEL_UNS_LIN_GEOM, MODEL_UNS_NONLIN_TL = 0, 1, 2, 3, 4, 5
+MODEL_LIN_GEOM_TOTAL_DISP, MODEL_NONLIN_TL_TOTAL_DISP, MODEL_NONLIN_TL, MODEL_NONLIN_UL, MODEL_UNS_LIN_GEOM, MODEL_UNS_NONLIN_TL, MODEL_UNS_NONLIN_UL = 0, 1, 2, 3, 4, 5, 6
 LAW_LINEAR_ELASTIC, LAW_NEO_HOOKEAN_ELASTIC, LAW_NEO_HOOKEAN_MISES_PLASTIC, LAW_LINEAR_ELASTIC_MISES_PLASTIC = 0, 1, 2, 3
 GRAD_LEAST_SQUARES, GRAD_GAUSS_LINEAR, GRAD_POINT_CELLS_LEAST_SQUARES = 0, 1, 2
 D2DT2_STEADY_STATE, D2DT2_EULER, D2DT2_BACKWARD = 0, 1, 2
@@ -49,7 +49,10 @@ MODEL_NAMES = {
     "nonLinearGeometryUpdatedLagrangian": MODEL_NONLIN_UL,
     "unsLinearGeometry": MODEL_UNS_LIN_GEOM,
     "unsNonLinearGeometryTotalLagrangian": MODEL_UNS_NONLIN_TL,
+    "unsNonLinearGeometryUpdatedLagrangian": MODEL_UNS_NONLIN_UL,
 }
+INCREMENTAL_MODELS = (MODEL_NONLIN_TL, MODEL_NONLIN_UL, MODEL_UNS_NONLIN_UL)      # the models that solve for DD
+MOVING_MESH_MODELS = (MODEL_NONLIN_UL, MODEL_UNS_NONLIN_UL)
 LAW_NAMES = {
     "linearElastic": LAW_LINEAR_ELASTIC,
     "neoHookeanElastic": LAW_NEO_HOOKEAN_ELASTIC,

@@ -86,7 +86,7 @@ int s4f_read_outer_scalars(s4fgpu_ctx* c, s4fgpu_stats* st, bool* converged, int
         *converged = conv;
         return 0;
     }
-    const bool incremental = (c->ctl.solidModel == S4F_MODEL_NONLIN_TL || c->ctl.solidModel == S4F_MODEL_NONLIN_UL);
+    const bool incremental = c->incremental();
     double denom = incremental ? o.maxMag : o.maxIncr;
     if (denom < 1e-15) denom = std::max(o.maxMag, 1e-15);
     const double residualvf = o.maxDelta / denom;
@@ -239,7 +239,7 @@ int s4fgpu_set_law(s4fgpu_handle c, const s4fgpu_law* law) {
 int s4fgpu_set_controls(s4fgpu_handle c, const s4fgpu_controls* ctl) {
     S4F_CHECK_CUDA(c, cudaSetDevice(c->device));
     S4F_REQUIRE(c, ctl, "set_controls: null");
-    S4F_REQUIRE(c, ctl->solidModel >= S4F_MODEL_LIN_GEOM_TOTAL_DISP && ctl->solidModel <= S4F_MODEL_UNS_NONLIN_TL, "set_controls: unknown solidModel");
+    S4F_REQUIRE(c, ctl->solidModel >= S4F_MODEL_LIN_GEOM_TOTAL_DISP && ctl->solidModel <= S4F_MODEL_UNS_NONLIN_UL, "set_controls: unknown solidModel");
     S4F_REQUIRE(c, ctl->solidModel != S4F_MODEL_NONLIN_TL || ctl->d2dt2Scheme == S4F_D2DT2_STEADY_STATE,
                 "set_controls: nonLinearGeometryTotalLagrangian is available with the steadyState d2dt2 scheme");
     S4F_REQUIRE(c, ctl->solver == S4F_SOLVER_PCG || ctl->solver == S4F_SOLVER_PBICGSTAB, "set_controls: solver PCG or PBiCGStab");
@@ -353,7 +353,10 @@ int s4fgpu_initialise(s4fgpu_handle c) {
     if ((rc = d2d(c, c->Dprev.p, c->D.p, 3 * (size_t)c->ld))) return rc;
     if ((rc = s4f_halo_exchange(c, c->D.p, 3))) return rc;
     c->mValid = false;
-    if ((rc = s4f_grad(c))) return rc;
+    c->unsGradientsOnly = true;
+    rc = s4f_grad(c);
+    c->unsGradientsOnly = false;
+    if (rc) return rc;
     if ((rc = s4f_update_totals(c, false, true))) return rc;
     if ((rc = s4f_kinematics(c))) return rc;                     // F, Finv, J of the finite-strain models (ctor, restart branch)
     if ((rc = s4f_assemble_matrix(c))) return rc;
@@ -393,6 +396,7 @@ int s4fgpu_new_timestep(s4fgpu_handle c, double deltaT) {
     }
     rc |= d2d(c, c->sigmaOld.p, c->sigma.p, 6 * ld);
     if (c->lawF.p) { rc |= d2d(c, c->lawFold.p, c->lawF.p, 9 * ld); rc |= d2d(c, c->lawJold.p, c->lawJ.p, ld); }
+    rc |= s4f_uns_new_timestep(c);
     if (c->bEbar.p) {
         rc |= d2d(c, c->bEbarOld.p, c->bEbar.p, 6 * ld); rc |= d2d(c, c->epsPOld.p, c->epsP.p, 6 * ld);
         rc |= d2d(c, c->epsPEqOld.p, c->epsPEq.p, ld); rc |= d2d(c, c->sigmaYOld.p, c->sigmaY.p, ld);

@@ -271,12 +271,16 @@ struct s4fgpu_ctx {
     long long totalInner = 0;
     s4fgpu_stats last{};
 
-    bool incremental() const { return ctl.solidModel == S4F_MODEL_NONLIN_TL || ctl.solidModel == S4F_MODEL_NONLIN_UL; }
-    bool UL() const { return ctl.solidModel == S4F_MODEL_NONLIN_UL; }
-    bool unsModel() const { return ctl.solidModel == S4F_MODEL_UNS_LIN_GEOM || ctl.solidModel == S4F_MODEL_UNS_NONLIN_TL; }
+    bool incremental() const { return ctl.solidModel == S4F_MODEL_NONLIN_TL || ctl.solidModel == S4F_MODEL_NONLIN_UL || ctl.solidModel == S4F_MODEL_UNS_NONLIN_UL; }
+    bool UL() const { return ctl.solidModel == S4F_MODEL_NONLIN_UL || ctl.solidModel == S4F_MODEL_UNS_NONLIN_UL; }
+    bool unsModel() const { return ctl.solidModel == S4F_MODEL_UNS_LIN_GEOM || ctl.solidModel == S4F_MODEL_UNS_NONLIN_TL || ctl.solidModel == S4F_MODEL_UNS_NONLIN_UL; }
     bool unsTL() const { return ctl.solidModel == S4F_MODEL_UNS_NONLIN_TL; }
+    bool unsUL() const { return ctl.solidModel == S4F_MODEL_UNS_NONLIN_UL; }
+    bool unsFinite() const { return unsTL() || unsUL(); }
     double unsMaxRes = 0;                 // unsNonLinGeomTotalLagSolid::evolve: largest relative residual of the time step
-    bool finiteStrain() const { return ctl.solidModel == S4F_MODEL_NONLIN_TL_TOTAL_DISP || ctl.solidModel == S4F_MODEL_NONLIN_TL || ctl.solidModel == S4F_MODEL_NONLIN_UL; }
+    bool unsGradientsOnly = false;        // s4fgpu_initialise: the uns models' constructors update the gradients, not sigmaf
+    // cell-level F / Finv / J of the solver (the uns updated-Lagrangian model needs relJ of the cells for its density update)
+    bool finiteStrain() const { return ctl.solidModel == S4F_MODEL_NONLIN_TL_TOTAL_DISP || ctl.solidModel == S4F_MODEL_NONLIN_TL || UL(); }
     bool pointCellsGrad() const { return ctl.gradScheme == S4F_GRAD_POINT_CELLS_LEAST_SQUARES; }
     // rows the least-squares gradient kernels run over
     const int* gradSlicePtr() const { return pointCellsGrad() ? gSlicePtr.p : slicePtr.p; }
@@ -310,6 +314,7 @@ int s4f_uns_setup(s4fgpu_ctx* c);                    // s4f_uns.cu: the face-str
 int s4f_uns_gradients(s4fgpu_ctx* c);
 int s4f_uns_bc_update(s4fgpu_ctx* c);
 int s4f_uns_source(s4fgpu_ctx* c);
+int s4f_uns_new_timestep(s4fgpu_ctx* c);        // Ff.oldTime() of the uns updated-Lagrangian model
 int s4f_uns_download(s4fgpu_ctx* c, int field, double* host);
 void s4f_uns_destroy(s4fgpu_ctx* c);
 int s4f_bc_sngrad_store(s4fgpu_ctx* c);              // snGrad() of every boundary face into bSn

@@ -663,7 +663,7 @@ __global__ void k_d2dt2_hist(const double* __restrict__ D1, const double* __rest
 struct UlCoeffs { double diag; double m[4]; double mo[3]; double moo[3]; double c[3]; double co[3]; double coo[3]; double g[3]; int mode; };
 static UlCoeffs ul_coeffs(const s4fgpu_ctx* c) {
     UlCoeffs k{}; k.mode = c->ctl.d2dt2Scheme;
-    for (int q = 0; q < 3; q++) k.g[q] = c->ctl.g[q];
+    for (int q = 0; q < 3; q++) k.g[q] = c->unsUL() ? 0.0 : c->ctl.g[q];      // the uns model adds rho()*g() itself (s4f_uns_source)
     const double dt = c->ctl.deltaT, dt0 = c->ctl.deltaT0 > 0 ? c->ctl.deltaT0 : dt;
     if (k.mode == S4F_D2DT2_EULER) {
         const double cf = (dt + dt0) / (2 * dt), cf00 = (dt + dt0) / (2 * dt0), r2 = 4.0 / ((dt + dt0) * (dt + dt0));

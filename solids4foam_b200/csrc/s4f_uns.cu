@@ -28,10 +28,16 @@ struct S4fUns {
     DevBuf<double> gradDf, sigmaf;       // [9*ldF], [6*ldF]
     DevBuf<double> gLS;                  // [9*ld] fvc::grad(D) of the gradScheme (non-orthogonal part of snGrad(D))
     DevBuf<int> procFace;                // [G] boundary face of each processor-patch ghost (decomposed meshes)
-    DevBuf<double> faceT;                // [3*ldF] total-Lagrangian model: (Jf Finvf.T() & Sf) & sigmaf, owner orientation
+    DevBuf<double> faceT;                // [3*ldF] finite-strain models: (Jf Finvf.T() & Sf) & sigmaf, owner orientation
+    DevBuf<double> Ff, FfOld;            // [9*ldF] updated-Lagrangian model: total deformation gradient of the faces, its oldTime()
 };
 
 namespace {
+
+__global__ void k_uns_fill(double* p, double v, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
 
 __global__ void k_uns_face_pre(const int* __restrict__ fPtr, const int* __restrict__ fVerts, const double* __restrict__ pts,
                                const double* __restrict__ pD, const int* __restrict__ faceEntry, const double* __restrict__ eSf,
@@ -153,7 +159,8 @@ __global__ void k_uns_face_stress(const int* __restrict__ fOwn, const int* __res
                                   const double* __restrict__ bSn, const double* __restrict__ D, const double* __restrict__ gLS,
                                   const double* __restrict__ fT, double* __restrict__ gradDf, double* __restrict__ sigmaf, int F, int B,
                                   int ld, int ldF, long long nE, double mu, double lambda, S6u s0,
-                                  const double* __restrict__ bSf, double* __restrict__ faceT /* null: linear geometry */, double K) {
+                                  const double* __restrict__ bSf, double* __restrict__ faceT /* null: linear geometry */, double K,
+                                  const double* __restrict__ FfOld /* updated Lagrangian only */, double* __restrict__ FfOut) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F + B) return;
     double n[3], sn[3], Sv[3];
@@ -191,11 +198,27 @@ __global__ void k_uns_face_stress(const int* __restrict__ fOwn, const int* __res
     for (int i = 0; i < 3; i++)
 #pragma unroll
         for (int j = 0; j < 3; j++) g[3 * i + j] += n[i] * sn[j];
+#pragma unroll
+    for (int q = 0; q < 9; q++) gradDf[(size_t)q * ldF + f] = g[q];
+    if (!sigmaf) return;            // constructor: the gradients only
     double s[6];
     if (faceT) {
         // Ff = I + gradDf.T(); neoHookeanElastic::correctF: bEbar = J^(-2/3) symm(F & F.T()), sigma = (0.5 K (J^2 - 1) I + mu dev(bEbar)) / J
-        double Fm[9], FT[9], FFT[9], b6[6], Fi[9];
-        t_transpose(g, Fm); Fm[0] += 1; Fm[4] += 1; Fm[8] += 1;
+        // updated Lagrangian (unsNonLinGeomUpdatedLagSolid.C:283-301): g is grad(DD)f, rF = relFf = I + g.T(), Ff = relFf & Ff.oldTime();
+        // the stress takes Ff, the flux (relJf relFinvf.T() & Sf) & sigmaf the relative tensors
+        double rF[9], Fm[9], FT[9], FFT[9], b6[6], Fi[9];
+        t_transpose(g, rF); rF[0] += 1; rF[4] += 1; rF[8] += 1;
+        if (FfOld) {
+            double Fo[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) Fo[q] = FfOld[(size_t)q * ldF + f];
+            t_mul(rF, Fo, Fm);
+#pragma unroll
+            for (int q = 0; q < 9; q++) FfOut[(size_t)q * ldF + f] = Fm[q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 9; q++) Fm[q] = rF[q];
+        }
         const double J = t_det(Fm);
         t_transpose(Fm, FT); t_mul(Fm, FT, FFT); t_symm(FFT, b6);
         const double sc = pow(J, -2.0 / 3.0);
@@ -208,11 +231,12 @@ __global__ void k_uns_face_stress(const int* __restrict__ fOwn, const int* __res
         s[0] += sh; s[3] += sh; s[5] += sh;
 #pragma unroll
         for (int q = 0; q < 6; q++) s[q] *= rJ;
-        // (Jf Finvf.T() & Sf) & sigmaf
-        t_inv(Fm, Fi);
+        // (Jf Finvf.T() & Sf) & sigmaf, relative tensors for the updated-Lagrangian model
+        t_inv(rF, Fi);
+        const double Jr = FfOld ? t_det(rF) : J;
         double a[3];
 #pragma unroll
-        for (int i = 0; i < 3; i++) a[i] = J * (Fi[i] * Sv[0] + Fi[3 + i] * Sv[1] + Fi[6 + i] * Sv[2]);      // Finv.T()_ij = Finv_ji
+        for (int i = 0; i < 3; i++) a[i] = Jr * (Fi[i] * Sv[0] + Fi[3 + i] * Sv[1] + Fi[6 + i] * Sv[2]);      // Finv.T()_ij = Finv_ji
         faceT[f] = a[0] * s[0] + a[1] * s[1] + a[2] * s[2];
         faceT[(size_t)ldF + f] = a[0] * s[1] + a[1] * s[3] + a[2] * s[4];
         faceT[2 * (size_t)ldF + f] = a[0] * s[2] + a[1] * s[4] + a[2] * s[5];
@@ -224,8 +248,6 @@ __global__ void k_uns_face_stress(const int* __restrict__ fOwn, const int* __res
         for (int q = 0; q < 6; q++) s[q] = 2.0 * mu * e6[q] + s0.v[q];
         s[0] += lambda * tr; s[3] += lambda * tr; s[5] += lambda * tr;
     }
-#pragma unroll
-    for (int q = 0; q < 9; q++) gradDf[(size_t)q * ldF + f] = g[q];
 #pragma unroll
     for (int q = 0; q < 6; q++) sigmaf[(size_t)q * ldF + f] = s[q];
 }
@@ -262,17 +284,45 @@ __global__ void k_uns_proc_sngrad(const int* __restrict__ procFace, const int* _
     for (int j = 0; j < 3; j++) bSn[(size_t)j * B + b] = sn[j];
 }
 
+// The face traction (relJf relFinvf.T() & Sf) & sigmaf again, from the stored grad(DD)f and sigmaf and the CURRENT face area
+// vectors: the reference evaluates the product when it assembles the equation, i.e. after updateTotalFields moved the mesh,
+// with the relative tensors still those of the last iteration of the previous step.
+__global__ void k_uns_flux_refresh(const int* __restrict__ faceEntry, const double* __restrict__ eSf, const double* __restrict__ bSf,
+                                   const double* __restrict__ gradDf, const double* __restrict__ sigmaf, double* __restrict__ faceT, int F,
+                                   int B, int ldF, long long nE) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F + B) return;
+    double S[3], g[9], s[6], rF[9], Fi[9];
+    if (f < F) { const long long e = faceEntry[f]; S[0] = eSf[e]; S[1] = eSf[nE + e]; S[2] = eSf[2 * nE + e]; }
+    else { const int b = f - F; S[0] = bSf[b]; S[1] = bSf[(size_t)B + b]; S[2] = bSf[2 * (size_t)B + b]; }
+#pragma unroll
+    for (int q = 0; q < 9; q++) g[q] = gradDf[(size_t)q * ldF + f];
+#pragma unroll
+    for (int q = 0; q < 6; q++) s[q] = sigmaf[(size_t)q * ldF + f];
+    t_transpose(g, rF); rF[0] += 1; rF[4] += 1; rF[8] += 1;
+    const double Jr = t_det(rF);
+    t_inv(rF, Fi);
+    double a[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) a[i] = Jr * (Fi[i] * S[0] + Fi[3 + i] * S[1] + Fi[6 + i] * S[2]);
+    faceT[f] = a[0] * s[0] + a[1] * s[1] + a[2] * s[2];
+    faceT[(size_t)ldF + f] = a[0] * s[1] + a[1] * s[3] + a[2] * s[4];
+    faceT[2 * (size_t)ldF + f] = a[0] * s[2] + a[1] * s[4] + a[2] * s[5];
+}
+
 // traction patches: unsLinGeomSolid::tractionBoundarySnGrad (unsLinGeomSolid.C:193-230) on the face fields
 __global__ void k_bc_update_uns(const int* __restrict__ bKind, const double* __restrict__ bN, const double* __restrict__ bcValue,
                                 const double* __restrict__ bcPressure, const double* __restrict__ impK, const double* __restrict__ sigmaf,
                                 const double* __restrict__ gradDf, double* __restrict__ tracGrad, double* __restrict__ D, int F, int B,
-                                int bOff, int ld, int ldF, int TL) {
+                                int bOff, int ld, int ldF, int TL /* 0 linear, 1 total, 2 updated Lagrangian */,
+                                const double* __restrict__ Dold /* incremental model: the field solved for is DD */) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int kind = bKind[b];
     if (kind == S4F_BC_FIXED_DISPLACEMENT) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) D[(size_t)c * ld + bOff + b] = bcValue[(size_t)c * B + b];
+        for (int c = 0; c < 3; c++)
+            D[(size_t)c * ld + bOff + b] = bcValue[(size_t)c * B + b] - (Dold ? Dold[(size_t)c * ld + bOff + b] : 0.0);   // fixedDisplacement...C:279-287
     } else if (kind == S4F_BC_SOLID_TRACTION) {
         double n[3], t[3], g[9], s[6], M[9];
 #pragma unroll
@@ -285,7 +335,8 @@ __global__ void k_bc_update_uns(const int* __restrict__ bKind, const double* __r
         s_to_t(s, M);
         if (TL) {
             // unsNonLinGeomTotalLagSolid::tractionBoundarySnGrad (:420-488): nCurrent = Jf Finvf.T() & n (not normalised);
-            // ((t - nCurrent p) - (nCurrent & sigmaf) + (n & (impK gradDf))) / impK
+            // ((t - nCurrent p) - (nCurrent & sigmaf) + (n & (impK gradDf))) / impK.  The updated-Lagrangian model
+            // (unsNonLinGeomUpdatedLagSolid.C:373-419) takes the relative tensors (g is grad(DD)f) and lets the pressure act along n
             double Fm[9], Fi[9], nc[3];
             t_transpose(g, Fm); Fm[0] += 1; Fm[4] += 1; Fm[8] += 1;
             const double J = t_det(Fm);
@@ -296,7 +347,7 @@ __global__ void k_bc_update_uns(const int* __restrict__ bKind, const double* __r
             for (int c = 0; c < 3; c++) {
                 const double ns = nc[0] * M[c] + nc[1] * M[3 + c] + nc[2] * M[6 + c];
                 const double ng = n[0] * g[c] + n[1] * g[3 + c] + n[2] * g[6 + c];
-                tracGrad[(size_t)c * B + b] = ((t[c] - nc[c] * p) - ns + k * ng) / k;
+                tracGrad[(size_t)c * B + b] = ((t[c] - (TL == 2 ? n[c] : nc[c]) * p) - ns + k * ng) / k;
             }
             return;
         }
@@ -382,9 +433,9 @@ int s4f_uns_setup(s4fgpu_ctx* c) {
         c->err = "unsLinearGeometry on a decomposed mesh: call s4fgpu_set_points before s4fgpu_set_geometry";
         return 1;
     }
-    if (!c->unsTL() && c->law.kind != S4F_LAW_LINEAR_ELASTIC) { c->err = "unsLinearGeometry: linearElastic is the law available on the faces"; return 1; }
-    if (c->unsTL() && c->law.kind != S4F_LAW_NEO_HOOKEAN_ELASTIC) {
-        c->err = "unsNonLinearGeometryTotalLagrangian: neoHookeanElastic is the law available on the faces"; return 1;
+    if (!c->unsFinite() && c->law.kind != S4F_LAW_LINEAR_ELASTIC) { c->err = "unsLinearGeometry: linearElastic is the law available on the faces"; return 1; }
+    if (c->unsFinite() && c->law.kind != S4F_LAW_NEO_HOOKEAN_ELASTIC) {
+        c->err = "unsNonLinearGeometryTotalLagrangian / UpdatedLagrangian: neoHookeanElastic is the law available on the faces"; return 1;
     }
     const int N = c->N, F = c->F, B = c->B;
     if (!c->uns) c->uns = new S4fUns();
@@ -464,7 +515,21 @@ int s4f_uns_setup(s4fgpu_ctx* c) {
         S4F_CHECK_CUDA(c, u.gradDf.alloc(9 * lf)); S4F_CHECK_CUDA(c, u.sigmaf.alloc(6 * lf));
     }
     if (c->nonOrth && u.gLS.n != 9 * (size_t)c->ld) S4F_CHECK_CUDA(c, u.gLS.alloc(9 * (size_t)c->ld));
-    if (c->unsTL()) { if (u.faceT.n != 3 * lf) S4F_CHECK_CUDA(c, u.faceT.alloc(3 * lf)); } else u.faceT.release();
+    bool keptState = false;
+    if (c->unsFinite()) { if (u.faceT.n != 3 * lf) S4F_CHECK_CUDA(c, u.faceT.alloc(3 * lf)); else keptState = true; } else u.faceT.release();
+    if (c->unsUL() && u.Ff.n != 9 * lf) {          // identity at the start; kept across mesh motion (face fields follow the topology)
+        S4F_CHECK_CUDA(c, u.Ff.alloc(9 * lf)); S4F_CHECK_CUDA(c, u.FfOld.alloc(9 * lf));
+        for (DevBuf<double>* b : {&u.Ff, &u.FfOld}) for (int d : {0, 4, 8}) {
+            k_uns_fill<<<(unsigned)((lf + 255) / 256), 256, 0, c->stream>>>(b->p + (size_t)d * lf, 1.0, (long long)lf);
+            c->launches++;
+        }
+    }
+    if (keptState) {      // a geometry refresh (mesh motion): the face tractions with the new area vectors
+        k_uns_flux_refresh<<<(u.nF + 127) / 128, 128, 0, c->stream>>>(c->faceEntry.p, c->eSf.p, c->bSf.p, u.gradDf.p, u.sigmaf.p, u.faceT.p, F, B, u.ldF,
+                                                                    c->nEntries);
+        c->launches++;
+        S4F_CHECK_CUDA(c, cudaGetLastError());
+    }
     c->unsValid = true;
     return 0;
 }
@@ -503,8 +568,11 @@ int s4f_uns_gradients(s4fgpu_ctx* c) {
     S6u s0; for (int q = 0; q < 6; q++) s0.v[q] = c->law.sigma0[q];
     k_uns_face_stress<<<(nF + 127) / 128, 128, 0, c->stream>>>(u.fOwn.p, u.fNei.p, c->faceEntry.p, c->eSf.p, c->eDn.p, c->eW.p,
                                                               c->nonOrth ? c->eCorr.p : nullptr, c->bN.p, c->bSn.p, c->D.p, u.gLS.p, u.fT.p,
-                                                              u.gradDf.p, u.sigmaf.p, F, B, ld, u.ldF, c->nEntries, c->law.mu, c->law.lambda, s0,
-                                                              c->bSf.p, c->unsTL() ? u.faceT.p : nullptr, c->law.K);
+                                                              u.gradDf.p, c->unsGradientsOnly ? nullptr : u.sigmaf.p /* constructor
+                                                              (unsLinGeomSolid.C:86-89): the gradients, sigmaf keeps its initial value */,
+                                                              F, B, ld, u.ldF, c->nEntries, c->law.mu, c->law.lambda, s0,
+                                                              c->bSf.p, c->unsFinite() ? u.faceT.p : nullptr, c->law.K,
+                                                              c->unsUL() ? u.FfOld.p : nullptr, c->unsUL() ? u.Ff.p : nullptr);
     c->launches++;
     S4F_CHECK_CUDA(c, cudaGetLastError());
     return s4f_halo_exchange(c, c->gradD.p, 9);
@@ -515,7 +583,8 @@ int s4f_uns_bc_update(s4fgpu_ctx* c) {
     S4fUns& u = *c->uns;
     if (c->B == 0) return 0;
     k_bc_update_uns<<<(c->B + 127) / 128, 128, 0, c->stream>>>(c->bKind.p, c->bN.p, c->bcValue.p, c->bcPressure.p, c->impK.p, u.sigmaf.p, u.gradDf.p,
-                                                              c->tracGrad.p, c->D.p, c->F, c->B, c->bOff(), c->ld, u.ldF, c->unsTL() ? 1 : 0);
+                                                              c->tracGrad.p, c->D.p, c->F, c->B, c->bOff(), c->ld, u.ldF,
+                                                              c->unsUL() ? 2 : (c->unsTL() ? 1 : 0), c->incremental() ? c->Dold.p : nullptr);
     c->launches++;
     return 0;
 }
@@ -523,12 +592,21 @@ int s4f_uns_bc_update(s4fgpu_ctx* c) {
 int s4f_uns_source(s4fgpu_ctx* c) {
     if (!c->unsValid) { int rc = s4f_uns_setup(c); if (rc) return rc; }
     S4fUns& u = *c->uns;
-    const double* hist = c->ctl.d2dt2Scheme == S4F_D2DT2_STEADY_STATE ? nullptr : c->d2Hist.p;
+    // updated Lagrangian: the explicit inertia terms exist for every scheme (fvc::d2dt2(rho_, D.oldTime())); rho()*g() with the
+    // reference density is added here, not inside the history (unsNonLinGeomUpdatedLagSolid.C:263)
+    const double* hist = (c->ctl.d2dt2Scheme == S4F_D2DT2_STEADY_STATE && !c->UL()) ? nullptr : c->d2Hist.p;
     const double rs = c->law.rho;
     k_source_uns<<<s4f_grid(c->numSMs, (long long)c->nSlices * 32, 4), S4F_BLOCK, 0, c->stream>>>(
         c->slicePtr.p, c->col.p, u.eFace.p, c->eSf.p, c->eA.p, c->D.p, u.sigmaf.p, c->V.p, hist, c->source.p, c->N, c->ld, u.ldF, c->nEntries,
-        c->nSlices, rs * c->ctl.g[0], rs * c->ctl.g[1], rs * c->ctl.g[2], c->unsTL() ? u.faceT.p : nullptr);
+        c->nSlices, rs * c->ctl.g[0], rs * c->ctl.g[1], rs * c->ctl.g[2], c->unsFinite() ? u.faceT.p : nullptr);
     c->launches++;
+    return 0;
+}
+
+// time-step roll of the face deformation gradient: Ff.oldTime() = Ff
+int s4f_uns_new_timestep(s4fgpu_ctx* c) {
+    if (!c->unsUL() || !c->uns || c->uns->Ff.n == 0) return 0;
+    S4F_CHECK_CUDA(c, cudaMemcpyAsync(c->uns->FfOld.p, c->uns->Ff.p, c->uns->Ff.n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     return 0;
 }
 

@@ -206,7 +206,7 @@ def read_controls(case_dir: str, **overrides) -> K.Controls:
     grad = grad[0] if isinstance(grad, list) else grad
     kw["gradScheme"] = {"Gauss": K.GRAD_GAUSS_LINEAR, "pointCellsLeastSquares": K.GRAD_POINT_CELLS_LEAST_SQUARES}.get(str(grad), K.GRAD_LEAST_SQUARES)
     sol = read_foam_dict(os.path.join(case_dir, "system", "fvSolution"))
-    field = "DD" if kw["solidModel"] in (K.MODEL_NONLIN_TL, K.MODEL_NONLIN_UL) else "D"
+    field = "DD" if kw["solidModel"] in K.INCREMENTAL_MODELS else "D"
     sd = _lookup(sol.get("solvers", {}), field, {})
     kw["solver"] = K.SOLVER_PBICGSTAB if str(sd.get("solver", "PCG")) == "PBiCGStab" else K.SOLVER_PCG
     pre = str(sd.get("preconditioner", "DIC"))
@@ -346,7 +346,7 @@ def read_case(case_dir: str, mesh: Optional[M.FvMesh] = None, **overrides) -> K.
         mesh = read_poly_mesh(os.path.join(case_dir, "constant", "polyMesh"))
     law = read_mechanical_law(case_dir)
     ctl = read_controls(case_dir, **overrides)
-    field = "DD" if ctl.solidModel in (K.MODEL_NONLIN_TL, K.MODEL_NONLIN_UL) and os.path.exists(os.path.join(case_dir, "0", "DD")) else "D"
+    field = "DD" if ctl.solidModel in K.INCREMENTAL_MODELS and os.path.exists(os.path.join(case_dir, "0", "DD")) else "D"
     bcs = read_boundary_conditions(case_dir, mesh, field)
     return K.SolidCase(mesh, bcs, law, ctl, name=os.path.basename(os.path.normpath(case_dir)))
 
@@ -563,7 +563,7 @@ def read_decomposed_case(case_dir: str, rank: int, nRanks: int, exchange, **over
     mesh = read_poly_mesh(os.path.join(pdir, "constant", "polyMesh"), rank=rank, nRanks=nRanks, exchange=exchange)
     law = read_mechanical_law(case_dir)
     ctl = read_controls(case_dir, **overrides)
-    field = "DD" if ctl.solidModel in (K.MODEL_NONLIN_TL, K.MODEL_NONLIN_UL) and os.path.exists(os.path.join(pdir, "0", "DD")) else "D"
+    field = "DD" if ctl.solidModel in K.INCREMENTAL_MODELS and os.path.exists(os.path.join(pdir, "0", "DD")) else "D"
     bcs = read_boundary_conditions(pdir, mesh, field)
     return K.SolidCase(mesh, bcs, law, ctl, name=os.path.basename(os.path.normpath(case_dir)) + f"/processor{rank}")
 

@@ -40,6 +40,8 @@ class SolidModel:
         "unsLinearGeometry": K.MODEL_UNS_LIN_GEOM,
         "gpuUnsNonLinearGeometryTotalLagrangian": K.MODEL_UNS_NONLIN_TL,
         "unsNonLinearGeometryTotalLagrangian": K.MODEL_UNS_NONLIN_TL,
+        "gpuUnsNonLinearGeometryUpdatedLagrangian": K.MODEL_UNS_NONLIN_UL,
+        "unsNonLinearGeometryUpdatedLagrangian": K.MODEL_UNS_NONLIN_UL,
         "gpuNonLinearGeometryUpdatedLagrangian": K.MODEL_NONLIN_UL,
         "nonLinearGeometryUpdatedLagrangian": K.MODEL_NONLIN_UL,
     }
@@ -153,7 +155,7 @@ class SolidModel:
         """solidModel::faceZonePointDisplacementIncrement (solidModel.C:1579-1593): pointDD at the interface's meshPoints."""
         self.enable_interface_fields()
         ids = self.patchMeshPoints(patch_name)
-        if self.case.controls.solidModel in (K.MODEL_NONLIN_TL, K.MODEL_NONLIN_UL):
+        if self.case.controls.solidModel in K.INCREMENTAL_MODELS:
             return self.interpolate_to_points("DD", with_gradient=True)[ids]
         return (self.pointD() - self._iface["pointD_old"])[ids]
 
@@ -211,7 +213,7 @@ class SolidModel:
 
     def movingMesh(self) -> bool:
         """solidModel::movingMesh(): the updated-Lagrangian model moves the mesh at the end of every step."""
-        return self.case.controls.solidModel == K.MODEL_NONLIN_UL
+        return self.case.controls.solidModel in K.MOVING_MESH_MODELS
 
     def updateTotalFields(self) -> None:
         """solidModel::updateTotalFields; for the updated-Lagrangian model nonLinGeomUpdatedLagSolid::updateTotalFields

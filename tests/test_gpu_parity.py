@@ -979,3 +979,42 @@ def test_uns_total_lagrangian_evolve_matches_oracle(warped):
     assert rel_l2(g.get("D"), o.get("D")) < SOLVE_TOL
     assert rel_l2(g.get("sigmaf"), o.get("sigmaf")) < SOLVE_TOL
     assert rel_l2(g.get("sigma"), o.get("sigma")) < SOLVE_TOL
+
+
+@pytest.mark.parametrize("dynamic", [False, True])
+def test_uns_updated_lagrangian_steps_match_oracle(dynamic):
+    """unsNonLinGeomUpdatedLagSolid (unsNonLinGeomUpdatedLagSolid.C:247-345): two load steps with the mesh moved in between
+    (device mesh motion on the GPU side, host route for the oracle): DD solve on the updated configuration, relFf / Ff =
+    relFf & Ff.oldTime() on the faces, the relative flux, the density update, solidModel::converged.  ``dynamic`` adds the
+    Euler inertia terms and gravity (rho()*g() with the reference density in this model)."""
+    from oracle.binding import OracleSolid
+    from solids4foam_b200.solid_model import SolidModel
+    kw = dict(general=True, L=2.0, nCorrectors=8000, tolerance=1e-14, relTol=0.0, solutionTolerance=1e-9, alternativeTolerance=1e-9,
+              solidModel=K.MODEL_UNS_NONLIN_UL)
+    if dynamic:
+        kw.update(d2dt2Scheme=K.D2DT2_EULER, deltaT=5e-3, g=(0.0, -9.81, 0.0))
+    g = SolidModel(cases.neo_hookean_cantilever(8, 4, 4, traction=(0.0, -1e4, 0.0), preconditioner=K.PRECOND_GAMG, **kw))
+    o = OracleSolid(cases.neo_hookean_cantilever(8, 4, 4, traction=(0.0, -1e4, 0.0), preconditioner=K.PRECOND_DIC, **kw))
+    assert g.movingMesh()
+    dt = 5e-3 if dynamic else 1.0
+    for step, load in enumerate((-1e4, -2e4)):
+        for s in (g, o):
+            s.new_timestep(dt)
+            s.set_bc("loaded", K.solidTraction((0.0, load, 0.0)))
+        for it in range(3):          # the same path from the first iterate on (tight inner solves: the preconditioners differ)
+            for s in (g, o):
+                s.outer_iteration()
+            assert rel_l2(g.get("DD"), o.get("DD")) < 1e-8, (step, it)
+            assert rel_l2(g.get("sigmaf"), o.get("sigmaf")) < 1e-8, (step, it)
+        sg, so = g.evolve(), o.evolve()
+        assert sg["converged"] and so["converged"], (step, sg, so)
+        assert rel_l2(g.get("DD"), o.get("DD")) < SOLVE_TOL
+        assert rel_l2(g.get("D"), o.get("D")) < SOLVE_TOL
+        assert rel_l2(g.get("sigmaf"), o.get("sigmaf")) < SOLVE_TOL
+        assert rel_l2(g.get("sigma"), o.get("sigma")) < SOLVE_TOL
+        for s in (g, o):
+            s.updateTotalFields()
+        assert np.abs(g.case.mesh.points - o.case.mesh.points).max() < 1e-9
+        assert rel_l2(g.get("rho"), o.get("rho")) < 1e-9
+    if not dynamic:
+        assert np.abs(o.get("D")[:, 1]).max() > 0.1

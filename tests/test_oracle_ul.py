@@ -599,3 +599,30 @@ def test_uns_total_lagrangian_model_reduces_to_the_linear_uns_model_at_small_str
     lin = a.get("D") * (2e4 / 1e-3)                              # the linear answer scaled to the large load
     assert big.get("D")[:, 1].min() < -0.1
     assert 2e-3 < rel_l2(big.get("D"), lin) < 0.1                # close to, but not, the linear extrapolation
+
+
+def test_uns_updated_lagrangian_first_step_equals_total_lagrangian_and_second_step_agrees():
+    """unsNonLinGeomUpdatedLagSolid against unsNonLinGeomTotalLagSolid: from the reference configuration relFf = Ff and the mesh
+    is the initial one, so the first load step is the same discrete problem (different convergence criteria: agreement to the
+    outer tolerance); after updateTotalFields (mesh moved, Ff.oldTime() stored, density updated) the second step is
+    discretised on the deformed mesh and agrees with the total-Lagrangian answer to discretisation accuracy."""
+    kw = dict(general=True, L=2.0, nCorrectors=8000, tolerance=1e-12, relTol=0.01, preconditioner=K.PRECOND_DIC)
+    tl = OracleSolid(cases.neo_hookean_cantilever(8, 4, 4, traction=(0.0, -1e4, 0.0), solidModel=K.MODEL_UNS_NONLIN_TL,
+                                                  solutionTolerance=1e-10, **kw))
+    ul = OracleSolid(cases.neo_hookean_cantilever(8, 4, 4, traction=(0.0, -1e4, 0.0), solidModel=K.MODEL_UNS_NONLIN_UL,
+                                                  solutionTolerance=1e-9, alternativeTolerance=1e-9, **kw))
+    for o in (tl, ul):
+        o.new_timestep(1.0)
+        assert o.evolve()["converged"]
+    assert rel_l2(ul.get("D"), tl.get("D")) < 1e-6
+    assert rel_l2(ul.get("sigmaf"), tl.get("sigmaf")) < 1e-6
+    p0 = ul.case.mesh.points.copy()
+    for o in (tl, ul):
+        o.update_total_fields()
+        o.new_timestep(1.0)
+        o.set_bc("loaded", K.solidTraction((0.0, -2e4, 0.0)))
+        assert o.evolve()["converged"]
+    assert np.abs(ul.case.mesh.points - p0).max() > 0.05          # the updated-Lagrangian mesh did move
+    assert np.abs(tl.get("D")[:, 1]).max() > 0.15
+    assert rel_l2(ul.get("D"), tl.get("D")) < 2e-3
+    assert rel_l2(ul.get("rho"), np.full(ul.case.mesh.nCells, ul.case.law.rho)) > 1e-4      # rho_ = rho_.oldTime() / relJ_
