@@ -307,6 +307,9 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = g.launch_count()
+    profiled = bool(os.environ.get("S4F_PROFILE_TIMED"))     # ncu --profile-from-start off: capture the timed region only
+    if profiled:
+        torch.cuda.profiler.start()
     g.timer_start()
     st = None
     stats = []
@@ -314,6 +317,8 @@ def main():
         st = g.outer_iteration()
         stats.append(st["nIterations"])
     ms = g.timer_stop()
+    if profiled:
+        torch.cuda.profiler.stop()
     launches = g.launch_count() - launches0
     barrier()
     clocks = sampler.stop() if rank == 0 else None

@@ -1132,7 +1132,11 @@ int s4f_amg_setup(s4fgpu_ctx* c) {
     if (c->nRanks == 1 && !getenv("S4F_AMG_HOST_SETUP")) {
         std::vector<std::unique_ptr<AmgDevLevel>> D;
         int rcd = s4f_amg_device_levels(c, D, 512, 3);
+        const double tAgg = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (!rcd) rcd = c->ctl.gamgSinglePrecision ? build_from_device<float>(c, D) : build_from_device<double>(c, D);
+        if (getenv("S4F_AMG_TIMING"))
+            fprintf(stderr, "libs4fgpu: GAMG set-up: agglomeration + Galerkin %.3f s, level build + coarsest inverse %.3f s\n", tAgg,
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() - tAgg);
         if (!rcd) {
             c->amg->setupSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             c->graphSerial++;
@@ -1145,6 +1149,10 @@ int s4f_amg_setup(s4fgpu_ctx* c) {
     const int N = c->N, F = c->F;
     std::vector<HostLevel> H(1);
     int rc;
+    const bool timing = getenv("S4F_AMG_TIMING") != nullptr;
+    auto lap = [&](const char* what) {
+        if (timing && c->rank == 0) fprintf(stderr, "libs4fgpu: GAMG host set-up: %6.3f s  after %s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), what);
+    };
     {
         HostLevel& L0 = H[0];
         L0.n = N; L0.own = c->own; L0.nei = c->nei; L0.a.resize(F);
@@ -1155,12 +1163,14 @@ int s4f_amg_setup(s4fgpu_ctx* c) {
         for (int q = 0; q < 3; q++) L0.diag[q].assign(d.begin() + (size_t)q * c->ld, d.begin() + (size_t)q * c->ld + N);
         if (c->nRanks > 1) { L0.dist = true; if ((rc = fine_interfaces(c, L0))) return rc; }
     }
+    lap("fine level download + interfaces");
     const int coarsest = 512;
     long long replicateBelow = 150000;          // global cells: below this a level costs less replicated than distributed
     if (const char* e = getenv("S4F_GAMG_REPLICATE_BELOW")) replicateBelow = atoll(e);
     while (H.back().dist) {
         HostLevel part;
         if ((rc = coarsen_distributed(c, H.back(), part))) return rc;
+        lap("coarsen_distributed");
         std::vector<int> cnt(c->nRanks);
         if ((rc = s4f_allgather_host(c, &part.n, sizeof(int), cnt.data()))) return rc;
         long long nGlobal = 0, fineGlobal = 0;
@@ -1172,6 +1182,7 @@ int s4f_amg_setup(s4fgpu_ctx* c) {
         if (nGlobal <= replicateBelow || stalled || H.size() >= 6) {
             HostLevel glob;
             if ((rc = gather_level(c, H.back(), part, glob))) return rc;
+            lap("gather_level");
             H.push_back(std::move(glob));
         } else H.push_back(std::move(part));
     }
@@ -1183,8 +1194,10 @@ int s4f_amg_setup(s4fgpu_ctx* c) {
         H.push_back(std::move(next));
     }
     if (H.back().n > 4096) { c->err = "GAMG: agglomeration stalled above the size of the dense coarsest solve"; return 1; }
+    lap("replicated levels");
     if (c->ctl.gamgSinglePrecision) rc = build<float>(c, H);
     else rc = build<double>(c, H);
+    lap("device level build");
     if (!rc) c->amg->setupSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     c->graphSerial++;
     return rc;

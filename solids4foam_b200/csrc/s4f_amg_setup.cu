@@ -13,7 +13,9 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 
 #include "s4f_amg_setup.h"
 #include "s4f_dev.cuh"
@@ -23,10 +25,22 @@ namespace {
 #define S4F_SETUP_MAXW 64
 
 struct Mat {                 // a matrix in SELL-32 rows on the device (fp64), per-component diagonal
-    int n = 0, ld = 0, nSlices = 0; long long nnz = 0;
+    int n = 0, ld = 0, nSlices = 0; long long nnz = 0; size_t nE = 0;      // nE: padded entries
     const int* slicePtr = nullptr; const int* col = nullptr; const double* a = nullptr; const double* dg = nullptr; int ldDg = 0;
-    DevBuf<int> slicePtrB, colB; DevBuf<double> aB, dgB;
+    DevBuf<int> slicePtrB, colB; DevBuf<double> aB, dgB;      // scratch, grown on demand and reused from pass to pass
     void own() { slicePtr = slicePtrB.p; col = colB.p; a = aB.p; dg = dgB.p; ldDg = ld; }
+};
+
+// cudaMalloc / cudaFree synchronise the device and cost up to milliseconds for large blocks: the temporaries of the passes
+// (15 passes, a dozen arrays each) live in buffers that only grow.  Measured at 8 M cells: 0.22-0.69 s of the set-up was
+// allocator time, the matching itself 0.12 s.
+template <class T>
+cudaError_t ensure(DevBuf<T>& b, size_t count) { return b.n >= count && b.p ? cudaSuccess : b.alloc(count, false); }
+struct Scratch {
+    DevBuf<int> match, pick, flag, scan, leaderOf, cnt, ent, cs, changed, agg, cursor;
+    DevBuf<char> tmp;
+    DevBuf<int> fail;
+    Mat ping, pong;
 };
 
 __device__ __forceinline__ unsigned int hash_edge(int a, int b) {
@@ -217,20 +231,25 @@ int read_int(s4fgpu_ctx* c, const int* p, int* host) {
     return 0;
 }
 
-// one pair-wise pass: matching on M, aggregates, Galerkin matrix C; agg[n] on return
-int pair_pass(s4fgpu_ctx* c, const Mat& M, Mat& C, DevBuf<int>& agg, DevBuf<char>& tmp, DevBuf<int>& fail) {
+// one pair-wise pass: matching on M, aggregates (S.agg[n]), Galerkin matrix C (in its scratch buffers)
+int pair_pass(s4fgpu_ctx* c, const Mat& M, Mat& C, Scratch& S) {
     const int n = M.n, g = (n + 255) / 256;
-    DevBuf<int> match, pick, flag, scan, leaderOf, cnt, ent;
-    S4F_CHECK_CUDA(c, match.alloc(n, false)); S4F_CHECK_CUDA(c, pick.alloc(n, false));
-    S4F_CHECK_CUDA(c, flag.alloc((size_t)n + 1)); S4F_CHECK_CUDA(c, scan.alloc((size_t)n + 1, false));
+    DevBuf<int>&match = S.match, &pick = S.pick, &flag = S.flag, &scan = S.scan, &leaderOf = S.leaderOf, &cnt = S.cnt, &ent = S.ent, &agg = S.agg;
+    DevBuf<char>& tmp = S.tmp;
+    S4F_CHECK_CUDA(c, ensure(match, n)); S4F_CHECK_CUDA(c, ensure(pick, n));
+    S4F_CHECK_CUDA(c, ensure(flag, (size_t)n + 1)); S4F_CHECK_CUDA(c, ensure(scan, (size_t)n + 1));
     S4F_CHECK_CUDA(c, cudaMemsetAsync(match.p, 0xFF, (size_t)n * sizeof(int), c->stream));
+    S4F_CHECK_CUDA(c, cudaMemsetAsync(flag.p, 0, ((size_t)n + 1) * sizeof(int), c->stream));
     // sweep rule for up to S4F_AMG_SWEEP_ROUNDS rounds (default 2048), then the finish rule; stop when a group of 4 rounds
     // matched nothing
     static const int sweepRounds = getenv("S4F_AMG_SWEEP_ROUNDS") ? atoi(getenv("S4F_AMG_SWEEP_ROUNDS")) : 2048;
-    DevBuf<int> changed;
-    S4F_CHECK_CUDA(c, changed.alloc(1));
+    DevBuf<int>& changed = S.changed;
+    S4F_CHECK_CUDA(c, ensure(changed, 1));
+    S4F_CHECK_CUDA(c, cudaMemsetAsync(changed.p, 0, sizeof(int), c->stream));
     bool sweep = sweepRounds > 0;
-    for (int round = 0, inPhase = 0; round < sweepRounds + 64; round++, inPhase++) {
+    const auto tm0 = std::chrono::steady_clock::now();
+    int roundsDone = 0;
+    for (int round = 0, inPhase = 0; round < sweepRounds + 64; round++, inPhase++, roundsDone++) {
         if (inPhase > 0 && inPhase % 4 == 0) {
             int h = 0;
             S4F_CHECK_CUDA(c, cudaMemcpyAsync(&h, changed.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -243,32 +262,41 @@ int pair_pass(s4fgpu_ctx* c, const Mat& M, Mat& C, DevBuf<int>& agg, DevBuf<char
         k_pair<<<g, 256, 0, c->stream>>>(n, pick.p, match.p, changed.p);
         c->launches += 2;
     }
+    if (getenv("S4F_AMG_TIMING")) {
+        cudaStreamSynchronize(c->stream);
+        fprintf(stderr, "libs4fgpu:   matching n = %d: %d rounds, %.1f ms\n", n, roundsDone,
+                1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - tm0).count());
+    }
     k_leader_flag<<<g, 256, 0, c->stream>>>(n, match.p, flag.p);
     c->launches++;
     int rc = exclusive_scan(c, flag.p, scan.p, n, tmp); if (rc) return rc;
     int nc = 0;
     if ((rc = read_int(c, scan.p + n, &nc))) return rc;
-    S4F_CHECK_CUDA(c, agg.alloc(n, false)); S4F_CHECK_CUDA(c, leaderOf.alloc(std::max(nc, 1), false));
+    S4F_CHECK_CUDA(c, ensure(agg, n)); S4F_CHECK_CUDA(c, ensure(leaderOf, std::max(nc, 1)));
     k_assign_agg<<<g, 256, 0, c->stream>>>(n, match.p, scan.p, agg.p, leaderOf.p);
     c->launches++;
     // coarse rows
     C.n = nc; C.nSlices = (nc + 31) / 32; C.ld = C.nSlices * 32; if (C.ld == 0) C.ld = 32;
-    S4F_CHECK_CUDA(c, cnt.alloc((size_t)std::max(nc, 1) + 1)); S4F_CHECK_CUDA(c, ent.alloc((size_t)C.nSlices + 1));
-    k_coarse_count<<<(nc + 127) / 128, 128, 0, c->stream>>>(nc, n, M.slicePtr, M.col, M.a, agg.p, leaderOf.p, match.p, cnt.p, fail.p);
+    S4F_CHECK_CUDA(c, ensure(cnt, (size_t)std::max(nc, 1) + 1)); S4F_CHECK_CUDA(c, ensure(ent, (size_t)C.nSlices + 1));
+    S4F_CHECK_CUDA(c, cudaMemsetAsync(cnt.p, 0, ((size_t)std::max(nc, 1) + 1) * sizeof(int), c->stream));
+    S4F_CHECK_CUDA(c, cudaMemsetAsync(ent.p, 0, ((size_t)C.nSlices + 1) * sizeof(int), c->stream));
+    k_coarse_count<<<(nc + 127) / 128, 128, 0, c->stream>>>(nc, n, M.slicePtr, M.col, M.a, agg.p, leaderOf.p, match.p, cnt.p, S.fail.p);
     k_slice_entries<<<(C.nSlices * 32 + 255) / 256, 256, 0, c->stream>>>(nc, C.nSlices, cnt.p, ent.p);
     c->launches += 2;
-    S4F_CHECK_CUDA(c, C.slicePtrB.alloc((size_t)C.nSlices + 1, false));
+    S4F_CHECK_CUDA(c, ensure(C.slicePtrB, (size_t)C.nSlices + 1));
     if ((rc = exclusive_scan(c, ent.p, C.slicePtrB.p, C.nSlices, tmp))) return rc;
     int nE = 0;
     if ((rc = read_int(c, C.slicePtrB.p + C.nSlices, &nE))) return rc;
     {   // true off-diagonal entries (for the byte counts)
-        DevBuf<int> cs; S4F_CHECK_CUDA(c, cs.alloc((size_t)nc + 1, false));
-        if ((rc = exclusive_scan(c, cnt.p, cs.p, nc, tmp))) return rc;
-        int tot = 0; if ((rc = read_int(c, cs.p + nc, &tot))) return rc;
+        S4F_CHECK_CUDA(c, ensure(S.cs, (size_t)nc + 1));
+        if ((rc = exclusive_scan(c, cnt.p, S.cs.p, nc, tmp))) return rc;
+        int tot = 0; if ((rc = read_int(c, S.cs.p + nc, &tot))) return rc;
         C.nnz = tot;
     }
-    S4F_CHECK_CUDA(c, C.colB.alloc(std::max(nE, 1), false)); S4F_CHECK_CUDA(c, C.aB.alloc(std::max(nE, 1), false));
-    S4F_CHECK_CUDA(c, C.dgB.alloc(3 * (size_t)C.ld));
+    C.nE = std::max(nE, 1);
+    S4F_CHECK_CUDA(c, ensure(C.colB, C.nE)); S4F_CHECK_CUDA(c, ensure(C.aB, C.nE));
+    S4F_CHECK_CUDA(c, ensure(C.dgB, 3 * (size_t)C.ld));
+    S4F_CHECK_CUDA(c, cudaMemsetAsync(C.dgB.p, 0, 3 * (size_t)C.ld * sizeof(double), c->stream));
     C.own();
     k_coarse_fill<<<(C.ld + 127) / 128, 128, 0, c->stream>>>(nc, n, M.slicePtr, M.col, M.a, M.dg, M.ldDg, agg.p, leaderOf.p, match.p, C.slicePtrB.p,
                                                            C.colB.p, C.aB.p, C.dgB.p, C.ld, C.ld);
@@ -282,59 +310,62 @@ int pair_pass(s4fgpu_ctx* c, const Mat& M, Mat& C, DevBuf<int>& agg, DevBuf<char
 // levels[0] describes the fine matrix (only `parent` is filled), levels[l >= 1] own their rows
 int s4f_amg_device_levels(s4fgpu_ctx* c, std::vector<std::unique_ptr<AmgDevLevel>>& levels, int coarsest, int mergeLevels) {
     levels.clear();
-    DevBuf<char> tmp; DevBuf<int> fail;
-    S4F_CHECK_CUDA(c, fail.alloc(1));
+    Scratch S;
+    S4F_CHECK_CUDA(c, S.fail.alloc(1));
     levels.emplace_back(new AmgDevLevel());
     levels[0]->n = c->N; levels[0]->ld = c->ld; levels[0]->nSlices = c->nSlices; levels[0]->nnz = c->nnzOff;
-    std::unique_ptr<Mat> cur(new Mat());
-    cur->n = c->N; cur->ld = c->ld; cur->nSlices = c->nSlices; cur->slicePtr = c->slicePtr.p; cur->col = c->col.p; cur->a = c->eA.p;
-    cur->dg = c->diagC.p; cur->ldDg = c->ld; cur->nnz = c->nnzOff;
-    while (cur->n > coarsest && levels.size() < 12) {
-        const int nFine = cur->n;
-        DevBuf<int> total;
+    Mat cur;            // the matrix being coarsened: the fine rows, then the rows of the level just made
+    cur.n = c->N; cur.ld = c->ld; cur.nSlices = c->nSlices; cur.slicePtr = c->slicePtr.p; cur.col = c->col.p; cur.a = c->eA.p;
+    cur.dg = c->diagC.p; cur.ldDg = c->ld; cur.nnz = c->nnzOff;
+    while (cur.n > coarsest && levels.size() < 12) {
+        const int nFine = cur.n;
+        DevBuf<int> total;                  // becomes the level's parent map
         S4F_CHECK_CUDA(c, total.alloc(nFine, false));
         k_iota<<<(nFine + 255) / 256, 256, 0, c->stream>>>(nFine, total.p);
         c->launches++;
-        std::unique_ptr<Mat> src;           // null: cur itself
-        const Mat* m = cur.get();
+        const Mat* m = &cur;
+        Mat* last = nullptr;
         int nc = nFine;
         for (int pass = 0; pass < mergeLevels; pass++) {
-            std::unique_ptr<Mat> dst(new Mat());
-            DevBuf<int> agg;
-            int rc = pair_pass(c, *m, *dst, agg, tmp, fail); if (rc) return rc;
-            k_compose<<<(nFine + 255) / 256, 256, 0, c->stream>>>(nFine, total.p, agg.p);
+            Mat* dst = (last == &S.ping) ? &S.pong : &S.ping;
+            int rc = pair_pass(c, *m, *dst, S); if (rc) return rc;
+            k_compose<<<(nFine + 255) / 256, 256, 0, c->stream>>>(nFine, total.p, S.agg.p);
             c->launches++;
-            S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));      // agg goes out of scope
             nc = dst->n;
-            src = std::move(dst);
-            m = src.get();
+            last = dst; m = dst;
             if (nc <= coarsest / 4) break;
         }
         int hf = 0;
-        { int rc = read_int(c, fail.p, &hf); if (rc) return rc; }
+        { int rc = read_int(c, S.fail.p, &hf); if (rc) return rc; }
         if (hf) { c->err = "GAMG device set-up: a coarse row has more than 64 neighbours"; return 1; }
         if (nc >= nFine) break;                 // no coarsening possible (no couplings)
         AmgDevLevel& F = *levels.back();
         F.parent.swap(total);
         levels.emplace_back(new AmgDevLevel());
         AmgDevLevel& L = *levels.back();
-        L.n = src->n; L.ld = src->ld; L.nSlices = src->nSlices; L.nnz = src->nnz;
-        L.slicePtr.swap(src->slicePtrB); L.col.swap(src->colB); L.a.swap(src->aB); L.dg.swap(src->dgB);
+        L.n = last->n; L.ld = last->ld; L.nSlices = last->nSlices; L.nnz = last->nnz;
+        // the level keeps exact-size copies; the scratch matrices go on to the next level
+        S4F_CHECK_CUDA(c, L.slicePtr.alloc((size_t)L.nSlices + 1, false)); S4F_CHECK_CUDA(c, L.col.alloc(last->nE, false));
+        S4F_CHECK_CUDA(c, L.a.alloc(last->nE, false)); S4F_CHECK_CUDA(c, L.dg.alloc(3 * (size_t)L.ld, false));
+        S4F_CHECK_CUDA(c, cudaMemcpyAsync(L.slicePtr.p, last->slicePtrB.p, ((size_t)L.nSlices + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+        S4F_CHECK_CUDA(c, cudaMemcpyAsync(L.col.p, last->colB.p, last->nE * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+        S4F_CHECK_CUDA(c, cudaMemcpyAsync(L.a.p, last->aB.p, last->nE * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        S4F_CHECK_CUDA(c, cudaMemcpyAsync(L.dg.p, last->dgB.p, 3 * (size_t)L.ld * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         // children of the new level's cells in the finer one, ascending
-        DevBuf<int> cnt, cursor;
-        S4F_CHECK_CUDA(c, cnt.alloc((size_t)L.n + 1)); S4F_CHECK_CUDA(c, cursor.alloc(std::max(L.n, 1)));
+        S4F_CHECK_CUDA(c, ensure(S.cnt, (size_t)L.n + 1)); S4F_CHECK_CUDA(c, ensure(S.cursor, std::max(L.n, 1)));
+        S4F_CHECK_CUDA(c, cudaMemsetAsync(S.cnt.p, 0, ((size_t)L.n + 1) * sizeof(int), c->stream));
+        S4F_CHECK_CUDA(c, cudaMemsetAsync(S.cursor.p, 0, (size_t)std::max(L.n, 1) * sizeof(int), c->stream));
         S4F_CHECK_CUDA(c, L.childPtr.alloc((size_t)L.n + 1, false)); S4F_CHECK_CUDA(c, L.child.alloc(std::max(nFine, 1), false));
-        k_child_count<<<(nFine + 255) / 256, 256, 0, c->stream>>>(nFine, F.parent.p, cnt.p);
-        int rc = exclusive_scan(c, cnt.p, L.childPtr.p, L.n, tmp); if (rc) return rc;
-        k_child_fill<<<(nFine + 255) / 256, 256, 0, c->stream>>>(nFine, F.parent.p, L.childPtr.p, cursor.p, L.child.p);
+        k_child_count<<<(nFine + 255) / 256, 256, 0, c->stream>>>(nFine, F.parent.p, S.cnt.p);
+        int rc = exclusive_scan(c, S.cnt.p, L.childPtr.p, L.n, S.tmp); if (rc) return rc;
+        k_child_fill<<<(nFine + 255) / 256, 256, 0, c->stream>>>(nFine, F.parent.p, L.childPtr.p, S.cursor.p, L.child.p);
         k_child_sort<<<(L.n + 127) / 128, 128, 0, c->stream>>>(L.n, L.childPtr.p, L.child.p);
         c->launches += 3;
-        S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
         // continue from the new level
-        cur.reset(new Mat());
-        cur->n = L.n; cur->ld = L.ld; cur->nSlices = L.nSlices; cur->slicePtr = L.slicePtr.p; cur->col = L.col.p; cur->a = L.a.p;
-        cur->dg = L.dg.p; cur->ldDg = L.ld; cur->nnz = L.nnz;
+        cur.n = L.n; cur.ld = L.ld; cur.nSlices = L.nSlices; cur.slicePtr = L.slicePtr.p; cur.col = L.col.p; cur.a = L.a.p;
+        cur.dg = L.dg.p; cur.ldDg = L.ld; cur.nnz = L.nnz;
     }
+    S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));      // the scratch buffers go out of scope
     S4F_CHECK_CUDA(c, cudaGetLastError());
     return 0;
 }
