@@ -160,3 +160,60 @@ def test_default_controls_are_the_reference_defaults():
     assert (c.tolerance, c.relTol, c.maxIter) == (1e-9, 0.1, 1000)
     with pytest.raises(KeyError):
         K.default_controls(noSuchKey=1)
+
+
+def test_fvmesh_geometry_under_an_affine_map_follows_the_exact_transformation_rules():
+    """A check of mesh.py's geometry that shares no formula with it (the oracle and the GPU path both take their geometry from
+    mesh.py, so parity cannot see an error there): under x -> A x + b a box mesh keeps planar faces, and continuum kinematics
+    gives every quantity of the mapped mesh exactly from the unmapped one -- volumes scale with det A, centroids map like points,
+    area vectors follow Nanson's formula det(A) A^-T Sf, a mid-way face keeps the weight 1/2, and the delta coefficient is
+    1 / (n . A d0)."""
+    A = np.array([[1.1, 0.35, -0.2], [0.15, 0.9, 0.25], [-0.1, 0.3, 1.2]])
+    b = np.array([0.3, -0.2, 0.5])
+    m0 = M.hex_box_general(5, 4, 3, 2.0, 1.0, 1.5)
+    m1 = M.hex_box_general(5, 4, 3, 2.0, 1.0, 1.5, point_map=lambda p: p @ A.T + b)
+    detA = np.linalg.det(A)
+    AinvT = np.linalg.inv(A).T
+    assert detA > 0 and not m1.is_orthogonal()
+    assert np.abs(m1.V - detA * m0.V).max() < 1e-13
+    assert np.abs(m1.C - (m0.C @ A.T + b)).max() < 1e-13
+    assert np.abs(m1.Cf - (m0.Cf @ A.T + b)).max() < 1e-13
+    Sf = detA * (m0.Sf @ AinvT.T)                                   # Nanson: Sf = det(A) A^-T Sf0
+    assert np.abs(m1.Sf - Sf).max() < 1e-13
+    assert np.abs(m1.magSf - np.linalg.norm(Sf, axis=1)).max() < 1e-13
+    F = m1.nInternalFaces
+    assert np.abs(m1.weights[:F] - 0.5).max() < 1e-13               # uniform spacing: the face is mid-way, affine maps keep ratios
+    n = Sf / np.linalg.norm(Sf, axis=1)[:, None]
+    d0 = np.concatenate([m0.C[m0.neighbour] - m0.C[m0.owner], m0.Cf[F:] - m0.C[m0.faceCells]])
+    d = d0 @ A.T
+    nd = np.einsum("ij,ij->i", n, d)
+    assert nd.min() > 0.05 * np.linalg.norm(d, axis=1).max()         # the limiter of the delta coefficients is not active here
+    assert np.abs(m1.nonOrthDeltaCoeffs - 1.0 / nd).max() < 1e-12 * (1.0 / nd).max()
+    corr = n[:F] - d[:F] / nd[:F, None]
+    assert np.abs(m1.nonOrthCorrVec[:F] - corr).max() < 1e-12
+    assert np.abs(np.einsum("ij,ij->i", m1.nonOrthCorrVec[:F], n[:F])).max() < 1e-12     # n . corr = 1 - (n . d) / (n . d) = 0
+
+
+@pytest.mark.parametrize("which", ["warped", "plateHole", "notchedBar"])
+def test_fvmesh_cells_are_closed_and_volumes_add_up(which):
+    """Formula-independent identities on non-planar meshes: the outward area vectors of every cell sum to zero, and the cell
+    volumes sum to the volume enclosed by the boundary faces, (1/3) sum_b Sf_b . Cf_b (divergence theorem on the triangulated
+    boundary surface)."""
+    if which == "warped":
+        m = M.hex_box_general(6, 5, 4, 2.0, 1.0, 1.0, point_map=lambda p: p + 0.05 * np.sin(3.0 * p[:, [1, 2, 0]]))
+    elif which == "plateHole":
+        m = M.plate_hole(refine=1)
+    else:
+        m = cases.notched_bar(12, 4, 4).mesh
+    F = m.nInternalFaces
+    tot = np.zeros((m.nCells, 3))
+    np.add.at(tot, m.owner, m.Sf[:F]); np.add.at(tot, m.neighbour, -m.Sf[:F])
+    if which != "plateHole":                  # 2-D case: the faces of the empty patches are not part of the fvMesh
+        np.add.at(tot, m.faceCells, m.Sf[F:])
+        assert np.abs(tot).max() < 1e-14 * m.magSf.max() * 10
+        vol = np.einsum("ij,ij->", m.Sf[F:], m.Cf[F:]) / 3.0
+        assert abs(m.V.sum() - vol) < 1e-3 * vol       # non-planar faces: Cf is the area-magnitude-weighted centroid, not the exact first moment
+    else:
+        np.add.at(tot, m.faceCells, m.Sf[F:])
+        assert np.abs(tot[:, :2]).max() < 1e-13        # closed in the plane; the z faces are the empty patches
+        assert abs(m.V.sum() - 0.5 * (4.0 - np.pi * 0.25 / 4.0)) < 1e-3 * m.V.sum()    # quarter plate 2 x 2 minus a quarter disc r = 0.5, thickness 0.5 (polygonal hole)
