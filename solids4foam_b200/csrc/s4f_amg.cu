@@ -22,6 +22,8 @@
 // ranks and the rest of the hierarchy is replicated (identical arithmetic on every rank, no communication).
 #include <algorithm>
 #include <chrono>
+#include <cooperative_groups.h>
+#include <type_traits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -32,6 +34,7 @@
 #include "s4f_comm.h"
 #include "s4f_dev.cuh"
 
+namespace cg = cooperative_groups;
 namespace {
 
 // ================================================================================================
@@ -454,6 +457,112 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_amg_copy(const T* __restrict__ sr
         for (int q = 0; q < 3; q++) if (a[q]) dst[(size_t)q * ld + i] = src[(size_t)q * ld + i];
 }
 
+
+// ---- the small levels of the hierarchy as ONE kernel -----------------------------------------------------------------------
+// An experiment kept as an option (S4F_AMG_TAIL_MAX, off by default -- it is slower, see record_tail): below ~20 k rows a
+// level's kernels look launch-floor-bound: 9 launches per visit, visited twice per K-cycle.  The V-cycle from such a level
+// down can be recorded once, at set-up, as a list of operations (the same calls that launch the kernels above, in recording
+// mode), and replayed by one thread-block cluster of 8 x 1024 threads that steps through the list with a hardware cluster
+// barrier between operations instead of a kernel boundary.  Same arithmetic, same summation order inside a row.
+enum { TAIL_FIRST = 0, TAIL_STEP = 1, TAIL_RESID = 2, TAIL_RESTRICT = 3, TAIL_PROLONG = 4, TAIL_DENSE = 5, TAIL_COPY = 6 };
+template <class T>
+struct TailOp {
+    int kind, n, ld, ldc, nSlices, prevMode;
+    const int *slicePtr, *col, *idxA, *idxB;          // idxA/idxB: childPtr/child (restrict) or parent (prolong)
+    const T *a, *dg, *b, *x, *xprev;
+    T* xo;
+    T c1, c2;
+};
+#define S4F_TAIL_CTAS 8
+#define S4F_TAIL_THREADS 1024
+template <class T>
+__global__ void __cluster_dims__(S4F_TAIL_CTAS, 1, 1) __launch_bounds__(S4F_TAIL_THREADS, 1)
+k_amg_tail(const TailOp<T>* __restrict__ ops, int nOps, const int* __restrict__ act) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int tid = cluster.block_rank() * blockDim.x + threadIdx.x, nT = cluster.num_blocks() * blockDim.x;
+    const bool aq[3] = {act[0] != 0, act[1] != 0, act[2] != 0};
+    for (int o = 0; o < nOps; o++) {
+        const TailOp<T> op = ops[o];
+        const int n = op.n, ld = op.ld;
+        if (op.kind == TAIL_FIRST) {
+            for (int i = tid; i < n; i += nT)
+#pragma unroll
+                for (int q = 0; q < 3; q++) if (aq[q]) op.xo[(size_t)q * ld + i] = op.c2 * __ldcg(&op.b[(size_t)q * ld + i]) / op.dg[(size_t)q * ld + i];
+        } else if (op.kind == TAIL_STEP || op.kind == TAIL_RESID) {
+            for (int row = tid; row < op.nSlices * 32; row += nT) {
+                const int sl = row >> 5, lane = row & 31, base = op.slicePtr[sl], width = (op.slicePtr[sl + 1] - base) >> 5;
+                T s0 = 0, s1 = 0, s2 = 0;
+                for (int k0 = 0; k0 < width; k0 += 4) {
+                    int cc[4]; T e[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const bool ok = k0 + k < width;
+                        const int idx = base + 32 * (ok ? k0 + k : k0) + lane;
+                        cc[k] = op.col[idx];
+                        e[k] = ok ? op.a[idx] : (T)0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (aq[0]) s0 += e[k] * __ldcg(&op.x[cc[k]]);
+                        if (aq[1]) s1 += e[k] * __ldcg(&op.x[cc[k] + ld]);
+                        if (aq[2]) s2 += e[k] * __ldcg(&op.x[cc[k] + 2 * ld]);
+                    }
+                }
+                if (row < n) {
+                    const T acc[3] = {s0, s1, s2};
+#pragma unroll
+                    for (int q = 0; q < 3; q++) {
+                        if (!aq[q]) continue;
+                        const int j = q * ld + row;
+                        const T xv = __ldcg(&op.x[j]), d = op.dg[j];
+                        const T r = __ldcg(&op.b[j]) - (d * xv - acc[q]);
+                        if (op.kind == TAIL_RESID) op.xo[j] = r;
+                        else {
+                            T xn = xv + op.c2 * r / d;
+                            if (op.prevMode == 1) xn += op.c1 * (xv - __ldcg(&op.xprev[j]));
+                            else if (op.prevMode == 2) xn += op.c1 * xv;
+                            op.xo[j] = xn;
+                        }
+                    }
+                }
+            }
+        } else if (op.kind == TAIL_RESTRICT) {          // n = coarse rows, ld = fine ld, ldc = coarse ld
+            for (int I = tid; I < n; I += nT) {
+                T s0 = 0, s1 = 0, s2 = 0;
+                for (int e = op.idxA[I]; e < op.idxA[I + 1]; e++) {
+                    const int i = op.idxB[e];
+                    if (aq[0]) s0 += __ldcg(&op.x[i]);
+                    if (aq[1]) s1 += __ldcg(&op.x[(size_t)ld + i]);
+                    if (aq[2]) s2 += __ldcg(&op.x[2 * (size_t)ld + i]);
+                }
+                op.xo[I] = s0; op.xo[(size_t)op.ldc + I] = s1; op.xo[2 * (size_t)op.ldc + I] = s2;
+            }
+        } else if (op.kind == TAIL_PROLONG) {           // x (fine, in xo) += c1 * e[parent]; e = op.x with ldc
+            for (int i = tid; i < n; i += nT) {
+                const int I = op.idxA[i];
+#pragma unroll
+                for (int q = 0; q < 3; q++) if (aq[q]) op.xo[(size_t)q * ld + i] = __ldcg(&op.xo[(size_t)q * ld + i]) + op.c1 * __ldcg(&op.x[(size_t)q * op.ldc + I]);
+            }
+        } else if (op.kind == TAIL_DENSE) {             // a = inverse [3][n][n]; one warp per (row, component)
+            const int lane = tid & 31;
+            for (int gw = tid >> 5; gw < 3 * n; gw += nT >> 5) {
+                const int q = gw / n, i = gw % n;
+                const T* row = op.a + ((size_t)q * n + i) * n;
+                T sum = 0;
+                for (int k = lane; k < n; k += 32) sum += row[k] * __ldcg(&op.b[(size_t)q * ld + k]);
+#pragma unroll
+                for (int sh = 16; sh > 0; sh >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, sh);
+                if (lane == 0) op.xo[(size_t)q * ld + i] = sum;
+            }
+        } else {                                        // TAIL_COPY
+            for (int i = tid; i < n; i += nT)
+#pragma unroll
+                for (int q = 0; q < 3; q++) if (aq[q]) op.xo[(size_t)q * ld + i] = __ldcg(&op.x[(size_t)q * ld + i]);
+        }
+        cluster.sync();
+    }
+}
+
 // ================================================================================================
 // hierarchy
 // ================================================================================================
@@ -503,6 +612,11 @@ struct Hierarchy : S4fAmg {
     const int* act = nullptr;           // device int[3]: components to work on (the fused PCG's active flags, or all ones)
     double omega = 2.2;
     double theta = 0, delta = 0;
+    // the V-cycle from level `tailLevel` down as one kernel (k_amg_tail): recorded once, after the levels are built
+    int tailLevel = -1;
+    bool recording = false;
+    std::vector<TailOp<T>> tailHost;
+    DevBuf<TailOp<T>> tailOps;
 
     int halo(s4fgpu_ctx* c, Level<T>& L, T* x) {
         if (!L.dist || !L.halo) return 0;
@@ -647,6 +761,15 @@ struct Hierarchy : S4fAmg {
     template <class TB, class TO>
     int step(s4fgpu_ctx* c, Level<T>& L, const TB* b, int ldb, const T* xin, const T* xprev, int prevMode, TO* xout, int ldo, double c1, double c2) {
         const int grid = step_grid(c, L);
+        if (recording) {
+            if constexpr (std::is_same<TB, T>::value && std::is_same<TO, T>::value) {
+                TailOp<T> op{}; op.kind = TAIL_STEP; op.n = L.n; op.ld = L.ld; op.nSlices = L.nSlices; op.prevMode = prevMode;
+                op.slicePtr = L.slicePtr; op.col = L.col; op.a = L.a; op.dg = L.dg.p; op.b = b; op.x = xin; op.xprev = xprev; op.xo = xout;
+                op.c1 = (T)c1; op.c2 = (T)c2;
+                tailHost.push_back(op);
+            }
+            return 0;
+        }
         int rc = halo(c, L, const_cast<T*>(xin)); if (rc) return rc;
         k_amg_step<T, TB, TO, 0><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, b, xin, xprev, xout, L.n, L.ld, ldb, ldo,
                                                                      L.nSlices, (T)c1, (T)c2, prevMode, act);
@@ -662,8 +785,15 @@ struct Hierarchy : S4fAmg {
         int k0 = 0, rc;
         if (fromZero) {
             const int grid = s4f_grid(c->numSMs, L.n);
-            k_amg_first<T, TB><<<grid, S4F_BLOCK, 0, c->stream>>>(L.dg.p, b, R.buf[R.cur], L.n, L.ld, ldb, (T)(1.0 / theta), act);
-            c->launches++;
+            if (recording) {
+                if constexpr (std::is_same<TB, T>::value) {
+                    TailOp<T> op{}; op.kind = TAIL_FIRST; op.n = L.n; op.ld = L.ld; op.dg = L.dg.p; op.b = b; op.xo = R.buf[R.cur]; op.c2 = (T)(1.0 / theta);
+                    tailHost.push_back(op);
+                }
+            } else {
+                k_amg_first<T, TB><<<grid, S4F_BLOCK, 0, c->stream>>>(L.dg.p, b, R.buf[R.cur], L.n, L.ld, ldb, (T)(1.0 / theta), act);
+                c->launches++;
+            }
             R.prev = -2;
             k0 = 1;
         } else R.prev = -1;
@@ -688,6 +818,17 @@ struct Hierarchy : S4fAmg {
         Level<T>& L = *lv[l];
         Level<T>& C = *lv[l + 1];
         const int grid = step_grid(c, L);
+        if (recording) {
+            if constexpr (std::is_same<TB, T>::value) {
+                TailOp<T> op{}; op.kind = TAIL_RESID; op.n = L.n; op.ld = L.ld; op.nSlices = L.nSlices;
+                op.slicePtr = L.slicePtr; op.col = L.col; op.a = L.a; op.dg = L.dg.p; op.b = b; op.x = x; op.xo = L.t.p;
+                tailHost.push_back(op);
+                TailOp<T> rs{}; rs.kind = TAIL_RESTRICT; rs.n = C.n; rs.ld = L.ld; rs.ldc = C.ld; rs.idxA = C.childPtr.p; rs.idxB = C.child.p;
+                rs.x = L.t.p; rs.xo = C.b.p;
+                tailHost.push_back(rs);
+            }
+            return 0;
+        }
         int rc = halo(c, L, x); if (rc) return rc;
         k_amg_step<T, TB, T, 1><<<grid, S4F_AMG_BLOCK, 0, c->stream>>>(L.slicePtr, L.col, L.a, L.dg.p, b, x, nullptr, L.t.p, L.n, L.ld, ldb, L.ld,
                                                                        L.nSlices, (T)0, (T)0, 0, act);
@@ -704,6 +845,11 @@ struct Hierarchy : S4fAmg {
     }
 
     int copy(s4fgpu_ctx* c, Level<T>& L, const T* src, T* dst) {
+        if (recording) {
+            TailOp<T> op{}; op.kind = TAIL_COPY; op.n = L.n; op.ld = L.ld; op.x = src; op.xo = dst;
+            tailHost.push_back(op);
+            return 0;
+        }
         k_amg_copy<T><<<s4f_grid(c->numSMs, L.n), S4F_BLOCK, 0, c->stream>>>(src, dst, L.n, L.ld, act);
         c->launches++;
         return 0;
@@ -712,7 +858,23 @@ struct Hierarchy : S4fAmg {
     template <class TB>
     int cycle_level(s4fgpu_ctx* c, size_t l, const TB* b, int ldb, double* out, int ldo) {
         Level<T>& L = *lv[l];
+        if (!recording && (int)l == tailLevel && !out) {
+            if constexpr (std::is_same<TB, T>::value) {
+                if (b == L.b.p) {       // the recorded program reads this level's own right-hand side
+                    k_amg_tail<T><<<S4F_TAIL_CTAS, S4F_TAIL_THREADS, 0, c->stream>>>(tailOps.p, (int)tailHost.size(), act);
+                    c->launches++;
+                    return 0;
+                }
+            }
+        }
         if (l + 1 == lv.size()) {     // coarsest: dense inverse
+            if (recording) {
+                if constexpr (std::is_same<TB, T>::value) {
+                    TailOp<T> op{}; op.kind = TAIL_DENSE; op.n = L.n; op.ld = L.ld; op.a = denseInv.p; op.b = b; op.xo = L.x.p;
+                    tailHost.push_back(op);
+                }
+                return 0;
+            }
             const int warps = 3 * L.n, blocks = (warps * 32 + 255) / 256;
             if (out) k_amg_dense<T, TB, double><<<blocks, 256, 0, c->stream>>>(denseInv.p, b, out, L.n, ldb, ldo);
             else k_amg_dense<T, TB, T><<<blocks, 256, 0, c->stream>>>(denseInv.p, b, L.x.p, L.n, ldb, L.ld);
@@ -728,7 +890,10 @@ struct Hierarchy : S4fAmg {
         const bool kcycle = (cycle == 2 && l == 0 && lv.size() > 2);
         if (kcycle) { rc = kcycle_level1(c); if (rc) return rc; }
         else { rc = cycle_level<T>(c, l + 1, C.b.p, C.ld, nullptr, 0); if (rc) return rc; }
-        {
+        if (recording) {
+            TailOp<T> op{}; op.kind = TAIL_PROLONG; op.n = L.n; op.ld = L.ld; op.ldc = C.ld; op.idxA = L.parent.p; op.x = C.x.p; op.xo = x; op.c1 = (T)omega;
+            tailHost.push_back(op);
+        } else {
             const int grid = s4f_grid(c->numSMs, L.n);
             k_amg_prolong<T><<<grid, S4F_BLOCK, 0, c->stream>>>(L.parent.p, C.x.p, x, L.n, L.ld, C.ld, (T)(kcycle ? omegaK : omega), act);
             c->launches++;
@@ -795,6 +960,33 @@ struct Hierarchy : S4fAmg {
     }
 
     // dense inverse of the coarsest matrix from its device rows (<= 512 cells; host Cholesky)
+    // choose the first level from which everything is small and local, and record its V-cycle (called when the levels, their
+    // work vectors and the coarsest inverse exist; pointers stay valid across coefficient refreshes)
+    int record_tail(s4fgpu_ctx* c) {
+        tailLevel = -1; tailHost.clear();
+        // OFF by default: measured at 8 M cells (profiles/r2_amg_tail_ab.log), ms per outer iteration / launches per outer iteration:
+        // off 11.36 / 297; levels <= 2048 rows fused 11.54 / 242; <= 20000 rows 11.91 / 190; <= 200000 rows 13.89 / 134.  Inside
+        // the PCG graph a small kernel costs ~1.5 us and spreads over 148 SMs; one cluster of 8 SMs stepping through the same
+        // operations is latency-bound and slower, barrier or not.  S4F_AMG_TAIL_MAX=<rows> turns it on.
+        long long maxRows = 0;
+        if (const char* e = getenv("S4F_AMG_TAIL_MAX")) maxRows = atoll(e);
+        if (cycle == 1 || maxRows <= 0 || lv.size() < 3) return 0;
+        int lt = -1;
+        for (int l = (int)lv.size() - 1; l >= 2; l--) {
+            const Level<T>& L = *lv[l];
+            if (L.dist || L.gather || L.n > maxRows) break;
+            lt = l;
+        }
+        if (lt < 0 || lt + 1 >= (int)lv.size()) return 0;          // nothing to fuse (the coarsest level alone is one launch already)
+        recording = true;
+        int rc = cycle_level<T>(c, (size_t)lt, lv[lt]->b.p, lv[lt]->ld, nullptr, 0);
+        recording = false;
+        if (rc) return rc;
+        S4F_CHECK_CUDA(c, tailOps.upload(tailHost));
+        tailLevel = lt;
+        return 0;
+    }
+
     int invert_coarsest(s4fgpu_ctx* c) {
         Level<T>& LC = *lv.back();
         const int n = LC.n;
@@ -909,6 +1101,7 @@ int build(s4fgpu_ctx* c, std::vector<HostLevel>& H) {
     }
     S4F_CHECK_CUDA(c, A->denseInv.upload(inv));
     S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+    { int rt = A->record_tail(c); if (rt) return rt; }
     A->bytesPerApply = A->bytes_per_apply();
     A->step0Bytes = A->lv[0]->nnz * (4 + sizeof(T)) + 0.125 * c->N + 3.0 * c->N * (8 + 3 * sizeof(T) + sizeof(T));   // col,a | b(fp64) x xprev diag in, x' out
     c->amg = guard.release();
@@ -974,6 +1167,7 @@ int build_from_device(s4fgpu_ctx* c, std::vector<std::unique_ptr<AmgDevLevel>>& 
     if (A->lv.back()->n > 4096) { c->err = "GAMG: agglomeration stalled above the size of the dense coarsest solve"; return 1; }
     S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
     int rc = A->invert_coarsest(c); if (rc) return rc;
+    if ((rc = A->record_tail(c))) return rc;
     A->bytesPerApply = A->bytes_per_apply();
     A->step0Bytes = A->lv[0]->nnz * (4 + sizeof(T)) + 0.125 * c->N + 3.0 * c->N * (8 + 3 * sizeof(T) + sizeof(T));
     c->amg = guard.release();
