@@ -273,7 +273,10 @@ int s4fgpu_interpolate_to_points(s4fgpu_handle h, int field, int mode, double* p
  * weights are recomputed from the new points; fields, boundary data and law history stay, the GAMG hierarchy keeps its
  * aggregates and re-sums its coefficients.  pointDD: host [3*nPoints], or NULL = the point field the last
  * s4fgpu_interpolate_to_points left on the device (no host round trip).  Needs s4fgpu_set_points; meshes with empty
- * patches (2-D cases) are refused: mirror their moved geometry with set_geometry / set_points instead. */
+ * patches (2-D cases) are refused: mirror their moved geometry with set_geometry / set_points instead.
+ * Decomposed meshes: collective; every rank moves its own points (the interpolated point displacement is identical on
+ * all ranks that hold a point), the cell and boundary-face centres are exchanged over the processor patches and the
+ * point-neighbour ghosts; the GAMG hierarchy is set up again (the coefficient refresh is single-rank). */
 int s4fgpu_move_points(s4fgpu_handle h, const double* pointDD);
 
 /* ---- models ---------------------------------------------------------------------------------- */

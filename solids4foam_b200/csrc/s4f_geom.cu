@@ -138,6 +138,12 @@ __global__ void __launch_bounds__(S4F_BLOCK) k_geo_entries(const int* __restrict
             const double nod = 1.0 / fmax(nd, 0.05 * magd);
 #pragma unroll
             for (int q = 0; q < 3; q++) o.eSf[(size_t)q * nE + e] = Sf[q];
+            if (!bnd && f >= nF - B) {       // processor-patch face: its normal and area also live in the boundary-face arrays (uns kernels)
+                const int b = f - (nF - B);
+#pragma unroll
+                for (int q = 0; q < 3; q++) { o.bN[(size_t)q * B + b] = n[q]; o.bSf[(size_t)q * B + b] = Sf[q]; }
+                o.bMagSf[b] = magSf; o.bDelta[b] = nod;
+            }
             if (bnd) {
                 const int b = cc - bOff;
                 o.eW[e] = 0.0; o.eDn[e] = 0.0;
@@ -197,9 +203,9 @@ __global__ void k_geo_point_weights(const int* __restrict__ ptPtr, const int* __
     double sw = 0;
     for (int j = ptPtr[p]; j < ptPtr[p + 1]; j++) {
         const int s = ptCol[j];
-        double X[3];
-        if (s >= bOff) { const int f = F + s - bOff; X[0] = fCtr[f]; X[1] = fCtr[(size_t)nF + f]; X[2] = fCtr[2 * (size_t)nF + f]; }
-        else { X[0] = C[s]; X[1] = C[(size_t)ld + s]; X[2] = C[2 * (size_t)ld + s]; }
+        // the centre field holds cell centres, boundary-face centres in the boundary slots (k_geo_boundary_centres) and, on a
+        // decomposed mesh, the centres of the other ranks' cells / boundary faces in the point-neighbour ghost slots
+        const double X[3] = {C[s], C[(size_t)ld + s], C[2 * (size_t)ld + s]};
         const double w = 1.0 / sqrt((x[0] - X[0]) * (x[0] - X[0]) + (x[1] - X[1]) * (x[1] - X[1]) + (x[2] - X[2]) * (x[2] - X[2]));
         ptW[j] = w; sw += w;
     }
@@ -213,6 +219,13 @@ __global__ void k_geo_point_weights(const int* __restrict__ ptPtr, const int* __
         pgDelta[j] = d[0]; pgDelta[nnzG + j] = d[1]; pgDelta[2 * nnzG + j] = d[2];
     }
     for (int j = pgPtr[p]; j < pgPtr[p + 1]; j++) pgW[j] /= sw;
+}
+
+__global__ void k_geo_boundary_centres(const double* __restrict__ fCtr, double* __restrict__ C, int F, int B, int nF, int bOff, int ld) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+#pragma unroll
+    for (int q = 0; q < 3; q++) C[(size_t)q * ld + bOff + b] = fCtr[(size_t)q * nF + F + b];
 }
 
 __global__ void k_soa3_to_aos(const double* __restrict__ soa, double* __restrict__ aos, int n, size_t stride, int offset) {
@@ -273,6 +286,14 @@ int s4f_refresh_host_geometry(s4fgpu_ctx* c) {
     }
     c->hPoints.resize(3 * (size_t)nP);
     S4F_CHECK_CUDA(c, cudaMemcpy(c->hPoints.data(), c->dPoints.p, 3 * (size_t)nP * sizeof(double), cudaMemcpyDeviceToHost));
+    if (c->X > 0) {      // decomposed: the moved centres of the other ranks' cells / boundary faces at shared points
+        std::vector<double> x(3 * (size_t)c->X);
+        DevBuf<double> tx; S4F_CHECK_CUDA(c, tx.alloc(3 * (size_t)c->X, false));
+        k_soa3_to_aos<<<(c->X + 255) / 256, 256, 0, c->stream>>>(c->Cc.p, tx.p, c->X, (size_t)c->ld, c->xOff());
+        S4F_CHECK_CUDA(c, cudaMemcpyAsync(x.data(), tx.p, x.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        S4F_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (size_t e = 0; e < c->extSlot.size(); e++) for (int q = 0; q < 3; q++) c->extCtr[3 * e + q] = x[3 * (size_t)(c->extSlot[e] - c->xOff()) + q];
+    }
     c->launches += 3;
     c->hostGeomStale = false;
     return 0;
@@ -283,7 +304,7 @@ int s4f_refresh_host_geometry(s4fgpu_ctx* c) {
 int s4f_move_points_device(s4fgpu_ctx* c, const double* hostPointDD) {
     const int N = c->N, F = c->F, B = c->B, nF = F + B, nP = c->nPoints, ld = c->ld;
     if (nP == 0) { c->err = "move_points: call set_points first"; return 1; }
-    if (c->nRanks > 1) { c->err = "move_points: decomposed meshes move on the host (set_points, then set_geometry, on every rank)"; return 1; }
+    if (c->nRanks > 1 && c->extPtr.size() != (size_t)nP + 1) { c->err = "move_points on a decomposed mesh: call set_points before set_geometry"; return 1; }
     for (int p = 0; p < c->nPatches; p++)
         if (c->pKind[p] == S4F_PATCH_EMPTY) { c->err = "move_points: meshes with empty patches (2-D cases) move on the host (set_geometry / set_points)"; return 1; }
     if (c->eFaceS.n != (size_t)std::max<long long>(c->nEntries, 1)) { int rc = build_entry_faces(c); if (rc) return rc; }
@@ -306,6 +327,8 @@ int s4f_move_points_device(s4fgpu_ctx* c, const double* hostPointDD) {
     k_geo_cells<<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->eFaceS.p, c->fCtr.p, c->fSf.p, c->Cc.p, c->V.p, c->rV.p, N, ld, nF, c->nSlices);
     c->launches += 3;
     int rc = s4f_halo_exchange(c, c->Cc.p, 3); if (rc) return rc;       // neighbour cell centres across processor patches
+    if (B > 0) { k_geo_boundary_centres<<<(B + 127) / 128, 128, 0, c->stream>>>(c->fCtr.p, c->Cc.p, F, B, nF, c->bOff(), ld); c->launches++; }
+    if ((rc = s4f_point_ghost_exchange(c, c->Cc.p, 3))) return rc;      // decomposed: centres of the other ranks' cells / faces at shared points
     GeoOut o{c->eW.p, c->eSf.p, c->eDn.p, c->eCorr.p, c->eLs.p, c->bN.p, c->bK.p, c->bSf.p, c->bDelta.p, c->bMagSf.p};
     k_geo_entries<<<gridM, S4F_BLOCK, 0, c->stream>>>(c->slicePtr.p, c->col.p, c->eFaceS.p, c->fCtr.p, c->fSf.p, c->Cc.p, o, N, c->bOff(), B, ld, nF,
                                                      c->nEntries, c->nSlices, c->solD[0], c->solD[1], c->solD[2]);

@@ -307,8 +307,11 @@ def move_points(mesh: FvMesh, new_points: np.ndarray) -> FvMesh:
     C, V = cell_centres_and_volumes(mesh.nCells, fCtrs, fAreas, t["own_all"], mesh.neighbour.astype(np.int64))
     Sf = np.concatenate([fAreas[:F], fAreas[F:][t["kb"]]])
     Cf = np.concatenate([fCtrs[:F], fCtrs[F:][t["kb"]]])
+    # a processor's part of a decomposed mesh: this host mirror (file output, FSI points) keeps the neighbour cell centres of
+    # before the move for the interpolation geometry of its processor faces; the device computes its own from a halo exchange
     new = _finish_mesh(mesh.nCells, mesh.owner.astype(np.int64), mesh.neighbour.astype(np.int64), mesh.faceCells, mesh.patches,
-                       C, V, Sf, Cf, None, mesh.solutionD, cellGlobal=mesh.cellGlobal)
+                       C, V, Sf, Cf, mesh.CnbrB if mesh.nRanks > 1 else None, mesh.solutionD, cellGlobal=mesh.cellGlobal,
+                       rank=mesh.rank, nRanks=mesh.nRanks)
     new.points = pts.copy(); new.faces = mesh.faces; new.topo = t; new.meta = dict(mesh.meta)
     return new
 

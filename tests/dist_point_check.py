@@ -15,6 +15,10 @@ processorN directory, and the checks against the single-domain CPU oracle on the
 * both vol->point interpolations of that field (patch mode and gradient-extrapolated), point by point;
 * the converged solution of the case (D, sigma) to north_star's 1e-6.
 
+``ul`` / ``unsul`` run the updated-Lagrangian models (cell-centred with pointCellsLeastSquares, and the face-stress form) with
+neoHookeanElastic through two load steps with the mesh moved in between on every rank's device (s4fgpu_move_points: consistent
+point displacements from the point-neighbour ghosts, neighbour centres by halo exchange), against the serial oracle.
+
 ``uns`` runs the unsLinearGeometry model instead (vertex values from vol->point, face gradients and face stress; the processor
 faces take the corrected snGrad of an internal face with the cell across the cut); ``warped`` distorts the mesh so that the
 non-orthogonal correction (and its ghost gradients) is exercised."""
@@ -30,6 +34,56 @@ sys.path.insert(0, ROOT)
 def field(C):
     x, y, z = C[:, 0], C[:, 1], C[:, 2]
     return 1e-3 * np.stack([x * y + 0.3 * z * z * x, np.sin(0.7 * x) + y * z, 0.2 * x * x * y - z ** 3], axis=1)
+
+
+def moving_steps(solid, case, case_dir, rank, world, IO, K, dist, model, mode, shape):
+    """two load steps of an updated-Lagrangian model, mesh moved on the devices in between; rank 0 compares with the oracle"""
+    loads = (-1e4, -2e4)
+    res = []
+    pts0 = solid.case.mesh.points.copy()
+    for load in loads:
+        solid.new_timestep(1.0)
+        solid.set_bc("loaded", K.solidTraction((0.0, load, 0.0)))
+        st = solid.evolve()
+        D, S = solid.get("D"), solid.get("sigma")
+        solid.updateTotalFields()
+        res.append((st["converged"], st["nCorr"], D, S, solid.case.mesh.points.copy(), solid.get("rho")))
+    out = [None] * world
+    dist.all_gather_object(out, (solid.case.mesh.cellGlobal, res, pts0))
+    if rank != 0:
+        return True
+    from oracle.binding import OracleSolid
+    serial = IO.read_case(case_dir, preconditioner=K.PRECOND_DIC)
+    o = OracleSolid(serial)
+    N = serial.mesh.nCells
+    ok = True
+    p0 = serial.mesh.points.copy()
+    msg = []
+    for step, load in enumerate(loads):
+        o.new_timestep(1.0)
+        o.set_bc("loaded", K.solidTraction((0.0, load, 0.0)))
+        so = o.evolve()
+        Do, So = o.get("D"), o.get("sigma")
+        o.updateTotalFields()
+        D = np.zeros((N, 3)); S = np.zeros((N, 6)); R = np.zeros(N)
+        conv = True
+        ePts = 0.0
+        key = {tuple(x): i for i, x in enumerate(np.round(p0, 12).tolist())}
+        for r, (cg, rs, _) in enumerate(out):
+            c_, n_, d_, s_, pts_, rho_ = rs[step]
+            D[cg] = d_; S[cg] = s_; R[cg] = rho_
+            conv = conv and c_
+        # moved points: every rank's copy against the oracle's moved serial mesh, matched through the ORIGINAL coordinates
+        for r in range(world):
+            ids = np.array([key[tuple(x)] for x in np.round(out[r][2], 12).tolist()])
+            ePts = max(ePts, np.abs(out[r][1][step][4] - o.case.mesh.points[ids]).max())
+        eD = np.linalg.norm(D - Do) / np.linalg.norm(Do)
+        eS = np.linalg.norm(S - So) / np.linalg.norm(So)
+        eR = np.abs(R - o.get("rho")).max() / np.abs(o.get("rho")).max()
+        msg.append(f"step {step}: gpu converged {conv} oracle {so['converged']} ({so['nCorr']}); relL2 D {eD:.2e} sigma {eS:.2e} rho {eR:.2e} points {ePts:.2e}")
+        ok = ok and conv and so["converged"] and eD < 1e-6 and eS < 1e-6 and eR < 1e-8 and ePts < 1e-8
+    print(f"moving mesh on {world} GPUs ({mode}, {model}, {shape}): " + "; ".join(msg) + f"; max |point motion| {np.abs(o.case.mesh.points - p0).max():.3f}", flush=True)
+    return bool(ok)
 
 
 def main():
@@ -50,12 +104,21 @@ def main():
     nx, ny, nz = 12, 6, 4
     kw = dict(L=2.0, fieldRelaxD=0.9, nCorrectors=6000, solutionTolerance=1e-11, alternativeTolerance=1e-11, tolerance=1e-13,
               preconditioner=K.PRECOND_GAMG, general=True)
+    moving = model in ("ul", "unsul")
     if model == "uns":
         kw["solidModel"] = K.MODEL_UNS_LIN_GEOM
+    elif model == "unsul":
+        kw["solidModel"] = K.MODEL_UNS_NONLIN_UL
+    elif model == "ul":
+        kw.update(solidModel=K.MODEL_NONLIN_UL, gradScheme=K.GRAD_POINT_CELLS_LEAST_SQUARES)
     else:
         kw["gradScheme"] = K.GRAD_POINT_CELLS_LEAST_SQUARES
+    if moving:
+        kw.update(solutionTolerance=1e-9, alternativeTolerance=1e-9, tolerance=1e-12, relTol=0.01, nCorrectors=8000)
+        kw.pop("fieldRelaxD", None)
     if rank == 0:
-        serial = cases.cantilever(nx, ny, nz, **kw)
+        serial = (cases.neo_hookean_cantilever(nx, ny, nz, traction=(0.0, -1e4, 0.0), **kw) if moving
+                  else cases.cantilever(nx, ny, nz, **kw))
         if shape == "warped":
             from solids4foam_b200 import mesh as M
 
@@ -70,7 +133,8 @@ def main():
         # of them faces of the other rank
         pf = serial.mesh.patch("fixed")
         F = serial.mesh.nInternalFaces
-        serial.bcs["fixed"].value = 1e-2 * field(serial.mesh.Cf[F + pf.start:F + pf.start + pf.size])
+        if not moving:
+            serial.bcs["fixed"].value = 1e-2 * field(serial.mesh.Cf[F + pf.start:F + pf.start + pf.size])
         IO.write_case(case_dir, serial, end_time=1.0)
         C = serial.mesh.C
         if mode == "checker":
@@ -90,6 +154,12 @@ def main():
     case = IO.read_decomposed_case(case_dir, rank, world, run_case.dist_exchange(rank), preconditioner=K.PRECOND_GAMG)
     solid = SolidModel(case, device=local, comm=(world, rank, bytes(uid.cpu().tolist())))
     m = case.mesh
+    if moving:
+        ok = moving_steps(solid, case, case_dir, rank, world, IO, K, dist, model, mode, shape)
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.broadcast(flag, 0)
+        dist.destroy_process_group()
+        sys.exit(0 if int(flag.item()) else 1)
     # operators on an analytic field, fresh model
     solid.set("D", field(m.C))
     solid.op_grad()

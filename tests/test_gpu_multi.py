@@ -33,7 +33,8 @@ def test_decomposed_case_directory_runs_on_two_gpus(tmp_path):
 
 
 @pytest.mark.parametrize("mode,model,shape", [("checker", "pointCells", "box"), ("slab", "pointCells", "warped"),
-                                              ("checker", "uns", "box"), ("checker", "uns", "warped")])
+                                              ("checker", "uns", "box"), ("checker", "uns", "warped"),
+                                              ("checker", "ul", "box"), ("slab", "unsul", "box")])
 def test_point_stencils_on_a_decomposed_mesh(tmp_path, mode, model, shape):
     """pointCellsLeastSquares gradient, vol->point interpolation and the unsLinearGeometry model across processor patches
     (point-neighbour ghosts, s4f_build_point_ghosts): operators on an analytic field and the converged case against the
