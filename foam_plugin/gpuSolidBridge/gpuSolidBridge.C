@@ -137,6 +137,11 @@ void gpuSolidBridge::mirrorGeometry(const bool withPoints)
         }
     }
 
+    // Decomposed case: the points first -- s4fgpu_set_geometry then identifies the processor-patch points across ranks and
+    // reserves the point-neighbour ghost slots of the point stencils (include/s4fgpu.h, s4fgpu_set_points).  Serial: the
+    // library builds the vol->point weights inside set_points, which needs the geometry.
+    if (withPoints && Pstream::parRun()) mirrorPoints();
+
     check
     (
         s4fgpu_set_geometry
@@ -152,7 +157,14 @@ void gpuSolidBridge::mirrorGeometry(const bool withPoints)
         "gpuSolidBridge::mirrorGeometry()"
     );
 
-    if (!withPoints) return;
+    if (withPoints && !Pstream::parRun()) mirrorPoints();
+}
+
+
+void gpuSolidBridge::mirrorPoints()
+{
+    const fvMesh& m = mesh_;
+    const label nF = m.nFaces(), nI = m.nInternalFaces();
 
     // points() and faces() of the fv faces (empty-patch faces are not fv faces of the mirror): CSR
     const faceList& fs = m.faces();
