@@ -47,3 +47,17 @@ def test_point_stencils_on_a_decomposed_mesh(tmp_path, mode, model, shape):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
     print(r.stdout[-1500:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("model,shape", [("pointCells", "warped"), ("ul", "box")])
+def test_point_stencils_on_a_two_by_two_decomposition(tmp_path, model, shape):
+    """4 GPUs, blocks dealt out 2 x 2: the diagonal pairs of ranks touch only along the central edge -- no processor patch
+    between them -- yet their cells share points; the point-neighbour ghosts find them through the point coordinates."""
+    import torch
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "4", "--master-addr", "127.0.0.1",
+           "--master-port", "29520", os.path.join(HERE, "dist_point_check.py"), str(tmp_path / "case"), "checker", model, shape]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
+    print(r.stdout[-1500:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
