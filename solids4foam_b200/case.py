@@ -124,7 +124,7 @@ def default_controls(**kw) -> Controls:
     c.gamgSinglePrecision = 0
     c.gamgOverCorrection = 2.2
     c.gamgSmootherDegree = 3
-    c.gamgCycle = 2          # K-cycle on level 1 (single rank; decomposed runs fall back to the V-cycle)
+    c.gamgCycle = 2          # K-cycle on level 1 (also on decomposed meshes: its dot products are all-reduced in the kernel)
     c.gamgSmootherRatio = 0.3
     for k, v in kw.items():
         if k == "g":

@@ -3,13 +3,15 @@
 //
 // Reference behaviour: [OF-ext] pairGAMGAgglomeration ("faceAreaPair"): every cell is paired with its most strongly
 // coupled free neighbour, `mergeLevels` such passes make one solver level, coarse coefficients are the sums of the fine
-// ones.  Round 1 (and the decomposed runs still) did this on one host thread: 2.0 s at 8 M cells, more than 150 outer
-// iterations.  The sequential greedy sweep becomes a parallel maximal matching by locally dominant edges: every free cell
-// picks its best free neighbour under a total order of the edges that both end points evaluate identically --
-// (coefficient as float, smaller index distance, even lower end point, hash of the edge) -- and an edge whose two cells
-// picked each other is matched; a few rounds leave only isolated cells, which stay single.  On a structured hex mesh the
-// order reproduces the greedy result (pairs along the strongest direction, then the next: 2x2x2 blocks with 6-12 coarse
-// neighbours), so the iteration counts of the host-built hierarchy are kept (tests/test_gpu_parity.py::test_device_built_gamg_hierarchy_matches_the_host_built_one).
+// ones.  Round 1 (and the decomposed runs still, per rank) did this on one host thread: 2.2 s at 8 M cells, the time of 175
+// outer iterations.  The sequential greedy sweep becomes a parallel matching by mutual picks: every free cell picks its
+// best free neighbour -- strongest coefficient, ties to the LOWER neighbour index ("sweep rule", see `better`) -- and two
+// cells that picked each other are matched; repeat until a round matches nothing.  The lowest-numbered end point of the
+// strongest class of edges is always picked back, so every round makes progress, and along a line of equally coupled cells
+// the pairs form from its low end exactly as the sequential sweep forms them: on a structured hex mesh the aggregates are
+// the same 2x2x2 bricks (rounds ~ longest line / 2; a hash / parity tie rule needs O(log n) rounds but staggers the bricks
+// and costs PCG iterations -- it remains as the finish rule after S4F_AMG_SWEEP_ROUNDS).  0.17 s at 8 M cells;
+// tests/test_gpu_parity.py::test_device_built_gamg_hierarchy_matches_the_host_built_one compares with the host sweep.
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
