@@ -276,7 +276,7 @@ int s4fgpu_interpolate_to_points(s4fgpu_handle h, int field, int mode, double* p
  * patches (2-D cases) are refused: mirror their moved geometry with set_geometry / set_points instead.
  * Decomposed meshes: collective; every rank moves its own points (the interpolated point displacement is identical on
  * all ranks that hold a point), the cell and boundary-face centres are exchanged over the processor patches and the
- * point-neighbour ghosts; the GAMG hierarchy is set up again (the coefficient refresh is single-rank). */
+ * point-neighbour ghosts; the GAMG hierarchy keeps its aggregates there too. */
 int s4fgpu_move_points(s4fgpu_handle h, const double* pointDD);
 
 /* ---- models ---------------------------------------------------------------------------------- */

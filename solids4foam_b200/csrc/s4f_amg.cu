@@ -41,7 +41,10 @@ namespace {
 // host: agglomeration
 // ================================================================================================
 // couplings of this rank's cells to cells of one neighbour rank, in an order both sides agree on
-struct Iface { int rank = -1; std::vector<int> cell, remote; std::vector<double> a; };
+struct Iface {
+    int rank = -1; std::vector<int> cell, remote; std::vector<double> a;
+    std::vector<int> remoteParent;      // aggregate (local index on the other rank) of remote[f] in the next level (coefficient refresh)
+};
 struct HostLevel {
     int n = 0;
     std::vector<int> own, nei;          // faces, upper-triangular order
@@ -51,6 +54,7 @@ struct HostLevel {
     bool dist = false;                  // one part per rank (n = this rank's cells); false: the whole level on every rank
     std::vector<Iface> ifc;             // dist: couplings across rank boundaries
     int childOff = 0, childCnt = 0;     // the range of the next level's cells that this rank's cells feed
+    std::vector<int> rankOff;           // gathered next level: first global cell of every rank
 };
 
 // one pair-wise pass: greedy matching of every still-unmatched cell with its strongest unmatched
@@ -318,15 +322,18 @@ template <class T>
 __global__ void k_amg_galerkin(const int* __restrict__ spF, const int* __restrict__ colF, const T* __restrict__ aF, const T* __restrict__ dgF,
                                const int* __restrict__ parent, int nFine, int ldF, const int* __restrict__ spC, const int* __restrict__ colC,
                                T* __restrict__ aC, T* __restrict__ dgC, const int* __restrict__ childPtr, const int* __restrict__ child, int nC,
-                               int ldC, int* __restrict__ fail) {
-    const int I = blockIdx.x * blockDim.x + threadIdx.x;
-    if (I >= nC) return;
+                               int ldC, int* __restrict__ fail, const int* __restrict__ ghostParent /* decomposed fine level, else null */,
+                               int nGhostFine, int rowOff) {
+    // nC rows starting at rowOff: all rows, or -- next level gathered from the ranks -- the rows of this rank's aggregates
+    const int Iloc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (Iloc >= nC) return;
+    const int I = rowOff + Iloc;
     const int sC = I >> 5, lC = I & 31, baseC = spC[sC], wC = (spC[sC + 1] - baseC) >> 5;
     if (wC > S4F_AMG_MAXW) { *fail = 1; return; }
     int cc[S4F_AMG_MAXW]; double acc[S4F_AMG_MAXW];
     for (int k = 0; k < wC; k++) { cc[k] = colC[baseC + 32 * k + lC]; acc[k] = 0.0; }
     double dsub = 0, dsum[3] = {0, 0, 0};
-    for (int ce = childPtr[I]; ce < childPtr[I + 1]; ce++) {
+    for (int ce = childPtr[Iloc]; ce < childPtr[Iloc + 1]; ce++) {
         const int i = child[ce];
         const int sF = i >> 5, lF = i & 31, baseF = spF[sF], wF = (spF[sF + 1] - baseF) >> 5;
 #pragma unroll
@@ -335,8 +342,8 @@ __global__ void k_amg_galerkin(const int* __restrict__ spF, const int* __restric
             const double a = (double)aF[baseF + 32 * k + lF];
             if (a == 0.0) continue;
             const int j = colF[baseF + 32 * k + lF];
-            if (j >= nFine) continue;
-            const int J = parent[j];
+            if (j >= nFine && !(ghostParent && j - nFine < nGhostFine)) continue;      // boundary slots
+            const int J = j < nFine ? parent[j] : ghostParent[j - nFine];                // across a processor patch: the other rank's aggregate
             if (J == I) { dsub += a; continue; }
             int k2 = 0;
             while (k2 < wC && cc[k2] != J) k2++;
@@ -347,6 +354,32 @@ __global__ void k_amg_galerkin(const int* __restrict__ spF, const int* __restric
     for (int k = 0; k < wC; k++) aC[baseC + 32 * k + lC] = (T)acc[k];
 #pragma unroll
     for (int q = 0; q < 3; q++) dgC[(size_t)q * ldC + I] = (T)(dsum[q] - dsub);
+}
+
+// Refresh of a gathered level: every rank has re-summed the rows of ITS aggregates; the rows travel to all ranks three SELL
+// entry positions at a time through the gather plan of the level above (the one that carries the restricted right-hand side).
+template <class T>
+__global__ void k_amg_rows_pack(const int* __restrict__ sp, const T* __restrict__ a, int rowOff, int nLocal, int k0, T* __restrict__ out, int stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nLocal) return;
+    const int I = rowOff + i, base = sp[I >> 5], w = (sp[(I >> 5) + 1] - base) >> 5;
+#pragma unroll
+    for (int q = 0; q < 3; q++) out[(size_t)q * stride + i] = (k0 + q < w) ? a[base + 32 * (k0 + q) + (I & 31)] : (T)0;
+}
+template <class T>
+__global__ void k_amg_rows_unpack(const int* __restrict__ sp, T* __restrict__ a, int n, int k0, const T* __restrict__ in, int ld) {
+    const int I = blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= n) return;
+    const int base = sp[I >> 5], w = (sp[(I >> 5) + 1] - base) >> 5;
+#pragma unroll
+    for (int q = 0; q < 3; q++) if (k0 + q < w) a[base + 32 * (k0 + q) + (I & 31)] = in[(size_t)q * ld + I];
+}
+template <class T>
+__global__ void k_amg_diag_pack(const T* __restrict__ dg, int rowOff, int nLocal, int ld, T* __restrict__ out, int stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nLocal) return;
+#pragma unroll
+    for (int q = 0; q < 3; q++) out[(size_t)q * stride + i] = dg[(size_t)q * ld + rowOff + i];
 }
 
 // ---- K-cycle on level 1 (gamgCycle 2): two flexible-CG steps on the coarse problem A_1 x = b, each preconditioned by the
@@ -580,6 +613,9 @@ struct Level {
     // transition to the replicated part of the hierarchy: this (distributed) level restricts into `gsend`, which is
     // gathered to every rank as the right-hand side of the next level
     S4fGatherPlan* gather = nullptr; DevBuf<T> gsend; int gLocal = 0, gStride = 0;
+    // coefficient refresh of a decomposed hierarchy: coarse column of every ghost column of this (distributed) level, the
+    // first row of the next level this rank computes, and the widest SELL slice of this level's rows
+    DevBuf<int> ghostParent; int rowOff = 0, maxWidth = 0;
     double nnz = 0;
     ~Level() { if (ownHalo) s4f_halo_plan_destroy(halo); s4f_gather_plan_destroy(gather); }
 };
@@ -685,6 +721,8 @@ struct Hierarchy : S4fAmg {
             }
         }
         L.nnz = (double)rowPtr[n];
+        L.maxWidth = 0;
+        for (int sl = 0; sl < L.nSlices; sl++) L.maxWidth = std::max(L.maxWidth, (sp[sl + 1] - sp[sl]) / 32);
         S4F_CHECK_CUDA(c, L.slicePtrB.upload(sp)); S4F_CHECK_CUDA(c, L.colB.upload(hc)); S4F_CHECK_CUDA(c, L.aB.upload(ha));
         L.slicePtr = L.slicePtrB.p; L.col = L.colB.p; L.a = L.aB.p;
         std::vector<T> hd(3 * (size_t)L.ld, (T)1);
@@ -931,9 +969,10 @@ struct Hierarchy : S4fAmg {
         return 0;
     }
 
-    // The fine matrix changed its coefficients but not its graph (mesh motion): keep the aggregates, re-sum every coarse
-    // level on the device, invert the coarsest matrix again.  Single rank (the gathered levels of a decomposed run would
-    // need the other ranks' sums: those runs rebuild the hierarchy).
+    // The fine matrix changed its coefficients but not its graph (mesh motion, a new time step size): keep the aggregates,
+    // re-sum every coarse level on the device, invert the coarsest matrix again.  Decomposed: couplings across processor
+    // patches go to the other rank's aggregate (ghostParent); where the hierarchy is gathered, every rank re-sums the rows of
+    // its own aggregates and the rows are exchanged.
     int refresh(s4fgpu_ctx* c) override {
         Level<T>& L0 = *lv[0];
         if (sizeof(T) != sizeof(double)) {
@@ -947,10 +986,28 @@ struct Hierarchy : S4fAmg {
         for (size_t l = 1; l < lv.size(); l++) {
             Level<T>& Fn = *lv[l - 1];
             Level<T>& C = *lv[l];
-            k_amg_galerkin<T><<<(C.n + 127) / 128, 128, 0, c->stream>>>(Fn.slicePtr, Fn.col, Fn.a, Fn.dg.p, Fn.parent.p, Fn.n, Fn.ld, C.slicePtrB.p,
-                                                                       C.colB.p, C.aB.p, C.dg.p, C.childPtr.p, C.child.p, C.n, C.ld, fail.p);
-            c->launches++;
+            const int nRows = Fn.gather ? Fn.gLocal : C.n, rowOff = Fn.gather ? Fn.rowOff : 0;
+            if (Fn.dist && Fn.nGhost > 0 && Fn.ghostParent.n == 0) { c->err = "GAMG refresh: hierarchy without interface parents"; return 1; }
+            if (nRows > 0) {
+                k_amg_galerkin<T><<<(nRows + 127) / 128, 128, 0, c->stream>>>(Fn.slicePtr, Fn.col, Fn.a, Fn.dg.p, Fn.parent.p, Fn.n, Fn.ld, C.slicePtrB.p,
+                                                                           C.colB.p, C.aB.p, C.dg.p, C.childPtr.p, C.child.p, nRows, C.ld, fail.p,
+                                                                           Fn.dist && Fn.nGhost > 0 ? Fn.ghostParent.p : nullptr, Fn.nGhost, rowOff);
+                c->launches++;
+            }
             S4F_CHECK_CUDA(c, cudaGetLastError());
+            if (Fn.gather) {        // rows of all ranks -> every rank (C.t is free here: 3 * ld work values)
+                const int gp = (Fn.gLocal + 127) / 128, gu = (C.n + 127) / 128;
+                for (int k0 = 0; k0 < C.maxWidth; k0 += 3) {
+                    if (Fn.gLocal > 0) k_amg_rows_pack<T><<<gp, 128, 0, c->stream>>>(C.slicePtrB.p, C.aB.p, rowOff, Fn.gLocal, k0, Fn.gsend.p, Fn.gStride);
+                    int rg = s4f_gather_run<T>(c, Fn.gather, Fn.gsend.p, Fn.gStride, C.t.p, C.ld, c->ones3.p); if (rg) return rg;
+                    k_amg_rows_unpack<T><<<gu, 128, 0, c->stream>>>(C.slicePtrB.p, C.aB.p, C.n, k0, C.t.p, C.ld);
+                    c->launches += 2;
+                }
+                if (Fn.gLocal > 0) k_amg_diag_pack<T><<<gp, 128, 0, c->stream>>>(C.dg.p, rowOff, Fn.gLocal, C.ld, Fn.gsend.p, Fn.gStride);
+                int rg = s4f_gather_run<T>(c, Fn.gather, Fn.gsend.p, Fn.gStride, C.dg.p, C.ld, c->ones3.p); if (rg) return rg;
+                c->launches++;
+                S4F_CHECK_CUDA(c, cudaGetLastError());
+            }
         }
         int hf = 0;
         S4F_CHECK_CUDA(c, cudaMemcpyAsync(&hf, fail.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -1073,6 +1130,37 @@ int build(s4fgpu_ctx* c, std::vector<HostLevel>& H) {
             Level<T>& Fn = *A->lv[l - 1];
             const HostLevel& HF = H[l - 1];
             if ((rc = A->set_transfer(c, Fn, L, HF.parent, HF.childCnt, HF.childOff))) return rc;
+            Fn.rowOff = HF.childOff;
+            if (HF.dist && Fn.nGhost > 0) {     // coefficient refresh: the coarse column behind every ghost column of the finer level
+                const HostLevel& HC2 = H[l];
+                std::vector<std::vector<int>> gC(HC2.ifc.size()); std::vector<int> baseC(HC2.ifc.size(), 0);
+                if (HC2.dist) {
+                    int nG = 0;
+                    for (size_t k = 0; k < HC2.ifc.size(); k++) {
+                        std::vector<int> g(HC2.ifc[k].remote);
+                        std::sort(g.begin(), g.end()); g.erase(std::unique(g.begin(), g.end()), g.end());
+                        gC[k] = g; baseC[k] = nG; nG += (int)g.size();
+                    }
+                }
+                std::vector<int> gp(Fn.nGhost, -1);
+                int baseF = 0;
+                for (size_t k = 0; k < HF.ifc.size(); k++) {
+                    const Iface& I = HF.ifc[k];
+                    if (I.remoteParent.size() != I.remote.size()) { c->err = "GAMG: interface without the remote aggregates"; return 1; }
+                    std::vector<int> gF;
+                    if (l - 1 > 0) { gF = I.remote; std::sort(gF.begin(), gF.end()); gF.erase(std::unique(gF.begin(), gF.end()), gF.end()); }
+                    for (size_t f = 0; f < I.remote.size(); f++) {
+                        // level 0: one ghost per processor face, in patch order; coarser levels: the distinct remote cells, ascending
+                        const int g = baseF + (l - 1 == 0 ? (int)f : (int)(std::lower_bound(gF.begin(), gF.end(), I.remote[f]) - gF.begin()));
+                        const int R = I.remoteParent[f];
+                        gp[g] = HC2.dist ? HC2.n + baseC[k] + (int)(std::lower_bound(gC[k].begin(), gC[k].end(), R) - gC[k].begin())
+                                         : HF.rankOff[I.rank] + R;
+                    }
+                    baseF += (l - 1 == 0) ? (int)I.remote.size() : (int)gF.size();
+                }
+                for (int v : gp) if (v < 0) { c->err = "GAMG: a ghost column without a coarse column"; return 1; }
+                S4F_CHECK_CUDA(c, Fn.ghostParent.upload(gp));
+            }
             if (HF.dist && !H[l].dist) {        // the distributed part ends here: gather to all ranks
                 std::vector<int> cnt(c->nRanks);
                 if ((rc = s4f_allgather_host(c, &HF.childCnt, sizeof(int), cnt.data()))) return rc;
@@ -1259,6 +1347,7 @@ int coarsen_distributed(s4fgpu_ctx* c, HostLevel& L, HostLevel& C) {
         send.push_back(std::move(s));
     }
     int rc = s4f_exchange_nbr_ints(c, nbrRank, send, recv); if (rc) return rc;
+    for (size_t k = 0; k < L.ifc.size(); k++) L.ifc[k].remoteParent = recv[k];
     C.ifc.clear();
     for (size_t k = 0; k < L.ifc.size(); k++) {
         const Iface& I = L.ifc[k];
@@ -1311,7 +1400,7 @@ int gather_level(s4fgpu_ctx* c, HostLevel& fine, const HostLevel& part, HostLeve
         for (int q = 0; q < 3; q++) for (int i = 0; i < cnt[r]; i++) glob.diag[q][off[r] + i] = pd[nf + (size_t)q * cnt[r] + i];
     }
     for (int& p : fine.parent) p += off[me];
-    fine.childOff = off[me]; fine.childCnt = cnt[me];
+    fine.childOff = off[me]; fine.childCnt = cnt[me]; fine.rankOff = off;
     return 0;
 }
 
@@ -1399,9 +1488,17 @@ int s4f_amg_setup(s4fgpu_ctx* c) {
 
 // after mesh motion: same aggregates, new coefficients.  Falls back to a full set-up when there is nothing to refresh.
 int s4f_amg_refresh(s4fgpu_ctx* c) {
-    if (!c->amg || c->nRanks > 1) return s4f_amg_setup(c);
+    if (!c->amg) return s4f_amg_setup(c);
     const auto t0 = std::chrono::steady_clock::now();
     int rc = c->amg->refresh(c);
+    if (c->nRanks > 1) {        // the rebuild is collective: every rank takes it if one must
+        std::vector<int> all(c->nRanks, 0);
+        const int mine = rc ? 1 : 0;
+        int ra = s4f_allgather_host(c, &mine, sizeof(int), all.data()); if (ra) return ra;
+        for (int v : all) if (v && !rc) { rc = 1; c->err = "another rank could not refresh"; }
+    }
+    if (getenv("S4F_AMG_TIMING") && !rc && c->rank == 0)
+        fprintf(stderr, "libs4fgpu: GAMG coefficient refresh %.4f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
     if (rc) {
         fprintf(stderr, "libs4fgpu: GAMG coefficient refresh not possible (%s); rebuilding the hierarchy\n", c->err.c_str());
         c->err.clear();

@@ -759,7 +759,7 @@ int s4f_assemble_matrix(s4fgpu_ctx* c) {
     c->launches++;
     c->matrixValid = true;
     // new coefficients on the same graph: an existing GAMG hierarchy keeps its aggregates and re-sums its levels on the device
-    c->amgRefresh = (c->amg != nullptr && c->nRanks == 1 && !getenv("S4F_NO_AMG_REFRESH"));      // the variable: A/B aid of the tests
+    c->amgRefresh = (c->amg != nullptr && !getenv("S4F_NO_AMG_REFRESH"));      // the variable: A/B aid of the tests
     c->amgValid = false; c->dicValid = false;
     S4F_CHECK_CUDA(c, cudaGetLastError());
     return 0;

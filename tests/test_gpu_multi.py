@@ -61,3 +61,16 @@ def test_point_stencils_on_a_two_by_two_decomposition(tmp_path, model, shape):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
     print(r.stdout[-1500:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_gamg_coefficient_refresh_on_two_gpus():
+    """Same graph, new coefficients on a decomposed mesh: the hierarchy is refreshed on the devices (interface couplings to the
+    other rank's aggregates, gathered rows exchanged) and preconditions like one rebuilt from scratch."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29521", os.path.join(HERE, "dist_refresh_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
+    print(r.stdout[-1500:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
