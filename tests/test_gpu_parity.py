@@ -1018,3 +1018,25 @@ def test_uns_updated_lagrangian_steps_match_oracle(dynamic):
         assert rel_l2(g.get("rho"), o.get("rho")) < 1e-9
     if not dynamic:
         assert np.abs(o.get("D")[:, 1]).max() > 0.1
+
+
+def test_fused_small_level_kernel_equals_the_per_operation_kernels(monkeypatch):
+    """S4F_AMG_TAIL_MAX: the V-cycle below the first level with at most that many rows replayed by one cluster kernel
+    (k_amg_tail) from the recorded operation list.  Same arithmetic and summation order as the separate kernels: the PCG
+    iteration counts are equal and the solutions agree to round-off.  (Off by default: it is slower, profiles/r2_amg_tail_ab.log.)"""
+    from solids4foam_b200.solid_model import SolidModel
+    kw = dict(nx=48, ny=17, nz=17, L=2.0, preconditioner=K.PRECOND_GAMG, tolerance=1e-11, relTol=0.0, maxIter=200)
+    res = {}
+    for mode in ("separate", "fused"):
+        if mode == "fused":
+            monkeypatch.setenv("S4F_AMG_TAIL_MAX", "4000")
+        g = SolidModel(cases.cantilever(**kw))
+        rng = np.random.default_rng(5)
+        src = rng.standard_normal((g.case.mesh.nCells, 3))
+        psi, st = g.op_solve(np.zeros_like(src), src)
+        res[mode] = (psi, st["nIterations"], g.gamg_info()["levels"], g.launch_count())
+    (pa, ia, la, na), (pb, ib, lb, nb) = res["separate"], res["fused"]
+    assert la == lb and len(la) >= 3 and la[-2] <= 4000
+    assert ia == ib, (ia, ib)
+    assert rel_l2(pb, pa) < 1e-10
+    assert nb < na                      # fewer launches with the fused kernel
