@@ -263,3 +263,54 @@ def test_decomposed_case_directories_round_trip(tmp_path):
     # the loaded patch lives on the last processor only, with its traction
     last = IO.read_decomposed_case(str(tmp_path), 2, 3, lambda send: {q: sent[(q, 2)] for q in send})
     assert last.mesh.patch("loaded").size == 6 and np.allclose(last.bcs["loaded"].value, [0.0, -1e6, 0.0])
+
+
+def test_manual_decomposition_with_corners_matches_face_by_face(tmp_path):
+    """decompose_case with a cell -> processor map as ``method manual`` would give it: blocks dealt out like a chess board on two
+    processors and 2 x 2 on four (where the diagonal processors share an edge but no face).  On every pair of processors the two
+    sides of the processor patch list the same faces in the same order (centres equal, area vectors opposite), the points of
+    those faces are bit-identical copies (what the device-side point matching relies on), cells and volumes add up, and the
+    geometry of a warped serial mesh is reproduced cell by cell."""
+    nx, ny, nz = 8, 6, 3
+    c = cases.cantilever(nx, ny, nz, general=True, L=2.0)
+    c.mesh = M.hex_box_general(nx, ny, nz, 2.0, 1.0, 1.0, names=("fixed", "loaded", "yMin", "yMax", "zMin", "zMax"),
+                               point_map=lambda p: p + 0.03 * np.sin(3.0 * p[:, [1, 2, 0]]))
+    idx = np.arange(c.mesh.nCells)
+    bx, by = ((idx % nx) >= nx // 2).astype(np.int64), (((idx // nx) % ny) >= ny // 2).astype(np.int64)
+    for world, cell_rank in ((2, (bx + by) % 2), (4, bx + 2 * by)):
+        d = tmp_path / f"w{world}"
+        IO.write_case(str(d), c)
+        IO.decompose_case(str(d), world, cell_rank=cell_rank)
+        sent = {}
+        for r in range(world):
+            def collect(send, r=r):
+                for q, a in send.items():
+                    sent[(r, q)] = a
+                return {q: a + 1.0 for q, a in send.items()}
+            IO.read_poly_mesh(str(d / f"processor{r}" / "constant" / "polyMesh"), rank=r, nRanks=world, exchange=collect)
+        parts = [IO.read_decomposed_case(str(d), r, world, lambda send, r=r: {q: sent[(q, r)] for q in send}).mesh for r in range(world)]
+        assert sum(m.nCells for m in parts) == c.mesh.nCells
+        V = np.zeros(c.mesh.nCells); C = np.zeros((c.mesh.nCells, 3))
+        for m in parts:
+            V[m.cellGlobal] = m.V; C[m.cellGlobal] = m.C
+        assert np.allclose(V, c.mesh.V, rtol=1e-13) and np.allclose(C, c.mesh.C, atol=1e-13)
+        nbrs = {r: {p.nbr_rank for p in parts[r].patches if p.kind == M.PROCESSOR} for r in range(world)}
+        if world == 4:
+            assert 3 not in nbrs[0] and 2 not in nbrs[1]                    # diagonal blocks: no processor patch between them ...
+            shared = set(map(tuple, parts[0].points.tolist())) & set(map(tuple, parts[3].points.tolist()))
+            assert len(shared) == nz + 1                                     # ... but the points of the central edge, bit for bit
+        for r in range(world):
+            m = parts[r]
+            F = m.nInternalFaces
+            for p in m.patches:
+                if p.kind != M.PROCESSOR:
+                    continue
+                o = parts[p.nbr_rank]
+                q = next(x for x in o.patches if x.kind == M.PROCESSOR and x.nbr_rank == r)
+                assert q.size == p.size
+                a, b = slice(F + p.start, F + p.start + p.size), slice(o.nInternalFaces + q.start, o.nInternalFaces + q.start + q.size)
+                assert np.allclose(m.Cf[a], o.Cf[b], rtol=0, atol=1e-14) and np.allclose(m.Sf[a], -o.Sf[b], rtol=0, atol=1e-15)   # reversed vertex order: round-off
+                assert np.allclose(m.weights[a] + o.weights[b], 1.0, atol=1e-14)
+                mine = set(map(tuple, m.points[np.unique(m.faces[a])].tolist()))
+                theirs = set(map(tuple, o.points[np.unique(o.faces[b])].tolist()))
+                assert mine == theirs
