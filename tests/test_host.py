@@ -217,3 +217,26 @@ def test_fvmesh_cells_are_closed_and_volumes_add_up(which):
         np.add.at(tot, m.faceCells, m.Sf[F:])
         assert np.abs(tot[:, :2]).max() < 1e-13        # closed in the plane; the z faces are the empty patches
         assert abs(m.V.sum() - 0.5 * (4.0 - np.pi * 0.25 / 4.0)) < 1e-3 * m.V.sum()    # quarter plate 2 x 2 minus a quarter disc r = 0.5, thickness 0.5 (polygonal hole)
+
+
+def test_move_points_keeps_the_processor_identity_of_a_decomposed_mesh(tmp_path):
+    """mesh.move_points on one processor's part of a decomposed mesh (the host mirror that follows the device-side mesh
+    motion): rank, number of ranks, global cell numbers and processor patches survive, the geometry is that of the moved points."""
+    from solids4foam_b200 import foam_io as IO
+    c = cases.cantilever(6, 3, 2, general=True, L=2.0)
+    IO.write_case(str(tmp_path), c)
+    IO.decompose_case(str(tmp_path), 2)
+    sent = {}
+    for r in range(2):
+        def collect(send, r=r):
+            for q, a in send.items():
+                sent[(r, q)] = a
+            return {q: a for q, a in send.items()}
+        IO.read_poly_mesh(str(tmp_path / f"processor{r}" / "constant" / "polyMesh"), rank=r, nRanks=2, exchange=collect)
+    m = IO.read_decomposed_case(str(tmp_path), 0, 2, lambda send: {q: sent[(q, 0)] for q in send}).mesh
+    assert m.nRanks == 2 and any(p.kind == M.PROCESSOR for p in m.patches)
+    shift = np.array([0.1, -0.2, 0.05])
+    moved = M.move_points(m, m.points + shift)
+    assert moved.rank == 0 and moved.nRanks == 2 and np.array_equal(moved.cellGlobal, m.cellGlobal)
+    assert [(p.name, p.kind, p.size, p.nbr_rank) for p in moved.patches] == [(p.name, p.kind, p.size, p.nbr_rank) for p in m.patches]
+    assert np.allclose(moved.C, m.C + shift) and np.allclose(moved.V, m.V) and np.allclose(moved.Sf, m.Sf)
