@@ -231,7 +231,7 @@ def test_move_points_keeps_the_processor_identity_of_a_decomposed_mesh(tmp_path)
         def collect(send, r=r):
             for q, a in send.items():
                 sent[(r, q)] = a
-            return {q: a for q, a in send.items()}
+            return {q: a + 1.0 for q, a in send.items()}     # placeholder centres for this first pass (it only collects)
         IO.read_poly_mesh(str(tmp_path / f"processor{r}" / "constant" / "polyMesh"), rank=r, nRanks=2, exchange=collect)
     m = IO.read_decomposed_case(str(tmp_path), 0, 2, lambda send: {q: sent[(q, 0)] for q in send}).mesh
     assert m.nRanks == 2 and any(p.kind == M.PROCESSOR for p in m.patches)
