@@ -140,14 +140,18 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-def cpu_reference_run(dims, steps, warmup, precond_dic=True):
-    """The CPU oracle: outer iterations/s of the cantilever at `dims`, measured (never scaled)."""
+def cpu_reference_run(dims, steps, warmup, precond_dic=True, cpu_gamg=False):
+    """The CPU oracle: outer iterations/s of the cantilever at `dims`, measured (never scaled).  ``cpu_gamg``: PCG with the
+    oracle's own CPU multigrid of the GPU path's preconditioner family (pair-wise agglomeration, Chebyshev-Jacobi, K-cycle)
+    instead of the reference's DIC -- the like-for-like algorithm, not the reference's."""
     from oracle.binding import OracleSolid
     from solids4foam_b200 import case as K
     from solids4foam_b200 import cases
-    pre = K.PRECOND_DIC if precond_dic else K.PRECOND_DIAGONAL
+    pre = K.PRECOND_GAMG if cpu_gamg else (K.PRECOND_DIC if precond_dic else K.PRECOND_DIAGONAL)
     c = cases.cantilever(*dims, preconditioner=pre)
     o = OracleSolid(c)
+    if cpu_gamg:
+        o.set_cpu_gamg(True)
     # every host core this process may run on, set explicitly: torchrun exports OMP_NUM_THREADS=1, which must not
     # turn the N>1 reference runs into single-thread runs.  DIC becomes block-Jacobi over the thread ranges,
     cores = int(o.L.s4fo_set_threads(o.h, host_cores()))
@@ -161,6 +165,16 @@ def cpu_reference_run(dims, steps, warmup, precond_dic=True):
     dt = time.perf_counter() - t0
     inner = (st["totalInnerIterations"] - inner0) / max(steps, 1) if st else 0      # PCG iterations per outer iteration (3 components)
     return steps / dt, dt, inner, c.mesh.nCells, cores
+
+
+def same_family_cpu_figure(dims):
+    """The second CPU figure: the CPU on the algorithm the GPU runs.  One warm-up outer iteration (it holds the
+    set-up of the hierarchy on one thread) and three timed ones."""
+    ips, dt, inner, nS, cores = cpu_reference_run(dims, 3, 1, cpu_gamg=True)
+    return dict(value=ips, unit="iter/s", cores=cores, kind="port", preconditioner="GAMG (CPU multigrid of the oracle, K-cycle)",
+                sample=f"CPU oracle with PCG + its own agglomeration multigrid (same preconditioner family as the GPU path) on the full "
+                       f"{dims[0]}x{dims[1]}x{dims[2]} = {nS}-cell workload: outer iterations 2-4 from D = 0 in {dt:.1f} s, "
+                       f"{inner:.1f} PCG iterations per outer iteration (3 components); measured, not scaled")
 
 
 def multi_gpu_parity(rank, world, local_rank, new_comm, dims=(48, 12, 12)):
@@ -252,6 +266,8 @@ def main():
                                              f"in {dt:.1f} s, {inner:.0f} PCG iterations per outer iteration (3 components); measured, not scaled"),
                     e2e=dict(value=ips, unit="iter/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                     note="the reference solids4Foam binary cannot be built here (needs OpenFOAM); this is the repo's CPU oracle")
+        # not the reference's algorithm (its tutorials run PCG + DIC, timed above): the CPU on the GPU path's preconditioner family
+        line["cpu_same_preconditioner"] = same_family_cpu_figure(dims)
         emit(line)
         return
 
@@ -459,6 +475,7 @@ def main():
                                            f"{dims[0]}x{dims[1]}x{dims[2]} = {nS}-cell workload: outer iterations 2-3 from D = 0 in {dt:.1f} s "
                                            f"(measured, not scaled); {inner:.0f} DIC-PCG iterations per outer iteration (3 components) against "
                                            f"{inner_per_outer:.0f} GAMG-PCG iterations on the GPU")
+        line["cpu_same_preconditioner"] = same_family_cpu_figure(dims)
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -41,6 +41,8 @@ def lib():
         L.s4fo_table_lookup.argtypes = [C.POINTER(K.Law), C.c_double]
         L.s4fo_table_lookup.restype = C.c_double
         L.s4fo_uns_grad_from_points.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.s4fo_set_cpu_gamg.argtypes = [C.c_void_p, C.c_int]
+        L.s4fo_cpu_gamg_levels.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int]
         _LIB = L
     return _LIB
 
@@ -58,6 +60,15 @@ class OracleSolid:
     def _check(self, rc):
         if rc != 0:
             raise RuntimeError("oracle: " + self.L.s4fo_last_error(self.h).decode())
+
+    def set_cpu_gamg(self, on: bool = True) -> None:
+        """preconditioner GAMG = the oracle's own CPU multigrid (the GPU path's preconditioner family) instead of DIC"""
+        self.L.s4fo_set_cpu_gamg(self.h, 1 if on else 0)
+
+    def cpu_gamg_levels(self):
+        sizes = (C.c_int * 16)()
+        n = self.L.s4fo_cpu_gamg_levels(self.h, sizes, 16)
+        return [int(sizes[i]) for i in range(n)]
 
     def __del__(self):
         try:

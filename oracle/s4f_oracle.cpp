@@ -111,6 +111,81 @@ double tableLookup(const s4fgpu_law& L, double x) {
 
 struct SolverPerf { double initRes, finalRes; int nIter; };
 
+// ------------------------------------------------------------------------------------------------
+// CPU agglomeration multigrid for the SAME preconditioner family as the GPU path's default: [OF-ext] GAMG-style pair-wise
+// agglomeration by strongest face coefficient (three passes per level), Galerkin sums for piece-wise constant transfer,
+// Chebyshev-Jacobi smoothing in three-term form, fixed over-correction, dense coarsest solve, optional K-cycle on level 1
+// (two flexible-CG steps).  NOT part of the reference's algorithm (its tutorials run PCG + DIC): it exists so that
+// bench.py can time the CPU on the algorithm the GPU runs ("a second CPU figure with the same preconditioner
+// family"), and it is its own restatement -- nothing here is shared with solids4foam_b200/csrc/s4f_amg.cu.
+// Enabled per handle with s4fo_set_cpu_gamg; otherwise S4F_PRECOND_GAMG keeps mapping onto DIC (the parity preconditioner).
+// ------------------------------------------------------------------------------------------------
+struct OLevel {
+    int n = 0;
+    std::vector<int> ptr, col; dvec val;      // rows: positive couplings a_ij (A_ij = -a_ij), both triangles
+    dvec diag[3];
+    std::vector<int> parent;                  // cell -> cell of the next level
+    std::vector<int> cptr, child;             // next level's cells -> their children here
+    dvec b, x, xp, xn, t;                     // work vectors of one scalar solve
+};
+struct OGamg {
+    std::vector<OLevel> lv;
+    dvec inv[3]; int nC = 0;
+    int deg = 3, cycle = 2; double omega = 2.2, theta = 1.3, delta = 0.7;
+    dvec kc1, kv1, kr, kc2;                   // K-cycle work on level 1
+    bool valid = false;
+};
+
+void ogPairPass(const OLevel& L, std::vector<int>& agg, int& nc) {
+    agg.assign(L.n, -1); nc = 0;
+    for (int i = 0; i < L.n; i++) {
+        if (agg[i] >= 0) continue;
+        int best = -1; float bw = 0.f;
+        for (int e = L.ptr[i]; e < L.ptr[i + 1]; e++) {
+            const int j = L.col[e];
+            if (agg[j] < 0 && j != i && (float)L.val[e] > bw * 1.0000001f) { bw = (float)L.val[e]; best = j; }
+        }
+        agg[i] = nc; if (best >= 0) agg[best] = nc;
+        nc++;
+    }
+}
+
+// coarse level of the aggregates agg (piece-wise constant transfer): couplings between aggregates add up, couplings
+// inside an aggregate leave the diagonal (A_c[I][I] = sum_i A_ii - 2 sum_{faces inside} a)
+void ogGalerkin(const OLevel& L, const std::vector<int>& agg, int nc, OLevel& C) {
+    C.n = nc;
+    for (int q = 0; q < 3; q++) C.diag[q].assign(nc, 0.0);
+    std::vector<int> cnt(nc + 1, 0);
+    for (int i = 0; i < L.n; i++) cnt[agg[i] + 1]++;
+    for (int I = 0; I < nc; I++) cnt[I + 1] += cnt[I];
+    std::vector<int> kids(L.n), cur(cnt.begin(), cnt.end() - 1);
+    for (int i = 0; i < L.n; i++) kids[cur[agg[i]]++] = i;
+    C.ptr.assign(nc + 1, 0); C.col.clear(); C.val.clear();
+    std::vector<std::pair<int, double>> row;
+    for (int I = 0; I < nc; I++) {
+        row.clear();
+        double inside = 0;
+        for (int k = cnt[I]; k < cnt[I + 1]; k++) {
+            const int i = kids[k];
+            for (int q = 0; q < 3; q++) C.diag[q][I] += L.diag[q][i];
+            for (int e = L.ptr[i]; e < L.ptr[i + 1]; e++) {
+                const int J = agg[L.col[e]];
+                if (J == I) inside += L.val[e]; else row.emplace_back(J, L.val[e]);
+            }
+        }
+        for (int q = 0; q < 3; q++) C.diag[q][I] -= inside;
+        std::sort(row.begin(), row.end(), [](const std::pair<int, double>& a, const std::pair<int, double>& b) { return a.first < b.first; });
+        for (size_t k = 0; k < row.size();) {
+            size_t m = k; double sum = 0;
+            while (m < row.size() && row[m].first == row[k].first) sum += row[m++].second;
+            C.col.push_back(row[k].first); C.val.push_back(sum);
+            k = m;
+        }
+        C.ptr[I + 1] = (int)C.col.size();
+    }
+}
+
+
 }  // namespace
 struct s4f_oracle;
 namespace { void updateSigmaHydSmoothed(s4f_oracle& o, double impK); }
@@ -159,6 +234,9 @@ struct s4f_oracle {
     // fvMatrix
     dvec upper, diag, diagC, source, intCoeffs, bouCoeffs;
     bool matrixValid = false;
+    bool cpuGamg = false;          // S4F_PRECOND_GAMG runs the CPU multigrid below instead of mapping onto DIC (s4fo_set_cpu_gamg)
+    OGamg gamg;
+    int curComp = 0;               // component being solved (the CPU multigrid keeps one diagonal per component)
     // Aitken
     dvec aitkenRes, aitkenResPrev, aitkenAlpha;
     // last solve
@@ -1097,6 +1175,7 @@ void assembleMatrix(s4f_oracle& o) {
     for (int c = 0; c < N; c++) for (int q = 0; q < 3; q++) o.diagC[3 * c + q] = o.diag[c];
     for (int b = 0; b < B; b++) for (int q = 0; q < 3; q++) o.diagC[3 * o.faceCells[b] + q] += o.intCoeffs[3 * b + q];
     o.matrixValid = true;
+    o.gamg.valid = false;
 }
 
 void assembleSource(s4f_oracle& o) {
@@ -1229,6 +1308,175 @@ void Amul(const s4f_oracle& o, const double* diag, const double* x, double* y) {
     });
 }
 
+
+// ---- CPU GAMG: set-up and cycle (see OLevel / OGamg above) -----------------------------------------------------------------
+bool ogBuild(const s4f_oracle& o, OGamg& G) {
+    const int N = o.N, F = o.F;
+    G = OGamg();
+    G.deg = o.ctl.gamgSmootherDegree > 0 ? o.ctl.gamgSmootherDegree : 3;
+    G.cycle = o.ctl.gamgCycle;
+    G.omega = o.ctl.gamgOverCorrection > 0 ? o.ctl.gamgOverCorrection : 2.2;
+    const double ratio = o.ctl.gamgSmootherRatio > 0 ? o.ctl.gamgSmootherRatio : 0.3, lmax = 2.0, lmin = ratio * lmax;   // Gershgorin bound of D^-1 A
+    G.theta = 0.5 * (lmax + lmin); G.delta = 0.5 * (lmax - lmin);
+    G.lv.emplace_back();
+    {
+        OLevel& L = G.lv[0];
+        L.n = N;
+        L.ptr.assign(N + 1, 0);
+        for (int f = 0; f < F; f++) { L.ptr[o.own[f] + 1]++; L.ptr[o.nei[f] + 1]++; }
+        for (int i = 0; i < N; i++) L.ptr[i + 1] += L.ptr[i];
+        L.col.resize(2 * (size_t)F); L.val.resize(2 * (size_t)F);
+        std::vector<int> cur(L.ptr.begin(), L.ptr.end() - 1);
+        for (int f = 0; f < F; f++) { const int e = cur[o.nei[f]]++; L.col[e] = o.own[f]; L.val[e] = -o.upper[f]; }   // lower neighbours first
+        for (int f = 0; f < F; f++) { const int e = cur[o.own[f]]++; L.col[e] = o.nei[f]; L.val[e] = -o.upper[f]; }
+        for (int q = 0; q < 3; q++) { L.diag[q].resize(N); for (int c = 0; c < N; c++) L.diag[q][c] = o.diagC[3 * (size_t)c + q]; }
+    }
+    while (G.lv.back().n > 512 && G.lv.size() < 12) {
+        const int nFine = G.lv.back().n;
+        std::vector<int> total(nFine); for (int i = 0; i < nFine; i++) total[i] = i;
+        OLevel curL; const OLevel* m = &G.lv.back();
+        int nc = nFine;
+        for (int pass = 0; pass < 3; pass++) {
+            std::vector<int> agg; ogPairPass(*m, agg, nc);
+            OLevel next; ogGalerkin(*m, agg, nc, next);
+            for (int i = 0; i < nFine; i++) total[i] = agg[total[i]];
+            curL = std::move(next); m = &curL;
+            if (nc <= 128) break;
+        }
+        if (nc >= nFine) break;
+        OLevel& Fn = G.lv.back();
+        Fn.parent = total;
+        Fn.cptr.assign(nc + 1, 0);
+        for (int i = 0; i < nFine; i++) Fn.cptr[total[i] + 1]++;
+        for (int I = 0; I < nc; I++) Fn.cptr[I + 1] += Fn.cptr[I];
+        Fn.child.resize(nFine);
+        { std::vector<int> cur(Fn.cptr.begin(), Fn.cptr.end() - 1); for (int i = 0; i < nFine; i++) Fn.child[cur[total[i]]++] = i; }
+        G.lv.push_back(std::move(curL));
+    }
+    for (OLevel& L : G.lv) { L.b.assign(L.n, 0.0); L.x.assign(L.n, 0.0); L.xp.assign(L.n, 0.0); L.xn.assign(L.n, 0.0); L.t.assign(L.n, 0.0); }
+    const OLevel& C = G.lv.back();
+    const int n = C.n; G.nC = n;
+    if (n > 4096) return false;
+    for (int q = 0; q < 3; q++) {         // dense inverse by Cholesky
+        dvec A((size_t)n * n, 0.0);
+        for (int i = 0; i < n; i++) { A[(size_t)i * n + i] = C.diag[q][i]; for (int e = C.ptr[i]; e < C.ptr[i + 1]; e++) A[(size_t)i * n + C.col[e]] -= C.val[e]; }
+        for (int j = 0; j < n; j++) {
+            double d = A[(size_t)j * n + j];
+            for (int k = 0; k < j; k++) d -= A[(size_t)j * n + k] * A[(size_t)j * n + k];
+            if (!(d > 0)) return false;
+            d = std::sqrt(d); A[(size_t)j * n + j] = d;
+            for (int i = j + 1; i < n; i++) {
+                double v = A[(size_t)i * n + j];
+                for (int k = 0; k < j; k++) v -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+                A[(size_t)i * n + j] = v / d;
+            }
+        }
+        G.inv[q].assign((size_t)n * n, 0.0);
+        dvec y(n);
+        for (int c = 0; c < n; c++) {
+            for (int i = 0; i < n; i++) { double v = (i == c) ? 1.0 : 0.0; for (int k = 0; k < i; k++) v -= A[(size_t)i * n + k] * y[k]; y[i] = v / A[(size_t)i * n + i]; }
+            for (int i = n - 1; i >= 0; i--) { double v = y[i]; for (int k = i + 1; k < n; k++) v -= A[(size_t)k * n + i] * G.inv[q][(size_t)k * n + c]; G.inv[q][(size_t)i * n + c] = v / A[(size_t)i * n + i]; }
+        }
+    }
+    if (G.lv.size() > 1) { const int n1 = G.lv[1].n; G.kc1.assign(n1, 0.0); G.kv1.assign(n1, 0.0); G.kr.assign(n1, 0.0); G.kc2.assign(n1, 0.0); }
+    G.valid = true;
+    return true;
+}
+
+// y = A_l x for component q
+void ogAmul(const s4f_oracle& o, const OLevel& L, int q, const double* x, double* y) {
+    S4FO_PAR_FOR
+    for (int i = 0; i < L.n; i++) {
+        double acc = 0;
+        for (int e = L.ptr[i]; e < L.ptr[i + 1]; e++) acc += L.val[e] * x[L.col[e]];
+        y[i] = L.diag[q][i] * x[i] - acc;
+    }
+}
+
+// Chebyshev-Jacobi of degree G.deg in three-term form on level l: from the zero initial guess (pre) or from x (post)
+void ogSmooth(const s4f_oracle& o, OGamg& G, OLevel& L, int q, const double* b, bool fromZero) {
+    const double sigma = G.theta / G.delta;
+    double rho = 1.0 / sigma;
+    const int n = L.n;
+    int k0 = 0; bool havePrev = false, prevZero = false;
+    if (fromZero) {
+        S4FO_PAR_FOR
+        for (int i = 0; i < n; i++) L.x[i] = b[i] / (G.theta * L.diag[q][i]);
+        k0 = 1; prevZero = true;
+    }
+    for (int k = k0; k < G.deg; k++) {
+        double c1, c2;
+        if (k == 0) { c1 = 0.0; c2 = 1.0 / G.theta; }
+        else { const double rhon = 1.0 / (2.0 * sigma - rho); c1 = rhon * rho; c2 = 2.0 * rhon / G.delta; rho = rhon; }
+        S4FO_PAR_FOR
+        for (int i = 0; i < n; i++) {
+            double acc = 0;
+            for (int e = L.ptr[i]; e < L.ptr[i + 1]; e++) acc += L.val[e] * L.x[L.col[e]];
+            const double d = L.diag[q][i], xv = L.x[i], r = b[i] - (d * xv - acc);
+            double xn = xv + c2 * r / d;
+            if (k > 0) { if (havePrev) xn += c1 * (xv - L.xp[i]); else if (prevZero) xn += c1 * xv; }
+            L.xn[i] = xn;
+        }
+        L.xp.swap(L.x); L.x.swap(L.xn);       // previous <- current, current <- new
+        havePrev = true; prevZero = false;
+    }
+}
+
+void ogCycle(const s4f_oracle& o, OGamg& G, size_t l, int q, const double* b);
+
+// two flexible-CG steps on A_1 x = b_1, each preconditioned by the V-cycle from level 1 (Notay's K-cycle); result in lv[1].x
+void ogKcycle1(const s4f_oracle& o, OGamg& G, int q) {
+    OLevel& C = G.lv[1];
+    const int n = C.n;
+    dvec b(C.b);                                        // the cycle below overwrites the deeper right-hand sides only, keep b
+    ogCycle(o, G, 1, q, b.data());
+    G.kc1 = C.x;
+    ogAmul(o, C, q, G.kc1.data(), G.kv1.data());
+    double rho1 = 0, alpha1 = 0;
+    for (int i = 0; i < n; i++) { rho1 += G.kc1[i] * G.kv1[i]; alpha1 += G.kc1[i] * b[i]; }
+    const double s1 = std::fabs(rho1) > 1e-300 ? alpha1 / rho1 : 0.0;
+    for (int i = 0; i < n; i++) G.kr[i] = b[i] - s1 * G.kv1[i];
+    ogCycle(o, G, 1, q, G.kr.data());
+    G.kc2 = C.x;
+    dvec v2(n); ogAmul(o, C, q, G.kc2.data(), v2.data());
+    double beta = 0, alpha2 = 0, gamma = 0;
+    for (int i = 0; i < n; i++) { beta += G.kc2[i] * v2[i]; alpha2 += G.kc2[i] * G.kr[i]; gamma += G.kc2[i] * G.kv1[i]; }
+    double k1 = 0, k2 = 0;
+    if (std::fabs(rho1) > 1e-300) {
+        k1 = alpha1 / rho1;
+        const double rho2 = beta - gamma * gamma / rho1;
+        if (std::fabs(rho2) > 1e-300 * std::fabs(beta) && std::fabs(rho2) > 1e-300) { k2 = alpha2 / rho2; k1 -= gamma * k2 / rho1; }
+    }
+    for (int i = 0; i < n; i++) C.x[i] = k1 * G.kc1[i] + k2 * G.kc2[i];
+}
+
+// x_l ~ A_l^-1 b (V-cycle; K-cycle step on level 1 when called for level 0 with G.cycle == 2); result in lv[l].x
+void ogCycle(const s4f_oracle& o, OGamg& G, size_t l, int q, const double* b) {
+    OLevel& L = G.lv[l];
+    if (l + 1 == G.lv.size()) {
+        const int n = L.n;
+        for (int i = 0; i < n; i++) { double v = 0; const double* row = &G.inv[q][(size_t)i * n]; for (int k = 0; k < n; k++) v += row[k] * b[k]; L.x[i] = v; }
+        return;
+    }
+    OLevel& C = G.lv[l + 1];
+    ogSmooth(o, G, L, q, b, true);
+    {   // residual and restriction
+        S4FO_PAR_FOR
+        for (int i = 0; i < L.n; i++) {
+            double acc = 0;
+            for (int e = L.ptr[i]; e < L.ptr[i + 1]; e++) acc += L.val[e] * L.x[L.col[e]];
+            L.t[i] = b[i] - (L.diag[q][i] * L.x[i] - acc);
+        }
+        S4FO_PAR_FOR
+        for (int I = 0; I < C.n; I++) { double v = 0; for (int k = L.cptr[I]; k < L.cptr[I + 1]; k++) v += L.t[L.child[k]]; C.b[I] = v; }
+    }
+    if (G.cycle == 2 && l == 0 && G.lv.size() > 2) ogKcycle1(o, G, q);
+    else ogCycle(o, G, l + 1, q, C.b.data());
+    S4FO_PAR_FOR
+    for (int i = 0; i < L.n; i++) L.x[i] += G.omega * C.x[L.parent[i]];
+    ogSmooth(o, G, L, q, b, false);
+}
+
 struct Precond {
     int kind; dvec rD;
     void init(const s4f_oracle& o, const double* diag, int k) {
@@ -1294,11 +1542,17 @@ SolverPerf solvePCG(s4f_oracle& o, const double* diag, double* psi, const double
         // GPU-only preconditioners map onto the reference's own: Chebyshev -> diagonal, GAMG -> DIC
         int pk = o.ctl.preconditioner;
         if (pk == S4F_PRECOND_CHEBYSHEV) pk = S4F_PRECOND_DIAGONAL;
-        if (pk == S4F_PRECOND_GAMG) pk = S4F_PRECOND_DIC;
-        Precond pre; pre.init(o, diag, pk);
+        const bool mg = (pk == S4F_PRECOND_GAMG && o.cpuGamg);
+        if (pk == S4F_PRECOND_GAMG && !mg) pk = S4F_PRECOND_DIC;
+        Precond pre;
+        if (mg) { if (!o.gamg.valid && !ogBuild(o, o.gamg)) { o.err = "CPU GAMG: set-up failed"; return perf; } }
+        else pre.init(o, diag, pk);
+        const bool flexible = mg && o.gamg.cycle == 2;       // the K-cycle is a variable preconditioner: Polak-Ribiere beta
+        dvec rOld; if (flexible) rOld.assign(N, 0.0);
         do {
             wArAold = wArA;
-            pre.apply(o, wA.data(), rA.data());
+            if (mg) { ogCycle(o, o.gamg, 0, o.curComp, rA.data()); std::memcpy(wA.data(), o.gamg.lv[0].x.data(), sizeof(double) * N); }
+            else pre.apply(o, wA.data(), rA.data());
             wArA = 0;
 #pragma omp parallel for schedule(static) reduction(+ : wArA) num_threads(o.nThreads) if (o.nThreads > 1)
             for (int c = 0; c < N; c++) wArA += wA[c] * rA[c];
@@ -1307,6 +1561,12 @@ SolverPerf solvePCG(s4f_oracle& o, const double* diag, double* psi, const double
                 for (int c = 0; c < N; c++) pA[c] = wA[c];
             } else {
                 double beta = wArA / wArAold;
+                if (flexible) {
+                    double num = 0;
+#pragma omp parallel for schedule(static) reduction(+ : num) num_threads(o.nThreads) if (o.nThreads > 1)
+                    for (int c = 0; c < N; c++) num += wA[c] * (rA[c] - rOld[c]);
+                    beta = num / wArAold;
+                }
                 S4FO_PAR_FOR
                 for (int c = 0; c < N; c++) pA[c] = wA[c] + beta * pA[c];
             }
@@ -1316,6 +1576,7 @@ SolverPerf solvePCG(s4f_oracle& o, const double* diag, double* psi, const double
             for (int c = 0; c < N; c++) wApA += wA[c] * pA[c];
             if (std::fabs(wApA) / nf < VSMALL) break;   // checkSingularity
             double alpha = wArA / wApA;
+            if (flexible) std::memcpy(rOld.data(), rA.data(), sizeof(double) * N);
             sm = 0;
 #pragma omp parallel for schedule(static) reduction(+ : sm) num_threads(o.nThreads) if (o.nThreads > 1)
             for (int c = 0; c < N; c++) { psi[c] += alpha * pA[c]; rA[c] -= alpha * wA[c]; sm += std::fabs(rA[c]); }
@@ -1466,6 +1727,7 @@ void solveSegregated(s4f_oracle& o, double* psi /*AoS [3N]*/, const double* sour
         o.perf[q] = SolverPerf{0, 0, 0};
         if (!o.solD[q]) continue;
         for (int c = 0; c < N; c++) { x[c] = psi[3 * c + q]; b[c] = source[3 * c + q]; dg[c] = o.diagC[3 * c + q]; }
+        o.curComp = q;
         o.perf[q] = (o.ctl.solver == S4F_SOLVER_PBICGSTAB) ? solvePBiCGStab(o, dg.data(), x.data(), b.data())
                                                        : solvePCG(o, dg.data(), x.data(), b.data());
         for (int c = 0; c < N; c++) psi[3 * c + q] = x[c];
@@ -1949,6 +2211,16 @@ int s4fo_get_ls_vectors(s4f_oracle* o, double* lsP, double* lsN) {
 }
 double s4fo_table_lookup(const s4fgpu_law* law, double x) { return tableLookup(*law, x); }
 // host threads for the timing baseline (0 = all cores); 1 restores the literal serial loops
+// S4F_PRECOND_GAMG as a CPU multigrid of the GPU path's preconditioner family (bench.py's like-for-like CPU figure) instead of
+// the mapping onto DIC; returns the previous setting
+int s4fo_set_cpu_gamg(s4f_oracle* o, int on) { const int was = o->cpuGamg ? 1 : 0; o->cpuGamg = on != 0; o->gamg.valid = false; return was; }
+// levels of the CPU multigrid after its last set-up (sizes[maxLevels]); returns the number of levels
+int s4fo_cpu_gamg_levels(s4f_oracle* o, int* sizes, int maxLevels) {
+    if (!o->gamg.valid) return 0;
+    for (size_t l = 0; l < o->gamg.lv.size() && (int)l < maxLevels; l++) sizes[l] = o->gamg.lv[l].n;
+    return (int)o->gamg.lv.size();
+}
+
 int s4fo_set_threads(s4f_oracle* o, int n) {
     if (n <= 0) n = omp_get_max_threads();
     o->nThreads = n;

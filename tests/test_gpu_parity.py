@@ -1040,3 +1040,20 @@ def test_fused_small_level_kernel_equals_the_per_operation_kernels(monkeypatch):
     assert ia == ib, (ia, ib)
     assert rel_l2(pb, pa) < 1e-10
     assert nb < na                      # fewer launches with the fused kernel
+
+
+def test_gpu_gamg_and_the_oracles_cpu_multigrid_take_the_same_iteration_counts():
+    """bench.py's second CPU figure runs the oracle's own CPU multigrid of the same preconditioner family (K-cycle, Chebyshev
+    degree 3, over-correction 2.2, pair-wise agglomeration): on a structured mesh the two hierarchies have the same level
+    sizes and PCG stops after the same number of iterations (within one) with the same solution."""
+    from oracle.binding import OracleSolid
+    from solids4foam_b200.solid_model import SolidModel
+    kw = dict(nx=48, ny=17, nz=17, L=2.0, preconditioner=K.PRECOND_GAMG, tolerance=1e-11, relTol=0.0, maxIter=200)
+    g, o = SolidModel(cases.cantilever(**kw)), OracleSolid(cases.cantilever(**kw))
+    o.set_cpu_gamg(True)
+    src = np.random.default_rng(3).standard_normal((g.case.mesh.nCells, 3))
+    pg, sg = g.op_solve(np.zeros_like(src), src)
+    po, so = o.op_solve(np.zeros_like(src), src)
+    assert g.gamg_info()["levels"] == o.cpu_gamg_levels()
+    assert max(abs(a - b) for a, b in zip(sg["nIterations"], so["nIterations"])) <= 1, (sg, so)
+    assert rel_l2(pg, po) < 1e-9

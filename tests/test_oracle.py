@@ -599,3 +599,35 @@ def test_backward_d2dt2_free_vibration_is_less_damped_than_euler():
         tips[scheme] = np.array(tip)
     assert (tips[K.D2DT2_BACKWARD] < 0).all() and (tips[K.D2DT2_EULER] < 0).all()
     assert tips[K.D2DT2_BACKWARD][-1] < tips[K.D2DT2_EULER][-1]          # has fallen further
+
+
+# ---------------------------------------------------------------------------------------------
+# the oracle's CPU multigrid (bench.py's like-for-like CPU figure; not the reference's algorithm)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cycle", [2, 0])
+def test_cpu_gamg_pcg_solves_the_assembled_system(cycle):
+    """PCG preconditioned by the oracle's own agglomeration multigrid (s4fo_set_cpu_gamg: pair-wise agglomeration, Galerkin
+    sums, Chebyshev-Jacobi, K- or V-cycle) against the DIC-PCG solve of the same system: same solution, a sixth of the
+    iterations; without the switch S4F_PRECOND_GAMG keeps mapping onto DIC."""
+    kw = dict(nx=48, ny=17, nz=17, L=2.0, tolerance=1e-11, relTol=0.0, maxIter=400, gamgCycle=cycle)
+    a = OracleSolid(cases.cantilever(preconditioner=K.PRECOND_DIC, **kw))
+    b = OracleSolid(cases.cantilever(preconditioner=K.PRECOND_GAMG, **kw))
+    src = np.random.default_rng(3).standard_normal((a.case.mesh.nCells, 3))
+    pa, sa = a.op_solve(np.zeros_like(src), src)
+    pm, sm = b.op_solve(np.zeros_like(src), src)            # switch off: the mapping onto DIC
+    assert sm["nIterations"] == sa["nIterations"] and np.array_equal(pm, pa) and b.cpu_gamg_levels() == []
+    b.set_cpu_gamg(True)
+    pb, sb = b.op_solve(np.zeros_like(src), src)
+    assert b.cpu_gamg_levels() == [13872, 1734, 217]
+    assert max(sb["nIterations"]) <= 16 and min(sa["nIterations"]) >= 80, (sa, sb)
+    assert rel_l2(pb, pa) < 1e-10
+
+
+def test_cpu_gamg_drives_the_outer_loop_to_the_dic_solution():
+    kw = dict(nx=24, ny=8, nz=8, L=2.0, nCorrectors=3000, solutionTolerance=1e-9, alternativeTolerance=1e-9)
+    a = OracleSolid(cases.cantilever(preconditioner=K.PRECOND_DIC, **kw))
+    b = OracleSolid(cases.cantilever(preconditioner=K.PRECOND_GAMG, **kw))
+    b.set_cpu_gamg(True)
+    sa, sb = a.evolve(), b.evolve()
+    assert sa["converged"] and sb["converged"]
+    assert rel_l2(b.get("D"), a.get("D")) < 1e-6 and rel_l2(b.get("sigma"), a.get("sigma")) < 1e-6
