@@ -314,3 +314,23 @@ def test_manual_decomposition_with_corners_matches_face_by_face(tmp_path):
                 mine = set(map(tuple, m.points[np.unique(m.faces[a])].tolist()))
                 theirs = set(map(tuple, o.points[np.unique(o.faces[b])].tolist()))
                 assert mine == theirs
+
+
+@needs_ref
+def test_hron_turek_fsi3_solid_dictionaries_select_the_uns_total_lagrangian_model():
+    """tutorials/fluidSolidInteraction/HronTurekFsi3 (the FSI benchmark): its solid region runs
+    unsNonLinearGeometryTotalLagrangian with neoHookeanElastic (E 5.6e6, nu 0.4, rho 1000) -- the face-stress model and the
+    surface-field law of SURVEY 8f row f1.  The readers map the dictionaries onto the corresponding enums and parameters."""
+    base = os.path.join(REF, "fluidSolidInteraction/HronTurekFsi3")
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "constant")); os.makedirs(os.path.join(tmp, "system"))
+        for sub, names in (("constant", ("solidProperties", "mechanicalProperties")), ("system", ("fvSchemes", "fvSolution"))):
+            for n in names:
+                os.symlink(os.path.join(base, sub, "solid", n), os.path.join(tmp, sub, n))
+        law = IO.read_mechanical_law(tmp)
+        ctl = IO.read_controls(tmp)
+    ref = K.mechanical_law("neoHookeanElastic", rho=1000.0, E=5.6e6, nu=0.4)
+    assert (law.kind, law.rho, law.mu, law.K) == (K.LAW_NEO_HOOKEAN_ELASTIC, ref.rho, ref.mu, ref.K)
+    assert ctl.solidModel == K.MODEL_UNS_NONLIN_TL
+    assert ctl.nCorrectors == 1000 and ctl.solutionTolerance == 1e-7
