@@ -22,6 +22,10 @@ parity     (every N) the decomposed run against the single-domain CPU oracle on 
 cpu_baseline / --impl reference: the CPU oracle (oracle/, a restatement of the reference algorithm in
            its own LDU face-loop form, PCG + DIC) on the SAME workload and all host cores, measured, never
            scaled -- the reference itself needs OpenFOAM, which is not installable here.
+cpu_same_preconditioner   (N = 1 and --impl reference) the same CPU oracle with ITS OWN agglomeration multigrid of the GPU
+           path's preconditioner family instead of DIC: the like-for-like algorithm on the host cores (not the reference's).
+late_window, fp32_preconditioner   (N = 1) side blocks, not the headline: outer iterations 126-145 of the same solve; the same
+           window with the GAMG cycle in fp32.
 """
 from __future__ import annotations
 
