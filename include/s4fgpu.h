@@ -94,11 +94,14 @@ enum { S4F_SOLVER_PCG = 0, S4F_SOLVER_PBICGSTAB = 1 };     /* [OF-ext] PCG.C / P
 enum {
     S4F_PRECOND_NONE = 0,
     S4F_PRECOND_DIAGONAL = 1,   /* [OF-ext] diagonalPreconditioner (Jacobi) */
-    S4F_PRECOND_DIC = 2,        /* [OF-ext] DICPreconditioner / FDIC (oracle: exact; GPU: see DESIGN.md) */
+    S4F_PRECOND_DIC = 2,        /* [OF-ext] DICPreconditioner / FDIC: the sequential face sweeps evaluated level by level on the
+                                   device (the CPU solver's iteration counts) */
     S4F_PRECOND_CHEBYSHEV = 3,  /* GPU polynomial preconditioner (no reference counterpart) */
     S4F_PRECOND_GAMG = 4        /* [OF-ext] GAMG (agglomeration multigrid) used as PCG preconditioner: pair-wise
-                                   agglomeration like faceAreaPair, Galerkin coarse matrices, V-cycle with a
-                                   Chebyshev-Jacobi smoother, dense solve on the coarsest level */
+                                   agglomeration like faceAreaPair, Galerkin coarse matrices, V- or K-cycle with a
+                                   Chebyshev-Jacobi smoother, dense solve on the coarsest level; set up on the device
+                                   (one rank) or per rank with distributed levels (decomposed), coefficients refreshed
+                                   on the device when a later matrix has the same graph */
 };
 
 /* field ids for upload / download */
