@@ -334,3 +334,54 @@ def test_hron_turek_fsi3_solid_dictionaries_select_the_uns_total_lagrangian_mode
     assert (law.kind, law.rho, law.mu, law.K) == (K.LAW_NEO_HOOKEAN_ELASTIC, ref.rho, ref.mu, ref.K)
     assert ctl.solidModel == K.MODEL_UNS_NONLIN_TL
     assert ctl.nCorrectors == 1000 and ctl.solutionTolerance == 1e-7
+
+
+def test_point_neighbours_across_processors_are_recovered_from_the_point_coordinates(tmp_path):
+    """The host logic behind the point-neighbour ghosts of decomposed meshes (s4f_build_point_ghosts), restated in numpy: every
+    processor publishes, per point, its coordinates and the cells around it; identifying points across processors by their
+    coordinates BIT FOR BIT gives every processor, for each of its points, exactly the cells the serial mesh has around that
+    point -- also the cells of a processor that shares only an edge with it (2 x 2 blocks), with no tolerance involved."""
+    nx, ny, nz = 8, 6, 3
+    c = cases.cantilever(nx, ny, nz, general=True, L=2.0)
+    c.mesh = M.hex_box_general(nx, ny, nz, 2.0, 1.0, 1.0, names=("fixed", "loaded", "yMin", "yMax", "zMin", "zMax"),
+                               point_map=lambda p: p + 0.03 * np.sin(3.0 * p[:, [1, 2, 0]]))
+    idx = np.arange(c.mesh.nCells)
+    bx, by = ((idx % nx) >= nx // 2).astype(np.int64), (((idx // nx) % ny) >= ny // 2).astype(np.int64)
+
+    def point_cells(mesh):          # point -> set of (global) cells, from the fv faces (the hex faces cover every cell-point pair)
+        F = mesh.nInternalFaces
+        cg = mesh.cellGlobal if mesh.cellGlobal is not None else np.arange(mesh.nCells)
+        out = [set() for _ in range(mesh.points.shape[0])]
+        for f in range(mesh.faces.shape[0]):
+            cells = [mesh.owner[f], mesh.neighbour[f]] if f < F else [mesh.faceCells[f - F]]
+            for v in mesh.faces[f]:
+                out[v].update(int(cg[x]) for x in cells)
+        return out
+
+    serial = {tuple(x): s for x, s in zip(c.mesh.points.tolist(), point_cells(c.mesh))}
+    world, cell_rank = 4, bx + 2 * by
+    IO.write_case(str(tmp_path), c)
+    IO.decompose_case(str(tmp_path), world, cell_rank=cell_rank)
+    sent = {}
+    for r in range(world):
+        def collect(send, r=r):
+            for q, a in send.items():
+                sent[(r, q)] = a
+            return {q: a + 1.0 for q, a in send.items()}
+        IO.read_poly_mesh(str(tmp_path / f"processor{r}" / "constant" / "polyMesh"), rank=r, nRanks=world, exchange=collect)
+    parts = [IO.read_decomposed_case(str(tmp_path), r, world, lambda send, r=r: {q: sent[(q, r)] for q in send}).mesh for r in range(world)]
+    published = []                                          # what every processor publishes: coordinates -> its cells around the point
+    for m in parts:
+        published.append({tuple(x): s for x, s in zip(m.points.tolist(), point_cells(m))})
+    nRemote = 0
+    for r, mine in enumerate(published):
+        for xyz, local in mine.items():
+            found = set(local)
+            for q, theirs in enumerate(published):
+                if q != r and xyz in theirs:                # the same point on another processor: bit-identical coordinates
+                    found |= theirs[xyz]; nRemote += len(theirs[xyz])
+            assert found == serial[xyz], (r, xyz)
+    assert nRemote > 0
+    # processors 0 and 3 share no face, yet the points of the central edge see each other's cells
+    edge = set(published[0]) & set(published[3])
+    assert len(edge) == nz + 1 and all(published[3][x] - published[0][x] for x in edge)
